@@ -1,0 +1,1131 @@
+/*
+ * cimba_port.c - TEST INFRASTRUCTURE ONLY (the parity oracle, "port" kind).
+ *
+ * CPU restatement of the hot path of ambonvik/cimba in plain C11: sfc64 +
+ * ziggurat samplers, the hashheap future-event list, the event dispatcher, the
+ * resource-guard wait list, cmb_objectqueue and cmb_resourcepool, the running
+ * summaries, and the three queueing workloads of SURVEY.md section 8d.
+ *
+ * The reference runs each simulated process on its own stack
+ * (src/cmi_coroutine.c); here a process is a resume-point index plus locals -
+ * the same re-expression the CUDA engine uses - while the data structures keep
+ * the reference's shapes (1-based binary heap with slot 0 as the pop scratch,
+ * the same sift loops, the same comparators), so pop order follows from the
+ * same algorithm, not merely from the same ordering relation.
+ *
+ * Compiled with -ffp-contract=off: the reference build has no FMA contraction
+ * (no -march=native, meson.build:22-27).
+ *
+ * Parity: pinned - see cimba_port.h and tests/test_oracle_*.py.
+ */
+#include "cimba_port.h"
+
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdbool.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "zig_tables.h"
+
+/* ===================================================================== RNG */
+
+/* src/cmb_random.c:70-80 (MurmurHash3 finaliser over seed + nonce) */
+uint64_t port_fmix64(uint64_t seed, uint64_t nonce)
+{
+    uint64_t h = seed + nonce;
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+/* src/cmb_random.c:54-62 */
+uint64_t port_sfc64(port_rng *r)
+{
+    const uint64_t out = r->a + r->b + r->d++;
+    r->a = r->b ^ (r->b >> 11);
+    r->b = r->c + (r->c << 3);
+    r->c = ((r->c << 24) | (r->c >> 40)) + out;
+    return out;
+}
+
+/* src/cmb_random.c:91-124: splitmix64 x4 -> a,b,c,d, then 20 discarded draws */
+void port_rng_init(port_rng *r, uint64_t seed)
+{
+    uint64_t sm = seed;
+    uint64_t *dst[4] = { &r->a, &r->b, &r->c, &r->d };
+    for (int i = 0; i < 4; i++) {
+        uint64_t z = (sm += 0x9e3779b97f4a7c15ULL);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        *dst[i] = z ^ (z >> 31);
+    }
+    for (int i = 0; i < 20; i++) {
+        (void)port_sfc64(r);
+    }
+}
+
+/* include/cmb_random.h:149-152 */
+double port_random(port_rng *r)
+{
+    return ldexp((double)(port_sfc64(r) >> 11), -53);
+}
+
+/* include/cmb_random.h:165-173 */
+double port_uniform(port_rng *r, double lo, double hi)
+{
+    return lo + (hi - lo) * port_random(r);
+}
+
+/* include/cmb_random.h:749-754 */
+unsigned port_bernoulli(port_rng *r, double p)
+{
+    return (port_random(r) <= p) ? 1u : 0u;
+}
+
+/* include/cmb_random.h:840-846 */
+long port_dice(port_rng *r, long a, long b)
+{
+    const double x = (double)(b - a + 1) * port_random(r);
+    return (long)floor((double)a + x);
+}
+
+/* src/cmb_random.c:198-206: map integer coordinates inside overhang j to doubles */
+static double exp_overhang_x(unsigned j, uint64_t u)
+{
+    return ldexp(zt_exp_x[j], 64) + (zt_exp_x[j - 1] - zt_exp_x[j]) * (double)u;
+}
+
+static double exp_overhang_y(unsigned j, uint64_t u)
+{
+    return ldexp(zt_exp_y[j - 1], 64) + (zt_exp_y[j] - zt_exp_y[j - 1]) * (double)u;
+}
+
+/* src/cmb_random.c:216-285: the 1.56 % of draws that miss the ziggurat body */
+static double exp_slow(port_rng *r, uint64_t ux)
+{
+    double shift = 0.0;
+    for (;;) {
+        uint64_t uy = port_sfc64(r);
+        unsigned j = (unsigned)(uy & 0xff);
+        if (port_sfc64(r) >= zt_exp_prob[j]) {
+            j = zt_exp_alias[j];
+        }
+        if (j > 0u) {
+            for (;;) {
+                if (uy > (UINT64_MAX - ux)) {           /* reflect into the triangle */
+                    uy = UINT64_MAX - uy;
+                    ux = UINT64_MAX - ux;
+                }
+                const uint64_t gap = (UINT64_MAX - ux) - uy;
+                const double x = exp_overhang_x(j, ux);
+                if (gap >= zt_exp_concavity[j]) {
+                    return x + shift;
+                }
+                if (exp_overhang_y(j, uy) <= exp(-x)) {
+                    return x + shift;
+                }
+                uy = port_sfc64(r);
+                ux = port_sfc64(r);
+            }
+        }
+        shift += ZT_EXP_TAIL;                           /* memoryless tail */
+        ux = port_sfc64(r);
+        const unsigned i = (unsigned)(ux & 0xff);
+        if (i <= ZT_EXP_MAX) {
+            return zt_exp_x[i] * (double)ux + shift;
+        }
+    }
+}
+
+/* include/cmb_random.h:319-329 */
+double port_std_exponential(port_rng *r)
+{
+    const uint64_t u = port_sfc64(r);
+    const unsigned i = (unsigned)(u & 0xff);
+    return (i <= ZT_EXP_MAX) ? zt_exp_x[i] * (double)u : exp_slow(r, u);
+}
+
+/* include/cmb_random.h:344-352 */
+double port_exponential(port_rng *r, double mean)
+{
+    return mean * port_std_exponential(r);
+}
+
+/* include/cmb_random.h:366-378 */
+double port_erlang(port_rng *r, unsigned k, double m)
+{
+    double x = 0.0;
+    for (unsigned i = 0u; i < k; i++) {
+        x += port_exponential(r, m);
+    }
+    return x;
+}
+
+/* src/cmb_random.c:321-345 helpers */
+static double nor_overhang_x(unsigned j, int64_t ix)
+{
+    return ldexp(zt_nor_x[j], 63) + (zt_nor_x[j - 1] - zt_nor_x[j]) * (double)ix;
+}
+
+static double nor_overhang_y(unsigned j, uint64_t uy)
+{
+    return ldexp(zt_nor_y[j - 1], 63) + (zt_nor_y[j] - zt_nor_y[j - 1]) * (double)uy;
+}
+
+static int64_t draw63(port_rng *r)
+{
+    return (int64_t)(port_sfc64(r) & (uint64_t)INT64_MAX);
+}
+
+static double nor_pdf_scaled(double x)
+{
+    return exp(-0.5 * x * x);
+}
+
+/* src/cmb_random.c:352-451 */
+static double nor_slow(port_rng *r, int64_t ix)
+{
+    const double sign = (ix < 0) ? -1.0 : 1.0;
+    ix &= INT64_MAX;
+
+    int64_t iy = draw63(r);
+    unsigned j = (unsigned)(iy & 0xff);
+    if (ix >= zt_nor_prob[j]) {
+        j = zt_nor_alias[j];
+    }
+
+    if (j > ZT_NOR_INFLECTION) {                        /* convex overhang */
+        for (;;) {
+            const double x = nor_overhang_x(j, ix);
+            const int64_t gap = (INT64_MAX - ix) - iy;
+            if (gap >= 0) {
+                return sign * x;
+            }
+            if (gap + zt_nor_convexity[j] >= 0) {
+                if (nor_overhang_y(j, (uint64_t)iy) < nor_pdf_scaled(x)) {
+                    return sign * x;
+                }
+            }
+            ix = draw63(r);
+            iy = draw63(r);
+        }
+    }
+    else if (j == 0u) {                                 /* tail (Marsaglia) */
+        double x, z;
+        do {
+            x = ZT_NOR_INV_TAIL * port_exponential(r, 1.0);
+            z = port_exponential(r, 1.0);
+        } while (2 * z <= x * x);
+        return sign * (x + ZT_NOR_TAIL);
+    }
+    else if (j < ZT_NOR_INFLECTION) {                   /* concave overhang */
+        for (;;) {
+            if (iy > INT64_MAX - ix) {
+                iy = INT64_MAX - iy;
+                ix = INT64_MAX - ix;
+            }
+            const double x = nor_overhang_x(j, ix);
+            const int64_t gap = (INT64_MAX - ix) - iy;
+            if (gap >= zt_nor_concavity[j]) {
+                return sign * x;
+            }
+            if (nor_overhang_y(j, (uint64_t)iy) <= nor_pdf_scaled(x)) {
+                return sign * x;
+            }
+            ix = draw63(r);
+            iy = draw63(r);
+        }
+    }
+    else {                                              /* the inflection layer */
+        for (;;) {
+            const double x = nor_overhang_x(j, ix);
+            const int64_t gap = (INT64_MAX - ix) - iy;
+            if (gap >= zt_nor_concavity[j]) {
+                return sign * x;
+            }
+            if (gap + zt_nor_convexity[j] > 0) {
+                if (nor_overhang_y(j, (uint64_t)iy) < nor_pdf_scaled(x)) {
+                    return sign * x;
+                }
+            }
+            ix = draw63(r);
+            iy = draw63(r);
+        }
+    }
+}
+
+/* include/cmb_random.h:206-215: the sign rides in the signed integer */
+double port_std_normal(port_rng *r)
+{
+    const int64_t ix = (int64_t)port_sfc64(r);
+    const unsigned i = (unsigned)(ix & 0xff);
+    return (i <= ZT_NOR_MAX) ? zt_nor_x[i] * (double)ix : nor_slow(r, ix);
+}
+
+/* include/cmb_random.h:230-235 */
+double port_normal(port_rng *r, double mu, double sigma)
+{
+    return mu + sigma * port_std_normal(r);
+}
+
+int port_rng_draws(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out)
+{
+    port_rng r;
+    port_rng_init(&r, seed);
+    for (uint64_t i = 0u; i < n; i++) {
+        switch (kind) {
+        case 0: { uint64_t u = port_sfc64(&r); memcpy(&out[i], &u, 8); break; }
+        case 1: out[i] = port_exponential(&r, p0); break;
+        case 2: out[i] = port_std_normal(&r); break;
+        case 3: out[i] = port_random(&r); break;
+        case 4: out[i] = port_normal(&r, p0, p1); break;
+        case 5: out[i] = port_erlang(&r, (unsigned)p0, p1); break;
+        case 6: out[i] = port_uniform(&r, p0, p1); break;
+        case 7: out[i] = (double)port_dice(&r, (long)p0, (long)p1); break;
+        case 8: out[i] = (double)port_bernoulli(&r, p0); break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
+/* =============================================================== summaries */
+
+/* src/cmb_datasummary.c:37-50 */
+void port_summary_init(port_summary *s)
+{
+    s->count = 0u;
+    s->min = DBL_MAX;
+    s->max = -DBL_MAX;
+    s->m1 = s->m2 = s->m3 = s->m4 = 0.0;
+}
+
+/* src/cmb_datasummary.c:144-166 (Meng's update order) */
+uint64_t port_summary_add(port_summary *s, double y)
+{
+    s->max = (y > s->max) ? y : s->max;
+    s->min = (y < s->min) ? y : s->min;
+
+    const double d = y - s->m1;
+    const double d_2 = d * d;
+    const double d_3 = d * d_2;
+    const double n = (double)(++s->count);
+    const double d_n = d / n;
+    const double d_n_2 = d_n * d_n;
+    const double d_n_3 = d_n_2 * d_n;
+
+    s->m1 += d_n;
+    s->m2 += d * (d - d_n);
+    s->m3 += d * (d_2 - d_n_2) - 3.0 * d_n * s->m2;
+    s->m4 += d * (d_3 - d_n_3) - 6.0 * d_n_2 * s->m2 - 4.0 * d_n * s->m3;
+    return s->count;
+}
+
+/* src/cmb_datasummary.c:93-131 (Pebay pairwise merge; tgt may alias a source) */
+uint64_t port_summary_merge(port_summary *tgt, const port_summary *a, const port_summary *b)
+{
+    port_summary c;
+    port_summary_init(&c);
+    c.count = a->count + b->count;
+    c.min = (a->min < b->min) ? a->min : b->min;
+    c.max = (a->max > b->max) ? a->max : b->max;
+
+    const double n1 = (double)a->count;
+    const double n2 = (double)b->count;
+    const double n = (double)c.count;
+    const double d21 = b->m1 - a->m1;
+    const double d21_n = d21 / n;
+    const double d21_n_2 = d21_n * d21_n;
+    const double d21_n_3 = d21_n * d21_n_2;
+
+    c.m1 = a->m1 + n2 * d21_n;
+    c.m2 = a->m2 + b->m2 + n1 * n2 * d21 * d21_n;
+    c.m3 = a->m3 + b->m3
+         + n1 * n2 * (n1 - n2) * d21 * d21_n_2
+         + 3.0 * (n1 * b->m2 - n2 * a->m2) * d21_n;
+    c.m4 = a->m4 + b->m4
+         + n1 * n2 * (n1 * n1 - n1 * n2 + n2 * n2) * d21 * d21_n_3
+         + 6.0 * (n1 * n1 * b->m2 + n2 * n2 * a->m2) * d21_n_2
+         + 4.0 * (n1 * b->m3 - n2 * a->m3) * d21_n;
+    *tgt = c;
+    return tgt->count;
+}
+
+void port_wsummary_init(port_wsummary *s)
+{
+    port_summary_init(&s->ds);
+    s->wsum = 0.0;
+}
+
+/* src/cmb_wtdsummary.c:82-137 */
+uint64_t port_wsummary_add(port_wsummary *s, double x, double w)
+{
+    port_summary *d = &s->ds;
+    if (w == 0.0) {
+        return d->count;
+    }
+    if (d->count == 0u) {
+        d->count = 1u;
+        d->max = x;
+        d->min = x;
+        d->m1 = x;
+        d->m2 = d->m3 = d->m4 = 0.0;
+        s->wsum = w;
+        return d->count;
+    }
+
+    d->max = (x > d->max) ? x : d->max;
+    d->min = (x < d->min) ? x : d->min;
+    d->count++;
+
+    const double w1 = s->wsum;
+    const double w2 = w;
+    const double ws = w1 + w2;
+    const double d21 = x - d->m1;
+    const double d21_w = d21 / ws;
+    const double d21_w_2 = d21_w * d21_w;
+    const double d21_w_3 = d21_w * d21_w_2;
+
+    const double m1 = d->m1 + w2 * d21_w;
+    const double m2 = d->m2 + w1 * w2 * d21 * d21_w;
+    const double m3 = d->m3
+                    + w1 * w2 * (w1 - w2) * d21 * d21_w_2
+                    - 3.0 * w2 * d->m2 * d21_w;
+    const double m4 = d->m4
+                    + w1 * w2 * (w1 * w1 - w1 * w2 + w2 * w2) * d21 * d21_w_3
+                    + 6.0 * w2 * w2 * d->m2 * d21_w_2
+                    - 4.0 * w2 * d->m3 * d21_w;
+    d->m1 = m1;
+    d->m2 = m2;
+    d->m3 = m3;
+    d->m4 = m4;
+    s->wsum = ws;
+    return d->count;
+}
+
+/* src/cmb_wtdsummary.c:152-194 */
+uint64_t port_wsummary_merge(port_wsummary *tgt, const port_wsummary *a, const port_wsummary *b)
+{
+    port_wsummary t;
+    port_wsummary_init(&t);
+    const port_summary *p = &a->ds, *q = &b->ds;
+    t.ds.count = p->count + q->count;
+    t.ds.min = (p->min < q->min) ? p->min : q->min;
+    t.ds.max = (p->max > q->max) ? p->max : q->max;
+
+    const double w1 = a->wsum;
+    const double w2 = b->wsum;
+    const double ws = w1 + w2;
+    const double d21 = q->m1 - p->m1;
+    const double d21_w = d21 / ws;
+    const double d21_w_2 = d21_w * d21_w;
+    const double d21_w_3 = d21_w * d21_w_2;
+
+    t.wsum = ws;
+    t.ds.m1 = p->m1 + w2 * d21_w;
+    t.ds.m2 = p->m2 + q->m2 + w1 * w2 * d21 * d21_w;
+    t.ds.m3 = p->m3 + q->m3
+            + w1 * w2 * (w1 - w2) * d21 * d21_w_2
+            + 3.0 * (w1 * q->m2 - w2 * p->m2) * d21_w;
+    t.ds.m4 = p->m4 + q->m4
+            + w1 * w2 * (w1 * w1 - w1 * w2 + w2 * w2) * d21 * d21_w_3
+            + 6.0 * (w1 * w1 * q->m2 + w2 * w2 * p->m2) * d21_w_2
+            + 4.0 * (w1 * q->m3 - w2 * p->m3) * d21_w;
+    *tgt = t;
+    return t.ds.count;
+}
+
+static void flat_summary(const port_summary *s, double *out)
+{
+    out[0] = (double)s->count;
+    out[1] = s->min;
+    out[2] = s->max;
+    out[3] = s->m1;
+    out[4] = s->m2;
+    out[5] = s->m3;
+    out[6] = s->m4;
+}
+
+int port_datasummary_of(const double *x, uint64_t n, double *out)
+{
+    port_summary s;
+    port_summary_init(&s);
+    for (uint64_t i = 0u; i < n; i++) {
+        port_summary_add(&s, x[i]);
+    }
+    flat_summary(&s, out);
+    return 0;
+}
+
+int port_datasummary_split_merge(const double *x, uint64_t na, uint64_t n, double *out)
+{
+    port_summary a, b, m;
+    port_summary_init(&a);
+    port_summary_init(&b);
+    for (uint64_t i = 0u; i < na; i++) {
+        port_summary_add(&a, x[i]);
+    }
+    for (uint64_t i = na; i < n; i++) {
+        port_summary_add(&b, x[i]);
+    }
+    port_summary_merge(&m, &a, &b);
+    flat_summary(&m, out);
+    return 0;
+}
+
+int port_wtdsummary_of(const double *x, const double *w, uint64_t n, double *out)
+{
+    port_wsummary s;
+    port_wsummary_init(&s);
+    for (uint64_t i = 0u; i < n; i++) {
+        port_wsummary_add(&s, x[i], w[i]);
+    }
+    flat_summary(&s.ds, out);
+    out[7] = s.wsum;
+    return 0;
+}
+
+int port_wtdsummary_split_merge(const double *x, const double *w, uint64_t na, uint64_t n, double *out)
+{
+    port_wsummary a, b, m;
+    port_wsummary_init(&a);
+    port_wsummary_init(&b);
+    for (uint64_t i = 0u; i < na; i++) {
+        port_wsummary_add(&a, x[i], w[i]);
+    }
+    for (uint64_t i = na; i < n; i++) {
+        port_wsummary_add(&b, x[i], w[i]);
+    }
+    port_wsummary_merge(&m, &a, &b);
+    flat_summary(&m.ds, out);
+    out[7] = m.wsum;
+    return 0;
+}
+
+/* ================================================================ hashheap */
+
+/* src/cmi_hashheap.h:53-59 without the hash_index back-pointer: the key->slot
+ * map only accelerates lookups (src/cmi_hashheap.c:587-622); a linear search
+ * finds the same slot, so heap contents and order are unaffected. */
+typedef struct {
+    uint64_t key;
+    double   d;         /* rank_d64 */
+    int64_t  i;         /* rank_i64 */
+    int64_t  item[4];
+} heap_tag;
+
+typedef bool (*heap_before)(const heap_tag *a, const heap_tag *b);
+
+typedef struct {
+    heap_tag *slot;         /* 1-based; slot[0] = last popped (src/cmi_hashheap.c:496-498) */
+    uint64_t cap, count, issued;
+    heap_before before;
+} heap;
+
+/* src/cmi_hashheap.c:55-80: time asc, priority desc, key asc */
+static bool fel_before(const heap_tag *a, const heap_tag *b)
+{
+    if (a->d < b->d) return true;
+    if (a->d > b->d) return false;
+    if (a->i > b->i) return true;
+    if (a->i < b->i) return false;
+    return a->key < b->key;
+}
+
+/* src/cmb_resourceguard.c:71-90, copied in meaning INCLUDING its fall-through
+ * when a has the lower priority */
+static bool guard_before(const heap_tag *a, const heap_tag *b)
+{
+    if (a->i > b->i) return true;
+    if (a->d < b->d) return true;
+    if (a->key < b->key) return true;
+    return false;
+}
+
+static void heap_init(heap *h, unsigned exp2, heap_before before)
+{
+    h->cap = 1u << exp2;
+    h->slot = calloc(h->cap + 1u, sizeof(heap_tag));
+    h->count = 0u;
+    h->issued = 0u;
+    h->before = before;
+}
+
+static void heap_free(heap *h)
+{
+    free(h->slot);
+    h->slot = NULL;
+}
+
+/* src/cmi_hashheap.c:277-316 */
+static void sift_up(heap *h, uint64_t k)
+{
+    const heap_tag moving = h->slot[k];
+    uint64_t parent;
+    while ((parent = (k >> 1)) > 0u) {
+        if (!h->before(&moving, &h->slot[parent])) {
+            break;
+        }
+        h->slot[k] = h->slot[parent];
+        k = parent;
+    }
+    h->slot[k] = moving;
+}
+
+/* src/cmi_hashheap.c:321-370 */
+static void sift_down(heap *h, uint64_t k)
+{
+    const heap_tag moving = h->slot[k];
+    const uint64_t last_parent = h->count >> 1;
+    while (k <= last_parent) {
+        uint64_t child = k << 1;
+        if (child + 1u <= h->count && h->before(&h->slot[child + 1u], &h->slot[child])) {
+            child++;
+        }
+        if (h->before(&moving, &h->slot[child])) {
+            break;
+        }
+        h->slot[k] = h->slot[child];
+        k = child;
+    }
+    h->slot[k] = moving;
+}
+
+/* src/cmi_hashheap.c:428-478; doubles on demand like :381-421 */
+static uint64_t heap_push(heap *h, uint64_t key, double d, int64_t i,
+                          int64_t p0, int64_t p1, int64_t p2)
+{
+    if (h->count == h->cap) {
+        h->cap <<= 1;
+        h->slot = realloc(h->slot, (h->cap + 1u) * sizeof(heap_tag));
+    }
+    const uint64_t at = ++h->count;
+    h->issued += 1u;
+    if (key == 0u) {
+        key = h->issued;
+    }
+    heap_tag *t = &h->slot[at];
+    t->key = key;
+    t->d = d;
+    t->i = i;
+    t->item[0] = p0;
+    t->item[1] = p1;
+    t->item[2] = p2;
+    t->item[3] = 0;
+    sift_up(h, at);
+    return key;
+}
+
+/* src/cmi_hashheap.c:486-524: result left in slot[0] */
+static bool heap_pop(heap *h)
+{
+    if (h->count == 0u) {
+        return false;
+    }
+    h->slot[0] = h->slot[1];
+    if (h->count > 1u) {
+        h->slot[1] = h->slot[h->count];
+        h->count--;
+        if (h->count > 1u) {
+            sift_down(h, 1u);
+        }
+    }
+    else {
+        h->count = 0u;
+    }
+    return true;
+}
+
+/* src/cmi_hashheap.c:529-579 (lookup by linear search, see heap_tag note) */
+static bool heap_remove(heap *h, uint64_t key)
+{
+    uint64_t at = 0u;
+    for (uint64_t k = 1u; k <= h->count; k++) {
+        if (h->slot[k].key == key) {
+            at = k;
+            break;
+        }
+    }
+    if (at == 0u) {
+        return false;
+    }
+    if (at == h->count) {
+        h->count--;
+        return true;
+    }
+    const bool down = h->before(&h->slot[at], &h->slot[h->count]);
+    h->slot[at] = h->slot[h->count];
+    h->count--;
+    if (down) {
+        sift_down(h, at);
+    }
+    else {
+        sift_up(h, at);
+    }
+    return true;
+}
+
+int port_heap_script(uint64_t n, const int *ops, const double *vals_d,
+                     const int64_t *vals_i, uint64_t *out_key)
+{
+    heap h;
+    heap_init(&h, 3u, fel_before);
+    for (uint64_t s = 0u; s < n; s++) {
+        switch (ops[s]) {
+        case 0: out_key[s] = heap_push(&h, 0u, vals_d[s], vals_i[s], 0, 0, 0); break;
+        case 1: out_key[s] = heap_pop(&h) ? h.slot[0].key : 0u; break;
+        case 2: out_key[s] = heap_remove(&h, (uint64_t)vals_i[s]) ? 1u : 0u; break;
+        default: heap_free(&h); return -1;
+        }
+    }
+    heap_free(&h);
+    return 0;
+}
+
+/* ======================================================== simulation kernel */
+
+enum { SIG_SUCCESS = 0 };                               /* include/cmb_process.h:59-99 */
+enum { ACT_START = 1, ACT_WAKE_TIME, ACT_WAKE_RESOURCE };
+enum { ST_CREATED = 0, ST_RUNNING, ST_FINISHED };
+
+struct sim;
+struct proc;
+typedef void (*proc_body)(struct sim *s, struct proc *p, int64_t sig);
+
+typedef struct proc {
+    proc_body body;
+    int       pc;           /* resume point */
+    int       status;
+    int64_t   prio;
+    int       id;
+    /* model locals */
+    uint64_t  n_done;
+    double    stamp;
+    struct proc *next_free;
+} proc;
+
+typedef struct {
+    heap waiting;           /* cmb_resourceguard "is a" hashheap (src/cmb_resourceguard.c:93-106) */
+} guard;
+
+typedef struct sim {
+    port_rng rng;
+    double   now;           /* src/cmb_event.c:39 */
+    heap     fel;           /* src/cmb_event.c:44 */
+    uint64_t guard_seq;     /* src/cmb_resourceguard.c:64 (thread-local; per trial here, monotone either way) */
+    proc    *current;
+    /* workload */
+    int      model;
+    uint64_t num_objects;
+    double   arr_mean, srv_mean;
+    /* objectqueue (src/cmb_objectqueue.c:45-52): FIFO of arrival stamps */
+    double  *ring;
+    uint64_t ring_cap, ring_head, ring_len;
+    guard    q_front;
+    /* resourcepool (src/cmb_resourcepool.c) */
+    uint64_t pool_cap, pool_in_use;
+    guard    pool_guard;
+    proc   **cust;
+    unsigned cust_count, cust_cap;
+    proc    *cust_free;
+    /* results */
+    port_result *res;
+    uint64_t trace_cap;
+    uint64_t *trace_key;
+    double   *trace_time;
+} sim;
+
+/* src/cmb_event.c:123-140 */
+static uint64_t schedule(sim *s, int action, proc *subject, int64_t arg, double t, int64_t prio)
+{
+    return heap_push(&s->fel, 0u, t, prio, action, (int64_t)(intptr_t)subject, arg);
+}
+
+/* src/cmb_process.c:127-135 */
+static void process_start(sim *s, proc *p)
+{
+    schedule(s, ACT_START, p, 0, s->now, p->prio);
+}
+
+/* src/cmb_process.c:262-285 + 316-333: schedule own wake-up; the caller then yields */
+static void process_hold(sim *s, proc *p, double dur)
+{
+    schedule(s, ACT_WAKE_TIME, p, SIG_SUCCESS, s->now + dur, p->prio);
+}
+
+/* src/cmb_resourceguard.c:125-146: join the wait list; the caller then yields */
+static void guard_wait(sim *s, guard *g, proc *p)
+{
+    const uint64_t key = ++s->guard_seq;
+    heap_push(&g->waiting, key, s->now, p->prio, (int64_t)(intptr_t)p, 0, 0);
+}
+
+/* src/cmb_resourceguard.c:202-242: wake at most the head, if its demand holds */
+static bool guard_signal(sim *s, guard *g, bool demand_holds)
+{
+    if (g->waiting.count == 0u || !demand_holds) {
+        return false;
+    }
+    proc *p = (proc *)(intptr_t)g->waiting.slot[1].item[0];
+    heap_pop(&g->waiting);
+    schedule(s, ACT_WAKE_RESOURCE, p, SIG_SUCCESS, s->now, p->prio);
+    return true;
+}
+
+/* src/cmb_process.c:671-684 via the trampoline (cmi_coroutine_context.asm:140-148):
+ * nothing held, nothing awaited, nobody waiting in these workloads; the final
+ * cmb_event_pattern_cancel(ANY, p, ANY) (src/cmb_process.c:618-619) is kept. */
+static void process_exit(sim *s, proc *p)
+{
+    for (uint64_t k = 1u; k <= s->fel.count; ) {
+        if ((proc *)(intptr_t)s->fel.slot[k].item[1] == p) {
+            heap_remove(&s->fel, s->fel.slot[k].key);
+            k = 1u;
+        }
+        else {
+            k++;
+        }
+    }
+    p->status = ST_FINISHED;
+}
+
+/* ---- cmb_objectqueue as a ring of stamps ---- */
+
+static void ring_push(sim *s, double v)
+{
+    if (s->ring_len == s->ring_cap) {
+        double *bigger = malloc(2u * s->ring_cap * sizeof(double));
+        for (uint64_t k = 0u; k < s->ring_len; k++) {
+            bigger[k] = s->ring[(s->ring_head + k) % s->ring_cap];
+        }
+        free(s->ring);
+        s->ring = bigger;
+        s->ring_head = 0u;
+        s->ring_cap *= 2u;
+    }
+    s->ring[(s->ring_head + s->ring_len) % s->ring_cap] = v;
+    s->ring_len++;
+}
+
+/* src/cmb_objectqueue.c:262-314, unlimited capacity: append, signal the front guard */
+static void objectqueue_put(sim *s, double stamp)
+{
+    ring_push(s, stamp);
+    if (s->ring_len > s->res->max_queue) {
+        s->res->max_queue = s->ring_len;
+    }
+    guard_signal(s, &s->q_front, s->ring_len > 0u);     /* demand = has_content (:119-131) */
+}
+
+/* src/cmb_objectqueue.c:203-239: true if an object was taken (rear guard has no waiters) */
+static bool objectqueue_try_get(sim *s, double *stamp)
+{
+    if (s->ring_len == 0u) {
+        return false;
+    }
+    *stamp = s->ring[s->ring_head];
+    s->ring_head = (s->ring_head + 1u) % s->ring_cap;
+    s->ring_len--;
+    return true;
+}
+
+/* ---- the two queue processes: benchmark/MM1_multi.c:52-89 as resume points ---- */
+
+static double draw_interarrival(sim *s)
+{
+    if (s->model == 1) {
+        return port_erlang(&s->rng, 2u, 0.5 * s->arr_mean);
+    }
+    return port_exponential(&s->rng, s->arr_mean);
+}
+
+static double draw_service(sim *s)
+{
+    if (s->model == 1) {
+        double v;
+        do {
+            v = port_normal(&s->rng, s->srv_mean, 0.25 * s->srv_mean);
+        } while (v < 0.0);
+        return v;
+    }
+    return port_exponential(&s->rng, s->srv_mean);
+}
+
+static void source_body(sim *s, proc *p, int64_t sig)
+{
+    (void)sig;
+    switch (p->pc) {
+    case 0:
+        p->n_done = 0u;
+        for (;;) {
+            if (p->n_done >= s->num_objects) {
+                process_exit(s, p);
+                return;
+            }
+            process_hold(s, p, draw_interarrival(s));
+            p->pc = 1;
+            return;
+    case 1:
+            objectqueue_put(s, s->now);
+            p->n_done++;
+        }
+    }
+}
+
+static void server_body(sim *s, proc *p, int64_t sig)
+{
+    (void)sig;
+    switch (p->pc) {
+    case 0:
+        for (;;) {
+            while (!objectqueue_try_get(s, &p->stamp)) {
+                guard_wait(s, &s->q_front, p);
+                p->pc = 1;
+                return;
+    case 1:     ;
+            }
+            process_hold(s, p, draw_service(s));
+            p->pc = 2;
+            return;
+    case 2:
+            s->res->sum_wait += s->now - p->stamp;
+            s->res->objects += 1u;
+        }
+    }
+}
+
+/* ---- M/M/c: oracle/ref_build/ref_driver.c c_source_body / c_customer_body ---- */
+
+/* src/cmb_resourcepool.c:362-533 with req = 1, no preemption, nobody interrupts */
+static void customer_body(sim *s, proc *p, int64_t sig)
+{
+    (void)sig;
+    switch (p->pc) {
+    case 0:
+        for (;;) {
+            if (s->pool_cap - s->pool_in_use >= 1u) {
+                s->pool_in_use += 1u;
+                /* "in case someone else can use the leftovers" (:408-409) */
+                guard_signal(s, &s->pool_guard, s->pool_cap - s->pool_in_use > 0u);
+                break;
+            }
+            guard_wait(s, &s->pool_guard, p);
+            p->pc = 1;
+            return;
+    case 1:     ;
+        }
+        process_hold(s, p, port_exponential(&s->rng, s->srv_mean));
+        p->pc = 2;
+        return;
+    case 2:
+        /* src/cmb_resourcepool.c:561-605 */
+        s->pool_in_use -= 1u;
+        guard_signal(s, &s->pool_guard, s->pool_cap - s->pool_in_use > 0u);
+        s->res->sum_wait += s->now - p->stamp;
+        s->res->objects += 1u;
+        p->next_free = s->cust_free;
+        s->cust_free = p;
+        process_exit(s, p);
+        return;
+    }
+}
+
+static void generator_body(sim *s, proc *p, int64_t sig)
+{
+    (void)sig;
+    switch (p->pc) {
+    case 0:
+        p->n_done = 0u;
+        for (;;) {
+            if (p->n_done >= s->num_objects) {
+                process_exit(s, p);
+                return;
+            }
+            process_hold(s, p, port_exponential(&s->rng, s->arr_mean));
+            p->pc = 1;
+            return;
+    case 1: {
+            proc *cu = s->cust_free;
+            if (cu != NULL) {
+                s->cust_free = cu->next_free;
+            }
+            else {
+                cu = calloc(1, sizeof(*cu));
+                cu->body = customer_body;
+                cu->id = (int)(s->cust_count + 1u);
+                if (s->cust_count == s->cust_cap) {
+                    s->cust_cap *= 2u;
+                    s->cust = realloc(s->cust, s->cust_cap * sizeof(proc *));
+                }
+                s->cust[s->cust_count++] = cu;
+            }
+            cu->stamp = s->now;
+            process_start(s, cu);
+            p->n_done++;
+            }
+        }
+    }
+}
+
+/* ---- dispatcher: src/cmb_event.c:229-252, 259-267 ---- */
+
+static void dispatch_all(sim *s)
+{
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > s->res->max_fel) {
+            s->res->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < s->trace_cap) {
+            s->trace_key[n] = ev.key;
+            s->trace_time[n] = s->now;
+        }
+        n++;
+        proc *p = (proc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:                                 /* src/cmb_process.c:115-122, src/cmi_coroutine.c:172-196 */
+            p->status = ST_RUNNING;
+            p->pc = 0;
+            s->current = p;
+            p->body(s, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:                             /* src/cmb_process.c:292-308 */
+            s->current = p;
+            p->body(s, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:                         /* src/cmb_resourceguard.c:168-180 */
+            if (p->status == ST_RUNNING) {
+                s->current = p;
+                p->body(s, p, ev.item[2]);
+            }
+            break;
+        }
+        s->current = NULL;
+    }
+    s->res->events = n;
+    s->res->t_end = s->now;
+}
+
+static void run_one(int model, int servers, uint64_t seed, uint64_t num_objects,
+                    double arr_mean, double srv_mean, uint64_t trace_cap,
+                    uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    sim s;
+    memset(&s, 0, sizeof(s));
+    memset(out, 0, sizeof(*out));
+    s.res = out;
+    s.model = model;
+    s.num_objects = num_objects;
+    s.arr_mean = arr_mean;
+    s.srv_mean = srv_mean;
+    s.trace_cap = trace_cap;
+    s.trace_key = trace_key;
+    s.trace_time = trace_time;
+
+    port_rng_init(&s.rng, seed);                        /* benchmark/MM1_multi.c:96 (seeded) */
+    s.now = 0.0;
+    heap_init(&s.fel, 3u, fel_before);                  /* src/cmb_event.c:47,74-81 */
+
+    proc source, server;
+    memset(&source, 0, sizeof(source));
+    memset(&server, 0, sizeof(server));
+    if (model == 2) {
+        s.pool_cap = (uint64_t)servers;
+        heap_init(&s.pool_guard.waiting, 3u, guard_before);
+        s.cust_cap = 64u;
+        s.cust = malloc(s.cust_cap * sizeof(proc *));
+        source.body = generator_body;
+        process_start(&s, &source);
+    }
+    else {
+        s.ring_cap = 64u;
+        s.ring = malloc(s.ring_cap * sizeof(double));
+        heap_init(&s.q_front.waiting, 3u, guard_before);
+        source.body = source_body;
+        server.body = server_body;
+        server.id = 1;
+        process_start(&s, &source);                     /* benchmark/MM1_multi.c:107-111 */
+        process_start(&s, &server);
+    }
+
+    dispatch_all(&s);
+
+    if (model == 2) {
+        out->max_queue = s.cust_count;
+        for (unsigned k = 0u; k < s.cust_count; k++) {
+            free(s.cust[k]);
+        }
+        free(s.cust);
+        heap_free(&s.pool_guard.waiting);
+    }
+    else {
+        free(s.ring);
+        heap_free(&s.q_front.waiting);
+    }
+    heap_free(&s.fel);
+}
+
+/* ------------------------------------------------- experiment executive */
+
+typedef struct {
+    int model, servers;
+    uint64_t master_seed, first, count, num_objects;
+    double arr_mean, srv_mean;
+    port_result *out;
+    uint64_t next;          /* shared work counter, as src/cimba.c:112-118 */
+} job;
+
+static void *worker(void *arg)
+{
+    job *j = arg;
+    for (;;) {
+        const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
+        if (k >= j->count) {
+            break;
+        }
+        run_one(j->model, j->servers, port_fmix64(j->master_seed, j->first + k),
+                j->num_objects, j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+    }
+    return NULL;
+}
+
+int port_run_trials(int model, int servers, uint64_t master_seed,
+                    uint64_t first, uint64_t count, uint64_t num_objects,
+                    double arr_mean, double srv_mean, int threads,
+                    port_result *out)
+{
+    job j = { model, servers, master_seed, first, count, num_objects,
+              arr_mean, srv_mean, out, 0u };
+    if (threads <= 1) {
+        worker(&j);
+        return 0;
+    }
+    pthread_t *tid = malloc((size_t)threads * sizeof(*tid));
+    for (int t = 0; t < threads; t++) {
+        pthread_create(&tid[t], NULL, worker, &j);
+    }
+    for (int t = 0; t < threads; t++) {
+        pthread_join(tid[t], NULL);
+    }
+    free(tid);
+    return 0;
+}
+
+int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects,
+                     double arr_mean, double srv_mean, uint64_t trace_cap,
+                     uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    run_one(model, servers, seed, num_objects, arr_mean, srv_mean,
+            trace_cap, trace_key, trace_time, out);
+    return 0;
+}

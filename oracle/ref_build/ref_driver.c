@@ -1,0 +1,459 @@
+/*
+ * ref_driver.c - TEST INFRASTRUCTURE ONLY.
+ *
+ * Seeded model drivers written against the UNMODIFIED reference library
+ * (ambonvik/cimba, compiled from /root/reference by oracle/Makefile into
+ * oracle/_ref/).  They exist so that (a) the C restatement in oracle/port and
+ * the CUDA engine in cimba_b200/csrc can be compared trial-for-trial with the
+ * real reference, and (b) bench.py can time the reference's own pthread
+ * executive (cimba_run_experiment, src/cimba.c:151) on the GPU box's host
+ * cores.  Nothing here is linked into the product library.
+ *
+ * Workloads:
+ *   model 0  M/M/1   = benchmark/MM1_multi.c:52-125, but seeded with
+ *                      cmb_random_fmix64(master, trial index) exactly like
+ *                      test/test_cimba.c:396 instead of the hardware seed.
+ *   model 1  G/G/1   = same structure; inter-arrival cmb_random_erlang(2, m/2),
+ *                      service = normal(mean, mean/4) redrawn while negative.
+ *   model 2  M/M/c   = generator process starting one customer process per
+ *                      arrival (recycled process structs), customers contend
+ *                      for a cmb_resourcepool of capacity c.
+ *
+ * An "event" is one successful cmb_event_execute_next() (src/cmb_event.c:229).
+ */
+#include <inttypes.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cimba.h>
+
+#include "cmi_mempool.h"
+
+struct ref_trial {
+    /* in */
+    uint64_t seed;
+    uint64_t num_objects;
+    double arr_mean;
+    double srv_mean;
+    int32_t model;
+    int32_t servers;
+    /* out */
+    uint64_t events;
+    uint64_t objects;
+    double t_end;
+    double sum_wait;
+    uint64_t max_fel;
+    uint64_t max_queue;
+    /* optional pop trace (single-trial calls only) */
+    uint64_t trace_cap;
+    uint64_t *trace_key;
+    double *trace_time;
+};
+
+/* ---------------------------------------------------------------- queues */
+
+static CMB_THREAD_LOCAL struct cmi_mempool stamp_pool = CMI_MEMPOOL_STATIC_INIT(8u, 512u);
+
+struct q_world {
+    struct ref_trial *trl;
+    struct cmb_objectqueue *queue;
+    struct cmb_process *source;
+    struct cmb_process *server;
+};
+
+static double draw_interarrival(const struct ref_trial *t)
+{
+    if (t->model == 1) {
+        return cmb_random_erlang(2u, 0.5 * t->arr_mean);
+    }
+    return cmb_random_exponential(t->arr_mean);
+}
+
+static double draw_service(const struct ref_trial *t)
+{
+    if (t->model == 1) {
+        double s;
+        do {
+            s = cmb_random_normal(t->srv_mean, 0.25 * t->srv_mean);
+        } while (s < 0.0);
+        return s;
+    }
+    return cmb_random_exponential(t->srv_mean);
+}
+
+static void *q_source_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct q_world *w = vw;
+    for (uint64_t i = 0u; i < w->trl->num_objects; i++) {
+        cmb_process_hold(draw_interarrival(w->trl));
+        double *stamp = cmi_mempool_alloc(&stamp_pool);
+        *stamp = cmb_time();
+        cmb_objectqueue_put(w->queue, stamp);
+        const uint64_t len = cmb_objectqueue_length(w->queue);
+        if (len > w->trl->max_queue) {
+            w->trl->max_queue = len;
+        }
+    }
+    return NULL;
+}
+
+static void *q_server_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct q_world *w = vw;
+    for (;;) {
+        void *obj = NULL;
+        cmb_objectqueue_get(w->queue, &obj);
+        cmb_process_hold(draw_service(w->trl));
+        w->trl->sum_wait += cmb_time() - *(double *)obj;
+        w->trl->objects += 1u;
+        cmi_mempool_free(&stamp_pool, obj);
+    }
+}
+
+/* ----------------------------------------------------------------- M/M/c */
+
+struct c_world;
+
+struct c_customer {
+    struct cmb_process proc;        /* parent "class" first, as the reference's tutorials do */
+    struct c_world *world;
+    double t_arrival;
+    struct c_customer *next_free;
+};
+
+struct c_world {
+    struct ref_trial *trl;
+    struct cmb_resourcepool *pool;
+    struct cmb_process *source;
+    struct c_customer *free_list;
+    struct c_customer *all_list[4096];
+    unsigned all_count;
+};
+
+static void *c_customer_body(struct cmb_process *me, void *vw)
+{
+    struct c_customer *cu = (struct c_customer *)me;
+    struct c_world *w = vw;
+    cmb_resourcepool_acquire(w->pool, 1u);
+    cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
+    cmb_resourcepool_release(w->pool, 1u);
+    w->trl->sum_wait += cmb_time() - cu->t_arrival;
+    w->trl->objects += 1u;
+    cu->next_free = w->free_list;
+    w->free_list = cu;
+    return NULL;
+}
+
+static void *c_source_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct c_world *w = vw;
+    for (uint64_t i = 0u; i < w->trl->num_objects; i++) {
+        cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        struct c_customer *cu = w->free_list;
+        if (cu != NULL) {
+            w->free_list = cu->next_free;
+        }
+        else {
+            cu = calloc(1, sizeof(*cu));
+            cmb_process_initialize(&cu->proc, "Customer", c_customer_body, w, 0);
+            cu->world = w;
+            if (w->all_count >= 4096u) {
+                fprintf(stderr, "ref_driver: more than 4096 live customers\n");
+                abort();
+            }
+            w->all_list[w->all_count++] = cu;
+        }
+        cu->t_arrival = cmb_time();
+        cmb_process_start(&cu->proc);
+    }
+    return NULL;
+}
+
+/* -------------------------------------------------------------- dispatcher */
+
+static void pump_events(struct ref_trial *t)
+{
+    uint64_t n = 0u;
+    for (;;) {
+        const uint64_t depth = cmb_event_queue_count();
+        if (depth > t->max_fel) {
+            t->max_fel = depth;
+        }
+        if (!cmb_event_execute_next()) {
+            break;
+        }
+        if (n < t->trace_cap) {
+            t->trace_key[n] = cmb_event_current();
+            t->trace_time[n] = cmb_time();
+        }
+        n++;
+    }
+    t->events = n;
+    t->t_end = cmb_time();
+}
+
+static void run_queue_trial(struct ref_trial *t)
+{
+    struct q_world w = { .trl = t };
+    w.queue = cmb_objectqueue_create();
+    cmb_objectqueue_initialize(w.queue, "Queue", CMB_UNLIMITED);
+    w.source = cmb_process_create();
+    cmb_process_initialize(w.source, "Arrival", q_source_body, &w, 0);
+    cmb_process_start(w.source);
+    w.server = cmb_process_create();
+    cmb_process_initialize(w.server, "Service", q_server_body, &w, 0);
+    cmb_process_start(w.server);
+
+    pump_events(t);
+
+    cmb_process_stop(w.server, NULL);
+    cmb_process_terminate(w.source);
+    cmb_process_terminate(w.server);
+    cmb_process_destroy(w.source);
+    cmb_process_destroy(w.server);
+    cmb_objectqueue_destroy(w.queue);
+}
+
+static void run_pool_trial(struct ref_trial *t)
+{
+    struct c_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->pool = cmb_resourcepool_create();
+    cmb_resourcepool_initialize(w->pool, "Servers", (uint64_t)t->servers);
+    w->source = cmb_process_create();
+    cmb_process_initialize(w->source, "Arrival", c_source_body, w, 0);
+    cmb_process_start(w->source);
+
+    pump_events(t);
+
+    cmb_process_terminate(w->source);
+    cmb_process_destroy(w->source);
+    for (unsigned i = 0u; i < w->all_count; i++) {
+        cmb_process_terminate(&w->all_list[i]->proc);
+        free(w->all_list[i]);
+    }
+    t->max_queue = w->all_count;
+    cmb_resourcepool_destroy(w->pool);
+    free(w);
+}
+
+static void run_trial(void *vt)
+{
+    struct ref_trial *t = vt;
+    t->events = 0u;
+    t->objects = 0u;
+    t->sum_wait = 0.0;
+    t->t_end = 0.0;
+    t->max_fel = 0u;
+    t->max_queue = 0u;
+
+    cmb_logger_flags_off(CMB_LOGGER_INFO);
+    cmb_random_initialize(t->seed);
+    cmb_event_queue_initialize(0.0);
+    if (t->model == 2) {
+        run_pool_trial(t);
+    }
+    else {
+        run_queue_trial(t);
+    }
+    cmb_event_queue_terminate();
+}
+
+/* ------------------------------------------------------------------ C ABI */
+
+struct ref_result {
+    uint64_t events;
+    uint64_t objects;
+    double t_end;
+    double sum_wait;
+    uint64_t max_fel;
+    uint64_t max_queue;
+};
+
+/*
+ * Run trials [first, first + count) of an experiment whose per-trial seed is
+ * cmb_random_fmix64(master_seed, global trial index).
+ * parallel != 0: through the reference's own executive, cimba_run_experiment()
+ * (one pthread per logical core, src/cimba.c:171); parallel == 0: serially on
+ * the calling thread.
+ */
+int ref_run_trials(int model, int servers, uint64_t master_seed,
+                   uint64_t first, uint64_t count, uint64_t num_objects,
+                   double arr_mean, double srv_mean, int parallel,
+                   struct ref_result *out)
+{
+    struct ref_trial *exp = calloc(count, sizeof(*exp));
+    if (exp == NULL) {
+        return -1;
+    }
+    for (uint64_t i = 0u; i < count; i++) {
+        exp[i].seed = cmb_random_fmix64(master_seed, first + i);
+        exp[i].num_objects = num_objects;
+        exp[i].arr_mean = arr_mean;
+        exp[i].srv_mean = srv_mean;
+        exp[i].model = model;
+        exp[i].servers = servers;
+    }
+    if (parallel) {
+        cimba_run_experiment(exp, count, sizeof(*exp), run_trial);
+    }
+    else {
+        for (uint64_t i = 0u; i < count; i++) {
+            run_trial(&exp[i]);
+        }
+    }
+    for (uint64_t i = 0u; i < count; i++) {
+        out[i].events = exp[i].events;
+        out[i].objects = exp[i].objects;
+        out[i].t_end = exp[i].t_end;
+        out[i].sum_wait = exp[i].sum_wait;
+        out[i].max_fel = exp[i].max_fel;
+        out[i].max_queue = exp[i].max_queue;
+    }
+    free(exp);
+    return 0;
+}
+
+/* One trial with an explicit seed, recording (key, clock) of the first pops. */
+int ref_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects,
+                    double arr_mean, double srv_mean, uint64_t trace_cap,
+                    uint64_t *trace_key, double *trace_time,
+                    struct ref_result *out)
+{
+    struct ref_trial t = { .seed = seed, .num_objects = num_objects,
+                           .arr_mean = arr_mean, .srv_mean = srv_mean,
+                           .model = model, .servers = servers,
+                           .trace_cap = trace_cap, .trace_key = trace_key,
+                           .trace_time = trace_time };
+    run_trial(&t);
+    out->events = t.events;
+    out->objects = t.objects;
+    out->t_end = t.t_end;
+    out->sum_wait = t.sum_wait;
+    out->max_fel = t.max_fel;
+    out->max_queue = t.max_queue;
+    return 0;
+}
+
+uint64_t ref_fmix64(uint64_t seed, uint64_t nonce)
+{
+    return cmb_random_fmix64(seed, nonce);
+}
+
+extern uint32_t cmi_cpu_cores(void);   /* src/port/x86-64/linux/cmi_cpu_cores.c:23 */
+
+int ref_cpu_cores(void)
+{
+    return (int)cmi_cpu_cores();
+}
+
+/*
+ * Draw n variates after cmb_random_initialize(seed).
+ * kind 0: raw sfc64 (bit pattern stored in the double slot)
+ *      1: cmb_random_exponential(p0)     2: cmb_random_std_normal()
+ *      3: cmb_random()                   4: cmb_random_normal(p0, p1)
+ *      5: cmb_random_erlang((unsigned)p0, p1)
+ *      6: cmb_random_uniform(p0, p1)     7: cmb_random_dice((long)p0,(long)p1) as double
+ *      8: cmb_random_bernoulli(p0) as 0/1
+ */
+int ref_rng_draws(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out)
+{
+    cmb_random_initialize(seed);
+    for (uint64_t i = 0u; i < n; i++) {
+        switch (kind) {
+        case 0: { uint64_t u = cmb_random_sfc64(); memcpy(&out[i], &u, 8); break; }
+        case 1: out[i] = cmb_random_exponential(p0); break;
+        case 2: out[i] = cmb_random_std_normal(); break;
+        case 3: out[i] = cmb_random(); break;
+        case 4: out[i] = cmb_random_normal(p0, p1); break;
+        case 5: out[i] = cmb_random_erlang((unsigned)p0, p1); break;
+        case 6: out[i] = cmb_random_uniform(p0, p1); break;
+        case 7: out[i] = (double)cmb_random_dice((long)p0, (long)p1); break;
+        case 8: out[i] = (double)cmb_random_bernoulli(p0); break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
+/* Summary parity helpers: out = {count, min, max, m1, m2, m3, m4} */
+static void export_summary(const struct cmb_datasummary *ds, double *out)
+{
+    out[0] = (double)ds->count;
+    out[1] = ds->min;
+    out[2] = ds->max;
+    out[3] = ds->m1;
+    out[4] = ds->m2;
+    out[5] = ds->m3;
+    out[6] = ds->m4;
+}
+
+int ref_datasummary_of(const double *x, uint64_t n, double *out)
+{
+    struct cmb_datasummary ds;
+    cmb_datasummary_initialize(&ds);
+    for (uint64_t i = 0u; i < n; i++) {
+        cmb_datasummary_add(&ds, x[i]);
+    }
+    export_summary(&ds, out);
+    return 0;
+}
+
+/* Summarise x[0..na) and x[na..n) separately, merge (src/cmb_datasummary.c:93) */
+int ref_datasummary_split_merge(const double *x, uint64_t na, uint64_t n, double *out)
+{
+    struct cmb_datasummary a, b, m;
+    cmb_datasummary_initialize(&a);
+    cmb_datasummary_initialize(&b);
+    cmb_datasummary_initialize(&m);
+    for (uint64_t i = 0u; i < na; i++) {
+        cmb_datasummary_add(&a, x[i]);
+    }
+    for (uint64_t i = na; i < n; i++) {
+        cmb_datasummary_add(&b, x[i]);
+    }
+    cmb_datasummary_merge(&m, &a, &b);
+    export_summary(&m, out);
+    return 0;
+}
+
+/* Weighted twins: out = {count, min, max, m1, m2, m3, m4, wsum} */
+static void export_wsummary(const struct cmb_wtdsummary *ws, double *out)
+{
+    export_summary(&ws->ds, out);
+    out[7] = ws->wsum;
+}
+
+int ref_wtdsummary_of(const double *x, const double *w, uint64_t n, double *out)
+{
+    struct cmb_wtdsummary ws;
+    cmb_wtdsummary_initialize(&ws);
+    for (uint64_t i = 0u; i < n; i++) {
+        cmb_wtdsummary_add(&ws, x[i], w[i]);
+    }
+    export_wsummary(&ws, out);
+    return 0;
+}
+
+int ref_wtdsummary_split_merge(const double *x, const double *w, uint64_t na,
+                               uint64_t n, double *out)
+{
+    struct cmb_wtdsummary a, b, m;
+    cmb_wtdsummary_initialize(&a);
+    cmb_wtdsummary_initialize(&b);
+    cmb_wtdsummary_initialize(&m);
+    for (uint64_t i = 0u; i < na; i++) {
+        cmb_wtdsummary_add(&a, x[i], w[i]);
+    }
+    for (uint64_t i = na; i < n; i++) {
+        cmb_wtdsummary_add(&b, x[i], w[i]);
+    }
+    cmb_wtdsummary_merge(&m, &a, &b);
+    export_wsummary(&m, out);
+    return 0;
+}
