@@ -1,0 +1,336 @@
+// capi.cu - the C-ABI shared library (include/cimba_b200.h) over the CUDA engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false ...
+// (see __graft_entry__.build()).  No CPU fallback exists anywhere in this file:
+// every compute entry point ends in a kernel launch or fails.
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cimba_b200.h"
+#include "engine.cuh"
+#include "queue_model.cuh"
+#include "rng.cuh"
+#include "summary.cuh"
+
+using namespace cimba_b200;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return CIMBA_B200_ECUDA;
+}
+
+#define CUDA_TRY(expr)                                             \
+    do {                                                           \
+        cudaError_t e_ = (expr);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr);        \
+    } while (0)
+
+constexpr uint32_t QUEUE_SPILL_CAP = 512u;     // doubles per trial behind the 32-entry window
+
+bool is_queue_model(int m) { return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1; }
+
+// ---------------------------------------------------------------- RNG KAT kernel
+__global__ void rng_draws_kernel(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out)
+{
+    __shared__ ZigHot hot;
+    stage_zig_hot(hot, true);
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    Sfc64 r;
+    r.seed(seed);
+    for (uint64_t i = 0; i < n; i++) {
+        double v = 0.0;
+        switch (kind) {
+        case 0: v = __longlong_as_double((long long)r.next()); break;
+        case 1: v = r.exponential(hot, p0); break;
+        case 2: v = r.std_normal(hot); break;
+        case 3: v = r.uniform01(); break;
+        case 4: v = r.normal(hot, p0, p1); break;
+        case 5: v = r.erlang(hot, (unsigned)p0, p1); break;
+        case 6: v = r.uniform(p0, p1); break;
+        case 7: v = (double)r.dice((long long)p0, (long long)p1); break;
+        case 8: v = (double)r.bernoulli(p0); break;
+        }
+        out[i] = v;
+    }
+}
+
+template <int MODEL>
+int launch_queue(const QueueArgs &qa, bool trace, dim3 grid, cudaStream_t st)
+{
+    if (trace) {
+        queue_kernel<MODEL, true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+    }
+    else {
+        queue_kernel<MODEL, false><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+    }
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "queue_kernel launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cimba_b200_version(void) { return CIMBA_B200_VERSION_STRING; }
+const char *cimba_b200_last_error(void) { return g_err; }
+uint64_t cimba_b200_launch_count(void) { return g_launches.load(); }
+uint64_t cimba_b200_fmix64(uint64_t seed, uint64_t nonce) { return fmix64(seed, nonce); }
+
+int cimba_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
+{
+    if (job == nullptr) {
+        return 0u;
+    }
+    if (is_queue_model(job->model)) {
+        return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
+    }
+    return 0u;
+}
+
+int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
+{
+    if (job == nullptr) return fail(CIMBA_B200_EINVAL, "job is NULL");
+    if (job->num_trials == 0u) return fail(CIMBA_B200_EINVAL, "num_trials must be > 0 (src/cimba.c:157)");
+    if (job->arr_mean == nullptr || job->srv_mean == nullptr)
+        return fail(CIMBA_B200_EINVAL, "arr_mean/srv_mean device arrays are required");
+    if (job->num_objects >= 0xffffffffull) return fail(CIMBA_B200_EINVAL, "num_objects must be < 2^32-1");
+    const int mapping = job->mapping == 0 ? CIMBA_B200_MAP_LANE : job->mapping;
+    if (mapping != CIMBA_B200_MAP_LANE && mapping != CIMBA_B200_MAP_WARP)
+        return fail(CIMBA_B200_EINVAL, "mapping must be CIMBA_B200_MAP_LANE or CIMBA_B200_MAP_WARP");
+    const bool trace = job->trace_cap > 0u;
+    if (trace && (job->trace_key == nullptr || job->trace_time == nullptr))
+        return fail(CIMBA_B200_EINVAL, "trace_cap > 0 needs trace_key and trace_time");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    if (is_queue_model(job->model)) {
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        QueueArgs qa{};
+        qa.mapping = mapping;
+        qa.master_seed = job->master_seed;
+        qa.first_trial = job->first_trial;
+        qa.num_trials = job->num_trials;
+        qa.num_objects = job->num_objects;
+        qa.arr_mean = job->arr_mean;
+        qa.srv_mean = job->srv_mean;
+        qa.events = job->events;
+        qa.objects = job->objects;
+        qa.t_end = job->t_end;
+        qa.sum_wait = job->sum_wait;
+        qa.status = job->status;
+        qa.max_queue = job->max_queue;
+        qa.spill = (double *)job->workspace;
+        qa.spill_cap = QUEUE_SPILL_CAP;
+        qa.trace_cap = job->trace_cap;
+        qa.trace_key = job->trace_key;
+        qa.trace_time = job->trace_time;
+        const uint64_t threads = job->num_trials * (uint64_t)mapping;
+        const uint64_t blocks = (threads + QUEUE_BLOCK - 1) / QUEUE_BLOCK;
+        if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
+        dim3 grid((unsigned)blocks);
+        return job->model == CIMBA_B200_MODEL_MM1 ? launch_queue<0>(qa, trace, grid, st)
+                                                  : launch_queue<1>(qa, trace, grid, st);
+    }
+    return fail(CIMBA_B200_EINVAL, "unknown model");
+}
+
+int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
+                         uint64_t num_trials, double *out_summary, void *stream)
+{
+    if (sum_wait == nullptr || objects == nullptr || out_summary == nullptr || num_trials == 0u)
+        return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_summarize");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    summarize_kernel<<<1, SUMMARY_BLOCK, 0, (cudaStream_t)stream>>>(sum_wait, objects, num_trials, out_summary);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "summarize_kernel launch");
+}
+
+int cimba_b200_rng_draws(uint64_t seed, int kind, double p0, double p1,
+                         uint64_t n, double *out, void *stream)
+{
+    if (out == nullptr || kind < 0 || kind > 8) return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_rng_draws");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    rng_draws_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(seed, kind, p0, p1, n, out);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "rng_draws_kernel launch");
+}
+
+// ------------------------------------------------------------ host-buffer path
+
+int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
+                              const cimba_b200_experiment *d)
+{
+    if (array == nullptr || d == nullptr) return fail(CIMBA_B200_EINVAL, "NULL experiment array or descriptor");
+    if (num_trials == 0u || stride == 0u) return fail(CIMBA_B200_EINVAL, "num_trials and trial_struct_size must be > 0");
+    if (d->off_arr_mean == CIMBA_B200_NO_FIELD || d->off_srv_mean == CIMBA_B200_NO_FIELD)
+        return fail(CIMBA_B200_EINVAL, "off_arr_mean and off_srv_mean are required");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    if (d->device >= 0) CUDA_TRY(cudaSetDevice(d->device));
+
+    const uint64_t n = num_trials;
+    char *base = (char *)array;
+
+    // gather the two input columns into pinned staging, scatter results back the same way
+    double *h_in = nullptr;
+    unsigned char *h_out = nullptr;
+    const size_t out_row = 2 * sizeof(uint64_t) + 2 * sizeof(double) + sizeof(uint32_t) + sizeof(uint32_t);
+    CUDA_TRY(cudaMallocHost(&h_in, 2 * n * sizeof(double)));
+    CUDA_TRY(cudaMallocHost(&h_out, n * out_row));
+    for (uint64_t i = 0; i < n; i++) {
+        memcpy(&h_in[i], base + i * stride + d->off_arr_mean, sizeof(double));
+        memcpy(&h_in[n + i], base + i * stride + d->off_srv_mean, sizeof(double));
+    }
+
+    cimba_b200_device_job job{};
+    job.model = d->model;
+    job.servers = d->servers;
+    job.mapping = d->mapping;
+    job.master_seed = d->master_seed;
+    job.first_trial = d->first_trial;
+    job.num_trials = n;
+    job.num_objects = d->num_objects;
+
+    unsigned char *dev = nullptr;
+    const uint64_t ws = cimba_b200_workspace_bytes(&job);
+    const size_t in_bytes = 2 * n * sizeof(double);
+    const size_t out_bytes = n * out_row;
+    int rc = CIMBA_B200_OK;
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreate(&st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamCreate"); goto done; }
+    e = cudaMalloc(&dev, in_bytes + out_bytes + ws + 256);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); goto done; }
+    {
+        double *d_in = (double *)dev;
+        unsigned char *d_out = dev + in_bytes;
+        job.arr_mean = d_in;
+        job.srv_mean = d_in + n;
+        job.events = (uint64_t *)d_out;
+        job.objects = job.events + n;
+        job.t_end = (double *)(job.objects + n);
+        job.sum_wait = job.t_end + n;
+        job.status = (uint32_t *)(job.sum_wait + n);
+        job.max_queue = job.status + n;
+        job.workspace = dev + ((in_bytes + out_bytes + 255) / 256) * 256;
+        job.workspace_bytes = ws;
+
+        e = cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); goto done; }
+        rc = cimba_b200_launch(&job, st);
+        if (rc != CIMBA_B200_OK) goto done;
+        e = cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); goto done; }
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamSynchronize"); goto done; }
+
+        const uint64_t *ev = (const uint64_t *)h_out;
+        const uint64_t *ob = ev + n;
+        const double *te = (const double *)(ob + n);
+        const double *sw = te + n;
+        const uint32_t *stt = (const uint32_t *)(sw + n);
+        bool any_bad = false;
+        for (uint64_t i = 0; i < n; i++) {
+            char *row = base + i * stride;
+            if (d->off_obj_cnt != CIMBA_B200_NO_FIELD) memcpy(row + d->off_obj_cnt, &ob[i], 8);
+            if (d->off_sum_wait != CIMBA_B200_NO_FIELD) memcpy(row + d->off_sum_wait, &sw[i], 8);
+            if (d->off_avg_wait != CIMBA_B200_NO_FIELD) {
+                const double avg = sw[i] / (double)ob[i];
+                memcpy(row + d->off_avg_wait, &avg, 8);
+            }
+            if (d->off_events != CIMBA_B200_NO_FIELD) memcpy(row + d->off_events, &ev[i], 8);
+            if (d->off_t_end != CIMBA_B200_NO_FIELD) memcpy(row + d->off_t_end, &te[i], 8);
+            if (d->off_status != CIMBA_B200_NO_FIELD) memcpy(row + d->off_status, &stt[i], 4);
+            any_bad |= (stt[i] != 0u);
+        }
+        if (any_bad) rc = fail(CIMBA_B200_ETRIAL, "at least one trial reported a capacity violation");
+    }
+done:
+    if (dev) cudaFree(dev);
+    if (st) cudaStreamDestroy(st);
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    return rc;
+}
+
+// ------------------------------------------------- cmb_datasummary on the host
+
+void cimba_b200_datasummary_initialize(cimba_b200_datasummary *s)
+{   // src/cmb_datasummary.c:37-50
+    s->cookie = 0x1ce1ce1ce1ce1ce1ull;
+    s->count = 0u;
+    s->min = DBL_MAX;
+    s->max = -DBL_MAX;
+    s->m1 = s->m2 = s->m3 = s->m4 = 0.0;
+}
+
+uint64_t cimba_b200_datasummary_add(cimba_b200_datasummary *s, double y)
+{
+    SummaryAcc a{s->count, s->min, s->max, s->m1, s->m2, s->m3, s->m4};
+    summary_add(a, y);
+    s->count = a.count; s->min = a.min; s->max = a.max;
+    s->m1 = a.m1; s->m2 = a.m2; s->m3 = a.m3; s->m4 = a.m4;
+    return s->count;
+}
+
+uint64_t cimba_b200_datasummary_merge(cimba_b200_datasummary *tgt,
+                                      const cimba_b200_datasummary *p,
+                                      const cimba_b200_datasummary *q)
+{
+    const SummaryAcc a{p->count, p->min, p->max, p->m1, p->m2, p->m3, p->m4};
+    const SummaryAcc b{q->count, q->min, q->max, q->m1, q->m2, q->m3, q->m4};
+    const SummaryAcc c = summary_merge(a, b);
+    cimba_b200_datasummary_initialize(tgt);
+    tgt->count = c.count; tgt->min = c.min; tgt->max = c.max;
+    tgt->m1 = c.m1; tgt->m2 = c.m2; tgt->m3 = c.m3; tgt->m4 = c.m4;
+    return tgt->count;
+}
+
+double cimba_b200_datasummary_mean(const cimba_b200_datasummary *s) { return s->m1; }
+
+double cimba_b200_datasummary_variance(const cimba_b200_datasummary *s)
+{   // include/cmb_datasummary.h:197-210 (sample variance)
+    return (s->count > 1u) ? s->m2 / (double)(s->count - 1u) : 0.0;
+}
+
+double cimba_b200_datasummary_stddev(const cimba_b200_datasummary *s)
+{
+    return sqrt(cimba_b200_datasummary_variance(s));
+}
+
+}  // extern "C"

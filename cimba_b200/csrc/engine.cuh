@@ -1,0 +1,207 @@
+// engine.cuh - device-side simulation kernel pieces shared by all models.
+//
+// What the reference does per event:
+//   cmb_event_execute_next (src/cmb_event.c:229-252) pops the future-event list
+//   (cmi_hashheap_dequeue, src/cmi_hashheap.c:486-524), advances the clock and
+//   calls the event's action, which resumes a stackful coroutine
+//   (src/cmi_coroutine.c:296) that runs user code until its next blocking call
+//   (cmb_process_hold -> cmb_event_schedule -> cmi_hashheap_enqueue) and yields.
+//
+// What this engine does instead (B200-first, not a translation):
+//   * a process is a resume-point index; a blocking call is a *command* the
+//     process body hands back to the dispatcher (hold for a duration, hold for a
+//     random variate, wait on a guard, exit).  The dispatcher executes commands
+//     in warp-converged code, so lanes that are in different processes still
+//     share the expensive part (variate generation, event-list insert);
+//   * event records are 16-24 bytes, not 64 (time, issue key, action, owner);
+//   * ordering is the reference's strict total order - time ascending, priority
+//     descending, issue key ascending (default_compare, src/cmi_hashheap.c:55-80)
+//     - and keys are issued 1,2,3... per trial in program order
+//     (src/cmi_hashheap.c:449-453), so pop order is bit-identical whatever the
+//     container's internal layout ("Event ordering").
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cimba_b200 {
+
+// Signals a blocking call returns (include/cmb_process.h:59-99) - same values.
+enum : int64_t {
+    SIG_SUCCESS = 0,
+    SIG_PREEMPTED = -1,
+    SIG_INTERRUPTED = -2,
+    SIG_STOPPED = -3,
+    SIG_CANCELLED = -4,
+    SIG_TIMEOUT = -5,
+};
+
+// Event actions = the reference's event functions.
+enum : uint32_t {
+    ACT_NONE = 0u,
+    ACT_START = 1u,            // start_event,            src/cmb_process.c:115-122
+    ACT_WAKE_TIME = 2u,        // wakeup_event_time,      src/cmb_process.c:292-308
+    ACT_WAKE_RESOURCE = 3u,    // wakeup_event_resource,  src/cmb_resourceguard.c:168-180
+};
+
+// Per-trial status word written back with the results (SURVEY.md section 8b,
+// "Error convention": the host turns non-zero into the reference's fatal path).
+enum : uint32_t {
+    TRIAL_OK = 0u,
+    TRIAL_ERR_QUEUE_OVERFLOW = 1u,     // object queue outgrew window + spill ring
+    TRIAL_ERR_FEL_OVERFLOW = 2u,       // more pending events than the container holds
+    TRIAL_ERR_KEY_OVERFLOW = 4u,       // more than 2^32-1 events issued in one trial
+    TRIAL_ERR_GUARD_OVERFLOW = 8u,     // more waiters than the guard holds
+    TRIAL_ERR_PROC_OVERFLOW = 16u,     // more live processes than the pool holds
+    TRIAL_ERR_NEGATIVE_HOLD = 32u,     // cmb_process_hold(dur < 0), src/cmb_process.c:264
+};
+
+// ---------------------------------------------------------------------------
+// SlotFel<N>: future-event list for models in which every process owns at most
+// one pending event (start, hold wake-up or resource wake-up) - true for any
+// model without timers/interrupts.  Slot p belongs to process p, so an insert
+// is a register write and pop-min is an N-way compare; the whole list lives in
+// registers.  Equal priorities only (all shipped workloads use priority 0).
+// ---------------------------------------------------------------------------
+template <int N>
+struct SlotFel {
+    double   t[N];
+    uint32_t key[N];
+    uint32_t act[N];
+    uint32_t issued;           // item_counter, src/cmi_hashheap.c:449-453
+
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            t[i] = __longlong_as_double(0x7ff0000000000000LL);   // +inf = empty
+            key[i] = 0u;
+            act[i] = ACT_NONE;
+        }
+        issued = 0u;
+    }
+
+    // cmb_event_schedule (src/cmb_event.c:123-140) for owner process p.
+    // Returns false if p already has a pending event (capacity violation).
+    __device__ __forceinline__ bool schedule(int p, uint32_t action, double time)
+    {
+        const uint32_t k = ++issued;
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i == p) {
+                ok = (act[i] == ACT_NONE);
+                t[i] = time;
+                key[i] = k;
+                act[i] = action;
+            }
+        }
+        return ok;
+    }
+
+    __device__ __forceinline__ int count() const
+    {
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            n += (act[i] != ACT_NONE) ? 1 : 0;
+        }
+        return n;
+    }
+
+    // cmi_hashheap_dequeue (src/cmi_hashheap.c:486-524): remove the entry that is
+    // first under (time asc, key asc).  Returns false when the list is empty.
+    __device__ __forceinline__ bool pop(int &p, uint32_t &action, double &time, uint32_t &k)
+    {
+        int best = 0;
+        double bt = t[0];
+        uint32_t bk = key[0];
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const bool before = (t[i] < bt) || (t[i] == bt && key[i] < bk);
+            if (before) {
+                best = i;
+                bt = t[i];
+                bk = key[i];
+            }
+        }
+        uint32_t ba = ACT_NONE;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i == best) {
+                ba = act[i];
+                act[i] = ACT_NONE;
+                t[i] = __longlong_as_double(0x7ff0000000000000LL);
+            }
+        }
+        p = best;
+        action = ba;
+        time = bt;
+        k = bk;
+        return ba != ACT_NONE;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// StampRing: the cmb_objectqueue of the queueing workloads.  The reference
+// keeps a linked list of 16-byte tags pointing at pooled 8-byte objects
+// (src/cmb_objectqueue.c:45-52, benchmark/MM1_multi.c:61-64); the only payload
+// is the arrival timestamp, so the queue is a FIFO ring of doubles.
+//
+// The oldest WINDOW entries live in shared memory (one column per thread,
+// element i of thread tid at win[i * stride + tid]: with 8-byte elements and a
+// stride that is a multiple of 16 the 32 lanes of a warp hit 32 distinct bank
+// pairs whatever their row, so accesses are conflict-free); anything beyond
+// spills to a per-trial ring in HBM and is pulled back one element per get.
+// ---------------------------------------------------------------------------
+template <int WINDOW>
+struct StampRing {
+    static_assert((WINDOW & (WINDOW - 1)) == 0, "window must be a power of two");
+    double  *win;              // shared memory, already offset by threadIdx.x
+    double  *spill;            // global memory, this trial's ring (spill_cap doubles)
+    uint32_t stride;           // blockDim.x
+    uint32_t spill_mask;       // spill_cap - 1 (spill_cap is a power of two, may be 0)
+    uint32_t head;             // index of the oldest entry (monotone)
+    uint32_t len;
+
+    __device__ __forceinline__ void init(double *w, uint32_t s, double *sp, uint32_t spill_cap)
+    {
+        win = w;
+        stride = s;
+        spill = sp;
+        spill_mask = spill_cap - 1u;
+        head = 0u;
+        len = 0u;
+    }
+
+    // false = overflow (entry dropped, trial must be flagged)
+    __device__ __forceinline__ bool put(double v)
+    {
+        const uint32_t pos = head + len;
+        if (len < (uint32_t)WINDOW) {
+            win[(pos & (WINDOW - 1)) * stride] = v;
+        }
+        else {
+            if (spill == nullptr || len - WINDOW > spill_mask) {
+                return false;
+            }
+            spill[pos & spill_mask] = v;
+        }
+        len++;
+        return true;
+    }
+
+    __device__ __forceinline__ double take()
+    {
+        const double v = win[(head & (WINDOW - 1)) * stride];
+        head++;
+        len--;
+        if (len >= (uint32_t)WINDOW) {
+            const uint32_t pos = head + WINDOW - 1u;
+            win[(pos & (WINDOW - 1)) * stride] = spill[pos & spill_mask];
+        }
+        return v;
+    }
+};
+
+}  // namespace cimba_b200

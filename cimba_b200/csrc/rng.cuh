@@ -1,0 +1,314 @@
+// rng.cuh - per-trial pseudo-random stream and variate samplers, device side.
+//
+// Drop-in arithmetic for the reference's cmb_random (src/cmb_random.c,
+// include/cmb_random.h): the same generator (sfc64, 256-bit state, seeded by
+// four splitmix64 outputs plus 20 discarded draws) and the same McFarland
+// ziggurat samplers over the same 256-layer tables, so that a trial seeded with
+// cmb_random_fmix64(master, index) consumes and produces the identical stream.
+//
+// B200 mapping: the four 64-bit state words live in registers (8 x 32-bit) for
+// the whole trial; the 2 KB layer-width tables used by 98.4 % of the draws are
+// staged once per CTA in shared memory (lanes index them with unrelated
+// indices, which constant memory would serialise); the overhang tables used by
+// the remaining 1.6 % stay in global memory behind L1/L2.
+//
+// Bit parity rules ("Bit parity of doubles"): every
+// floating-point operation is spelled with a round-to-nearest intrinsic so that
+// nvcc cannot contract a*b+c into an FMA (the reference build has no FMA), and
+// uint64/int64 -> double conversions use the _rn forms (= C casts on x86-64).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "zig_tables.cuh"
+
+namespace cimba_b200 {
+
+// ------------------------------------------------------------- host + device
+// cmb_random_fmix64, src/cmb_random.c:70-80
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t seed, uint64_t nonce)
+{
+    uint64_t h = seed + nonce;
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+// Shared-memory staging area for the two hot tables.
+struct ZigHot {
+    double exp_x[256];
+    double nor_x[256];
+};
+
+__device__ __forceinline__ void stage_zig_hot(ZigHot &hot, bool want_normal)
+{
+    for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x) {
+        hot.exp_x[i] = zig::zig_exp_x[i];
+        hot.nor_x[i] = want_normal ? zig::zig_nor_x[i] : 0.0;
+    }
+}
+
+constexpr double TWO_POW_64 = 18446744073709551616.0;
+constexpr double TWO_POW_63 = 9223372036854775808.0;
+constexpr double TWO_POW_M53 = 1.1102230246251565404e-16;
+
+struct Sfc64 {
+    uint64_t a, b, c, d;
+
+    // cmb_random_sfc64, src/cmb_random.c:54-62
+    __device__ __forceinline__ uint64_t next()
+    {
+        const uint64_t out = a + b + d++;
+        a = b ^ (b >> 11);
+        b = c + (c << 3);
+        c = ((c << 24) | (c >> 40)) + out;
+        return out;
+    }
+
+    // cmb_random_initialize, src/cmb_random.c:112-124 (splitmix64 at :99-106)
+    __device__ __forceinline__ void seed(uint64_t s)
+    {
+        uint64_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t z = (s += 0x9e3779b97f4a7c15ULL);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+            w[i] = z ^ (z >> 31);
+        }
+        a = w[0];
+        b = w[1];
+        c = w[2];
+        d = w[3];
+#pragma unroll 1
+        for (int i = 0; i < 20; i++) {
+            (void)next();
+        }
+    }
+
+    // cmb_random(), include/cmb_random.h:149-152
+    __device__ __forceinline__ double uniform01()
+    {
+        return __dmul_rn(__ull2double_rn(next() >> 11), TWO_POW_M53);
+    }
+
+    // cmb_random_uniform, include/cmb_random.h:165-173
+    __device__ __forceinline__ double uniform(double lo, double hi)
+    {
+        return __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), uniform01()));
+    }
+
+    // cmb_random_bernoulli, include/cmb_random.h:749-754
+    __device__ __forceinline__ unsigned bernoulli(double p)
+    {
+        return uniform01() <= p ? 1u : 0u;
+    }
+
+    // cmb_random_dice, include/cmb_random.h:840-846
+    __device__ __forceinline__ long long dice(long long lo, long long hi)
+    {
+        const double x = __dmul_rn(__ll2double_rn(hi - lo + 1), uniform01());
+        return (long long)floor(__dadd_rn(__ll2double_rn(lo), x));
+    }
+
+    // ------------------------------------------------------------ exponential
+
+    // Is u inside the rectangular body of the exponential ziggurat?
+    static __device__ __forceinline__ bool exp_is_hot(uint64_t u)
+    {
+        return (unsigned)(u & 0xffu) <= ZIG_EXP_MAX;
+    }
+
+    // include/cmb_random.h:321-325: width of layer (u & 255) times the FULL u
+    static __device__ __forceinline__ double exp_hot(const ZigHot &hot, uint64_t u)
+    {
+        return __dmul_rn(hot.exp_x[u & 0xffu], __ull2double_rn(u));
+    }
+
+    // cmi_random_exp_not_hot, src/cmb_random.c:216-285
+    __device__ __forceinline__ double exp_cold(uint64_t ux)
+    {
+        double shift = 0.0;
+        for (;;) {
+            uint64_t uy = next();
+            unsigned j = (unsigned)(uy & 0xffu);
+            if (next() >= zig::zig_exp_prob[j]) {
+                j = zig::zig_exp_alias[j];
+            }
+            if (j > 0u) {
+                const double xj = zig::zig_exp_x[j];
+                const double dx = __dsub_rn(zig::zig_exp_x[j - 1u], xj);
+                for (;;) {
+                    if (uy > (UINT64_MAX - ux)) {
+                        uy = UINT64_MAX - uy;
+                        ux = UINT64_MAX - ux;
+                    }
+                    const uint64_t gap = (UINT64_MAX - ux) - uy;
+                    // zig_exp_convert_x, src/cmb_random.c:198-201
+                    const double x = __dadd_rn(__dmul_rn(xj, TWO_POW_64),
+                                               __dmul_rn(dx, __ull2double_rn(ux)));
+                    if (gap >= zig::zig_exp_concavity[j]) {
+                        return __dadd_rn(x, shift);
+                    }
+                    // zig_exp_convert_y, src/cmb_random.c:203-206
+                    const double y0 = zig::zig_exp_y[j - 1u];
+                    const double y = __dadd_rn(__dmul_rn(y0, TWO_POW_64),
+                                               __dmul_rn(__dsub_rn(zig::zig_exp_y[j], y0),
+                                                         __ull2double_rn(uy)));
+                    if (y <= exp(-x)) {
+                        return __dadd_rn(x, shift);
+                    }
+                    uy = next();
+                    ux = next();
+                }
+            }
+            shift = __dadd_rn(shift, ZIG_EXP_TAIL);
+            ux = next();
+            const unsigned i = (unsigned)(ux & 0xffu);
+            if (i <= ZIG_EXP_MAX) {
+                return __dadd_rn(__dmul_rn(zig::zig_exp_x[i], __ull2double_rn(ux)), shift);
+            }
+        }
+    }
+
+    // cmb_random_std_exponential, include/cmb_random.h:319-329
+    __device__ __forceinline__ double std_exponential(const ZigHot &hot)
+    {
+        const uint64_t u = next();
+        return exp_is_hot(u) ? exp_hot(hot, u) : exp_cold(u);
+    }
+
+    // cmb_random_exponential, include/cmb_random.h:344-352
+    __device__ __forceinline__ double exponential(const ZigHot &hot, double mean)
+    {
+        return __dmul_rn(mean, std_exponential(hot));
+    }
+
+    // cmb_random_erlang, include/cmb_random.h:366-378
+    __device__ __forceinline__ double erlang(const ZigHot &hot, unsigned k, double m)
+    {
+        double x = 0.0;
+        for (unsigned i = 0u; i < k; i++) {
+            x = __dadd_rn(x, exponential(hot, m));
+        }
+        return x;
+    }
+
+    // ----------------------------------------------------------------- normal
+
+    __device__ __forceinline__ int64_t draw63()         // zig_sample63, src/cmb_random.c:333-337
+    {
+        return (int64_t)(next() & (uint64_t)INT64_MAX);
+    }
+
+    static __device__ __forceinline__ double nor_x_of(unsigned j, int64_t ix)
+    {                                                   // zig_nor_convert_x, :321-324
+        const double xj = zig::zig_nor_x[j];
+        return __dadd_rn(__dmul_rn(xj, TWO_POW_63),
+                         __dmul_rn(__dsub_rn(zig::zig_nor_x[j - 1u], xj), __ll2double_rn(ix)));
+    }
+
+    static __device__ __forceinline__ double nor_y_of(unsigned j, int64_t iy)
+    {                                                   // zig_nor_convert_y, :326-329
+        const double y0 = zig::zig_nor_y[j - 1u];
+        return __dadd_rn(__dmul_rn(y0, TWO_POW_63),
+                         __dmul_rn(__dsub_rn(zig::zig_nor_y[j], y0),
+                                   __ull2double_rn((uint64_t)iy)));
+    }
+
+    static __device__ __forceinline__ double nor_pdf_scaled(double x)
+    {                                                   // sc_nor_pdf, :340-343
+        return exp(__dmul_rn(__dmul_rn(-0.5, x), x));
+    }
+
+    // cmi_random_nor_not_hot, src/cmb_random.c:352-451
+    __device__ __forceinline__ double nor_cold(const ZigHot &hot, int64_t ix)
+    {
+        const double sign = (ix < 0) ? -1.0 : 1.0;
+        ix &= INT64_MAX;
+        int64_t iy = draw63();
+        unsigned j = (unsigned)(iy & 0xff);
+        if (ix >= zig::zig_nor_prob[j]) {
+            j = zig::zig_nor_alias[j];
+        }
+        if (j > ZIG_NOR_INFLECTION) {
+            for (;;) {
+                const double x = nor_x_of(j, ix);
+                const int64_t gap = (INT64_MAX - ix) - iy;
+                if (gap >= 0) {
+                    return __dmul_rn(sign, x);
+                }
+                if (gap + zig::zig_nor_convexity[j] >= 0) {
+                    if (nor_y_of(j, iy) < nor_pdf_scaled(x)) {
+                        return __dmul_rn(sign, x);
+                    }
+                }
+                ix = draw63();
+                iy = draw63();
+            }
+        }
+        else if (j == 0u) {
+            double x, z;
+            do {
+                x = __dmul_rn(ZIG_NOR_INV_TAIL, exponential(hot, 1.0));
+                z = exponential(hot, 1.0);
+            } while (__dmul_rn(2.0, z) <= __dmul_rn(x, x));
+            return __dmul_rn(sign, __dadd_rn(x, ZIG_NOR_TAIL));
+        }
+        else if (j < ZIG_NOR_INFLECTION) {
+            for (;;) {
+                if (iy > INT64_MAX - ix) {
+                    iy = INT64_MAX - iy;
+                    ix = INT64_MAX - ix;
+                }
+                const double x = nor_x_of(j, ix);
+                const int64_t gap = (INT64_MAX - ix) - iy;
+                if (gap >= zig::zig_nor_concavity[j]) {
+                    return __dmul_rn(sign, x);
+                }
+                if (nor_y_of(j, iy) <= nor_pdf_scaled(x)) {
+                    return __dmul_rn(sign, x);
+                }
+                ix = draw63();
+                iy = draw63();
+            }
+        }
+        else {
+            for (;;) {
+                const double x = nor_x_of(j, ix);
+                const int64_t gap = (INT64_MAX - ix) - iy;
+                if (gap >= zig::zig_nor_concavity[j]) {
+                    return __dmul_rn(sign, x);
+                }
+                if (gap + zig::zig_nor_convexity[j] > 0) {
+                    if (nor_y_of(j, iy) < nor_pdf_scaled(x)) {
+                        return __dmul_rn(sign, x);
+                    }
+                }
+                ix = draw63();
+                iy = draw63();
+            }
+        }
+    }
+
+    // cmb_random_std_normal, include/cmb_random.h:206-215
+    __device__ __forceinline__ double std_normal(const ZigHot &hot)
+    {
+        const int64_t ix = (int64_t)next();
+        const unsigned i = (unsigned)(ix & 0xff);
+        return (i <= ZIG_NOR_MAX) ? __dmul_rn(hot.nor_x[i], __ll2double_rn(ix))
+                                  : nor_cold(hot, ix);
+    }
+
+    // cmb_random_normal, include/cmb_random.h:230-235
+    __device__ __forceinline__ double normal(const ZigHot &hot, double mu, double sigma)
+    {
+        return __dadd_rn(mu, __dmul_rn(sigma, std_normal(hot)));
+    }
+};
+
+}  // namespace cimba_b200

@@ -1,0 +1,187 @@
+"""Experiment executive: the GPU counterpart of ``cimba_run_experiment``.
+
+Reference contract (include/cimba.h:144-147, src/cimba.c:151-188): the caller owns
+an array of trial structs holding each trial's parameters and result fields; the
+executive runs every trial (there: one pthread per core pulling trial indices off
+an atomic counter) and returns when all results have been written in place.
+Here the trial function is one of the device-resident models and trial ``i`` is
+seeded with ``cmb_random_fmix64(master_seed, first_trial + i)``
+(src/cmb_random.c:70-80, the scheme of test/test_cimba.c:396).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+# struct trial of benchmark/MM1_multi.c:39-45, plus optional engine outputs
+TRIAL_DTYPE = np.dtype([
+    ("arr_mean", "<f8"), ("srv_mean", "<f8"), ("obj_cnt", "<u8"),
+    ("sum_wait", "<f8"), ("avg_wait", "<f8"),
+    ("events", "<u8"), ("t_end", "<f8"), ("status", "<u4"), ("_pad", "<u4"),
+])
+
+
+def fmix64(seed: int, nonce: int) -> int:
+    """cmb_random_fmix64 (src/cmb_random.c:70-80)."""
+    return int(lib.cimba_b200_fmix64(seed & (2**64 - 1), nonce & (2**64 - 1)))
+
+
+def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODEL_MM1,
+                         num_objects: int, master_seed: int, first_trial: int = 0,
+                         servers: int = 1, mapping: int = 0, device: int = -1) -> None:
+    """Run every trial of a host-resident experiment array on the GPU, in place.
+
+    ``experiment_array`` is a 1-D numpy structured array (any dtype that has
+    ``arr_mean`` and ``srv_mean`` double fields; result fields named ``obj_cnt``,
+    ``sum_wait``, ``avg_wait``, ``events``, ``t_end``, ``status`` are filled when
+    present).  Host->device and device->host copies happen inside the call.
+    Raises CimbaError(ETRIAL) if any trial overflowed a device structure.
+    """
+    arr = experiment_array
+    if not isinstance(arr, np.ndarray) or arr.ndim != 1 or arr.dtype.fields is None:
+        raise TypeError("experiment_array must be a 1-D numpy structured array")
+    if len(arr) == 0:
+        raise ValueError("num_trials must be > 0 (reference asserts this, src/cimba.c:157)")
+    if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
+        raise ValueError("experiment_array must be C-contiguous and writeable")
+    f = arr.dtype.fields
+
+    def off(name, kind):
+        if name not in f:
+            return _lib.NO_FIELD
+        if f[name][0] != np.dtype(kind):
+            raise TypeError(f"field {name} must have dtype {kind}")
+        return f[name][1]
+
+    if "arr_mean" not in f or "srv_mean" not in f:
+        raise TypeError("trial struct needs arr_mean and srv_mean double fields")
+    desc = _lib.Experiment(
+        model=model, servers=servers, mapping=mapping, device=device,
+        master_seed=master_seed & (2**64 - 1), first_trial=first_trial, num_objects=num_objects,
+        off_arr_mean=off("arr_mean", "<f8"), off_srv_mean=off("srv_mean", "<f8"),
+        off_obj_cnt=off("obj_cnt", "<u8"), off_sum_wait=off("sum_wait", "<f8"),
+        off_avg_wait=off("avg_wait", "<f8"), off_events=off("events", "<u8"),
+        off_t_end=off("t_end", "<f8"), off_status=off("status", "<u4"))
+    check(lib.cimba_b200_run_experiment(arr.ctypes.data_as(C.c_void_p), len(arr),
+                                        arr.dtype.itemsize, C.byref(desc)))
+
+
+@dataclass
+class TrialResults:
+    """Device-resident per-trial results (SoA), one entry per trial."""
+    events: torch.Tensor      # int64 view of uint64 pop counts
+    objects: torch.Tensor
+    t_end: torch.Tensor
+    sum_wait: torch.Tensor
+    status: torch.Tensor
+    max_queue: torch.Tensor
+    trace_key: Optional[torch.Tensor] = None
+    trace_time: Optional[torch.Tensor] = None
+
+    def total_events(self) -> int:
+        return int(self.events.sum().item())
+
+
+class TrialBuffers:
+    """Reusable device buffers for repeated launches of the same shape."""
+
+    def __init__(self, num_trials: int, device: torch.device, trace_cap: int = 0,
+                 model: int = _lib.MODEL_MM1):
+        n = num_trials
+        self.n = n
+        self.device = device
+        self.events = torch.zeros(n, dtype=torch.int64, device=device)
+        self.objects = torch.zeros(n, dtype=torch.int64, device=device)
+        self.t_end = torch.zeros(n, dtype=torch.float64, device=device)
+        self.sum_wait = torch.zeros(n, dtype=torch.float64, device=device)
+        self.status = torch.zeros(n, dtype=torch.int32, device=device)
+        self.max_queue = torch.zeros(n, dtype=torch.int32, device=device)
+        self.trace_cap = trace_cap
+        self.trace_key = self.trace_time = None
+        if trace_cap:
+            self.trace_key = torch.zeros((n, trace_cap), dtype=torch.int64, device=device)
+            self.trace_time = torch.zeros((n, trace_cap), dtype=torch.float64, device=device)
+        job = _lib.DeviceJob(model=model, num_trials=n)
+        ws = int(lib.cimba_b200_workspace_bytes(C.byref(job)))
+        self.workspace = torch.empty(max(ws, 8), dtype=torch.uint8, device=device)
+        self.workspace_bytes = ws
+
+    def results(self) -> TrialResults:
+        return TrialResults(self.events, self.objects, self.t_end, self.sum_wait,
+                            self.status, self.max_queue, self.trace_key, self.trace_time)
+
+
+def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects: int,
+                  master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
+                  servers: int = 1, mapping: int = 0, buffers: Optional[TrialBuffers] = None,
+                  trace_cap: int = 0) -> TrialResults:
+    """Asynchronously run one trial per element of ``arr_mean`` on the current stream.
+
+    Inputs are float64 CUDA tensors already resident in HBM (the device-resident
+    hot path: no host copies).  Returns device tensors; synchronise before reading.
+    """
+    if not (arr_mean.is_cuda and srv_mean.is_cuda):
+        raise ValueError("arr_mean and srv_mean must be CUDA tensors (there is no CPU path)")
+    if arr_mean.dtype != torch.float64 or srv_mean.dtype != torch.float64:
+        raise TypeError("arr_mean and srv_mean must be float64")
+    if arr_mean.shape != srv_mean.shape or arr_mean.dim() != 1:
+        raise ValueError("arr_mean and srv_mean must be 1-D and of equal length")
+    arr_mean = arr_mean.contiguous()
+    srv_mean = srv_mean.contiguous()
+    n = arr_mean.numel()
+    if n == 0:
+        raise ValueError("num_trials must be > 0 (reference asserts this, src/cimba.c:157)")
+    b = buffers if buffers is not None else TrialBuffers(n, arr_mean.device, trace_cap, model)
+    if b.n != n or b.trace_cap != trace_cap:
+        raise ValueError("buffers do not match this launch")
+    job = _lib.DeviceJob(
+        model=model, servers=servers, mapping=mapping,
+        master_seed=master_seed & (2**64 - 1), first_trial=first_trial,
+        num_trials=n, num_objects=num_objects,
+        arr_mean=arr_mean.data_ptr(), srv_mean=srv_mean.data_ptr(),
+        events=b.events.data_ptr(), objects=b.objects.data_ptr(),
+        t_end=b.t_end.data_ptr(), sum_wait=b.sum_wait.data_ptr(),
+        status=b.status.data_ptr(), max_queue=b.max_queue.data_ptr(),
+        workspace=b.workspace.data_ptr(), workspace_bytes=b.workspace_bytes,
+        trace_cap=trace_cap,
+        trace_key=b.trace_key.data_ptr() if trace_cap else None,
+        trace_time=b.trace_time.data_ptr() if trace_cap else None)
+    with torch.cuda.device(arr_mean.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.cimba_b200_launch(C.byref(job), C.c_void_p(stream)))
+    return b.results()
+
+
+def run_trials(num_trials: int, *, arr_mean: float, srv_mean: float, num_objects: int,
+               master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
+               servers: int = 1, mapping: int = 0, trace_cap: int = 0,
+               device: Optional[torch.device] = None) -> TrialResults:
+    """Convenience: identical parameters for every trial, results after a sync."""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    a = torch.full((num_trials,), arr_mean, dtype=torch.float64, device=dev)
+    s = torch.full((num_trials,), srv_mean, dtype=torch.float64, device=dev)
+    res = launch_trials(a, s, num_objects=num_objects, master_seed=master_seed,
+                        first_trial=first_trial, model=model, servers=servers,
+                        mapping=mapping, trace_cap=trace_cap)
+    torch.cuda.synchronize(dev)
+    return res
+
+
+def rng_draws(seed: int, kind: int, n: int, p0: float = 0.0, p1: float = 0.0,
+              device: Optional[torch.device] = None) -> torch.Tensor:
+    """n variates from the device-side stream seeded with ``seed`` (KAT helper)."""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.cimba_b200_rng_draws(seed & (2**64 - 1), kind, p0, p1, n,
+                                       out.data_ptr(), C.c_void_p(stream)))
+    torch.cuda.synchronize(dev)
+    return out

@@ -1,0 +1,192 @@
+/*
+ * cimba_b200.h - C ABI of the B200-native replication-parallel discrete-event
+ * engine.  Plain C, plain pointers and sizes; no CUDA or torch types.
+ *
+ * This is the GPU drop-in for the reference's experiment executive
+ *
+ *     void cimba_run_experiment(void *your_experiment_array,
+ *                               uint64_t num_trials,
+ *                               size_t trial_struct_size,
+ *                               cimba_trial_func *your_trial_func);
+ *                                   (reference include/cimba.h:144-147,
+ *                                    src/cimba.c:151-188)
+ *
+ * A C function pointer cannot run on the device, so `your_trial_func` is
+ * replaced by a model descriptor naming one of the device-resident models and
+ * telling the library where the parameter and result fields sit inside the
+ * caller's trial struct.  Everything else keeps the reference's contract: the
+ * caller owns the array, the call blocks until every trial has run, results are
+ * written in place, trials are independent, and trial i is seeded with
+ * cmb_random_fmix64(master_seed, first_trial + i) (src/cmb_random.c:70-80, the
+ * scheme of test/test_cimba.c:396).
+ *
+ * Errors: the reference has no error codes (violations abort through
+ * cmb_assert_release -> cmi_assert_failed, include/cmb_assert.h:44-80).  Here
+ * every entry point returns 0 on success or a negative CIMBA_B200_E* code and
+ * never aborts the host process; per-trial capacity violations come back in the
+ * per-trial status word.  There is NO CPU fallback: without a CUDA device the
+ * calls fail with CIMBA_B200_ENODEVICE.
+ */
+#ifndef CIMBA_B200_H
+#define CIMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CIMBA_B200_VERSION_STRING "0.1.0"
+
+/* Device-resident models (SURVEY.md section 8d workloads). */
+#define CIMBA_B200_MODEL_MM1 0   /* benchmark/MM1_multi.c:52-89: exp arrivals, exp service, cmb_objectqueue */
+#define CIMBA_B200_MODEL_GG1 1   /* same structure: cmb_random_erlang(2, m/2) arrivals, normal(m, m/4) service redrawn while < 0 */
+#define CIMBA_B200_MODEL_MMC 2   /* generator + one process per customer contending for a cmb_resourcepool of `servers` units */
+
+/* Error codes */
+#define CIMBA_B200_OK         0
+#define CIMBA_B200_EINVAL    -1  /* bad argument */
+#define CIMBA_B200_ENODEVICE -2  /* no usable CUDA device */
+#define CIMBA_B200_ECUDA     -3  /* CUDA runtime error; see cimba_b200_last_error() */
+#define CIMBA_B200_ETRIAL    -4  /* at least one trial reported a non-zero status */
+#define CIMBA_B200_ENOMEM    -5
+
+/* Per-trial status bits (0 = ok) */
+#define CIMBA_B200_TRIAL_QUEUE_OVERFLOW 1u
+#define CIMBA_B200_TRIAL_FEL_OVERFLOW   2u
+#define CIMBA_B200_TRIAL_KEY_OVERFLOW   4u
+#define CIMBA_B200_TRIAL_GUARD_OVERFLOW 8u
+#define CIMBA_B200_TRIAL_PROC_OVERFLOW  16u
+#define CIMBA_B200_TRIAL_NEGATIVE_HOLD  32u
+
+/* How trials map onto the machine.  LANE: one trial per CUDA thread (32 trials
+ * advance per warp instruction; the default for models whose per-trial state is
+ * a few dozen bytes).  WARP: one trial per warp with lane 0 as the dispatcher
+ * (the mapping BASELINE.json's north_star names; kept for models with large
+ * event lists and for the measured comparison in DESIGN.md). */
+#define CIMBA_B200_MAP_LANE 1
+#define CIMBA_B200_MAP_WARP 32
+
+/* ------------------------------------------------------------------------
+ * Device-resident interface: all pointers are DEVICE pointers; the launch is
+ * asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default
+ * stream).  This is the hot path proper.
+ * ---------------------------------------------------------------------- */
+typedef struct cimba_b200_device_job {
+    int32_t  model;             /* CIMBA_B200_MODEL_* */
+    int32_t  servers;           /* pool capacity for MODEL_MMC, ignored otherwise */
+    int32_t  mapping;           /* CIMBA_B200_MAP_LANE (default if 0) or _WARP */
+    int32_t  reserved;
+    uint64_t master_seed;
+    uint64_t first_trial;       /* global index of trial 0 of this job (sharding) */
+    uint64_t num_trials;
+    uint64_t num_objects;       /* customers generated per trial (NUM_OBJECTS, benchmark/MM1_multi.c:26) */
+    /* per-trial parameters, [num_trials] doubles each (struct trial.arr_mean / .srv_mean) */
+    const double *arr_mean;
+    const double *srv_mean;
+    /* per-trial results, [num_trials] each; any may be NULL */
+    uint64_t *events;           /* future-event-list pops = cmb_event_execute_next() calls */
+    uint64_t *objects;          /* struct trial.obj_cnt */
+    double   *t_end;            /* cmb_time() when the event list ran dry */
+    double   *sum_wait;         /* struct trial.sum_wait */
+    uint32_t *status;           /* CIMBA_B200_TRIAL_* bits */
+    uint32_t *max_queue;        /* diagnostic: longest queue seen */
+    /* scratch in HBM for queue/wait-list spill; size from cimba_b200_workspace_bytes() */
+    void     *workspace;
+    uint64_t  workspace_bytes;
+    /* optional pop trace: the first trace_cap pops of EVERY trial, row-major
+     * [num_trials][trace_cap]; NULL / 0 to disable */
+    uint64_t  trace_cap;
+    uint64_t *trace_key;        /* cmb_event_current() after each pop */
+    double   *trace_time;       /* cmb_time() after each pop */
+} cimba_b200_device_job;
+
+/* Bytes of HBM scratch the job needs (0 is possible). */
+uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job);
+
+/* Enqueue the persistent simulation kernel for the job.  Asynchronous. */
+int cimba_b200_launch(const cimba_b200_device_job *job, void *stream);
+
+/* Number of kernels this library has launched so far in this process. */
+uint64_t cimba_b200_launch_count(void);
+
+/* Reduce per-trial results to a cmb_datasummary of avg = sum_wait/objects on
+ * the device (benchmark/MM1_multi.c:143-148 does this with a serial host loop).
+ * out_summary: DEVICE pointer to 8 doubles {count, min, max, m1, m2, m3, m4, 0}.
+ * Deterministic (fixed merge tree, cmb_datasummary_merge arithmetic). */
+int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
+                         uint64_t num_trials, double *out_summary, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer interface = the cimba_run_experiment() replacement.
+ * ---------------------------------------------------------------------- */
+#define CIMBA_B200_NO_FIELD ((size_t)-1)
+
+typedef struct cimba_b200_experiment {
+    int32_t  model;
+    int32_t  servers;
+    int32_t  mapping;           /* 0 = default */
+    int32_t  device;            /* CUDA device ordinal, -1 = current */
+    uint64_t master_seed;
+    uint64_t first_trial;
+    uint64_t num_objects;
+    /* byte offsets of the fields inside one trial struct */
+    size_t off_arr_mean;        /* double, in  (required) */
+    size_t off_srv_mean;        /* double, in  (required) */
+    size_t off_obj_cnt;         /* uint64, out (or NO_FIELD) */
+    size_t off_sum_wait;        /* double, out (or NO_FIELD) */
+    size_t off_avg_wait;        /* double, out = sum_wait / obj_cnt (or NO_FIELD) */
+    size_t off_events;          /* uint64, out (or NO_FIELD) */
+    size_t off_t_end;           /* double, out (or NO_FIELD) */
+    size_t off_status;          /* uint32, out (or NO_FIELD) */
+} cimba_b200_experiment;
+
+/* Blocks until all trials are done; results written into the caller's array.
+ * Returns CIMBA_B200_ETRIAL if any trial's status is non-zero (results of the
+ * other trials are still valid). */
+int cimba_b200_run_experiment(void *your_experiment_array,
+                              uint64_t num_trials,
+                              size_t trial_struct_size,
+                              const cimba_b200_experiment *desc);
+
+/* ------------------------------------------------------------------------
+ * cmb_datasummary on the host (reference include/cmb_datasummary.h:42-51,
+ * src/cmb_datasummary.c:93-166): same field order and arithmetic, used to fold
+ * per-GPU summaries after the NCCL all-gather.
+ * ---------------------------------------------------------------------- */
+typedef struct cimba_b200_datasummary {
+    uint64_t cookie;
+    uint64_t count;
+    double   min, max;
+    double   m1, m2, m3, m4;
+} cimba_b200_datasummary;
+
+void     cimba_b200_datasummary_initialize(cimba_b200_datasummary *dsp);
+uint64_t cimba_b200_datasummary_add(cimba_b200_datasummary *dsp, double y);
+uint64_t cimba_b200_datasummary_merge(cimba_b200_datasummary *tgt,
+                                      const cimba_b200_datasummary *dsp1,
+                                      const cimba_b200_datasummary *dsp2);
+double   cimba_b200_datasummary_mean(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_variance(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_stddev(const cimba_b200_datasummary *dsp);
+
+/* cmb_random_fmix64 (src/cmb_random.c:70-80): per-trial seed derivation. */
+uint64_t cimba_b200_fmix64(uint64_t seed, uint64_t nonce);
+
+/* Device-side variate generation for stream KATs: n draws from the stream
+ * seeded with `seed`, written to the DEVICE buffer `out` (n doubles).
+ * kind: 0 raw sfc64 bits, 1 exponential(p0), 2 std_normal, 3 uniform01,
+ *       4 normal(p0,p1), 5 erlang((unsigned)p0, p1), 6 uniform(p0,p1),
+ *       7 dice((long)p0,(long)p1), 8 bernoulli(p0) */
+int cimba_b200_rng_draws(uint64_t seed, int kind, double p0, double p1,
+                         uint64_t n, double *out, void *stream);
+
+const char *cimba_b200_version(void);
+const char *cimba_b200_last_error(void);
+int         cimba_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIMBA_B200_H */

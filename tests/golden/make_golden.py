@@ -1,0 +1,115 @@
+#!/usr/bin/env python3
+"""Regenerate the committed golden vectors from the UNMODIFIED reference.
+
+Runs in the build container only (needs oracle/_ref, i.e. /root/reference and
+`make -C oracle ref`).  Everything written here comes out of the reference's own
+code: cmb_random_* streams, seeded runs of the benchmark model through
+cmb_event_execute_next(), and cmb_datasummary/cmb_wtdsummary add + merge.
+
+Doubles are stored as C99 hex-float strings (exact).  Long streams are stored as
+the first values verbatim plus XOR / wrapping-sum checksums of the 64-bit
+patterns of every value, so a single flipped bit anywhere in 10^6 draws fails.
+
+usage: python tests/golden/make_golden.py
+"""
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT / "tests"))
+from oracle_libs import load_ref, Result, trace_trial, rng_draws   # noqa: E402
+
+KAT_SEED = 0x34F05C64D7AD598F          # test/tools/test_stochastic.py:58-69
+SEEDS = [KAT_SEED, 12345, 7, 0, 2**64 - 1]
+RNG_KINDS = {0: (0.0, 0.0), 1: (1.0, 0.0), 2: (0.0, 0.0), 3: (0.0, 0.0), 4: (1.0, 0.25),
+             5: (2.0, 0.625), 6: (-3.0, 5.5), 7: (1.0, 6.0), 8: (0.3, 0.0)}
+MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, servers=1),
+          2: dict(arr=1 / 6.4, srv=1.0, servers=8)}
+
+
+def hexes(a):
+    return [float.hex(float(x)) for x in a]
+
+
+def checksum(a):
+    u = np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+    return {"xor": int(np.bitwise_xor.reduce(u)), "sum": int(np.add.reduce(u, dtype=np.uint64))}
+
+
+def main():
+    ref = load_ref()
+    if ref is None:
+        sys.exit("oracle/_ref is not built; run `make -C oracle ref` first")
+    out = {"source": "ambonvik/cimba via oracle/_ref (unmodified reference build)"}
+
+    rng = {}
+    for seed in SEEDS[:3]:
+        per = {}
+        for kind, (p0, p1) in RNG_KINDS.items():
+            n = 1_000_000 if kind in (0, 1, 2, 4, 5) else 100_000
+            v = rng_draws(ref, "ref", seed, kind, p0, p1, n)
+            if kind == 0:
+                first = [int(x) for x in v[:16].view(np.uint64)]
+            else:
+                first = hexes(v[:16])
+            per[str(kind)] = {"p0": p0, "p1": p1, "n": n, "first": first, **checksum(v)}
+        rng[str(seed)] = per
+    out["rng"] = rng
+    out["fmix64"] = {str(s): [int(ref.ref_fmix64(s, k)) for k in range(4)] for s in SEEDS}
+
+    trials = []
+    for model, par in MODELS.items():
+        for seed in SEEDS:
+            for nobj in (0, 1, 2, 3, 10, 1000, 100_000):
+                r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
+                                             par["arr"], par["srv"], 512 if nobj == 1000 else 0)
+                rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
+                       "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
+                       "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
+                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue}
+                if nobj == 1000:
+                    rec["trace_key"] = [int(k) for k in keys]
+                    rec["trace_time"] = hexes(times)
+                trials.append(rec)
+        # the full-size known answer
+        r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
+        trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
+                       "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
+                       "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
+                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue})
+    out["trials"] = trials
+
+    # experiment-level: first 64 trials of the fmix64-seeded M/M/1 experiment, 10 000 objects
+    n = 64
+    res = (Result * n)()
+    ref.ref_run_trials(0, 1, KAT_SEED, 0, n, 10_000, 1 / 0.9, 1.0, 0, res)
+    out["experiment_mm1"] = {"master_seed": KAT_SEED, "num_objects": 10_000, "trials": [
+        {"events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end), "sum_wait": float.hex(r.sum_wait)}
+        for r in res]}
+
+    # summaries
+    g = np.random.default_rng(1234)
+    x = g.gamma(2.0, 3.0, size=1000)
+    w = g.uniform(0.1, 2.0, size=1000)
+    o7, o8 = (C.c_double * 8)(), (C.c_double * 8)()
+    xs = x.ctypes.data_as(C.POINTER(C.c_double))
+    wsp = w.ctypes.data_as(C.POINTER(C.c_double))
+    summ = {"x": hexes(x), "w": hexes(w)}
+    ref.ref_datasummary_of(xs, 1000, o7); summ["data_all"] = hexes(o7[:7])
+    ref.ref_wtdsummary_of(xs, wsp, 1000, o8); summ["wtd_all"] = hexes(o8[:8])
+    for na in (1, 333, 500, 999):
+        ref.ref_datasummary_split_merge(xs, na, 1000, o7); summ[f"data_merge_{na}"] = hexes(o7[:7])
+        ref.ref_wtdsummary_split_merge(xs, wsp, na, 1000, o8); summ[f"wtd_merge_{na}"] = hexes(o8[:8])
+    out["summary"] = summ
+
+    path = ROOT / "tests/golden/reference_vectors.json"
+    path.write_text(json.dumps(out, indent=0) + "\n")
+    print("wrote", path, path.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+"""Loaders for the two CPU checkers (test infrastructure; never imported by cimba_b200).
+
+* ``load_port()``  - oracle/liboracle_port.so, the plain-C restatement
+  (built on demand with gcc; travels to the GPU box as a prebuilt .so too).
+* ``load_ref()``   - oracle/_ref/librefdrv.so, model drivers linked against the
+  unmodified reference library.  Present wherever `make -C oracle ref` has run
+  (needs /root/reference); returns None otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+ORACLE = ROOT / "oracle"
+
+
+class Result(C.Structure):
+    _fields_ = [("events", C.c_uint64), ("objects", C.c_uint64), ("t_end", C.c_double),
+                ("sum_wait", C.c_double), ("max_fel", C.c_uint64), ("max_queue", C.c_uint64)]
+
+    def key(self):
+        return (self.events, self.objects, self.t_end, self.sum_wait)
+
+
+_DP = C.POINTER(C.c_double)
+_UP = C.POINTER(C.c_uint64)
+
+
+def _bind(lib, prefix):
+    run = getattr(lib, f"{prefix}_run_trials")
+    run.restype = C.c_int
+    run.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                    C.c_double, C.c_double, C.c_int, C.POINTER(Result)]
+    tr = getattr(lib, f"{prefix}_trace_trial")
+    tr.restype = C.c_int
+    tr.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
+                   C.c_uint64, _UP, _DP, C.POINTER(Result)]
+    dr = getattr(lib, f"{prefix}_rng_draws")
+    dr.restype = C.c_int
+    dr.argtypes = [C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_uint64, _DP]
+    fm = getattr(lib, f"{prefix}_fmix64")
+    fm.restype = C.c_uint64
+    fm.argtypes = [C.c_uint64, C.c_uint64]
+    for name, nargs in (("datasummary_of", 2), ("datasummary_split_merge", 3)):
+        f = getattr(lib, f"{prefix}_{name}")
+        f.restype = C.c_int
+        f.argtypes = [_DP] + [C.c_uint64] * (nargs - 1) + [_DP]
+    f = getattr(lib, f"{prefix}_wtdsummary_of")
+    f.restype = C.c_int
+    f.argtypes = [_DP, _DP, C.c_uint64, _DP]
+    f = getattr(lib, f"{prefix}_wtdsummary_split_merge")
+    f.restype = C.c_int
+    f.argtypes = [_DP, _DP, C.c_uint64, C.c_uint64, _DP]
+    return lib
+
+
+def load_port():
+    so = ORACLE / "liboracle_port.so"
+    src = [ORACLE / "port/cimba_port.c", ORACLE / "port/cimba_port.h", ORACLE / "port/zig_tables.h"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in src):
+        subprocess.run(["make", "-C", str(ORACLE), "port"], check=True, capture_output=True)
+    lib = _bind(C.CDLL(str(so)), "port")
+    lib.port_heap_script.restype = C.c_int
+    lib.port_heap_script.argtypes = [C.c_uint64, C.POINTER(C.c_int), _DP,
+                                     C.POINTER(C.c_int64), _UP]
+    return lib
+
+
+def load_ref():
+    so = ORACLE / "_ref/librefdrv.so"
+    if not so.exists():
+        return None
+    lib = _bind(C.CDLL(str(so)), "ref")
+    lib.ref_cpu_cores.restype = C.c_int
+    return lib
+
+
+def trace_trial(lib, prefix, model, servers, seed, nobj, arr, srv, cap):
+    r = Result()
+    keys = (C.c_uint64 * max(cap, 1))()
+    times = (C.c_double * max(cap, 1))()
+    getattr(lib, f"{prefix}_trace_trial")(model, servers, seed, nobj, arr, srv, cap, keys, times, C.byref(r))
+    n = min(cap, r.events)
+    return r, list(keys)[:n], list(times)[:n]
+
+
+def run_trials(lib, prefix, model, servers, master, first, count, nobj, arr, srv, par=0):
+    res = (Result * count)()
+    getattr(lib, f"{prefix}_run_trials")(model, servers, master, first, count, nobj, arr, srv, par, res)
+    return res
+
+
+def rng_draws(lib, prefix, seed, kind, p0, p1, n):
+    out = np.empty(n, dtype=np.float64)
+    rc = getattr(lib, f"{prefix}_rng_draws")(seed, kind, p0, p1, n, out.ctypes.data_as(_DP))
+    assert rc == 0
+    return out

