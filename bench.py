@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--trials", type=int, default=65536, help="replications per GPU per step")
     p.add_argument("--objects", type=int, default=1_000_000, help="customers per replication")
     p.add_argument("--mapping", type=int, default=1, choices=[1, 32], help="1 lane/trial or 32 (warp/trial)")
+    p.add_argument("--variant", type=int, default=0, help="0 default kernel, 1 unfused formulation (A/B)")
     p.add_argument("--ref-trials", type=int, default=0, help="CPU sample size (0 = 16 per core)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -194,7 +195,7 @@ def main():
 
     def step():
         return cb.launch_trials(arr, srv, num_objects=NOBJ, master_seed=MASTER_SEED, first_trial=first,
-                                mapping=args.mapping, buffers=bufs)
+                                mapping=args.mapping, buffers=bufs, variant=args.variant)
 
     def barrier():
         if world > 1:

@@ -22,7 +22,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
 class DeviceJob(C.Structure):
     """struct cimba_b200_device_job"""
     _fields_ = [
-        ("model", C.c_int32), ("servers", C.c_int32), ("mapping", C.c_int32), ("reserved", C.c_int32),
+        ("model", C.c_int32), ("servers", C.c_int32), ("mapping", C.c_int32), ("variant", C.c_int32),
         ("master_seed", C.c_uint64), ("first_trial", C.c_uint64),
         ("num_trials", C.c_uint64), ("num_objects", C.c_uint64),
         ("arr_mean", C.c_void_p), ("srv_mean", C.c_void_p),

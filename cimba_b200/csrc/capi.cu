@@ -16,6 +16,7 @@
 #include "../../include/cimba_b200.h"
 #include "engine.cuh"
 #include "queue_model.cuh"
+#include "mm1_fast.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -162,8 +163,17 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const uint64_t blocks = (threads + QUEUE_BLOCK - 1) / QUEUE_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
         dim3 grid((unsigned)blocks);
-        return job->model == CIMBA_B200_MODEL_MM1 ? launch_queue<0>(qa, trace, grid, st)
-                                                  : launch_queue<1>(qa, trace, grid, st);
+        if (job->model == CIMBA_B200_MODEL_GG1) return launch_queue<1>(qa, trace, grid, st);
+        if (job->variant == 1) return launch_queue<0>(qa, trace, grid, st);
+        if (trace) {
+            mm1_kernel<true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+        }
+        else {
+            mm1_kernel<false><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+        }
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "mm1_kernel launch");
     }
     return fail(CIMBA_B200_EINVAL, "unknown model");
 }

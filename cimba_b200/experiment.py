@@ -121,7 +121,7 @@ class TrialBuffers:
 def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects: int,
                   master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
                   servers: int = 1, mapping: int = 0, buffers: Optional[TrialBuffers] = None,
-                  trace_cap: int = 0) -> TrialResults:
+                  trace_cap: int = 0, variant: int = 0) -> TrialResults:
     """Asynchronously run one trial per element of ``arr_mean`` on the current stream.
 
     Inputs are float64 CUDA tensors already resident in HBM (the device-resident
@@ -142,7 +142,7 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
     if b.n != n or b.trace_cap != trace_cap:
         raise ValueError("buffers do not match this launch")
     job = _lib.DeviceJob(
-        model=model, servers=servers, mapping=mapping,
+        model=model, servers=servers, mapping=mapping, variant=variant,
         master_seed=master_seed & (2**64 - 1), first_trial=first_trial,
         num_trials=n, num_objects=num_objects,
         arr_mean=arr_mean.data_ptr(), srv_mean=srv_mean.data_ptr(),
@@ -161,7 +161,7 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
 
 def run_trials(num_trials: int, *, arr_mean: float, srv_mean: float, num_objects: int,
                master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
-               servers: int = 1, mapping: int = 0, trace_cap: int = 0,
+               servers: int = 1, mapping: int = 0, trace_cap: int = 0, variant: int = 0,
                device: Optional[torch.device] = None) -> TrialResults:
     """Convenience: identical parameters for every trial, results after a sync."""
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -169,7 +169,7 @@ def run_trials(num_trials: int, *, arr_mean: float, srv_mean: float, num_objects
     s = torch.full((num_trials,), srv_mean, dtype=torch.float64, device=dev)
     res = launch_trials(a, s, num_objects=num_objects, master_seed=master_seed,
                         first_trial=first_trial, model=model, servers=servers,
-                        mapping=mapping, trace_cap=trace_cap)
+                        mapping=mapping, trace_cap=trace_cap, variant=variant)
     torch.cuda.synchronize(dev)
     return res
 

@@ -77,7 +77,7 @@ typedef struct cimba_b200_device_job {
     int32_t  model;             /* CIMBA_B200_MODEL_* */
     int32_t  servers;           /* pool capacity for MODEL_MMC, ignored otherwise */
     int32_t  mapping;           /* CIMBA_B200_MAP_LANE (default if 0) or _WARP */
-    int32_t  reserved;
+    int32_t  variant;           /* 0 = default kernel; 1 = the unfused formulation (queue_model.cuh), kept for A/B measurement */
     uint64_t master_seed;
     uint64_t first_trial;       /* global index of trial 0 of this job (sharding) */
     uint64_t num_trials;
