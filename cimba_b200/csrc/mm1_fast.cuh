@@ -41,6 +41,14 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     return v;
 }
 
+// Event keys carry the action in their two low bits: key = (issue counter << 2) | action.
+// Counters are unique, so ordering by this word is ordering by issue counter (the
+// reference's FIFO tie-break, src/cmi_hashheap.c:55-80) and one register holds both.
+__device__ __forceinline__ uint32_t pack_key(uint32_t counter, uint32_t action)
+{
+    return (counter << 2) | action;
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(QUEUE_BLOCK)
 mm1_kernel(const QueueArgs a)
@@ -73,13 +81,14 @@ mm1_kernel(const QueueArgs a)
     // ---- per-trial state (registers)
     Sfc64 rng;
     rng.a = rng.b = rng.c = rng.d = 0u;
-    // event slot 0 = arrival process, slot 1 = service process (SlotFel<2> spelled out)
+    // event slot 0 = arrival process, slot 1 = service process; an empty slot has
+    // time +inf and key 0 (action ACT_NONE)
     double t_arr = INF, t_srv = INF;
-    uint32_t k_arr = 0u, k_srv = 0u, a_arr = ACT_NONE, a_srv = ACT_NONE;
+    uint32_t k_arr = 0u, k_srv = 0u;
     uint32_t issued = 0u;                               // item_counter, src/cmi_hashheap.c:449-453
     double now = 0.0, stamp = 0.0, sum_wait = 0.0;
     double arr_mean = 1.0, srv_mean = 1.0;
-    uint32_t pops = 0u, produced = 0u, served = 0u, status = TRIAL_OK, longest = 0u;
+    uint32_t produced = 0u, served = 0u, status = TRIAL_OK, longest = 0u;
     uint32_t q_head = 0u, q_len = 0u;
     bool server_waiting = false;
     const uint32_t quota = (uint32_t)a.num_objects;
@@ -88,49 +97,47 @@ mm1_kernel(const QueueArgs a)
     double *const spill = (a.spill_cap && alive) ? a.spill + trial * a.spill_cap : nullptr;
     const uint32_t spill_mask = a.spill_cap - 1u;
 
+    // one variate of look-ahead: the next raw sfc64 output is drawn as soon as the
+    // previous one is consumed, so its table lookup and conversion are off the
+    // critical path of the step that uses it.  The stream order is unchanged; one
+    // unused raw draw remains when the trial ends.
+    uint64_t u_next = 0u;
+    double e_next = 0.0;                                // hot-path std exponential of u_next
+    uint32_t pops = 0u;
+
     if (alive) {
         arr_mean = a.arr_mean[trial];
         srv_mean = a.srv_mean[trial];
         rng.seed(fmix64(a.master_seed, a.first_trial + trial));
-        t_arr = 0.0; k_arr = 1u; a_arr = ACT_START;     // cmb_process_start(arrival), MM1_multi.c:107-108
-        t_srv = 0.0; k_srv = 2u; a_srv = ACT_START;     // cmb_process_start(service), :109-111
+        t_arr = 0.0; k_arr = pack_key(1u, ACT_START);   // cmb_process_start(arrival), MM1_multi.c:107-108
+        t_srv = 0.0; k_srv = pack_key(2u, ACT_START);   // cmb_process_start(service), :109-111
         issued = 2u;
+        u_next = rng.next();
+        e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
     }
 
-    bool parked = false;
-    uint64_t parked_u = 0u;
+    bool parked = false;                                // look-ahead variate needs the ziggurat slow path
     bool parked_is_arr = false;
 
     while (__any_sync(FULL, alive)) {
-        // ---------------- speculative variate: the next sfc64 output and its
-        // hot-path exponential, computed before we know whether this step draws
-        // (independent of the pop, so it overlaps it); state is committed below.
-        Sfc64 nxt = rng;
-        const uint64_t u = nxt.next();
-        const bool hot = Sfc64::exp_is_hot(u);
-        const double std_exp = __dmul_rn(lds_f64(tab + ((uint32_t)u & 0xffu) * 8u), __ull2double_rn(u));
-
         // ---------------- pop-min (cmi_hashheap_dequeue order: time asc, key asc)
         const bool go0 = alive & !parked;
         const bool first_arr = (t_arr < t_srv) | ((t_arr == t_srv) & (k_arr < k_srv));
-        const uint32_t act = first_arr ? a_arr : a_srv;
-        const bool go = go0 & (act != ACT_NONE);
-        const bool done = go0 & (act == ACT_NONE);      // event list ran dry
+        const uint32_t key = first_arr ? k_arr : k_srv;
+        const uint32_t act = key & 3u;
+        const bool go = go0 & (key != 0u);
+        const bool done = go0 & (key == 0u);            // event list ran dry
         const bool is_arr = go & first_arr;
         const bool is_srv = go & !first_arr;
         const bool wake = act == ACT_WAKE_TIME;
         if (TRACE) {
             if (go && pops < a.trace_cap) {
-                a.trace_key[trial * a.trace_cap + pops] = first_arr ? k_arr : k_srv;
+                a.trace_key[trial * a.trace_cap + pops] = key >> 2;
                 a.trace_time[trial * a.trace_cap + pops] = first_arr ? t_arr : t_srv;
             }
+            pops += go ? 1u : 0u;
         }
-        now = go ? (first_arr ? t_arr : t_srv) : now;   // src/cmb_event.c:239-241
-        pops += go ? 1u : 0u;
-        t_arr = is_arr ? INF : t_arr;
-        a_arr = is_arr ? ACT_NONE : a_arr;
-        t_srv = is_srv ? INF : t_srv;
-        a_srv = is_srv ? ACT_NONE : a_srv;
+        if (go) now = first_arr ? t_arr : t_srv;        // src/cmb_event.c:239-241
 
         // ---------------- arrival body (MM1_multi.c:58-66): back from hold -> put
         const bool put = is_arr & wake;
@@ -148,22 +155,21 @@ mm1_kernel(const QueueArgs a)
                 q_len--;                                // entry dropped
             }
         }
-        q_len += put ? 1u : 0u;
-        produced += put ? 1u : 0u;
+        if (put) { q_len++; produced++; }
         longest = max(longest, q_len);
         // cmb_objectqueue_put -> cmb_resourceguard_signal(front guard): wake the server
         const bool ring_bell = put & server_waiting;
-        issued += ring_bell ? 1u : 0u;
-        t_srv = ring_bell ? now : t_srv;
-        k_srv = ring_bell ? issued : k_srv;
-        a_srv = ring_bell ? ACT_WAKE_RESOURCE : a_srv;
-        server_waiting = server_waiting & !ring_bell;
+        if (ring_bell) {
+            issued++;
+            t_srv = now;
+            k_srv = pack_key(issued, ACT_WAKE_RESOURCE);
+            server_waiting = false;
+        }
 
         // ---------------- service body (MM1_multi.c:78-88)
         const bool finished = is_srv & wake;            // back from the service hold
         const double new_sum = __dadd_rn(sum_wait, __dsub_rn(now, stamp));
-        sum_wait = finished ? new_sum : sum_wait;
-        served += finished ? 1u : 0u;
+        if (finished) { sum_wait = new_sum; served++; }
         // cmb_objectqueue_get: take the head or wait at the front guard
         const bool take = is_srv & (q_len > 0u);
         if (take) {
@@ -172,41 +178,35 @@ mm1_kernel(const QueueArgs a)
             if (q_len > (uint32_t)QUEUE_WINDOW) {       // rare: refill the freed slot from HBM
                 sts_f64(slot, spill[(q_head + QUEUE_WINDOW) & spill_mask]);
             }
+            q_head++;
+            q_len--;
         }
-        q_head += take ? 1u : 0u;
-        q_len -= take ? 1u : 0u;
-        server_waiting = server_waiting | (is_srv & !take);
+        if (is_srv & !take) server_waiting = true;
 
-        // ---------------- hold: commit the draw, insert the wake-up
+        // ---------------- hold: consume the look-ahead variate, insert the wake-up
         const bool draw = take | (is_arr & (produced < quota));
+        const bool hot = Sfc64::exp_is_hot(u_next);
         const bool push = draw & hot;
-        const double when = __dadd_rn(now, __dmul_rn(is_arr ? arr_mean : srv_mean, std_exp));
-        rng.a = draw ? nxt.a : rng.a;
-        rng.b = draw ? nxt.b : rng.b;
-        rng.c = draw ? nxt.c : rng.c;
-        rng.d = draw ? nxt.d : rng.d;
-        issued += push ? 1u : 0u;
-        const bool push_arr = push & is_arr;
-        const bool push_srv = push & is_srv;
-        t_arr = push_arr ? when : t_arr;
-        k_arr = push_arr ? issued : k_arr;
-        a_arr = push_arr ? ACT_WAKE_TIME : a_arr;
-        t_srv = push_srv ? when : t_srv;
-        k_srv = push_srv ? issued : k_srv;
-        a_srv = push_srv ? ACT_WAKE_TIME : a_srv;
-        const bool park = draw & !hot;
-        parked = parked | park;
-        parked_u = park ? u : parked_u;
-        parked_is_arr = park ? is_arr : parked_is_arr;
+        const double when = __dadd_rn(now, __dmul_rn(is_arr ? arr_mean : srv_mean, e_next));
+        if (push) issued++;
+        const double t_new = push ? when : INF;         // the popped slot is refilled or left empty
+        const uint32_t k_new = push ? pack_key(issued, ACT_WAKE_TIME) : 0u;
+        if (is_arr) { t_arr = t_new; k_arr = k_new; }
+        if (is_srv) { t_srv = t_new; k_srv = k_new; }
+        if (draw & !hot) { parked = true; parked_is_arr = is_arr; }
+        if (push) {                                     // refill the look-ahead
+            u_next = rng.next();
+            e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
+        }
 
         // ---------------- rare paths
         if (done) {
             alive = false;
-            if (a.events)    a.events[trial] = pops;
+            if (a.events)    a.events[trial] = issued;  // every scheduled event has been popped
             if (a.objects)   a.objects[trial] = served;
             if (a.t_end)     a.t_end[trial] = now;
             if (a.sum_wait)  a.sum_wait[trial] = sum_wait;
-            if (a.status)    a.status[trial] = status | (issued > 0xfffffff0u ? TRIAL_ERR_KEY_OVERFLOW : 0u);
+            if (a.status)    a.status[trial] = status | (issued > 0x3ffffff0u ? TRIAL_ERR_KEY_OVERFLOW : 0u);
             if (a.max_queue) a.max_queue[trial] = longest;
         }
         const unsigned pm = __ballot_sync(FULL, parked);
@@ -215,12 +215,13 @@ mm1_kernel(const QueueArgs a)
             if (__popc(pm) >= COLD_BATCH || pm == am) {
                 if (parked) {
                     const double mean = parked_is_arr ? arr_mean : srv_mean;
-                    const double dur = __dmul_rn(mean, rng.exp_cold(parked_u));
-                    const double at = __dadd_rn(now, dur);
+                    const double at = __dadd_rn(now, __dmul_rn(mean, rng.exp_cold(u_next)));
                     issued++;
-                    if (parked_is_arr) { t_arr = at; k_arr = issued; a_arr = ACT_WAKE_TIME; }
-                    else               { t_srv = at; k_srv = issued; a_srv = ACT_WAKE_TIME; }
+                    if (parked_is_arr) { t_arr = at; k_arr = pack_key(issued, ACT_WAKE_TIME); }
+                    else               { t_srv = at; k_srv = pack_key(issued, ACT_WAKE_TIME); }
                     parked = false;
+                    u_next = rng.next();
+                    e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
                 }
             }
         }

@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU,
+exports every symbol include/cimba_b200.h declares, keeps the reference's struct
+layouts, and fails loudly (never falls back) when no CUDA device is present."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def declared_functions():
+    text = (ROOT / "include" / "cimba_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(cimba_b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_and_library_agree(cb):
+    from cimba_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 16
+    raw = C.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/cimba_b200.h but not exported"
+    assert set(names) == set(_lib.SYMBOLS), "python binding and header drifted apart"
+
+
+def test_struct_layouts_match_the_header(cb):
+    from cimba_b200 import _lib
+    # struct cmb_datasummary is 8 x 8 bytes (reference include/cmb_datasummary.h:42-51)
+    assert C.sizeof(_lib.DataSummaryStruct) == 64
+    assert _lib.DataSummaryStruct.count.offset == 8 and _lib.DataSummaryStruct.m1.offset == 32
+    assert C.sizeof(_lib.DeviceJob) == 4 * 4 + 4 * 8 + 8 * 8 + 2 * 8 + 3 * 8
+    assert C.sizeof(_lib.Experiment) == 4 * 4 + 3 * 8 + 8 * C.sizeof(C.c_size_t)
+    # the reference's struct trial (benchmark/MM1_multi.c:39-45) is a prefix of TRIAL_DTYPE
+    f = cb.TRIAL_DTYPE.fields
+    assert [f[k][1] for k in ("arr_mean", "srv_mean", "obj_cnt", "sum_wait", "avg_wait")] == [0, 8, 16, 24, 32]
+
+
+def test_version_and_seed_derivation(cb):
+    assert cb.__version__ == "0.1.0"
+    # cmb_random_fmix64 known answers
+    assert cb.fmix64(0x34F05C64D7AD598F, 0) == 0xA9668314774003F8
+    assert cb.fmix64(0x34F05C64D7AD598F, 1) == 0x3A4431CFB7782955
+
+
+def test_no_cpu_fallback_without_a_device(cb):
+    """On a box without CUDA every compute entry point must fail with ENODEVICE."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; this checks the GPU-less behaviour")
+    from cimba_b200 import _lib
+    assert _lib.lib.cimba_b200_device_count() == 0
+    exp = np.zeros(4, dtype=cb.TRIAL_DTYPE)
+    exp["arr_mean"], exp["srv_mean"] = 1.1, 1.0
+    with pytest.raises(cb.CimbaError) as e:
+        cb.cimba_run_experiment(exp, num_objects=10, master_seed=1)
+    assert e.value.code == _lib.ENODEVICE
+    assert not exp["obj_cnt"].any()                     # nothing was computed anywhere
+    with pytest.raises(ValueError):
+        cb.launch_trials(torch.ones(2, dtype=torch.float64), torch.ones(2, dtype=torch.float64),
+                         num_objects=1, master_seed=1)
+
+
+def test_argument_validation_mirrors_reference_asserts(cb):
+    # cimba_run_experiment asserts array != NULL, num_trials > 0, struct size > 0 (src/cimba.c:155-158)
+    with pytest.raises(ValueError):
+        cb.cimba_run_experiment(np.zeros(0, dtype=cb.TRIAL_DTYPE), num_objects=1, master_seed=1)
+    with pytest.raises(TypeError):
+        cb.cimba_run_experiment(np.zeros(3), num_objects=1, master_seed=1)
+    with pytest.raises(TypeError):
+        cb.cimba_run_experiment(np.zeros(3, dtype=[("x", "<f8")]), num_objects=1, master_seed=1)
+    from cimba_b200 import _lib
+    job = _lib.DeviceJob(num_trials=0)
+    assert _lib.lib.cimba_b200_launch(C.byref(job), None) == _lib.EINVAL
+    assert b"num_trials" in _lib.lib.cimba_b200_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """No file of the shipped package may reference oracle/ (parity would be void)."""
+    for p in list((ROOT / "cimba_b200").rglob("*.py")) + list((ROOT / "cimba_b200" / "csrc").glob("*")):
+        if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".h"}:
+            text = p.read_text()
+            code = "\n".join(l for l in text.splitlines()
+                             if not l.lstrip().startswith(("//", "/*", "*", "#", '"""')))
+            assert "oracle_libs" not in code and "liboracle" not in code and "cimba_port" not in code, p

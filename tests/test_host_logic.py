@@ -1,0 +1,103 @@
+"""CPU tests of the host-side logic: cmb_datasummary mirror (vs the reference's
+golden numbers and the oracle), and the cross-rank merge over gloo, world_size 2."""
+import ctypes as C
+import math
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_datasummary_add_matches_reference_golden(cb, golden):
+    s = golden["summary"]
+    x = [float.fromhex(v) for v in s["x"]]
+    ds = cb.DataSummary.of(x)
+    assert [float.hex(v) for v in ds.to_list()[:7]] == s["data_all"]
+    assert ds.count() == 1000 and ds.mean() == float.fromhex(s["data_all"][3])
+    assert ds.variance() == float.fromhex(s["data_all"][4]) / 999.0
+
+
+@pytest.mark.parametrize("na", [1, 333, 500, 999])
+def test_datasummary_merge_matches_reference_golden(cb, golden, na):
+    s = golden["summary"]
+    x = [float.fromhex(v) for v in s["x"]]
+    m = cb.DataSummary.merge(cb.DataSummary.of(x[:na]), cb.DataSummary.of(x[na:]))
+    assert [float.hex(v) for v in m.to_list()[:7]] == s[f"data_merge_{na}"]
+
+
+def test_merge_with_empty_side_and_roundtrip(cb):
+    a = cb.DataSummary.of([1.0, 2.0, 4.0])
+    e = cb.DataSummary()
+    for m in (cb.DataSummary.merge(a, e), cb.DataSummary.merge(e, a)):
+        assert m.to_list() == a.to_list()
+    assert cb.DataSummary.from_list(a.to_list()).to_list() == a.to_list()
+    assert math.isnan(cb.DataSummary.of([3.0]).half_width_95())
+    assert e.count() == 0 and e.variance() == 0.0
+
+
+def test_tree_merge_is_within_tolerance_of_serial_fold(cb):
+    """A merged tree differs from the reference's serial add loop by rounding only
+    (<< 1e-9 relative, the BASELINE.json tolerance)."""
+    g = np.random.default_rng(7)
+    x = g.gamma(3.0, 3.3, size=4096)
+    serial = cb.DataSummary.of(x)
+    parts = [cb.DataSummary.of(x[i::8]) for i in range(8)]
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = cb.DataSummary.merge(acc, p)
+    assert acc.count() == serial.count() and acc.min() == serial.min() and acc.max() == serial.max()
+    for a, b in zip(acc.to_list()[3:7], serial.to_list()[3:7]):
+        assert abs(a - b) <= 1e-9 * abs(b)
+
+
+def test_merge_across_ranks_without_process_group(cb):
+    import torch
+    ds = cb.DataSummary.of([1.0, 5.0, 9.0])
+    out = cb.merge_across_ranks(torch.tensor(ds.to_list(), dtype=torch.float64))
+    assert out.to_list() == ds.to_list()
+
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    import cimba_b200 as cb
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    rank = dist.get_rank()
+    x = np.random.default_rng(11).gamma(2.0, 5.0, size=2000)
+    shard = x[rank * 1000:(rank + 1) * 1000]          # contiguous blocks of the trial array, section 8e
+    local = torch.tensor(cb.DataSummary.of(shard).to_list(), dtype=torch.float64)
+    merged = cb.merge_across_ranks(local)
+    print(json.dumps({{"rank": rank, "summary": [float.hex(v) for v in merged.to_list()]}}), flush=True)
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_merge_equals_single_process_merge(cb, tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=str(ROOT), port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=180)
+        assert p.returncode == 0, e
+        outs.append(o.strip().splitlines()[-1])
+    import json
+    got = [json.loads(o)["summary"] for o in outs]
+    assert got[0] == got[1]                          # every rank ends with the same merged summary
+    x = np.random.default_rng(11).gamma(2.0, 5.0, size=2000)
+    want = cb.DataSummary.merge(cb.DataSummary.of(x[:1000]), cb.DataSummary.of(x[1000:]))
+    assert got[0] == [float.hex(v) for v in want.to_list()]
+    serial = cb.DataSummary.of(x)
+    assert abs(want.mean() - serial.mean()) <= 1e-12 * abs(serial.mean())
