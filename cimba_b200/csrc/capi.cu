@@ -17,6 +17,7 @@
 #include "engine.cuh"
 #include "queue_model.cuh"
 #include "mm1_fast.cuh"
+#include "pool_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -115,7 +116,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (job == nullptr) {
         return 0u;
     }
-    if (is_queue_model(job->model)) {
+    if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
     return 0u;
@@ -174,6 +175,42 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "mm1_kernel launch");
+    }
+    if (job->model == CIMBA_B200_MODEL_MMC) {
+        if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1 for CIMBA_B200_MODEL_MMC");
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_MMC supports CIMBA_B200_MAP_LANE only");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        PoolArgs pa{};
+        pa.servers = job->servers;
+        pa.master_seed = job->master_seed;
+        pa.first_trial = job->first_trial;
+        pa.num_trials = job->num_trials;
+        pa.num_objects = job->num_objects;
+        pa.arr_mean = job->arr_mean;
+        pa.srv_mean = job->srv_mean;
+        pa.events = job->events;
+        pa.objects = job->objects;
+        pa.t_end = job->t_end;
+        pa.sum_wait = job->sum_wait;
+        pa.status = job->status;
+        pa.max_queue = job->max_queue;
+        pa.spill = (double *)job->workspace;
+        pa.spill_cap = QUEUE_SPILL_CAP;
+        pa.trace_cap = job->trace_cap;
+        pa.trace_key = job->trace_key;
+        pa.trace_time = job->trace_time;
+        const uint64_t blocks = (job->num_trials + POOL_BLOCK - 1) / POOL_BLOCK;
+        if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
+        if (trace) {
+            pool_kernel<true><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+        }
+        else {
+            pool_kernel<false><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+        }
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
     }
     return fail(CIMBA_B200_EINVAL, "unknown model");
 }

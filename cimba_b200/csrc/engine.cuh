@@ -205,3 +205,98 @@ struct StampRing {
 };
 
 }  // namespace cimba_b200
+
+namespace cimba_b200 {
+
+// ---------------------------------------------------------------------------
+// EventList<CAP>: general future-event list for lane-per-trial models whose
+// processes come and go (any number of pending events per process, up to CAP in
+// total).  The reference keeps a binary heap of 64-byte tags
+// (src/cmi_hashheap.c); with the 5-12 live entries of the pooled-server models
+// an unsorted array with a full scan per pop is cheaper on a SIMT machine: the
+// scan is a fixed instruction sequence that all lanes of a warp execute
+// together (sift loops would diverge per lane), inserts are O(1), and removal
+// moves the last entry into the hole.  Pop order is the reference's total order
+// (time asc, key asc at equal priority), which is all that parity needs.
+//
+// Layout: shared memory, one column per thread; entry i of thread tid is the
+// 16-byte record head[i * stride + tid] = {time, (key << 2 | action), tag} plus
+// an 8-byte payload pay[i * stride + tid] (the process-local state that travels
+// with the continuation, e.g. a customer's arrival time).  16-byte accesses at a
+// 16-byte lane pitch are conflict-free whatever row each lane addresses.
+// ---------------------------------------------------------------------------
+struct __align__(16) EventHead {
+    double   time;
+    uint32_t keyact;           // (issue key << 2) | action ; 0 = none
+    uint32_t tag;              // model-defined (process kind / id)
+};
+
+template <int CAP>
+struct EventList {
+    EventHead *head;           // shared memory, already offset by threadIdx.x
+    double    *pay;
+    uint32_t   stride;
+    uint32_t   count;
+    uint32_t   issued;         // item_counter, src/cmi_hashheap.c:449-453
+
+    __device__ __forceinline__ void init(EventHead *h, double *p, uint32_t s)
+    {
+        head = h;
+        pay = p;
+        stride = s;
+        count = 0u;
+        issued = 0u;
+    }
+
+    // cmb_event_schedule: false if the list is full (entry dropped; flag the trial)
+    __device__ __forceinline__ bool schedule(uint32_t action, uint32_t tag, double time, double payload)
+    {
+        const uint32_t k = ++issued;
+        if (count >= (uint32_t)CAP) {
+            return false;
+        }
+        EventHead e;
+        e.time = time;
+        e.keyact = (k << 2) | action;
+        e.tag = tag;
+        head[count * stride] = e;
+        pay[count * stride] = payload;
+        count++;
+        return true;
+    }
+
+    // Pop the first entry under (time asc, key asc).  `scan` = number of rows to
+    // look at; pass the warp-wide maximum of `count` so the loop trip count is
+    // uniform.  Returns false if this lane's list is empty.
+    __device__ __forceinline__ bool pop(uint32_t scan, EventHead &out, double &payload)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        double bt = INF;
+        uint32_t bk = 0xffffffffu, bi = 0u, btag = 0u;
+        for (uint32_t i = 0u; i < scan; i++) {
+            if (i < count) {
+                const EventHead e = head[i * stride];
+                const bool before = (e.time < bt) | ((e.time == bt) & (e.keyact < bk));
+                bt = before ? e.time : bt;
+                bk = before ? e.keyact : bk;
+                btag = before ? e.tag : btag;
+                bi = before ? i : bi;
+            }
+        }
+        if (count == 0u) {
+            return false;
+        }
+        out.time = bt;
+        out.keyact = bk;
+        out.tag = btag;
+        payload = pay[bi * stride];
+        count--;
+        if (bi != count) {                              // move the last entry into the hole
+            head[bi * stride] = head[count * stride];
+            pay[bi * stride] = pay[count * stride];
+        }
+        return true;
+    }
+};
+
+}  // namespace cimba_b200
