@@ -9,7 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcimba_b200.so"
+import os
+
+# CIMBA_B200_LIB selects an alternative build of the same library (tuning sweeps)
+LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
+                Path(__file__).resolve().parent / "lib" / "libcimba_b200.so")
 
 NO_FIELD = C.c_size_t(-1).value
 

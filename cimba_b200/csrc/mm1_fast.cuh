@@ -26,6 +26,14 @@
 
 namespace cimba_b200 {
 
+// tuning knobs (measured on B200, profiles/r01_mm1.md)
+#ifndef MM1_PARK_MASK
+#define MM1_PARK_MASK 7u      // the parked set is examined every 8th step
+#endif
+#ifndef MM1_COLD_BATCH
+#define MM1_COLD_BATCH 4       // parked lanes needed before the ziggurat slow path runs
+#endif
+
 // 32-bit shared-window accesses: one address register, no generic->shared
 // conversion per access (the static-__shared__ form costs five extra
 // instructions each time on sm_100a).
@@ -88,12 +96,15 @@ mm1_kernel(const QueueArgs a)
     uint32_t issued = 0u;                               // item_counter, src/cmi_hashheap.c:449-453
     double now = 0.0, stamp = 0.0, sum_wait = 0.0;
     double arr_mean = 1.0, srv_mean = 1.0;
-    uint32_t produced = 0u, served = 0u, status = TRIAL_OK, longest = 0u;
-    uint32_t q_head = 0u, q_len = 0u;
-    bool server_waiting = false;
+    // FIFO discipline: the k-th object put is the k-th object taken, so the ring's
+    // tail index is `produced`, its head index is `served`, its length their difference.
+    // The server is waiting at the front guard exactly when its event slot is empty
+    // at the moment an arrival puts (it otherwise always owns one pending event).
+    uint32_t produced = 0u, served = 0u, dropped = 0u, status = TRIAL_OK, longest = 0u;
     const uint32_t quota = (uint32_t)a.num_objects;
-    const uint32_t win = (uint32_t)__cvta_generic_to_shared(&ring_smem[threadIdx.x]);
-    const uint32_t tab = (uint32_t)__cvta_generic_to_shared(&exp_x[0]);
+    uint32_t win = (uint32_t)__cvta_generic_to_shared(&ring_smem[threadIdx.x]);
+    uint32_t tab = (uint32_t)__cvta_generic_to_shared(&exp_x[0]);
+    asm volatile("" : "+r"(win), "+r"(tab));            // keep both in registers (no per-step rematerialisation)
     double *const spill = (a.spill_cap && alive) ? a.spill + trial * a.spill_cap : nullptr;
     const uint32_t spill_mask = a.spill_cap - 1u;
 
@@ -117,6 +128,7 @@ mm1_kernel(const QueueArgs a)
     }
 
     bool parked = false;                                // look-ahead variate needs the ziggurat slow path
+    uint32_t step = 0u;
     bool parked_is_arr = false;
 
     while (__any_sync(FULL, alive)) {
@@ -140,48 +152,46 @@ mm1_kernel(const QueueArgs a)
         if (go) now = first_arr ? t_arr : t_srv;        // src/cmb_event.c:239-241
 
         // ---------------- arrival body (MM1_multi.c:58-66): back from hold -> put
+        const uint32_t q_len = produced - served;
         const bool put = is_arr & wake;
         const bool put_far = put & (q_len >= (uint32_t)QUEUE_WINDOW);
         if (put & !put_far) {
-            sts_f64(win + ((q_head + q_len) & WMASK) * ROW, now);
+            sts_f64(win + (produced & WMASK) * ROW, now);
         }
         if (put_far) {                                  // rare: beyond the on-chip window
-            const uint32_t pos = q_head + q_len;
             if (spill != nullptr && q_len - QUEUE_WINDOW <= spill_mask) {
-                spill[pos & spill_mask] = now;
+                spill[produced & spill_mask] = now;
             }
             else {
-                status |= TRIAL_ERR_QUEUE_OVERFLOW;
-                q_len--;                                // entry dropped
+                status |= TRIAL_ERR_QUEUE_OVERFLOW;     // entry dropped: the trial is void from here on
+                dropped++;
+                served++;                               // keep produced - served = entries actually stored
             }
         }
-        if (put) { q_len++; produced++; }
-        longest = max(longest, q_len);
+        if (put) produced++;
+        longest = max(longest, produced - served);
         // cmb_objectqueue_put -> cmb_resourceguard_signal(front guard): wake the server
-        const bool ring_bell = put & server_waiting;
+        const bool ring_bell = put & (k_srv == 0u);
         if (ring_bell) {
             issued++;
             t_srv = now;
             k_srv = pack_key(issued, ACT_WAKE_RESOURCE);
-            server_waiting = false;
         }
 
         // ---------------- service body (MM1_multi.c:78-88)
         const bool finished = is_srv & wake;            // back from the service hold
         const double new_sum = __dadd_rn(sum_wait, __dsub_rn(now, stamp));
-        if (finished) { sum_wait = new_sum; served++; }
-        // cmb_objectqueue_get: take the head or wait at the front guard
-        const bool take = is_srv & (q_len > 0u);
+        if (finished) sum_wait = new_sum;
+        // cmb_objectqueue_get: take the head, or wait at the front guard (slot stays empty)
+        const bool take = is_srv & (produced != served);
         if (take) {
-            const uint32_t slot = win + (q_head & WMASK) * ROW;
+            const uint32_t slot = win + (served & WMASK) * ROW;
             stamp = lds_f64(slot);
-            if (q_len > (uint32_t)QUEUE_WINDOW) {       // rare: refill the freed slot from HBM
-                sts_f64(slot, spill[(q_head + QUEUE_WINDOW) & spill_mask]);
+            if (produced - served > (uint32_t)QUEUE_WINDOW) {   // rare: refill the freed slot from HBM
+                sts_f64(slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
             }
-            q_head++;
-            q_len--;
+            served++;
         }
-        if (is_srv & !take) server_waiting = true;
 
         // ---------------- hold: consume the look-ahead variate, insert the wake-up
         const bool draw = take | (is_arr & (produced < quota));
@@ -203,16 +213,19 @@ mm1_kernel(const QueueArgs a)
         if (done) {
             alive = false;
             if (a.events)    a.events[trial] = issued;  // every scheduled event has been popped
-            if (a.objects)   a.objects[trial] = served;
+            if (a.objects)   a.objects[trial] = served - dropped;
             if (a.t_end)     a.t_end[trial] = now;
             if (a.sum_wait)  a.sum_wait[trial] = sum_wait;
             if (a.status)    a.status[trial] = status | (issued > 0x3ffffff0u ? TRIAL_ERR_KEY_OVERFLOW : 0u);
             if (a.max_queue) a.max_queue[trial] = longest;
         }
+        if ((++step & MM1_PARK_MASK) != 0u) {
+            continue;                                   // look at the parked set every (MM1_PARK_MASK+1)-th step only
+        }
         const unsigned pm = __ballot_sync(FULL, parked);
         if (pm != 0u) {
             const unsigned am = __ballot_sync(FULL, alive);
-            if (__popc(pm) >= COLD_BATCH || pm == am) {
+            if (__popc(pm) >= MM1_COLD_BATCH || pm == am) {
                 if (parked) {
                     const double mean = parked_is_arr ? arr_mean : srv_mean;
                     const double at = __dadd_rn(now, __dmul_rn(mean, rng.exp_cold(u_next)));
