@@ -57,6 +57,16 @@ def parse_args():
     return p.parse_args()
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the timed kernel from the committed ncu capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None if absent."""
+    f = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(f.read_text())
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -283,10 +293,21 @@ def main():
     kernel_s = sum(kernel_ms) / len(kernel_ms) * 1e-3
     ach = events_rank * BYTES_PER_EVENT / kernel_s / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "queue_kernel<MM1>",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "mm1_kernel" if args.variant == 0 else "queue_kernel<0>",
                 "kernel_ms": kernel_s * 1e3, "algorithmic_bytes_per_event": BYTES_PER_EVENT,
                 "achieved_reference_layout_gbs": events_rank * BYTES_PER_EVENT_REFLAYOUT / kernel_s / 1e9,
                 "note": "per-trial state is on-chip by design; actual HBM traffic is ~0, see DESIGN.md"}
+
+    tr = measured_traffic()
+    if tr and args.variant == 0 and args.mapping == 1:
+        # scale the captured launch to this launch by its event count (traffic is parameters +
+        # results + the ~3 % of queue entries that spill: all proportional to trials x objects)
+        roofline["traffic"] = tr["dram_bytes_per_event"] * events_rank
+        roofline["traffic_source"] = tr["source"]
+    roofline["sm_issue"] = {"note": "binding limit (see DESIGN.md section 5)",
+                            "warp_instructions_per_event_step": tr.get("warp_instructions_per_step") if tr else None,
+                            "issue_slots_busy": tr.get("issue_slots_busy") if tr else None}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
