@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
 
 NO_FIELD = C.c_size_t(-1).value
 
-MODEL_MM1, MODEL_GG1, MODEL_MMC = 0, 1, 2
+MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED = 0, 1, 2, 3
 MAP_LANE, MAP_WARP = 1, 32
 
 OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -32,7 +32,7 @@ class DeviceJob(C.Structure):
         ("arr_mean", C.c_void_p), ("srv_mean", C.c_void_p),
         ("events", C.c_void_p), ("objects", C.c_void_p),
         ("t_end", C.c_void_p), ("sum_wait", C.c_void_p),
-        ("status", C.c_void_p), ("max_queue", C.c_void_p),
+        ("status", C.c_void_p), ("max_queue", C.c_void_p), ("counters", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("trace_cap", C.c_uint64), ("trace_key", C.c_void_p), ("trace_time", C.c_void_p),
     ]

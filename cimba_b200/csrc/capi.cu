@@ -18,6 +18,7 @@
 #include "queue_model.cuh"
 #include "mm1_fast.cuh"
 #include "pool_model.cuh"
+#include "guarded_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -119,6 +120,9 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
+    if (job->model == CIMBA_B200_MODEL_GUARDED) {
+        return job->num_trials * (uint64_t)sizeof(GeneralState);
+    }
     return 0u;
 }
 
@@ -211,6 +215,43 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
+    }
+    if (job->model == CIMBA_B200_MODEL_GUARDED) {
+        if (job->servers < 1 || job->servers > 16)
+            return fail(CIMBA_B200_EINVAL, "queue capacity (servers) must be in 1..16 for CIMBA_B200_MODEL_GUARDED");
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        GuardedArgs ga{};
+        ga.capacity = job->servers;
+        ga.master_seed = job->master_seed;
+        ga.first_trial = job->first_trial;
+        ga.num_trials = job->num_trials;
+        ga.duration = job->num_objects;
+        ga.put_mean = job->arr_mean;
+        ga.get_mean = job->srv_mean;
+        ga.events = job->events;
+        ga.objects = job->objects;
+        ga.t_end = job->t_end;
+        ga.sum_wait = job->sum_wait;
+        ga.status = job->status;
+        ga.max_queue = job->max_queue;
+        ga.counters = job->counters;
+        ga.state = (GeneralState *)job->workspace;
+        ga.trace_cap = job->trace_cap;
+        ga.trace_key = job->trace_key;
+        ga.trace_time = job->trace_time;
+        const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
+        if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
+        if (trace) {
+            guarded_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        else {
+            guarded_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "guarded_kernel launch");
     }
     return fail(CIMBA_B200_EINVAL, "unknown model");
 }

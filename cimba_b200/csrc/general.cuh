@@ -1,0 +1,369 @@
+// general.cuh - the general (cancel / interrupt / stop / priority) half of the
+// simulation kernel, device side, for models that need more than "every process
+// owns one pending event".
+//
+// Reference pieces restated here:
+//   cmi_hashheap        src/cmi_hashheap.c:277-370 (sift loops), :428-478 (enqueue),
+//                       :486-524 (dequeue), :529-579 (remove by key)
+//   cmb_event           src/cmb_event.c:123-140 (schedule), :285-302 (cancel),
+//                       :385-425 (pattern cancel by subject)
+//   cmb_process         src/cmb_process.c:220-260 (awaitables), :262-285 + 316-349
+//                       (hold and its interrupted branch), :581-620 (cancel awaiteds),
+//                       :628-666 (interrupt), :698-723 (stop)
+//   cmb_resourceguard   src/cmb_resourceguard.c:71-90 (order), :125-163 (wait),
+//                       :202-226 (signal), :270-290 (remove)
+//
+// Unlike the event-order-only containers in engine.cuh, the heaps here keep the
+// reference's physical layout (1-based binary heap, slot 0 = last popped, same
+// sift and remove steps).  That matters for the guard wait lists: their
+// comparator is not a strict weak order when priorities differ (SURVEY.md quirk
+// 1), so which waiter reaches the head depends on the exact sequence of swaps.
+//
+// Storage: one GeneralState per trial in HBM (lane per trial, L1/L2-cached).
+// This path is about coverage and bit parity, not peak throughput.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "engine.cuh"
+#include "rng.cuh"
+
+namespace cimba_b200 {
+
+enum : uint32_t { ACT_WAKE_INTERRUPT = 4u, ACT_USER = 5u };
+enum : uint32_t { AWAIT_TIME = 0u, AWAIT_RESOURCE = 1u };
+enum : uint32_t { PROC_CREATED = 0u, PROC_RUNNING = 1u, PROC_FINISHED = 2u };
+
+struct HeapTag {                // cmi_heap_tag (src/cmi_hashheap.h:53-59) packed to 24 bytes
+    double   d;                 // rank_d64: event time / guard entry time
+    uint32_t key;               // hash_key
+    int32_t  prio;              // rank_i64
+    uint16_t act;               // item[0]: action id
+    uint16_t subj;              // item[1]: process index (0xffff = the model itself)
+    int32_t  arg;               // item[2]: signal
+};
+
+// default_compare, src/cmi_hashheap.c:55-80
+struct EventOrder {
+    static __device__ __forceinline__ bool before(const HeapTag &a, const HeapTag &b)
+    {
+        if (a.d < b.d) return true;
+        if (a.d > b.d) return false;
+        if (a.prio > b.prio) return true;
+        if (a.prio < b.prio) return false;
+        return a.key < b.key;
+    }
+};
+
+// guard_queue_check, src/cmb_resourceguard.c:71-90 - INCLUDING the fall-through when
+// a has the lower priority
+struct GuardOrder {
+    static __device__ __forceinline__ bool before(const HeapTag &a, const HeapTag &b)
+    {
+        if (a.prio > b.prio) return true;
+        if (a.d < b.d) return true;
+        if (a.key < b.key) return true;
+        return false;
+    }
+};
+
+template <int CAP, class Order>
+struct BinHeap {
+    HeapTag  slot[CAP + 1];     // 1-based; slot[0] = last popped
+    uint32_t count;
+    uint32_t issued;            // item_counter
+
+    __device__ void clear()
+    {
+        count = 0u;
+        issued = 0u;
+    }
+
+    __device__ void sift_up(uint32_t k)                 // heap_up, :277-316
+    {
+        const HeapTag moving = slot[k];
+        uint32_t parent;
+        while ((parent = (k >> 1)) > 0u) {
+            if (!Order::before(moving, slot[parent])) {
+                break;
+            }
+            slot[k] = slot[parent];
+            k = parent;
+        }
+        slot[k] = moving;
+    }
+
+    __device__ void sift_down(uint32_t k)               // heap_down, :321-370
+    {
+        const HeapTag moving = slot[k];
+        const uint32_t last_parent = count >> 1;
+        while (k <= last_parent) {
+            uint32_t child = k << 1;
+            if (child + 1u <= count && Order::before(slot[child + 1u], slot[child])) {
+                child++;
+            }
+            if (Order::before(moving, slot[child])) {
+                break;
+            }
+            slot[k] = slot[child];
+            k = child;
+        }
+        slot[k] = moving;
+    }
+
+    // cmi_hashheap_enqueue; key 0 = issue the next one.  Returns 0 on overflow.
+    __device__ uint32_t push(uint32_t key, double d, int32_t prio, uint32_t act, uint32_t subj, int32_t arg)
+    {
+        issued += 1u;
+        if (key == 0u) {
+            key = issued;
+        }
+        if (count >= (uint32_t)CAP) {
+            return 0u;
+        }
+        const uint32_t at = ++count;
+        HeapTag t;
+        t.d = d;
+        t.key = key;
+        t.prio = prio;
+        t.act = (uint16_t)act;
+        t.subj = (uint16_t)subj;
+        t.arg = arg;
+        slot[at] = t;
+        sift_up(at);
+        return key;
+    }
+
+    __device__ bool pop()                               // cmi_hashheap_dequeue
+    {
+        if (count == 0u) {
+            return false;
+        }
+        slot[0] = slot[1];
+        if (count > 1u) {
+            slot[1] = slot[count];
+            count--;
+            if (count > 1u) {
+                sift_down(1u);
+            }
+        }
+        else {
+            count = 0u;
+        }
+        return true;
+    }
+
+    __device__ bool remove(uint32_t key)                // cmi_hashheap_remove (lookup by scan)
+    {
+        uint32_t at = 0u;
+        for (uint32_t k = 1u; k <= count; k++) {
+            if (slot[k].key == key) {
+                at = k;
+                break;
+            }
+        }
+        if (at == 0u) {
+            return false;
+        }
+        if (at == count) {
+            count--;
+            return true;
+        }
+        const bool down = Order::before(slot[at], slot[count]);
+        slot[at] = slot[count];
+        count--;
+        if (down) {
+            sift_down(at);
+        }
+        else {
+            sift_up(at);
+        }
+        return true;
+    }
+};
+
+constexpr int GEN_FEL_CAP = 31;
+constexpr int GEN_GUARD_CAP = 15;
+constexpr int GEN_MAX_PROCS = 8;
+constexpr int GEN_MAX_AWAITS = 4;
+
+using EventHeap = BinHeap<GEN_FEL_CAP, EventOrder>;
+using GuardHeap = BinHeap<GEN_GUARD_CAP, GuardOrder>;
+
+struct GenProc {                // struct cmb_process (include/cmb_process.h:116-123), the parts that act
+    uint32_t pc, status, kind;
+    int32_t  prio;
+    uint32_t n_awaits;
+    uint32_t await_type[GEN_MAX_AWAITS];    // most recent first (cmi_slist push-front)
+    uint32_t await_ref[GEN_MAX_AWAITS];     // event handle or guard index
+    uint32_t hold_handle, guard_key;
+    double   stamp;
+};
+
+struct GeneralState {
+    EventHeap fel;
+    GuardHeap guard[2];         // 0 = front (getters wait here), 1 = rear (putters)
+    GenProc   proc[GEN_MAX_PROCS];
+    double    ring[16];
+    uint32_t  ring_cap, ring_head, ring_len;
+    uint32_t  guard_seq;        // enqueue_seq, src/cmb_resourceguard.c:64
+    uint32_t  status;
+};
+
+struct GeneralSim {
+    GeneralState *st;
+    Sfc64 rng;
+    double now;
+    const ZigHot *hot;
+
+    // ---- awaitables (src/cmb_process.c:220-260)
+    __device__ void await_push(GenProc &p, uint32_t type, uint32_t ref)
+    {
+        if (p.n_awaits >= (uint32_t)GEN_MAX_AWAITS) {
+            st->status |= TRIAL_ERR_PROC_OVERFLOW;
+            return;
+        }
+        for (uint32_t k = p.n_awaits; k > 0u; k--) {
+            p.await_type[k] = p.await_type[k - 1u];
+            p.await_ref[k] = p.await_ref[k - 1u];
+        }
+        p.await_type[0] = type;
+        p.await_ref[0] = ref;
+        p.n_awaits++;
+    }
+
+    __device__ bool await_remove(GenProc &p, uint32_t type, uint32_t ref)
+    {
+        for (uint32_t k = 0u; k < p.n_awaits; k++) {
+            if (p.await_type[k] == type && p.await_ref[k] == ref) {
+                for (uint32_t m = k; m + 1u < p.n_awaits; m++) {
+                    p.await_type[m] = p.await_type[m + 1u];
+                    p.await_ref[m] = p.await_ref[m + 1u];
+                }
+                p.n_awaits--;
+                return true;
+            }
+        }
+        return false;
+    }
+
+    // ---- events
+    __device__ uint32_t schedule(uint32_t act, uint32_t subj, int32_t arg, double t, int32_t prio)
+    {
+        const uint32_t key = st->fel.push(0u, t, prio, act, subj, arg);
+        if (key == 0u) {
+            st->status |= TRIAL_ERR_FEL_OVERFLOW;
+        }
+        return key;
+    }
+
+    __device__ bool event_cancel(uint32_t handle)       // src/cmb_event.c:285-302
+    {
+        return st->fel.remove(handle);
+    }
+
+    __device__ void cancel_events_of(uint32_t subj)     // cmb_event_pattern_cancel(ANY, subj, ANY)
+    {
+        uint32_t hit[GEN_FEL_CAP];
+        uint32_t n = 0u;
+        for (uint32_t k = 1u; k <= st->fel.count; k++) {        // first pass, array order
+            if (st->fel.slot[k].subj == subj) {
+                hit[n++] = st->fel.slot[k].key;
+            }
+        }
+        for (uint32_t k = 0u; k < n; k++) {                     // second pass
+            event_cancel(hit[k]);
+        }
+    }
+
+    // ---- process layer
+    __device__ void cancel_awaiteds(uint32_t pid)       // src/cmb_process.c:581-620
+    {
+        GenProc &p = st->proc[pid];
+        while (p.n_awaits > 0u) {
+            const uint32_t type = p.await_type[0];
+            const uint32_t ref = p.await_ref[0];
+            for (uint32_t m = 0u; m + 1u < p.n_awaits; m++) {
+                p.await_type[m] = p.await_type[m + 1u];
+                p.await_ref[m] = p.await_ref[m + 1u];
+            }
+            p.n_awaits--;
+            if (type == AWAIT_TIME) {
+                (void)event_cancel(ref);
+            }
+            // AWAIT_RESOURCE: cmb_resourceguard_remove(guard, process) searches for a key
+            // equal to the process ADDRESS; entries are keyed by sequence number, so it
+            // never finds one.  Nothing to do - the waiter removes its
+            // own entry with the right key when it resumes (wait_end).
+        }
+        cancel_events_of(pid);
+    }
+
+    __device__ void hold_begin(uint32_t pid, double dur)        // :262-273, 316-333
+    {
+        GenProc &p = st->proc[pid];
+        if (dur < 0.0) {
+            st->status |= TRIAL_ERR_NEGATIVE_HOLD;
+        }
+        p.hold_handle = schedule(ACT_WAKE_TIME, pid, (int32_t)SIG_SUCCESS, __dadd_rn(now, dur), p.prio);
+        await_push(p, AWAIT_TIME, p.hold_handle);
+    }
+
+    __device__ int32_t hold_end(uint32_t pid, int32_t sig)      // :274-284, 338-349
+    {
+        GenProc &p = st->proc[pid];
+        if (sig != (int32_t)SIG_SUCCESS) {
+            (void)await_remove(p, AWAIT_TIME, p.hold_handle);
+            (void)event_cancel(p.hold_handle);
+        }
+        return sig;
+    }
+
+    __device__ void wait_begin(uint32_t g, uint32_t pid)        // src/cmb_resourceguard.c:125-152
+    {
+        GenProc &p = st->proc[pid];
+        p.guard_key = ++st->guard_seq;
+        if (st->guard[g].push(p.guard_key, now, p.prio, 0u, pid, 0) == 0u) {
+            st->status |= TRIAL_ERR_GUARD_OVERFLOW;
+        }
+        await_push(p, AWAIT_RESOURCE, g);
+    }
+
+    __device__ int32_t wait_end(uint32_t g, uint32_t pid, int32_t sig)      // :153-162
+    {
+        GenProc &p = st->proc[pid];
+        if (sig != (int32_t)SIG_SUCCESS) {
+            (void)st->guard[g].remove(p.guard_key);
+        }
+        (void)await_remove(p, AWAIT_RESOURCE, g);
+        return sig;
+    }
+
+    __device__ void signal(uint32_t g, bool demand_holds)       // :202-226
+    {
+        GuardHeap &h = st->guard[g];
+        if (h.count > 0u && demand_holds) {
+            const uint32_t pid = h.slot[1].subj;
+            h.pop();
+            schedule(ACT_WAKE_RESOURCE, pid, (int32_t)SIG_SUCCESS, now, st->proc[pid].prio);
+        }
+    }
+
+    __device__ void interrupt(uint32_t pid, int32_t sig, int32_t pri)       // src/cmb_process.c:653-666
+    {
+        schedule(ACT_WAKE_INTERRUPT, pid, sig, now, pri);
+    }
+
+    __device__ void stop(uint32_t pid)                          // :698-723
+    {
+        GenProc &p = st->proc[pid];
+        if (p.status != PROC_RUNNING) {
+            return;
+        }
+        p.status = PROC_FINISHED;
+        cancel_awaiteds(pid);
+    }
+};
+
+}  // namespace cimba_b200

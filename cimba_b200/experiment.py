@@ -82,6 +82,7 @@ class TrialResults:
     sum_wait: torch.Tensor
     status: torch.Tensor
     max_queue: torch.Tensor
+    counters: torch.Tensor    # [n, 8] model counters (MODEL_GUARDED)
     trace_key: Optional[torch.Tensor] = None
     trace_time: Optional[torch.Tensor] = None
 
@@ -103,6 +104,7 @@ class TrialBuffers:
         self.sum_wait = torch.zeros(n, dtype=torch.float64, device=device)
         self.status = torch.zeros(n, dtype=torch.int32, device=device)
         self.max_queue = torch.zeros(n, dtype=torch.int32, device=device)
+        self.counters = torch.zeros((n, 8), dtype=torch.int64, device=device)
         self.trace_cap = trace_cap
         self.trace_key = self.trace_time = None
         if trace_cap:
@@ -115,7 +117,7 @@ class TrialBuffers:
 
     def results(self) -> TrialResults:
         return TrialResults(self.events, self.objects, self.t_end, self.sum_wait,
-                            self.status, self.max_queue, self.trace_key, self.trace_time)
+                            self.status, self.max_queue, self.counters, self.trace_key, self.trace_time)
 
 
 def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects: int,
@@ -148,7 +150,7 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
         arr_mean=arr_mean.data_ptr(), srv_mean=srv_mean.data_ptr(),
         events=b.events.data_ptr(), objects=b.objects.data_ptr(),
         t_end=b.t_end.data_ptr(), sum_wait=b.sum_wait.data_ptr(),
-        status=b.status.data_ptr(), max_queue=b.max_queue.data_ptr(),
+        status=b.status.data_ptr(), max_queue=b.max_queue.data_ptr(), counters=b.counters.data_ptr(),
         workspace=b.workspace.data_ptr(), workspace_bytes=b.workspace_bytes,
         trace_cap=trace_cap,
         trace_key=b.trace_key.data_ptr() if trace_cap else None,

@@ -43,6 +43,9 @@ extern "C" {
 #define CIMBA_B200_MODEL_MM1 0   /* benchmark/MM1_multi.c:52-89: exp arrivals, exp service, cmb_objectqueue */
 #define CIMBA_B200_MODEL_GG1 1   /* same structure: cmb_random_erlang(2, m/2) arrivals, normal(m, m/4) service redrawn while < 0 */
 #define CIMBA_B200_MODEL_MMC 2   /* generator + one process per customer contending for a cmb_resourcepool of `servers` units */
+#define CIMBA_B200_MODEL_GUARDED 3 /* test/test_objectqueue.c: 3 putters + 3 getters with random priorities on a BOUNDED
+                                    * cmb_objectqueue (capacity = `servers` <= 16), a nuisance process interrupting them,
+                                    * an end event at t = num_objects stopping everybody (general cancel/interrupt path) */
 
 /* Error codes */
 #define CIMBA_B200_OK         0
@@ -91,7 +94,9 @@ typedef struct cimba_b200_device_job {
     double   *t_end;            /* cmb_time() when the event list ran dry */
     double   *sum_wait;         /* struct trial.sum_wait */
     uint32_t *status;           /* CIMBA_B200_TRIAL_* bits */
-    uint32_t *max_queue;        /* diagnostic: longest queue seen */
+    uint32_t *max_queue;        /* diagnostic: longest queue seen (MODEL_MMC: most customers alive; MODEL_GUARDED: deepest event list) */
+    uint64_t *counters;         /* [num_trials][8] model counters (MODEL_GUARDED: puts, gets, interrupted holds/puts/gets,
+                                 * sum of signals, final queue length, interrupts issued); may be NULL */
     /* scratch in HBM for queue/wait-list spill; size from cimba_b200_workspace_bytes() */
     void     *workspace;
     uint64_t  workspace_bytes;

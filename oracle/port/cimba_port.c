@@ -1075,6 +1075,352 @@ static void run_one(int model, int servers, uint64_t seed, uint64_t num_objects,
     heap_free(&s.fel);
 }
 
+/* ===================================================== general kernel (model 3)
+ *
+ * The interrupt / cancel / stop half of the reference's process layer, restated:
+ * awaitable lists (src/cmb_process.c:220-260), cmb_process_hold with its
+ * interrupted branch (:262-285), cmb_process_interrupt and its wake-up event
+ * (:628-666), cmi_process_cancel_awaiteds (:581-620), cmb_process_stop
+ * (:698-723), cmb_event_cancel / cmb_event_pattern_cancel (src/cmb_event.c:285-302,
+ * 385-425), cmb_resourceguard_wait with its self-cancel (src/cmb_resourceguard.c:
+ * 125-163), cmb_resourceguard_remove keyed by process address (:270-290, never
+ * hits: SURVEY.md quirk 2), the bounded cmb_objectqueue with both guards
+ * (src/cmb_objectqueue.c:203-314) and event/guard ordering under unequal
+ * priorities (quirk 1).  Workload: oracle/ref_build/ref_driver.c model 3.
+ */
+enum { ACT_WAKE_INTERRUPT = 4, ACT_USER_END = 5 };
+enum { AW_TIME = 0, AW_RESOURCE = 1 };
+#define G_WORKERS 6
+#define G_NPUT 3
+
+struct gsim;
+typedef struct gproc {
+    int       pc, status, id, kind;     /* kind: 0 putter, 1 getter, 2 nuisance */
+    int64_t   prio;
+    /* awaits list, most recent first (cmi_slist push-front) */
+    struct { int type; uint64_t handle; void *ptr; } awaits[8];
+    int       n_awaits;
+    uint64_t  hold_handle, guard_key;
+    double    stamp;
+} gproc;
+
+typedef struct gsim {
+    port_rng rng;
+    double   now;
+    heap     fel;
+    uint64_t guard_seq;
+    uint64_t current_key;               /* cmb_event_current() */
+    heap     front, rear;               /* the queue's two guards */
+    double  *ring;
+    uint64_t cap, head, len;
+    double   put_mean, get_mean;
+    gproc    worker[G_WORKERS], nuisance;
+    port_result *res;
+    uint64_t trace_cap, *trace_key;
+    double  *trace_time;
+} gsim;
+
+static void aw_push(gproc *p, int type, uint64_t handle, void *ptr)
+{
+    for (int k = p->n_awaits; k > 0; k--) {
+        p->awaits[k] = p->awaits[k - 1];
+    }
+    p->awaits[0].type = type;
+    p->awaits[0].handle = handle;
+    p->awaits[0].ptr = ptr;
+    p->n_awaits++;
+}
+
+/* src/cmb_process.c:239-260: first entry of that type (and value, unless wildcard) */
+static bool aw_remove(gproc *p, int type, bool any, uint64_t handle, void *ptr)
+{
+    for (int k = 0; k < p->n_awaits; k++) {
+        if (p->awaits[k].type == type
+            && (any || (type == AW_TIME ? p->awaits[k].handle == handle : p->awaits[k].ptr == ptr))) {
+            for (int m = k; m + 1 < p->n_awaits; m++) {
+                p->awaits[m] = p->awaits[m + 1];
+            }
+            p->n_awaits--;
+            return true;
+        }
+    }
+    return false;
+}
+
+static uint64_t g_schedule(gsim *s, int action, void *subject, int64_t arg, double t, int64_t prio)
+{
+    return heap_push(&s->fel, 0u, t, prio, action, (int64_t)(intptr_t)subject, arg);
+}
+
+/* src/cmb_event.c:285-302 (no event waiters in this workload) */
+static bool g_event_cancel(gsim *s, uint64_t handle)
+{
+    return heap_remove(&s->fel, handle);
+}
+
+/* src/cmb_event.c:385-425 with (ANY action, subject, ANY object): two passes */
+static void g_cancel_events_of(gsim *s, void *subject)
+{
+    uint64_t hit[64];
+    unsigned n = 0u;
+    for (uint64_t k = 1u; k <= s->fel.count && n < 64u; k++) {
+        if ((void *)(intptr_t)s->fel.slot[k].item[1] == subject) {
+            hit[n++] = s->fel.slot[k].key;
+        }
+    }
+    for (unsigned k = 0u; k < n; k++) {
+        g_event_cancel(s, hit[k]);
+    }
+}
+
+/* src/cmb_resourceguard.c:270-290: looks the waiter up by PROCESS ADDRESS although
+ * entries are keyed by sequence number - reproduced literally */
+static bool g_guard_remove(heap *g, gproc *p)
+{
+    return heap_remove(g, (uint64_t)(uintptr_t)p);
+}
+
+/* src/cmb_process.c:581-620 */
+static void g_cancel_awaiteds(gsim *s, gproc *p)
+{
+    while (p->n_awaits > 0) {
+        const int type = p->awaits[0].type;
+        const uint64_t handle = p->awaits[0].handle;
+        void *ptr = p->awaits[0].ptr;
+        for (int m = 0; m + 1 < p->n_awaits; m++) {
+            p->awaits[m] = p->awaits[m + 1];
+        }
+        p->n_awaits--;
+        if (type == AW_TIME) {
+            (void)g_event_cancel(s, handle);
+        }
+        else {
+            (void)g_guard_remove((heap *)ptr, p);
+        }
+    }
+    g_cancel_events_of(s, p);
+}
+
+/* cmb_process_hold up to its yield (src/cmb_process.c:262-273, 316-333) */
+static void g_hold_begin(gsim *s, gproc *p, double dur)
+{
+    p->hold_handle = g_schedule(s, ACT_WAKE_TIME, p, SIG_SUCCESS, s->now + dur, p->prio);
+    aw_push(p, AW_TIME, p->hold_handle, NULL);
+}
+
+/* ... and after it (:274-284, 338-349) */
+static int64_t g_hold_end(gsim *s, gproc *p, int64_t sig)
+{
+    if (sig != SIG_SUCCESS) {
+        (void)aw_remove(p, AW_TIME, false, p->hold_handle, NULL);
+        (void)g_event_cancel(s, p->hold_handle);
+        (void)aw_remove(p, AW_TIME, false, p->hold_handle, NULL);
+    }
+    return sig;
+}
+
+/* src/cmb_resourceguard.c:125-152 */
+static void g_wait_begin(gsim *s, heap *g, gproc *p)
+{
+    p->guard_key = ++s->guard_seq;
+    heap_push(g, p->guard_key, s->now, p->prio, (int64_t)(intptr_t)p, 0, 0);
+    aw_push(p, AW_RESOURCE, 0u, g);
+}
+
+/* :153-162 */
+static int64_t g_wait_end(gsim *s, heap *g, gproc *p, int64_t sig)
+{
+    (void)s;
+    if (sig != SIG_SUCCESS) {
+        (void)heap_remove(g, p->guard_key);
+    }
+    (void)aw_remove(p, AW_RESOURCE, false, 0u, g);
+    return sig;
+}
+
+/* src/cmb_resourceguard.c:202-226 */
+static void g_signal(gsim *s, heap *g, bool demand_holds)
+{
+    if (g->count > 0u && demand_holds) {
+        gproc *p = (gproc *)(intptr_t)g->slot[1].item[0];
+        heap_pop(g);
+        g_schedule(s, ACT_WAKE_RESOURCE, p, SIG_SUCCESS, s->now, p->prio);
+    }
+}
+
+static void g_note(gsim *s, int64_t sig, unsigned which)
+{
+    if (sig != SIG_SUCCESS) {
+        s->res->counter[which] += 1u;
+        s->res->counter[5] += (uint64_t)sig;
+    }
+}
+
+/* the three process bodies of ref_driver.c model 3 as resume points */
+static void g_body(gsim *s, gproc *p, int64_t sig)
+{
+    switch (p->pc) {
+    case 0:
+        for (;;) {
+            g_hold_begin(s, p, port_exponential(&s->rng, p->kind == 0 ? s->put_mean
+                                                        : p->kind == 1 ? s->get_mean : 1.0));
+            p->pc = 1;
+            return;
+    case 1:
+            sig = g_hold_end(s, p, sig);
+            if (p->kind == 2) {
+                const long victim = port_dice(&s->rng, 0, G_WORKERS - 1);
+                const int64_t isig = port_dice(&s->rng, 1, 10);
+                const int64_t ipri = port_dice(&s->rng, -5, 5);
+                s->res->counter[7] += 1u;
+                /* cmb_process_interrupt, src/cmb_process.c:653-666 */
+                g_schedule(s, ACT_WAKE_INTERRUPT, &s->worker[victim], isig, s->now, ipri);
+                continue;
+            }
+            g_note(s, sig, 2u);
+            if (p->kind == 0) {
+                p->stamp = s->now;
+                for (;;) {                              /* cmb_objectqueue_put */
+                    if (s->len < s->cap) {
+                        s->ring[(s->head + s->len) % s->cap] = p->stamp;
+                        s->len++;
+                        g_signal(s, &s->front, s->len > 0u);
+                        s->res->counter[0] += 1u;
+                        break;
+                    }
+                    g_wait_begin(s, &s->rear, p);
+                    p->pc = 2;
+                    return;
+    case 2:
+                    sig = g_wait_end(s, &s->rear, p, sig);
+                    if (sig != SIG_SUCCESS) {
+                        g_note(s, sig, 3u);
+                        break;
+                    }
+                }
+            }
+            else {
+                for (;;) {                              /* cmb_objectqueue_get */
+                    if (s->len > 0u) {
+                        const double stamp = s->ring[s->head];
+                        s->head = (s->head + 1u) % s->cap;
+                        s->len--;
+                        g_signal(s, &s->rear, s->len < s->cap);
+                        s->res->counter[1] += 1u;
+                        s->res->sum_wait += s->now - stamp;
+                        break;
+                    }
+                    g_wait_begin(s, &s->front, p);
+                    p->pc = 3;
+                    return;
+    case 3:
+                    sig = g_wait_end(s, &s->front, p, sig);
+                    if (sig != SIG_SUCCESS) {
+                        g_note(s, sig, 4u);
+                        break;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* cmb_process_stop, src/cmb_process.c:698-723 */
+static void g_stop(gsim *s, gproc *p)
+{
+    if (p->status != ST_RUNNING) {
+        return;
+    }
+    p->status = ST_FINISHED;
+    g_cancel_awaiteds(s, p);
+}
+
+static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
+                        double put_mean, double get_mean, uint64_t trace_cap,
+                        uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    gsim *s = calloc(1, sizeof(*s));
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    s->put_mean = put_mean;
+    s->get_mean = get_mean;
+    s->trace_cap = trace_cap;
+    s->trace_key = trace_key;
+    s->trace_time = trace_time;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&s->front, 3u, guard_before);
+    heap_init(&s->rear, 3u, guard_before);
+    s->cap = (uint64_t)capacity;
+    s->ring = calloc(s->cap, sizeof(double));
+
+    for (int i = 0; i < G_WORKERS; i++) {
+        gproc *p = &s->worker[i];
+        p->id = i;
+        p->kind = (i < G_NPUT) ? 0 : 1;
+        p->prio = port_dice(&s->rng, -5, 5);
+        g_schedule(s, ACT_START, p, 0, s->now, p->prio);
+    }
+    s->nuisance.id = G_WORKERS;
+    s->nuisance.kind = 2;
+    g_schedule(s, ACT_START, &s->nuisance, 0, s->now, 0);
+    g_schedule(s, ACT_USER_END, s, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        s->current_key = ev.key;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        gproc *p = (gproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->status = ST_RUNNING;
+            p->pc = 0;
+            g_body(s, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:                             /* src/cmb_process.c:292-308 */
+            (void)aw_remove(p, AW_TIME, false, ev.key, NULL);
+            g_body(s, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+            if (p->status == ST_RUNNING) {
+                g_body(s, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_INTERRUPT:                        /* src/cmb_process.c:628-643 */
+            g_cancel_awaiteds(s, p);
+            g_body(s, p, ev.item[2]);
+            break;
+        case ACT_USER_END:                              /* g_end_event in ref_driver.c */
+            for (int i = 0; i < G_WORKERS; i++) {
+                g_stop(s, &s->worker[i]);
+            }
+            g_stop(s, &s->nuisance);
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->counter[6] = s->len;
+    out->objects = out->counter[1];
+    heap_free(&s->fel);
+    heap_free(&s->front);
+    heap_free(&s->rear);
+    free(s->ring);
+    free(s);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -1092,6 +1438,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 3) {
+            run_guarded(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                        j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         run_one(j->model, j->servers, port_fmix64(j->master_seed, j->first + k),
                 j->num_objects, j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
@@ -1125,6 +1476,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 3) {
+        run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     run_one(model, servers, seed, num_objects, arr_mean, srv_mean,
             trace_cap, trace_key, trace_time, out);
     return 0;

@@ -65,9 +65,11 @@ typedef struct {
     double   sum_wait;    /* sum of time-in-system */
     uint64_t max_fel;     /* deepest future-event list seen */
     uint64_t max_queue;   /* longest queue (models 0,1) / process structs created (model 2) */
+    uint64_t counter[8];  /* model 3: puts, gets, interrupted holds/puts/gets, signal sum, final length, interrupts */
 } port_result;
 
-/* model 0 = M/M/1, 1 = G/G/1 (erlang-2 / truncated normal), 2 = M/M/c pool */
+/* model 0 = M/M/1, 1 = G/G/1 (erlang-2 / truncated normal), 2 = M/M/c pool,
+ * 3 = bounded queue with interrupts (num_objects = duration, servers = capacity) */
 int port_run_trials(int model, int servers, uint64_t master_seed,
                     uint64_t first, uint64_t count, uint64_t num_objects,
                     double arr_mean, double srv_mean, int threads,

@@ -46,6 +46,7 @@ struct ref_trial {
     double sum_wait;
     uint64_t max_fel;
     uint64_t max_queue;
+    uint64_t counter[8];        /* model 3: see struct ref_counters below */
     /* optional pop trace (single-trial calls only) */
     uint64_t trace_cap;
     uint64_t *trace_key;
@@ -174,6 +175,140 @@ static void *c_source_body(struct cmb_process *me, void *vw)
     return NULL;
 }
 
+
+/* ------------------------------------------------- model 3: guarded queue under fire
+ *
+ * The reference's own object-queue torture test (test/test_objectqueue.c:40-170)
+ * restated with counters instead of log lines: three putters and three getters
+ * with random priorities on a BOUNDED cmb_objectqueue (both guards in play), a
+ * nuisance process that interrupts a random victim with a random signal and a
+ * random event priority, and an end event that stops everybody.  It exercises
+ * cmb_process_interrupt / cmi_process_cancel_awaiteds / cmb_event_cancel /
+ * cmb_event_pattern_cancel / cmi_hashheap_remove on the guard, process and event
+ * priorities in the event list and in the guard order, and cmb_process_stop.
+ *
+ *   num_objects = duration (time units), servers = queue capacity,
+ *   arr_mean = putter hold mean, srv_mean = getter hold mean, nuisance hold mean 1.
+ * counters: [0] successful puts [1] successful gets [2] interrupted holds
+ *           [3] interrupted puts [4] interrupted gets [5] sum of signals received
+ *           [6] final queue length [7] interrupts issued
+ * sum_wait = sum over successful gets of (get time - put time of that object)
+ */
+static void pump_events(struct ref_trial *t);
+#define G_PUTTERS 3u
+#define G_GETTERS 3u
+
+struct g_world {
+    struct ref_trial *trl;
+    struct cmb_objectqueue *queue;
+    struct cmb_process *worker[G_PUTTERS + G_GETTERS];
+    struct cmb_process *nuisance;
+};
+
+static void note_signal(struct ref_trial *t, int64_t sig, unsigned which)
+{
+    if (sig != CMB_PROCESS_SUCCESS) {
+        t->counter[which] += 1u;
+        t->counter[5] += (uint64_t)sig;
+    }
+}
+
+static void *g_putter_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct g_world *w = vw;
+    for (;;) {
+        int64_t sig = cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        note_signal(w->trl, sig, 2u);
+        double *stamp = cmi_mempool_alloc(&stamp_pool);
+        *stamp = cmb_time();
+        sig = cmb_objectqueue_put(w->queue, stamp);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[0] += 1u;
+        }
+        else {
+            note_signal(w->trl, sig, 3u);
+            cmi_mempool_free(&stamp_pool, stamp);
+        }
+    }
+}
+
+static void *g_getter_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct g_world *w = vw;
+    for (;;) {
+        int64_t sig = cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
+        note_signal(w->trl, sig, 2u);
+        void *obj = NULL;
+        sig = cmb_objectqueue_get(w->queue, &obj);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[1] += 1u;
+            w->trl->sum_wait += cmb_time() - *(double *)obj;
+            cmi_mempool_free(&stamp_pool, obj);
+        }
+        else {
+            note_signal(w->trl, sig, 4u);
+        }
+    }
+}
+
+static void *g_nuisance_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct g_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)(G_PUTTERS + G_GETTERS - 1u));
+        const int64_t sig = cmb_random_dice(1, 10);
+        const int64_t pri = cmb_random_dice(-5, 5);
+        w->trl->counter[7] += 1u;
+        cmb_process_interrupt(w->worker[victim], sig, pri);
+    }
+}
+
+static void g_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct g_world *w = subject;
+    for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
+        cmb_process_stop(w->worker[i], NULL);
+    }
+    cmb_process_stop(w->nuisance, NULL);
+}
+
+static void run_guarded_trial(struct ref_trial *t)
+{
+    struct g_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->queue = cmb_objectqueue_create();
+    cmb_objectqueue_initialize(w->queue, "Queue", (uint64_t)t->servers);
+    for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
+        w->worker[i] = cmb_process_create();
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_initialize(w->worker[i], (i < G_PUTTERS) ? "Putter" : "Getter",
+                               (i < G_PUTTERS) ? g_putter_body : g_getter_body, w, pri);
+        cmb_process_start(w->worker[i]);
+    }
+    w->nuisance = cmb_process_create();
+    cmb_process_initialize(w->nuisance, "Nuisance", g_nuisance_body, w, 0);
+    cmb_process_start(w->nuisance);
+    (void)cmb_event_schedule(g_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->counter[6] = cmb_objectqueue_length(w->queue);
+    t->objects = t->counter[1];
+    for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
+        cmb_process_terminate(w->worker[i]);
+        cmb_process_destroy(w->worker[i]);
+    }
+    cmb_process_terminate(w->nuisance);
+    cmb_process_destroy(w->nuisance);
+    cmb_objectqueue_destroy(w->queue);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -255,7 +390,11 @@ static void run_trial(void *vt)
     cmb_logger_flags_off(CMB_LOGGER_INFO);
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
-    if (t->model == 2) {
+    memset(t->counter, 0, sizeof(t->counter));
+    if (t->model == 3) {
+        run_guarded_trial(t);
+    }
+    else if (t->model == 2) {
         run_pool_trial(t);
     }
     else {
@@ -273,6 +412,7 @@ struct ref_result {
     double sum_wait;
     uint64_t max_fel;
     uint64_t max_queue;
+    uint64_t counter[8];
 };
 
 /*
@@ -314,6 +454,7 @@ int ref_run_trials(int model, int servers, uint64_t master_seed,
         out[i].sum_wait = exp[i].sum_wait;
         out[i].max_fel = exp[i].max_fel;
         out[i].max_queue = exp[i].max_queue;
+        memcpy(out[i].counter, exp[i].counter, sizeof(out[i].counter));
     }
     free(exp);
     return 0;
@@ -337,6 +478,7 @@ int ref_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects,
     out->sum_wait = t.sum_wait;
     out->max_fel = t.max_fel;
     out->max_queue = t.max_queue;
+    memcpy(out->counter, t.counter, sizeof(out->counter));
     return 0;
 }
 

@@ -28,7 +28,8 @@ SEEDS = [KAT_SEED, 12345, 7, 0, 2**64 - 1]
 RNG_KINDS = {0: (0.0, 0.0), 1: (1.0, 0.0), 2: (0.0, 0.0), 3: (0.0, 0.0), 4: (1.0, 0.25),
              5: (2.0, 0.625), 6: (-3.0, 5.5), 7: (1.0, 6.0), 8: (0.3, 0.0)}
 MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, servers=1),
-          2: dict(arr=1 / 6.4, srv=1.0, servers=8)}
+          2: dict(arr=1 / 6.4, srv=1.0, servers=8),
+          3: dict(arr=1.0, srv=1.0, servers=10)}     # model 3: num_objects = duration, servers = queue capacity
 
 
 def hexes(a):
@@ -64,17 +65,22 @@ def main():
     trials = []
     for model, par in MODELS.items():
         for seed in SEEDS:
-            for nobj in (0, 1, 2, 3, 10, 1000, 100_000):
+            # model 3: the size is a duration; 0 would stop workers before they start (they then
+            # run forever in the reference), so it starts at 1
+            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model != 3 else (1, 2, 3, 10, 100, 1000)):
                 r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
                                              par["arr"], par["srv"], 512 if nobj == 1000 else 0)
                 rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
                        "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                        "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
-                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue}
+                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
+                       "counters": r.counters()}
                 if nobj == 1000:
                     rec["trace_key"] = [int(k) for k in keys]
                     rec["trace_time"] = hexes(times)
                 trials.append(rec)
+        if model == 3:
+            continue
         # the full-size known answer
         r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
         trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,

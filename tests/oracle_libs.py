@@ -20,10 +20,14 @@ ORACLE = ROOT / "oracle"
 
 class Result(C.Structure):
     _fields_ = [("events", C.c_uint64), ("objects", C.c_uint64), ("t_end", C.c_double),
-                ("sum_wait", C.c_double), ("max_fel", C.c_uint64), ("max_queue", C.c_uint64)]
+                ("sum_wait", C.c_double), ("max_fel", C.c_uint64), ("max_queue", C.c_uint64),
+                ("counter", C.c_uint64 * 8)]
 
     def key(self):
         return (self.events, self.objects, self.t_end, self.sum_wait)
+
+    def counters(self):
+        return list(self.counter)
 
 
 _DP = C.POINTER(C.c_double)

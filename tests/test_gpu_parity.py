@@ -276,3 +276,31 @@ def test_pool_known_answer_full_size(cb, golden):
     assert ((ev >= 3_000_001) & (ev <= 4_100_000)).all()
     avg = (res.sum_wait / res.objects.double()).cpu().numpy()
     assert abs(avg.mean() - 1.30) < 0.02                 # M/M/8 at rho 0.8: W = 1 + C(8, 6.4)/(8 - 6.4)
+
+
+# ------------------------------------------------------------------ general path (interrupt / cancel / stop)
+
+@pytest.mark.parametrize("cap,dur,pm,gm", [(10, 600, 1.0, 1.0), (2, 400, 0.5, 1.0), (4, 400, 1.0, 0.4), (1, 300, 0.7, 0.7)])
+def test_guarded_queue_under_interrupts_matches_oracle(cb, port, cap, dur, pm, gm):
+    """test/test_objectqueue.c's model: priorities, interrupts, guard self-cancel, event cancel,
+    pattern cancel, stop - counts, clock, sums and all eight counters bit-exact."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=pm, srv_mean=gm, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_GUARDED, servers=cap)
+    want = run_trials(port, "port", 3, cap, KAT_SEED, 0, n, dur, pm, gm)
+    _compare(res, want, ("guarded", cap))
+    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+    assert sum(w.counters()[2] + w.counters()[3] + w.counters()[4] for w in want) > 100   # interrupts really hit
+
+
+def test_guarded_pop_order_bit_exact(cb, port):
+    n, cap, dur = 24, 8000, 700
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=99,
+                        model=cb.MODEL_GUARDED, servers=10, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 3, 10, cb.fmix64(99, i), dur, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
