@@ -19,6 +19,7 @@
 #include "mm1_fast.cuh"
 #include "pool_model.cuh"
 #include "guarded_model.cuh"
+#include "preempt_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -120,7 +121,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
-    if (job->model == CIMBA_B200_MODEL_GUARDED) {
+    if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
     }
     return 0u;
@@ -216,9 +217,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
     }
-    if (job->model == CIMBA_B200_MODEL_GUARDED) {
-        if (job->servers < 1 || job->servers > 16)
-            return fail(CIMBA_B200_EINVAL, "queue capacity (servers) must be in 1..16 for CIMBA_B200_MODEL_GUARDED");
+    if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT) {
+        const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
+        if (job->servers < 1 || (!pre && job->servers > 16))
+            return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1 (and <= 16 for CIMBA_B200_MODEL_GUARDED)");
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
@@ -243,7 +245,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.trace_time = job->trace_time;
         const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
-        if (trace) {
+        if (pre) {
+            if (trace) preempt_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+            else       preempt_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        else if (trace) {
             guarded_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
         }
         else {

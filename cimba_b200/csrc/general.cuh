@@ -68,6 +68,18 @@ struct GuardOrder {
     }
 };
 
+// holder_queue_check, src/cmb_resourcepool.c:75-92: lowest priority first (the likeliest
+// victim of a pre-emption), then the LARGER key first (the reference
+// keys holders by process address; here by process index + 1)
+struct HolderOrder {
+    static __device__ __forceinline__ bool before(const HeapTag &a, const HeapTag &b)
+    {
+        if (a.prio < b.prio) return true;
+        if (a.prio == b.prio && a.key > b.key) return true;
+        return false;
+    }
+};
+
 template <int CAP, class Order>
 struct BinHeap {
     HeapTag  slot[CAP + 1];     // 1-based; slot[0] = last popped
@@ -154,6 +166,34 @@ struct BinHeap {
         return true;
     }
 
+    __device__ uint32_t find(uint32_t key) const        // cmi_hash_find_index (by scan): 0 = absent
+    {
+        for (uint32_t k = 1u; k <= count; k++) {
+            if (slot[k].key == key) {
+                return k;
+            }
+        }
+        return 0u;
+    }
+
+    // cmi_hashheap_reprioritize, src/cmi_hashheap.c:679-711
+    __device__ void reprioritize(uint32_t key, double d, int32_t prio)
+    {
+        const uint32_t at = find(key);
+        if (at == 0u) {
+            return;
+        }
+        const HeapTag old = slot[at];
+        slot[at].d = d;
+        slot[at].prio = prio;
+        if (Order::before(old, slot[at])) {
+            sift_down(at);
+        }
+        else {
+            sift_up(at);
+        }
+    }
+
     __device__ bool remove(uint32_t key)                // cmi_hashheap_remove (lookup by scan)
     {
         uint32_t at = 0u;
@@ -190,6 +230,7 @@ constexpr int GEN_MAX_AWAITS = 4;
 
 using EventHeap = BinHeap<GEN_FEL_CAP, EventOrder>;
 using GuardHeap = BinHeap<GEN_GUARD_CAP, GuardOrder>;
+using HolderHeap = BinHeap<GEN_MAX_PROCS, HolderOrder>;     // tag.subj = holder, tag.arg = amount held
 
 struct GenProc {                // struct cmb_process (include/cmb_process.h:116-123), the parts that act
     uint32_t pc, status, kind;
@@ -199,6 +240,9 @@ struct GenProc {                // struct cmb_process (include/cmb_process.h:116
     uint32_t await_ref[GEN_MAX_AWAITS];     // event handle or guard index
     uint32_t hold_handle, guard_key;
     double   stamp;
+    // resource-pool bookkeeping of the process body (model 4)
+    uint32_t holds_pool;        // a cmi_process_holdable tag for the pool is on its resources list
+    uint32_t held, req, rem, initially_held;
 };
 
 struct GeneralState {
@@ -209,6 +253,9 @@ struct GeneralState {
     uint32_t  ring_cap, ring_head, ring_len;
     uint32_t  guard_seq;        // enqueue_seq, src/cmb_resourceguard.c:64
     uint32_t  status;
+    // cmb_resourcepool (model 4): guard[0] is its guard
+    HolderHeap holders;
+    uint32_t  pool_cap, pool_in_use;
 };
 
 struct GeneralSim {
@@ -363,6 +410,70 @@ struct GeneralSim {
         }
         p.status = PROC_FINISHED;
         cancel_awaiteds(pid);
+        if (p.holds_pool) {                                     // cmi_process_drop_resources, :507-527
+            p.holds_pool = 0u;
+            pool_drop_holder(pid);
+        }
+    }
+
+    // ---- cmb_resourcepool (src/cmb_resourcepool.c); guard index 0
+    __device__ void pool_signal()
+    {
+        signal(0u, st->pool_cap - st->pool_in_use > 0u);        // is_available, :198-211
+    }
+
+    __device__ uint32_t pool_held_by(uint32_t pid) const        // :302-318
+    {
+        const uint32_t k = st->holders.find(pid + 1u);
+        return k ? (uint32_t)st->holders.slot[k].arg : 0u;
+    }
+
+    __device__ void pool_update_record(uint32_t pid, uint32_t amount)       // :324-355
+    {
+        const uint32_t k = st->holders.find(pid + 1u);
+        if (k != 0u) {
+            st->holders.slot[k].arg += (int32_t)amount;
+        }
+        else {
+            st->proc[pid].holds_pool = 1u;
+            if (st->holders.push(pid + 1u, 0.0, st->proc[pid].prio, 0u, pid, (int32_t)amount) == 0u) {
+                st->status |= TRIAL_ERR_PROC_OVERFLOW;
+            }
+        }
+    }
+
+    __device__ void pool_release(uint32_t pid, uint32_t amount)             // :561-605
+    {
+        const uint32_t k = st->holders.find(pid + 1u);
+        if (k != 0u && (uint32_t)st->holders.slot[k].arg == amount) {
+            st->holders.remove(pid + 1u);
+            st->proc[pid].holds_pool = 0u;
+        }
+        else if (k != 0u) {
+            st->holders.slot[k].arg -= (int32_t)amount;
+        }
+        st->pool_in_use -= amount;
+        pool_signal();
+    }
+
+    __device__ void pool_drop_holder(uint32_t pid)                          // :98-121
+    {
+        const uint32_t k = st->holders.find(pid + 1u);
+        if (k != 0u) {
+            st->pool_in_use -= (uint32_t)st->holders.slot[k].arg;
+            st->holders.remove(pid + 1u);
+            pool_signal();
+        }
+    }
+
+    // cmb_process_priority_set for the RUNNING process (its awaits list is empty),
+    // src/cmb_process.c:150-198 -> reprioritize_holder, src/cmb_resourcepool.c:127-137
+    __device__ void priority_set_self(uint32_t pid, int32_t pri)
+    {
+        st->proc[pid].prio = pri;
+        if (st->proc[pid].holds_pool) {
+            st->holders.reprioritize(pid + 1u, 0.0, pri);
+        }
     }
 };
 

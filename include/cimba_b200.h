@@ -46,6 +46,8 @@ extern "C" {
 #define CIMBA_B200_MODEL_GUARDED 3 /* test/test_objectqueue.c: 3 putters + 3 getters with random priorities on a BOUNDED
                                     * cmb_objectqueue (capacity = `servers` <= 16), a nuisance process interrupting them,
                                     * an end event at t = num_objects stopping everybody (general cancel/interrupt path) */
+#define CIMBA_B200_MODEL_PREEMPT 4 /* test/test_resourcepool.c: 3 mice (priority_set + acquire), 2 rats (pre-empt), a cat
+                                    * interrupting them, on a cmb_resourcepool of `servers` units; end event at t = num_objects */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

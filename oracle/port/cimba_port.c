@@ -689,7 +689,7 @@ int port_heap_script(uint64_t n, const int *ops, const double *vals_d,
 
 /* ======================================================== simulation kernel */
 
-enum { SIG_SUCCESS = 0 };                               /* include/cmb_process.h:59-99 */
+enum { SIG_SUCCESS = 0, SIG_PREEMPTED = -1, SIG_INTERRUPTED = -2 };    /* include/cmb_process.h:59-99 */
 enum { ACT_START = 1, ACT_WAKE_TIME, ACT_WAKE_RESOURCE };
 enum { ST_CREATED = 0, ST_RUNNING, ST_FINISHED };
 
@@ -1421,6 +1421,379 @@ static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
     free(s);
 }
 
+/* ======================================== model 4: resource pool with pre-emption
+ *
+ * cmi_pool_acquire_inner (src/cmb_resourcepool.c:362-533) in full, release (:561-605),
+ * update_record (:324-355), reset_holder (:217-236), resourcepool_drop_holder
+ * (:98-121), reprioritize_holder (:127-137) -> cmi_hashheap_reprioritize
+ * (src/cmi_hashheap.c:679-711), holder_queue_check (:75-92),
+ * cmb_process_priority_set for a running process (src/cmb_process.c:150-198),
+ * cmi_process_drop_resources (:507-527).  Workload: ref_driver.c model 4.
+ * Holder keys are process index + 1 (the reference keys by process address; the
+ * driver allocates its processes in one array, so both orders agree).
+ */
+#define P_MICE 3
+#define P_RODENTS 5
+
+/* src/cmb_resourcepool.c:75-92: lowest priority first, then LARGER key first */
+static bool holder_before(const heap_tag *a, const heap_tag *b)
+{
+    if (a->i < b->i) return true;
+    if (a->i == b->i && a->key > b->key) return true;
+    return false;
+}
+
+typedef struct pproc {
+    gproc    g;                 /* pc, status, prio, awaits, hold_handle, guard_key */
+    bool     holds_pool;        /* a cmi_process_holdable tag for the pool is on the resources list */
+    uint64_t held, req, rem, initially_held;
+} pproc;
+
+typedef struct psim {
+    gsim     s;                 /* rng, now, fel, guard_seq; s.front is the pool's guard */
+    heap     holders;
+    uint64_t cap, in_use;
+    pproc    proc[P_RODENTS + 1];
+} psim;
+
+static uint64_t holder_slot(psim *w, uint64_t key)
+{
+    for (uint64_t k = 1u; k <= w->holders.count; k++) {
+        if (w->holders.slot[k].key == key) {
+            return k;
+        }
+    }
+    return 0u;
+}
+
+static uint64_t p_held_by(psim *w, pproc *p)             /* :302-318 */
+{
+    const uint64_t k = holder_slot(w, (uint64_t)(p - w->proc) + 1u);
+    return k ? (uint64_t)w->holders.slot[k].item[1] : 0u;
+}
+
+static void p_update_record(psim *w, pproc *p, uint64_t amount)     /* :324-355 */
+{
+    const uint64_t key = (uint64_t)(p - w->proc) + 1u;
+    const uint64_t k = holder_slot(w, key);
+    if (k != 0u) {
+        w->holders.slot[k].item[1] += (int64_t)amount;
+    }
+    else {
+        p->holds_pool = true;
+        heap_push(&w->holders, key, 0.0, p->g.prio, (int64_t)(intptr_t)p, (int64_t)amount, 0);
+    }
+}
+
+static void p_signal_guard(psim *w)
+{
+    g_signal(&w->s, &w->s.front, w->cap - w->in_use > 0u);          /* is_available, :198-211 */
+}
+
+/* cmi_hashheap_reprioritize, src/cmi_hashheap.c:679-711 */
+static void heap_reprioritize(heap *h, uint64_t key, double d, int64_t i)
+{
+    uint64_t at = 0u;
+    for (uint64_t k = 1u; k <= h->count; k++) {
+        if (h->slot[k].key == key) {
+            at = k;
+            break;
+        }
+    }
+    if (at == 0u) {
+        return;
+    }
+    const heap_tag old = h->slot[at];
+    h->slot[at].d = d;
+    h->slot[at].i = i;
+    if (h->before(&old, &h->slot[at])) {
+        sift_down(h, at);
+    }
+    else {
+        sift_up(h, at);
+    }
+}
+
+/* cmb_process_priority_set for the running process (its awaits list is empty) */
+static void p_priority_set(psim *w, pproc *p, int64_t pri)
+{
+    p->g.prio = pri;
+    if (p->holds_pool) {
+        heap_reprioritize(&w->holders, (uint64_t)(p - w->proc) + 1u, 0.0, pri);
+    }
+}
+
+static void p_release(psim *w, pproc *p, uint64_t amount)           /* :561-605 */
+{
+    const uint64_t key = (uint64_t)(p - w->proc) + 1u;
+    const uint64_t k = holder_slot(w, key);
+    if ((uint64_t)w->holders.slot[k].item[1] == amount) {
+        heap_remove(&w->holders, key);
+        p->holds_pool = false;
+    }
+    else {
+        w->holders.slot[k].item[1] -= (int64_t)amount;
+    }
+    w->in_use -= amount;
+    p_signal_guard(w);
+}
+
+static void p_check(psim *w, pproc *p)
+{
+    if (p_held_by(w, p) != p->held) {
+        w->s.res->counter[7] += 1u;
+    }
+}
+
+static void p_take_signal(psim *w, pproc *p, int64_t sig)
+{
+    if (sig == SIG_PREEMPTED) {
+        w->s.res->counter[2] += 1u;
+        p->held = 0u;
+    }
+    else if (sig != SIG_SUCCESS) {
+        w->s.res->counter[3] += 1u;
+    }
+    w->s.res->counter[4] += (uint64_t)sig;
+}
+
+static void p_rodent(psim *w, pproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    const bool rat = (p - w->proc) >= P_MICE;
+    switch (p->g.pc) {
+    case 0:
+        for (;;) {
+            p_check(w, p);
+            p->req = (uint64_t)port_dice(&s->rng, 1, 5);
+            if (!rat) {
+                p_priority_set(w, p, port_dice(&s->rng, -5, 5));
+            }
+            /* ---- cmi_pool_acquire_inner */
+            p->initially_held = p_held_by(w, p);
+            p->rem = p->req;
+            for (;;) {
+                const uint64_t avail = w->cap - w->in_use;
+                if (avail >= p->rem) {
+                    w->in_use += p->rem;
+                    p_update_record(w, p, p->rem);
+                    p_signal_guard(w);
+                    sig = SIG_SUCCESS;
+                    goto acquired;
+                }
+                else if (avail > 0u) {
+                    w->in_use += avail;
+                    p->rem -= avail;
+                    p_update_record(w, p, avail);
+                }
+                if (rat) {
+                    while (w->holders.count > 0u && w->holders.slot[1].i < p->g.prio) {
+                        heap_pop(&w->holders);
+                        pproc *victim = (pproc *)(intptr_t)w->holders.slot[0].item[0];
+                        const uint64_t loot = (uint64_t)w->holders.slot[0].item[1];
+                        victim->holds_pool = false;                 /* cmi_process_remove_holdable */
+                        g_schedule(s, ACT_WAKE_INTERRUPT, victim, SIG_PREEMPTED, s->now, victim->g.prio);
+                        if (loot < p->rem) {
+                            p_update_record(w, p, loot);
+                            p->rem -= loot;
+                        }
+                        else {
+                            p_update_record(w, p, p->rem);
+                            w->in_use -= loot - p->rem;
+                            p_signal_guard(w);
+                            sig = SIG_SUCCESS;
+                            goto acquired;
+                        }
+                    }
+                }
+                g_wait_begin(s, &s->front, &p->g);
+                p->g.pc = 1;
+                return;
+    case 1:
+                sig = g_wait_end(s, &s->front, &p->g, sig);
+                if (sig == SIG_PREEMPTED) {
+                    goto acquired;
+                }
+                else if (sig != SIG_SUCCESS) {
+                    if (p->initially_held > 0u) {                   /* reset_holder, :217-236 */
+                        const uint64_t k = holder_slot(w, (uint64_t)(p - w->proc) + 1u);
+                        const uint64_t surplus = (uint64_t)w->holders.slot[k].item[1] - p->initially_held;
+                        w->holders.slot[k].item[1] = (int64_t)p->initially_held;
+                        w->in_use -= surplus;
+                        p_signal_guard(w);
+                    }
+                    else {
+                        w->in_use -= p_held_by(w, p);
+                        if (heap_remove(&w->holders, (uint64_t)(p - w->proc) + 1u)) {
+                            p->holds_pool = false;
+                        }
+                    }
+                    goto acquired;
+                }
+            }
+acquired:
+            if (sig == SIG_SUCCESS) {
+                p->held += p->req;
+                s->res->counter[rat ? 1 : 0] += 1u;
+                p_check(w, p);
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+                p->g.pc = 2;
+                return;
+    case 2:
+                sig = g_hold_end(s, &p->g, sig);
+                if (sig == SIG_SUCCESS) {
+                    uint64_t rel = (uint64_t)port_dice(&s->rng, 1, 5);
+                    if (rel > p->held || port_dice(&s->rng, 0, 1) == 1) {
+                        rel = p->held;
+                    }
+                    p_release(w, p, rel);
+                    p->held -= rel;
+                    s->res->counter[5] += rel;
+                    s->res->sum_wait += s->now * (double)rel;
+                }
+                else {
+                    p_take_signal(w, p, sig);
+                }
+            }
+            else {
+                p_take_signal(w, p, sig);
+            }
+            p_check(w, p);
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 3;
+            return;
+    case 3:
+            sig = g_hold_end(s, &p->g, sig);
+            if (sig != SIG_SUCCESS) {
+                p_take_signal(w, p, sig);
+            }
+        }
+    }
+}
+
+static void p_cat(psim *w, pproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    switch (p->g.pc) {
+    case 0:
+        for (;;) {
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 1;
+            return;
+    case 1:
+            (void)g_hold_end(s, &p->g, sig);
+            {
+                const long victim = port_dice(&s->rng, 0, P_RODENTS - 1);
+                const int64_t loud = port_dice(&s->rng, 10, 100);
+                const int64_t isig = (port_dice(&s->rng, 0, 1) == 1) ? SIG_INTERRUPTED : loud;
+                g_schedule(s, ACT_WAKE_INTERRUPT, &w->proc[victim], isig, s->now, 0);
+            }
+        }
+    }
+}
+
+static void p_resume(psim *w, pproc *p, int64_t sig)
+{
+    if (p - w->proc == P_RODENTS) {
+        p_cat(w, p, sig);
+    }
+    else {
+        p_rodent(w, p, sig);
+    }
+}
+
+/* cmb_process_stop: cancel awaiteds, THEN drop resources (src/cmb_process.c:714-719) */
+static void p_stop(psim *w, pproc *p)
+{
+    if (p->g.status != ST_RUNNING) {
+        return;
+    }
+    p->g.status = ST_FINISHED;
+    g_cancel_awaiteds(&w->s, &p->g);
+    if (p->holds_pool) {                                /* resourcepool_drop_holder, :98-121 */
+        p->holds_pool = false;
+        const uint64_t key = (uint64_t)(p - w->proc) + 1u;
+        const uint64_t k = holder_slot(w, key);
+        if (k != 0u) {
+            w->in_use -= (uint64_t)w->holders.slot[k].item[1];
+            heap_remove(&w->holders, key);
+            p_signal_guard(w);
+        }
+    }
+}
+
+static void run_preempt(int capacity, uint64_t seed, uint64_t duration, uint64_t trace_cap,
+                        uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    psim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&s->front, 3u, guard_before);
+    heap_init(&w->holders, 3u, holder_before);
+    w->cap = (uint64_t)capacity;
+
+    for (int i = 0; i < P_RODENTS; i++) {
+        w->proc[i].g.prio = port_dice(&s->rng, -5, 5);
+        g_schedule(s, ACT_START, &w->proc[i], 0, s->now, w->proc[i].g.prio);
+    }
+    g_schedule(s, ACT_START, &w->proc[P_RODENTS], 0, s->now, 0);
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        pproc *p = (pproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->g.status = ST_RUNNING;
+            p->g.pc = 0;
+            p_resume(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(&p->g, AW_TIME, false, ev.key, NULL);
+            p_resume(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+            if (p->g.status == ST_RUNNING) {
+                p_resume(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_INTERRUPT:
+            g_cancel_awaiteds(s, &p->g);
+            p_resume(w, p, ev.item[2]);
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i <= P_RODENTS; i++) {
+                p_stop(w, &w->proc[i]);
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->counter[6] = w->in_use;
+    out->objects = out->counter[0] + out->counter[1];
+    heap_free(&s->fel);
+    heap_free(&s->front);
+    heap_free(&w->holders);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -1438,6 +1811,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 4) {
+            run_preempt(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                        0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 3) {
             run_guarded(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -1476,6 +1854,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 4) {
+        run_preempt(servers, seed, num_objects, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 3) {
         run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;

@@ -309,6 +309,152 @@ static void run_guarded_trial(struct ref_trial *t)
     free(w);
 }
 
+
+/* ------------------------------------------------- model 4: resource pool with pre-emption
+ *
+ * The reference's pool torture test (test/test_resourcepool.c:72-330) restated with
+ * counters: three "mice" that change their own priority and acquire politely, two
+ * "rats" that pre-empt (cmb_resourcepool_preempt), one "cat" that interrupts a random
+ * rodent, an end event that stops everybody (dropping what they hold).  Exercises
+ * cmi_pool_acquire_inner in full (partial grabs, the holders heap, pre-emption,
+ * roll-back on interrupt), cmb_resourcepool_release (partial), cmb_process_priority_set
+ * -> reprioritize_holder -> cmi_hashheap_reprioritize, resourcepool_drop_holder.
+ *
+ * All processes live in ONE array so that their addresses ascend with their index:
+ * the holders heap breaks priority ties by larger address first
+ * (src/cmb_resourcepool.c:82-89), and the device uses the index.
+ *
+ *   num_objects = duration, servers = pool capacity.
+ * counters: [0] acquires ok [1] pre-empts ok [2] PREEMPTED received [3] other signals
+ *           received [4] sum of signals (two's complement) [5] units released
+ *           [6] final in_use [7] own-vs-library holding mismatches (must stay 0)
+ * sum_wait = sum over releases of cmb_time() * units released
+ */
+#define P_MICE 3u
+#define P_RATS 2u
+#define P_RODENTS (P_MICE + P_RATS)
+
+struct p_world {
+    struct ref_trial *trl;
+    struct cmb_resourcepool *pool;
+    struct cmb_process *proc;           /* P_RODENTS + 1 contiguous process structs */
+};
+
+static void p_check(struct p_world *w, struct cmb_process *me, uint64_t held)
+{
+    if (cmb_resourcepool_held_by_process(w->pool, me) != held) {
+        w->trl->counter[7] += 1u;
+    }
+}
+
+static void p_signal(struct p_world *w, int64_t sig, uint64_t *held)
+{
+    if (sig == CMB_PROCESS_PREEMPTED) {
+        w->trl->counter[2] += 1u;
+        *held = 0u;
+    }
+    else if (sig != CMB_PROCESS_SUCCESS) {
+        w->trl->counter[3] += 1u;
+    }
+    w->trl->counter[4] += (uint64_t)sig;
+}
+
+static void *p_rodent_body(struct cmb_process *me, void *vw)
+{
+    struct p_world *w = vw;
+    const bool rat = (me >= &w->proc[P_MICE]);
+    uint64_t held = 0u;
+    for (;;) {
+        p_check(w, me, held);
+        const uint64_t req = (uint64_t)cmb_random_dice(1, 5);
+        int64_t sig;
+        if (rat) {
+            sig = cmb_resourcepool_preempt(w->pool, req);
+        }
+        else {
+            cmb_process_priority_set(me, cmb_random_dice(-5, 5));
+            sig = cmb_resourcepool_acquire(w->pool, req);
+        }
+        if (sig == CMB_PROCESS_SUCCESS) {
+            held += req;
+            w->trl->counter[rat ? 1 : 0] += 1u;
+            p_check(w, me, held);
+            sig = cmb_process_hold(cmb_random_exponential(1.0));
+            if (sig == CMB_PROCESS_SUCCESS) {
+                uint64_t rel = (uint64_t)cmb_random_dice(1, 5);
+                if (rel > held || cmb_random_dice(0, 1) == 1) {
+                    rel = held;                         /* every other time: give everything back */
+                }
+                cmb_resourcepool_release(w->pool, rel);
+                held -= rel;
+                w->trl->counter[5] += rel;
+                w->trl->sum_wait += cmb_time() * (double)rel;
+            }
+            else {
+                p_signal(w, sig, &held);
+            }
+        }
+        else {
+            p_signal(w, sig, &held);
+        }
+        p_check(w, me, held);
+        sig = cmb_process_hold(cmb_random_exponential(1.0));
+        if (sig != CMB_PROCESS_SUCCESS) {
+            p_signal(w, sig, &held);
+        }
+    }
+}
+
+static void *p_cat_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct p_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)P_RODENTS - 1);
+        const int64_t loud = cmb_random_dice(10, 100);
+        const int64_t sig = (cmb_random_dice(0, 1) == 1) ? CMB_PROCESS_INTERRUPTED : loud;
+        cmb_process_interrupt(&w->proc[victim], sig, 0);
+    }
+}
+
+static void p_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct p_world *w = subject;
+    for (unsigned i = 0u; i <= P_RODENTS; i++) {
+        cmb_process_stop(&w->proc[i], NULL);
+    }
+}
+
+static void run_preempt_trial(struct ref_trial *t)
+{
+    struct p_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->pool = cmb_resourcepool_create();
+    cmb_resourcepool_initialize(w->pool, "Cheese", (uint64_t)t->servers);
+    w->proc = calloc(P_RODENTS + 1u, sizeof(struct cmb_process));
+    for (unsigned i = 0u; i < P_RODENTS; i++) {
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_initialize(&w->proc[i], (i < P_MICE) ? "Mouse" : "Rat", p_rodent_body, w, pri);
+        cmb_process_start(&w->proc[i]);
+    }
+    cmb_process_initialize(&w->proc[P_RODENTS], "Cat", p_cat_body, w, 0);
+    cmb_process_start(&w->proc[P_RODENTS]);
+    (void)cmb_event_schedule(p_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->counter[6] = cmb_resourcepool_in_use(w->pool);
+    t->objects = t->counter[0] + t->counter[1];
+    for (unsigned i = 0u; i <= P_RODENTS; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    cmb_resourcepool_destroy(w->pool);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -391,7 +537,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 3) {
+    if (t->model == 4) {
+        run_preempt_trial(t);
+    }
+    else if (t->model == 3) {
         run_guarded_trial(t);
     }
     else if (t->model == 2) {

@@ -29,7 +29,8 @@ RNG_KINDS = {0: (0.0, 0.0), 1: (1.0, 0.0), 2: (0.0, 0.0), 3: (0.0, 0.0), 4: (1.0
              5: (2.0, 0.625), 6: (-3.0, 5.5), 7: (1.0, 6.0), 8: (0.3, 0.0)}
 MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, servers=1),
           2: dict(arr=1 / 6.4, srv=1.0, servers=8),
-          3: dict(arr=1.0, srv=1.0, servers=10)}     # model 3: num_objects = duration, servers = queue capacity
+          3: dict(arr=1.0, srv=1.0, servers=10),     # model 3: num_objects = duration, servers = queue capacity
+          4: dict(arr=1.0, srv=1.0, servers=20)}     # model 4: num_objects = duration, servers = pool capacity
 
 
 def hexes(a):
@@ -67,7 +68,7 @@ def main():
         for seed in SEEDS:
             # model 3: the size is a duration; 0 would stop workers before they start (they then
             # run forever in the reference), so it starts at 1
-            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model != 3 else (1, 2, 3, 10, 100, 1000)):
+            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model < 3 else (1, 2, 3, 10, 100, 1000)):
                 r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
                                              par["arr"], par["srv"], 512 if nobj == 1000 else 0)
                 rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
@@ -79,7 +80,7 @@ def main():
                     rec["trace_key"] = [int(k) for k in keys]
                     rec["trace_time"] = hexes(times)
                 trials.append(rec)
-        if model == 3:
+        if model >= 3:
             continue
         # the full-size known answer
         r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)

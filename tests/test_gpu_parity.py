@@ -304,3 +304,31 @@ def test_guarded_pop_order_bit_exact(cb, port):
         m = min(cap, r.events)
         assert list(keys[i, :m]) == k, i
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+@pytest.mark.parametrize("cap,dur", [(20, 500), (6, 400), (3, 300), (40, 300)])
+def test_pool_preemption_matches_oracle(cb, port, cap, dur):
+    """test/test_resourcepool.c's model: greedy partial acquire, pre-emption through the holders
+    heap, roll-back on interrupt, partial release, priority_set/reprioritize, drop on stop."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_PREEMPT, servers=cap)
+    want = run_trials(port, "port", 4, cap, KAT_SEED, 0, n, dur, 1.0, 1.0)
+    _compare(res, want, ("preempt", cap))
+    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+    assert all(w.counters()[7] == 0 and w.counters()[6] == 0 for w in want)     # holdings consistent, all dropped
+    if cap == 20:
+        assert sum(w.counters()[2] for w in want) > 500                            # pre-emptions really happen
+
+
+def test_pool_preemption_pop_order_bit_exact(cb, port):
+    n, cap, dur = 16, 8000, 600
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=5,
+                        model=cb.MODEL_PREEMPT, servers=20, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 4, 20, cb.fmix64(5, i), dur, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
