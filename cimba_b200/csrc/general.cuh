@@ -31,7 +31,8 @@
 
 namespace cimba_b200 {
 
-enum : uint32_t { ACT_WAKE_INTERRUPT = 4u, ACT_USER = 5u };
+enum : uint32_t { ACT_WAKE_INTERRUPT = 4u, ACT_USER = 5u,
+                  ACT_WAKE_PREEMPT = 6u };       // wakeup_event_preempt, src/cmb_resource.c:256-268
 enum : uint32_t { AWAIT_TIME = 0u, AWAIT_RESOURCE = 1u };
 enum : uint32_t { PROC_CREATED = 0u, PROC_RUNNING = 1u, PROC_FINISHED = 2u };
 
@@ -242,12 +243,13 @@ struct GenProc {                // struct cmb_process (include/cmb_process.h:116
     double   stamp;
     // resource-pool bookkeeping of the process body (model 4)
     uint32_t holds_pool;        // a cmi_process_holdable tag for the pool is on its resources list
+    uint32_t holds_tool;        // ... for the binary cmb_resource (model 5)
     uint32_t held, req, rem, initially_held;
 };
 
 struct GeneralState {
     EventHeap fel;
-    GuardHeap guard[2];         // 0 = front (getters wait here), 1 = rear (putters)
+    GuardHeap guard[3];         // 0 = front (getters wait here), 1 = rear (putters), 2 = binary resource
     GenProc   proc[GEN_MAX_PROCS];
     double    ring[16];
     uint32_t  ring_cap, ring_head, ring_len;
@@ -256,7 +258,12 @@ struct GeneralState {
     // cmb_resourcepool (model 4): guard[0] is its guard
     HolderHeap holders;
     uint32_t  pool_cap, pool_in_use;
+    // cmb_buffer (guards 0/1) and cmb_resource (guard 2), model 5
+    uint32_t  buf_cap, buf_level;
+    uint32_t  tool_holder;      // process index, or NO_HOLDER
 };
+
+constexpr uint32_t NO_HOLDER = 0xffffffffu;
 
 struct GeneralSim {
     GeneralState *st;
@@ -413,6 +420,11 @@ struct GeneralSim {
         if (p.holds_pool) {                                     // cmi_process_drop_resources, :507-527
             p.holds_pool = 0u;
             pool_drop_holder(pid);
+        }
+        if (p.holds_tool) {                                     // resource_drop_holder, src/cmb_resource.c:45-56
+            p.holds_tool = 0u;
+            st->tool_holder = NO_HOLDER;
+            signal(2u, true);
         }
     }
 

@@ -157,6 +157,9 @@ guarded_kernel(const GuardedArgs a)
     st->fel.clear();
     st->guard[0].clear();
     st->guard[1].clear();
+    st->guard[2].clear();
+    st->tool_holder = NO_HOLDER;
+    st->buf_cap = st->buf_level = 0u;
     st->ring_cap = (uint32_t)a.capacity;
     st->ring_head = 0u;
     st->ring_len = 0u;
@@ -173,7 +176,7 @@ guarded_kernel(const GuardedArgs a)
         p.hold_handle = 0u;
         p.guard_key = 0u;
         p.stamp = 0.0;
-        p.holds_pool = p.held = p.req = p.rem = p.initially_held = 0u;
+        p.holds_pool = p.holds_tool = p.held = p.req = p.rem = p.initially_held = 0u;
         p.kind = (i < GUARDED_PUTTERS) ? 0u : (i < GUARDED_WORKERS) ? 1u : 2u;
         p.prio = (i < GUARDED_WORKERS) ? (int32_t)s.rng.dice(-5, 5) : 0;
         s.schedule(ACT_START, i, 0, s.now, p.prio);     // cmb_process_start

@@ -207,6 +207,9 @@ preempt_kernel(const GuardedArgs a)
     st->fel.clear();
     st->guard[0].clear();
     st->guard[1].clear();
+    st->guard[2].clear();
+    st->tool_holder = NO_HOLDER;
+    st->buf_cap = st->buf_level = 0u;
     st->holders.clear();
     st->pool_cap = (uint32_t)a.capacity;
     st->pool_in_use = 0u;
@@ -223,7 +226,7 @@ preempt_kernel(const GuardedArgs a)
         p.n_awaits = 0u;
         p.hold_handle = p.guard_key = 0u;
         p.stamp = 0.0;
-        p.holds_pool = p.held = p.req = p.rem = p.initially_held = 0u;
+        p.holds_pool = p.holds_tool = p.held = p.req = p.rem = p.initially_held = 0u;
         p.prio = (i < PREEMPT_RODENTS) ? (int32_t)s.rng.dice(-5, 5) : 0;
         s.schedule(ACT_START, i, 0, s.now, p.prio);
     }

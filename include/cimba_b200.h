@@ -48,6 +48,8 @@ extern "C" {
                                     * an end event at t = num_objects stopping everybody (general cancel/interrupt path) */
 #define CIMBA_B200_MODEL_PREEMPT 4 /* test/test_resourcepool.c: 3 mice (priority_set + acquire), 2 rats (pre-empt), a cat
                                     * interrupting them, on a cmb_resourcepool of `servers` units; end event at t = num_objects */
+#define CIMBA_B200_MODEL_BUFFER 5  /* test/test_buffer.c + test/test_resource.c: 2 fillers + 2 drainers on a cmb_buffer of capacity
+                                    * `servers`, a polite and a pre-empting worker on one cmb_resource, a nuisance; end at t = num_objects */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -1794,6 +1794,297 @@ static void run_preempt(int capacity, uint64_t seed, uint64_t duration, uint64_t
     free(w);
 }
 
+/* ======================================== model 5: buffer + binary resource
+ *
+ * cmb_buffer_get / cmb_buffer_put with partial fulfilment (src/cmb_buffer.c:194-264,
+ * 279-346) and cmb_resource acquire / release / preempt with its wake-up event and
+ * drop handler (src/cmb_resource.c:45-56, 182-320).  Workload: ref_driver.c model 5.
+ */
+enum { ACT_WAKE_PREEMPT = 6 };
+#define B_PROCS 6
+
+typedef struct bproc {
+    gproc    g;
+    bool     holds_tool;
+    uint64_t want, rem, moved;
+    double   since;
+} bproc;
+
+typedef struct bsim {
+    gsim     s;                 /* s.front / s.rear are the buffer's guards */
+    heap     tool_guard;
+    bproc   *tool_holder;
+    uint64_t cap, level;
+    double   put_mean, get_mean;
+    bproc    proc[B_PROCS + 1];
+} bsim;
+
+static void b_note(bsim *w, int64_t sig)
+{
+    if (sig != SIG_SUCCESS) {
+        w->s.res->counter[6] += (uint64_t)sig;
+    }
+}
+
+static void b_body(bsim *w, bproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    const int id = (int)(p - w->proc);
+    switch (p->g.pc) {
+    case 0:
+        if (id == B_PROCS) {                            /* nuisance */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+                p->g.pc = 10;
+                return;
+    case 10:
+                (void)g_hold_end(s, &p->g, sig);
+                {
+                    const long victim = port_dice(&s->rng, 0, B_PROCS - 1);
+                    const int64_t isig = port_dice(&s->rng, 1, 10);
+                    const int64_t ipri = port_dice(&s->rng, -5, 5);
+                    g_schedule(s, ACT_WAKE_INTERRUPT, &w->proc[victim], isig, s->now, ipri);
+                }
+            }
+        }
+        if (id < 2) {                                   /* filler */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, w->put_mean));
+                p->g.pc = 20;
+                return;
+    case 20:
+                b_note(w, g_hold_end(s, &p->g, sig));
+                p->want = (uint64_t)port_dice(&s->rng, 1, 8);
+                p->rem = p->want;                       /* cmb_buffer_put: *amntp and rem_claim move together */
+                for (;;) {
+                    if (w->cap - w->level >= p->rem) {
+                        w->level += p->rem;
+                        p->rem = 0u;
+                        g_signal(s, &s->front, w->level > 0u);
+                        if (w->level < w->cap) {
+                            g_signal(s, &s->rear, w->level < w->cap);
+                        }
+                        sig = SIG_SUCCESS;
+                        break;
+                    }
+                    else if (w->level < w->cap) {
+                        const uint64_t grab = w->cap - w->level;
+                        w->level = w->cap;
+                        p->rem -= grab;
+                        g_signal(s, &s->front, w->level > 0u);
+                    }
+                    g_signal(s, &s->front, w->level > 0u);
+                    g_wait_begin(s, &s->rear, &p->g);
+                    p->g.pc = 21;
+                    return;
+    case 21:
+                    sig = g_wait_end(s, &s->rear, &p->g, sig);
+                    if (sig != SIG_SUCCESS) {
+                        break;
+                    }
+                }
+                s->res->counter[0] += p->want - p->rem;
+                if (sig != SIG_SUCCESS) {
+                    s->res->counter[2] += 1u;
+                    b_note(w, sig);
+                }
+            }
+        }
+        if (id < 4) {                                   /* drainer */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, w->get_mean));
+                p->g.pc = 30;
+                return;
+    case 30:
+                b_note(w, g_hold_end(s, &p->g, sig));
+                p->rem = (uint64_t)port_dice(&s->rng, 1, 8);
+                p->moved = 0u;
+                for (;;) {                              /* cmb_buffer_get */
+                    if (w->level >= p->rem) {
+                        w->level -= p->rem;
+                        p->moved += p->rem;
+                        g_signal(s, &s->rear, w->level < w->cap);
+                        if (w->level > 0u) {
+                            g_signal(s, &s->front, w->level > 0u);
+                        }
+                        sig = SIG_SUCCESS;
+                        break;
+                    }
+                    else if (w->level > 0u) {
+                        const uint64_t grab = w->level;
+                        w->level = 0u;
+                        p->moved += grab;
+                        p->rem -= grab;
+                        g_signal(s, &s->rear, w->level < w->cap);
+                    }
+                    g_signal(s, &s->rear, w->level < w->cap);
+                    g_wait_begin(s, &s->front, &p->g);
+                    p->g.pc = 31;
+                    return;
+    case 31:
+                    sig = g_wait_end(s, &s->front, &p->g, sig);
+                    if (sig != SIG_SUCCESS) {
+                        break;
+                    }
+                }
+                s->res->counter[1] += p->moved;
+                if (sig != SIG_SUCCESS) {
+                    s->res->counter[3] += 1u;
+                    b_note(w, sig);
+                }
+            }
+        }
+        for (;;) {                                      /* workers 4 (polite) and 5 (pushy) */
+            if (id == 5 && w->tool_holder != NULL && p->g.prio >= w->tool_holder->g.prio) {
+                /* cmb_resource_preempt, kick-out branch (src/cmb_resource.c:282-299) */
+                bproc *victim = w->tool_holder;
+                victim->holds_tool = false;
+                g_cancel_awaiteds(s, &p->g);            /* sic: the CALLER's awaiteds */
+                w->tool_holder = NULL;
+                g_schedule(s, ACT_WAKE_PREEMPT, victim, SIG_PREEMPTED, s->now, victim->g.prio);
+                w->tool_holder = p;
+                p->holds_tool = true;
+                sig = SIG_SUCCESS;
+            }
+            else if (w->tool_holder == NULL) {          /* free: grab (acquire :196-203, preempt :277-281) */
+                w->tool_holder = p;
+                p->holds_tool = true;
+                sig = SIG_SUCCESS;
+            }
+            else {                                      /* wait politely (:206-222) */
+                g_wait_begin(s, &w->tool_guard, &p->g);
+                p->g.pc = 40;
+                return;
+    case 40:
+                sig = g_wait_end(s, &w->tool_guard, &p->g, sig);
+                if (sig == SIG_SUCCESS) {
+                    w->tool_holder = p;
+                    p->holds_tool = true;
+                }
+            }
+            if (sig == SIG_SUCCESS) {
+                s->res->counter[4] += 1u;
+                p->since = s->now;
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+                p->g.pc = 41;
+                return;
+    case 41:
+                sig = g_hold_end(s, &p->g, sig);
+                if (sig == SIG_PREEMPTED) {
+                    s->res->counter[5] += 1u;
+                    b_note(w, sig);
+                }
+                else {
+                    b_note(w, sig);
+                    p->holds_tool = false;              /* cmb_resource_release, :234-250 */
+                    w->tool_holder = NULL;
+                    g_signal(s, &w->tool_guard, w->tool_holder == NULL);
+                    s->res->sum_wait += s->now - p->since;
+                }
+            }
+            else {
+                b_note(w, sig);
+            }
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 42;
+            return;
+    case 42:
+            b_note(w, g_hold_end(s, &p->g, sig));
+        }
+    }
+}
+
+static void b_stop(bsim *w, bproc *p)
+{
+    if (p->g.status != ST_RUNNING) {
+        return;
+    }
+    p->g.status = ST_FINISHED;
+    g_cancel_awaiteds(&w->s, &p->g);
+    if (p->holds_tool) {                                /* resource_drop_holder, :45-56 */
+        p->holds_tool = false;
+        w->tool_holder = NULL;
+        g_signal(&w->s, &w->tool_guard, true);
+    }
+}
+
+static void run_buffer(int capacity, uint64_t seed, uint64_t duration, double put_mean, double get_mean,
+                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    bsim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    w->put_mean = put_mean;
+    w->get_mean = get_mean;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&s->front, 3u, guard_before);
+    heap_init(&s->rear, 3u, guard_before);
+    heap_init(&w->tool_guard, 3u, guard_before);
+    w->cap = (uint64_t)capacity;
+
+    for (int i = 0; i < B_PROCS; i++) {
+        w->proc[i].g.prio = port_dice(&s->rng, -5, 5);
+        g_schedule(s, ACT_START, &w->proc[i], 0, s->now, w->proc[i].g.prio);
+    }
+    g_schedule(s, ACT_START, &w->proc[B_PROCS], 0, s->now, 0);
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        bproc *p = (bproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->g.status = ST_RUNNING;
+            p->g.pc = 0;
+            b_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(&p->g, AW_TIME, false, ev.key, NULL);
+            b_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+        case ACT_WAKE_PREEMPT:                          /* src/cmb_resource.c:256-268: no cancel_awaiteds */
+            if (p->g.status == ST_RUNNING) {
+                b_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_INTERRUPT:
+            g_cancel_awaiteds(s, &p->g);
+            b_body(w, p, ev.item[2]);
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i <= B_PROCS; i++) {
+                b_stop(w, &w->proc[i]);
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->counter[7] = w->level;
+    out->objects = out->counter[1];
+    heap_free(&s->fel);
+    heap_free(&s->front);
+    heap_free(&s->rear);
+    heap_free(&w->tool_guard);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -1811,6 +2102,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 5) {
+            run_buffer(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 4) {
             run_preempt(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -1854,6 +2150,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 5) {
+        run_buffer(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 4) {
         run_preempt(servers, seed, num_objects, trace_cap, trace_key, trace_time, out);
         return 0;

@@ -455,6 +455,150 @@ static void run_preempt_trial(struct ref_trial *t)
     free(w);
 }
 
+
+/* ------------------------------------------------- model 5: buffer + binary resource
+ *
+ * cmb_buffer with partial fulfilment (src/cmb_buffer.c:194-346) and cmb_resource with
+ * pre-emption (src/cmb_resource.c:182-320), driven like the reference's own
+ * test/test_buffer.c and test/test_resource.c: two fillers and two drainers moving
+ * random amounts through a buffer of capacity `servers`, one polite and one
+ * pre-empting worker sharing a binary resource, a nuisance interrupting all six,
+ * an end event stopping everybody.
+ * counters: [0] units put [1] units got [2] interrupted puts [3] interrupted gets
+ *           [4] resource acquisitions [5] PREEMPTED received [6] sum of signals
+ *           [7] final buffer level
+ * sum_wait = sum over completed resource tenures of their length
+ */
+#define B_PROCS 6u
+
+struct b_world {
+    struct ref_trial *trl;
+    struct cmb_buffer *buffer;
+    struct cmb_resource *tool;
+    struct cmb_process *proc;           /* B_PROCS + 1 contiguous */
+};
+
+static void b_note(struct b_world *w, int64_t sig)
+{
+    if (sig != CMB_PROCESS_SUCCESS) {
+        w->trl->counter[6] += (uint64_t)sig;
+    }
+}
+
+static void *b_filler_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct b_world *w = vw;
+    for (;;) {
+        b_note(w, cmb_process_hold(cmb_random_exponential(w->trl->arr_mean)));
+        const uint64_t want = (uint64_t)cmb_random_dice(1, 8);
+        uint64_t amount = want;
+        const int64_t sig = cmb_buffer_put(w->buffer, &amount);
+        w->trl->counter[0] += want - amount;
+        if (sig != CMB_PROCESS_SUCCESS) {
+            w->trl->counter[2] += 1u;
+            b_note(w, sig);
+        }
+    }
+}
+
+static void *b_drainer_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct b_world *w = vw;
+    for (;;) {
+        b_note(w, cmb_process_hold(cmb_random_exponential(w->trl->srv_mean)));
+        uint64_t amount = (uint64_t)cmb_random_dice(1, 8);
+        const int64_t sig = cmb_buffer_get(w->buffer, &amount);
+        w->trl->counter[1] += amount;
+        if (sig != CMB_PROCESS_SUCCESS) {
+            w->trl->counter[3] += 1u;
+            b_note(w, sig);
+        }
+    }
+}
+
+static void *b_worker_body(struct cmb_process *me, void *vw)
+{
+    struct b_world *w = vw;
+    const bool pushy = (me == &w->proc[5]);
+    for (;;) {
+        int64_t sig = pushy ? cmb_resource_preempt(w->tool) : cmb_resource_acquire(w->tool);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[4] += 1u;
+            const double since = cmb_time();
+            sig = cmb_process_hold(cmb_random_exponential(1.0));
+            if (sig == CMB_PROCESS_PREEMPTED) {
+                w->trl->counter[5] += 1u;
+                b_note(w, sig);
+            }
+            else {
+                b_note(w, sig);
+                cmb_resource_release(w->tool);
+                w->trl->sum_wait += cmb_time() - since;
+            }
+        }
+        else {
+            b_note(w, sig);
+        }
+        b_note(w, cmb_process_hold(cmb_random_exponential(1.0)));
+    }
+}
+
+static void *b_nuisance_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct b_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)B_PROCS - 1);
+        const int64_t sig = cmb_random_dice(1, 10);
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_interrupt(&w->proc[victim], sig, pri);
+    }
+}
+
+static void b_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct b_world *w = subject;
+    for (unsigned i = 0u; i <= B_PROCS; i++) {
+        cmb_process_stop(&w->proc[i], NULL);
+    }
+}
+
+static void run_buffer_trial(struct ref_trial *t)
+{
+    struct b_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->buffer = cmb_buffer_create();
+    cmb_buffer_initialize(w->buffer, "Buffer", (uint64_t)t->servers);
+    w->tool = cmb_resource_create();
+    cmb_resource_initialize(w->tool, "Tool");
+    w->proc = calloc(B_PROCS + 1u, sizeof(struct cmb_process));
+    for (unsigned i = 0u; i < B_PROCS; i++) {
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_initialize(&w->proc[i], "Proc",
+                               (i < 2u) ? b_filler_body : (i < 4u) ? b_drainer_body : b_worker_body, w, pri);
+        cmb_process_start(&w->proc[i]);
+    }
+    cmb_process_initialize(&w->proc[B_PROCS], "Nuisance", b_nuisance_body, w, 0);
+    cmb_process_start(&w->proc[B_PROCS]);
+    (void)cmb_event_schedule(b_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->counter[7] = cmb_buffer_level(w->buffer);
+    t->objects = t->counter[1];
+    for (unsigned i = 0u; i <= B_PROCS; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    cmb_resource_destroy(w->tool);
+    cmb_buffer_destroy(w->buffer);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -537,7 +681,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 4) {
+    if (t->model == 5) {
+        run_buffer_trial(t);
+    }
+    else if (t->model == 4) {
         run_preempt_trial(t);
     }
     else if (t->model == 3) {

@@ -30,7 +30,8 @@ RNG_KINDS = {0: (0.0, 0.0), 1: (1.0, 0.0), 2: (0.0, 0.0), 3: (0.0, 0.0), 4: (1.0
 MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, servers=1),
           2: dict(arr=1 / 6.4, srv=1.0, servers=8),
           3: dict(arr=1.0, srv=1.0, servers=10),     # model 3: num_objects = duration, servers = queue capacity
-          4: dict(arr=1.0, srv=1.0, servers=20)}     # model 4: num_objects = duration, servers = pool capacity
+          4: dict(arr=1.0, srv=1.0, servers=20),     # model 4: num_objects = duration, servers = pool capacity
+          5: dict(arr=1.0, srv=1.0, servers=10)}     # model 5: num_objects = duration, servers = buffer capacity
 
 
 def hexes(a):

@@ -332,3 +332,27 @@ def test_pool_preemption_pop_order_bit_exact(cb, port):
         m = min(cap, r.events)
         assert list(keys[i, :m]) == k, i
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+@pytest.mark.parametrize("cap,dur,pm,gm", [(10, 500, 1.0, 1.0), (3, 400, 0.5, 1.0), (1, 300, 1.0, 0.6), (30, 300, 0.3, 0.3)])
+def test_buffer_and_resource_match_oracle(cb, port, cap, dur, pm, gm):
+    """cmb_buffer partial get/put + cmb_resource acquire/release/preempt under interrupts."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=pm, srv_mean=gm, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_BUFFER, servers=cap)
+    want = run_trials(port, "port", 5, cap, KAT_SEED, 0, n, dur, pm, gm)
+    _compare(res, want, ("buffer", cap))
+    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+
+
+def test_buffer_and_resource_pop_order_bit_exact(cb, port):
+    n, cap, dur = 16, 8000, 500
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=6,
+                        model=cb.MODEL_BUFFER, servers=5, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 5, 5, cb.fmix64(6, i), dur, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
