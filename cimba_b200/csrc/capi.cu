@@ -21,6 +21,7 @@
 #include "guarded_model.cuh"
 #include "preempt_model.cuh"
 #include "buffer_model.cuh"
+#include "prioq_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -123,7 +124,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
     if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT ||
-        job->model == CIMBA_B200_MODEL_BUFFER) {
+        job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_PRIOQ) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
     }
     return 0u;
@@ -220,10 +221,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
     }
     if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT ||
-        job->model == CIMBA_B200_MODEL_BUFFER) {
+        job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_PRIOQ) {
+        const bool prq = job->model == CIMBA_B200_MODEL_PRIOQ;
         const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
         const bool buf = job->model == CIMBA_B200_MODEL_BUFFER;
-        if (job->servers < 1 || (!pre && !buf && job->servers > 16))
+        if (job->servers < 1 || (!pre && !buf && job->servers > (prq ? 15 : 16)))
             return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1 (and <= 16 for CIMBA_B200_MODEL_GUARDED)");
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -249,7 +251,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.trace_time = job->trace_time;
         const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
-        if (buf) {
+        if (prq) {
+            if (trace) prioq_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+            else       prioq_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        else if (buf) {
             if (trace) buffer_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
             else       buffer_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
         }

@@ -32,7 +32,8 @@
 namespace cimba_b200 {
 
 enum : uint32_t { ACT_WAKE_INTERRUPT = 4u, ACT_USER = 5u,
-                  ACT_WAKE_PREEMPT = 6u };       // wakeup_event_preempt, src/cmb_resource.c:256-268
+                  ACT_WAKE_PREEMPT = 6u,         // wakeup_event_preempt, src/cmb_resource.c:256-268
+                  ACT_WAKE_CONDITION = 7u };     // wakeup_event_condition, src/cmb_condition.c:85-103
 enum : uint32_t { AWAIT_TIME = 0u, AWAIT_RESOURCE = 1u };
 enum : uint32_t { PROC_CREATED = 0u, PROC_RUNNING = 1u, PROC_FINISHED = 2u };
 
@@ -78,6 +79,15 @@ struct HolderOrder {
         if (a.prio < b.prio) return true;
         if (a.prio == b.prio && a.key > b.key) return true;
         return false;
+    }
+};
+
+// compare_func of cmb_priorityqueue, src/cmb_priorityqueue.c:43-54: priority desc, then FIFO
+struct PrioOrder {
+    static __device__ __forceinline__ bool before(const HeapTag &a, const HeapTag &b)
+    {
+        if (a.prio != b.prio) return a.prio > b.prio;
+        return a.key < b.key;
     }
 };
 
@@ -232,6 +242,7 @@ constexpr int GEN_MAX_AWAITS = 4;
 using EventHeap = BinHeap<GEN_FEL_CAP, EventOrder>;
 using GuardHeap = BinHeap<GEN_GUARD_CAP, GuardOrder>;
 using HolderHeap = BinHeap<GEN_MAX_PROCS, HolderOrder>;     // tag.subj = holder, tag.arg = amount held
+using PrioHeap = BinHeap<GEN_GUARD_CAP, PrioOrder>;         // tag.arg = the queued object (a small integer)
 
 struct GenProc {                // struct cmb_process (include/cmb_process.h:116-123), the parts that act
     uint32_t pc, status, kind;
@@ -261,6 +272,11 @@ struct GeneralState {
     // cmb_buffer (guards 0/1) and cmb_resource (guard 2), model 5
     uint32_t  buf_cap, buf_level;
     uint32_t  tool_holder;      // process index, or NO_HOLDER
+    // cmb_priorityqueue (guards 0/1) and cmb_condition (guard 2), model 6
+    PrioHeap  pq;
+    uint32_t  pq_cap;
+    uint32_t  last_handle[2];
+    int32_t   level;
 };
 
 constexpr uint32_t NO_HOLDER = 0xffffffffu;
@@ -285,6 +301,22 @@ struct GeneralSim {
         p.await_type[0] = type;
         p.await_ref[0] = ref;
         p.n_awaits++;
+    }
+
+    // cmi_process_remove_awaitable(pp, type, NULL): first entry of that type, any value
+    __device__ bool await_remove_any(GenProc &p, uint32_t type)
+    {
+        for (uint32_t k = 0u; k < p.n_awaits; k++) {
+            if (p.await_type[k] == type) {
+                for (uint32_t m = k; m + 1u < p.n_awaits; m++) {
+                    p.await_type[m] = p.await_type[m + 1u];
+                    p.await_ref[m] = p.await_ref[m + 1u];
+                }
+                p.n_awaits--;
+                return true;
+            }
+        }
+        return false;
     }
 
     __device__ bool await_remove(GenProc &p, uint32_t type, uint32_t ref)

@@ -2085,6 +2085,333 @@ static void run_buffer(int capacity, uint64_t seed, uint64_t duration, double pu
     free(w);
 }
 
+/* ======================================== model 6: priority queue + condition
+ *
+ * cmb_priorityqueue_put/get (src/cmb_priorityqueue.c:189-284), position (:286-320),
+ * cancel / reprioritize by handle (include/cmb_priorityqueue.h:152-185), the queue's
+ * order (:43-54); cmb_condition_wait / signal with its two passes over the guard in
+ * array order and its own wake-up event (src/cmb_condition.c:63-167).
+ * Workload: ref_driver.c model 6.
+ */
+enum { ACT_WAKE_CONDITION = 7 };
+#define C_PROCS 7
+
+/* src/cmb_priorityqueue.c:43-54 */
+static bool prioq_before(const heap_tag *a, const heap_tag *b)
+{
+    if (a->i != b->i) {
+        return a->i > b->i;
+    }
+    return a->key < b->key;
+}
+
+typedef struct cproc {
+    gproc    g;
+    uint64_t handle;
+    int64_t  weight, pri;
+} cproc;
+
+typedef struct csim {
+    gsim     s;                 /* s.front / s.rear guard the priority queue */
+    heap     pq, cv;            /* cv = the condition's guard */
+    uint64_t cap;
+    uint64_t last_handle[2];
+    long     level, threshold[2];
+    double   put_mean, get_mean;
+    cproc    proc[C_PROCS + 1];
+} csim;
+
+static void c_note(csim *w, int64_t sig)
+{
+    if (sig != SIG_SUCCESS) {
+        w->s.res->counter[6] += (uint64_t)sig;
+    }
+}
+
+/* cmb_condition_signal, src/cmb_condition.c:120-167 */
+static uint64_t c_condition_signal(csim *w)
+{
+    gsim *s = &w->s;
+    uint64_t hit[16];
+    uint64_t cnt = 0u;
+    for (uint64_t k = 1u; k <= w->cv.count; k++) {
+        cproc *p = (cproc *)(intptr_t)w->cv.slot[k].item[0];
+        const long thr = w->threshold[(p - w->proc) - 5];
+        if (w->level >= thr) {
+            hit[cnt++] = w->cv.slot[k].key;
+            g_schedule(s, ACT_WAKE_CONDITION, p, SIG_SUCCESS, s->now, p->g.prio);
+        }
+    }
+    for (uint64_t k = 0u; k < cnt; k++) {
+        heap_remove(&w->cv, hit[k]);
+    }
+    return cnt;
+}
+
+/* cmb_priorityqueue_position, src/cmb_priorityqueue.c:286-320 */
+static uint64_t c_position(csim *w, uint64_t handle)
+{
+    uint64_t at = 0u;
+    for (uint64_t k = 1u; k <= w->pq.count; k++) {
+        if (w->pq.slot[k].key == handle) {
+            at = k;
+            break;
+        }
+    }
+    if (at == 0u) {
+        return 0u;
+    }
+    uint64_t ahead = 0u;
+    for (uint64_t k = 1u; k <= w->pq.count; k++) {
+        if (k != at && prioq_before(&w->pq.slot[k], &w->pq.slot[at])) {
+            ahead++;
+        }
+    }
+    return ahead + 1u;
+}
+
+static void c_body(csim *w, cproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    const int id = (int)(p - w->proc);
+    switch (p->g.pc) {
+    case 0:
+        if (id == C_PROCS) {                            /* nuisance */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+                p->g.pc = 10;
+                return;
+    case 10:
+                (void)g_hold_end(s, &p->g, sig);
+                {
+                    const long victim = port_dice(&s->rng, 0, C_PROCS - 1);
+                    const int64_t isig = port_dice(&s->rng, 1, 10);
+                    const int64_t ipri = port_dice(&s->rng, -5, 5);
+                    g_schedule(s, ACT_WAKE_INTERRUPT, &w->proc[victim], isig, s->now, ipri);
+                }
+            }
+        }
+        if (id < 2) {                                   /* producer */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, w->put_mean));
+                p->g.pc = 20;
+                return;
+    case 20:
+                c_note(w, g_hold_end(s, &p->g, sig));
+                p->weight = port_dice(&s->rng, 1, 9);
+                p->pri = port_dice(&s->rng, -3, 3);
+                for (;;) {                              /* cmb_priorityqueue_put */
+                    if (w->pq.count < w->cap) {
+                        p->handle = heap_push(&w->pq, 0u, 0.0, p->pri, p->weight, 0, 0);
+                        g_signal(s, &s->front, w->pq.count > 0u);
+                        sig = SIG_SUCCESS;
+                        break;
+                    }
+                    g_wait_begin(s, &s->rear, &p->g);
+                    p->g.pc = 21;
+                    return;
+    case 21:
+                    sig = g_wait_end(s, &s->rear, &p->g, sig);
+                    if (sig != SIG_SUCCESS) {
+                        break;
+                    }
+                }
+                if (sig == SIG_SUCCESS) {
+                    s->res->counter[0] += 1u;
+                    w->last_handle[id] = p->handle;
+                }
+                else {
+                    s->res->counter[2] += 1u;
+                    c_note(w, sig);
+                }
+            }
+        }
+        if (id == 2) {                                  /* consumer */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, w->get_mean));
+                p->g.pc = 30;
+                return;
+    case 30:
+                c_note(w, g_hold_end(s, &p->g, sig));
+                for (;;) {                              /* cmb_priorityqueue_get */
+                    if (w->pq.count > 0u) {
+                        heap_pop(&w->pq);
+                        p->weight = w->pq.slot[0].item[0];
+                        g_signal(s, &s->rear, w->pq.count < w->cap);
+                        sig = SIG_SUCCESS;
+                        break;
+                    }
+                    g_wait_begin(s, &s->front, &p->g);
+                    p->g.pc = 31;
+                    return;
+    case 31:
+                    sig = g_wait_end(s, &s->front, &p->g, sig);
+                    if (sig != SIG_SUCCESS) {
+                        break;
+                    }
+                }
+                if (sig == SIG_SUCCESS) {
+                    s->res->counter[1] += (uint64_t)p->weight;
+                    s->res->sum_wait += s->now * (double)(uint64_t)p->weight;
+                }
+                else {
+                    s->res->counter[2] += 1u;
+                    c_note(w, sig);
+                }
+            }
+        }
+        if (id == 3) {                                  /* shuffler */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.5));
+                p->g.pc = 40;
+                return;
+    case 40:
+                c_note(w, g_hold_end(s, &p->g, sig));
+                {
+                    const uint64_t handle = w->last_handle[port_dice(&s->rng, 0, 1)];
+                    if (handle == 0u) {
+                        continue;
+                    }
+                    const uint64_t pos = c_position(w, handle);
+                    s->res->counter[3] += pos;
+                    if (pos > 0u) {
+                        if (port_dice(&s->rng, 0, 1) == 1) {
+                            heap_reprioritize(&w->pq, handle, 0.0, port_dice(&s->rng, -3, 3));
+                        }
+                        else {
+                            (void)heap_remove(&w->pq, handle);
+                            s->res->counter[3] += 1000u;
+                        }
+                    }
+                }
+            }
+        }
+        if (id == 4) {                                  /* tide */
+            for (;;) {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+                p->g.pc = 50;
+                return;
+    case 50:
+                c_note(w, g_hold_end(s, &p->g, sig));
+                w->level = port_dice(&s->rng, 0, 5);
+                s->res->counter[4] += c_condition_signal(w);
+            }
+        }
+        for (;;) {                                      /* waiters 5, 6 */
+            {
+                bool through = true;
+                while (w->level < w->threshold[id - 5]) {
+                    g_wait_begin(s, &w->cv, &p->g);     /* cmb_condition_wait = cmb_resourceguard_wait */
+                    p->g.pc = 60;
+                    return;
+    case 60:
+                    through = true;
+                    sig = g_wait_end(s, &w->cv, &p->g, sig);
+                    if (sig != SIG_SUCCESS) {
+                        c_note(w, sig);
+                        through = false;
+                        break;
+                    }
+                }
+                if (through) {
+                    s->res->counter[5] += 1u;
+                }
+            }
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 61;
+            return;
+    case 61:
+            c_note(w, g_hold_end(s, &p->g, sig));
+        }
+    }
+}
+
+static void run_prioq(int capacity, uint64_t seed, uint64_t duration, double put_mean, double get_mean,
+                      uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    csim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    w->put_mean = put_mean;
+    w->get_mean = get_mean;
+    w->threshold[0] = 2;
+    w->threshold[1] = 4;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&s->front, 3u, guard_before);
+    heap_init(&s->rear, 3u, guard_before);
+    heap_init(&w->cv, 3u, guard_before);
+    heap_init(&w->pq, 3u, prioq_before);
+    w->cap = (uint64_t)capacity;
+
+    for (int i = 0; i < C_PROCS; i++) {
+        w->proc[i].g.prio = port_dice(&s->rng, -5, 5);
+        g_schedule(s, ACT_START, &w->proc[i], 0, s->now, w->proc[i].g.prio);
+    }
+    g_schedule(s, ACT_START, &w->proc[C_PROCS], 0, s->now, 0);
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        cproc *p = (cproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->g.status = ST_RUNNING;
+            p->g.pc = 0;
+            c_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(&p->g, AW_TIME, false, ev.key, NULL);
+            c_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+            if (p->g.status == ST_RUNNING) {
+                c_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_CONDITION:                        /* src/cmb_condition.c:85-103 */
+            (void)aw_remove(&p->g, AW_RESOURCE, true, 0u, NULL);
+            if (p->g.status == ST_RUNNING) {
+                c_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_INTERRUPT:
+            g_cancel_awaiteds(s, &p->g);
+            c_body(w, p, ev.item[2]);
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i <= C_PROCS; i++) {
+                g_stop(s, &w->proc[i].g);
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->counter[7] = w->pq.count;
+    out->objects = out->counter[0];
+    heap_free(&s->fel);
+    heap_free(&s->front);
+    heap_free(&s->rear);
+    heap_free(&w->cv);
+    heap_free(&w->pq);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -2102,6 +2429,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 6) {
+            run_prioq(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                      j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 5) {
             run_buffer(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -2150,6 +2482,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 6) {
+        run_prioq(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 5) {
         run_buffer(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;

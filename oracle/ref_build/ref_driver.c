@@ -28,6 +28,8 @@
 #include <string.h>
 
 #include <cimba.h>
+#include <cmb_priorityqueue.h>
+#include <cmb_condition.h>
 
 #include "cmi_mempool.h"
 
@@ -599,6 +601,205 @@ static void run_buffer_trial(struct ref_trial *t)
     free(w);
 }
 
+
+/* ------------------------------------------------- model 6: priority queue + condition
+ *
+ * cmb_priorityqueue put/get/position/cancel/reprioritize (src/cmb_priorityqueue.c:189-320,
+ * include/cmb_priorityqueue.h:152-185) and cmb_condition wait/signal with user
+ * predicates (src/cmb_condition.c:63-167), in the manner of test/test_priorityqueue.c
+ * and test/test_condition.c: two producers and a consumer on a bounded priority
+ * queue, a shuffler that looks up / re-ranks / withdraws queued items by handle, a
+ * tide process that changes a level and signals a condition two waiters watch with
+ * different thresholds, a nuisance interrupting all seven, an end event.
+ * Objects are small integers ("weights") smuggled through the void * payload.
+ * counters: [0] puts ok [1] weight received [2] interrupted puts + gets
+ *           [3] sum of positions + 1000 * items withdrawn [4] condition wake-ups issued
+ *           [5] waiter passes [6] sum of signals [7] final queue length
+ * sum_wait = sum over gets of cmb_time() * weight
+ */
+#define C_PROCS 7u
+
+struct c6_world {
+    struct ref_trial *trl;
+    struct cmb_priorityqueue *pq;
+    struct cmb_condition *cv;
+    struct cmb_process *proc;           /* C_PROCS + 1 contiguous */
+    uint64_t last_handle[2];
+    long level;
+    long threshold[2];
+};
+
+static void c6_note(struct c6_world *w, int64_t sig)
+{
+    if (sig != CMB_PROCESS_SUCCESS) {
+        w->trl->counter[6] += (uint64_t)sig;
+    }
+}
+
+static void *c6_producer_body(struct cmb_process *me, void *vw)
+{
+    struct c6_world *w = vw;
+    const unsigned self = (unsigned)(me - w->proc);
+    for (;;) {
+        c6_note(w, cmb_process_hold(cmb_random_exponential(w->trl->arr_mean)));
+        const long weight = cmb_random_dice(1, 9);
+        const int64_t pri = cmb_random_dice(-3, 3);
+        uint64_t handle = 0u;
+        const int64_t sig = cmb_priorityqueue_put(w->pq, (void *)(uintptr_t)weight, pri, &handle);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[0] += 1u;
+            w->last_handle[self] = handle;
+        }
+        else {
+            w->trl->counter[2] += 1u;
+            c6_note(w, sig);
+        }
+    }
+}
+
+static void *c6_consumer_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct c6_world *w = vw;
+    for (;;) {
+        c6_note(w, cmb_process_hold(cmb_random_exponential(w->trl->srv_mean)));
+        void *obj = NULL;
+        const int64_t sig = cmb_priorityqueue_get(w->pq, &obj);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            const uint64_t weight = (uint64_t)(uintptr_t)obj;
+            w->trl->counter[1] += weight;
+            w->trl->sum_wait += cmb_time() * (double)weight;
+        }
+        else {
+            w->trl->counter[2] += 1u;
+            c6_note(w, sig);
+        }
+    }
+}
+
+static void *c6_shuffler_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct c6_world *w = vw;
+    for (;;) {
+        c6_note(w, cmb_process_hold(cmb_random_exponential(1.5)));
+        const uint64_t handle = w->last_handle[cmb_random_dice(0, 1)];
+        if (handle == 0u) {
+            continue;
+        }
+        const uint64_t pos = cmb_priorityqueue_position(w->pq, handle);
+        w->trl->counter[3] += pos;
+        if (pos > 0u) {
+            if (cmb_random_dice(0, 1) == 1) {
+                cmb_priorityqueue_reprioritize(w->pq, handle, cmb_random_dice(-3, 3));
+            }
+            else {
+                (void)cmb_priorityqueue_cancel(w->pq, handle);
+                w->trl->counter[3] += 1000u;
+            }
+        }
+    }
+}
+
+static void *c6_tide_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct c6_world *w = vw;
+    for (;;) {
+        c6_note(w, cmb_process_hold(cmb_random_exponential(1.0)));
+        w->level = cmb_random_dice(0, 5);
+        w->trl->counter[4] += cmb_condition_signal(w->cv);
+    }
+}
+
+static bool c6_high_enough(const struct cmb_condition *cvp, const struct cmb_process *pp, const void *ctx)
+{
+    cmb_unused(pp);
+    cmb_unused(cvp);
+    const struct c6_world *w = *(struct c6_world *const *)ctx;
+    const long *thr = ((const long *const *)ctx)[1];
+    return w->level >= *thr;
+}
+
+static void *c6_waiter_body(struct cmb_process *me, void *vw)
+{
+    struct c6_world *w = vw;
+    const unsigned self = (unsigned)(me - w->proc) - 5u;
+    const void *ctx[2] = { w, &w->threshold[self] };
+    for (;;) {
+        bool through = true;
+        while (w->level < w->threshold[self]) {
+            const int64_t sig = cmb_condition_wait(w->cv, c6_high_enough, ctx);
+            if (sig != CMB_PROCESS_SUCCESS) {
+                c6_note(w, sig);
+                through = false;
+                break;
+            }
+        }
+        if (through) {
+            w->trl->counter[5] += 1u;
+        }
+        c6_note(w, cmb_process_hold(cmb_random_exponential(1.0)));
+    }
+}
+
+static void *c6_nuisance_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct c6_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)C_PROCS - 1);
+        const int64_t sig = cmb_random_dice(1, 10);
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_interrupt(&w->proc[victim], sig, pri);
+    }
+}
+
+static void c6_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct c6_world *w = subject;
+    for (unsigned i = 0u; i <= C_PROCS; i++) {
+        cmb_process_stop(&w->proc[i], NULL);
+    }
+}
+
+static void run_prioq_trial(struct ref_trial *t)
+{
+    struct c6_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->pq = cmb_priorityqueue_create();
+    cmb_priorityqueue_initialize(w->pq, "PQ", (uint64_t)t->servers);
+    w->cv = cmb_condition_create();
+    cmb_condition_initialize(w->cv, "Tide");
+    w->threshold[0] = 2;
+    w->threshold[1] = 4;
+    w->proc = calloc(C_PROCS + 1u, sizeof(struct cmb_process));
+    cmb_process_func *body[C_PROCS] = { c6_producer_body, c6_producer_body, c6_consumer_body,
+                                        c6_shuffler_body, c6_tide_body, c6_waiter_body, c6_waiter_body };
+    for (unsigned i = 0u; i < C_PROCS; i++) {
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_initialize(&w->proc[i], "Proc", body[i], w, pri);
+        cmb_process_start(&w->proc[i]);
+    }
+    cmb_process_initialize(&w->proc[C_PROCS], "Nuisance", c6_nuisance_body, w, 0);
+    cmb_process_start(&w->proc[C_PROCS]);
+    (void)cmb_event_schedule(c6_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->counter[7] = cmb_priorityqueue_length(w->pq);
+    t->objects = t->counter[0];
+    for (unsigned i = 0u; i <= C_PROCS; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    cmb_condition_destroy(w->cv);
+    cmb_priorityqueue_destroy(w->pq);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -681,7 +882,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 5) {
+    if (t->model == 6) {
+        run_prioq_trial(t);
+    }
+    else if (t->model == 5) {
         run_buffer_trial(t);
     }
     else if (t->model == 4) {

@@ -31,7 +31,8 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           2: dict(arr=1 / 6.4, srv=1.0, servers=8),
           3: dict(arr=1.0, srv=1.0, servers=10),     # model 3: num_objects = duration, servers = queue capacity
           4: dict(arr=1.0, srv=1.0, servers=20),     # model 4: num_objects = duration, servers = pool capacity
-          5: dict(arr=1.0, srv=1.0, servers=10)}     # model 5: num_objects = duration, servers = buffer capacity
+          5: dict(arr=1.0, srv=1.0, servers=10),     # model 5: num_objects = duration, servers = buffer capacity
+          6: dict(arr=1.0, srv=1.0, servers=8)}      # model 6: num_objects = duration, servers = queue capacity
 
 
 def hexes(a):

@@ -356,3 +356,27 @@ def test_buffer_and_resource_pop_order_bit_exact(cb, port):
         m = min(cap, r.events)
         assert list(keys[i, :m]) == k, i
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+@pytest.mark.parametrize("cap,dur,pm,gm", [(8, 500, 1.0, 1.0), (2, 400, 0.5, 1.0), (1, 300, 1.0, 0.6), (12, 300, 0.3, 0.5)])
+def test_priorityqueue_and_condition_match_oracle(cb, port, cap, dur, pm, gm):
+    """cmb_priorityqueue put/get/position/reprioritize/cancel + cmb_condition wait/signal under interrupts."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=pm, srv_mean=gm, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_PRIOQ, servers=cap)
+    want = run_trials(port, "port", 6, cap, KAT_SEED, 0, n, dur, pm, gm)
+    _compare(res, want, ("prioq", cap))
+    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+
+
+def test_priorityqueue_and_condition_pop_order_bit_exact(cb, port):
+    n, cap, dur = 16, 8000, 500
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=66,
+                        model=cb.MODEL_PRIOQ, servers=6, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 6, 6, cb.fmix64(66, i), dur, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i

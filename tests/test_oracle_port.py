@@ -162,7 +162,8 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (1, 1.25, 1.0, 1), (2, 1 / 6.4, 1.0, 8), (2, 0.5, 1.0, 3),
                                                    (3, 1.0, 1.0, 10), (3, 0.5, 1.0, 2), (3, 0.7, 0.7, 1),
                                                    (4, 1.0, 1.0, 20), (4, 1.0, 1.0, 5),
-                                                   (5, 1.0, 1.0, 10), (5, 0.5, 1.0, 2)])
+                                                   (5, 1.0, 1.0, 10), (5, 0.5, 1.0, 2),
+                                                   (6, 1.0, 1.0, 8), (6, 0.5, 1.0, 2)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
