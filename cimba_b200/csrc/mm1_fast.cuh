@@ -104,7 +104,9 @@ mm1_kernel(const QueueArgs a)
     const uint32_t quota = (uint32_t)a.num_objects;
     uint32_t win = (uint32_t)__cvta_generic_to_shared(&ring_smem[threadIdx.x]);
     uint32_t tab = (uint32_t)__cvta_generic_to_shared(&exp_x[0]);
-    asm volatile("" : "+r"(win), "+r"(tab));            // keep both in registers (no per-step rematerialisation)
+    __shared__ double scratch_smem[QUEUE_BLOCK];        // sink for the store of lanes that do not put
+    uint32_t scratch = (uint32_t)__cvta_generic_to_shared(&scratch_smem[threadIdx.x]);
+    asm volatile("" : "+r"(win), "+r"(tab), "+r"(scratch));     // keep in registers (no per-step rematerialisation)
     double *const spill = (a.spill_cap && alive) ? a.spill + trial * a.spill_cap : nullptr;
     const uint32_t spill_mask = a.spill_cap - 1u;
 
@@ -152,12 +154,12 @@ mm1_kernel(const QueueArgs a)
         if (go) now = first_arr ? t_arr : t_srv;        // src/cmb_event.c:239-241
 
         // ---------------- arrival body (MM1_multi.c:58-66): back from hold -> put
+        // Ring accesses are unconditional (a lane that does not put writes its private
+        // scratch row instead): a select on the address is cheaper than a divergent region.
         const uint32_t q_len = produced - served;
         const bool put = is_arr & wake;
         const bool put_far = put & (q_len >= (uint32_t)QUEUE_WINDOW);
-        if (put & !put_far) {
-            sts_f64(win + (produced & WMASK) * ROW, now);
-        }
+        sts_f64((put & !put_far) ? win + (produced & WMASK) * ROW : scratch, now);
         if (put_far) {                                  // rare: beyond the on-chip window
             if (spill != nullptr && q_len - QUEUE_WINDOW <= spill_mask) {
                 spill[produced & spill_mask] = now;
@@ -184,14 +186,13 @@ mm1_kernel(const QueueArgs a)
         if (finished) sum_wait = new_sum;
         // cmb_objectqueue_get: take the head, or wait at the front guard (slot stays empty)
         const bool take = is_srv & (produced != served);
-        if (take) {
-            const uint32_t slot = win + (served & WMASK) * ROW;
-            stamp = lds_f64(slot);
-            if (produced - served > (uint32_t)QUEUE_WINDOW) {   // rare: refill the freed slot from HBM
-                sts_f64(slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
-            }
-            served++;
+        const uint32_t head_slot = win + (served & WMASK) * ROW;
+        const double head_stamp = lds_f64(head_slot);   // harmless when the ring is empty
+        if (take) stamp = head_stamp;
+        if (take & (produced - served > (uint32_t)QUEUE_WINDOW)) {      // rare: refill the freed slot from HBM
+            sts_f64(head_slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
         }
+        if (take) served++;
 
         // ---------------- hold: consume the look-ahead variate, insert the wake-up
         const bool draw = take | (is_arr & (produced < quota));

@@ -199,7 +199,8 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
         }
         for (;;) {                                      // waiters
             {
-                bool through = true;
+                bool through;
+                through = true;
                 while (st->level < prioq_threshold(pid)) {
                     s.wait_begin(2u, pid);              // cmb_condition_wait = cmb_resourceguard_wait
                     p.pc = 60u;
