@@ -129,13 +129,14 @@ mm1_kernel(const QueueArgs a)
         e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
     }
 
-    bool parked = false;                                // look-ahead variate needs the ziggurat slow path
+    // lane state in one word: bit 0 alive, bit 1 parked (the look-ahead variate needs the
+    // ziggurat slow path), bit 2 the parked draw belongs to the arrival process
+    uint32_t flags = alive ? 1u : 0u;
     uint32_t step = 0u;
-    bool parked_is_arr = false;
 
-    while (__any_sync(FULL, alive)) {
+    while (__any_sync(FULL, flags & 1u)) {
         // ---------------- pop-min (cmi_hashheap_dequeue order: time asc, key asc)
-        const bool go0 = alive & !parked;
+        const bool go0 = (flags & 3u) == 1u;           // alive and not parked
         const bool first_arr = (t_arr < t_srv) | ((t_arr == t_srv) & (k_arr < k_srv));
         const uint32_t key = first_arr ? k_arr : k_srv;
         const uint32_t act = key & 3u;
@@ -204,7 +205,7 @@ mm1_kernel(const QueueArgs a)
         const uint32_t k_new = push ? pack_key(issued, ACT_WAKE_TIME) : 0u;
         if (is_arr) { t_arr = t_new; k_arr = k_new; }
         if (is_srv) { t_srv = t_new; k_srv = k_new; }
-        if (draw & !hot) { parked = true; parked_is_arr = is_arr; }
+        if (draw & !hot) flags = is_arr ? 7u : 3u;
         if (push) {                                     // refill the look-ahead
             u_next = rng.next();
             e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
@@ -212,7 +213,7 @@ mm1_kernel(const QueueArgs a)
 
         // ---------------- rare paths
         if (done) {
-            alive = false;
+            flags = 0u;
             if (a.events)    a.events[trial] = issued;  // every scheduled event has been popped
             if (a.objects)   a.objects[trial] = served - dropped;
             if (a.t_end)     a.t_end[trial] = now;
@@ -223,17 +224,18 @@ mm1_kernel(const QueueArgs a)
         if ((++step & MM1_PARK_MASK) != 0u) {
             continue;                                   // look at the parked set every (MM1_PARK_MASK+1)-th step only
         }
-        const unsigned pm = __ballot_sync(FULL, parked);
+        const unsigned pm = __ballot_sync(FULL, flags & 2u);
         if (pm != 0u) {
-            const unsigned am = __ballot_sync(FULL, alive);
+            const unsigned am = __ballot_sync(FULL, flags & 1u);
             if (__popc(pm) >= MM1_COLD_BATCH || pm == am) {
-                if (parked) {
+                if (flags & 2u) {
+                    const bool parked_is_arr = (flags & 4u) != 0u;
                     const double mean = parked_is_arr ? arr_mean : srv_mean;
                     const double at = __dadd_rn(now, __dmul_rn(mean, rng.exp_cold(u_next)));
                     issued++;
                     if (parked_is_arr) { t_arr = at; k_arr = pack_key(issued, ACT_WAKE_TIME); }
                     else               { t_srv = at; k_srv = pack_key(issued, ACT_WAKE_TIME); }
-                    parked = false;
+                    flags = 1u;
                     u_next = rng.next();
                     e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
                 }
