@@ -22,6 +22,7 @@
 #include "preempt_model.cuh"
 #include "buffer_model.cuh"
 #include "prioq_model.cuh"
+#include "hold_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
 
@@ -272,6 +273,42 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "guarded_kernel launch");
+    }
+    if (job->model == CIMBA_B200_MODEL_HOLD) {
+        if (job->servers < 1 || job->servers > HOLD_CAP - 8)
+            return fail(CIMBA_B200_EINVAL, "workers (servers) must be in 1..1080 for CIMBA_B200_MODEL_HOLD");
+        HoldArgs ha{};
+        ha.workers = job->servers;
+        ha.master_seed = job->master_seed;
+        ha.first_trial = job->first_trial;
+        ha.num_trials = job->num_trials;
+        ha.duration = job->num_objects;
+        ha.mean = job->arr_mean;
+        ha.events = job->events;
+        ha.objects = job->objects;
+        ha.t_end = job->t_end;
+        ha.sum_wait = job->sum_wait;
+        ha.status = job->status;
+        ha.max_queue = job->max_queue;
+        ha.counters = job->counters;
+        ha.trace_cap = job->trace_cap;
+        ha.trace_key = job->trace_key;
+        ha.trace_time = job->trace_time;
+        // persistent one-warp CTAs: as many as fit on the machine (13 per SM by shared memory)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const uint64_t resident = (uint64_t)sms * 13u;
+        const unsigned blocks = (unsigned)(job->num_trials < resident ? job->num_trials : resident);
+        if (trace) {
+            hold_kernel<true><<<blocks, 32, HOLD_SMEM_BYTES, st>>>(ha);
+        }
+        else {
+            hold_kernel<false><<<blocks, 32, HOLD_SMEM_BYTES, st>>>(ha);
+        }
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "hold_kernel launch");
     }
     return fail(CIMBA_B200_EINVAL, "unknown model");
 }

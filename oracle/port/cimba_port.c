@@ -2412,6 +2412,65 @@ static void run_prioq(int capacity, uint64_t seed, uint64_t duration, double put
     free(w);
 }
 
+/* ======================================== model 7: the hold model (large event list)
+ *
+ * ref_driver.c model 7: `servers` workers in cmb_process_hold loops + a ticker + an end
+ * event.  Every worker owns exactly one pending event, so the end event's
+ * cmb_process_stop loop (cancel each hold, src/cmb_process.c:698-723) empties the list.
+ */
+static void run_hold(int workers, uint64_t seed, uint64_t duration, double mean,
+                     uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    port_rng rng;
+    heap fel;
+    double now = 0.0;
+    memset(out, 0, sizeof(*out));
+    port_rng_init(&rng, seed);
+    heap_init(&fel, 3u, fel_before);
+    const int64_t ticker = workers;
+    for (int64_t i = 0; i <= ticker; i++) {
+        heap_push(&fel, 0u, now, 0, ACT_START, i, 0);               /* cmb_process_start */
+    }
+    heap_push(&fel, 0u, (double)duration, 0, ACT_USER_END, -1, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (fel.count > out->max_fel) {
+            out->max_fel = fel.count;
+        }
+        if (!heap_pop(&fel)) {
+            break;
+        }
+        const heap_tag ev = fel.slot[0];
+        now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = now;
+        }
+        n++;
+        const int64_t who = ev.item[1];
+        if ((int)ev.item[0] == ACT_USER_END) {
+            fel.count = 0u;                             /* every pending event is a stopped process's hold */
+            continue;
+        }
+        if ((int)ev.item[0] == ACT_WAKE_TIME) {
+            if (who == ticker) {
+                out->counter[1] += 1u;
+            }
+            else {
+                out->counter[0] += 1u;
+                out->sum_wait += now;
+            }
+        }
+        const double dur = (who == ticker) ? 1.0 : port_exponential(&rng, mean);
+        heap_push(&fel, 0u, now + dur, 0, ACT_WAKE_TIME, who, SIG_SUCCESS);
+    }
+    out->events = n;
+    out->t_end = now;
+    out->objects = out->counter[0];
+    heap_free(&fel);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -2429,6 +2488,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 7) {
+            run_hold(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                     j->arr_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 6) {
             run_prioq(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -2482,6 +2546,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 7) {
+        run_hold(servers, seed, num_objects, arr_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 6) {
         run_prioq(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;

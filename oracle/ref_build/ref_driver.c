@@ -800,6 +800,78 @@ static void run_prioq_trial(struct ref_trial *t)
     free(w);
 }
 
+
+/* ------------------------------------------------- model 7: the hold model (large event list)
+ *
+ * `servers` worker processes that do nothing but hold for an exponential time, plus a
+ * ticker that holds exactly 1.0 (the shape of tutorial/tut_5_1.c: 1000 target processes
+ * in cmb_process_hold loops and a sensor ticking once a second, SURVEY.md section 8d-5,
+ * without its float32 physics), and an end event at t = num_objects that stops
+ * everybody.  The future-event list holds servers + 2 entries for the whole run, so
+ * every event is a pop and a push on a deep heap (src/cmi_hashheap.c:428-524).
+ * counters: [0] worker wake-ups [1] ticks
+ * sum_wait = sum over worker wake-ups of cmb_time()
+ */
+struct h_world {
+    struct ref_trial *trl;
+    struct cmb_process *proc;           /* servers + 1 contiguous */
+    unsigned count;
+};
+
+static void *h_worker_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct h_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        w->trl->counter[0] += 1u;
+        w->trl->sum_wait += cmb_time();
+    }
+}
+
+static void *h_ticker_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct h_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(1.0);
+        w->trl->counter[1] += 1u;
+    }
+}
+
+static void h_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct h_world *w = subject;
+    for (unsigned i = 0u; i < w->count; i++) {
+        cmb_process_stop(&w->proc[i], NULL);
+    }
+}
+
+static void run_hold_trial(struct ref_trial *t)
+{
+    struct h_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->count = (unsigned)t->servers + 1u;
+    w->proc = calloc(w->count, sizeof(struct cmb_process));
+    for (unsigned i = 0u; i + 1u < w->count; i++) {
+        cmb_process_initialize(&w->proc[i], "Worker", h_worker_body, w, 0);
+        cmb_process_start(&w->proc[i]);
+    }
+    cmb_process_initialize(&w->proc[w->count - 1u], "Ticker", h_ticker_body, w, 0);
+    cmb_process_start(&w->proc[w->count - 1u]);
+    (void)cmb_event_schedule(h_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->objects = t->counter[0];
+    for (unsigned i = 0u; i < w->count; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -882,7 +954,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 6) {
+    if (t->model == 7) {
+        run_hold_trial(t);
+    }
+    else if (t->model == 6) {
         run_prioq_trial(t);
     }
     else if (t->model == 5) {

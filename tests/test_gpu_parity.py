@@ -380,3 +380,43 @@ def test_priorityqueue_and_condition_pop_order_bit_exact(cb, port):
         m = min(cap, r.events)
         assert list(keys[i, :m]) == k, i
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+# ------------------------------------------------------------------ hold model (warp per trial, 32-ary heap)
+
+@pytest.mark.parametrize("workers,dur,mean", [(1000, 20, 1.0), (100, 50, 0.5), (7, 100, 1.0), (1, 30, 2.0),
+                                              (33, 40, 1.0), (1080, 6, 1.0)])
+def test_hold_model_matches_oracle(cb, port, workers, dur, mean):
+    """A future-event list 3..1082 deep, one trial per warp: counts, clock, the wake-time sum
+    (order-sensitive in floating point) and the deepest list seen, bit-exact."""
+    n = 40
+    res = cb.run_trials(n, arr_mean=mean, srv_mean=1.0, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_HOLD, servers=workers)
+    want = run_trials(port, "port", 7, workers, KAT_SEED, 0, n, dur, mean, 1.0)
+    _compare(res, want, ("hold", workers))
+    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+
+
+def test_hold_model_pop_order_bit_exact(cb, port):
+    n, cap = 6, 20000
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=15, master_seed=12,
+                        model=cb.MODEL_HOLD, servers=1000, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 7, 1000, cb.fmix64(12, i), 15, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+def test_hold_model_more_trials_than_resident_warps(cb, port):
+    """4096 trials on 1924 resident warps: the persistent loop reuses its heap storage."""
+    n = 4096
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=3, master_seed=1,
+                        model=cb.MODEL_HOLD, servers=300)
+    idx = list(range(0, n, 97))
+    ev, sw = res.events.cpu().tolist(), res.sum_wait.cpu().tolist()
+    for i in idx:
+        r, _, _ = trace_trial(port, "port", 7, 300, cb.fmix64(1, i), 3, 1.0, 1.0, 0)
+        assert (ev[i], sw[i]) == (r.events, r.sum_wait), i
