@@ -294,11 +294,16 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ha.trace_cap = job->trace_cap;
         ha.trace_key = job->trace_key;
         ha.trace_time = job->trace_time;
-        // persistent one-warp CTAs: as many as fit on the machine (13 per SM by shared memory)
-        int dev = 0, sms = 148;
+        // persistent one-warp CTAs: exactly as many as are resident at once (shared memory
+        // bounds it at ~12 per SM), so no CTA waits for another to retire
+        int dev = 0, sms = 148, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const uint64_t resident = (uint64_t)sms * 13u;
+        cudaError_t oe = trace
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_kernel<true>, 32, HOLD_SMEM_BYTES)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_kernel<false>, 32, HOLD_SMEM_BYTES);
+        if (oe != cudaSuccess || per_sm < 1) per_sm = 8;
+        const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
         const unsigned blocks = (unsigned)(job->num_trials < resident ? job->num_trials : resident);
         if (trace) {
             hold_kernel<true><<<blocks, 32, HOLD_SMEM_BYTES, st>>>(ha);

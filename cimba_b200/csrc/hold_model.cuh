@@ -47,10 +47,32 @@ struct HoldArgs {
     double   *trace_time;
 };
 
+// shared-window accessors on 32-bit addresses (no generic->shared conversion per access)
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, unsigned long long v)
+{
+    asm volatile("st.shared.u64 [%0], %1;" :: "r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 struct WarpHeap {
-    unsigned long long *t;     // time as its IEEE-754 bit pattern (times are >= 0)
-    uint32_t *key;
-    uint32_t *info;            // (process << 3) | action
+    uint32_t  t;               // shared-window byte address of time[] (IEEE-754 bit patterns; times are >= 0)
+    uint32_t  key;             // ... of key[]
+    uint32_t  info;            // ... of info[]: (process << 3) | action
     uint32_t  count;           // warp-uniform
 
     // Sink the entry (mt, mk, mi) from node i to its place (heap_down, src/cmi_hashheap.c:321-370,
@@ -66,31 +88,38 @@ struct WarpHeap {
             }
             const uint32_t c = first + lane;
             const bool valid = c < count;
-            const unsigned long long ct = valid ? t[c] : ~0ull;
-            const uint32_t ck = valid ? key[c] : 0xffffffffu;
-            const uint32_t ci = valid ? info[c] : 0u;
+            const unsigned long long ct = valid ? lds_u64(t + c * 8u) : ~0ull;
+            const uint32_t ck = valid ? lds_u32(key + c * 4u) : 0xffffffffu;
             const uint32_t hi = (uint32_t)(ct >> 32), lo = (uint32_t)ct;
+            // first child under (time asc, key asc).  Fast path: the high words of the
+            // 32 times are almost always distinct, so one REDUX + one ballot decide.
             const uint32_t mhi = __reduce_min_sync(FULL, hi);
-            const uint32_t mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
-            const bool tie = (hi == mhi) & (lo == mlo);
-            const uint32_t mkey = __reduce_min_sync(FULL, tie ? ck : 0xffffffffu);
-            const unsigned winner = __ffs(__ballot_sync(FULL, tie & (ck == mkey))) - 1u;
+            unsigned cand = __ballot_sync(FULL, hi == mhi);
+            uint32_t mlo = __shfl_sync(FULL, lo, __ffs(cand) - 1u);
+            uint32_t mkey = __shfl_sync(FULL, ck, __ffs(cand) - 1u);
+            if (__popc(cand) > 1) {                     // ties in the high word: settle low word, then key
+                mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+                const bool tie = (hi == mhi) & (lo == mlo);
+                mkey = __reduce_min_sync(FULL, tie ? ck : 0xffffffffu);
+                cand = __ballot_sync(FULL, tie & (ck == mkey));
+            }
             const unsigned long long best = ((unsigned long long)mhi << 32) | mlo;
             if (mt < best || (mt == best && mk < mkey)) {
                 break;                                  // the moving entry goes before every child
             }
-            const uint32_t wi = __shfl_sync(FULL, ci, winner);
-            if (lane == 0u) {
-                t[i] = best;
-                key[i] = mkey;
-                info[i] = wi;
+            const unsigned winner = __ffs(cand) - 1u;
+            const uint32_t w = first + winner;
+            if (lane == 0u) {                           // move the first child up
+                sts_u64(t + i * 8u, best);
+                sts_u32(key + i * 4u, mkey);
+                sts_u32(info + i * 4u, lds_u32(info + w * 4u));
             }
-            i = first + winner;
+            i = w;
         }
         if (lane == 0u) {
-            t[i] = mt;
-            key[i] = mk;
-            info[i] = mi;
+            sts_u64(t + i * 8u, mt);
+            sts_u32(key + i * 4u, mk);
+            sts_u32(info + i * 4u, mi);
         }
         __syncwarp();
     }
@@ -102,19 +131,19 @@ struct WarpHeap {
             uint32_t i = count;
             while (i > 0u) {
                 const uint32_t p = (i - 1u) >> 5;
-                const unsigned long long pt = t[p];
-                const uint32_t pk = key[p];
+                const unsigned long long pt = lds_u64(t + p * 8u);
+                const uint32_t pk = lds_u32(key + p * 4u);
                 if (!(mt < pt || (mt == pt && mk < pk))) {
                     break;
                 }
-                t[i] = pt;
-                key[i] = pk;
-                info[i] = info[p];
+                sts_u64(t + i * 8u, pt);
+                sts_u32(key + i * 4u, pk);
+                sts_u32(info + i * 4u, lds_u32(info + p * 4u));
                 i = p;
             }
-            t[i] = mt;
-            key[i] = mk;
-            info[i] = mi;
+            sts_u64(t + i * 8u, mt);
+            sts_u32(key + i * 4u, mk);
+            sts_u32(info + i * 4u, mi);
         }
         count++;
         __syncwarp();
@@ -127,9 +156,11 @@ hold_kernel(const HoldArgs a)
 {
     extern __shared__ __align__(16) unsigned char hold_smem[];
     WarpHeap h;
-    h.t = reinterpret_cast<unsigned long long *>(hold_smem);
-    h.key = reinterpret_cast<uint32_t *>(hold_smem + HOLD_CAP * 8u);
-    h.info = reinterpret_cast<uint32_t *>(hold_smem + HOLD_CAP * 12u);
+    h.t = (uint32_t)__cvta_generic_to_shared(hold_smem);
+    h.key = h.t + HOLD_CAP * 8u;
+    h.info = h.t + HOLD_CAP * 12u;
+    h.count = 0u;
+    asm volatile("" : "+r"(h.t), "+r"(h.key), "+r"(h.info));
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t ticker = (uint32_t)a.workers;       // process index of the ticker
@@ -142,14 +173,17 @@ hold_kernel(const HoldArgs a)
         double now = 0.0, sum_wait = 0.0;
         uint64_t pops = 0u, wakes = 0u, ticks = 0u;
         uint32_t issued = 0u, deepest = 0u;
+        // one variate of look-ahead (the draw does not depend on the event list, so it
+        // is taken off the pop -> push critical path; stream order is unchanged)
+        double e_next = rng.std_exponential_global();
 
         // cmb_process_start for workers 0..n-1 and the ticker: START events at t = 0 with
         // keys 1, 2, ...  Equal times and ascending keys in index order already form a heap.
         __syncwarp();
         for (uint32_t j = lane; j <= ticker; j += 32u) {
-            h.t[j] = 0ull;
-            h.key[j] = j + 1u;
-            h.info[j] = (j << 3) | ACT_START;
+            sts_u64(h.t + j * 8u, 0ull);
+            sts_u32(h.key + j * 4u, j + 1u);
+            sts_u32(h.info + j * 4u, (j << 3) | ACT_START);
         }
         h.count = ticker + 1u;
         issued = ticker + 1u;
@@ -162,9 +196,9 @@ hold_kernel(const HoldArgs a)
                 break;
             }
             // cmi_hashheap_dequeue: the root (all lanes read it: a broadcast)
-            const unsigned long long rt = h.t[0];
-            const uint32_t rk = h.key[0];
-            const uint32_t ri = h.info[0];
+            const unsigned long long rt = lds_u64(h.t);
+            const uint32_t rk = lds_u32(h.key);
+            const uint32_t ri = lds_u32(h.info);
             now = __longlong_as_double((long long)rt);
             if (TRACE) {
                 if (lane == 0u && pops < a.trace_cap) {
@@ -190,17 +224,13 @@ hold_kernel(const HoldArgs a)
                 }
             }
             // back in the body: hold again (cmb_process_hold -> cmb_event_schedule)
-            double dur = 1.0;
-            if (who != ticker) {
-                const uint64_t u = rng.next();
-                const double e = Sfc64::exp_is_hot(u)
-                    ? __dmul_rn(zig::zig_exp_x[u & 0xffu], __ull2double_rn(u))
-                    : rng.exp_cold(u);
-                dur = __dmul_rn(mean, e);
-            }
-            const double when = __dadd_rn(now, dur);
+            const bool draws = who != ticker;
+            const double when = __dadd_rn(now, draws ? __dmul_rn(mean, e_next) : 1.0);
             // dequeue + enqueue fused: the new event replaces the root and sinks
             h.sift_down(0u, (unsigned long long)__double_as_longlong(when), ++issued, (who << 3) | ACT_WAKE_TIME);
+            if (draws) {
+                e_next = rng.std_exponential_global();  // refill after use, overlapping the next pop
+            }
         }
 
         if (lane == 0u) {

@@ -182,6 +182,14 @@ struct Sfc64 {
         return exp_is_hot(u) ? exp_hot(hot, u) : exp_cold(u);
     }
 
+    // the same draw with the layer table read from global memory (L1-resident): for
+    // kernels that cannot spare shared memory for the table
+    __device__ __forceinline__ double std_exponential_global()
+    {
+        const uint64_t u = next();
+        return exp_is_hot(u) ? __dmul_rn(zig::zig_exp_x[u & 0xffu], __ull2double_rn(u)) : exp_cold(u);
+    }
+
     // cmb_random_exponential, include/cmb_random.h:344-352
     __device__ __forceinline__ double exponential(const ZigHot &hot, double mean)
     {
