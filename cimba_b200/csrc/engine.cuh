@@ -233,19 +233,36 @@ struct __align__(16) EventHead {
 
 template <int CAP>
 struct EventList {
-    EventHead *head;           // shared memory, already offset by threadIdx.x
-    double    *pay;
-    uint32_t   stride;
+    uint32_t   head;           // shared-window byte address of this thread's column of EventHead records
+    uint32_t   pay;            // ... of its column of payloads
+    uint32_t   hstride;        // bytes between consecutive rows of head (blockDim.x * 16)
+    uint32_t   pstride;        // ... of pay (blockDim.x * 8)
     uint32_t   count;
     uint32_t   issued;         // item_counter, src/cmi_hashheap.c:449-453
 
-    __device__ __forceinline__ void init(EventHead *h, double *p, uint32_t s)
+    __device__ __forceinline__ void init(EventHead *h, double *p, uint32_t threads)
     {
-        head = h;
-        pay = p;
-        stride = s;
+        head = (uint32_t)__cvta_generic_to_shared(h);
+        pay = (uint32_t)__cvta_generic_to_shared(p);
+        hstride = threads * 16u;
+        pstride = threads * 8u;
         count = 0u;
         issued = 0u;
+    }
+
+    static __device__ __forceinline__ void ld_head(uint32_t addr, double &time, uint32_t &keyact, uint32_t &tag)
+    {
+        uint32_t lo, hi;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(hi), "=r"(keyact), "=r"(tag) : "r"(addr) : "memory");
+        time = __hiloint2double((int)hi, (int)lo);
+    }
+
+    static __device__ __forceinline__ void st_head(uint32_t addr, double time, uint32_t keyact, uint32_t tag)
+    {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(addr), "r"((uint32_t)__double2loint(time)), "r"((uint32_t)__double2hiint(time)),
+                        "r"(keyact), "r"(tag) : "memory");
     }
 
     // cmb_event_schedule: false if the list is full (entry dropped; flag the trial)
@@ -255,12 +272,8 @@ struct EventList {
         if (count >= (uint32_t)CAP) {
             return false;
         }
-        EventHead e;
-        e.time = time;
-        e.keyact = (k << 2) | action;
-        e.tag = tag;
-        head[count * stride] = e;
-        pay[count * stride] = payload;
+        st_head(head + count * hstride, time, (k << 2) | action, tag);
+        asm volatile("st.shared.f64 [%0], %1;" :: "r"(pay + count * pstride), "d"(payload) : "memory");
         count++;
         return true;
     }
@@ -275,11 +288,13 @@ struct EventList {
         uint32_t bk = 0xffffffffu, bi = 0u, btag = 0u;
         for (uint32_t i = 0u; i < scan; i++) {
             if (i < count) {
-                const EventHead e = head[i * stride];
-                const bool before = (e.time < bt) | ((e.time == bt) & (e.keyact < bk));
-                bt = before ? e.time : bt;
-                bk = before ? e.keyact : bk;
-                btag = before ? e.tag : btag;
+                double et;
+                uint32_t ek, etag;
+                ld_head(head + i * hstride, et, ek, etag);
+                const bool before = (et < bt) | ((et == bt) & (ek < bk));
+                bt = before ? et : bt;
+                bk = before ? ek : bk;
+                btag = before ? etag : btag;
                 bi = before ? i : bi;
             }
         }
@@ -289,11 +304,15 @@ struct EventList {
         out.time = bt;
         out.keyact = bk;
         out.tag = btag;
-        payload = pay[bi * stride];
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(payload) : "r"(pay + bi * pstride) : "memory");
         count--;
         if (bi != count) {                              // move the last entry into the hole
-            head[bi * stride] = head[count * stride];
-            pay[bi * stride] = pay[count * stride];
+            double lt, lp;
+            uint32_t lk, ltag;
+            ld_head(head + count * hstride, lt, lk, ltag);
+            st_head(head + bi * hstride, lt, lk, ltag);
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lp) : "r"(pay + count * pstride) : "memory");
+            asm volatile("st.shared.f64 [%0], %1;" :: "r"(pay + bi * pstride), "d"(lp) : "memory");
         }
         return true;
     }

@@ -106,11 +106,7 @@ pool_kernel(const PoolArgs a)
             break;
         }
         // uniform trip count for the event-list scan
-        uint32_t scan = (alive && !parked) ? fel.count : 0u;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            scan = max(scan, __shfl_xor_sync(FULL, scan, s));
-        }
+        const uint32_t scan = __reduce_max_sync(FULL, (alive && !parked) ? fel.count : 0u);
 
         bool draw = false;
         double draw_mean = 0.0, draw_pay = 0.0;
