@@ -65,6 +65,8 @@ SYMBOLS = {
     "cimba_b200_launch_count": (C.c_uint64, []),
     "cimba_b200_summarize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cimba_b200_run_experiment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment)]),
+    "cimba_b200_run_experiment_all_gpus": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment),
+                                                     C.c_int]),
     "cimba_b200_datasummary_initialize": (None, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_add": (C.c_uint64, [C.POINTER(DataSummaryStruct), C.c_double]),
     "cimba_b200_datasummary_merge": (C.c_uint64, [C.POINTER(DataSummaryStruct)] * 3),

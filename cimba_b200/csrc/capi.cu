@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -361,7 +363,13 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
     unsigned char *h_out = nullptr;
     const size_t out_row = 2 * sizeof(uint64_t) + 2 * sizeof(double) + sizeof(uint32_t) + sizeof(uint32_t);
     CUDA_TRY(cudaMallocHost(&h_in, 2 * n * sizeof(double)));
-    CUDA_TRY(cudaMallocHost(&h_out, n * out_row));
+    {
+        cudaError_t he = cudaMallocHost(&h_out, n * out_row);
+        if (he != cudaSuccess) {
+            cudaFreeHost(h_in);
+            return cuda_fail(he, "cudaMallocHost");
+        }
+    }
     for (uint64_t i = 0; i < n; i++) {
         memcpy(&h_in[i], base + i * stride + d->off_arr_mean, sizeof(double));
         memcpy(&h_in[n + i], base + i * stride + d->off_srv_mean, sizeof(double));
@@ -436,6 +444,47 @@ done:
     if (h_in) cudaFreeHost(h_in);
     if (h_out) cudaFreeHost(h_out);
     return rc;
+}
+
+// The reference's executive starts one pthread per logical core and lets them pull
+// trials (src/cimba.c:151-188).  The counterpart here: one host thread per GPU, each
+// running a contiguous block of the trial array on its own device and stream.  Seeds
+// depend on the global trial index only, so results do not depend on the GPU count.
+int cimba_b200_run_experiment_all_gpus(void *array, uint64_t num_trials, size_t stride,
+                                       const cimba_b200_experiment *d, int max_gpus)
+{
+    if (array == nullptr || d == nullptr) return fail(CIMBA_B200_EINVAL, "NULL experiment array or descriptor");
+    if (num_trials == 0u || stride == 0u) return fail(CIMBA_B200_EINVAL, "num_trials and trial_struct_size must be > 0");
+    int gpus = cimba_b200_device_count();
+    if (gpus <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    if (max_gpus > 0 && max_gpus < gpus) gpus = max_gpus;
+    if ((uint64_t)gpus > num_trials) gpus = (int)num_trials;
+
+    std::vector<int> rc((size_t)gpus, CIMBA_B200_OK);
+    std::vector<std::string> msg((size_t)gpus);
+    std::vector<std::thread> pool;
+    for (int g = 0; g < gpus; g++) {
+        pool.emplace_back([&, g]() {
+            const uint64_t lo = num_trials * (uint64_t)g / (uint64_t)gpus;
+            const uint64_t hi = num_trials * (uint64_t)(g + 1) / (uint64_t)gpus;
+            cimba_b200_experiment mine = *d;
+            mine.device = g;
+            mine.first_trial = d->first_trial + lo;
+            rc[(size_t)g] = cimba_b200_run_experiment((char *)array + lo * stride, hi - lo, stride, &mine);
+            msg[(size_t)g] = g_err;                     // thread-local message of this worker
+        });
+    }
+    for (auto &t : pool) {
+        t.join();
+    }
+    int worst = CIMBA_B200_OK;
+    for (int g = 0; g < gpus; g++) {
+        if (rc[(size_t)g] != CIMBA_B200_OK && (worst == CIMBA_B200_OK || worst == CIMBA_B200_ETRIAL)) {
+            worst = rc[(size_t)g];
+            snprintf(g_err, sizeof(g_err), "GPU %d: %s", g, msg[(size_t)g].c_str());
+        }
+    }
+    return worst;
 }
 
 // ------------------------------------------------- cmb_datasummary on the host

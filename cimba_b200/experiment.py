@@ -35,7 +35,8 @@ def fmix64(seed: int, nonce: int) -> int:
 
 def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODEL_MM1,
                          num_objects: int, master_seed: int, first_trial: int = 0,
-                         servers: int = 1, mapping: int = 0, device: int = -1) -> None:
+                         servers: int = 1, mapping: int = 0, device: int = -1,
+                         all_gpus: bool = False, max_gpus: int = 0) -> None:
     """Run every trial of a host-resident experiment array on the GPU, in place.
 
     ``experiment_array`` is a 1-D numpy structured array (any dtype that has
@@ -43,6 +44,8 @@ def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODE
     ``sum_wait``, ``avg_wait``, ``events``, ``t_end``, ``status`` are filled when
     present).  Host->device and device->host copies happen inside the call.
     Raises CimbaError(ETRIAL) if any trial overflowed a device structure.
+    With ``all_gpus`` the array is sharded over every visible GPU, one host thread
+    each (the counterpart of the reference's one pthread per core).
     """
     arr = experiment_array
     if not isinstance(arr, np.ndarray) or arr.ndim != 1 or arr.dtype.fields is None:
@@ -69,8 +72,12 @@ def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODE
         off_obj_cnt=off("obj_cnt", "<u8"), off_sum_wait=off("sum_wait", "<f8"),
         off_avg_wait=off("avg_wait", "<f8"), off_events=off("events", "<u8"),
         off_t_end=off("t_end", "<f8"), off_status=off("status", "<u4"))
-    check(lib.cimba_b200_run_experiment(arr.ctypes.data_as(C.c_void_p), len(arr),
-                                        arr.dtype.itemsize, C.byref(desc)))
+    if all_gpus:
+        check(lib.cimba_b200_run_experiment_all_gpus(arr.ctypes.data_as(C.c_void_p), len(arr),
+                                                     arr.dtype.itemsize, C.byref(desc), max_gpus))
+    else:
+        check(lib.cimba_b200_run_experiment(arr.ctypes.data_as(C.c_void_p), len(arr),
+                                            arr.dtype.itemsize, C.byref(desc)))
 
 
 @dataclass

@@ -165,6 +165,16 @@ int cimba_b200_run_experiment(void *your_experiment_array,
                               size_t trial_struct_size,
                               const cimba_b200_experiment *desc);
 
+/* The same, sharded over every visible GPU (or the first max_gpus > 0 of them): one host
+ * thread per GPU runs a contiguous block of the array - the counterpart of the
+ * reference executive's one pthread per core (src/cimba.c:171-182).  Results do not
+ * depend on the GPU count (seeds are a function of the global trial index). */
+int cimba_b200_run_experiment_all_gpus(void *your_experiment_array,
+                                       uint64_t num_trials,
+                                       size_t trial_struct_size,
+                                       const cimba_b200_experiment *desc,
+                                       int max_gpus);
+
 /* ------------------------------------------------------------------------
  * cmb_datasummary on the host (reference include/cmb_datasummary.h:42-51,
  * src/cmb_datasummary.c:93-166): same field order and arithmetic, used to fold

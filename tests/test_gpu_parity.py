@@ -420,3 +420,17 @@ def test_hold_model_more_trials_than_resident_warps(cb, port):
     for i in idx:
         r, _, _ = trace_trial(port, "port", 7, 300, cb.fmix64(1, i), 3, 1.0, 1.0, 0)
         assert (ev[i], sw[i]) == (r.events, r.sum_wait), i
+
+
+def test_all_gpus_executive_is_count_independent(cb, port):
+    """One host thread per GPU (the reference: one pthread per core): same results whatever the GPU count."""
+    n = 301
+    one = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    one["arr_mean"], one["srv_mean"] = 1 / 0.9, 1.0
+    many = one.copy()
+    cb.cimba_run_experiment(one, num_objects=1500, master_seed=KAT_SEED)
+    cb.cimba_run_experiment(many, num_objects=1500, master_seed=KAT_SEED, all_gpus=True)
+    for f in ("events", "obj_cnt", "sum_wait", "t_end", "avg_wait", "status"):
+        assert np.array_equal(one[f], many[f]), f
+    want = run_trials(port, "port", 0, 1, KAT_SEED, 0, n, 1500, 1 / 0.9, 1.0)
+    assert many["sum_wait"].tolist() == [w.sum_wait for w in want]
