@@ -24,6 +24,7 @@
 #include "preempt_model.cuh"
 #include "buffer_model.cuh"
 #include "prioq_model.cuh"
+#include "timers_model.cuh"
 #include "hold_model.cuh"
 #include "rng.cuh"
 #include "summary.cuh"
@@ -56,6 +57,11 @@ int cuda_fail(cudaError_t e, const char *where)
 constexpr uint32_t QUEUE_SPILL_CAP = 512u;     // doubles per trial behind the 32-entry window
 
 bool is_queue_model(int m) { return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1; }
+bool is_general_model(int m)
+{
+    return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
+           m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_TIMERS;
+}
 
 // ---------------------------------------------------------------- RNG KAT kernel
 __global__ void rng_draws_kernel(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out)
@@ -126,8 +132,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
-    if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT ||
-        job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_PRIOQ) {
+    if (is_general_model(job->model)) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
     }
     return 0u;
@@ -223,12 +228,12 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
     }
-    if (job->model == CIMBA_B200_MODEL_GUARDED || job->model == CIMBA_B200_MODEL_PREEMPT ||
-        job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_PRIOQ) {
+    if (is_general_model(job->model)) {
+        const bool tmr = job->model == CIMBA_B200_MODEL_TIMERS;
         const bool prq = job->model == CIMBA_B200_MODEL_PRIOQ;
         const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
         const bool buf = job->model == CIMBA_B200_MODEL_BUFFER;
-        if (job->servers < 1 || (!pre && !buf && job->servers > (prq ? 15 : 16)))
+        if (!tmr && (job->servers < 1 || (!pre && !buf && job->servers > (prq ? 15 : 16))))
             return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1 (and <= 16 for CIMBA_B200_MODEL_GUARDED)");
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -254,7 +259,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.trace_time = job->trace_time;
         const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
-        if (prq) {
+        if (tmr) {
+            if (trace) timers_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+            else       timers_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        else if (prq) {
             if (trace) prioq_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
             else       prioq_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
         }

@@ -33,8 +33,12 @@ namespace cimba_b200 {
 
 enum : uint32_t { ACT_WAKE_INTERRUPT = 4u, ACT_USER = 5u,
                   ACT_WAKE_PREEMPT = 6u,         // wakeup_event_preempt, src/cmb_resource.c:256-268
-                  ACT_WAKE_CONDITION = 7u };     // wakeup_event_condition, src/cmb_condition.c:85-103
-enum : uint32_t { AWAIT_TIME = 0u, AWAIT_RESOURCE = 1u };
+                  ACT_WAKE_CONDITION = 7u,       // wakeup_event_condition, src/cmb_condition.c:85-103
+                  ACT_WAKE_PROCESS = 8u,         // wakeup_event_process, src/cmb_process.c:386-410
+                  ACT_WAKE_EVENT = 9u,           // wakeup_event_event, src/cmb_event.c:176-198
+                  ACT_RESUME = 10u,              // resume_event, src/cmb_process.c:731-745
+                  ACT_BELL = 11u };              // a user event with no process behind it (model 8)
+enum : uint32_t { AWAIT_TIME = 0u, AWAIT_RESOURCE = 1u, AWAIT_PROCESS = 2u, AWAIT_EVENT = 3u };
 enum : uint32_t { PROC_CREATED = 0u, PROC_RUNNING = 1u, PROC_FINISHED = 2u };
 
 struct HeapTag {                // cmi_heap_tag (src/cmi_hashheap.h:53-59) packed to 24 bytes
@@ -238,6 +242,7 @@ constexpr int GEN_FEL_CAP = 31;
 constexpr int GEN_GUARD_CAP = 15;
 constexpr int GEN_MAX_PROCS = 8;
 constexpr int GEN_MAX_AWAITS = 4;
+constexpr int GEN_EVENT_WAITERS = 16;
 
 using EventHeap = BinHeap<GEN_FEL_CAP, EventOrder>;
 using GuardHeap = BinHeap<GEN_GUARD_CAP, GuardOrder>;
@@ -256,6 +261,12 @@ struct GenProc {                // struct cmb_process (include/cmb_process.h:116
     uint32_t holds_pool;        // a cmi_process_holdable tag for the pool is on its resources list
     uint32_t holds_tool;        // ... for the binary cmb_resource (model 5)
     uint32_t held, req, rem, initially_held;
+    // processes waiting for this one to finish (cmb_process::waiters), most recent first
+    uint8_t  waiters[GEN_MAX_PROCS];
+    uint32_t n_waiters;
+    // body-local variables of the model-8 processes
+    uint32_t timer, bell;
+    int32_t  jobs, job;
 };
 
 struct GeneralState {
@@ -277,6 +288,14 @@ struct GeneralState {
     uint32_t  pq_cap;
     uint32_t  last_handle[2];
     int32_t   level;
+    // processes waiting for events (the waiters list riding in item[3] of an event's heap
+    // tag, src/cmb_event.c:51-58), here a side table keyed by event handle, in registration order
+    uint32_t  ew_key[GEN_EVENT_WAITERS];
+    uint8_t   ew_pid[GEN_EVENT_WAITERS];
+    uint32_t  n_ew;
+    uint32_t  tool_observer;    // 1 + index of the guard registered as observer of guard[2], 0 = none
+    uint32_t  bell;             // model 8: handle of the latest bell event
+    uint32_t  clerk_start_pending;
 };
 
 constexpr uint32_t NO_HOLDER = 0xffffffffu;
@@ -344,9 +363,71 @@ struct GeneralSim {
         return key;
     }
 
+    // wake_event_waiters, src/cmb_event.c:200-221 (the list is push-front / pop-front)
+    __device__ void wake_event_waiters(uint32_t key, int32_t sig)
+    {
+        for (uint32_t k = st->n_ew; k > 0u; k--) {
+            if (st->ew_key[k - 1u] == key) {
+                const uint32_t pid = st->ew_pid[k - 1u];
+                schedule(ACT_WAKE_EVENT, pid, sig, now, st->proc[pid].prio);
+                for (uint32_t m = k - 1u; m + 1u < st->n_ew; m++) {
+                    st->ew_key[m] = st->ew_key[m + 1u];
+                    st->ew_pid[m] = st->ew_pid[m + 1u];
+                }
+                st->n_ew--;
+            }
+        }
+    }
+
+    // cmi_event_remove_waiter, src/cmb_event.c:486-508: first match from the head
+    __device__ void event_remove_waiter(uint32_t key, uint32_t pid)
+    {
+        for (uint32_t k = st->n_ew; k > 0u; k--) {
+            if (st->ew_key[k - 1u] == key && st->ew_pid[k - 1u] == pid) {
+                for (uint32_t m = k - 1u; m + 1u < st->n_ew; m++) {
+                    st->ew_key[m] = st->ew_key[m + 1u];
+                    st->ew_pid[m] = st->ew_pid[m + 1u];
+                }
+                st->n_ew--;
+                return;
+            }
+        }
+    }
+
     __device__ bool event_cancel(uint32_t handle)       // src/cmb_event.c:285-302
     {
-        return st->fel.remove(handle);
+        if (!st->fel.remove(handle)) {
+            return false;
+        }
+        if (st->n_ew != 0u) {
+            wake_event_waiters(handle, (int32_t)SIG_CANCELLED);
+        }
+        return true;
+    }
+
+    __device__ bool event_is_scheduled(uint32_t handle) const   // src/cmb_event.c:145-150
+    {
+        return st->fel.find(handle) != 0u;
+    }
+
+    __device__ bool event_reschedule(uint32_t handle, double t)         // :308-324
+    {
+        const uint32_t at = st->fel.find(handle);
+        if (at == 0u) {
+            return false;
+        }
+        st->fel.reprioritize(handle, t, st->fel.slot[at].prio);
+        return true;
+    }
+
+    __device__ bool event_reprioritize(uint32_t handle, int32_t prio)   // :330-344
+    {
+        const uint32_t at = st->fel.find(handle);
+        if (at == 0u) {
+            return false;
+        }
+        st->fel.reprioritize(handle, st->fel.slot[at].d, prio);
+        return true;
     }
 
     __device__ void cancel_events_of(uint32_t subj)     // cmb_event_pattern_cancel(ANY, subj, ANY)
@@ -377,6 +458,21 @@ struct GeneralSim {
             p.n_awaits--;
             if (type == AWAIT_TIME) {
                 (void)event_cancel(ref);
+            }
+            else if (type == AWAIT_PROCESS) {                   // cmi_process_remove_waiter, :529-551
+                GenProc &awaited = st->proc[ref];
+                for (uint32_t k = 0u; k < awaited.n_waiters; k++) {
+                    if (awaited.waiters[k] == pid) {
+                        for (uint32_t m = k; m + 1u < awaited.n_waiters; m++) {
+                            awaited.waiters[m] = awaited.waiters[m + 1u];
+                        }
+                        awaited.n_waiters--;
+                        break;
+                    }
+                }
+            }
+            else if (type == AWAIT_EVENT) {
+                event_remove_waiter(ref, pid);
             }
             // AWAIT_RESOURCE: cmb_resourceguard_remove(guard, process) searches for a key
             // equal to the process ADDRESS; entries are keyed by sequence number, so it
@@ -456,8 +552,99 @@ struct GeneralSim {
         if (p.holds_tool) {                                     // resource_drop_holder, src/cmb_resource.c:45-56
             p.holds_tool = 0u;
             st->tool_holder = NO_HOLDER;
-            signal(2u, true);
+            tool_signal();
         }
+        wake_process_waiters(pid, (int32_t)SIG_STOPPED);
+    }
+
+    // cmb_resourceguard_signal on the binary resource's guard, forwarded to its observer
+    // (src/cmb_resourceguard.c:202-242); both demands are "the resource has no holder"
+    __device__ void tool_signal()
+    {
+        signal(2u, st->tool_holder == NO_HOLDER);
+        if (st->tool_observer != 0u) {
+            signal(st->tool_observer - 1u, st->tool_holder == NO_HOLDER);
+        }
+    }
+
+    __device__ void wake_process_waiters(uint32_t pid, int32_t sig)         // src/cmb_process.c:485-505
+    {
+        GenProc &p = st->proc[pid];
+        for (uint32_t k = 0u; k < p.n_waiters; k++) {
+            const uint32_t q = p.waiters[k];
+            schedule(ACT_WAKE_PROCESS, q, sig, now, st->proc[q].prio);
+        }
+        p.n_waiters = 0u;
+    }
+
+    // cmb_process_exit for a process that holds nothing, :671-684
+    __device__ void exit(uint32_t pid)
+    {
+        cancel_awaiteds(pid);
+        wake_process_waiters(pid, (int32_t)SIG_SUCCESS);
+        st->proc[pid].status = PROC_FINISHED;
+    }
+
+    __device__ uint32_t timer_add(uint32_t pid, double dur, int32_t sig)    // :316-333
+    {
+        GenProc &p = st->proc[pid];
+        const uint32_t h = schedule(ACT_WAKE_TIME, pid, sig, __dadd_rn(now, dur), p.prio);
+        await_push(p, AWAIT_TIME, h);
+        return h;
+    }
+
+    __device__ bool timer_cancel(uint32_t pid, uint32_t handle)             // :338-349
+    {
+        (void)await_remove(st->proc[pid], AWAIT_TIME, handle);
+        return event_cancel(handle);
+    }
+
+    __device__ void timers_clear(uint32_t pid)                              // :354-381
+    {
+        GenProc &p = st->proc[pid];
+        uint32_t k = 0u;
+        while (k < p.n_awaits) {
+            if (p.await_type[k] == AWAIT_TIME) {
+                const uint32_t handle = p.await_ref[k];
+                for (uint32_t m = k; m + 1u < p.n_awaits; m++) {
+                    p.await_type[m] = p.await_type[m + 1u];
+                    p.await_ref[m] = p.await_ref[m + 1u];
+                }
+                p.n_awaits--;
+                (void)event_cancel(handle);
+            }
+            else {
+                k++;
+            }
+        }
+    }
+
+    __device__ void wait_process_begin(uint32_t pid, uint32_t awaited)      // :428-452
+    {
+        GenProc &a = st->proc[awaited];
+        await_push(st->proc[pid], AWAIT_PROCESS, awaited);
+        for (uint32_t k = a.n_waiters; k > 0u; k--) {
+            a.waiters[k] = a.waiters[k - 1u];
+        }
+        a.waiters[0] = (uint8_t)pid;
+        a.n_waiters++;
+    }
+
+    __device__ void wait_event_begin(uint32_t pid, uint32_t handle)         // :461-483
+    {
+        if (st->n_ew >= (uint32_t)GEN_EVENT_WAITERS) {
+            st->status |= TRIAL_ERR_PROC_OVERFLOW;
+            return;
+        }
+        st->ew_key[st->n_ew] = handle;
+        st->ew_pid[st->n_ew] = (uint8_t)pid;
+        st->n_ew++;
+        await_push(st->proc[pid], AWAIT_EVENT, handle);
+    }
+
+    __device__ void resume(uint32_t pid, int32_t sig)                       // :751-760
+    {
+        schedule(ACT_RESUME, pid, sig, now, st->proc[pid].prio);
     }
 
     // ---- cmb_resourcepool (src/cmb_resourcepool.c); guard index 0

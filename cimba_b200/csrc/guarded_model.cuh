@@ -164,6 +164,8 @@ guarded_kernel(const GuardedArgs a)
     st->ring_head = 0u;
     st->ring_len = 0u;
     st->guard_seq = 0u;
+    st->n_ew = 0u;
+    st->tool_observer = 0u;
     st->status = TRIAL_OK;
 
     // run_guarded_trial in ref_driver.c: priorities are drawn, and START events
@@ -173,6 +175,7 @@ guarded_kernel(const GuardedArgs a)
         p.pc = 0u;
         p.status = PROC_CREATED;
         p.n_awaits = 0u;
+        p.n_waiters = 0u;
         p.hold_handle = 0u;
         p.guard_key = 0u;
         p.stamp = 0.0;

@@ -214,6 +214,8 @@ preempt_kernel(const GuardedArgs a)
     st->pool_cap = (uint32_t)a.capacity;
     st->pool_in_use = 0u;
     st->guard_seq = 0u;
+    st->n_ew = 0u;
+    st->tool_observer = 0u;
     st->status = TRIAL_OK;
     st->ring_cap = 1u;
     st->ring_head = st->ring_len = 0u;
@@ -224,6 +226,7 @@ preempt_kernel(const GuardedArgs a)
         p.status = PROC_CREATED;
         p.kind = (i < PREEMPT_MICE) ? 0u : (i < PREEMPT_RODENTS) ? 1u : 2u;
         p.n_awaits = 0u;
+        p.n_waiters = 0u;
         p.hold_handle = p.guard_key = 0u;
         p.stamp = 0.0;
         p.holds_pool = p.holds_tool = p.held = p.req = p.rem = p.initially_held = 0u;

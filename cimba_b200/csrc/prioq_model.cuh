@@ -267,6 +267,8 @@ prioq_kernel(const GuardedArgs a)
     st->buf_cap = st->buf_level = 0u;
     st->tool_holder = NO_HOLDER;
     st->guard_seq = 0u;
+    st->n_ew = 0u;
+    st->tool_observer = 0u;
     st->status = TRIAL_OK;
     st->ring_cap = 1u;
     st->ring_head = st->ring_len = 0u;
@@ -277,6 +279,7 @@ prioq_kernel(const GuardedArgs a)
         p.status = PROC_CREATED;
         p.kind = i;
         p.n_awaits = 0u;
+        p.n_waiters = 0u;
         p.hold_handle = p.guard_key = 0u;
         p.stamp = 0.0;
         p.holds_pool = p.holds_tool = p.held = p.req = p.rem = p.initially_held = 0u;

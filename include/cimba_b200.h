@@ -56,6 +56,11 @@ extern "C" {
 #define CIMBA_B200_MODEL_PRIOQ 6   /* test/test_priorityqueue.c + test/test_condition.c: 2 producers, a consumer and a shuffler
                                     * (position / reprioritize / cancel by handle) on a cmb_priorityqueue of capacity `servers` <= 15,
                                     * a tide process signalling a cmb_condition two waiters watch, a nuisance; end at t = num_objects */
+#define CIMBA_B200_MODEL_TIMERS 8   /* tutorial/tut_3_1.c + test/test_process.c + test/test_event.c: two patients reneging on a
+                                    * cmb_resource with cmb_process_timer_add / timer_cancel / timers_clear / timer_set + yield,
+                                    * a clerk (cmb_process_resume, cmb_process_exit), a supervisor (cmb_process_wait_process, restart),
+                                    * a ringer (cmb_event_reschedule / reprioritize / cancel, cmb_process_wait_event), a listener,
+                                    * a watcher on a condition OBSERVING the desk's guard, a nuisance; end at t = num_objects */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -2471,6 +2471,543 @@ static void run_hold(int workers, uint64_t seed, uint64_t duration, double mean,
     heap_free(&fel);
 }
 
+/* ======================================== model 8: timers, waits, observers
+ *
+ * cmb_process_timer_add / timer_cancel / timers_clear / timer_set (src/cmb_process.c:316-381,
+ * include/cmb_process.h:280-289), cmb_process_yield + cmb_process_resume (:751-760),
+ * cmb_process_wait_process / wait_event with their wake-up events (:386-483, src/cmb_event.c:176-221),
+ * cmb_process_exit (:671-684) and restart of a FINISHED process, cmb_event_reschedule /
+ * reprioritize / cancel with waiter notification (src/cmb_event.c:285-344), and signal
+ * forwarding to a guard's observers (src/cmb_resourceguard.c:227-239).
+ * Workload: ref_driver.c model 8.
+ */
+enum { AW_PROCESS = 2, AW_EVENT = 3 };
+enum { ACT_WAKE_PROCESS = 8, ACT_WAKE_EVENT = 9, ACT_RESUME = 10, ACT_BELL = 11 };
+enum { SIG_STOPPED = -3, SIG_CANCELLED = -4, SIG_TIMEOUT = -5 };
+enum { T_SIG_ALARM = 77, T_SIG_DOZE = 55, T_SIG_NUDGE = 9 };
+#define T_PROCS 8
+
+typedef struct tproc {
+    gproc    g;
+    bool     holds_desk;
+    uint64_t timer, bell;
+    double   since;
+    long     jobs, j;
+    int      waiters[T_PROCS];          /* processes waiting for this one, most recent first */
+    int      n_waiters;
+} tproc;
+
+typedef struct tsim {
+    gsim     s;
+    heap     desk_guard, cv;            /* cv = the condition's guard, an observer of desk_guard */
+    tproc   *desk_holder;
+    uint64_t bell;
+    bool     clerk_start_pending;
+    struct { uint64_t key; int pid; } ew[64];   /* event waiters in registration order */
+    int      n_ew;
+    double   arr_mean, srv_mean;
+    tproc    proc[T_PROCS];
+} tsim;
+
+static void t_note(tsim *w, int64_t sig)
+{
+    if (sig != SIG_SUCCESS) {
+        w->s.res->counter[7] += (uint64_t)sig;
+    }
+}
+
+static bool t_is_scheduled(tsim *w, uint64_t handle)
+{
+    for (uint64_t k = 1u; k <= w->s.fel.count; k++) {
+        if (w->s.fel.slot[k].key == handle) {
+            return true;
+        }
+    }
+    return false;
+}
+
+/* wake_event_waiters, src/cmb_event.c:200-221: the list is push-front / pop-front */
+static void t_wake_event_waiters(tsim *w, uint64_t key, int64_t sig)
+{
+    for (int k = w->n_ew - 1; k >= 0; k--) {
+        if (w->ew[k].key == key) {
+            tproc *p = &w->proc[w->ew[k].pid];
+            g_schedule(&w->s, ACT_WAKE_EVENT, p, sig, w->s.now, p->g.prio);
+            for (int m = k; m + 1 < w->n_ew; m++) {
+                w->ew[m] = w->ew[m + 1];
+            }
+            w->n_ew--;
+        }
+    }
+}
+
+/* cmi_event_remove_waiter, src/cmb_event.c:486-508: first match from the head */
+static void t_event_remove_waiter(tsim *w, uint64_t key, int pid)
+{
+    for (int k = w->n_ew - 1; k >= 0; k--) {
+        if (w->ew[k].key == key && w->ew[k].pid == pid) {
+            for (int m = k; m + 1 < w->n_ew; m++) {
+                w->ew[m] = w->ew[m + 1];
+            }
+            w->n_ew--;
+            return;
+        }
+    }
+}
+
+/* cmb_event_cancel, src/cmb_event.c:285-302 */
+static bool t_event_cancel(tsim *w, uint64_t handle)
+{
+    if (!heap_remove(&w->s.fel, handle)) {
+        return false;
+    }
+    t_wake_event_waiters(w, handle, SIG_CANCELLED);
+    return true;
+}
+
+/* wake_process_waiters, src/cmb_process.c:485-505 */
+static void t_wake_process_waiters(tsim *w, tproc *p, int64_t sig)
+{
+    for (int k = 0; k < p->n_waiters; k++) {
+        tproc *q = &w->proc[p->waiters[k]];
+        g_schedule(&w->s, ACT_WAKE_PROCESS, q, sig, w->s.now, q->g.prio);
+    }
+    p->n_waiters = 0;
+}
+
+/* cmi_process_cancel_awaiteds, src/cmb_process.c:581-620 */
+static void t_cancel_awaiteds(tsim *w, tproc *p)
+{
+    gsim *s = &w->s;
+    const int pid = (int)(p - w->proc);
+    while (p->g.n_awaits > 0) {
+        const int type = p->g.awaits[0].type;
+        const uint64_t handle = p->g.awaits[0].handle;
+        void *ptr = p->g.awaits[0].ptr;
+        for (int m = 0; m + 1 < p->g.n_awaits; m++) {
+            p->g.awaits[m] = p->g.awaits[m + 1];
+        }
+        p->g.n_awaits--;
+        if (type == AW_TIME) {
+            (void)t_event_cancel(w, handle);
+        }
+        else if (type == AW_RESOURCE) {
+            (void)g_guard_remove((heap *)ptr, &p->g);   /* never hits: SURVEY.md quirk 2 */
+        }
+        else if (type == AW_PROCESS) {
+            tproc *awaited = ptr;                       /* cmi_process_remove_waiter, :529-551 */
+            for (int k = 0; k < awaited->n_waiters; k++) {
+                if (awaited->waiters[k] == pid) {
+                    for (int m = k; m + 1 < awaited->n_waiters; m++) {
+                        awaited->waiters[m] = awaited->waiters[m + 1];
+                    }
+                    awaited->n_waiters--;
+                    break;
+                }
+            }
+        }
+        else {
+            t_event_remove_waiter(w, handle, pid);
+        }
+    }
+    uint64_t hit[64];                                   /* cmb_event_pattern_cancel(ANY, p, ANY) */
+    unsigned n = 0u;
+    for (uint64_t k = 1u; k <= s->fel.count && n < 64u; k++) {
+        if ((void *)(intptr_t)s->fel.slot[k].item[1] == (void *)p) {
+            hit[n++] = s->fel.slot[k].key;
+        }
+    }
+    for (unsigned k = 0u; k < n; k++) {
+        (void)t_event_cancel(w, hit[k]);
+    }
+}
+
+/* cmb_process_timer_add, src/cmb_process.c:316-333 */
+static uint64_t t_timer_add(tsim *w, tproc *p, double dur, int64_t sig)
+{
+    const uint64_t h = g_schedule(&w->s, ACT_WAKE_TIME, p, sig, w->s.now + dur, p->g.prio);
+    aw_push(&p->g, AW_TIME, h, NULL);
+    return h;
+}
+
+/* cmb_process_timer_cancel, :338-349 */
+static bool t_timer_cancel(tsim *w, tproc *p, uint64_t handle)
+{
+    (void)aw_remove(&p->g, AW_TIME, false, handle, NULL);
+    return t_event_cancel(w, handle);
+}
+
+/* cmb_process_timers_clear, :354-381: list order, other awaitables skipped */
+static void t_timers_clear(tsim *w, tproc *p)
+{
+    int k = 0;
+    while (k < p->g.n_awaits) {
+        if (p->g.awaits[k].type == AW_TIME) {
+            const uint64_t handle = p->g.awaits[k].handle;
+            for (int m = k; m + 1 < p->g.n_awaits; m++) {
+                p->g.awaits[m] = p->g.awaits[m + 1];
+            }
+            p->g.n_awaits--;
+            (void)t_event_cancel(w, handle);
+        }
+        else {
+            k++;
+        }
+    }
+}
+
+/* cmb_resourceguard_signal on the desk's guard, then on its observer (the condition's guard),
+ * src/cmb_resourceguard.c:202-242; both demands are "the desk has no holder" */
+static void t_desk_signal(tsim *w)
+{
+    g_signal(&w->s, &w->desk_guard, w->desk_holder == NULL);
+    g_signal(&w->s, &w->cv, w->desk_holder == NULL);
+}
+
+/* cmb_process_wait_event up to its yield, src/cmb_process.c:461-483 */
+static void t_wait_event_begin(tsim *w, tproc *p, uint64_t handle)
+{
+    w->ew[w->n_ew].key = handle;
+    w->ew[w->n_ew].pid = (int)(p - w->proc);
+    w->n_ew++;
+    aw_push(&p->g, AW_EVENT, handle, NULL);
+}
+
+static void t_body(tsim *w, tproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    tproc *clerk = &w->proc[2];
+    switch (p->g.kind * 10 + p->g.pc) {
+    /* ---- patients */
+    case 0:
+        for (;;) {
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, w->arr_mean));
+            p->g.pc = 1;
+            return;
+    case 1:
+            t_note(w, g_hold_end(s, &p->g, sig));
+            p->timer = t_timer_add(w, p, port_exponential(&s->rng, 2.0 * w->srv_mean), SIG_TIMEOUT);
+            if (w->desk_holder == NULL) {               /* cmb_resource_acquire, src/cmb_resource.c:191-229 */
+                w->desk_holder = p;
+                p->holds_desk = true;
+                sig = SIG_SUCCESS;
+            }
+            else {
+                g_wait_begin(s, &w->desk_guard, &p->g);
+                p->g.pc = 2;
+                return;
+    case 2:
+                sig = g_wait_end(s, &w->desk_guard, &p->g, sig);
+                if (sig == SIG_SUCCESS) {
+                    w->desk_holder = p;
+                    p->holds_desk = true;
+                }
+            }
+            if (sig == SIG_SUCCESS) {
+                (void)t_timer_cancel(w, p, p->timer);
+                s->res->counter[0] += 1u;
+                p->since = s->now;
+                (void)t_timer_add(w, p, port_exponential(&s->rng, 3.0), T_SIG_ALARM);
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, w->srv_mean));
+                p->g.pc = 3;
+                return;
+    case 3:
+                t_note(w, g_hold_end(s, &p->g, sig));
+                t_timers_clear(w, p);
+                p->holds_desk = false;                  /* cmb_resource_release, :234-250 */
+                w->desk_holder = NULL;
+                t_desk_signal(w);
+                s->res->sum_wait += s->now - p->since;
+                t_timers_clear(w, p);                   /* cmb_process_timer_set = clear + add */
+                (void)t_timer_add(w, p, port_exponential(&s->rng, 0.3), T_SIG_DOZE);
+                p->g.pc = 4;                            /* cmb_process_yield */
+                return;
+    case 4:
+                t_note(w, sig);
+                if (sig != T_SIG_DOZE) {
+                    t_timers_clear(w, p);
+                }
+            }
+            else if (sig == SIG_TIMEOUT) {
+                s->res->counter[1] += 1u;
+            }
+            else {
+                t_note(w, sig);
+                t_timers_clear(w, p);
+            }
+        }
+    /* ---- clerk */
+    case 10:
+        w->clerk_start_pending = false;
+        p->jobs = port_dice(&s->rng, 2, 5);
+        for (p->j = 0; p->j < p->jobs; p->j++) {
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 1;
+            return;
+    case 11:
+            t_note(w, g_hold_end(s, &p->g, sig));
+            if (port_dice(&s->rng, 0, 2) == 0) {        /* cmb_process_resume, :751-760 */
+                tproc *tgt = &w->proc[port_dice(&s->rng, 0, 1)];
+                g_schedule(s, ACT_RESUME, tgt, T_SIG_NUDGE, s->now, tgt->g.prio);
+            }
+            s->res->counter[3] += 1u;
+        }
+        /* cmb_process_exit, :671-684: nothing held, nothing awaited */
+        t_cancel_awaiteds(w, p);
+        t_wake_process_waiters(w, p, SIG_SUCCESS);
+        p->g.status = ST_FINISHED;
+        return;
+    /* ---- supervisor */
+    case 20:
+        for (;;) {
+            if (clerk->g.status == ST_FINISHED) {       /* cmb_process_wait_process, :428-452 */
+                sig = SIG_SUCCESS;
+            }
+            else {
+                aw_push(&p->g, AW_PROCESS, 0u, clerk);
+                for (int k = clerk->n_waiters; k > 0; k--) {
+                    clerk->waiters[k] = clerk->waiters[k - 1];
+                }
+                clerk->waiters[0] = (int)(p - w->proc);
+                clerk->n_waiters++;
+                p->g.pc = 1;
+                return;
+            }
+            /* fall through */
+    case 21:
+            if (sig == SIG_SUCCESS) {
+                s->res->counter[2] += 1u;
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 0.5));
+                p->g.pc = 2;
+                return;
+    case 22:
+                t_note(w, g_hold_end(s, &p->g, sig));
+                if (clerk->g.status == ST_FINISHED && !w->clerk_start_pending) {
+                    w->clerk_start_pending = true;
+                    g_schedule(s, ACT_START, clerk, 0, s->now, clerk->g.prio);
+                }
+            }
+            else {
+                t_note(w, sig);
+            }
+        }
+    /* ---- ringer */
+    case 30:
+        for (;;) {
+            {
+                const double when = s->now + port_exponential(&s->rng, 2.0);
+                const int64_t pri = port_dice(&s->rng, -2, 2);
+                p->bell = g_schedule(s, ACT_BELL, w, 0, when, pri);
+                w->bell = p->bell;
+            }
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 0.7));
+            p->g.pc = 1;
+            return;
+    case 31:
+            t_note(w, g_hold_end(s, &p->g, sig));
+            if (t_is_scheduled(w, p->bell)) {
+                const long op = port_dice(&s->rng, 0, 3);
+                uint64_t at = 0u;
+                for (uint64_t k = 1u; k <= s->fel.count; k++) {
+                    if (s->fel.slot[k].key == p->bell) {
+                        at = k;
+                    }
+                }
+                if (op == 0) {                          /* cmb_event_reschedule, src/cmb_event.c:308-324 */
+                    const double t = s->now + port_exponential(&s->rng, 1.0);
+                    heap_reprioritize(&s->fel, p->bell, t, s->fel.slot[at].i);
+                    s->res->counter[5] += 1u;
+                }
+                else if (op == 1) {                     /* cmb_event_reprioritize, :330-344 */
+                    const int64_t pri = port_dice(&s->rng, -5, 5);
+                    heap_reprioritize(&s->fel, p->bell, s->fel.slot[at].d, pri);
+                    s->res->counter[5] += 100u;
+                }
+                else if (op == 2) {
+                    (void)t_event_cancel(w, p->bell);
+                    s->res->counter[5] += 10000u;
+                }
+            }
+            if (t_is_scheduled(w, p->bell)) {
+                t_wait_event_begin(w, p, p->bell);
+                p->g.pc = 2;
+                return;
+    case 32:
+                t_note(w, sig);
+            }
+        }
+    /* ---- listener */
+    case 40:
+        for (;;) {
+            p->bell = w->bell;
+            if (p->bell != 0u && t_is_scheduled(w, p->bell)) {
+                t_wait_event_begin(w, p, p->bell);
+                p->g.pc = 1;
+                return;
+    case 41:
+                if (sig == SIG_SUCCESS) {
+                    s->res->counter[6] += 1000u;
+                }
+                else {
+                    t_note(w, sig);
+                }
+            }
+            else {
+                g_hold_begin(s, &p->g, port_exponential(&s->rng, 0.5));
+                p->g.pc = 2;
+                return;
+    case 42:
+                t_note(w, g_hold_end(s, &p->g, sig));
+            }
+        }
+    /* ---- watcher: cmb_condition_wait = cmb_resourceguard_wait on the condition's guard */
+    case 50:
+        for (;;) {
+            g_wait_begin(s, &w->cv, &p->g);
+            p->g.pc = 1;
+            return;
+    case 51:
+            sig = g_wait_end(s, &w->cv, &p->g, sig);
+            if (sig == SIG_SUCCESS) {
+                s->res->counter[6] += 1u;
+            }
+            else {
+                t_note(w, sig);
+            }
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 0.8));
+            p->g.pc = 2;
+            return;
+    case 52:
+            t_note(w, g_hold_end(s, &p->g, sig));
+        }
+    /* ---- nuisance */
+    case 60:
+        for (;;) {
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, 1.0));
+            p->g.pc = 1;
+            return;
+    case 61:
+            (void)g_hold_end(s, &p->g, sig);
+            {
+                tproc *victim = &w->proc[port_dice(&s->rng, 0, T_PROCS - 2)];
+                const int64_t isig = port_dice(&s->rng, 1, 10);
+                const int64_t ipri = port_dice(&s->rng, -5, 5);
+                if (victim->g.status == ST_RUNNING) {
+                    g_schedule(s, ACT_WAKE_INTERRUPT, victim, isig, s->now, ipri);
+                }
+            }
+        }
+    }
+}
+
+/* cmb_process_stop, src/cmb_process.c:698-723 */
+static void t_stop(tsim *w, tproc *p)
+{
+    if (p->g.status != ST_RUNNING) {
+        return;
+    }
+    p->g.status = ST_FINISHED;
+    t_cancel_awaiteds(w, p);
+    if (p->holds_desk) {                                /* resource_drop_holder, src/cmb_resource.c:45-56 */
+        p->holds_desk = false;
+        w->desk_holder = NULL;
+        t_desk_signal(w);
+    }
+    t_wake_process_waiters(w, p, SIG_STOPPED);
+}
+
+static void run_timers(uint64_t seed, uint64_t duration, double arr_mean, double srv_mean,
+                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    static const int kind_of[T_PROCS] = { 0, 0, 1, 2, 3, 4, 5, 6 };
+    tsim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    w->arr_mean = arr_mean;
+    w->srv_mean = srv_mean;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&w->desk_guard, 3u, guard_before);
+    heap_init(&w->cv, 3u, guard_before);
+
+    for (int i = 0; i < T_PROCS; i++) {
+        w->proc[i].g.kind = kind_of[i];
+        w->proc[i].g.prio = (i + 1 < T_PROCS) ? port_dice(&s->rng, -5, 5) : 0;
+        g_schedule(s, ACT_START, &w->proc[i], 0, s->now, w->proc[i].g.prio);
+    }
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        t_wake_event_waiters(w, ev.key, SIG_SUCCESS);   /* src/cmb_event.c:243-246 */
+        tproc *p = (tproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->g.status = ST_RUNNING;
+            p->g.pc = 0;
+            t_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(&p->g, AW_TIME, false, ev.key, NULL);
+            t_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+            if (p->g.status == ST_RUNNING) {
+                t_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_PROCESS:                          /* src/cmb_process.c:386-410 */
+            (void)aw_remove(&p->g, AW_PROCESS, true, 0u, NULL);
+            if (p->g.status == ST_RUNNING) {
+                t_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_EVENT:                            /* src/cmb_event.c:176-198 */
+            (void)aw_remove(&p->g, AW_EVENT, true, 0u, NULL);
+            if (p->g.status == ST_RUNNING) {
+                t_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_RESUME:                                /* src/cmb_process.c:731-745 */
+            t_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_INTERRUPT:
+            t_cancel_awaiteds(w, p);
+            t_body(w, p, ev.item[2]);
+            break;
+        case ACT_BELL:
+            out->counter[4] += 1u;
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i < T_PROCS; i++) {
+                t_stop(w, &w->proc[i]);
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->objects = out->counter[0];
+    heap_free(&s->fel);
+    heap_free(&w->desk_guard);
+    heap_free(&w->cv);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -2488,6 +3025,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 8) {
+            run_timers(port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 7) {
             run_hold(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -2546,6 +3088,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 8) {
+        run_timers(seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 7) {
         run_hold(servers, seed, num_objects, arr_mean, trace_cap, trace_key, trace_time, out);
         return 0;

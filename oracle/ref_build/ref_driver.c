@@ -872,6 +872,267 @@ static void run_hold_trial(struct ref_trial *t)
     free(w);
 }
 
+/* ------------------------------------------------- model 8: timers, waits, observers
+ *
+ * The remaining asynchronous calls of cmb_process / cmb_event / cmb_resourceguard in one
+ * workload, in the manner of tutorial/tut_3_1.c (reneging with cmb_process_timer_add /
+ * timer_set / timers_clear, cmb_process_yield + cmb_process_resume) and
+ * test/test_process.c:104-129 (cmb_process_wait_event, cmb_process_wait_process,
+ * cmb_process_exit) and test/test_event.c:175-181 (cmb_event_reschedule / reprioritize):
+ *   0,1 patients   hold; patience timer; cmb_resource_acquire(desk) (renege on TIMEOUT);
+ *                  timer_cancel; alarm timer; service hold; timers_clear; release;
+ *                  timer_set + cmb_process_yield
+ *   2   clerk      a few holds, now and then cmb_process_resume(patient, 9), then
+ *                  cmb_process_exit
+ *   3   supervisor cmb_process_wait_process(clerk); hold; restart the FINISHED clerk
+ *   4   ringer     schedules a bell event, holds, then reschedules / reprioritizes /
+ *                  cancels it (waiters get CANCELLED), then cmb_process_wait_event
+ *   5   listener   cmb_process_wait_event(current bell)
+ *   6   watcher    cmb_condition_wait on a condition whose guard is registered as an
+ *                  OBSERVER of the desk's guard (cmb_resourceguard_register,
+ *                  src/cmb_resourceguard.c:231-239 forwards every signal)
+ *   7   nuisance   interrupts one of 0..6 with a random signal at a random priority
+ * and an end event at t = num_objects stopping all eight (bells still pending ring later).
+ * counters: [0] desk acquisitions [1] reneges [2] supervisor saw the clerk finish
+ *           [3] clerk jobs [4] bell rings [5] ringer ops (1 resched, 100 reprio, 10000 cancel)
+ *           [6] watcher passes + 1000 * bells heard by the listener [7] sum of signals
+ * sum_wait = sum of desk occupation times
+ */
+#define T_PROCS 8u
+#define T_SIG_ALARM 77
+#define T_SIG_DOZE 55
+#define T_SIG_NUDGE 9
+
+struct t_world {
+    struct ref_trial *trl;
+    struct cmb_resource *desk;
+    struct cmb_condition *cv;
+    struct cmb_process *proc;           /* T_PROCS contiguous */
+    uint64_t bell;
+    bool clerk_start_pending;
+};
+
+static void t_note(struct t_world *w, int64_t sig)
+{
+    if (sig != CMB_PROCESS_SUCCESS) {
+        w->trl->counter[7] += (uint64_t)sig;
+    }
+}
+
+static void *t_patient_body(struct cmb_process *me, void *vw)
+{
+    struct t_world *w = vw;
+    for (;;) {
+        t_note(w, cmb_process_hold(cmb_random_exponential(w->trl->arr_mean)));
+        const uint64_t patience = cmb_process_timer_add(me, cmb_random_exponential(2.0 * w->trl->srv_mean),
+                                                        CMB_PROCESS_TIMEOUT);
+        int64_t sig = cmb_resource_acquire(w->desk);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            (void)cmb_process_timer_cancel(me, patience);
+            w->trl->counter[0] += 1u;
+            const double since = cmb_time();
+            (void)cmb_process_timer_add(me, cmb_random_exponential(3.0), T_SIG_ALARM);
+            t_note(w, cmb_process_hold(cmb_random_exponential(w->trl->srv_mean)));
+            cmb_process_timers_clear(me);
+            cmb_resource_release(w->desk);
+            w->trl->sum_wait += cmb_time() - since;
+            (void)cmb_process_timer_set(me, cmb_random_exponential(0.3), T_SIG_DOZE);
+            sig = cmb_process_yield();
+            t_note(w, sig);
+            if (sig != T_SIG_DOZE) {
+                cmb_process_timers_clear(me);
+            }
+        }
+        else if (sig == CMB_PROCESS_TIMEOUT) {
+            w->trl->counter[1] += 1u;
+        }
+        else {
+            t_note(w, sig);
+            cmb_process_timers_clear(me);
+        }
+    }
+}
+
+static void *t_clerk_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    w->clerk_start_pending = false;
+    const long jobs = cmb_random_dice(2, 5);
+    for (long j = 0; j < jobs; j++) {
+        t_note(w, cmb_process_hold(cmb_random_exponential(1.0)));
+        if (cmb_random_dice(0, 2) == 0) {
+            cmb_process_resume(&w->proc[cmb_random_dice(0, 1)], T_SIG_NUDGE);
+        }
+        w->trl->counter[3] += 1u;
+    }
+    cmb_process_exit((void *)(uintptr_t)jobs);
+    return NULL;
+}
+
+static void *t_supervisor_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    struct cmb_process *clerk = &w->proc[2];
+    for (;;) {
+        const int64_t sig = cmb_process_wait_process(clerk);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[2] += 1u;
+            t_note(w, cmb_process_hold(cmb_random_exponential(0.5)));
+            if (cmb_process_status(clerk) == CMB_PROCESS_FINISHED && !w->clerk_start_pending) {
+                w->clerk_start_pending = true;
+                cmb_process_start(clerk);
+            }
+        }
+        else {
+            t_note(w, sig);
+        }
+    }
+}
+
+static void t_bell_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct t_world *w = subject;
+    w->trl->counter[4] += 1u;
+}
+
+static void *t_ringer_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    for (;;) {
+        const double when = cmb_time() + cmb_random_exponential(2.0);
+        const uint64_t h = cmb_event_schedule(t_bell_event, w, NULL, when, cmb_random_dice(-2, 2));
+        w->bell = h;
+        t_note(w, cmb_process_hold(cmb_random_exponential(0.7)));
+        if (cmb_event_is_scheduled(h)) {
+            const long op = cmb_random_dice(0, 3);
+            if (op == 0) {
+                (void)cmb_event_reschedule(h, cmb_time() + cmb_random_exponential(1.0));
+                w->trl->counter[5] += 1u;
+            }
+            else if (op == 1) {
+                (void)cmb_event_reprioritize(h, cmb_random_dice(-5, 5));
+                w->trl->counter[5] += 100u;
+            }
+            else if (op == 2) {
+                (void)cmb_event_cancel(h);
+                w->trl->counter[5] += 10000u;
+            }
+        }
+        if (cmb_event_is_scheduled(h)) {
+            t_note(w, cmb_process_wait_event(h));
+        }
+    }
+}
+
+static void *t_listener_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    for (;;) {
+        const uint64_t h = w->bell;
+        if (h != 0u && cmb_event_is_scheduled(h)) {
+            const int64_t sig = cmb_process_wait_event(h);
+            if (sig == CMB_PROCESS_SUCCESS) {
+                w->trl->counter[6] += 1000u;
+            }
+            else {
+                t_note(w, sig);
+            }
+        }
+        else {
+            t_note(w, cmb_process_hold(cmb_random_exponential(0.5)));
+        }
+    }
+}
+
+static bool t_desk_is_free(const struct cmb_condition *cvp, const struct cmb_process *pp, const void *ctx)
+{
+    cmb_unused(cvp);
+    cmb_unused(pp);
+    const struct t_world *w = ctx;
+    return w->desk->holder == NULL;
+}
+
+static void *t_watcher_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    for (;;) {
+        const int64_t sig = cmb_condition_wait(w->cv, t_desk_is_free, w);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[6] += 1u;
+        }
+        else {
+            t_note(w, sig);
+        }
+        t_note(w, cmb_process_hold(cmb_random_exponential(0.8)));
+    }
+}
+
+static void *t_nuisance_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct t_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)T_PROCS - 2);
+        const int64_t sig = cmb_random_dice(1, 10);
+        const int64_t pri = cmb_random_dice(-5, 5);
+        /* the clerk may have exited: interrupting a FINISHED process would resume a dead coroutine */
+        if (cmb_process_status(&w->proc[victim]) == CMB_PROCESS_RUNNING) {
+            cmb_process_interrupt(&w->proc[victim], sig, pri);
+        }
+    }
+}
+
+static void t_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct t_world *w = subject;
+    for (unsigned i = 0u; i < T_PROCS; i++) {
+        if (cmb_process_status(&w->proc[i]) == CMB_PROCESS_RUNNING) {
+            cmb_process_stop(&w->proc[i], NULL);
+        }
+    }
+}
+
+static void run_timers_trial(struct ref_trial *t)
+{
+    struct t_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->desk = cmb_resource_create();
+    cmb_resource_initialize(w->desk, "Desk");
+    w->cv = cmb_condition_create();
+    cmb_condition_initialize(w->cv, "DeskFree");
+    cmb_resourceguard_register(&w->desk->guard, &w->cv->guard);
+    w->proc = calloc(T_PROCS, sizeof(struct cmb_process));
+    cmb_process_func *body[T_PROCS] = { t_patient_body, t_patient_body, t_clerk_body, t_supervisor_body,
+                                        t_ringer_body, t_listener_body, t_watcher_body, t_nuisance_body };
+    for (unsigned i = 0u; i < T_PROCS; i++) {
+        const int64_t pri = (i + 1u < T_PROCS) ? cmb_random_dice(-5, 5) : 0;
+        cmb_process_initialize(&w->proc[i], "Proc", body[i], w, pri);
+        cmb_process_start(&w->proc[i]);
+    }
+    (void)cmb_event_schedule(t_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->objects = t->counter[0];
+    for (unsigned i = 0u; i < T_PROCS; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    (void)cmb_resourceguard_unregister(&w->desk->guard, &w->cv->guard);
+    cmb_condition_destroy(w->cv);
+    cmb_resource_destroy(w->desk);
+    free(w);
+}
+
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -954,7 +1215,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 7) {
+    if (t->model == 8) {
+        run_timers_trial(t);
+    }
+    else if (t->model == 7) {
         run_hold_trial(t);
     }
     else if (t->model == 6) {

@@ -33,7 +33,8 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           4: dict(arr=1.0, srv=1.0, servers=20),     # model 4: num_objects = duration, servers = pool capacity
           5: dict(arr=1.0, srv=1.0, servers=10),     # model 5: num_objects = duration, servers = buffer capacity
           6: dict(arr=1.0, srv=1.0, servers=8),      # model 6: num_objects = duration, servers = queue capacity
-          7: dict(arr=1.0, srv=1.0, servers=200)}    # model 7: num_objects = duration, servers = worker processes
+          7: dict(arr=1.0, srv=1.0, servers=200),    # model 7: num_objects = duration, servers = worker processes
+          8: dict(arr=1.0, srv=0.6, servers=1)}      # model 8: num_objects = duration
 
 
 def hexes(a):
@@ -71,15 +72,16 @@ def main():
         for seed in SEEDS:
             # model 3: the size is a duration; 0 would stop workers before they start (they then
             # run forever in the reference), so it starts at 1
-            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model < 3 else ((1, 2, 3, 10, 100, 1000) if model < 7 else (1, 2, 3, 10, 50))):
+            traced = 10 if model == 7 else 1000
+            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model < 3 else ((1, 2, 3, 10, 50) if model == 7 else (1, 2, 3, 10, 100, 1000))):
                 r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
-                                             par["arr"], par["srv"], 512 if nobj == (1000 if model < 7 else 10) else 0)
+                                             par["arr"], par["srv"], 512 if nobj == traced else 0)
                 rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
                        "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                        "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
                        "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
                        "counters": r.counters()}
-                if nobj == (1000 if model < 7 else 10):
+                if nobj == traced:
                     rec["trace_key"] = [int(k) for k in keys]
                     rec["trace_time"] = hexes(times)
                 trials.append(rec)

@@ -21,6 +21,11 @@ def _u64(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
+def _counts(t):
+    """Device counters are uint64 carried in an int64 tensor (sums of negative signals wrap)."""
+    return np.ascontiguousarray(t.cpu().numpy(), dtype=np.int64).view(np.uint64).tolist()
+
+
 def _compare(res, want, tag=""):
     ev, ob = res.events.cpu().numpy(), res.objects.cpu().numpy()
     te, sw = res.t_end.cpu().numpy(), res.sum_wait.cpu().numpy()
@@ -289,7 +294,7 @@ def test_guarded_queue_under_interrupts_matches_oracle(cb, port, cap, dur, pm, g
                         model=cb.MODEL_GUARDED, servers=cap)
     want = run_trials(port, "port", 3, cap, KAT_SEED, 0, n, dur, pm, gm)
     _compare(res, want, ("guarded", cap))
-    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
     assert sum(w.counters()[2] + w.counters()[3] + w.counters()[4] for w in want) > 100   # interrupts really hit
 
@@ -315,7 +320,7 @@ def test_pool_preemption_matches_oracle(cb, port, cap, dur):
                         model=cb.MODEL_PREEMPT, servers=cap)
     want = run_trials(port, "port", 4, cap, KAT_SEED, 0, n, dur, 1.0, 1.0)
     _compare(res, want, ("preempt", cap))
-    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
     assert all(w.counters()[7] == 0 and w.counters()[6] == 0 for w in want)     # holdings consistent, all dropped
     if cap == 20:
@@ -342,7 +347,7 @@ def test_buffer_and_resource_match_oracle(cb, port, cap, dur, pm, gm):
                         model=cb.MODEL_BUFFER, servers=cap)
     want = run_trials(port, "port", 5, cap, KAT_SEED, 0, n, dur, pm, gm)
     _compare(res, want, ("buffer", cap))
-    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
 
 
@@ -366,7 +371,7 @@ def test_priorityqueue_and_condition_match_oracle(cb, port, cap, dur, pm, gm):
                         model=cb.MODEL_PRIOQ, servers=cap)
     want = run_trials(port, "port", 6, cap, KAT_SEED, 0, n, dur, pm, gm)
     _compare(res, want, ("prioq", cap))
-    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
 
 
@@ -377,6 +382,36 @@ def test_priorityqueue_and_condition_pop_order_bit_exact(cb, port):
     keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
     for i in range(n):
         r, k, t = trace_trial(port, "port", 6, 6, cb.fmix64(66, i), dur, 1.0, 1.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+# ------------------------------------------------------------------ timers, waits, observers (model 8)
+
+@pytest.mark.parametrize("dur,am,sm", [(500, 1.0, 0.6), (300, 0.4, 1.2), (200, 2.0, 0.3), (1, 1.0, 1.0), (3, 1.0, 1.0)])
+def test_timers_waits_observers_match_oracle(cb, port, dur, am, sm):
+    """cmb_process_timer_add/cancel/clear/set, yield + resume, wait_process, wait_event, exit + restart,
+    cmb_event_reschedule/reprioritize/cancel with waiter notification, guard observers - under interrupts."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=am, srv_mean=sm, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_TIMERS, servers=1)
+    want = run_trials(port, "port", 8, 1, KAT_SEED, 0, n, dur, am, sm)
+    _compare(res, want, ("timers", dur))
+    assert _counts(res.counters) == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
+    if dur >= 200:
+        c = res.counters.cpu().numpy().sum(axis=0)
+        assert c[0] > 0 and c[1] > 0 and c[2] > 0 and c[3] > 0 and c[4] > 0 and c[5] >= 10101 and c[6] >= 1001
+
+
+def test_timers_waits_observers_pop_order_bit_exact(cb, port):
+    n, cap, dur = 16, 8000, 500
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=0.6, num_objects=dur, master_seed=88,
+                        model=cb.MODEL_TIMERS, servers=1, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 8, 1, cb.fmix64(88, i), dur, 1.0, 0.6, cap)
         m = min(cap, r.events)
         assert list(keys[i, :m]) == k, i
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
@@ -394,7 +429,7 @@ def test_hold_model_matches_oracle(cb, port, workers, dur, mean):
                         model=cb.MODEL_HOLD, servers=workers)
     want = run_trials(port, "port", 7, workers, KAT_SEED, 0, n, dur, mean, 1.0)
     _compare(res, want, ("hold", workers))
-    assert res.counters.cpu().tolist() == [w.counters() for w in want]
+    assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
 
 

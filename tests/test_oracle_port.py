@@ -164,19 +164,20 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (4, 1.0, 1.0, 20), (4, 1.0, 1.0, 5),
                                                    (5, 1.0, 1.0, 10), (5, 0.5, 1.0, 2),
                                                    (6, 1.0, 1.0, 8), (6, 0.5, 1.0, 2),
-                                                   (7, 1.0, 1.0, 500), (7, 0.5, 1.0, 5)])
+                                                   (7, 1.0, 1.0, 500), (7, 0.5, 1.0, 5),
+                                                   (8, 1.0, 0.6, 1), (8, 0.4, 1.2, 1)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
     n = 48
-    size = 20_000 if model < 3 else (1500 if model < 7 else 30)    # models 3..7: duration in time units
+    size = 20_000 if model < 3 else (30 if model == 7 else 1500)    # models 3..8: duration in time units
     a = run_trials(ref, "ref", model, servers, 0xC0FFEE, 100, n, size, arr, srv, par=0)
     b = run_trials(port, "port", model, servers, 0xC0FFEE, 100, n, size, arr, srv)
     assert [x.key() for x in a] == [x.key() for x in b]
     assert [(x.max_fel, x.max_queue) for x in a] == [(x.max_fel, x.max_queue) for x in b]
     assert [x.counters() for x in a] == [x.counters() for x in b]
-    ra, ka, ta = trace_trial(ref, "ref", model, servers, 99, 3000 if model < 3 else (800 if model < 7 else 15), arr, srv, 9000)
-    rb, kb, tb = trace_trial(port, "port", model, servers, 99, 3000 if model < 3 else (800 if model < 7 else 15), arr, srv, 9000)
+    ra, ka, ta = trace_trial(ref, "ref", model, servers, 99, 3000 if model < 3 else (15 if model == 7 else 800), arr, srv, 9000)
+    rb, kb, tb = trace_trial(port, "port", model, servers, 99, 3000 if model < 3 else (15 if model == 7 else 800), arr, srv, 9000)
     assert ka == kb and ta == tb and ra.key() == rb.key()
 
 
