@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
 
 NO_FIELD = C.c_size_t(-1).value
 
-MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS = 0, 1, 2, 3, 4, 5, 6, 7, 8
+MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 MAP_LANE, MAP_WARP = 1, 32
 
 OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -58,6 +58,11 @@ class DataSummaryStruct(C.Structure):
     ]
 
 
+class WtdSummaryStruct(C.Structure):
+    """struct cimba_b200_wtdsummary == reference struct cmb_wtdsummary layout"""
+    _fields_ = [("base", DataSummaryStruct), ("wsum", C.c_double)]
+
+
 # every symbol include/cimba_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "cimba_b200_workspace_bytes": (C.c_uint64, [C.POINTER(DeviceJob)]),
@@ -73,6 +78,13 @@ SYMBOLS = {
     "cimba_b200_datasummary_mean": (C.c_double, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_variance": (C.c_double, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_stddev": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_summarize_weighted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cimba_b200_merge_weighted_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cimba_b200_wtdsummary_initialize": (None, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_add": (C.c_uint64, [C.POINTER(WtdSummaryStruct), C.c_double, C.c_double]),
+    "cimba_b200_wtdsummary_merge": (C.c_uint64, [C.POINTER(WtdSummaryStruct)] * 3),
+    "cimba_b200_wtdsummary_mean": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_variance": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
     "cimba_b200_fmix64": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "cimba_b200_rng_draws": (C.c_int, [C.c_uint64, C.c_int, C.c_double, C.c_double,
                                        C.c_uint64, C.c_void_p, C.c_void_p]),

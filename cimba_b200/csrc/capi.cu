@@ -56,7 +56,10 @@ int cuda_fail(cudaError_t e, const char *where)
 
 constexpr uint32_t QUEUE_SPILL_CAP = 512u;     // doubles per trial behind the 32-entry window
 
-bool is_queue_model(int m) { return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1; }
+bool is_queue_model(int m)
+{
+    return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1 || m == CIMBA_B200_MODEL_MM1_RECORDED;
+}
 bool is_general_model(int m)
 {
     return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
@@ -171,6 +174,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         qa.sum_wait = job->sum_wait;
         qa.status = job->status;
         qa.max_queue = job->max_queue;
+        qa.counters = job->counters;
         qa.spill = (double *)job->workspace;
         qa.spill_cap = QUEUE_SPILL_CAP;
         qa.trace_cap = job->trace_cap;
@@ -181,6 +185,15 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
         dim3 grid((unsigned)blocks);
         if (job->model == CIMBA_B200_MODEL_GG1) return launch_queue<1>(qa, trace, grid, st);
+        if (job->model == CIMBA_B200_MODEL_MM1_RECORDED) {
+            if (job->counters == nullptr)
+                return fail(CIMBA_B200_EINVAL, "CIMBA_B200_MODEL_MM1_RECORDED writes its cmb_wtdsummary to counters[]");
+            if (trace) queue_kernel<0, true, true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+            else       queue_kernel<0, false, true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+            g_launches++;
+            cudaError_t e = cudaGetLastError();
+            return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "queue_kernel (recorded) launch");
+        }
         if (job->variant == 1) return launch_queue<0>(qa, trace, grid, st);
         if (trace) {
             mm1_kernel<true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
@@ -494,6 +507,78 @@ int cimba_b200_run_experiment_all_gpus(void *array, uint64_t num_trials, size_t 
         }
     }
     return worst;
+}
+
+int cimba_b200_summarize_weighted(const double *x, const double *w, uint64_t n,
+                                  uint64_t *out_row, void *stream)
+{
+    if (x == nullptr || w == nullptr || out_row == nullptr || n == 0u)
+        return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_summarize_weighted");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    summarize_weighted_kernel<<<1, SUMMARY_BLOCK, 0, (cudaStream_t)stream>>>(x, w, n, out_row);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "summarize_weighted_kernel launch");
+}
+
+int cimba_b200_merge_weighted_rows(const uint64_t *rows, uint64_t n, uint64_t *out_row, void *stream)
+{
+    if (rows == nullptr || out_row == nullptr || n == 0u)
+        return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_merge_weighted_rows");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    merge_weighted_rows_kernel<<<1, SUMMARY_BLOCK, 0, (cudaStream_t)stream>>>(rows, n, out_row);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "merge_weighted_rows_kernel launch");
+}
+
+// ------------------------------------------------- cmb_wtdsummary on the host
+namespace {
+WtdAcc wtd_from(const cimba_b200_wtdsummary *s)
+{
+    return WtdAcc{s->base.count, s->base.min, s->base.max, s->base.m1, s->base.m2, s->base.m3, s->base.m4, s->wsum};
+}
+void wtd_to(const WtdAcc &a, cimba_b200_wtdsummary *s)
+{
+    cimba_b200_datasummary_initialize(&s->base);
+    s->base.count = a.count;
+    s->base.min = a.min;
+    s->base.max = a.max;
+    s->base.m1 = a.m1;
+    s->base.m2 = a.m2;
+    s->base.m3 = a.m3;
+    s->base.m4 = a.m4;
+    s->wsum = a.wsum;
+}
+}  // namespace
+
+void cimba_b200_wtdsummary_initialize(cimba_b200_wtdsummary *s)
+{   // src/cmb_wtdsummary.c:40-46
+    cimba_b200_datasummary_initialize(&s->base);
+    s->wsum = 0.0;
+}
+
+uint64_t cimba_b200_wtdsummary_add(cimba_b200_wtdsummary *s, double x, double w)
+{
+    WtdAcc a = wtd_from(s);
+    wtd_add(a, x, w);
+    wtd_to(a, s);
+    return s->base.count;
+}
+
+uint64_t cimba_b200_wtdsummary_merge(cimba_b200_wtdsummary *tgt, const cimba_b200_wtdsummary *p,
+                                     const cimba_b200_wtdsummary *q)
+{
+    const WtdAcc c = wtd_merge(wtd_from(p), wtd_from(q));
+    wtd_to(c, tgt);
+    return tgt->base.count;
+}
+
+double cimba_b200_wtdsummary_mean(const cimba_b200_wtdsummary *s) { return s->base.m1; }
+
+double cimba_b200_wtdsummary_variance(const cimba_b200_wtdsummary *s)
+{   // include/cmb_wtdsummary.h:192-197 delegates to cmb_datasummary_variance on the base part
+    return cimba_b200_datasummary_variance(&s->base);
 }
 
 // ------------------------------------------------- cmb_datasummary on the host

@@ -20,6 +20,7 @@
 
 #include "engine.cuh"
 #include "rng.cuh"
+#include "summary.cuh"
 
 namespace cimba_b200 {
 
@@ -34,6 +35,7 @@ struct QueueArgs {
     uint64_t *events, *objects;
     double   *t_end, *sum_wait;
     uint32_t *status, *max_queue;
+    uint64_t *counters;                // [num_trials][8]: RECORD kernels write the queue-length cmb_wtdsummary here
     double   *spill;                   // [num_trials][spill_cap]
     uint32_t  spill_cap;               // power of two, or 0
     uint64_t  trace_cap;
@@ -43,7 +45,11 @@ struct QueueArgs {
 
 enum { PROC_ARRIVAL = 0, PROC_SERVICE = 1 };
 
-template <int MODEL, bool TRACE>
+// RECORD = the queue's history is on (cmb_objectqueue_recording_start, src/cmb_objectqueue.c:161-177,
+// as tutorial/tut_1_*.c and test/test_cimba.c run it): every put and get is a (length, time)
+// sample of a cmb_timeseries, folded on the fly into the time-weighted cmb_wtdsummary that
+// cmb_timeseries_summarize (src/cmb_timeseries.c:167-188) would compute from the stored history.
+template <int MODEL, bool TRACE, bool RECORD = false>
 __global__ void __launch_bounds__(QUEUE_BLOCK)
 queue_kernel(const QueueArgs a)
 {
@@ -77,6 +83,12 @@ queue_kernel(const QueueArgs a)
     uint32_t produced = 0u, served = 0u, status = TRIAL_OK, longest = 0u;
     bool server_waiting = false;       // the front guard's only possible waiter
     const uint32_t quota = (uint32_t)a.num_objects;
+
+    TimeWeighted hist;
+    hist.start();
+    if (RECORD) {
+        hist.sample(0.0, 0.0);         // recording_start: the empty queue at t = 0
+    }
 
     fel.clear();
     q.init(&ring_smem[threadIdx.x], QUEUE_BLOCK,
@@ -115,6 +127,10 @@ queue_kernel(const QueueArgs a)
                 if (a.sum_wait)  a.sum_wait[trial] = sum_wait;
                 if (a.status)    a.status[trial] = status;
                 if (a.max_queue) a.max_queue[trial] = longest;
+                if (RECORD) {
+                    hist.sample((double)q.len, now);            // recording_stop closes the last interval
+                    if (a.counters) wtd_store_row(hist.acc, a.counters + trial * 8u);
+                }
             }
             else {
                 now = when;            // src/cmb_event.c:239-241
@@ -133,6 +149,9 @@ queue_kernel(const QueueArgs a)
                             status |= TRIAL_ERR_QUEUE_OVERFLOW;
                         }
                         longest = max(longest, q.len);
+                        if (RECORD) {
+                            hist.sample((double)q.len, now);    // record_sample in put, src/cmb_objectqueue.c:289
+                        }
                         produced++;
                         // cmb_objectqueue_put -> cmb_resourceguard_signal(front_guard):
                         // wake the head waiter if has_content holds (src/cmb_objectqueue.c:286-287,
@@ -157,6 +176,9 @@ queue_kernel(const QueueArgs a)
                     // wake-up the loop re-tests (:213)
                     if (q.len > 0u) {
                         stamp = q.take();
+                        if (RECORD) {
+                            hist.sample((double)q.len, now);    // ... and in get, :226-229
+                        }
                         draw = true;
                     }
                     else {

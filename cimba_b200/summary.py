@@ -15,7 +15,7 @@ from typing import Iterable, List, Optional
 
 import torch
 
-from ._lib import DataSummaryStruct, lib, check
+from ._lib import DataSummaryStruct, WtdSummaryStruct, lib, check
 
 
 class DataSummary:
@@ -82,6 +82,104 @@ class DataSummary:
     def __repr__(self) -> str:
         return (f"DataSummary(n={self.count()}, mean={self.mean():.9g}, "
                 f"sd={self.stddev():.6g}, min={self.min():.6g}, max={self.max():.6g})")
+
+
+class WtdSummary:
+    """Same fields and semantics as the reference's ``struct cmb_wtdsummary``
+    (include/cmb_wtdsummary.h:41-44; add src/cmb_wtdsummary.c:82-137, merge :152-194)."""
+
+    def __init__(self) -> None:
+        self._s = WtdSummaryStruct()
+        lib.cimba_b200_wtdsummary_initialize(C.byref(self._s))
+
+    def add(self, x: float, w: float) -> int:
+        return int(lib.cimba_b200_wtdsummary_add(C.byref(self._s), float(x), float(w)))
+
+    @staticmethod
+    def merge(a: "WtdSummary", b: "WtdSummary") -> "WtdSummary":
+        out = WtdSummary()
+        lib.cimba_b200_wtdsummary_merge(C.byref(out._s), C.byref(a._s), C.byref(b._s))
+        return out
+
+    def count(self) -> int:
+        return int(self._s.base.count)
+
+    def wsum(self) -> float:
+        return self._s.wsum
+
+    def mean(self) -> float:
+        return lib.cimba_b200_wtdsummary_mean(C.byref(self._s))
+
+    def variance(self) -> float:
+        return lib.cimba_b200_wtdsummary_variance(C.byref(self._s))
+
+    # --- the 8-word row {count (u64), min, max, m1..m4, wsum (f64 bits)} the engine writes ---
+    def to_row(self) -> List[int]:
+        import struct
+        b = self._s.base
+        return [int(b.count)] + [struct.unpack("<Q", struct.pack("<d", v))[0]
+                                 for v in (b.min, b.max, b.m1, b.m2, b.m3, b.m4, self._s.wsum)]
+
+    @staticmethod
+    def from_row(row: Iterable[int]) -> "WtdSummary":
+        import struct
+        row = [int(v) & 0xFFFFFFFFFFFFFFFF for v in row]
+        f = [struct.unpack("<d", struct.pack("<Q", v))[0] for v in row[1:8]]
+        out = WtdSummary()
+        b = out._s.base
+        b.count = row[0]
+        b.min, b.max, b.m1, b.m2, b.m3, b.m4 = f[:6]
+        out._s.wsum = f[6]
+        return out
+
+    def fields(self) -> List[float]:
+        b = self._s.base
+        return [float(b.count), b.min, b.max, b.m1, b.m2, b.m3, b.m4, self._s.wsum]
+
+    def __repr__(self) -> str:
+        return f"WtdSummary(n={self.count()}, mean={self.mean():.9g}, wsum={self.wsum():.9g})"
+
+
+def summarize_weighted_on_device(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """cmb_wtdsummary_add over device-resident (x, w) -> one 8-word row (int64 tensor)."""
+    if not x.is_cuda:
+        raise ValueError("summarize_weighted_on_device needs CUDA tensors (no CPU path)")
+    out = torch.empty(8, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.cimba_b200_summarize_weighted(x.data_ptr(), w.data_ptr(), x.numel(),
+                                                out.data_ptr(), C.c_void_p(stream)))
+    return out
+
+
+def merge_weighted_rows_on_device(rows: torch.Tensor) -> torch.Tensor:
+    """cmb_wtdsummary_merge over per-trial rows [n, 8] on the device -> one row."""
+    if not rows.is_cuda:
+        raise ValueError("merge_weighted_rows_on_device needs a CUDA tensor (no CPU path)")
+    rows = rows.contiguous()
+    out = torch.empty(8, dtype=torch.int64, device=rows.device)
+    with torch.cuda.device(rows.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.cimba_b200_merge_weighted_rows(rows.data_ptr(), rows.shape[0], out.data_ptr(),
+                                                 C.c_void_p(stream)))
+    return out
+
+
+def merge_weighted_across_ranks(local_row: torch.Tensor, group=None) -> WtdSummary:
+    """All-gather the per-rank rows and fold them in rank order with cmb_wtdsummary_merge
+    (the weighted half of SURVEY.md section 8e's one exchange step)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        parts = [torch.empty_like(local_row) for _ in range(world)]
+        dist.all_gather(parts, local_row.contiguous(), group=group)
+    else:
+        parts = [local_row]
+    acc: Optional[WtdSummary] = None
+    for p in parts:
+        s = WtdSummary.from_row(p.detach().cpu().tolist())
+        acc = s if acc is None else WtdSummary.merge(acc, s)
+    return acc
 
 
 def summarize_on_device(sum_wait: torch.Tensor, objects: torch.Tensor) -> torch.Tensor:

@@ -61,6 +61,11 @@ extern "C" {
                                     * a clerk (cmb_process_resume, cmb_process_exit), a supervisor (cmb_process_wait_process, restart),
                                     * a ringer (cmb_event_reschedule / reprioritize / cancel, cmb_process_wait_event), a listener,
                                     * a watcher on a condition OBSERVING the desk's guard, a nuisance; end at t = num_objects */
+#define CIMBA_B200_MODEL_MM1_RECORDED 9 /* MODEL_MM1 with the queue's history on (cmb_objectqueue_recording_start, as
+                                    * tutorial/tut_1_*.c and test/test_cimba.c run it): counters[trial][0..7] receive the
+                                    * time-weighted queue-length cmb_wtdsummary {count, min, max, m1, m2, m3, m4, wsum}
+                                    * (count as u64, the rest as IEEE-754 bit patterns) that cmb_timeseries_summarize
+                                    * (src/cmb_timeseries.c:167-188) computes from the stored history - folded on the fly */
 
 /* Error codes */
 #define CIMBA_B200_OK         0
@@ -138,6 +143,16 @@ uint64_t cimba_b200_launch_count(void);
 int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
                          uint64_t num_trials, double *out_summary, void *stream);
 
+/* cmb_wtdsummary_add (src/cmb_wtdsummary.c:82-137) over n device-resident (x, w) pairs.
+ * out_row: DEVICE pointer to 8 words {count (u64), min, max, m1, m2, m3, m4, wsum (f64 bit
+ * patterns)} - the row format MODEL_MM1_RECORDED writes per trial. */
+int cimba_b200_summarize_weighted(const double *x, const double *w, uint64_t n,
+                                  uint64_t *out_row, void *stream);
+
+/* cmb_wtdsummary_merge (src/cmb_wtdsummary.c:152-194) over n device-resident rows of that
+ * format (one per trial) into one row: the per-GPU step before the NCCL all-gather. */
+int cimba_b200_merge_weighted_rows(const uint64_t *rows, uint64_t n, uint64_t *out_row, void *stream);
+
 /* ------------------------------------------------------------------------
  * Host-buffer interface = the cimba_run_experiment() replacement.
  * ---------------------------------------------------------------------- */
@@ -200,6 +215,21 @@ uint64_t cimba_b200_datasummary_merge(cimba_b200_datasummary *tgt,
 double   cimba_b200_datasummary_mean(const cimba_b200_datasummary *dsp);
 double   cimba_b200_datasummary_variance(const cimba_b200_datasummary *dsp);
 double   cimba_b200_datasummary_stddev(const cimba_b200_datasummary *dsp);
+
+/* cmb_wtdsummary (include/cmb_wtdsummary.h:41-44: the data summary plus the sum of weights;
+ * src/cmb_wtdsummary.c:82-137 add, :152-194 merge).  Same arithmetic as the device kernels. */
+typedef struct cimba_b200_wtdsummary {
+    cimba_b200_datasummary base;
+    double   wsum;
+} cimba_b200_wtdsummary;
+
+void     cimba_b200_wtdsummary_initialize(cimba_b200_wtdsummary *wsp);
+uint64_t cimba_b200_wtdsummary_add(cimba_b200_wtdsummary *wsp, double x, double w);
+uint64_t cimba_b200_wtdsummary_merge(cimba_b200_wtdsummary *tgt,
+                                     const cimba_b200_wtdsummary *ws1,
+                                     const cimba_b200_wtdsummary *ws2);
+double   cimba_b200_wtdsummary_mean(const cimba_b200_wtdsummary *wsp);
+double   cimba_b200_wtdsummary_variance(const cimba_b200_wtdsummary *wsp);
 
 /* cmb_random_fmix64 (src/cmb_random.c:70-80): per-trial seed derivation. */
 uint64_t cimba_b200_fmix64(uint64_t seed, uint64_t nonce);

@@ -727,6 +727,11 @@ typedef struct sim {
     double  *ring;
     uint64_t ring_cap, ring_head, ring_len;
     guard    q_front;
+    /* the queue's history (model 9): cmb_timeseries_add fused with cmb_timeseries_summarize */
+    bool     recording;
+    uint64_t rec_n;
+    double   rec_x, rec_t;
+    port_wsummary hist;
     /* resourcepool (src/cmb_resourcepool.c) */
     uint64_t pool_cap, pool_in_use;
     guard    pool_guard;
@@ -812,10 +817,27 @@ static void ring_push(sim *s, double v)
     s->ring_len++;
 }
 
+/* record_sample (src/cmb_objectqueue.c:151-159) -> cmb_timeseries_add (src/cmb_timeseries.c:106-141):
+ * a new sample fixes the duration of the previous one, which is all cmb_timeseries_summarize
+ * (:167-188) ever feeds to cmb_wtdsummary_add - so the history need not be stored */
+static void record_sample(sim *s)
+{
+    if (!s->recording) {
+        return;
+    }
+    if (s->rec_n > 0u) {
+        (void)port_wsummary_add(&s->hist, s->rec_x, s->now - s->rec_t);
+    }
+    s->rec_x = (double)s->ring_len;
+    s->rec_t = s->now;
+    s->rec_n++;
+}
+
 /* src/cmb_objectqueue.c:262-314, unlimited capacity: append, signal the front guard */
 static void objectqueue_put(sim *s, double stamp)
 {
     ring_push(s, stamp);
+    record_sample(s);
     if (s->ring_len > s->res->max_queue) {
         s->res->max_queue = s->ring_len;
     }
@@ -831,6 +853,7 @@ static bool objectqueue_try_get(sim *s, double *stamp)
     *stamp = s->ring[s->ring_head];
     s->ring_head = (s->ring_head + 1u) % s->ring_cap;
     s->ring_len--;
+    record_sample(s);
     return true;
 }
 
@@ -1051,6 +1074,11 @@ static void run_one(int model, int servers, uint64_t seed, uint64_t num_objects,
         s.ring_cap = 64u;
         s.ring = malloc(s.ring_cap * sizeof(double));
         heap_init(&s.q_front.waiting, 3u, guard_before);
+        if (model == 9) {                               /* cmb_objectqueue_recording_start */
+            s.recording = true;
+            port_wsummary_init(&s.hist);
+            record_sample(&s);
+        }
         source.body = source_body;
         server.body = server_body;
         server.id = 1;
@@ -1069,6 +1097,13 @@ static void run_one(int model, int servers, uint64_t seed, uint64_t num_objects,
         heap_free(&s.pool_guard.waiting);
     }
     else {
+        if (model == 9) {                               /* cmb_objectqueue_recording_stop + summarize */
+            record_sample(&s);
+            const double v[7] = { s.hist.ds.min, s.hist.ds.max, s.hist.ds.m1, s.hist.ds.m2,
+                                  s.hist.ds.m3, s.hist.ds.m4, s.hist.wsum };
+            out->counter[0] = s.hist.ds.count;
+            memcpy(&out->counter[1], v, sizeof(v));
+        }
         free(s.ring);
         heap_free(&s.q_front.waiting);
     }

@@ -1161,6 +1161,11 @@ static void run_queue_trial(struct ref_trial *t)
     struct q_world w = { .trl = t };
     w.queue = cmb_objectqueue_create();
     cmb_objectqueue_initialize(w.queue, "Queue", CMB_UNLIMITED);
+    if (t->model == 9) {
+        /* model 9 = model 0 with the queue's history switched on, as tutorial/tut_1_*.c and
+         * test/test_cimba.c do: every put/get appends (length, cmb_time()) to a cmb_timeseries */
+        cmb_objectqueue_recording_start(w.queue);
+    }
     w.source = cmb_process_create();
     cmb_process_initialize(w.source, "Arrival", q_source_body, &w, 0);
     cmb_process_start(w.source);
@@ -1170,6 +1175,18 @@ static void run_queue_trial(struct ref_trial *t)
 
     pump_events(t);
 
+    if (t->model == 9) {
+        /* time-weighted queue length: cmb_timeseries_summarize -> cmb_wtdsummary_add per sample
+         * (src/cmb_timeseries.c:167-188); exported as bit patterns in counter[0..7] */
+        cmb_objectqueue_recording_stop(w.queue);
+        struct cmb_wtdsummary ws;
+        cmb_wtdsummary_initialize(&ws);
+        (void)cmb_timeseries_summarize(cmb_objectqueue_history(w.queue), &ws);
+        const struct cmb_datasummary *ds = (const struct cmb_datasummary *)&ws;
+        const double v[7] = { ds->min, ds->max, ds->m1, ds->m2, ds->m3, ds->m4, ws.wsum };
+        t->counter[0] = ds->count;
+        memcpy(&t->counter[1], v, sizeof(v));
+    }
     cmb_process_stop(w.server, NULL);
     cmb_process_terminate(w.source);
     cmb_process_terminate(w.server);

@@ -34,7 +34,8 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           5: dict(arr=1.0, srv=1.0, servers=10),     # model 5: num_objects = duration, servers = buffer capacity
           6: dict(arr=1.0, srv=1.0, servers=8),      # model 6: num_objects = duration, servers = queue capacity
           7: dict(arr=1.0, srv=1.0, servers=200),    # model 7: num_objects = duration, servers = worker processes
-          8: dict(arr=1.0, srv=0.6, servers=1)}      # model 8: num_objects = duration
+          8: dict(arr=1.0, srv=0.6, servers=1),      # model 8: num_objects = duration
+          9: dict(arr=1 / 0.9, srv=1.0, servers=1)}  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
 
 
 def hexes(a):
@@ -73,7 +74,7 @@ def main():
             # model 3: the size is a duration; 0 would stop workers before they start (they then
             # run forever in the reference), so it starts at 1
             traced = 10 if model == 7 else 1000
-            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model < 3 else ((1, 2, 3, 10, 50) if model == 7 else (1, 2, 3, 10, 100, 1000))):
+            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model in (0, 1, 2, 9) else ((1, 2, 3, 10, 50) if model == 7 else (1, 2, 3, 10, 100, 1000))):
                 r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
                                              par["arr"], par["srv"], 512 if nobj == traced else 0)
                 rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
@@ -85,14 +86,15 @@ def main():
                     rec["trace_key"] = [int(k) for k in keys]
                     rec["trace_time"] = hexes(times)
                 trials.append(rec)
-        if model >= 3:
+        if model not in (0, 1, 2, 9):
             continue
         # the full-size known answer
         r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
         trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
                        "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                        "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
-                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue})
+                       "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
+                       "counters": r.counters()})
     out["trials"] = trials
 
     # experiment-level: first 64 trials of the fmix64-seeded M/M/1 experiment, 10 000 objects

@@ -387,6 +387,58 @@ def test_priorityqueue_and_condition_pop_order_bit_exact(cb, port):
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
 
 
+# ------------------------------------------------------------------ time-weighted statistics (model 9, cmb_wtdsummary)
+
+@pytest.mark.parametrize("nobj,rho", [(2000, 0.9), (500, 0.5), (0, 0.9), (1, 0.9), (3, 0.9), (20000, 0.95)])
+def test_recorded_queue_length_wtdsummary_bit_exact(cb, port, nobj, rho):
+    """M/M/1 with the queue's history on: the time-weighted queue-length cmb_wtdsummary the reference
+    computes from its stored cmb_timeseries, folded on the fly on the device - every field bit-exact."""
+    n = 128
+    res = cb.run_trials(n, arr_mean=1 / rho, srv_mean=1.0, num_objects=nobj, master_seed=KAT_SEED,
+                        model=cb.MODEL_MM1_RECORDED)
+    want = run_trials(port, "port", 9, 1, KAT_SEED, 0, n, nobj, 1 / rho, 1.0)
+    _compare(res, want, ("recorded", nobj))
+    assert _counts(res.counters) == [w.counters() for w in want]
+    plain = cb.run_trials(n, arr_mean=1 / rho, srv_mean=1.0, num_objects=nobj, master_seed=KAT_SEED, model=cb.MODEL_MM1)
+    assert torch.equal(plain.events, res.events) and torch.equal(plain.sum_wait, res.sum_wait)   # recording changes nothing else
+    if nobj >= 2000:
+        s = cb.WtdSummary.from_row(_counts(res.counters)[0])
+        assert abs(s.wsum() - float(res.t_end[0])) <= 1e-9 * s.wsum()      # the weights are the whole run's durations
+
+
+def test_device_weighted_reductions(cb, golden):
+    """cmb_wtdsummary_add over device arrays, and cmb_wtdsummary_merge over per-trial rows."""
+    s = golden["summary"]
+    x = np.array([float.fromhex(v) for v in s["x"]])
+    w = np.array([float.fromhex(v) for v in s["w"]])
+    row = cb.summarize_weighted_on_device(torch.tensor(x, device="cuda"), torch.tensor(w, device="cuda"))
+    got = cb.WtdSummary.from_row(row.cpu().tolist()).fields()
+    ref_all = [float.fromhex(v) for v in s["wtd_all"]]
+    assert got[0] == ref_all[0] and got[1:3] == ref_all[1:3]
+    for g, r in zip(got[3:], ref_all[3:]):
+        assert abs(g - r) <= 1e-11 * abs(r)           # a 256-way merge tree vs the reference's serial adds
+    # per-trial rows merged on the device == the same rows merged on the host in the same tree order, bit for bit
+    res = cb.run_trials(700, arr_mean=1 / 0.9, srv_mean=1.0, num_objects=400, master_seed=5, model=cb.MODEL_MM1_RECORDED)
+    dev = cb.WtdSummary.from_row(cb.merge_weighted_rows_on_device(res.counters).cpu().tolist())
+    rows = [cb.WtdSummary.from_row(r) for r in _counts(res.counters)]
+    part = []
+    for t0 in range(256):
+        acc = cb.WtdSummary()
+        for i in range(t0, 700, 256):
+            acc = cb.WtdSummary.merge(acc, rows[i])
+        part.append(acc)
+    k = 128
+    while k > 0:
+        for i in range(k):
+            part[i] = cb.WtdSummary.merge(part[i], part[i + k])
+        k //= 2
+    assert dev.fields() == part[0].fields()
+    serial = cb.WtdSummary()
+    for r in rows:
+        serial = cb.WtdSummary.merge(serial, r)
+    assert dev.count() == serial.count() and abs(dev.mean() - serial.mean()) <= 1e-12 * serial.mean()
+
+
 # ------------------------------------------------------------------ timers, waits, observers (model 8)
 
 @pytest.mark.parametrize("dur,am,sm", [(500, 1.0, 0.6), (300, 0.4, 1.2), (200, 2.0, 0.3), (1, 1.0, 1.0), (3, 1.0, 1.0)])

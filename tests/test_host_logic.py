@@ -63,6 +63,31 @@ def test_merge_across_ranks_without_process_group(cb):
     assert out.to_list() == ds.to_list()
 
 
+def _wtd_of(cb, x, w):
+    out = cb.WtdSummary()
+    for xi, wi in zip(x, w):
+        out.add(xi, wi)
+    return out
+
+
+def test_wtdsummary_add_and_merge_match_reference_golden(cb, golden):
+    """cmb_wtdsummary_add / _merge of the C-ABI library vs numbers produced by the reference itself."""
+    s = golden["summary"]
+    x = [float.fromhex(v) for v in s["x"]]
+    w = [float.fromhex(v) for v in s["w"]]
+    assert [float.hex(v) for v in _wtd_of(cb, x, w).fields()] == s["wtd_all"]
+    for na in (1, 333, 500, 999):
+        m = cb.WtdSummary.merge(_wtd_of(cb, x[:na], w[:na]), _wtd_of(cb, x[na:], w[na:]))
+        assert [float.hex(v) for v in m.fields()] == s[f"wtd_merge_{na}"]
+    a = _wtd_of(cb, x[:10], w[:10])
+    assert cb.WtdSummary.from_row(a.to_row()).fields() == a.fields()
+    assert a.variance() == a.fields()[4] / 9.0        # include/cmb_wtdsummary.h:192-197: the base-class variance
+    e = cb.WtdSummary()
+    assert cb.WtdSummary.merge(a, e).fields() == a.fields() == cb.WtdSummary.merge(e, a).fields()
+    z = cb.WtdSummary()
+    assert z.add(3.0, 0.0) == 0 and z.count() == 0    # zero weight: ignored (src/cmb_wtdsummary.c:92-94)
+
+
 WORKER = textwrap.dedent("""
     import os, sys, json
     sys.path.insert(0, {root!r})
@@ -74,7 +99,14 @@ WORKER = textwrap.dedent("""
     shard = x[rank * 1000:(rank + 1) * 1000]          # contiguous blocks of the trial array, section 8e
     local = torch.tensor(cb.DataSummary.of(shard).to_list(), dtype=torch.float64)
     merged = cb.merge_across_ranks(local)
-    print(json.dumps({{"rank": rank, "summary": [float.hex(v) for v in merged.to_list()]}}), flush=True)
+    w = np.random.default_rng(12).uniform(0.1, 2.0, size=2000)[rank * 1000:(rank + 1) * 1000]
+    mine = cb.WtdSummary()
+    for xi, wi in zip(shard, w):
+        mine.add(xi, wi)
+    wmerged = cb.merge_weighted_across_ranks(torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in mine.to_row()],
+                                                          dtype=torch.int64))
+    print(json.dumps({{"rank": rank, "summary": [float.hex(v) for v in merged.to_list()],
+                      "wsummary": [float.hex(v) for v in wmerged.fields()]}}), flush=True)
     dist.destroy_process_group()
 """)
 
@@ -101,3 +133,9 @@ def test_two_rank_gloo_merge_equals_single_process_merge(cb, tmp_path):
     assert got[0] == [float.hex(v) for v in want.to_list()]
     serial = cb.DataSummary.of(x)
     assert abs(want.mean() - serial.mean()) <= 1e-12 * abs(serial.mean())
+    # the weighted half of the same exchange: cmb_wtdsummary rows all-gathered and merged in rank order
+    wgot = [json.loads(o)["wsummary"] for o in outs]
+    assert wgot[0] == wgot[1]
+    w = np.random.default_rng(12).uniform(0.1, 2.0, size=2000)
+    wwant = cb.WtdSummary.merge(_wtd_of(cb, x[:1000], w[:1000]), _wtd_of(cb, x[1000:], w[1000:]))
+    assert wgot[0] == [float.hex(v) for v in wwant.fields()]

@@ -75,7 +75,7 @@ def test_trials_match_golden(port, golden):
             assert [float.hex(x) for x in times] == t["trace_time"], tag
 
 
-@pytest.mark.parametrize("model", [0, 1, 2])
+@pytest.mark.parametrize("model", [0, 1, 2, 9])
 def test_full_size_known_answer(port, golden, model):
     """The 10^6-object known answers (M/M/1 2 099 622 events, ...)."""
     t = [x for x in golden["trials"] if x["num_objects"] == 1_000_000 and x["model"] == model][0]
@@ -83,6 +83,7 @@ def test_full_size_known_answer(port, golden, model):
                           float.fromhex(t["arr_mean"]), float.fromhex(t["srv_mean"]), 0)
     assert (r.events, r.objects) == (t["events"], t["objects"])
     assert float.hex(r.t_end) == t["t_end"] and float.hex(r.sum_wait) == t["sum_wait"]
+    assert r.counters() == t["counters"]            # model 9: the time-weighted queue-length cmb_wtdsummary
     if model == 0:
         assert r.events == 2_099_622 and r.t_end == 1109668.9795469602 and r.sum_wait == 9895522.5628889836
 
@@ -165,19 +166,20 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (5, 1.0, 1.0, 10), (5, 0.5, 1.0, 2),
                                                    (6, 1.0, 1.0, 8), (6, 0.5, 1.0, 2),
                                                    (7, 1.0, 1.0, 500), (7, 0.5, 1.0, 5),
-                                                   (8, 1.0, 0.6, 1), (8, 0.4, 1.2, 1)])
+                                                   (8, 1.0, 0.6, 1), (8, 0.4, 1.2, 1),
+                                                   (9, 1 / 0.9, 1.0, 1), (9, 2.0, 1.0, 1)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
     n = 48
-    size = 20_000 if model < 3 else (30 if model == 7 else 1500)    # models 3..8: duration in time units
+    size = 20_000 if model in (0, 1, 2, 9) else (30 if model == 7 else 1500)    # models 3..8: duration in time units
     a = run_trials(ref, "ref", model, servers, 0xC0FFEE, 100, n, size, arr, srv, par=0)
     b = run_trials(port, "port", model, servers, 0xC0FFEE, 100, n, size, arr, srv)
     assert [x.key() for x in a] == [x.key() for x in b]
     assert [(x.max_fel, x.max_queue) for x in a] == [(x.max_fel, x.max_queue) for x in b]
     assert [x.counters() for x in a] == [x.counters() for x in b]
-    ra, ka, ta = trace_trial(ref, "ref", model, servers, 99, 3000 if model < 3 else (15 if model == 7 else 800), arr, srv, 9000)
-    rb, kb, tb = trace_trial(port, "port", model, servers, 99, 3000 if model < 3 else (15 if model == 7 else 800), arr, srv, 9000)
+    ra, ka, ta = trace_trial(ref, "ref", model, servers, 99, 3000 if model in (0, 1, 2, 9) else (15 if model == 7 else 800), arr, srv, 9000)
+    rb, kb, tb = trace_trial(port, "port", model, servers, 99, 3000 if model in (0, 1, 2, 9) else (15 if model == 7 else 800), arr, srv, 9000)
     assert ka == kb and ta == tb and ra.key() == rb.key()
 
 
