@@ -88,6 +88,10 @@ SYMBOLS = {
     "cimba_b200_fmix64": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "cimba_b200_rng_draws": (C.c_int, [C.c_uint64, C.c_int, C.c_double, C.c_double,
                                        C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cimba_b200_rng_draws_ex": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_double), C.c_uint32,
+                                          C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cimba_b200_alias_create": (C.c_int, [C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint32)]),
     "cimba_b200_version": (C.c_char_p, []),
     "cimba_b200_last_error": (C.c_char_p, []),
     "cimba_b200_device_count": (C.c_int, []),

@@ -27,6 +27,7 @@
 #include "timers_model.cuh"
 #include "hold_model.cuh"
 #include "rng.cuh"
+#include "distributions.cuh"
 #include "summary.cuh"
 
 using namespace cimba_b200;
@@ -92,6 +93,65 @@ __global__ void rng_draws_kernel(uint64_t seed, int kind, double p0, double p1, 
         }
         out[i] = v;
     }
+}
+
+struct DrawParams {
+    double   v[CIMBA_B200_RNG_MAX_PARAMS];
+    uint64_t uprob[CIMBA_B200_RNG_MAX_PARAMS];
+    uint32_t alias[CIMBA_B200_RNG_MAX_PARAMS];
+};
+
+__global__ void rng_draws_ex_kernel(uint64_t seed, int kind, const DrawParams par, uint64_t n, double *out)
+{
+    __shared__ ZigHot hot;
+    stage_zig_hot(hot, true);
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    Sfc64 r;
+    r.seed(seed);
+    FlipCache flips{0u, 0u};
+    const double *p = par.v;
+    const unsigned cnt = (unsigned)p[0];
+    for (uint64_t i = 0; i < n; i++) {
+        double v = 0.0;
+        switch (kind) {
+        case 9:  v = rnd_triangular(r, p[0], p[1], p[2]); break;
+        case 10: v = rnd_lognormal(r, hot, p[0], p[1]); break;
+        case 11: v = rnd_logistic(r, p[0], p[1]); break;
+        case 12: v = rnd_cauchy(r, hot, p[0], p[1]); break;
+        case 13: v = rnd_hypoexponential(r, hot, cnt, p + 1); break;
+        case 14: v = rnd_hyperexponential(r, hot, cnt, p + 1, p + 1 + cnt); break;
+        case 15: v = rnd_gamma(r, hot, p[0], p[1]); break;
+        case 16: v = rnd_beta(r, hot, p[0], p[1], p[2], p[3]); break;
+        case 17: v = rnd_PERT_mod(r, hot, p[0], p[1], p[2], 4.0); break;
+        case 18: v = rnd_weibull(r, hot, p[0], p[1]); break;
+        case 19: v = rnd_pareto(r, p[0], p[1]); break;
+        case 20: v = rnd_chisquared(r, hot, p[0]); break;
+        case 21: v = rnd_F_dist(r, hot, p[0], p[1]); break;
+        case 22: v = rnd_t_dist(r, hot, p[0], p[1], p[2]); break;
+        case 23: v = rnd_rayleigh(r, hot, p[0]); break;
+        case 24: v = (double)rnd_flip(r, flips); break;
+        case 25: v = (double)rnd_geometric(r, hot, p[0]); break;
+        case 26: v = (double)rnd_binomial(r, cnt, p[1]); break;
+        case 27: v = (double)rnd_negative_binomial(r, hot, cnt, p[1]); break;
+        case 28: v = (double)rnd_poisson(r, hot, p[0]); break;
+        case 29: v = (double)rnd_loaded_dice(r, cnt, p + 1); break;
+        case 30: v = (double)rnd_alias_sample(r, cnt, par.uprob, par.alias); break;
+        case 31: v = rnd_std_gamma(r, hot, p[0]); break;
+        case 32: v = rnd_PERT_mod(r, hot, p[0], p[1], p[2], p[3]); break;
+        case 33: v = (double)rnd_negative_binomial(r, hot, cnt, p[1]); break;
+        }
+        out[i] = v;
+    }
+}
+
+uint64_t alias_secure(double p)        // src/cmb_random.c:672-686
+{
+    if (p <= 0.0) return 0u;
+    if (p >= 1.0) return UINT64_MAX;
+    return (uint64_t)(p * (double)UINT64_MAX);
 }
 
 template <int MODEL>
@@ -363,6 +423,62 @@ int cimba_b200_rng_draws(uint64_t seed, int kind, double p0, double p1,
     g_launches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "rng_draws_kernel launch");
+}
+
+// cmb_random_alias_create, src/cmb_random.c:688-752 (Vose): host-side table construction;
+// the tables are what rnd_alias_sample (csrc/distributions.cuh) reads on the device.
+int cimba_b200_alias_create(uint32_t n, const double *pa, uint64_t *uprob, uint32_t *alias)
+{
+    if (n == 0u || pa == nullptr || uprob == nullptr || alias == nullptr)
+        return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_alias_create");
+    std::vector<double> work(n);
+    std::vector<uint32_t> small(n), large(n);
+    double psum = 0.0;
+    for (uint32_t i = 0; i < n; i++) {
+        psum += pa[i];
+        uprob[i] = 0u;
+        alias[i] = 0u;
+    }
+    if (fabs(psum - 1.0) > 1.0e-3) return fail(CIMBA_B200_EINVAL, "probabilities must sum to one (src/cmb_random.c:634-642)");
+    uint32_t ns = 0u, nl = 0u;
+    for (uint32_t i = 0; i < n; i++) {
+        work[i] = pa[i] * n / psum;
+        if (work[i] < 1.0) small[ns++] = i;
+        else large[nl++] = i;
+    }
+    while (ns > 0u && nl > 0u) {
+        const uint32_t l = small[--ns];
+        const uint32_t g = large[--nl];
+        uprob[l] = alias_secure(work[l]);
+        alias[l] = g;
+        work[g] = (work[g] + work[l]) - 1.0;
+        if (work[g] < 1.0) small[ns++] = g;
+        else large[nl++] = g;
+    }
+    while (nl > 0u) uprob[large[--nl]] = UINT64_MAX;
+    while (ns > 0u) uprob[small[--ns]] = UINT64_MAX;
+    return CIMBA_B200_OK;
+}
+
+int cimba_b200_rng_draws_ex(uint64_t seed, int kind, const double *params, uint32_t num_params,
+                            uint64_t n, double *out, void *stream)
+{
+    if (out == nullptr || kind < 9 || kind > 33 || num_params > CIMBA_B200_RNG_MAX_PARAMS ||
+        (num_params > 0u && params == nullptr))
+        return fail(CIMBA_B200_EINVAL, "bad argument to cimba_b200_rng_draws_ex");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    DrawParams par{};
+    for (uint32_t i = 0; i < num_params; i++) par.v[i] = params[i];
+    if (kind == 30) {
+        const uint32_t cnt = num_params > 0u ? (uint32_t)params[0] : 0u;
+        if (cnt == 0u || cnt + 1u > num_params) return fail(CIMBA_B200_EINVAL, "alias: params = {n, p[0..n-1]}");
+        const int rc = cimba_b200_alias_create(cnt, params + 1, par.uprob, par.alias);
+        if (rc != CIMBA_B200_OK) return rc;
+    }
+    rng_draws_ex_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(seed, kind, par, n, out);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "rng_draws_ex_kernel launch");
 }
 
 // ------------------------------------------------------------ host-buffer path

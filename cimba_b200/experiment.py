@@ -194,3 +194,27 @@ def rng_draws(seed: int, kind: int, n: int, p0: float = 0.0, p1: float = 0.0,
                                        out.data_ptr(), C.c_void_p(stream)))
     torch.cuda.synchronize(dev)
     return out
+
+
+def rng_draws_ex(seed: int, kind: int, n: int, params=(), device: Optional[torch.device] = None) -> torch.Tensor:
+    """n variates of one of the remaining cmb_random distributions (kinds 9..33, see
+    include/cimba_b200.h) from the device-side stream seeded with ``seed``."""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    par = (C.c_double * max(1, len(params)))(*[float(v) for v in params])
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib.cimba_b200_rng_draws_ex(seed & (2**64 - 1), kind, par, len(params), n,
+                                          out.data_ptr(), C.c_void_p(stream)))
+    torch.cuda.synchronize(dev)
+    return out
+
+
+def alias_create(probabilities):
+    """cmb_random_alias_create: (uprob, alias) Vose tables for the given probabilities."""
+    n = len(probabilities)
+    pa = (C.c_double * n)(*[float(v) for v in probabilities])
+    uprob = (C.c_uint64 * n)()
+    alias = (C.c_uint32 * n)()
+    check(lib.cimba_b200_alias_create(n, pa, uprob, alias))
+    return list(uprob), list(alias)

@@ -242,6 +242,24 @@ uint64_t cimba_b200_fmix64(uint64_t seed, uint64_t nonce);
 int cimba_b200_rng_draws(uint64_t seed, int kind, double p0, double p1,
                          uint64_t n, double *out, void *stream);
 
+/* The rest of cmb_random (include/cmb_random.h:189-940) on the device, same calling form:
+ * kind  9 triangular(min,mode,max)   10 lognormal(m,s)        11 logistic(m,s)     12 cauchy(mode,scale)
+ *      13 hypoexponential(n, m[n])   14 hyperexponential(n, m[n], p[n])            15 gamma(shape,scale)
+ *      16 beta(a,b,min,max)          17 PERT(min,mode,max)    18 weibull(shape,scale)  19 pareto(shape,mode)
+ *      20 chisquared(k)              21 F_dist(a,b)           22 t_dist(m,s,v)     23 rayleigh(s)
+ *      24 flip()                     25 geometric(p)          26 binomial(n,p)     27 negative_binomial(m,p)
+ *      28 poisson(r)                 29 loaded_dice(n, p[n])  30 alias_sample over alias_create(n, p[n])
+ *      31 std_gamma(shape)           32 PERT_mod(min,mode,max,lambda)              33 pascal(m,p)
+ * params: HOST array of num_params <= CIMBA_B200_RNG_MAX_PARAMS doubles; out: DEVICE buffer of n doubles. */
+#define CIMBA_B200_RNG_MAX_PARAMS 16
+int cimba_b200_rng_draws_ex(uint64_t seed, int kind, const double *params, uint32_t num_params,
+                            uint64_t n, double *out, void *stream);
+
+/* cmb_random_alias_create (src/cmb_random.c:688-752): Vose alias tables for n alternatives with
+ * probabilities pa[n], written to the caller's uprob[n] / alias[n] (host memory; upload them for
+ * device-side alias sampling). */
+int cimba_b200_alias_create(uint32_t n, const double *pa, uint64_t *uprob, uint32_t *alias);
+
 const char *cimba_b200_version(void);
 const char *cimba_b200_last_error(void);
 int         cimba_b200_device_count(void);

@@ -294,6 +294,329 @@ int port_rng_draws(uint64_t seed, int kind, double p0, double p1, uint64_t n, do
     return 0;
 }
 
+/* =================================================== the rest of cmb_random
+ *
+ * include/cmb_random.h:189-940 and src/cmb_random.c:299-313, 465-766, restated.  Kind
+ * numbers as in ref_rng_draws_ex (oracle/ref_build/ref_driver.c).  Everything here is a
+ * thin layer over sfc64 / the two ziggurats plus sqrt (IEEE exact) and, for some, libm's
+ * log / exp / pow - on the CPU that is the same glibc the reference links, so this
+ * restatement is bit-identical to it; the CUDA side documents which kinds can differ in
+ * the last place because of that.
+ */
+
+/* src/cmb_random.c:500-520 */
+double port_triangular(port_rng *r, double min, double mode, double max)
+{
+    const double u = port_random(r);
+    if (u < (mode - min) / (max - min)) {
+        return min + sqrt(u * (max - min) * (mode - min));
+    }
+    return max - sqrt((1.0 - u) * (max - min) * (max - mode));
+}
+
+double port_lognormal(port_rng *r, double m, double s)         /* include/cmb_random.h:249-257 */
+{
+    return exp(port_normal(r, m, s));
+}
+
+double port_logistic(port_rng *r, double m, double s)          /* :267-273 */
+{
+    const double x = port_random(r);
+    return m + s * log(x / (1.0 - x));
+}
+
+double port_cauchy(port_rng *r, double mode, double scale)     /* :290-299 */
+{
+    const double x = port_std_normal(r);
+    double y;
+    while ((y = port_std_normal(r)) == 0.0) {}
+    return mode + scale * x / y;
+}
+
+double port_hypoexponential(port_rng *r, unsigned n, const double *ma)     /* :394-408 */
+{
+    double x = 0.0;
+    for (unsigned i = 0u; i < n; i++) {
+        x += port_exponential(r, ma[i]);
+    }
+    return x;
+}
+
+unsigned port_loaded_dice(port_rng *r, unsigned n, const double *pa)       /* src/cmb_random.c:644-662 */
+{
+    const double x = port_random(r);
+    double q = 0.0;
+    unsigned ui;
+    for (ui = 0u; ui < n; ui++) {
+        q += pa[ui];
+        if (x < q) {
+            break;
+        }
+    }
+    return ui;
+}
+
+double port_hyperexponential(port_rng *r, unsigned n, const double *ma, const double *pa)  /* :299-313 */
+{
+    const unsigned ui = port_loaded_dice(r, n, pa);
+    return port_exponential(r, ma[ui]);
+}
+
+/* Marsaglia & Tsang, src/cmb_random.c:465-497 */
+double port_std_gamma(port_rng *r, double shape)
+{
+    const double d = shape - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    double x, v;
+    for (;;) {
+        do {
+            x = port_std_normal(r);
+            v = 1.0 + c * x;
+        } while (v <= 0.0);
+        const double w = v * v * v;
+        const double u = port_random(r);
+        if ((u < 1.0 - 0.331 * (x * x) * (x * x))
+            || (log(u) < (0.5 * x * x) + (d * (1.0 - w + log(w))))) {
+            return d * w;
+        }
+    }
+}
+
+/* include/cmb_random.h:451-463.  The two factors of the shape < 1 branch are unsequenced in
+ * the reference; gcc evaluates the std_gamma call first (checked against oracle/_ref) */
+double port_gamma(port_rng *r, double shape, double scale)
+{
+    if (shape >= 1.0) {
+        return scale * port_std_gamma(r, shape);
+    }
+    const double g = port_std_gamma(r, shape + 1.0);
+    const double u = port_random(r);
+    return scale * (g * pow(u, 1.0 / shape));
+}
+
+double port_std_beta(port_rng *r, double a, double b)          /* :476-487 */
+{
+    const double x = port_std_gamma(r, a);
+    const double y = port_std_gamma(r, b);
+    return x / (x + y);
+}
+
+double port_beta(port_rng *r, double a, double b, double min, double max)  /* :500-512 */
+{
+    return min + (max - min) * port_std_beta(r, a, b);
+}
+
+double port_PERT_mod(port_rng *r, double min, double mode, double max, double lambda)  /* src/cmb_random.c:523-538 */
+{
+    const double rng = max - min;
+    const double a = 1.0 + lambda * (mode - min) / rng;
+    const double b = 1.0 + lambda * (max - mode) / rng;
+    return min + rng * port_std_beta(r, a, b);
+}
+
+double port_weibull(port_rng *r, double shape, double scale)   /* include/cmb_random.h:571-582 */
+{
+    const double u = port_exponential(r, 1.0);
+    return scale * pow(u, 1.0 / shape);
+}
+
+double port_pareto(port_rng *r, double shape, double mode)     /* :595-605 */
+{
+    return mode / pow(port_random(r), 1.0 / shape);
+}
+
+double port_chisquared(port_rng *r, double k)                  /* :618-626 */
+{
+    return port_gamma(r, k / 2.0, 2.0);
+}
+
+double port_F_dist(port_rng *r, double a, double b)            /* :639-653 */
+{
+    const double x = port_chisquared(r, a) / a;
+    double y;
+    while ((y = port_chisquared(r, b) / b) == 0.0) {}
+    return x / y;
+}
+
+double port_std_t_dist(port_rng *r, double v)                  /* :668-679 */
+{
+    const double x = port_std_normal(r);
+    double y;
+    while ((y = port_chisquared(r, v)) == 0.0) {}
+    return x / sqrt(y / v);
+}
+
+double port_rayleigh(port_rng *r, double s)                    /* :714-725 */
+{
+    const double x = port_normal(r, 0.0, s);
+    const double y = port_normal(r, 0.0, s);
+    return sqrt(x * x + y * y);
+}
+
+/* src/cmb_random.c:541-552: 64 coin flips per sfc64 word, most significant bit first */
+typedef struct { uint64_t bits; unsigned pos; } port_flipper;
+
+static int port_flip(port_rng *r, port_flipper *f)
+{
+    if (f->pos == 0u) {
+        f->bits = port_sfc64(r);
+        f->pos = 64u;
+    }
+    return (int)((f->bits >> --f->pos) & 1u);
+}
+
+unsigned port_geometric(port_rng *r, double p)                 /* :558-573 */
+{
+    const double denom = -log(1.0 - p);
+    return (unsigned)ceil(port_std_exponential(r) / denom);
+}
+
+unsigned port_binomial(port_rng *r, unsigned n, double p)      /* :576-588 */
+{
+    unsigned s = 0u;
+    for (unsigned i = 0u; i < n; i++) {
+        s += port_bernoulli(r, p);
+    }
+    return s;
+}
+
+unsigned port_negative_binomial(port_rng *r, unsigned m, double p)         /* :594-606 */
+{
+    unsigned f = 0u;
+    for (unsigned i = 0u; i < m; i++) {
+        f += port_geometric(r, p) - 1u;
+    }
+    return f;
+}
+
+unsigned port_poisson(port_rng *r, double rate)                /* :612-632 */
+{
+    const double m = 1.0 / rate;
+    double t = 0.0;
+    unsigned ctr = 0u;
+    for (;;) {
+        t += port_exponential(r, m);
+        if (t <= 1.0) {
+            ctr++;
+        }
+        else {
+            break;
+        }
+    }
+    return ctr;
+}
+
+/* Vose alias tables, src/cmb_random.c:672-752; sampling include/cmb_random.h:922-933 */
+static uint64_t alias_secure(double p)
+{
+    if (p <= 0.0) {
+        return 0u;
+    }
+    if (p >= 1.0) {
+        return UINT64_MAX;
+    }
+    return (uint64_t)(p * (double)UINT64_MAX);
+}
+
+void port_alias_create(unsigned n, const double *pa, uint64_t *uprob, unsigned *alias)
+{
+    double *work = calloc(n, sizeof(double));
+    unsigned *small = calloc(n, sizeof(unsigned));
+    unsigned *large = calloc(n, sizeof(unsigned));
+    double psum = 0.0;
+    for (unsigned i = 0u; i < n; i++) {
+        psum += pa[i];
+        uprob[i] = 0u;
+        alias[i] = 0u;
+    }
+    unsigned ns = 0u, nl = 0u;
+    for (unsigned i = 0u; i < n; i++) {
+        work[i] = pa[i] * n / psum;
+        if (work[i] < 1.0) {
+            small[ns++] = i;
+        }
+        else {
+            large[nl++] = i;
+        }
+    }
+    while (ns > 0u && nl > 0u) {
+        const unsigned l = small[--ns];
+        const unsigned g = large[--nl];
+        uprob[l] = alias_secure(work[l]);
+        alias[l] = g;
+        work[g] = (work[g] + work[l]) - 1.0;
+        if (work[g] < 1.0) {
+            small[ns++] = g;
+        }
+        else {
+            large[nl++] = g;
+        }
+    }
+    while (nl > 0u) {
+        uprob[large[--nl]] = UINT64_MAX;
+    }
+    while (ns > 0u) {
+        uprob[small[--ns]] = UINT64_MAX;
+    }
+    free(large);
+    free(small);
+    free(work);
+}
+
+unsigned port_alias_sample(port_rng *r, unsigned n, const uint64_t *uprob, const unsigned *alias)
+{
+    const unsigned idx = (unsigned)floor(n * port_random(r));
+    const bool c = port_sfc64(r) >= uprob[idx];
+    return c ? alias[idx] : idx;
+}
+
+int port_rng_draws_ex(uint64_t seed, int kind, const double *par, uint32_t npar, uint64_t n, double *out)
+{
+    (void)npar;
+    port_rng r;
+    port_rng_init(&r, seed);
+    port_flipper flips = { 0u, 0u };
+    uint64_t uprob[64];
+    unsigned alias[64];
+    if (kind == 30) {
+        if ((unsigned)par[0] > 64u) {
+            return -1;
+        }
+        port_alias_create((unsigned)par[0], &par[1], uprob, alias);
+    }
+    for (uint64_t i = 0u; i < n; i++) {
+        switch (kind) {
+        case 9:  out[i] = port_triangular(&r, par[0], par[1], par[2]); break;
+        case 10: out[i] = port_lognormal(&r, par[0], par[1]); break;
+        case 11: out[i] = port_logistic(&r, par[0], par[1]); break;
+        case 12: out[i] = port_cauchy(&r, par[0], par[1]); break;
+        case 13: out[i] = port_hypoexponential(&r, (unsigned)par[0], &par[1]); break;
+        case 14: out[i] = port_hyperexponential(&r, (unsigned)par[0], &par[1], &par[1 + (unsigned)par[0]]); break;
+        case 15: out[i] = port_gamma(&r, par[0], par[1]); break;
+        case 16: out[i] = port_beta(&r, par[0], par[1], par[2], par[3]); break;
+        case 17: out[i] = port_PERT_mod(&r, par[0], par[1], par[2], 4.0); break;
+        case 18: out[i] = port_weibull(&r, par[0], par[1]); break;
+        case 19: out[i] = port_pareto(&r, par[0], par[1]); break;
+        case 20: out[i] = port_chisquared(&r, par[0]); break;
+        case 21: out[i] = port_F_dist(&r, par[0], par[1]); break;
+        case 22: out[i] = par[0] + par[1] * port_std_t_dist(&r, par[2]); break;
+        case 23: out[i] = port_rayleigh(&r, par[0]); break;
+        case 24: out[i] = (double)port_flip(&r, &flips); break;
+        case 25: out[i] = (double)port_geometric(&r, par[0]); break;
+        case 26: out[i] = (double)port_binomial(&r, (unsigned)par[0], par[1]); break;
+        case 27: out[i] = (double)port_negative_binomial(&r, (unsigned)par[0], par[1]); break;
+        case 28: out[i] = (double)port_poisson(&r, par[0]); break;
+        case 29: out[i] = (double)port_loaded_dice(&r, (unsigned)par[0], &par[1]); break;
+        case 30: out[i] = (double)port_alias_sample(&r, (unsigned)par[0], uprob, alias); break;
+        case 31: out[i] = port_std_gamma(&r, par[0]); break;
+        case 32: out[i] = port_PERT_mod(&r, par[0], par[1], par[2], par[3]); break;
+        case 33: out[i] = (double)port_negative_binomial(&r, (unsigned)par[0], par[1]); break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
 /* =============================================================== summaries */
 
 /* src/cmb_datasummary.c:37-50 */

@@ -39,6 +39,8 @@ long     port_dice(port_rng *r, long a, long b);
 
 /* same kinds as ref_rng_draws() in oracle/ref_build/ref_driver.c */
 int port_rng_draws(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out);
+/* kinds 9..33 = the rest of cmb_random, same numbering as ref_rng_draws_ex() */
+int port_rng_draws_ex(uint64_t seed, int kind, const double *par, uint32_t npar, uint64_t n, double *out);
 
 /* ---- cmb_datasummary / cmb_wtdsummary ---- */
 typedef struct { uint64_t count; double min, max, m1, m2, m3, m4; } port_summary;

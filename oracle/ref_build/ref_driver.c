@@ -1379,6 +1379,53 @@ int ref_rng_draws(uint64_t seed, int kind, double p0, double p1, uint64_t n, dou
     return 0;
 }
 
+/* The rest of cmb_random (include/cmb_random.h:189-940, src/cmb_random.c:299-766): kinds 9..33,
+ * parameters in par[] (arrays inline: a count, then the values).  The same kind numbers are
+ * implemented by oracle/port (port_rng_draws_ex) and the CUDA library (cimba_b200_rng_draws_ex). */
+int ref_rng_draws_ex(uint64_t seed, int kind, const double *par, uint32_t npar, uint64_t n, double *out)
+{
+    cmb_unused(npar);
+    cmb_random_initialize(seed);
+    struct cmb_random_alias *alias = NULL;
+    if (kind == 30) {
+        alias = cmb_random_alias_create((unsigned)par[0], &par[1]);
+    }
+    for (uint64_t i = 0u; i < n; i++) {
+        switch (kind) {
+        case 9:  out[i] = cmb_random_triangular(par[0], par[1], par[2]); break;
+        case 10: out[i] = cmb_random_lognormal(par[0], par[1]); break;
+        case 11: out[i] = cmb_random_logistic(par[0], par[1]); break;
+        case 12: out[i] = cmb_random_cauchy(par[0], par[1]); break;
+        case 13: out[i] = cmb_random_hypoexponential((unsigned)par[0], &par[1]); break;
+        case 14: out[i] = cmb_random_hyperexponential((unsigned)par[0], &par[1], &par[1 + (unsigned)par[0]]); break;
+        case 15: out[i] = cmb_random_gamma(par[0], par[1]); break;
+        case 16: out[i] = cmb_random_beta(par[0], par[1], par[2], par[3]); break;
+        case 17: out[i] = cmb_random_PERT(par[0], par[1], par[2]); break;
+        case 18: out[i] = cmb_random_weibull(par[0], par[1]); break;
+        case 19: out[i] = cmb_random_pareto(par[0], par[1]); break;
+        case 20: out[i] = cmb_random_chisquared(par[0]); break;
+        case 21: out[i] = cmb_random_F_dist(par[0], par[1]); break;
+        case 22: out[i] = cmb_random_t_dist(par[0], par[1], par[2]); break;
+        case 23: out[i] = cmb_random_rayleigh(par[0]); break;
+        case 24: out[i] = (double)cmb_random_flip(); break;
+        case 25: out[i] = (double)cmb_random_geometric(par[0]); break;
+        case 26: out[i] = (double)cmb_random_binomial((unsigned)par[0], par[1]); break;
+        case 27: out[i] = (double)cmb_random_negative_binomial((unsigned)par[0], par[1]); break;
+        case 28: out[i] = (double)cmb_random_poisson(par[0]); break;
+        case 29: out[i] = (double)cmb_random_loaded_dice((unsigned)par[0], &par[1]); break;
+        case 30: out[i] = (double)cmb_random_alias_sample(alias); break;
+        case 31: out[i] = cmb_random_std_gamma(par[0]); break;
+        case 32: out[i] = cmb_random_PERT_mod(par[0], par[1], par[2], par[3]); break;
+        case 33: out[i] = (double)cmb_random_pascal((unsigned)par[0], par[1]); break;
+        default: return -1;
+        }
+    }
+    if (alias != NULL) {
+        cmb_random_alias_destroy(alias);
+    }
+    return 0;
+}
+
 /* Summary parity helpers: out = {count, min, max, m1, m2, m3, m4} */
 static void export_summary(const struct cmb_datasummary *ds, double *out)
 {

@@ -21,7 +21,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT / "tests"))
-from oracle_libs import load_ref, Result, trace_trial, rng_draws   # noqa: E402
+from oracle_libs import DIST_CASES, rng_draws_ex, load_ref, Result, trace_trial, rng_draws   # noqa: E402
 
 KAT_SEED = 0x34F05C64D7AD598F          # test/tools/test_stochastic.py:58-69
 SEEDS = [KAT_SEED, 12345, 7, 0, 2**64 - 1]
@@ -66,6 +66,13 @@ def main():
             per[str(kind)] = {"p0": p0, "p1": p1, "n": n, "first": first, **checksum(v)}
         rng[str(seed)] = per
     out["rng"] = rng
+
+    # the rest of cmb_random: 65 536 draws per case (a multiple of 64, see rng_draws_ex), KAT seed
+    dist = []
+    for kind, par in DIST_CASES:
+        v = np.array(rng_draws_ex(ref, "ref", KAT_SEED, kind, par, 65_536))
+        dist.append({"kind": kind, "params": par, "n": 65_536, "first": hexes(v[:8]), **checksum(v)})
+    out["distributions"] = dist
     out["fmix64"] = {str(s): [int(ref.ref_fmix64(s, k)) for k in range(4)] for s in SEEDS}
 
     trials = []

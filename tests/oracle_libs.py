@@ -103,3 +103,29 @@ def rng_draws(lib, prefix, seed, kind, p0, p1, n):
     rc = getattr(lib, f"{prefix}_rng_draws")(seed, kind, p0, p1, n, out.ctypes.data_as(_DP))
     assert rc == 0
     return out
+
+
+# kinds 9..33 of *_rng_draws_ex: one parameter set per distribution (+ a few extra corners)
+DIST_CASES = [
+    (9, [1.0, 2.5, 7.0]), (10, [0.5, 0.75]), (11, [1.0, 2.0]), (12, [0.0, 1.5]), (13, [3, 0.5, 1.0, 2.0]),
+    (14, [3, 0.5, 1.0, 4.0, 0.2, 0.5, 0.3]), (15, [2.5, 1.5]), (16, [2.0, 3.5, 1.0, 4.0]), (17, [1.0, 2.0, 6.0]),
+    (18, [1.7, 2.0]), (19, [2.5, 1.0]), (20, [3.0]), (21, [4.0, 7.0]), (22, [1.0, 2.0, 5.0]), (23, [1.3]), (24, []),
+    (25, [0.3]), (26, [12, 0.35]), (27, [4, 0.4]), (28, [3.5]), (29, [4, 0.1, 0.2, 0.3, 0.4]),
+    (30, [5, 0.05, 0.25, 0.4, 0.1, 0.2]), (31, [4.2]), (32, [1.0, 2.0, 6.0, 2.5]), (33, [3, 0.6]),
+    (15, [0.6, 2.0]), (20, [1.0]), (31, [1.0]), (9, [0.0, 0.0, 1.0]), (28, [0.2]),
+]
+# the variate IS a log / exp / pow result: CUDA's libm vs glibc may differ in the last places
+DIST_LIBM_KINDS = {10, 11, 18, 19}
+
+
+def rng_draws_ex(lib, prefix, seed, kind, params, n):
+    """n variates of kind 9..33 from {ref,port}_rng_draws_ex (n % 64 == 0 keeps the reference's
+    thread-local coin-flip cache empty between calls)."""
+    f = getattr(lib, f"{prefix}_rng_draws_ex")
+    f.restype = C.c_int
+    f.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_double), C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]
+    out = (C.c_double * n)()
+    par = (C.c_double * max(1, len(params)))(*[float(v) for v in params])
+    rc = f(seed, kind, par, len(params), n, out)
+    assert rc == 0, (prefix, kind, rc)
+    return list(out)

@@ -55,6 +55,30 @@ def test_rng_streams_match_golden_checksums(port, golden, kind):
         assert int(np.add.reduce(u, dtype=np.uint64)) == g["sum"]
 
 
+def test_remaining_distributions_match_golden(port, golden):
+    """Kinds 9..33 (triangular ... pascal): the restatement against streams drawn from the reference."""
+    from oracle_libs import rng_draws_ex
+    assert len(golden["distributions"]) >= 25
+    for g in golden["distributions"]:
+        v = np.array(rng_draws_ex(port, "port", KAT_SEED, g["kind"], g["params"], g["n"]))
+        u = _u64(v)
+        tag = (g["kind"], g["params"])
+        assert [float.hex(float(x)) for x in v[:8]] == g["first"], tag
+        assert int(np.bitwise_xor.reduce(u)) == g["xor"], tag
+        assert int(np.add.reduce(u, dtype=np.uint64)) == g["sum"], tag
+
+
+def test_remaining_distributions_match_live_reference(port, ref):
+    from oracle_libs import DIST_CASES, rng_draws_ex
+    if ref is None:
+        pytest.skip("oracle/_ref not built here (no /root/reference)")
+    for kind, par in DIST_CASES:
+        for seed in (1, 0xC0FFEE):
+            a = rng_draws_ex(ref, "ref", seed, kind, par, 8192)
+            b = rng_draws_ex(port, "port", seed, kind, par, 8192)
+            assert a == b, (kind, par, seed)
+
+
 def test_trials_match_golden(port, golden):
     """Every committed single-trial record: counts exact, clock and sums bit-exact,
     and the first 512 pops (key, time) of the 1000-object runs."""
