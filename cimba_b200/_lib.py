@@ -70,6 +70,7 @@ SYMBOLS = {
     "cimba_b200_launch_count": (C.c_uint64, []),
     "cimba_b200_summarize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cimba_b200_run_experiment": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment)]),
+    "cimba_b200_release_cache": (None, []),
     "cimba_b200_run_experiment_all_gpus": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment),
                                                      C.c_int]),
     "cimba_b200_datasummary_initialize": (None, [C.POINTER(DataSummaryStruct)]),

@@ -185,6 +185,11 @@ int cimba_b200_run_experiment(void *your_experiment_array,
                               size_t trial_struct_size,
                               const cimba_b200_experiment *desc);
 
+/* cimba_b200_run_experiment keeps its pinned staging buffers, device arena and stream per device
+ * between calls (grow-only).  This frees them (the analogue of the reference's per-thread mempools
+ * being torn down at thread exit, src/cimba.c:134-139). */
+void cimba_b200_release_cache(void);
+
 /* The same, sharded over every visible GPU (or the first max_gpus > 0 of them): one host
  * thread per GPU runs a contiguous block of the array - the counterpart of the
  * reference executive's one pthread per core (src/cimba.c:171-182).  Results do not
