@@ -27,6 +27,7 @@
 #include "buffer_model.cuh"
 #include "prioq_model.cuh"
 #include "timers_model.cuh"
+#include "harbor_model.cuh"
 #include "hold_model.cuh"
 #include "rng.cuh"
 #include "distributions.cuh"
@@ -197,6 +198,9 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
     }
+    if (job->model == CIMBA_B200_MODEL_HARBOR) {
+        return job->num_trials * (uint64_t)sizeof(HarborState);
+    }
     if (is_general_model(job->model)) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
     }
@@ -359,6 +363,39 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "guarded_kernel launch");
+    }
+    if (job->model == CIMBA_B200_MODEL_HARBOR) {
+        if (job->servers < 3 || job->servers > 255)
+            return fail(CIMBA_B200_EINVAL, "tugs (servers) must be in 3..255 for CIMBA_B200_MODEL_HARBOR (a large ship needs 3)");
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_HARBOR supports CIMBA_B200_MAP_LANE only");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        HarborArgs ha{};
+        ha.tugs = job->servers;
+        ha.master_seed = job->master_seed;
+        ha.first_trial = job->first_trial;
+        ha.num_trials = job->num_trials;
+        ha.duration = job->num_objects;
+        ha.arr_mean = job->arr_mean;
+        ha.unload_small = job->srv_mean;
+        ha.events = job->events;
+        ha.objects = job->objects;
+        ha.t_end = job->t_end;
+        ha.sum_wait = job->sum_wait;
+        ha.status = job->status;
+        ha.max_queue = job->max_queue;
+        ha.counters = job->counters;
+        ha.state = (HarborState *)job->workspace;
+        ha.trace_cap = job->trace_cap;
+        ha.trace_key = job->trace_key;
+        ha.trace_time = job->trace_time;
+        const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
+        if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
+        if (trace) harbor_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ha);
+        else       harbor_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ha);
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "harbor_kernel launch");
     }
     if (job->model == CIMBA_B200_MODEL_HOLD) {
         if (job->servers < 1 || job->servers > HOLD_CAP - 8)

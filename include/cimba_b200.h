@@ -66,6 +66,13 @@ extern "C" {
                                     * time-weighted queue-length cmb_wtdsummary {count, min, max, m1, m2, m3, m4, wsum}
                                     * (count as u64, the rest as IEEE-754 bit patterns) that cmb_timeseries_summarize
                                     * (src/cmb_timeseries.c:167-188) computes from the stored history - folded on the fly */
+#define CIMBA_B200_MODEL_HARBOR 10   /* test/test_condition.c (= tutorial/tut_4_1.c), the reference's harbor: weather and tide processes
+                                    * signalling a cmb_condition every hour, one ship PROCESS per arrival (up to 120 alive at once)
+                                    * waiting on it with a predicate over depth, wind, `servers` tugs and 6 + 3 berths held in three
+                                    * cmb_resourcepools, a departure process on a second condition, an end event at t = num_objects
+                                    * hours.  arr_mean = mean inter-arrival time, srv_mean = mean unloading time of a small ship.
+                                    * counters: ships through (small, large), their mean system times, tug / berth history summaries,
+                                    * harbormaster reactivations - with the golden seed and 873 600 h exactly test/reference/condition.txt */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

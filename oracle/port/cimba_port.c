@@ -3366,6 +3366,424 @@ static void run_timers(uint64_t seed, uint64_t duration, double arr_mean, double
     free(w);
 }
 
+/* ======================================== model 10: the harbor (test/test_condition.c)
+ *
+ * ref_driver.c model 10 restated: dynamically created ship processes, a cmb_condition with
+ * user predicates signalled every hour by two processes (evaluate-all, two passes, in heap
+ * array order: src/cmb_condition.c:120-167), three cmb_resourcepools with greedy partial
+ * grabs (src/cmb_resourcepool.c:362-533) and their histories folded into time-weighted
+ * summaries, a second condition handing finished ships to a collector process, and an end
+ * event that stops everything - ships in arrival order - leaving the stale guard entries of
+ * SURVEY.md quirk 2 behind.
+ */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846     /* the reference's value (glibc math.h under _POSIX_C_SOURCE) */
+#endif
+enum { HB_WEATHER = 0, HB_TIDE, HB_ARRIVALS, HB_DEPARTURES, HB_DOTS, HB_SHIP };
+
+typedef struct hship {
+    gproc    g;
+    uint64_t id;
+    unsigned size, need, held_tugs, held_berth, rem;
+    double   max_wind, min_depth, t_arr, t_sys;
+    bool     tugs_listed_first;         /* order of the process's resources list (push-front) */
+    bool     active;
+    struct hship *next_departed, *next_all;
+} hship;
+
+typedef struct {
+    uint64_t cap, in_use;
+    heap     guard;
+    port_wsummary hist;                 /* cmb_timeseries_add fused with cmb_timeseries_summarize */
+    double   x, t;
+    uint64_t n;
+} hpool;
+
+typedef struct hsim {
+    gsim     s;
+    double   wind_magnitude, wind_direction, water_depth;
+    hpool    tugs, berth[2];
+    heap     harbormaster, davyjones;
+    hship    fixed[5];                  /* weather, tide, arrivals, departures, dots */
+    hship   *all;                       /* every ship struct still allocated */
+    hship   *departed;
+    uint64_t next_id, alive, most_alive;
+    double   arr_mean, unload_small;
+    port_summary through[2];
+} hsim;
+
+static void hb_record(hsim *w, hpool *p)                /* record_sample, src/cmb_resourcepool.c:239-247 */
+{
+    if (p->n > 0u) {
+        (void)port_wsummary_add(&p->hist, p->x, w->s.now - p->t);
+    }
+    p->x = (double)p->in_use;
+    p->t = w->s.now;
+    p->n++;
+}
+
+static void hb_pool_signal(hsim *w, hpool *p)
+{
+    g_signal(&w->s, &p->guard, p->cap - p->in_use > 0u);
+}
+
+/* one pass of cmi_pool_acquire_inner's loop (no pre-emption): true when the claim is filled */
+static bool hb_pool_grab(hsim *w, hpool *p, unsigned *rem, unsigned *held)
+{
+    const uint64_t available = p->cap - p->in_use;
+    if (available >= *rem) {
+        p->in_use += *rem;
+        hb_record(w, p);
+        *held += *rem;
+        *rem = 0u;
+        hb_pool_signal(w, p);
+        return true;
+    }
+    if (available > 0u) {
+        p->in_use += available;
+        hb_record(w, p);
+        *rem -= (unsigned)available;
+        *held += (unsigned)available;
+    }
+    return false;
+}
+
+static void hb_pool_release(hsim *w, hpool *p, unsigned amount, unsigned *held)     /* :561-605 */
+{
+    *held -= amount;
+    p->in_use -= amount;
+    hb_record(w, p);
+    hb_pool_signal(w, p);
+}
+
+static bool hb_can_dock(const hsim *w, const hship *sh)
+{
+    if (w->water_depth < sh->min_depth) {
+        return false;
+    }
+    if (w->wind_magnitude > sh->max_wind) {
+        return false;
+    }
+    if (w->tugs.cap - w->tugs.in_use < sh->need) {
+        return false;
+    }
+    return w->berth[sh->size].cap - w->berth[sh->size].in_use >= 1u;
+}
+
+/* cmb_condition_signal, src/cmb_condition.c:120-167 */
+static uint64_t hb_condition_signal(hsim *w, heap *cv, bool is_harbormaster)
+{
+    gsim *s = &w->s;
+    uint64_t *hit = malloc((cv->count + 1u) * sizeof(*hit));
+    uint64_t cnt = 0u;
+    for (uint64_t k = 1u; k <= cv->count; k++) {
+        hship *p = (hship *)(intptr_t)cv->slot[k].item[0];
+        const bool ok = is_harbormaster ? hb_can_dock(w, p) : (w->departed != NULL);
+        if (ok) {
+            hit[cnt++] = cv->slot[k].key;
+            g_schedule(s, ACT_WAKE_CONDITION, p, SIG_SUCCESS, s->now, p->g.prio);
+        }
+    }
+    for (uint64_t k = 0u; k < cnt; k++) {
+        heap_remove(cv, hit[k]);
+    }
+    free(hit);
+    return cnt;
+}
+
+static double hb_pert(hsim *w, double min, double mode, double max)
+{
+    return port_PERT_mod(&w->s.rng, min, mode, max, 4.0);
+}
+
+static void hb_body(hsim *w, hship *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    (void)sig;
+    switch (p->g.kind * 10 + p->g.pc) {
+    case HB_WEATHER * 10:
+        for (;;) {
+            {
+                const double gust = port_rayleigh(&s->rng, 5.0);
+                w->wind_magnitude = 0.5 * gust + 0.5 * w->wind_magnitude;
+                const double d1 = hb_pert(w, 0.0, 225.0, 360.0);
+                const double d2 = hb_pert(w, 0.0, 45.0, 360.0);
+                w->wind_direction = 0.75 * d1 + 0.25 * d2;
+                s->res->counter[7] += hb_condition_signal(w, &w->harbormaster, true);
+            }
+            g_hold_begin(s, &p->g, 1.0);
+            p->g.pc = 1;
+            return;
+    case HB_WEATHER * 10 + 1:
+            (void)g_hold_end(s, &p->g, sig);
+        }
+    case HB_TIDE * 10:
+        for (;;) {
+            {
+                const double half_month = 0.5 * 29.5 * 24.0;
+                const double t = fmod(s->now, half_month);
+                const double astro = 15.0 + 1.0 * sin(2.0 * M_PI * t / 12.4) + 0.5 * sin(2.0 * M_PI * t / 24.0)
+                                   + 0.25 * sin(2.0 * M_PI * t / (0.5 * 29.5 * 24));
+                const double surge = 0.5 * w->wind_magnitude
+                                   - 0.5 * w->wind_magnitude * sin(w->wind_direction * M_PI / 180.0);
+                w->water_depth = astro + surge;
+                s->res->counter[7] += hb_condition_signal(w, &w->harbormaster, true);
+            }
+            g_hold_begin(s, &p->g, 1.0);
+            p->g.pc = 1;
+            return;
+    case HB_TIDE * 10 + 1:
+            (void)g_hold_end(s, &p->g, sig);
+        }
+    case HB_ARRIVALS * 10:
+        for (;;) {
+            g_hold_begin(s, &p->g, port_exponential(&s->rng, w->arr_mean));
+            p->g.pc = 1;
+            return;
+    case HB_ARRIVALS * 10 + 1:
+            (void)g_hold_end(s, &p->g, sig);
+            {
+                hship *sh = calloc(1, sizeof(*sh));
+                sh->id = ++w->next_id;
+                sh->size = port_bernoulli(&s->rng, 0.25);
+                sh->max_wind = (sh->size == 0u) ? 10.0 : 12.0;
+                sh->min_depth = (sh->size == 0u) ? 8.0 : 13.0;
+                sh->need = (sh->size == 0u) ? 1u : 3u;
+                sh->g.kind = HB_SHIP;
+                sh->next_all = w->all;
+                w->all = sh;
+                g_schedule(s, ACT_START, sh, 0, s->now, 0);
+            }
+        }
+    case HB_DEPARTURES * 10:
+        for (;;) {
+            g_wait_begin(s, &w->davyjones, &p->g);
+            p->g.pc = 1;
+            return;
+    case HB_DEPARTURES * 10 + 1:
+            (void)g_wait_end(s, &w->davyjones, &p->g, sig);
+            {
+                hship *sh = w->departed;
+                w->departed = sh->next_departed;
+                (void)port_summary_add(&w->through[sh->size], sh->t_sys);
+                s->res->sum_wait += sh->t_sys;
+                s->res->counter[sh->size] += 1u;
+                for (hship **pp = &w->all; *pp != NULL; pp = &(*pp)->next_all) {
+                    if (*pp == sh) {
+                        *pp = sh->next_all;
+                        break;
+                    }
+                }
+                free(sh);
+            }
+        }
+    case HB_DOTS * 10:
+        for (;;) {
+            g_hold_begin(s, &p->g, 24.0 * 7 * 52);
+            p->g.pc = 1;
+            return;
+    case HB_DOTS * 10 + 1:
+            (void)g_hold_end(s, &p->g, sig);
+        }
+    case HB_SHIP * 10:
+        p->t_arr = s->now;
+        p->active = true;
+        if (++w->alive > w->most_alive) {
+            w->most_alive = w->alive;
+        }
+        while (!hb_can_dock(w, p)) {
+            g_wait_begin(s, &w->harbormaster, &p->g);
+            p->g.pc = 1;
+            return;
+    case HB_SHIP * 10 + 1:
+            (void)g_wait_end(s, &w->harbormaster, &p->g, sig);
+        }
+        p->rem = 1u;                                    /* both are there: the predicate just said so */
+        (void)hb_pool_grab(w, &w->berth[p->size], &p->rem, &p->held_berth);
+        p->rem = p->need;
+        (void)hb_pool_grab(w, &w->tugs, &p->rem, &p->held_tugs);
+        g_hold_begin(s, &p->g, hb_pert(w, 0.4, 0.5, 0.8));
+        p->g.pc = 2;
+        return;
+    case HB_SHIP * 10 + 2:
+        (void)g_hold_end(s, &p->g, sig);
+        hb_pool_release(w, &w->tugs, p->need, &p->held_tugs);
+        {
+            const double tua = (p->size == 0u) ? w->unload_small : 1.5 * w->unload_small;
+            g_hold_begin(s, &p->g, hb_pert(w, 0.75 * tua, tua, 2 * tua));
+        }
+        p->g.pc = 3;
+        return;
+    case HB_SHIP * 10 + 3:
+        (void)g_hold_end(s, &p->g, sig);
+        p->rem = p->need;
+        while (!hb_pool_grab(w, &w->tugs, &p->rem, &p->held_tugs)) {
+            g_wait_begin(s, &w->tugs.guard, &p->g);
+            p->g.pc = 4;
+            return;
+    case HB_SHIP * 10 + 4:
+            (void)g_wait_end(s, &w->tugs.guard, &p->g, sig);
+        }
+        g_hold_begin(s, &p->g, hb_pert(w, 0.4, 0.5, 0.8));
+        p->g.pc = 5;
+        return;
+    case HB_SHIP * 10 + 5:
+        (void)g_hold_end(s, &p->g, sig);
+        hb_pool_release(w, &w->berth[p->size], 1u, &p->held_berth);
+        hb_pool_release(w, &w->tugs, p->need, &p->held_tugs);
+        p->active = false;
+        w->alive--;
+        p->next_departed = w->departed;
+        w->departed = p;
+        (void)hb_condition_signal(w, &w->davyjones, false);
+        p->t_sys = s->now - p->t_arr;
+        p->g.status = ST_FINISHED;                      /* return -> cmb_process_exit: nothing held or awaited */
+        return;
+    }
+}
+
+/* cmb_process_stop, src/cmb_process.c:698-723, incl. cmi_process_drop_resources (:507-527) */
+static void hb_stop(hsim *w, hship *p)
+{
+    if (p->g.status != ST_RUNNING) {
+        return;
+    }
+    p->g.status = ST_FINISHED;
+    g_cancel_awaiteds(&w->s, &p->g);
+    /* resources list: a pool is pushed to the front when its first unit is taken */
+    if (p->held_tugs > 0u) {
+        w->tugs.in_use -= p->held_tugs;
+        p->held_tugs = 0u;
+        hb_pool_signal(w, &w->tugs);
+    }
+    if (p->held_berth > 0u) {
+        w->berth[p->size].in_use -= p->held_berth;
+        p->held_berth = 0u;
+        hb_pool_signal(w, &w->berth[p->size]);
+    }
+}
+
+static void hb_pool_init(hpool *p, uint64_t cap)
+{
+    p->cap = cap;
+    heap_init(&p->guard, 3u, guard_before);
+    port_wsummary_init(&p->hist);
+}
+
+static void run_harbor(int tugs, uint64_t seed, uint64_t duration, double arr_mean, double unload_small,
+                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+{
+    hsim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    w->arr_mean = arr_mean;
+    w->unload_small = unload_small;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&w->harbormaster, 3u, guard_before);
+    heap_init(&w->davyjones, 3u, guard_before);
+    hb_pool_init(&w->tugs, (uint64_t)tugs);
+    hb_pool_init(&w->berth[0], 6u);
+    hb_pool_init(&w->berth[1], 3u);
+    port_summary_init(&w->through[0]);
+    port_summary_init(&w->through[1]);
+
+    /* creation order of test/test_condition.c:523-586 fixes the event keys */
+    for (int i = 0; i < 5; i++) {
+        w->fixed[i].g.kind = i;
+    }
+    g_schedule(s, ACT_START, &w->fixed[HB_WEATHER], 0, s->now, 0);
+    g_schedule(s, ACT_START, &w->fixed[HB_TIDE], 0, s->now, 0);
+    hb_record(w, &w->tugs);                             /* cmb_resourcepool_start_recording */
+    hb_record(w, &w->berth[0]);
+    hb_record(w, &w->berth[1]);
+    g_schedule(s, ACT_START, &w->fixed[HB_ARRIVALS], 0, s->now, 0);
+    g_schedule(s, ACT_START, &w->fixed[HB_DEPARTURES], 0, s->now, 0);
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+    g_schedule(s, ACT_START, &w->fixed[HB_DOTS], 0, s->now, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        hship *p = (hship *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->g.status = ST_RUNNING;
+            p->g.pc = 0;
+            hb_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(&p->g, AW_TIME, false, ev.key, NULL);
+            hb_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+            if (p->g.status == ST_RUNNING) {
+                hb_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_WAKE_CONDITION:
+            (void)aw_remove(&p->g, AW_RESOURCE, true, 0u, NULL);
+            if (p->g.status == ST_RUNNING) {
+                hb_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i < 5; i++) {
+                hb_stop(w, &w->fixed[i]);
+            }
+            for (;;) {                                  /* active ships in (arrival time, id) order = id order */
+                hship *first = NULL;
+                for (hship *q = w->all; q != NULL; q = q->next_all) {
+                    if (q->active && (first == NULL || q->id < first->id)) {
+                        first = q;
+                    }
+                }
+                if (first == NULL) {
+                    break;
+                }
+                first->active = false;
+                hb_stop(w, first);
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    out->objects = out->counter[0] + out->counter[1];
+    out->max_queue = w->most_alive;
+    memcpy(&out->counter[2], &w->through[0].m1, 8);
+    memcpy(&out->counter[3], &w->through[1].m1, 8);
+    out->counter[4] = w->tugs.hist.ds.count;
+    memcpy(&out->counter[5], &w->tugs.hist.ds.m1, 8);
+    out->counter[6] = w->berth[0].hist.ds.count | (w->berth[1].hist.ds.count << 32);
+
+    while (w->all != NULL) {
+        hship *q = w->all;
+        w->all = q->next_all;
+        free(q);
+    }
+    heap_free(&s->fel);
+    heap_free(&w->harbormaster);
+    heap_free(&w->davyjones);
+    heap_free(&w->tugs.guard);
+    heap_free(&w->berth[0].guard);
+    heap_free(&w->berth[1].guard);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -3383,6 +3801,11 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 10) {
+            run_harbor(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
+                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 8) {
             run_timers(port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -3446,6 +3869,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 10) {
+        run_harbor(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 8) {
         run_timers(seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;

@@ -32,6 +32,8 @@
 #include <cmb_condition.h>
 
 #include "cmi_mempool.h"
+#include "cmi_hashheap.h"
+#include <math.h>
 
 struct ref_trial {
     /* in */
@@ -1133,6 +1135,292 @@ static void run_timers_trial(struct ref_trial *t)
 }
 
 
+/* ------------------------------------------------- model 10: the harbor (test/test_condition.c)
+ *
+ * The reference's own condition-variable test model (also tutorial/tut_4_1.c), the
+ * "cmb_condition + divergent process" workload of BASELINE config 5 and SURVEY.md 8f-2,
+ * restated against the reference API with the same process creation order, the same draws
+ * in the same order and the same parameters, so that seed 0x34f05c64d7ad598f and a duration
+ * of 100 years reproduce test/reference/condition.txt (N 328781 small / 109454 large ships,
+ * berth and tug utilisation).  A weather and a tide process update the state once an hour
+ * and signal the harbormaster condition; an arrival process creates one ship PROCESS per
+ * arrival; a ship waits on the harbormaster until depth, wind, tugs and a berth all suit
+ * it, takes a berth and tugs from three cmb_resourcepools, docks, unloads, undocks, joins
+ * the departed list and signals Davy Jones, whose departure process collects the exit
+ * value; an idle "entertainment" process ticks once a year; an end event stops them all.
+ * num_objects = duration in hours, servers = tugs, arr_mean = mean inter-arrival time,
+ * srv_mean = mean unloading time of a small ship (a large one takes 1.5 x that).
+ * counters: [0] small ships through [1] large ships through [2] mean system time small (bits)
+ *           [3] ... large (bits) [4] tug-history samples with a duration [5] time-weighted mean
+ *           tugs in use (bits) [6] berth-history samples, small | large << 32 [7] ships
+ *           reactivated by the harbormaster
+ * sum_wait = sum of all system times in departure order; max_queue = most ships alive at once
+ */
+struct hb_world;
+
+struct hb_ship {
+    struct cmb_process core;            /* a ship IS a process (first member) */
+    uint64_t id;
+    double max_wind, min_depth;
+    unsigned tugs, size;
+    double t_sys;
+    struct hb_ship *next_departed;
+    struct hb_world *world;
+};
+
+struct hb_world {
+    struct ref_trial *trl;
+    double wind_magnitude, wind_direction, water_depth;
+    struct cmb_process *weather, *tide, *arrivals, *departures, *dots;
+    struct cmb_resourcepool *tugs, *berths[2];
+    struct cmb_condition *harbormaster, *davyjones;
+    struct cmi_hashheap *active;
+    struct hb_ship *departed;           /* LIFO, like the test's cmi_slist */
+    struct cmb_datasummary through[2];
+    uint64_t alive, most_alive;
+};
+
+static void *hb_weather_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct hb_world *w = vw;
+    for (;;) {
+        const double gust = cmb_random_rayleigh(5.0);
+        w->wind_magnitude = 0.5 * gust + 0.5 * w->wind_magnitude;
+        const double d1 = cmb_random_PERT(0.0, 225.0, 360.0);
+        const double d2 = cmb_random_PERT(0.0, 45.0, 360.0);
+        w->wind_direction = 0.75 * d1 + 0.25 * d2;
+        w->trl->counter[7] += cmb_condition_signal(w->harbormaster);
+        (void)cmb_process_hold(1.0);
+    }
+}
+
+static void *hb_tide_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct hb_world *w = vw;
+    for (;;) {
+        const double half_month = 0.5 * 29.5 * 24.0;
+        const double t = fmod(cmb_time(), half_month);
+        const double astro = 15.0 + 1.0 * sin(2.0 * M_PI * t / 12.4) + 0.5 * sin(2.0 * M_PI * t / 24.0)
+                           + 0.25 * sin(2.0 * M_PI * t / (0.5 * 29.5 * 24));
+        const double surge = 0.5 * w->wind_magnitude
+                           - 0.5 * w->wind_magnitude * sin(w->wind_direction * M_PI / 180.0);
+        w->water_depth = astro + surge;
+        w->trl->counter[7] += cmb_condition_signal(w->harbormaster);
+        (void)cmb_process_hold(1.0);
+    }
+}
+
+static bool hb_can_dock(const struct cmb_condition *cvp, const struct cmb_process *pp, const void *ctx)
+{
+    cmb_unused(cvp);
+    cmb_unused(ctx);
+    const struct hb_ship *s = (const struct hb_ship *)pp;
+    const struct hb_world *w = s->world;
+    if (w->water_depth < s->min_depth) {
+        return false;
+    }
+    if (w->wind_magnitude > s->max_wind) {
+        return false;
+    }
+    if (cmb_resourcepool_available(w->tugs) < s->tugs) {
+        return false;
+    }
+    return cmb_resourcepool_available(w->berths[s->size]) >= 1u;
+}
+
+static void *hb_ship_body(struct cmb_process *me, void *vw)
+{
+    struct hb_world *w = vw;
+    struct hb_ship *s = (struct hb_ship *)me;
+    const double t_arr = cmb_time();
+    cmi_hashheap_enqueue(w->active, s, NULL, NULL, NULL, s->id, t_arr, 0u);
+    if (++w->alive > w->most_alive) {
+        w->most_alive = w->alive;
+    }
+    while (!hb_can_dock(NULL, me, NULL)) {
+        (void)cmb_condition_wait(w->harbormaster, hb_can_dock, NULL);
+    }
+    (void)cmb_resourcepool_acquire(w->berths[s->size], 1u);
+    (void)cmb_resourcepool_acquire(w->tugs, s->tugs);
+    (void)cmb_process_hold(cmb_random_PERT(0.4, 0.5, 0.8));
+    cmb_resourcepool_release(w->tugs, s->tugs);
+    const double tua = (s->size == 0u) ? w->trl->srv_mean : 1.5 * w->trl->srv_mean;
+    (void)cmb_process_hold(cmb_random_PERT(0.75 * tua, tua, 2 * tua));
+    (void)cmb_resourcepool_acquire(w->tugs, s->tugs);
+    (void)cmb_process_hold(cmb_random_PERT(0.4, 0.5, 0.8));
+    cmb_resourcepool_release(w->berths[s->size], 1u);
+    cmb_resourcepool_release(w->tugs, s->tugs);
+    (void)cmi_hashheap_remove(w->active, s->id);
+    w->alive--;
+    s->next_departed = w->departed;
+    w->departed = s;
+    (void)cmb_condition_signal(w->davyjones);
+    s->t_sys = cmb_time() - t_arr;
+    return &s->t_sys;
+}
+
+static void *hb_arrivals_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct hb_world *w = vw;
+    uint64_t cnt = 0u;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        struct hb_ship *s = calloc(1, sizeof(*s));
+        s->id = ++cnt;
+        s->size = cmb_random_bernoulli(0.25);
+        s->max_wind = (s->size == 0u) ? 10.0 : 12.0;
+        s->min_depth = (s->size == 0u) ? 8.0 : 13.0;
+        s->tugs = (s->size == 0u) ? 1u : 3u;
+        s->world = w;
+        cmb_process_initialize(&s->core, "Ship", hb_ship_body, w, 0);
+        cmb_process_start(&s->core);
+    }
+}
+
+static bool hb_somebody_left(const struct cmb_condition *cvp, const struct cmb_process *pp, const void *ctx)
+{
+    cmb_unused(cvp);
+    cmb_unused(pp);
+    const struct hb_world *w = ctx;
+    return w->departed != NULL;
+}
+
+static void *hb_departures_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct hb_world *w = vw;
+    for (;;) {
+        (void)cmb_condition_wait(w->davyjones, hb_somebody_left, w);
+        struct hb_ship *s = w->departed;
+        w->departed = s->next_departed;
+        const double *t_sys = cmb_process_exit_value(&s->core);
+        (void)cmb_datasummary_add(&w->through[s->size], *t_sys);
+        w->trl->sum_wait += *t_sys;
+        w->trl->counter[s->size] += 1u;
+        cmb_process_terminate(&s->core);
+        free(s);
+    }
+}
+
+static void *hb_dots_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    cmb_unused(vw);
+    for (;;) {
+        (void)cmb_process_hold(24.0 * 7 * 52);          /* one (unprinted) dot per simulated year */
+    }
+}
+
+static void hb_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct hb_world *w = subject;
+    cmb_process_stop(w->weather, NULL);
+    cmb_process_stop(w->tide, NULL);
+    cmb_process_stop(w->arrivals, NULL);
+    cmb_process_stop(w->departures, NULL);
+    cmb_process_stop(w->dots, NULL);
+    while (cmi_hashheap_count(w->active) > 0u) {
+        void **item = cmi_hashheap_dequeue(w->active);
+        struct hb_ship *s = item[0];
+        (void)cmb_process_stop(&s->core, NULL);
+        cmb_process_terminate(&s->core);
+        free(s);
+    }
+}
+
+static uint64_t hb_history_summary(struct cmb_resourcepool *rp, double *mean)
+{
+    struct cmb_wtdsummary ws;
+    cmb_wtdsummary_initialize(&ws);
+    const struct cmb_timeseries *hist = cmb_resourcepool_get_history(rp);
+    if (cmb_timeseries_count(hist) > 0u) {
+        (void)cmb_timeseries_summarize(hist, &ws);
+    }
+    *mean = cmb_wtdsummary_mean(&ws);
+    return cmb_wtdsummary_count(&ws);
+}
+
+static void run_harbor_trial(struct ref_trial *t)
+{
+    struct hb_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    cmb_datasummary_initialize(&w->through[0]);
+    cmb_datasummary_initialize(&w->through[1]);
+
+    w->weather = cmb_process_create();
+    cmb_process_initialize(w->weather, "Wind", hb_weather_body, w, 0);
+    cmb_process_start(w->weather);
+    w->tide = cmb_process_create();
+    cmb_process_initialize(w->tide, "Depth", hb_tide_body, w, 0);
+    cmb_process_start(w->tide);
+
+    w->tugs = cmb_resourcepool_create();
+    cmb_resourcepool_initialize(w->tugs, "Tugs", (uint64_t)t->servers);
+    cmb_resourcepool_start_recording(w->tugs);
+    for (int i = 0; i < 2; i++) {
+        w->berths[i] = cmb_resourcepool_create();
+        cmb_resourcepool_initialize(w->berths[i], (i == 0) ? "Small berth" : "Large berth", (i == 0) ? 6u : 3u);
+        cmb_resourcepool_start_recording(w->berths[i]);
+    }
+    w->harbormaster = cmb_condition_create();
+    cmb_condition_initialize(w->harbormaster, "Harbormaster");
+    w->davyjones = cmb_condition_create();
+    cmb_condition_initialize(w->davyjones, "Davy Jones");
+
+    w->arrivals = cmb_process_create();
+    cmb_process_initialize(w->arrivals, "Arrivals", hb_arrivals_body, w, 0);
+    cmb_process_start(w->arrivals);
+    w->departures = cmb_process_create();
+    cmb_process_initialize(w->departures, "Departures", hb_departures_body, w, 0);
+    cmb_process_start(w->departures);
+
+    w->active = cmi_hashheap_create();
+    cmi_hashheap_initialize(w->active, 3u, NULL);
+    (void)cmb_event_schedule(hb_end_event, w, NULL, (double)t->num_objects, 0);
+
+    w->dots = cmb_process_create();
+    cmb_process_initialize(w->dots, "Dot", hb_dots_body, NULL, 0);
+    cmb_process_start(w->dots);
+
+    pump_events(t);
+
+    t->objects = t->counter[0] + t->counter[1];
+    t->max_queue = w->most_alive;
+    const double mean_small = cmb_datasummary_mean(&w->through[0]);
+    const double mean_large = cmb_datasummary_mean(&w->through[1]);
+    memcpy(&t->counter[2], &mean_small, 8);
+    memcpy(&t->counter[3], &mean_large, 8);
+    double tug_mean, berth_mean;
+    t->counter[4] = hb_history_summary(w->tugs, &tug_mean);
+    memcpy(&t->counter[5], &tug_mean, 8);
+    t->counter[6] = hb_history_summary(w->berths[0], &berth_mean);
+    t->counter[6] |= hb_history_summary(w->berths[1], &berth_mean) << 32;
+
+    while (w->departed != NULL) {                       /* left the harbor in the very last instant */
+        struct hb_ship *s = w->departed;
+        w->departed = s->next_departed;
+        cmb_process_terminate(&s->core);
+        free(s);
+    }
+    cmb_process_terminate(w->weather);  cmb_process_destroy(w->weather);
+    cmb_process_terminate(w->tide);     cmb_process_destroy(w->tide);
+    cmb_process_terminate(w->arrivals); cmb_process_destroy(w->arrivals);
+    cmb_process_terminate(w->departures); cmb_process_destroy(w->departures);
+    cmb_process_terminate(w->dots);     cmb_process_destroy(w->dots);
+    cmi_hashheap_terminate(w->active);
+    cmi_hashheap_destroy(w->active);
+    cmb_condition_destroy(w->harbormaster);
+    cmb_condition_destroy(w->davyjones);
+    cmb_resourcepool_destroy(w->tugs);
+    cmb_resourcepool_destroy(w->berths[0]);
+    cmb_resourcepool_destroy(w->berths[1]);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -1232,7 +1520,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 8) {
+    if (t->model == 10) {
+        run_harbor_trial(t);
+    }
+    else if (t->model == 8) {
         run_timers_trial(t);
     }
     else if (t->model == 7) {

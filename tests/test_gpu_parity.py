@@ -498,6 +498,73 @@ def test_timers_waits_observers_pop_order_bit_exact(cb, port):
         assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
 
 
+# ------------------------------------------------------------------ the harbor (model 10, test/test_condition.c)
+
+@pytest.mark.parametrize("tugs,arr,unl,dur", [(10, 2.0, 8.0, 2000), (5, 1.5, 10.0, 777), (10, 1.0, 6.0, 400), (3, 2.0, 8.0, 150),
+                                              (10, 2.0, 8.0, 1), (10, 2.0, 8.0, 24)])
+def test_harbor_matches_oracle(cb, port, tugs, arr, unl, dur):
+    """Dynamic ship processes, cmb_condition_signal with predicates, three resourcepools with partial
+    grabs, pool histories, the end-of-run stop cascade with its stale guard entries: bit-exact."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=arr, srv_mean=unl, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_HARBOR, servers=tugs)
+    want = run_trials(port, "port", 10, tugs, KAT_SEED, 0, n, dur, arr, unl)
+    _compare(res, want, ("harbor", tugs, dur))
+    assert _counts(res.counters) == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
+
+
+def test_harbor_pop_order_bit_exact(cb, port):
+    n, cap, dur = 16, 12000, 1500
+    res = cb.run_trials(n, arr_mean=2.0, srv_mean=8.0, num_objects=dur, master_seed=1010,
+                        model=cb.MODEL_HARBOR, servers=10, trace_cap=cap)
+    keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
+    for i in range(n):
+        r, k, t = trace_trial(port, "port", 10, 10, cb.fmix64(1010, i), dur, 2.0, 8.0, cap)
+        m = min(cap, r.events)
+        assert list(keys[i, :m]) == k, i
+        assert np.array_equal(_u64(times[i, :m]), _u64(np.array(t))), i
+
+
+def _inverse_fmix64(y):
+    """cmb_random_fmix64 is a bijection of seed + nonce: the master seed whose trial 0 gets seed y."""
+    m = (1 << 64) - 1
+    y ^= y >> 33
+    y = (y * pow(0xc4ceb9fe1a85ec53, -1, 1 << 64)) & m
+    y ^= y >> 33
+    y = (y * pow(0xff51afd7ed558ccd, -1, 1 << 64)) & m
+    y ^= y >> 33
+    return y
+
+
+def test_harbor_reproduces_the_reference_golden_file_on_device(cb, golden):
+    """test/reference/condition.txt on the GPU: seed 0x34f05c64d7ad598f, 100 simulated years, 4.58 million
+    events in one lane - ship counts, mean system times, tug and berth history summaries as the reference
+    prints them, and every exported word equal to the committed reference record."""
+    import struct
+    master = _inverse_fmix64(KAT_SEED)
+    assert cb.fmix64(master, 0) == KAT_SEED
+    t = [x for x in golden["trials"] if x["model"] == 10 and x["num_objects"] == 873_600][0]
+    res = cb.run_trials(1, arr_mean=2.0, srv_mean=8.0, num_objects=873_600, master_seed=master,
+                        model=cb.MODEL_HARBOR, servers=10)
+    assert int(res.status[0]) == 0
+    c = _counts(res.counters)[0]
+    f = lambda u: struct.unpack("<d", struct.pack("<Q", u))[0]
+    assert (c[0], c[1]) == (328781, 109454)
+    assert ("%.4g" % f(c[2]), "%.4g" % f(c[3])) == ("10.91", "17.48")
+    assert (c[4], "%.4g" % f(c[5])) == (1736975, "0.8025")
+    assert (c[6] & 0xffffffff, c[6] >> 32) == (645947, 217380)
+    assert c == t["counters"]
+    assert (int(res.events[0]), int(res.objects[0])) == (t["events"], t["objects"])
+    assert float.hex(float(res.t_end[0])) == t["t_end"] and float.hex(float(res.sum_wait[0])) == t["sum_wait"]
+
+
+def test_harbor_ship_table_overflow_is_reported(cb):
+    """More ships alive than the device table holds: flagged in status, never silent."""
+    res = cb.run_trials(8, arr_mean=0.7, srv_mean=8.0, num_objects=1000, master_seed=3, model=cb.MODEL_HARBOR, servers=10)
+    assert int((res.status != 0).sum()) == 8
+
+
 # ------------------------------------------------------------------ hold model (warp per trial, 32-ary heap)
 
 @pytest.mark.parametrize("workers,dur,mean", [(1000, 20, 1.0), (100, 50, 0.5), (7, 100, 1.0), (1, 30, 2.0),

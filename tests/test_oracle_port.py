@@ -112,6 +112,24 @@ def test_full_size_known_answer(port, golden, model):
         assert r.events == 2_099_622 and r.t_end == 1109668.9795469602 and r.sum_wait == 9895522.5628889836
 
 
+def test_harbor_reproduces_the_reference_golden_file(port, golden):
+    """test/reference/condition.txt (the reference's own golden output for its harbor model, seed
+    0x34f05c64d7ad598f, 100 simulated years): N 328781 small / 109454 large ships, mean system times
+    10.91 / 17.48, tug history N 1736975 mean 0.8025, berth histories N 645947 / 217380."""
+    import struct
+    t = [x for x in golden["trials"] if x["model"] == 10 and x["num_objects"] == 873_600][0]
+    r, _, _ = trace_trial(port, "port", 10, 10, KAT_SEED, 873_600, 2.0, 8.0, 0)
+    assert (r.events, r.objects, float.hex(r.t_end), float.hex(r.sum_wait)) == \
+           (t["events"], t["objects"], t["t_end"], t["sum_wait"])
+    assert r.counters() == t["counters"] and (r.max_fel, r.max_queue) == (t["max_fel"], t["max_queue"])
+    c = r.counters()
+    f = lambda u: struct.unpack("<d", struct.pack("<Q", u))[0]
+    assert (c[0], c[1]) == (328781, 109454)
+    assert ("%.4g" % f(c[2]), "%.4g" % f(c[3])) == ("10.91", "17.48")
+    assert (c[4], "%.4g" % f(c[5])) == (1736975, "0.8025")
+    assert (c[6] & 0xffffffff, c[6] >> 32) == (645947, 217380)
+
+
 def test_experiment_seeding_matches_golden(port, golden):
     g = golden["experiment_mm1"]
     res = run_trials(port, "port", 0, 1, g["master_seed"], 0, len(g["trials"]), g["num_objects"], 1 / 0.9, 1.0)
@@ -191,7 +209,8 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (6, 1.0, 1.0, 8), (6, 0.5, 1.0, 2),
                                                    (7, 1.0, 1.0, 500), (7, 0.5, 1.0, 5),
                                                    (8, 1.0, 0.6, 1), (8, 0.4, 1.2, 1),
-                                                   (9, 1 / 0.9, 1.0, 1), (9, 2.0, 1.0, 1)])
+                                                   (9, 1 / 0.9, 1.0, 1), (9, 2.0, 1.0, 1),
+                                                   (10, 2.0, 8.0, 10), (10, 1.2, 8.0, 4), (10, 0.9, 8.0, 3)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
