@@ -29,6 +29,7 @@
 #include "timers_model.cuh"
 #include "harbor_model.cuh"
 #include "hold_model.cuh"
+#include "hold_deep.cuh"
 #include "rng.cuh"
 #include "distributions.cuh"
 #include "summary.cuh"
@@ -64,6 +65,14 @@ bool is_queue_model(int m)
 {
     return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1 || m == CIMBA_B200_MODEL_MM1_RECORDED;
 }
+// spill area of one warp of hold_deep_kernel: the heap nodes below level 1, whole rows of 32
+uint64_t deep_row_entries(int workers)
+{
+    const uint64_t count = (uint64_t)(workers < 1 ? 1 : workers) + 2u;
+    const uint64_t below = count > 33u ? count - 33u : 0u;
+    return ((below + 31u) / 32u) * 32u + 32u;
+}
+
 bool is_general_model(int m)
 {
     return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
@@ -200,6 +209,9 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     }
     if (job->model == CIMBA_B200_MODEL_HARBOR) {
         return job->num_trials * (uint64_t)sizeof(HarborState);
+    }
+    if (job->model == CIMBA_B200_MODEL_HOLD && job->variant != 1) {
+        return job->num_trials * deep_row_entries(job->servers) * (uint64_t)sizeof(uint4);
     }
     if (is_general_model(job->model)) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
@@ -398,8 +410,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "harbor_kernel launch");
     }
     if (job->model == CIMBA_B200_MODEL_HOLD) {
-        if (job->servers < 1 || job->servers > HOLD_CAP - 8)
-            return fail(CIMBA_B200_EINVAL, "workers (servers) must be in 1..1080 for CIMBA_B200_MODEL_HOLD");
+        const bool on_chip = job->variant == 1;         // hold_model.cuh: the whole list in shared memory
+        if (job->servers < 1 || (on_chip && job->servers > HOLD_CAP - 8) ||
+            (uint32_t)job->servers + 2u > DEEP_MAX_ENTRIES)
+            return fail(CIMBA_B200_EINVAL, "workers (servers) must be in 1..33822 for CIMBA_B200_MODEL_HOLD (1..1080 with variant 1)");
         HoldArgs ha{};
         ha.workers = job->servers;
         ha.master_seed = job->master_seed;
@@ -417,6 +431,31 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ha.trace_cap = job->trace_cap;
         ha.trace_key = job->trace_key;
         ha.trace_time = job->trace_time;
+        if (!on_chip) {
+            // hold_deep.cuh: levels >= 2 of the 32-ary heap in HBM/L2, persistent warps
+            if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+                return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+            int dev = 0, sms = 148, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaError_t oe = trace
+                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_deep_kernel<true>, DEEP_BLOCK, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_deep_kernel<false>, DEEP_BLOCK, 0);
+            if (oe != cudaSuccess || per_sm < 1) per_sm = 8;
+            const uint64_t warps_per_block = DEEP_BLOCK / 32;
+            const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
+            const uint64_t wanted = (job->num_trials + warps_per_block - 1) / warps_per_block;
+            const unsigned blocks = (unsigned)(wanted < resident ? wanted : resident);
+            DeepArgs da{};
+            da.h = ha;
+            da.rows = (uint4 *)job->workspace;
+            da.row_entries = deep_row_entries(job->servers);
+            if (trace) hold_deep_kernel<true><<<blocks, DEEP_BLOCK, 0, st>>>(da);
+            else       hold_deep_kernel<false><<<blocks, DEEP_BLOCK, 0, st>>>(da);
+            g_launches++;
+            cudaError_t e = cudaGetLastError();
+            return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "hold_deep_kernel launch");
+        }
         // persistent one-warp CTAs: exactly as many as are resident at once (shared memory
         // bounds it at ~12 per SM), so no CTA waits for another to retire
         int dev = 0, sms = 148, per_sm = 0;

@@ -101,7 +101,7 @@ class TrialBuffers:
     """Reusable device buffers for repeated launches of the same shape."""
 
     def __init__(self, num_trials: int, device: torch.device, trace_cap: int = 0,
-                 model: int = _lib.MODEL_MM1):
+                 model: int = _lib.MODEL_MM1, servers: int = 1, variant: int = 0):
         n = num_trials
         self.n = n
         self.device = device
@@ -117,7 +117,7 @@ class TrialBuffers:
         if trace_cap:
             self.trace_key = torch.zeros((n, trace_cap), dtype=torch.int64, device=device)
             self.trace_time = torch.zeros((n, trace_cap), dtype=torch.float64, device=device)
-        job = _lib.DeviceJob(model=model, num_trials=n)
+        job = _lib.DeviceJob(model=model, num_trials=n, servers=servers, variant=variant)
         ws = int(lib.cimba_b200_workspace_bytes(C.byref(job)))
         self.workspace = torch.empty(max(ws, 8), dtype=torch.uint8, device=device)
         self.workspace_bytes = ws
@@ -147,7 +147,7 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
     n = arr_mean.numel()
     if n == 0:
         raise ValueError("num_trials must be > 0 (reference asserts this, src/cimba.c:157)")
-    b = buffers if buffers is not None else TrialBuffers(n, arr_mean.device, trace_cap, model)
+    b = buffers if buffers is not None else TrialBuffers(n, arr_mean.device, trace_cap, model, servers, variant)
     if b.n != n or b.trace_cap != trace_cap:
         raise ValueError("buffers do not match this launch")
     job = _lib.DeviceJob(

@@ -50,9 +50,10 @@ extern "C" {
                                     * interrupting them, on a cmb_resourcepool of `servers` units; end event at t = num_objects */
 #define CIMBA_B200_MODEL_BUFFER 5  /* test/test_buffer.c + test/test_resource.c: 2 fillers + 2 drainers on a cmb_buffer of capacity
                                     * `servers`, a polite and a pre-empting worker on one cmb_resource, a nuisance; end at t = num_objects */
-#define CIMBA_B200_MODEL_HOLD 7    /* the hold model: `servers` <= 1080 processes in cmb_process_hold(exp(arr_mean)) loops + a 1.0 s
+#define CIMBA_B200_MODEL_HOLD 7    /* the hold model: `servers` <= 33 822 processes in cmb_process_hold(exp(arr_mean)) loops + a 1.0 s
                                     * ticker + an end event at t = num_objects (tutorial/tut_5_1.c's event-list shape); one trial
-                                    * per WARP, 32-ary shared-memory heap (always CIMBA_B200_MAP_WARP) */
+                                    * per WARP, 32-ary heap: root + level 1 in registers, deeper levels in HBM/L2 moved as coalesced
+                                    * 512-byte rows (variant 1: the whole list in shared memory, <= 1080 processes) */
 #define CIMBA_B200_MODEL_PRIOQ 6   /* test/test_priorityqueue.c + test/test_condition.c: 2 producers, a consumer and a shuffler
                                     * (position / reprioritize / cancel by handle) on a cmb_priorityqueue of capacity `servers` <= 15,
                                     * a tide process signalling a cmb_condition two waiters watch, a nuisance; end at t = num_objects */
