@@ -21,6 +21,7 @@
 #include "engine.cuh"
 #include "queue_model.cuh"
 #include "mm1_fast.cuh"
+#include "gg1_fast.cuh"
 #include "pool_model.cuh"
 #include "guarded_model.cuh"
 #include "preempt_model.cuh"
@@ -262,7 +263,14 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const uint64_t blocks = (threads + QUEUE_BLOCK - 1) / QUEUE_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
         dim3 grid((unsigned)blocks);
-        if (job->model == CIMBA_B200_MODEL_GG1) return launch_queue<1>(qa, trace, grid, st);
+        if (job->model == CIMBA_B200_MODEL_GG1) {
+            if (job->variant == 1) return launch_queue<1>(qa, trace, grid, st);
+            if (trace) gg1_kernel<true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+            else       gg1_kernel<false><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
+            g_launches++;
+            cudaError_t e = cudaGetLastError();
+            return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "gg1_kernel launch");
+        }
         if (job->model == CIMBA_B200_MODEL_MM1_RECORDED) {
             if (job->counters == nullptr)
                 return fail(CIMBA_B200_EINVAL, "CIMBA_B200_MODEL_MM1_RECORDED writes its cmb_wtdsummary to counters[]");

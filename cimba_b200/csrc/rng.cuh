@@ -69,6 +69,23 @@ struct Sfc64 {
         return out;
     }
 
+    // The inverse of next(): puts the last output back.  sfc64's state transition is a bijection
+    // (a' = b ^ (b >> 11), b' = 9c, c' = rotl(c, 24) + out, d' = d + 1), so a kernel that runs a few
+    // raw draws ahead of the simulation can hand the stream back to the reference-order slow path.
+    __device__ __forceinline__ void rewind()
+    {
+        const uint64_t pc = b * 0x8e38e38e38e38e39ULL;  // 9^-1 mod 2^64
+        uint64_t pb = a;                                // undo b ^ (b >> 11)
+        pb ^= pb >> 11;
+        pb ^= pb >> 22;
+        pb ^= pb >> 44;
+        const uint64_t out = c - ((pc << 24) | (pc >> 40));
+        d -= 1u;
+        a = out - pb - d;
+        b = pb;
+        c = pc;
+    }
+
     // cmb_random_initialize, src/cmb_random.c:112-124 (splitmix64 at :99-106)
     __device__ __forceinline__ void seed(uint64_t s)
     {

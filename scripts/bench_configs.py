@@ -30,6 +30,9 @@ CONFIGS = [
     ("MMc c=8 rho0.8 262144 trials", cb.MODEL_MMC, 262144, 1 / 6.4, 1.0, 8),
     ("GG1 erlang2/normal rho0.8 65536 trials", cb.MODEL_GG1, 65536, 1.25, 1.0, 1),
     ("GG1 erlang2/normal rho0.8 1048576 trials (config 4)", cb.MODEL_GG1, 1048576, 1.25, 1.0, 1),
+    ("HOLD 1000 processes 4096 trials (config 5's event-list shape; objects = duration/1000)", cb.MODEL_HOLD, 4096, 1.0, 1.0, 1000),
+    ("HARBOR test_condition.c 4096 trials (config 5's cmb_condition shape; objects = hours/10)", cb.MODEL_HARBOR, 4096, 2.0, 8.0, 10),
+    ("HARBOR test_condition.c 65536 trials", cb.MODEL_HARBOR, 65536, 2.0, 8.0, 10),
 ]
 dev = torch.device("cuda", 0)
 for name, model, n, arr, srv, servers in CONFIGS:
@@ -37,8 +40,9 @@ for name, model, n, arr, srv, servers in CONFIGS:
         continue
     a = torch.full((n,), arr, dtype=torch.float64, device=dev)
     s = torch.full((n,), srv, dtype=torch.float64, device=dev)
-    bufs = TrialBuffers(n, dev, 0, model)
-    run = lambda: cb.launch_trials(a, s, num_objects=args.objects, master_seed=0x34F05C64D7AD598F,
+    bufs = TrialBuffers(n, dev, 0, model, servers)
+    size = args.objects // 1000 if model == cb.MODEL_HOLD else (args.objects // 10 if model == cb.MODEL_HARBOR else args.objects)
+    run = lambda: cb.launch_trials(a, s, num_objects=size, master_seed=0x34F05C64D7AD598F,
                                    model=model, servers=servers, buffers=bufs)
     run()
     torch.cuda.synchronize()
@@ -49,7 +53,7 @@ for name, model, n, arr, srv, servers in CONFIGS:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     ev = res.total_events()
-    print(json.dumps({"config": name, "trials": n, "objects": args.objects, "events": ev, "ms": ms,
+    print(json.dumps({"config": name, "trials": n, "objects": size, "events": ev, "ms": ms,
                       "events_per_s": ev / ms * 1e3, "failed": int((res.status != 0).sum()),
-                      "mean_time_in_system": float((res.sum_wait / res.objects.double()).mean())}), flush=True)
+                      "mean_time_in_system": float((res.sum_wait / res.objects.double().clamp(min=1)).mean())}), flush=True)
     del bufs, a, s

@@ -110,6 +110,19 @@ def test_trials_match_oracle(cb, port, model, arr, srv, mapping):
     _compare(res, want, (model, mapping))
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("arr,srv,nobj,n", [(1.25, 1.0, 20000, 256), (1.05, 1.0, 3000, 700), (3.0, 0.5, 4000, 100)])
+def test_gg1_both_kernels_match_oracle(cb, port, arr, srv, nobj, n, variant):
+    """G/G/1 (Erlang-2 arrivals, truncated-normal service): the predicated kernel with two raw draws of
+    look-ahead and the rewind-to-reference slow path (variant 0) and the readable formulation (variant 1).
+    5e6 normals per case: ~150 of them are negative and take the redraw loop."""
+    res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=KAT_SEED, model=cb.MODEL_GG1,
+                        variant=variant)
+    want = run_trials(port, "port", 1, 1, KAT_SEED, 0, n, nobj, arr, srv)
+    _compare(res, want, ("gg1", variant))
+    assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
+
+
 @pytest.mark.parametrize("model", [0, 1])
 def test_pop_order_bit_exact(cb, port, model):
     """FEL pop order: (key, clock) of the first 4096 pops of 33 trials."""
