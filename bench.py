@@ -173,11 +173,27 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "events_convention_4_per_object": 4.0 * trials * args.objects * args.steps / t_total,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one), so file descriptor 1 is pointed at stderr for the whole run and the
+    # line goes to the saved descriptor at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -217,8 +233,7 @@ def main():
     barrier()
 
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                                     # every rank watches its own GPU
     launches0 = cb.lib.cimba_b200_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -234,7 +249,7 @@ def main():
     launches = cb.lib.cimba_b200_launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = [a.elapsed_time(b) for a, b in per_launch]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
 
     events_rank = int(res.events.sum().item())
     bad = int((res.status != 0).sum().item())
@@ -247,6 +262,14 @@ def main():
         ms_total, events_all, bad = float(tmax[0]), int(tsum[1]), int(tsum[2])
     else:
         events_all = events_rank
+    per_rank = None
+    if world > 1:
+        # the slowest rank sets the number; record every rank's own time and clocks beside it
+        mine = {"rank": rank, "ms_per_step": float(t[0]) / args.steps, "sm_mhz": clocks.get("sm_mhz"),
+                "reasons": clocks.get("reasons")}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     ms_per_step = ms_total / args.steps
     value = events_all / (ms_per_step * 1e-3)
 
@@ -333,14 +356,14 @@ def main():
                    "mapping": "lane-per-trial" if args.mapping == 1 else "warp-per-trial",
                    "seeding": "cmb_random_fmix64(0x34f05c64d7ad598f, global trial index)",
                    "l2": "no input re-use between steps: 1 MB of inputs, all state regenerated on chip"},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "per_rank": per_rank, "roofline": roofline,
         "cpu_baseline": cpu,
         "events_per_step": events_all, "failed_trials": bad,
         "events_convention_4_per_object": 4.0 * T * world * NOBJ / (ms_per_step * 1e-3),
         "summary": {"n": merged.count(), "mean_time_in_system": merged.mean(),
                     "ci95_half_width": merged.half_width_95(), "expected": 1.0 / (SERVICE_RATE - ARRIVAL_RATE)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
