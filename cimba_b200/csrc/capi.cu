@@ -31,6 +31,7 @@
 #include "harbor_model.cuh"
 #include "hold_model.cuh"
 #include "hold_deep.cuh"
+#include "hold_group.cuh"
 #include "rng.cuh"
 #include "distributions.cuh"
 #include "summary.cuh"
@@ -66,6 +67,10 @@ bool is_queue_model(int m)
 {
     return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1 || m == CIMBA_B200_MODEL_MM1_RECORDED;
 }
+#ifndef HOLD_DEFAULT_LANES
+#define HOLD_DEFAULT_LANES 32      // lanes per trial of the default hold kernel (profiles/r01_hold.md)
+#endif
+
 // spill area of one warp of hold_deep_kernel: the heap nodes below level 1, whole rows of 32
 uint64_t deep_row_entries(int workers)
 {
@@ -443,25 +448,28 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             // hold_deep.cuh: levels >= 2 of the 32-ary heap in HBM/L2, persistent warps
             if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
                 return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+            // variant 0 = the default below; 2 = one warp per trial (hold_deep.cuh); 3 / 4 = 16 / 8 lanes per trial
+            const int lanes = job->variant == 2 ? 32 : (job->variant == 4 ? 8 : (job->variant == 3 ? 16 : HOLD_DEFAULT_LANES));
+            const void *fn = lanes == 32 ? (trace ? (const void *)hold_deep_kernel<true> : (const void *)hold_deep_kernel<false>)
+                           : lanes == 16 ? (trace ? (const void *)hold_group_kernel<16, true> : (const void *)hold_group_kernel<16, false>)
+                                         : (trace ? (const void *)hold_group_kernel<8, true> : (const void *)hold_group_kernel<8, false>);
             int dev = 0, sms = 148, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaError_t oe = trace
-                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_deep_kernel<true>, DEEP_BLOCK, 0)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_deep_kernel<false>, DEEP_BLOCK, 0);
+            cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, DEEP_BLOCK, 0);
             if (oe != cudaSuccess || per_sm < 1) per_sm = 8;
-            const uint64_t warps_per_block = DEEP_BLOCK / 32;
+            const uint64_t trials_per_block = (uint64_t)(DEEP_BLOCK / 32) * (uint64_t)(32 / lanes);
             const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
-            const uint64_t wanted = (job->num_trials + warps_per_block - 1) / warps_per_block;
+            const uint64_t wanted = (job->num_trials + trials_per_block - 1) / trials_per_block;
             const unsigned blocks = (unsigned)(wanted < resident ? wanted : resident);
             DeepArgs da{};
             da.h = ha;
             da.rows = (uint4 *)job->workspace;
             da.row_entries = deep_row_entries(job->servers);
-            if (trace) hold_deep_kernel<true><<<blocks, DEEP_BLOCK, 0, st>>>(da);
-            else       hold_deep_kernel<false><<<blocks, DEEP_BLOCK, 0, st>>>(da);
+            void *kargs[] = { (void *)&da };
+            cudaError_t le = cudaLaunchKernel(fn, dim3(blocks), dim3(DEEP_BLOCK), kargs, 0, st);
             g_launches++;
-            cudaError_t e = cudaGetLastError();
+            cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
             return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "hold_deep_kernel launch");
         }
         // persistent one-warp CTAs: exactly as many as are resident at once (shared memory

@@ -580,14 +580,15 @@ def test_harbor_ship_table_overflow_is_reported(cb):
 
 # ------------------------------------------------------------------ hold model (warp per trial, 32-ary heap)
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("workers,dur,mean", [(1000, 20, 1.0), (100, 50, 0.5), (7, 100, 1.0), (1, 30, 2.0),
                                               (33, 40, 1.0), (1080, 6, 1.0)])
 def test_hold_model_matches_oracle(cb, port, workers, dur, mean, variant):
     """A future-event list 3..1082 deep, one trial per warp: counts, clock, the wake-time sum
-    (order-sensitive in floating point) and the deepest list seen, bit-exact.  variant 0 keeps
-    the heap's deep levels in HBM/L2 (hold_deep.cuh), variant 1 the whole list in shared memory."""
-    n = 40
+    (order-sensitive in floating point) and the deepest list seen, bit-exact.  variant 1 keeps the
+    whole list in shared memory; 2 / 3 / 4 give a trial 32 / 16 / 8 lanes and keep the heap's deep
+    levels in HBM/L2 (hold_deep.cuh, hold_group.cuh); 0 is the default among those."""
+    n = 41
     res = cb.run_trials(n, arr_mean=mean, srv_mean=1.0, num_objects=dur, master_seed=KAT_SEED,
                         model=cb.MODEL_HOLD, servers=workers, variant=variant)
     want = run_trials(port, "port", 7, workers, KAT_SEED, 0, n, dur, mean, 1.0)
@@ -596,14 +597,16 @@ def test_hold_model_matches_oracle(cb, port, workers, dur, mean, variant):
     assert res.max_queue.cpu().tolist() == [w.max_fel for w in want]
 
 
-@pytest.mark.parametrize("workers,dur", [(30, 30), (31, 30), (32, 30), (1054, 5), (1055, 5), (1056, 5), (5000, 3),
-                                         (33822, 1)])
-def test_hold_model_deep_levels_in_hbm(cb, port, workers, dur):
+@pytest.mark.parametrize("variant", [2, 3, 4])
+@pytest.mark.parametrize("workers,dur", [(5, 30), (6, 30), (7, 30), (14, 30), (15, 30), (30, 30), (31, 30), (32, 30), (70, 20),
+                                         (71, 20), (270, 10), (271, 10), (583, 8), (1054, 5), (1055, 5), (1056, 5),
+                                         (5000, 3), (33822, 1)])
+def test_hold_model_deep_levels_in_hbm(cb, port, workers, dur, variant):
     """Heap row boundaries (33, 34, 1057, 1058 entries) and lists far beyond what fits on chip:
     up to 33 824 pending events per trial, levels 2 and 3 of the 32-ary heap in HBM."""
-    n = 12
+    n = 13
     res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=77,
-                        model=cb.MODEL_HOLD, servers=workers)
+                        model=cb.MODEL_HOLD, servers=workers, variant=variant)
     want = run_trials(port, "port", 7, workers, 77, 0, n, dur, 1.0, 1.0)
     _compare(res, want, ("hold-deep", workers))
     assert _counts(res.counters) == [w.counters() for w in want]
@@ -612,7 +615,7 @@ def test_hold_model_deep_levels_in_hbm(cb, port, workers, dur):
 
 def test_hold_model_pop_order_bit_exact(cb, port):
     n, cap = 6, 20000
-    for variant, workers in ((0, 1000), (1, 1000), (0, 3000)):
+    for variant, workers in ((2, 1000), (1, 1000), (2, 3000), (3, 1000), (4, 1000), (4, 3000)):
         res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=15 if workers == 1000 else 5, master_seed=12,
                             model=cb.MODEL_HOLD, servers=workers, trace_cap=cap, variant=variant)
         keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
