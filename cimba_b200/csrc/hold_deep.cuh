@@ -28,6 +28,7 @@
 
 #include "engine.cuh"
 #include "hold_model.cuh"
+#include "mm1_fast.cuh"
 #include "rng.cuh"
 
 namespace cimba_b200 {
@@ -72,11 +73,27 @@ __device__ __forceinline__ bool goes_before(unsigned long long at, uint32_t ak, 
     return at < bt || (at == bt && ak < bk);
 }
 
+// cmb_random_std_exponential with the layer table at a 32-bit shared-window address
+__device__ __forceinline__ double std_exponential_shared(Sfc64 &rng, uint32_t tab)
+{
+    const uint64_t u = rng.next();
+    return Sfc64::exp_is_hot(u)
+        ? __dmul_rn(lds_f64(tab + ((uint32_t)u & 0xffu) * 8u), __ull2double_rn(u))
+        : rng.exp_cold(u);
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(DEEP_BLOCK)
 hold_deep_kernel(const DeepArgs d)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double exp_x[256];                       // ziggurat layer widths (hot table), 32-bit addressed
+    for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x) {
+        exp_x[i] = zig::zig_exp_x[i];
+    }
+    __syncthreads();
+    uint32_t tab = (uint32_t)__cvta_generic_to_shared(&exp_x[0]);
+    asm volatile("" : "+r"(tab));
     const HoldArgs &a = d.h;
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t warps = (uint64_t)gridDim.x * (DEEP_BLOCK / 32);
@@ -90,8 +107,9 @@ hold_deep_kernel(const DeepArgs d)
         rng.seed(fmix64(a.master_seed, a.first_trial + trial));
         const double mean = a.mean[trial];
         double now = 0.0, sum_wait = 0.0;
-        uint64_t pops = 0u, wakes = 0u, ticks = 0u;
-        double e_next = rng.std_exponential_global();   // one variate of look-ahead, as hold_model.cuh
+        uint32_t pops = 0u, wakes = 0u, ticks = 0u;
+        // one variate of look-ahead, as hold_model.cuh; the hot path reads the shared-memory table
+        double e_next = std_exponential_shared(rng, tab);
 
         // cmb_process_start x (workers + 1): START events at t = 0 with keys 1, 2, ... and the end
         // event (key workers + 2) at t = duration.  In index order that is already a heap:
@@ -204,7 +222,7 @@ hold_deep_kernel(const DeepArgs d)
                 }
             }
             if (draws) {
-                e_next = rng.std_exponential_global();  // refill after use, overlapping the next pop
+                e_next = std_exponential_shared(rng, tab);      // refill after use, overlapping the next pop
             }
         }
 
