@@ -42,10 +42,12 @@ class Experiment(C.Structure):
     """struct cimba_b200_experiment"""
     _fields_ = [
         ("model", C.c_int32), ("servers", C.c_int32), ("mapping", C.c_int32), ("device", C.c_int32),
+        ("variant", C.c_int32), ("reserved", C.c_int32),
         ("master_seed", C.c_uint64), ("first_trial", C.c_uint64), ("num_objects", C.c_uint64),
         ("off_arr_mean", C.c_size_t), ("off_srv_mean", C.c_size_t),
         ("off_obj_cnt", C.c_size_t), ("off_sum_wait", C.c_size_t), ("off_avg_wait", C.c_size_t),
         ("off_events", C.c_size_t), ("off_t_end", C.c_size_t), ("off_status", C.c_size_t),
+        ("off_max_queue", C.c_size_t), ("off_counters", C.c_size_t),
     ]
 
 

@@ -666,9 +666,13 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
     if (devno < 0 || devno >= MAX_CACHED_DEVICES) return fail(CIMBA_B200_EINVAL, "device index out of range");
     DeviceCache &cache = g_cache[devno];
     std::lock_guard<std::mutex> hold(cache.mu);
+    // counters (8 words per trial) travel only when the caller asks for them; the device side always has
+    // them because some models write nothing else of interest
+    const bool want_counters = d->off_counters != CIMBA_B200_NO_FIELD;
     const size_t out_row = 2 * sizeof(uint64_t) + 2 * sizeof(double) + sizeof(uint32_t) + sizeof(uint32_t);
+    const size_t cnt_row = 8 * sizeof(uint64_t);
     {
-        const int rc0 = cache.reserve_host(2 * n * sizeof(double), n * out_row);
+        const int rc0 = cache.reserve_host(2 * n * sizeof(double), n * (out_row + (want_counters ? cnt_row : 0)));
         if (rc0 != CIMBA_B200_OK) return rc0;
     }
     double *h_in = (double *)cache.h_in;
@@ -684,6 +688,7 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
     job.model = d->model;
     job.servers = d->servers;
     job.mapping = d->mapping;
+    job.variant = d->variant;
     job.master_seed = d->master_seed;
     job.first_trial = d->first_trial;
     job.num_trials = n;
@@ -693,7 +698,8 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
     const uint64_t ws = cimba_b200_workspace_bytes(&job);
     const size_t in_bytes = 2 * n * sizeof(double);
     const size_t out_bytes = n * out_row;
-    int rc = cache.reserve_device(in_bytes + out_bytes + ws + 256);
+    const size_t cnt_bytes = n * cnt_row;
+    int rc = cache.reserve_device(in_bytes + out_bytes + cnt_bytes + ws + 256);
     if (rc != CIMBA_B200_OK) return rc;
     dev = (unsigned char *)cache.dev;
     cudaStream_t st = cache.st;
@@ -710,14 +716,15 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
         job.sum_wait = job.t_end + n;
         job.status = (uint32_t *)(job.sum_wait + n);
         job.max_queue = job.status + n;
-        job.workspace = dev + ((in_bytes + out_bytes + 255) / 256) * 256;
+        job.counters = (uint64_t *)(d_out + out_bytes);
+        job.workspace = dev + ((in_bytes + out_bytes + cnt_bytes + 255) / 256) * 256;
         job.workspace_bytes = ws;
 
         e = cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D"); goto done; }
         rc = cimba_b200_launch(&job, st);
         if (rc != CIMBA_B200_OK) goto done;
-        e = cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(h_out, d_out, out_bytes + (want_counters ? cnt_bytes : 0), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "D2H"); goto done; }
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamSynchronize"); goto done; }
@@ -728,6 +735,8 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
         const double *te = (const double *)(ob + n);
         const double *sw = te + n;
         const uint32_t *stt = (const uint32_t *)(sw + n);
+        const uint32_t *mq = stt + n;
+        const uint64_t *cnt = (const uint64_t *)(h_out + out_bytes);
         bool any_bad = false;
         for (uint64_t i = 0; i < n; i++) {
             char *row = base + i * stride;
@@ -740,6 +749,8 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
             if (d->off_events != CIMBA_B200_NO_FIELD) memcpy(row + d->off_events, &ev[i], 8);
             if (d->off_t_end != CIMBA_B200_NO_FIELD) memcpy(row + d->off_t_end, &te[i], 8);
             if (d->off_status != CIMBA_B200_NO_FIELD) memcpy(row + d->off_status, &stt[i], 4);
+            if (d->off_max_queue != CIMBA_B200_NO_FIELD) memcpy(row + d->off_max_queue, &mq[i], 4);
+            if (want_counters) memcpy(row + d->off_counters, &cnt[i * 8u], cnt_row);
             any_bad |= (stt[i] != 0u);
         }
         if (any_bad) rc = fail(CIMBA_B200_ETRIAL, "at least one trial reported a capacity violation");

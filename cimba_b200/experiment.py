@@ -35,14 +35,15 @@ def fmix64(seed: int, nonce: int) -> int:
 
 def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODEL_MM1,
                          num_objects: int, master_seed: int, first_trial: int = 0,
-                         servers: int = 1, mapping: int = 0, device: int = -1,
+                         servers: int = 1, mapping: int = 0, device: int = -1, variant: int = 0,
                          all_gpus: bool = False, max_gpus: int = 0) -> None:
     """Run every trial of a host-resident experiment array on the GPU, in place.
 
     ``experiment_array`` is a 1-D numpy structured array (any dtype that has
     ``arr_mean`` and ``srv_mean`` double fields; result fields named ``obj_cnt``,
-    ``sum_wait``, ``avg_wait``, ``events``, ``t_end``, ``status`` are filled when
-    present).  Host->device and device->host copies happen inside the call.
+    ``sum_wait``, ``avg_wait``, ``events``, ``t_end``, ``status``, ``max_queue`` and
+    ``counters`` (8 x uint64) are filled when present).  Host->device and device->host
+    copies happen inside the call.
     Raises CimbaError(ETRIAL) if any trial overflowed a device structure.
     With ``all_gpus`` the array is sharded over every visible GPU, one host thread
     each (the counterpart of the reference's one pthread per core).
@@ -63,15 +64,22 @@ def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODE
             raise TypeError(f"field {name} must have dtype {kind}")
         return f[name][1]
 
+    off_counters = _lib.NO_FIELD
+    if "counters" in f:
+        if f["counters"][0] != np.dtype(("<u8", (8,))):
+            raise TypeError("field counters must be 8 x uint64")
+        off_counters = f["counters"][1]
+
     if "arr_mean" not in f or "srv_mean" not in f:
         raise TypeError("trial struct needs arr_mean and srv_mean double fields")
     desc = _lib.Experiment(
-        model=model, servers=servers, mapping=mapping, device=device,
+        model=model, servers=servers, mapping=mapping, device=device, variant=variant, reserved=0,
         master_seed=master_seed & (2**64 - 1), first_trial=first_trial, num_objects=num_objects,
         off_arr_mean=off("arr_mean", "<f8"), off_srv_mean=off("srv_mean", "<f8"),
         off_obj_cnt=off("obj_cnt", "<u8"), off_sum_wait=off("sum_wait", "<f8"),
         off_avg_wait=off("avg_wait", "<f8"), off_events=off("events", "<u8"),
-        off_t_end=off("t_end", "<f8"), off_status=off("status", "<u4"))
+        off_t_end=off("t_end", "<f8"), off_status=off("status", "<u4"),
+        off_max_queue=off("max_queue", "<u4"), off_counters=off_counters)
     if all_gpus:
         check(lib.cimba_b200_run_experiment_all_gpus(arr.ctypes.data_as(C.c_void_p), len(arr),
                                                      arr.dtype.itemsize, C.byref(desc), max_gpus))

@@ -171,6 +171,8 @@ typedef struct cimba_b200_experiment {
     int32_t  servers;
     int32_t  mapping;           /* 0 = default */
     int32_t  device;            /* CUDA device ordinal, -1 = current */
+    int32_t  variant;           /* kernel variant, as cimba_b200_device_job.variant (0 = default) */
+    int32_t  reserved;          /* 0 */
     uint64_t master_seed;
     uint64_t first_trial;
     uint64_t num_objects;
@@ -183,6 +185,8 @@ typedef struct cimba_b200_experiment {
     size_t off_events;          /* uint64, out (or NO_FIELD) */
     size_t off_t_end;           /* double, out (or NO_FIELD) */
     size_t off_status;          /* uint32, out (or NO_FIELD) */
+    size_t off_max_queue;       /* uint32, out (or NO_FIELD): longest queue / deepest list / most ships alive */
+    size_t off_counters;        /* uint64[8], out (or NO_FIELD): the model's counters (see CIMBA_B200_MODEL_*) */
 } cimba_b200_experiment;
 
 /* Blocks until all trials are done; results written into the caller's array.

@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header(cb):
     assert C.sizeof(_lib.DataSummaryStruct) == 64
     assert _lib.DataSummaryStruct.count.offset == 8 and _lib.DataSummaryStruct.m1.offset == 32
     assert C.sizeof(_lib.DeviceJob) == 4 * 4 + 4 * 8 + 9 * 8 + 2 * 8 + 3 * 8
-    assert C.sizeof(_lib.Experiment) == 4 * 4 + 3 * 8 + 8 * C.sizeof(C.c_size_t)
+    assert C.sizeof(_lib.Experiment) == 6 * 4 + 3 * 8 + 10 * C.sizeof(C.c_size_t)
     # the reference's struct trial (benchmark/MM1_multi.c:39-45) is a prefix of TRIAL_DTYPE
     f = cb.TRIAL_DTYPE.fields
     assert [f[k][1] for k in ("arr_mean", "srv_mean", "obj_cnt", "sum_wait", "avg_wait")] == [0, 8, 16, 24, 32]

@@ -650,3 +650,25 @@ def test_all_gpus_executive_is_count_independent(cb, port):
         assert np.array_equal(one[f], many[f]), f
     want = run_trials(port, "port", 0, 1, KAT_SEED, 0, n, 1500, 1 / 0.9, 1.0)
     assert many["sum_wait"].tolist() == [w.sum_wait for w in want]
+
+
+def test_host_buffer_api_returns_counters_for_every_model(cb, port):
+    """cimba_b200_run_experiment with a trial struct that has max_queue and counters fields: the harbor,
+    the recorded M/M/1 and the timers model through the host-buffer path, results in place."""
+    dt = np.dtype([("arr_mean", "<f8"), ("srv_mean", "<f8"), ("obj_cnt", "<u8"), ("sum_wait", "<f8"),
+                   ("events", "<u8"), ("t_end", "<f8"), ("status", "<u4"), ("max_queue", "<u4"),
+                   ("counters", "<u8", (8,))])
+    for model, pm, servers, arr_mean, srv_mean, size in ((cb.MODEL_HARBOR, 10, 10, 2.0, 8.0, 500),
+                                                         (cb.MODEL_MM1_RECORDED, 9, 1, 1 / 0.9, 1.0, 3000),
+                                                         (cb.MODEL_TIMERS, 8, 1, 1.0, 0.6, 300)):
+        n = 70
+        exp = np.zeros(n, dtype=dt)
+        exp["arr_mean"], exp["srv_mean"] = arr_mean, srv_mean
+        cb.cimba_run_experiment(exp, model=model, num_objects=size, master_seed=KAT_SEED, servers=servers)
+        want = run_trials(port, "port", pm, servers, KAT_SEED, 0, n, size, arr_mean, srv_mean)
+        assert exp["events"].tolist() == [w.events for w in want], model
+        assert exp["sum_wait"].tolist() == [w.sum_wait for w in want], model
+        assert exp["counters"].tolist() == [w.counters() for w in want], model
+        assert int(exp["status"].sum()) == 0
+        if model == cb.MODEL_HARBOR:
+            assert exp["max_queue"].tolist() == [w.max_queue for w in want]
