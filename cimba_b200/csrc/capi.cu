@@ -410,10 +410,30 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ha.status = job->status;
         ha.max_queue = job->max_queue;
         ha.counters = job->counters;
-        ha.state = (HarborState *)job->workspace;
+        ha.state = job->workspace;
         ha.trace_cap = job->trace_cap;
         ha.trace_key = job->trace_key;
         ha.trace_time = job->trace_time;
+        if (job->variant == 1) {
+            // warp per trial, state in shared memory (smaller capacities; overflow -> status)
+            const size_t smem = (HARBOR_BLOCK_ON_CHIP / 32) * sizeof(HarborStateOnChip);
+            const void *fn = trace ? (const void *)harbor_on_chip_kernel<true> : (const void *)harbor_on_chip_kernel<false>;
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int dev = 0, sms = 148, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HARBOR_BLOCK_ON_CHIP, smem);
+            if (oe != cudaSuccess || per_sm < 1) per_sm = 4;
+            const uint64_t per_block = HARBOR_BLOCK_ON_CHIP / 32;
+            const uint64_t resident = (uint64_t)sms * (uint64_t)per_sm;
+            const uint64_t wanted = (job->num_trials + per_block - 1) / per_block;
+            const unsigned nb = (unsigned)(wanted < resident ? wanted : resident);
+            void *kargs[] = { (void *)&ha };
+            cudaError_t le = cudaLaunchKernel(fn, dim3(nb), dim3(HARBOR_BLOCK_ON_CHIP), kargs, smem, st);
+            g_launches++;
+            cudaError_t e2 = le != cudaSuccess ? le : cudaGetLastError();
+            return e2 == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e2, "harbor_on_chip_kernel launch");
+        }
         const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
         if (trace) harbor_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ha);

@@ -42,12 +42,9 @@
 
 namespace cimba_b200 {
 
-constexpr int HARBOR_FEL_CAP = 127;
-constexpr int HARBOR_GUARD_CAP = 127;
-constexpr int HARBOR_SHIPS = 120;
 constexpr uint32_t HARBOR_FIXED = 5u;                   // weather, tide, arrivals, departures, dots
-constexpr uint32_t HARBOR_PROCS = HARBOR_FIXED + (uint32_t)HARBOR_SHIPS;
 constexpr uint16_t HARBOR_NONE = 0xffffu;
+constexpr int HARBOR_BLOCK_ON_CHIP = 128;               // 4 warps = 4 trials per CTA when the state is in shared memory
 
 struct HarborProc {
     uint8_t  pc, status, n_awaits, active;
@@ -64,18 +61,26 @@ struct HarborPool {
     TimeWeighted hist;
 };
 
-struct HarborState {
-    BinHeap<HARBOR_FEL_CAP, EventOrder>   fel;
-    BinHeap<HARBOR_GUARD_CAP, GuardOrder> harbormaster;
-    BinHeap<HARBOR_GUARD_CAP, GuardOrder> tug_guard;
+// Capacities are template parameters: the HBM-resident state is generous (lane per trial), the
+// shared-memory-resident one (warp per trial) is sized for the tested regimes; both report an
+// overflow in the trial's status word.
+template <int FEL_CAP, int GUARD_CAP, int SHIPS>
+struct HarborStateT {
+    static constexpr int GUARD = GUARD_CAP;
+    static constexpr uint32_t PROCS = HARBOR_FIXED + (uint32_t)SHIPS;
+    BinHeap<FEL_CAP, EventOrder>   fel;
+    BinHeap<GUARD_CAP, GuardOrder> harbormaster;
+    BinHeap<GUARD_CAP, GuardOrder> tug_guard;
     BinHeap<3, GuardOrder>                davyjones;
     BinHeap<3, GuardOrder>                berth_guard[2];      // nobody ever waits here: a ship only asks when one is free
-    HarborProc proc[HARBOR_PROCS];
+    HarborProc proc[PROCS];
     HarborPool tugs, berth[2];
     double   wind_magnitude, wind_direction, water_depth;
     uint32_t guard_seq, status, next_id, alive, most_alive;
     uint16_t departed;
 };
+using HarborState = HarborStateT<127, 127, 120>;        // HBM-resident, one trial per lane (~17 KB)
+using HarborStateOnChip = HarborStateT<47, 47, 43>;     // shared-memory-resident, one trial per warp (~5.6 KB)
 
 struct HarborArgs {
     int32_t  tugs;
@@ -85,14 +90,15 @@ struct HarborArgs {
     double   *t_end, *sum_wait;
     uint32_t *status, *max_queue;
     uint64_t *counters;
-    HarborState *state;
+    void     *state;            // [num_trials] HarborState (lane per trial); unused by the on-chip kernel
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
 };
 
+template <class State>
 struct HarborSim {
-    HarborState *st;
+    State *st;
     Sfc64 rng;
     const ZigHot *hot;
     double now, arr_mean, unload_small, sum_wait;
@@ -211,7 +217,7 @@ struct HarborSim {
     __device__ uint32_t harbormaster_signal()
     {
         auto &cv = st->harbormaster;
-        uint32_t hit[HARBOR_GUARD_CAP];
+        uint32_t hit[State::GUARD];
         uint32_t cnt = 0u;
         for (uint32_t k = 1u; k <= cv.count; k++) {
             const uint32_t pid = cv.slot[k].subj;
@@ -292,7 +298,8 @@ struct HarborSim {
     }
 };
 
-__device__ void HarborSim::body(uint32_t pid)
+template <class State>
+__device__ void HarborSim<State>::body(uint32_t pid)
 {
     HarborProc &p = st->proc[pid];
     const uint32_t kind = pid < HARBOR_FIXED ? pid : HARBOR_FIXED;
@@ -340,12 +347,12 @@ __device__ void HarborSim::body(uint32_t pid)
     case 21:
             {
                 uint32_t slot = HARBOR_FIXED;
-                while (slot < HARBOR_PROCS && st->proc[slot].in_use) {
+                while (slot < State::PROCS && st->proc[slot].in_use) {
                     slot++;
                 }
                 const uint32_t id = ++st->next_id;
                 const uint32_t size = rng.bernoulli(0.25);
-                if (slot == HARBOR_PROCS) {
+                if (slot == State::PROCS) {
                     st->status |= TRIAL_ERR_PROC_OVERFLOW;      // the ship is lost: the trial is void from here on
                 }
                 else {
@@ -445,22 +452,14 @@ __device__ void HarborSim::body(uint32_t pid)
     }
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(GUARDED_BLOCK)
-harbor_kernel(const HarborArgs a)
+// one whole trial, start to finish, on the calling thread; `st` is in HBM (lane per trial) or in
+// shared memory (warp per trial, run by the warp's first lane)
+template <bool TRACE, class State>
+__device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, const ZigHot *hot)
 {
-    __shared__ ZigHot hot;
-    stage_zig_hot(hot, true);
-    __syncthreads();
-
-    const uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (trial >= a.num_trials) {
-        return;
-    }
-    HarborState *st = &a.state[trial];
-    HarborSim s;
+    HarborSim<State> s;
     s.st = st;
-    s.hot = &hot;
+    s.hot = hot;
     s.now = 0.0;
     s.sum_wait = 0.0;
     s.reactivated = 0u;
@@ -486,7 +485,7 @@ harbor_kernel(const HarborArgs a)
     st->berth[0].cap = 6u;
     st->berth[1].cap = 3u;
     st->tugs.in_use = st->berth[0].in_use = st->berth[1].in_use = 0u;
-    for (uint32_t i = 0u; i < HARBOR_PROCS; i++) {
+    for (uint32_t i = 0u; i < State::PROCS; i++) {
         HarborProc &p = st->proc[i];
         p.pc = 0u;
         p.status = PROC_CREATED;
@@ -552,14 +551,14 @@ harbor_kernel(const HarborArgs a)
                 s.stop(i);
             }
             for (;;) {                                  // active ships in (arrival time, id) order = id order
-                uint32_t first = HARBOR_PROCS;
-                for (uint32_t i = HARBOR_FIXED; i < HARBOR_PROCS; i++) {
+                uint32_t first = State::PROCS;
+                for (uint32_t i = HARBOR_FIXED; i < State::PROCS; i++) {
                     if (st->proc[i].in_use && st->proc[i].active &&
-                        (first == HARBOR_PROCS || st->proc[i].id < st->proc[first].id)) {
+                        (first == State::PROCS || st->proc[i].id < st->proc[first].id)) {
                         first = i;
                     }
                 }
-                if (first == HARBOR_PROCS) {
+                if (first == State::PROCS) {
                     break;
                 }
                 st->proc[first].active = 0u;
@@ -590,6 +589,49 @@ harbor_kernel(const HarborArgs a)
         c[7] = s.reactivated;
     }
     (void)deepest;
+}
+
+// Lane per trial, state in HBM: 32 trials share a warp's instruction stream, each in its own
+// process body - on this workload ~4 of 32 lanes execute any one instruction, and every state access
+// is an L2 / HBM round trip (profiles/r01_harbor.md).
+template <bool TRACE>
+__global__ void __launch_bounds__(GUARDED_BLOCK)
+harbor_kernel(const HarborArgs a)
+{
+    __shared__ ZigHot hot;
+    stage_zig_hot(hot, true);
+    __syncthreads();
+
+    const uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (trial >= a.num_trials) {
+        return;
+    }
+    harbor_trial<TRACE, HarborState>(a, trial, &((HarborState *)a.state)[trial], &hot);
+}
+
+// Warp per trial, state in SHARED memory (BASELINE.json north_star's mapping): for a model whose
+// lanes would all be in different process bodies anyway, one trial per warp loses nothing to
+// divergence, and its heaps, guards and process table answer in shared-memory latency instead of
+// an L2 / HBM round trip.  The warp's first lane runs the trial (the scalar event loop); the
+// CTA's warps are independent trials; persistent CTAs pull trials until none are left.
+template <bool TRACE>
+__global__ void __launch_bounds__(HARBOR_BLOCK_ON_CHIP)
+harbor_on_chip_kernel(const HarborArgs a)
+{
+    extern __shared__ __align__(16) unsigned char harbor_smem[];
+    __shared__ ZigHot hot;
+    stage_zig_hot(hot, true);
+    __syncthreads();
+
+    if ((threadIdx.x & 31u) != 0u) {
+        return;
+    }
+    constexpr uint32_t WARPS = HARBOR_BLOCK_ON_CHIP / 32;
+    const uint32_t w = threadIdx.x >> 5;
+    HarborStateOnChip *st = (HarborStateOnChip *)harbor_smem + w;
+    for (uint64_t trial = (uint64_t)blockIdx.x * WARPS + w; trial < a.num_trials; trial += (uint64_t)gridDim.x * WARPS) {
+        harbor_trial<TRACE, HarborStateOnChip>(a, trial, st, &hot);
+    }
 }
 
 }  // namespace cimba_b200

@@ -527,10 +527,29 @@ def test_harbor_matches_oracle(cb, port, tugs, arr, unl, dur):
     assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
 
 
-def test_harbor_pop_order_bit_exact(cb, port):
+@pytest.mark.parametrize("tugs,arr,unl,dur", [(10, 2.0, 8.0, 2000), (10, 2.5, 6.0, 800), (6, 2.0, 8.0, 300), (10, 2.0, 8.0, 1),
+                                              (10, 2.0, 8.0, 24)])
+def test_harbor_warp_per_trial_in_shared_memory_matches_oracle(cb, port, tugs, arr, unl, dur):
+    """variant 1: one trial per warp, heaps / guards / ship table in shared memory - same results."""
+    n = 150
+    res = cb.run_trials(n, arr_mean=arr, srv_mean=unl, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_HARBOR, servers=tugs, variant=1)
+    want = run_trials(port, "port", 10, tugs, KAT_SEED, 0, n, dur, arr, unl)
+    ok = res.status.cpu().numpy() == 0
+    assert ok.mean() > 0.9                              # a congested trial may outgrow the on-chip tables: reported
+    keep = np.flatnonzero(ok)
+    assert [int(res.events[i]) for i in keep] == [want[i].events for i in keep]
+    assert [float(res.sum_wait[i]) for i in keep] == [want[i].sum_wait for i in keep]
+    c = _counts(res.counters)
+    assert [c[i] for i in keep] == [want[i].counters() for i in keep]
+    assert [int(res.max_queue[i]) for i in keep] == [want[i].max_queue for i in keep]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_harbor_pop_order_bit_exact(cb, port, variant):
     n, cap, dur = 16, 12000, 1500
     res = cb.run_trials(n, arr_mean=2.0, srv_mean=8.0, num_objects=dur, master_seed=1010,
-                        model=cb.MODEL_HARBOR, servers=10, trace_cap=cap)
+                        model=cb.MODEL_HARBOR, servers=10, trace_cap=cap, variant=variant)
     keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
     for i in range(n):
         r, k, t = trace_trial(port, "port", 10, 10, cb.fmix64(1010, i), dur, 2.0, 8.0, cap)
@@ -574,8 +593,10 @@ def test_harbor_reproduces_the_reference_golden_file_on_device(cb, golden):
 
 def test_harbor_ship_table_overflow_is_reported(cb):
     """More ships alive than the device table holds: flagged in status, never silent."""
-    res = cb.run_trials(8, arr_mean=0.7, srv_mean=8.0, num_objects=1000, master_seed=3, model=cb.MODEL_HARBOR, servers=10)
-    assert int((res.status != 0).sum()) == 8
+    for variant in (0, 1):
+        res = cb.run_trials(8, arr_mean=0.7, srv_mean=8.0, num_objects=1000, master_seed=3, model=cb.MODEL_HARBOR,
+                            servers=10, variant=variant)
+        assert int((res.status != 0).sum()) == 8
 
 
 # ------------------------------------------------------------------ hold model (warp per trial, 32-ary heap)
