@@ -225,6 +225,10 @@ namespace cimba_b200 {
 // with the continuation, e.g. a customer's arrival time).  16-byte accesses at a
 // 16-byte lane pitch are conflict-free whatever row each lane addresses.
 // ---------------------------------------------------------------------------
+#ifndef EVENTLIST_BATCH
+#define EVENTLIST_BATCH 2      // measured on B200 (M/M/c, c = 8): 2 -> 2.97e10, 4 -> 2.90e10, 8 -> 2.74e10 events/s at 32 768 trials
+#endif
+
 struct __align__(16) EventHead {
     double   time;
     uint32_t keyact;           // (issue key << 2) | action ; 0 = none
@@ -286,17 +290,40 @@ struct EventList {
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         double bt = INF;
         uint32_t bk = 0xffffffffu, bi = 0u, btag = 0u;
-        for (uint32_t i = 0u; i < scan; i++) {
-            if (i < count) {
-                double et;
-                uint32_t ek, etag;
-                ld_head(head + i * hstride, et, ek, etag);
-                const bool before = (et < bt) | ((et == bt) & (ek < bk));
-                bt = before ? et : bt;
-                bk = before ? ek : bk;
-                btag = before ? etag : btag;
-                bi = before ? i : bi;
+        // EVENTLIST_BATCH rows at a time: their loads are independent (one shared-memory latency, not
+        // one per row) and the comparisons form a tournament, so the dependent chain of a scan over n
+        // rows is n / EVENTLIST_BATCH steps.  Rows beyond `count` enter as (+inf, key ~0) and never
+        // win.  The order is a strict total order (keys are unique), so the winner does not depend on
+        // the bracket.
+        for (uint32_t base = 0u; base < scan; base += EVENTLIST_BATCH) {
+            double et[EVENTLIST_BATCH];
+            uint32_t ek[EVENTLIST_BATCH], etag[EVENTLIST_BATCH], ei[EVENTLIST_BATCH];
+#pragma unroll
+            for (int j = 0; j < EVENTLIST_BATCH; j++) {
+                et[j] = INF;
+                ek[j] = 0xffffffffu;
+                etag[j] = 0u;
+                ei[j] = base + j;
+                if (base + j < count) {
+                    ld_head(head + (base + j) * hstride, et[j], ek[j], etag[j]);
+                }
             }
+#pragma unroll
+            for (int width = EVENTLIST_BATCH / 2; width >= 1; width /= 2) {
+#pragma unroll
+                for (int j = 0; j < width; j++) {
+                    const bool up = (et[j + width] < et[j]) | ((et[j + width] == et[j]) & (ek[j + width] < ek[j]));
+                    et[j] = up ? et[j + width] : et[j];
+                    ek[j] = up ? ek[j + width] : ek[j];
+                    etag[j] = up ? etag[j + width] : etag[j];
+                    ei[j] = up ? ei[j + width] : ei[j];
+                }
+            }
+            const bool before = (et[0] < bt) | ((et[0] == bt) & (ek[0] < bk));
+            bt = before ? et[0] : bt;
+            bk = before ? ek[0] : bk;
+            btag = before ? etag[0] : btag;
+            bi = before ? ei[0] : bi;
         }
         if (count == 0u) {
             return false;
