@@ -24,10 +24,29 @@
 
 namespace cimba_b200 {
 
+// Out-of-line draws for the general-path kernels.  rng.cuh's members inline their ziggurat slow
+// paths (exp(), alias tables, rejection loops: 400-600 instructions) into every call site, which is
+// right for the small hot kernels and wrong for code that draws in dozens of places: the harbor
+// kernel was 40 % inlined generator code and stalled on the instruction cache.
+__device__ __noinline__ double gp_std_normal(Sfc64 &r, const ZigHot &hot)
+{
+    return r.std_normal(hot);
+}
+
+__device__ __noinline__ double gp_exponential(Sfc64 &r, const ZigHot &hot, double mean)
+{
+    return r.exponential(hot, mean);
+}
+
+__device__ __noinline__ double gp_uniform01(Sfc64 &r)
+{
+    return r.uniform01();
+}
+
 // src/cmb_random.c:500-520
 __device__ inline double rnd_triangular(Sfc64 &r, double min, double mode, double max)
 {
-    const double u = r.uniform01();
+    const double u = gp_uniform01(r);
     if (u < (mode - min) / (max - min)) {
         return min + sqrt(u * (max - min) * (mode - min));
     }
@@ -37,22 +56,22 @@ __device__ inline double rnd_triangular(Sfc64 &r, double min, double mode, doubl
 // include/cmb_random.h:249-257
 __device__ inline double rnd_lognormal(Sfc64 &r, const ZigHot &hot, double m, double s)
 {
-    return exp(r.normal(hot, m, s));
+    return exp((m + s * gp_std_normal(r, hot)));
 }
 
 // :267-273
 __device__ inline double rnd_logistic(Sfc64 &r, double m, double s)
 {
-    const double x = r.uniform01();
+    const double x = gp_uniform01(r);
     return m + s * log(x / (1.0 - x));
 }
 
 // :290-299
 __device__ inline double rnd_cauchy(Sfc64 &r, const ZigHot &hot, double mode, double scale)
 {
-    const double x = r.std_normal(hot);
+    const double x = gp_std_normal(r, hot);
     double y;
-    while ((y = r.std_normal(hot)) == 0.0) {}
+    while ((y = gp_std_normal(r, hot)) == 0.0) {}
     return mode + scale * x / y;
 }
 
@@ -61,7 +80,7 @@ __device__ inline double rnd_hypoexponential(Sfc64 &r, const ZigHot &hot, unsign
 {
     double x = 0.0;
     for (unsigned i = 0u; i < n; i++) {
-        x += r.exponential(hot, ma[i]);
+        x += gp_exponential(r, hot, ma[i]);
     }
     return x;
 }
@@ -69,7 +88,7 @@ __device__ inline double rnd_hypoexponential(Sfc64 &r, const ZigHot &hot, unsign
 // src/cmb_random.c:644-662
 __device__ inline unsigned rnd_loaded_dice(Sfc64 &r, unsigned n, const double *pa)
 {
-    const double x = r.uniform01();
+    const double x = gp_uniform01(r);
     double q = 0.0;
     unsigned ui;
     for (ui = 0u; ui < n; ui++) {
@@ -86,22 +105,23 @@ __device__ inline double rnd_hyperexponential(Sfc64 &r, const ZigHot &hot, unsig
                                               const double *ma, const double *pa)
 {
     const unsigned ui = rnd_loaded_dice(r, n, pa);
-    return r.exponential(hot, ma[ui]);
+    return gp_exponential(r, hot, ma[ui]);
 }
 
-// Marsaglia & Tsang, src/cmb_random.c:465-497
-__device__ inline double rnd_std_gamma(Sfc64 &r, const ZigHot &hot, double shape)
+// Marsaglia & Tsang, src/cmb_random.c:465-497.  Out of line on purpose (it carries a full normal draw,
+// slow path included): callers are the cold, code-heavy general-path kernels.
+__device__ __noinline__ double rnd_std_gamma(Sfc64 &r, const ZigHot &hot, double shape)
 {
     const double d = shape - 1.0 / 3.0;
     const double c = 1.0 / sqrt(9.0 * d);
     double x, v;
     for (;;) {
         do {
-            x = r.std_normal(hot);
+            x = gp_std_normal(r, hot);
             v = 1.0 + c * x;
         } while (v <= 0.0);
         const double w = v * v * v;
-        const double u = r.uniform01();
+        const double u = gp_uniform01(r);
         if ((u < 1.0 - 0.331 * (x * x) * (x * x))
             || (log(u) < (0.5 * x * x) + (d * (1.0 - w + log(w))))) {
             return d * w;
@@ -116,7 +136,7 @@ __device__ inline double rnd_gamma(Sfc64 &r, const ZigHot &hot, double shape, do
         return scale * rnd_std_gamma(r, hot, shape);
     }
     const double g = rnd_std_gamma(r, hot, shape + 1.0);
-    const double u = r.uniform01();
+    const double u = gp_uniform01(r);
     return scale * (g * pow(u, 1.0 / shape));
 }
 
@@ -146,14 +166,14 @@ __device__ inline double rnd_PERT_mod(Sfc64 &r, const ZigHot &hot, double min, d
 // :571-582
 __device__ inline double rnd_weibull(Sfc64 &r, const ZigHot &hot, double shape, double scale)
 {
-    const double u = r.exponential(hot, 1.0);
+    const double u = gp_exponential(r, hot, 1.0);
     return scale * pow(u, 1.0 / shape);
 }
 
 // :595-605
 __device__ inline double rnd_pareto(Sfc64 &r, double shape, double mode)
 {
-    return mode / pow(r.uniform01(), 1.0 / shape);
+    return mode / pow(gp_uniform01(r), 1.0 / shape);
 }
 
 // :618-626
@@ -174,7 +194,7 @@ __device__ inline double rnd_F_dist(Sfc64 &r, const ZigHot &hot, double a, doubl
 // :668-679
 __device__ inline double rnd_std_t_dist(Sfc64 &r, const ZigHot &hot, double v)
 {
-    const double x = r.std_normal(hot);
+    const double x = gp_std_normal(r, hot);
     double y;
     while ((y = rnd_chisquared(r, hot, v)) == 0.0) {}
     return x / sqrt(y / v);
@@ -189,8 +209,8 @@ __device__ inline double rnd_t_dist(Sfc64 &r, const ZigHot &hot, double m, doubl
 // :714-725
 __device__ inline double rnd_rayleigh(Sfc64 &r, const ZigHot &hot, double s)
 {
-    const double x = r.normal(hot, 0.0, s);
-    const double y = r.normal(hot, 0.0, s);
+    const double x = (0.0 + s * gp_std_normal(r, hot));
+    const double y = (0.0 + s * gp_std_normal(r, hot));
     return sqrt(x * x + y * y);
 }
 
@@ -215,7 +235,7 @@ __device__ inline int rnd_flip(Sfc64 &r, FlipCache &f)
 __device__ inline unsigned rnd_geometric(Sfc64 &r, const ZigHot &hot, double p)
 {
     const double denom = -log(1.0 - p);
-    return (unsigned)ceil(r.exponential(hot, 1.0) / denom);
+    return (unsigned)ceil(gp_exponential(r, hot, 1.0) / denom);
 }
 
 // :576-588
@@ -245,7 +265,7 @@ __device__ inline unsigned rnd_poisson(Sfc64 &r, const ZigHot &hot, double rate)
     double t = 0.0;
     unsigned ctr = 0u;
     for (;;) {
-        t += r.exponential(hot, m);
+        t += gp_exponential(r, hot, m);
         if (t <= 1.0) {
             ctr++;
         }
@@ -259,7 +279,7 @@ __device__ inline unsigned rnd_poisson(Sfc64 &r, const ZigHot &hot, double rate)
 // cmb_random_alias_sample, include/cmb_random.h:922-933 (tables from cimba_b200_alias_create)
 __device__ inline unsigned rnd_alias_sample(Sfc64 &r, unsigned n, const uint64_t *uprob, const uint32_t *alias)
 {
-    const unsigned idx = (unsigned)floor((double)n * r.uniform01());
+    const unsigned idx = (unsigned)floor((double)n * gp_uniform01(r));
     const bool c = r.next() >= uprob[idx];
     return c ? alias[idx] : idx;
 }

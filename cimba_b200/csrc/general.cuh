@@ -107,7 +107,10 @@ struct BinHeap {
         issued = 0u;
     }
 
-    __device__ void sift_up(uint32_t k)                 // heap_up, :277-316
+    // The sift / remove routines are kept out of line: the general-path kernels call them from dozens of
+    // places, and inlined copies made those kernels 270-390 KB of code - every warp then waits on the
+    // instruction cache (profiles/r01_harbor.md).
+    __device__ __noinline__ void sift_up(uint32_t k)    // heap_up, :277-316
     {
         const HeapTag moving = slot[k];
         uint32_t parent;
@@ -121,7 +124,7 @@ struct BinHeap {
         slot[k] = moving;
     }
 
-    __device__ void sift_down(uint32_t k)               // heap_down, :321-370
+    __device__ __noinline__ void sift_down(uint32_t k)  // heap_down, :321-370
     {
         const HeapTag moving = slot[k];
         const uint32_t last_parent = count >> 1;
@@ -140,7 +143,7 @@ struct BinHeap {
     }
 
     // cmi_hashheap_enqueue; key 0 = issue the next one.  Returns 0 on overflow.
-    __device__ uint32_t push(uint32_t key, double d, int32_t prio, uint32_t act, uint32_t subj, int32_t arg)
+    __device__ __noinline__ uint32_t push(uint32_t key, double d, int32_t prio, uint32_t act, uint32_t subj, int32_t arg)
     {
         issued += 1u;
         if (key == 0u) {
@@ -162,7 +165,7 @@ struct BinHeap {
         return key;
     }
 
-    __device__ bool pop()                               // cmi_hashheap_dequeue
+    __device__ __noinline__ bool pop()                  // cmi_hashheap_dequeue
     {
         if (count == 0u) {
             return false;
@@ -192,7 +195,7 @@ struct BinHeap {
     }
 
     // cmi_hashheap_reprioritize, src/cmi_hashheap.c:679-711
-    __device__ void reprioritize(uint32_t key, double d, int32_t prio)
+    __device__ __noinline__ void reprioritize(uint32_t key, double d, int32_t prio)
     {
         const uint32_t at = find(key);
         if (at == 0u) {
@@ -209,7 +212,7 @@ struct BinHeap {
         }
     }
 
-    __device__ bool remove(uint32_t key)                // cmi_hashheap_remove (lookup by scan)
+    __device__ __noinline__ bool remove(uint32_t key)   // cmi_hashheap_remove (lookup by scan)
     {
         uint32_t at = 0u;
         for (uint32_t k = 1u; k <= count; k++) {

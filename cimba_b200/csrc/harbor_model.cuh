@@ -46,6 +46,13 @@ constexpr uint32_t HARBOR_FIXED = 5u;                   // weather, tide, arriva
 constexpr uint16_t HARBOR_NONE = 0xffffu;
 constexpr int HARBOR_BLOCK_ON_CHIP = 128;               // 4 warps = 4 trials per CTA when the state is in shared memory
 
+// libm's sin carries a large argument-reduction slow path; four inlined copies of it (the tide model)
+// are 10 % of this kernel's code.  One out-of-line copy instead.
+__device__ __noinline__ double harbor_sin(double x)
+{
+    return sin(x);
+}
+
 struct HarborProc {
     uint8_t  pc, status, n_awaits, active;
     uint8_t  await_type[2];
@@ -82,6 +89,9 @@ struct HarborStateT {
 using HarborState = HarborStateT<127, 127, 120>;        // HBM-resident, one trial per lane (~17 KB)
 using HarborStateOnChip = HarborStateT<47, 47, 43>;     // shared-memory-resident, one trial per warp (~5.6 KB)
 
+// the on-chip kernel's dynamic shared memory: [warps per CTA] HarborStateOnChip
+extern __shared__ __align__(16) unsigned char harbor_smem[];
+
 struct HarborArgs {
     int32_t  tugs;
     uint64_t master_seed, first_trial, num_trials, duration;
@@ -96,9 +106,23 @@ struct HarborArgs {
     double   *trace_time;
 };
 
-template <class State>
+template <class State, bool IN_SHARED>
 struct HarborSim {
-    State *st;
+    State *gst;                 // HBM-resident state (lane per trial)
+    uint32_t warp_in_cta;       // which of the CTA's shared-memory states (warp per trial)
+
+    // Every state access goes through here so that the compiler knows the address space: a
+    // pointer kept in a struct member is generic, and generic loads / stores cost an address-range
+    // check each (the on-chip kernel had 840 generic loads and 810 generic stores before this).
+    __device__ __forceinline__ State &S() const
+    {
+        if (IN_SHARED) {
+            return ((State *)harbor_smem)[warp_in_cta];
+        }
+        __builtin_assume(__isGlobal(gst));
+        return *gst;
+    }
+
     Sfc64 rng;
     const ZigHot *hot;
     double now, arr_mean, unload_small, sum_wait;
@@ -107,9 +131,9 @@ struct HarborSim {
 
     __device__ uint32_t schedule(uint32_t act, uint32_t subj, double t)
     {
-        const uint32_t key = st->fel.push(0u, t, 0, act, subj, (int32_t)SIG_SUCCESS);
+        const uint32_t key = S().fel.push(0u, t, 0, act, subj, (int32_t)SIG_SUCCESS);
         if (key == 0u) {
-            st->status |= TRIAL_ERR_FEL_OVERFLOW;
+            S().status |= TRIAL_ERR_FEL_OVERFLOW;
         }
         return key;
     }
@@ -117,7 +141,7 @@ struct HarborSim {
     __device__ void await_push(HarborProc &p, uint32_t type, uint32_t ref)
     {
         if (p.n_awaits >= 2u) {
-            st->status |= TRIAL_ERR_PROC_OVERFLOW;
+            S().status |= TRIAL_ERR_PROC_OVERFLOW;
             return;
         }
         p.await_type[1] = p.await_type[0];
@@ -143,7 +167,7 @@ struct HarborSim {
 
     __device__ void hold_begin(uint32_t pid, double dur)        // src/cmb_process.c:262-273
     {
-        HarborProc &p = st->proc[pid];
+        HarborProc &p = S().proc[pid];
         p.hold_handle = schedule(ACT_WAKE_TIME, pid, now + dur);
         await_push(p, AWAIT_TIME, p.hold_handle);
     }
@@ -151,10 +175,10 @@ struct HarborSim {
     template <class Guard>
     __device__ void wait_begin(Guard &g, uint32_t gid, uint32_t pid)    // src/cmb_resourceguard.c:125-152
     {
-        HarborProc &p = st->proc[pid];
-        p.guard_key = ++st->guard_seq;
+        HarborProc &p = S().proc[pid];
+        p.guard_key = ++S().guard_seq;
         if (g.push(p.guard_key, now, 0, 0u, pid, 0) == 0u) {
-            st->status |= TRIAL_ERR_GUARD_OVERFLOW;
+            S().status |= TRIAL_ERR_GUARD_OVERFLOW;
         }
         await_push(p, AWAIT_RESOURCE, gid);
     }
@@ -171,7 +195,7 @@ struct HarborSim {
 
     __device__ void record(HarborPool &p)               // record_sample, src/cmb_resourcepool.c:239-247
     {
-        p.hist.sample((double)p.in_use, now);
+        time_weighted_sample(p.hist, (double)p.in_use, now);
     }
 
     // one pass of cmi_pool_acquire_inner's loop (no pre-emption): true when the claim is filled
@@ -207,21 +231,21 @@ struct HarborSim {
 
     __device__ bool can_dock(const HarborProc &s) const // is_ready_to_dock, test/test_condition.c:192-236
     {
-        if (st->water_depth < (s.size == 0u ? 8.0 : 13.0)) return false;
-        if (st->wind_magnitude > (s.size == 0u ? 10.0 : 12.0)) return false;
-        if (st->tugs.cap - st->tugs.in_use < s.need) return false;
-        return st->berth[s.size].cap - st->berth[s.size].in_use >= 1u;
+        if (S().water_depth < (s.size == 0u ? 8.0 : 13.0)) return false;
+        if (S().wind_magnitude > (s.size == 0u ? 10.0 : 12.0)) return false;
+        if (S().tugs.cap - S().tugs.in_use < s.need) return false;
+        return S().berth[s.size].cap - S().berth[s.size].in_use >= 1u;
     }
 
     // cmb_condition_signal, src/cmb_condition.c:120-167
     __device__ uint32_t harbormaster_signal()
     {
-        auto &cv = st->harbormaster;
+        auto &cv = S().harbormaster;
         uint32_t hit[State::GUARD];
         uint32_t cnt = 0u;
         for (uint32_t k = 1u; k <= cv.count; k++) {
             const uint32_t pid = cv.slot[k].subj;
-            if (can_dock(st->proc[pid])) {
+            if (can_dock(S().proc[pid])) {
                 hit[cnt++] = cv.slot[k].key;
                 schedule(ACT_WAKE_CONDITION, pid, now);
             }
@@ -234,11 +258,11 @@ struct HarborSim {
 
     __device__ void davyjones_signal()
     {
-        auto &cv = st->davyjones;
+        auto &cv = S().davyjones;
         uint32_t hit[3];
         uint32_t cnt = 0u;
         for (uint32_t k = 1u; k <= cv.count; k++) {
-            if (st->departed != HARBOR_NONE) {          // is_departed
+            if (S().departed != HARBOR_NONE) {          // is_departed
                 hit[cnt++] = cv.slot[k].key;
                 schedule(ACT_WAKE_CONDITION, cv.slot[k].subj, now);
             }
@@ -258,7 +282,7 @@ struct HarborSim {
     // cmb_process_stop, src/cmb_process.c:698-723
     __device__ void stop(uint32_t pid)
     {
-        HarborProc &p = st->proc[pid];
+        HarborProc &p = S().proc[pid];
         if (p.status != PROC_RUNNING) {
             return;
         }
@@ -270,38 +294,38 @@ struct HarborSim {
             p.await_ref[0] = p.await_ref[1];
             p.n_awaits--;
             if (type == AWAIT_TIME) {
-                (void)st->fel.remove(ref);
+                (void)S().fel.remove(ref);
             }
             // AWAIT_RESOURCE: looked up by process address, never found:
             // the guard entry stays behind and may swallow a later signal
         }
         uint32_t hit[8];
         uint32_t n = 0u;
-        for (uint32_t k = 1u; k <= st->fel.count && n < 8u; k++) {     // cmb_event_pattern_cancel(ANY, p, ANY)
-            if (st->fel.slot[k].subj == pid) {
-                hit[n++] = st->fel.slot[k].key;
+        for (uint32_t k = 1u; k <= S().fel.count && n < 8u; k++) {     // cmb_event_pattern_cancel(ANY, p, ANY)
+            if (S().fel.slot[k].subj == pid) {
+                hit[n++] = S().fel.slot[k].key;
             }
         }
         for (uint32_t k = 0u; k < n; k++) {
-            (void)st->fel.remove(hit[k]);
+            (void)S().fel.remove(hit[k]);
         }
         // cmi_process_drop_resources, :507-527: the tugs were listed last, so they go first
         if (p.held_tugs > 0u) {
-            st->tugs.in_use -= p.held_tugs;
+            S().tugs.in_use -= p.held_tugs;
             p.held_tugs = 0u;
-            signal(st->tug_guard, st->tugs.cap - st->tugs.in_use > 0u);
+            signal(S().tug_guard, S().tugs.cap - S().tugs.in_use > 0u);
         }
         if (p.held_berth > 0u) {
-            st->berth[p.size].in_use -= p.held_berth;   // berth guards never have waiters
+            S().berth[p.size].in_use -= p.held_berth;   // berth guards never have waiters
             p.held_berth = 0u;
         }
     }
 };
 
-template <class State>
-__device__ void HarborSim<State>::body(uint32_t pid)
+template <class State, bool IN_SHARED>
+__device__ void HarborSim<State, IN_SHARED>::body(uint32_t pid)
 {
-    HarborProc &p = st->proc[pid];
+    HarborProc &p = S().proc[pid];
     const uint32_t kind = pid < HARBOR_FIXED ? pid : HARBOR_FIXED;
     switch (kind * 10u + p.pc) {
     // ---- weather
@@ -309,10 +333,10 @@ __device__ void HarborSim<State>::body(uint32_t pid)
         for (;;) {
             {
                 const double gust = rnd_rayleigh(rng, *hot, 5.0);
-                st->wind_magnitude = 0.5 * gust + 0.5 * st->wind_magnitude;
+                S().wind_magnitude = 0.5 * gust + 0.5 * S().wind_magnitude;
                 const double d1 = pert(0.0, 225.0, 360.0);
                 const double d2 = pert(0.0, 45.0, 360.0);
-                st->wind_direction = 0.75 * d1 + 0.25 * d2;
+                S().wind_direction = 0.75 * d1 + 0.25 * d2;
                 reactivated += harbormaster_signal();
             }
             hold_begin(pid, 1.0);
@@ -326,11 +350,11 @@ __device__ void HarborSim<State>::body(uint32_t pid)
             {
                 const double half_month = 0.5 * 29.5 * 24.0;
                 const double t = fmod(now, half_month);
-                const double astro = 15.0 + 1.0 * sin(2.0 * M_PI * t / 12.4) + 0.5 * sin(2.0 * M_PI * t / 24.0)
-                                   + 0.25 * sin(2.0 * M_PI * t / (0.5 * 29.5 * 24));
-                const double surge = 0.5 * st->wind_magnitude
-                                   - 0.5 * st->wind_magnitude * sin(st->wind_direction * M_PI / 180.0);
-                st->water_depth = astro + surge;
+                const double astro = 15.0 + 1.0 * harbor_sin(2.0 * M_PI * t / 12.4) + 0.5 * harbor_sin(2.0 * M_PI * t / 24.0)
+                                   + 0.25 * harbor_sin(2.0 * M_PI * t / (0.5 * 29.5 * 24));
+                const double surge = 0.5 * S().wind_magnitude
+                                   - 0.5 * S().wind_magnitude * harbor_sin(S().wind_direction * M_PI / 180.0);
+                S().water_depth = astro + surge;
                 reactivated += harbormaster_signal();
             }
             hold_begin(pid, 1.0);
@@ -341,22 +365,22 @@ __device__ void HarborSim<State>::body(uint32_t pid)
     // ---- arrivals
     case 20:
         for (;;) {
-            hold_begin(pid, rng.exponential(*hot, arr_mean));
+            hold_begin(pid, gp_exponential(rng, *hot, arr_mean));
             p.pc = 1u;
             return;
     case 21:
             {
                 uint32_t slot = HARBOR_FIXED;
-                while (slot < State::PROCS && st->proc[slot].in_use) {
+                while (slot < State::PROCS && S().proc[slot].in_use) {
                     slot++;
                 }
-                const uint32_t id = ++st->next_id;
+                const uint32_t id = ++S().next_id;
                 const uint32_t size = rng.bernoulli(0.25);
                 if (slot == State::PROCS) {
-                    st->status |= TRIAL_ERR_PROC_OVERFLOW;      // the ship is lost: the trial is void from here on
+                    S().status |= TRIAL_ERR_PROC_OVERFLOW;      // the ship is lost: the trial is void from here on
                 }
                 else {
-                    HarborProc &s = st->proc[slot];
+                    HarborProc &s = S().proc[slot];
                     s.pc = 0u;
                     s.status = PROC_CREATED;
                     s.n_awaits = 0u;
@@ -374,15 +398,15 @@ __device__ void HarborSim<State>::body(uint32_t pid)
     // ---- departures
     case 30:
         for (;;) {
-            wait_begin(st->davyjones, 2u, pid);
+            wait_begin(S().davyjones, 2u, pid);
             p.pc = 1u;
             return;
     case 31:
             await_remove(p, AWAIT_RESOURCE, false, 2u);
             {
-                const uint32_t slot = st->departed;
-                HarborProc &s = st->proc[slot];
-                st->departed = s.next_departed;
+                const uint32_t slot = S().departed;
+                HarborProc &s = S().proc[slot];
+                S().departed = s.next_departed;
                 summary_add(sys_time[s.size], s.t_sys);
                 sum_wait = sum_wait + s.t_sys;
                 through[s.size] += 1u;
@@ -401,25 +425,25 @@ __device__ void HarborSim<State>::body(uint32_t pid)
     case 50:
         p.t_arr = now;
         p.active = 1u;
-        if (++st->alive > st->most_alive) {
-            st->most_alive = st->alive;
+        if (++S().alive > S().most_alive) {
+            S().most_alive = S().alive;
         }
         while (!can_dock(p)) {
-            wait_begin(st->harbormaster, 0u, pid);
+            wait_begin(S().harbormaster, 0u, pid);
             p.pc = 1u;
             return;
     case 51:
             await_remove(p, AWAIT_RESOURCE, false, 0u);
         }
         p.rem = 1u;                                     // both are there: the predicate just said so
-        (void)pool_grab(st->berth[p.size], st->berth_guard[p.size], p.rem, p.held_berth);
+        (void)pool_grab(S().berth[p.size], S().berth_guard[p.size], p.rem, p.held_berth);
         p.rem = p.need;
-        (void)pool_grab(st->tugs, st->tug_guard, p.rem, p.held_tugs);
+        (void)pool_grab(S().tugs, S().tug_guard, p.rem, p.held_tugs);
         hold_begin(pid, pert(0.4, 0.5, 0.8));
         p.pc = 2u;
         return;
     case 52:
-        pool_release(st->tugs, st->tug_guard, p.need, p.held_tugs);
+        pool_release(S().tugs, S().tug_guard, p.need, p.held_tugs);
         {
             const double tua = (p.size == 0u) ? unload_small : 1.5 * unload_small;
             hold_begin(pid, pert(0.75 * tua, tua, 2 * tua));
@@ -428,8 +452,8 @@ __device__ void HarborSim<State>::body(uint32_t pid)
         return;
     case 53:
         p.rem = p.need;
-        while (!pool_grab(st->tugs, st->tug_guard, p.rem, p.held_tugs)) {
-            wait_begin(st->tug_guard, 1u, pid);
+        while (!pool_grab(S().tugs, S().tug_guard, p.rem, p.held_tugs)) {
+            wait_begin(S().tug_guard, 1u, pid);
             p.pc = 4u;
             return;
     case 54:
@@ -439,12 +463,12 @@ __device__ void HarborSim<State>::body(uint32_t pid)
         p.pc = 5u;
         return;
     case 55:
-        pool_release(st->berth[p.size], st->berth_guard[p.size], 1u, p.held_berth);
-        pool_release(st->tugs, st->tug_guard, p.need, p.held_tugs);
+        pool_release(S().berth[p.size], S().berth_guard[p.size], 1u, p.held_berth);
+        pool_release(S().tugs, S().tug_guard, p.need, p.held_tugs);
         p.active = 0u;
-        st->alive--;
-        p.next_departed = st->departed;
-        st->departed = (uint16_t)pid;
+        S().alive--;
+        p.next_departed = S().departed;
+        S().departed = (uint16_t)pid;
         davyjones_signal();
         p.t_sys = now - p.t_arr;
         p.status = PROC_FINISHED;                       // return -> cmb_process_exit: nothing held or awaited
@@ -454,11 +478,14 @@ __device__ void HarborSim<State>::body(uint32_t pid)
 
 // one whole trial, start to finish, on the calling thread; `st` is in HBM (lane per trial) or in
 // shared memory (warp per trial, run by the warp's first lane)
-template <bool TRACE, class State>
-__device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, const ZigHot *hot)
+template <bool TRACE, class State, bool IN_SHARED>
+__device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *global_state, uint32_t warp_in_cta,
+                             const ZigHot *hot)
 {
-    HarborSim<State> s;
-    s.st = st;
+    __builtin_assume(__isShared(hot));
+    HarborSim<State, IN_SHARED> s;
+    s.gst = global_state;
+    s.warp_in_cta = warp_in_cta;
     s.hot = hot;
     s.now = 0.0;
     s.sum_wait = 0.0;
@@ -470,23 +497,23 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
     s.unload_small = a.unload_small[trial];
     s.rng.seed(fmix64(a.master_seed, a.first_trial + trial));
 
-    st->fel.clear();
-    st->harbormaster.clear();
-    st->tug_guard.clear();
-    st->davyjones.clear();
-    st->berth_guard[0].clear();
-    st->berth_guard[1].clear();
-    st->wind_magnitude = st->wind_direction = st->water_depth = 0.0;
-    st->guard_seq = 0u;
-    st->status = TRIAL_OK;
-    st->next_id = st->alive = st->most_alive = 0u;
-    st->departed = HARBOR_NONE;
-    st->tugs.cap = (uint32_t)a.tugs;
-    st->berth[0].cap = 6u;
-    st->berth[1].cap = 3u;
-    st->tugs.in_use = st->berth[0].in_use = st->berth[1].in_use = 0u;
+    s.S().fel.clear();
+    s.S().harbormaster.clear();
+    s.S().tug_guard.clear();
+    s.S().davyjones.clear();
+    s.S().berth_guard[0].clear();
+    s.S().berth_guard[1].clear();
+    s.S().wind_magnitude = s.S().wind_direction = s.S().water_depth = 0.0;
+    s.S().guard_seq = 0u;
+    s.S().status = TRIAL_OK;
+    s.S().next_id = s.S().alive = s.S().most_alive = 0u;
+    s.S().departed = HARBOR_NONE;
+    s.S().tugs.cap = (uint32_t)a.tugs;
+    s.S().berth[0].cap = 6u;
+    s.S().berth[1].cap = 3u;
+    s.S().tugs.in_use = s.S().berth[0].in_use = s.S().berth[1].in_use = 0u;
     for (uint32_t i = 0u; i < State::PROCS; i++) {
-        HarborProc &p = st->proc[i];
+        HarborProc &p = s.S().proc[i];
         p.pc = 0u;
         p.status = PROC_CREATED;
         p.n_awaits = 0u;
@@ -500,12 +527,12 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
     // creation order of test/test_condition.c:523-586 fixes the event keys
     s.schedule(ACT_START, 0u, 0.0);
     s.schedule(ACT_START, 1u, 0.0);
-    st->tugs.hist.start();
-    st->berth[0].hist.start();
-    st->berth[1].hist.start();
-    s.record(st->tugs);                                 // cmb_resourcepool_start_recording
-    s.record(st->berth[0]);
-    s.record(st->berth[1]);
+    s.S().tugs.hist.start();
+    s.S().berth[0].hist.start();
+    s.S().berth[1].hist.start();
+    s.record(s.S().tugs);                                 // cmb_resourcepool_start_recording
+    s.record(s.S().berth[0]);
+    s.record(s.S().berth[1]);
     s.schedule(ACT_START, 2u, 0.0);
     s.schedule(ACT_START, 3u, 0.0);
     s.schedule(ACT_USER, SUBJ_MODEL, (double)a.duration);
@@ -514,11 +541,11 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
     uint64_t pops = 0u;
     uint32_t deepest = 0u;
     for (;;) {
-        deepest = max(deepest, st->fel.count);
-        if (!st->fel.pop()) {
+        deepest = max(deepest, s.S().fel.count);
+        if (!s.S().fel.pop()) {
             break;
         }
-        const HeapTag ev = st->fel.slot[0];
+        const HeapTag ev = s.S().fel.slot[0];
         s.now = ev.d;
         if (TRACE) {
             if (pops < a.trace_cap) {
@@ -531,20 +558,20 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
         bool run = false;
         switch (ev.act) {
         case ACT_START:
-            st->proc[pid].status = PROC_RUNNING;
-            st->proc[pid].pc = 0u;
+            s.S().proc[pid].status = PROC_RUNNING;
+            s.S().proc[pid].pc = 0u;
             run = true;
             break;
         case ACT_WAKE_TIME:
-            s.await_remove(st->proc[pid], AWAIT_TIME, false, ev.key);
+            s.await_remove(s.S().proc[pid], AWAIT_TIME, false, ev.key);
             run = true;
             break;
         case ACT_WAKE_RESOURCE:
-            run = st->proc[pid].status == PROC_RUNNING;
+            run = s.S().proc[pid].status == PROC_RUNNING;
             break;
         case ACT_WAKE_CONDITION:
-            s.await_remove(st->proc[pid], AWAIT_RESOURCE, true, 0u);
-            run = st->proc[pid].status == PROC_RUNNING;
+            s.await_remove(s.S().proc[pid], AWAIT_RESOURCE, true, 0u);
+            run = s.S().proc[pid].status == PROC_RUNNING;
             break;
         case ACT_USER:                                  // end_sim_evt, test/test_condition.c:462-484
             for (uint32_t i = 0u; i < HARBOR_FIXED; i++) {
@@ -553,15 +580,15 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
             for (;;) {                                  // active ships in (arrival time, id) order = id order
                 uint32_t first = State::PROCS;
                 for (uint32_t i = HARBOR_FIXED; i < State::PROCS; i++) {
-                    if (st->proc[i].in_use && st->proc[i].active &&
-                        (first == State::PROCS || st->proc[i].id < st->proc[first].id)) {
+                    if (s.S().proc[i].in_use && s.S().proc[i].active &&
+                        (first == State::PROCS || s.S().proc[i].id < s.S().proc[first].id)) {
                         first = i;
                     }
                 }
                 if (first == State::PROCS) {
                     break;
                 }
-                st->proc[first].active = 0u;
+                s.S().proc[first].active = 0u;
                 s.stop(first);
             }
             break;
@@ -575,17 +602,17 @@ __device__ void harbor_trial(const HarborArgs &a, uint64_t trial, State *st, con
     if (a.objects)   a.objects[trial] = s.through[0] + s.through[1];
     if (a.t_end)     a.t_end[trial] = s.now;
     if (a.sum_wait)  a.sum_wait[trial] = s.sum_wait;
-    if (a.status)    a.status[trial] = st->status;
-    if (a.max_queue) a.max_queue[trial] = st->most_alive;
+    if (a.status)    a.status[trial] = s.S().status;
+    if (a.max_queue) a.max_queue[trial] = s.S().most_alive;
     if (a.counters) {
         uint64_t *c = a.counters + trial * 8u;
         c[0] = s.through[0];
         c[1] = s.through[1];
         c[2] = (uint64_t)__double_as_longlong(s.sys_time[0].m1);
         c[3] = (uint64_t)__double_as_longlong(s.sys_time[1].m1);
-        c[4] = st->tugs.hist.acc.count;
-        c[5] = (uint64_t)__double_as_longlong(st->tugs.hist.acc.m1);
-        c[6] = st->berth[0].hist.acc.count | (st->berth[1].hist.acc.count << 32);
+        c[4] = s.S().tugs.hist.acc.count;
+        c[5] = (uint64_t)__double_as_longlong(s.S().tugs.hist.acc.m1);
+        c[6] = s.S().berth[0].hist.acc.count | (s.S().berth[1].hist.acc.count << 32);
         c[7] = s.reactivated;
     }
     (void)deepest;
@@ -606,7 +633,7 @@ harbor_kernel(const HarborArgs a)
     if (trial >= a.num_trials) {
         return;
     }
-    harbor_trial<TRACE, HarborState>(a, trial, &((HarborState *)a.state)[trial], &hot);
+    harbor_trial<TRACE, HarborState, false>(a, trial, &((HarborState *)a.state)[trial], 0u, &hot);
 }
 
 // Warp per trial, state in SHARED memory (BASELINE.json north_star's mapping): for a model whose
@@ -618,7 +645,6 @@ template <bool TRACE>
 __global__ void __launch_bounds__(HARBOR_BLOCK_ON_CHIP)
 harbor_on_chip_kernel(const HarborArgs a)
 {
-    extern __shared__ __align__(16) unsigned char harbor_smem[];
     __shared__ ZigHot hot;
     stage_zig_hot(hot, true);
     __syncthreads();
@@ -628,9 +654,8 @@ harbor_on_chip_kernel(const HarborArgs a)
     }
     constexpr uint32_t WARPS = HARBOR_BLOCK_ON_CHIP / 32;
     const uint32_t w = threadIdx.x >> 5;
-    HarborStateOnChip *st = (HarborStateOnChip *)harbor_smem + w;
     for (uint64_t trial = (uint64_t)blockIdx.x * WARPS + w; trial < a.num_trials; trial += (uint64_t)gridDim.x * WARPS) {
-        harbor_trial<TRACE, HarborStateOnChip>(a, trial, st, &hot);
+        harbor_trial<TRACE, HarborStateOnChip, true>(a, trial, nullptr, w, &hot);
     }
 }
 

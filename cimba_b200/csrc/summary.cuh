@@ -200,6 +200,12 @@ struct TimeWeighted {
     }
 };
 
+// the same, out of line, for code that samples in many places (general-path kernels)
+__device__ __noinline__ void time_weighted_sample(TimeWeighted &h, double value, double now)
+{
+    h.sample(value, now);
+}
+
 constexpr int SUMMARY_BLOCK = 256;
 
 // One CTA: thread t adds trials t, t+256, ... (coalesced reads), then a fixed
