@@ -33,17 +33,20 @@ CONFIGS = [
     ("HOLD 1000 processes 4096 trials (config 5's event-list shape; objects = duration/1000)", cb.MODEL_HOLD, 4096, 1.0, 1.0, 1000),
     ("HARBOR test_condition.c 4096 trials (config 5's cmb_condition shape; objects = hours/10)", cb.MODEL_HARBOR, 4096, 2.0, 8.0, 10),
     ("HARBOR test_condition.c 65536 trials", cb.MODEL_HARBOR, 65536, 2.0, 8.0, 10),
+    ("HARBOR warp per trial, state in shared memory (variant 1), 4096 trials", cb.MODEL_HARBOR, 4096, 2.0, 8.0, 10, 1),
+    ("HARBOR warp per trial, state in shared memory (variant 1), 65536 trials", cb.MODEL_HARBOR, 65536, 2.0, 8.0, 10, 1),
 ]
 dev = torch.device("cuda", 0)
-for name, model, n, arr, srv, servers in CONFIGS:
+for name, model, n, arr, srv, servers, *rest in CONFIGS:
+    variant = rest[0] if rest else 0
     if args.only and args.only not in name:
         continue
     a = torch.full((n,), arr, dtype=torch.float64, device=dev)
     s = torch.full((n,), srv, dtype=torch.float64, device=dev)
-    bufs = TrialBuffers(n, dev, 0, model, servers)
+    bufs = TrialBuffers(n, dev, 0, model, servers, variant)
     size = args.objects // 1000 if model == cb.MODEL_HOLD else (args.objects // 10 if model == cb.MODEL_HARBOR else args.objects)
     run = lambda: cb.launch_trials(a, s, num_objects=size, master_seed=0x34F05C64D7AD598F,
-                                   model=model, servers=servers, buffers=bufs)
+                                   model=model, servers=servers, buffers=bufs, variant=variant)
     run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
