@@ -38,7 +38,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
     case 0:
         if (pid == BUFFER_PROCS) {                      // nuisance
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
                 p.pc = 10u;
                 return;
     case 10:
@@ -53,7 +53,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
         }
         if (pid < 2u) {                                 // filler: cmb_buffer_put
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, t.put_mean));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.put_mean));
                 p.pc = 20u;
                 return;
     case 20:
@@ -96,7 +96,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
         }
         if (pid < 4u) {                                 // drainer: cmb_buffer_get
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, t.get_mean));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.get_mean));
                 p.pc = 30u;
                 return;
     case 30:
@@ -169,7 +169,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
             if (sig == (int32_t)SIG_SUCCESS) {
                 t.c[4] += 1u;
                 p.stamp = s.now;
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
                 p.pc = 41u;
                 return;
     case 41:
@@ -189,7 +189,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
             else {
                 buffer_note(t, sig);
             }
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 42u;
             return;
     case 42:

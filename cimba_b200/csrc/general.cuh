@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "distributions.cuh"
 #include "engine.cuh"
 #include "rng.cuh"
 
@@ -310,7 +311,7 @@ struct GeneralSim {
     const ZigHot *hot;
 
     // ---- awaitables (src/cmb_process.c:220-260)
-    __device__ void await_push(GenProc &p, uint32_t type, uint32_t ref)
+    __device__ __noinline__ void await_push(GenProc &p, uint32_t type, uint32_t ref)
     {
         if (p.n_awaits >= (uint32_t)GEN_MAX_AWAITS) {
             st->status |= TRIAL_ERR_PROC_OVERFLOW;
@@ -326,7 +327,7 @@ struct GeneralSim {
     }
 
     // cmi_process_remove_awaitable(pp, type, NULL): first entry of that type, any value
-    __device__ bool await_remove_any(GenProc &p, uint32_t type)
+    __device__ __noinline__ bool await_remove_any(GenProc &p, uint32_t type)
     {
         for (uint32_t k = 0u; k < p.n_awaits; k++) {
             if (p.await_type[k] == type) {
@@ -341,7 +342,7 @@ struct GeneralSim {
         return false;
     }
 
-    __device__ bool await_remove(GenProc &p, uint32_t type, uint32_t ref)
+    __device__ __noinline__ bool await_remove(GenProc &p, uint32_t type, uint32_t ref)
     {
         for (uint32_t k = 0u; k < p.n_awaits; k++) {
             if (p.await_type[k] == type && p.await_ref[k] == ref) {
@@ -367,7 +368,7 @@ struct GeneralSim {
     }
 
     // wake_event_waiters, src/cmb_event.c:200-221 (the list is push-front / pop-front)
-    __device__ void wake_event_waiters(uint32_t key, int32_t sig)
+    __device__ __noinline__ void wake_event_waiters(uint32_t key, int32_t sig)
     {
         for (uint32_t k = st->n_ew; k > 0u; k--) {
             if (st->ew_key[k - 1u] == key) {
@@ -433,7 +434,7 @@ struct GeneralSim {
         return true;
     }
 
-    __device__ void cancel_events_of(uint32_t subj)     // cmb_event_pattern_cancel(ANY, subj, ANY)
+    __device__ __noinline__ void cancel_events_of(uint32_t subj)     // cmb_event_pattern_cancel(ANY, subj, ANY)
     {
         uint32_t hit[GEN_FEL_CAP];
         uint32_t n = 0u;
@@ -448,7 +449,7 @@ struct GeneralSim {
     }
 
     // ---- process layer
-    __device__ void cancel_awaiteds(uint32_t pid)       // src/cmb_process.c:581-620
+    __device__ __noinline__ void cancel_awaiteds(uint32_t pid)       // src/cmb_process.c:581-620
     {
         GenProc &p = st->proc[pid];
         while (p.n_awaits > 0u) {
@@ -485,7 +486,7 @@ struct GeneralSim {
         cancel_events_of(pid);
     }
 
-    __device__ void hold_begin(uint32_t pid, double dur)        // :262-273, 316-333
+    __device__ __noinline__ void hold_begin(uint32_t pid, double dur)        // :262-273, 316-333
     {
         GenProc &p = st->proc[pid];
         if (dur < 0.0) {
@@ -505,7 +506,7 @@ struct GeneralSim {
         return sig;
     }
 
-    __device__ void wait_begin(uint32_t g, uint32_t pid)        // src/cmb_resourceguard.c:125-152
+    __device__ __noinline__ void wait_begin(uint32_t g, uint32_t pid)        // src/cmb_resourceguard.c:125-152
     {
         GenProc &p = st->proc[pid];
         p.guard_key = ++st->guard_seq;
@@ -525,7 +526,7 @@ struct GeneralSim {
         return sig;
     }
 
-    __device__ void signal(uint32_t g, bool demand_holds)       // :202-226
+    __device__ __noinline__ void signal(uint32_t g, bool demand_holds)       // :202-226
     {
         GuardHeap &h = st->guard[g];
         if (h.count > 0u && demand_holds) {
@@ -540,7 +541,7 @@ struct GeneralSim {
         schedule(ACT_WAKE_INTERRUPT, pid, sig, now, pri);
     }
 
-    __device__ void stop(uint32_t pid)                          // :698-723
+    __device__ __noinline__ void stop(uint32_t pid)                          // :698-723
     {
         GenProc &p = st->proc[pid];
         if (p.status != PROC_RUNNING) {
@@ -570,7 +571,7 @@ struct GeneralSim {
         }
     }
 
-    __device__ void wake_process_waiters(uint32_t pid, int32_t sig)         // src/cmb_process.c:485-505
+    __device__ __noinline__ void wake_process_waiters(uint32_t pid, int32_t sig)         // src/cmb_process.c:485-505
     {
         GenProc &p = st->proc[pid];
         for (uint32_t k = 0u; k < p.n_waiters; k++) {
@@ -602,7 +603,7 @@ struct GeneralSim {
         return event_cancel(handle);
     }
 
-    __device__ void timers_clear(uint32_t pid)                              // :354-381
+    __device__ __noinline__ void timers_clear(uint32_t pid)                              // :354-381
     {
         GenProc &p = st->proc[pid];
         uint32_t k = 0u;
@@ -662,7 +663,7 @@ struct GeneralSim {
         return k ? (uint32_t)st->holders.slot[k].arg : 0u;
     }
 
-    __device__ void pool_update_record(uint32_t pid, uint32_t amount)       // :324-355
+    __device__ __noinline__ void pool_update_record(uint32_t pid, uint32_t amount)       // :324-355
     {
         const uint32_t k = st->holders.find(pid + 1u);
         if (k != 0u) {
@@ -676,7 +677,7 @@ struct GeneralSim {
         }
     }
 
-    __device__ void pool_release(uint32_t pid, uint32_t amount)             // :561-605
+    __device__ __noinline__ void pool_release(uint32_t pid, uint32_t amount)             // :561-605
     {
         const uint32_t k = st->holders.find(pid + 1u);
         if (k != 0u && (uint32_t)st->holders.slot[k].arg == amount) {
@@ -690,7 +691,7 @@ struct GeneralSim {
         pool_signal();
     }
 
-    __device__ void pool_drop_holder(uint32_t pid)                          // :98-121
+    __device__ __noinline__ void pool_drop_holder(uint32_t pid)                          // :98-121
     {
         const uint32_t k = st->holders.find(pid + 1u);
         if (k != 0u) {

@@ -65,7 +65,7 @@ __device__ void guarded_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32
         for (;;) {
             {
                 const double mean = (p.kind == 0u) ? t.put_mean : (p.kind == 1u) ? t.get_mean : 1.0;
-                s.hold_begin(pid, s.rng.exponential(*s.hot, mean));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, mean));
             }
             p.pc = 1u;
             return;

@@ -106,6 +106,11 @@ struct HarborArgs {
     double   *trace_time;
 };
 
+// Member functions come in two bindings (the `_out` / `_impl` pairs below): out of line for the
+// lane-per-trial kernel - 32 trials share the instruction stream, and lanes that reach the same
+// routine from different call sites RECONVERGE inside one out-of-line copy (3.9e8 -> 4.6e8
+// events/s) - and inline for the warp-per-trial kernel, where one lane runs alone and a call is
+// pure latency (2.8e8 -> 3.4e8).  Measured on B200, profiles/r01_harbor.md.
 template <class State, bool IN_SHARED>
 struct HarborSim {
     State *gst;                 // HBM-resident state (lane per trial)
@@ -138,7 +143,9 @@ struct HarborSim {
         return key;
     }
 
-    __device__ void await_push(HarborProc &p, uint32_t type, uint32_t ref)
+    __device__ __noinline__ void await_push_out(HarborProc &p, uint32_t type, uint32_t ref) { return await_push_impl(p, type, ref); }
+    __device__ __forceinline__ void await_push(HarborProc &p, uint32_t type, uint32_t ref) { if (IN_SHARED) return await_push_impl(p, type, ref); else return await_push_out(p, type, ref); }
+    __device__ __forceinline__ void await_push_impl(HarborProc &p, uint32_t type, uint32_t ref)
     {
         if (p.n_awaits >= 2u) {
             S().status |= TRIAL_ERR_PROC_OVERFLOW;
@@ -151,7 +158,9 @@ struct HarborSim {
         p.n_awaits++;
     }
 
-    __device__ void await_remove(HarborProc &p, uint32_t type, bool any, uint32_t ref)
+    __device__ __noinline__ void await_remove_out(HarborProc &p, uint32_t type, bool any, uint32_t ref) { return await_remove_impl(p, type, any, ref); }
+    __device__ __forceinline__ void await_remove(HarborProc &p, uint32_t type, bool any, uint32_t ref) { if (IN_SHARED) return await_remove_impl(p, type, any, ref); else return await_remove_out(p, type, any, ref); }
+    __device__ __forceinline__ void await_remove_impl(HarborProc &p, uint32_t type, bool any, uint32_t ref)
     {
         for (uint32_t k = 0u; k < p.n_awaits; k++) {
             if (p.await_type[k] == type && (any || p.await_ref[k] == ref)) {
@@ -165,7 +174,9 @@ struct HarborSim {
         }
     }
 
-    __device__ void hold_begin(uint32_t pid, double dur)        // src/cmb_process.c:262-273
+    __device__ __noinline__ void hold_begin_out(uint32_t pid, double dur) { return hold_begin_impl(pid, dur); }
+    __device__ __forceinline__ void hold_begin(uint32_t pid, double dur) { if (IN_SHARED) return hold_begin_impl(pid, dur); else return hold_begin_out(pid, dur); }
+    __device__ __forceinline__ void hold_begin_impl(uint32_t pid, double dur)        // src/cmb_process.c:262-273
     {
         HarborProc &p = S().proc[pid];
         p.hold_handle = schedule(ACT_WAKE_TIME, pid, now + dur);
@@ -173,7 +184,11 @@ struct HarborSim {
     }
 
     template <class Guard>
-    __device__ void wait_begin(Guard &g, uint32_t gid, uint32_t pid)    // src/cmb_resourceguard.c:125-152
+    __device__ __noinline__ void wait_begin_out(Guard &g, uint32_t gid, uint32_t pid) { return wait_begin_impl(g, gid, pid); }
+    template <class Guard>
+    __device__ __forceinline__ void wait_begin(Guard &g, uint32_t gid, uint32_t pid) { if (IN_SHARED) return wait_begin_impl(g, gid, pid); else return wait_begin_out(g, gid, pid); }
+    template <class Guard>
+    __device__ __forceinline__ void wait_begin_impl(Guard &g, uint32_t gid, uint32_t pid)    // src/cmb_resourceguard.c:125-152
     {
         HarborProc &p = S().proc[pid];
         p.guard_key = ++S().guard_seq;
@@ -200,7 +215,11 @@ struct HarborSim {
 
     // one pass of cmi_pool_acquire_inner's loop (no pre-emption): true when the claim is filled
     template <class Guard>
-    __device__ bool pool_grab(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held)
+    __device__ __noinline__ bool pool_grab_out(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held) { return pool_grab_impl(p, g, rem, held); }
+    template <class Guard>
+    __device__ __forceinline__ bool pool_grab(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held) { if (IN_SHARED) return pool_grab_impl(p, g, rem, held); else return pool_grab_out(p, g, rem, held); }
+    template <class Guard>
+    __device__ __forceinline__ bool pool_grab_impl(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held)
     {
         const uint32_t available = p.cap - p.in_use;
         if (available >= rem) {
@@ -221,7 +240,11 @@ struct HarborSim {
     }
 
     template <class Guard>
-    __device__ void pool_release(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held)   // :561-605
+    __device__ __noinline__ void pool_release_out(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held) { return pool_release_impl(p, g, amount, held); }
+    template <class Guard>
+    __device__ __forceinline__ void pool_release(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held) { if (IN_SHARED) return pool_release_impl(p, g, amount, held); else return pool_release_out(p, g, amount, held); }
+    template <class Guard>
+    __device__ __forceinline__ void pool_release_impl(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held)   // :561-605
     {
         held -= (uint8_t)amount;
         p.in_use -= amount;
@@ -238,7 +261,9 @@ struct HarborSim {
     }
 
     // cmb_condition_signal, src/cmb_condition.c:120-167
-    __device__ uint32_t harbormaster_signal()
+    __device__ __noinline__ uint32_t harbormaster_signal_out() { return harbormaster_signal_impl(); }
+    __device__ __forceinline__ uint32_t harbormaster_signal() { if (IN_SHARED) return harbormaster_signal_impl(); else return harbormaster_signal_out(); }
+    __device__ __forceinline__ uint32_t harbormaster_signal_impl()
     {
         auto &cv = S().harbormaster;
         uint32_t hit[State::GUARD];
@@ -256,7 +281,9 @@ struct HarborSim {
         return cnt;
     }
 
-    __device__ void davyjones_signal()
+    __device__ __noinline__ void davyjones_signal_out() { return davyjones_signal_impl(); }
+    __device__ __forceinline__ void davyjones_signal() { if (IN_SHARED) return davyjones_signal_impl(); else return davyjones_signal_out(); }
+    __device__ __forceinline__ void davyjones_signal_impl()
     {
         auto &cv = S().davyjones;
         uint32_t hit[3];
@@ -272,7 +299,9 @@ struct HarborSim {
         }
     }
 
-    __device__ double pert(double min, double mode, double max)
+    __device__ __noinline__ double pert_out(double min, double mode, double max) { return pert_impl(min, mode, max); }
+    __device__ __forceinline__ double pert(double min, double mode, double max) { if (IN_SHARED) return pert_impl(min, mode, max); else return pert_out(min, mode, max); }
+    __device__ __forceinline__ double pert_impl(double min, double mode, double max)
     {
         return rnd_PERT_mod(rng, *hot, min, mode, max, 4.0);
     }
@@ -280,7 +309,9 @@ struct HarborSim {
     __device__ void body(uint32_t pid);
 
     // cmb_process_stop, src/cmb_process.c:698-723
-    __device__ void stop(uint32_t pid)
+    __device__ __noinline__ void stop_out(uint32_t pid) { return stop_impl(pid); }
+    __device__ __forceinline__ void stop(uint32_t pid) { if (IN_SHARED) return stop_impl(pid); else return stop_out(pid); }
+    __device__ __forceinline__ void stop_impl(uint32_t pid)
     {
         HarborProc &p = S().proc[pid];
         if (p.status != PROC_RUNNING) {

@@ -122,7 +122,7 @@ acquired:
                 p.held += p.req;
                 t.c[rat ? 1 : 0] += 1u;
                 preempt_check(s, t, pid);
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
                 p.pc = 2u;
                 return;
     case 2:
@@ -145,7 +145,7 @@ acquired:
                 preempt_take_signal(s, t, pid, sig);
             }
             preempt_check(s, t, pid);
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 3u;
             return;
     case 3:
@@ -163,7 +163,7 @@ __device__ void preempt_cat(GeneralSim &s, uint32_t pid, int32_t sig)
     switch (p.pc) {
     case 0:
         for (;;) {
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 1u;
             return;
     case 1:

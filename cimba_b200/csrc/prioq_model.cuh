@@ -78,7 +78,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
     case 0:
         if (pid == PRIOQ_PROCS) {                       // nuisance
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
                 p.pc = 10u;
                 return;
     case 10:
@@ -93,7 +93,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
         }
         if (pid < 2u) {                                 // producer
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, t.put_mean));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.put_mean));
                 p.pc = 20u;
                 return;
     case 20:
@@ -128,7 +128,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
         }
         if (pid == 2u) {                                // consumer
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, t.get_mean));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.get_mean));
                 p.pc = 30u;
                 return;
     case 30:
@@ -162,7 +162,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
         }
         if (pid == 3u) {                                // shuffler
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.5));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.5));
                 p.pc = 40u;
                 return;
     case 40:
@@ -188,7 +188,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
         }
         if (pid == 4u) {                                // tide
             for (;;) {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
                 p.pc = 50u;
                 return;
     case 50:
@@ -218,7 +218,7 @@ __device__ void prioq_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_t
                     t.c[5] += 1u;
                 }
             }
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 61u;
             return;
     case 61:

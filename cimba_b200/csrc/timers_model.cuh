@@ -43,12 +43,12 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
     // ---- patients (t_patient_body)
     case 0:
         for (;;) {
-            s.hold_begin(pid, s.rng.exponential(*s.hot, t.put_mean));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.put_mean));
             p.pc = 1u;
             return;
     case 1:
             timers_note(t, s.hold_end(pid, sig));
-            p.timer = s.timer_add(pid, s.rng.exponential(*s.hot, __dmul_rn(2.0, t.get_mean)), (int32_t)SIG_TIMEOUT);
+            p.timer = s.timer_add(pid, gp_exponential(s.rng, *s.hot, __dmul_rn(2.0, t.get_mean)), (int32_t)SIG_TIMEOUT);
             if (st->tool_holder == NO_HOLDER) {         // cmb_resource_acquire, src/cmb_resource.c:191-229
                 st->tool_holder = pid;
                 p.holds_tool = 1u;
@@ -69,8 +69,8 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                 (void)s.timer_cancel(pid, p.timer);
                 t.c[0] += 1u;
                 p.stamp = s.now;
-                (void)s.timer_add(pid, s.rng.exponential(*s.hot, 3.0), TIMERS_SIG_ALARM);
-                s.hold_begin(pid, s.rng.exponential(*s.hot, t.get_mean));
+                (void)s.timer_add(pid, gp_exponential(s.rng, *s.hot, 3.0), TIMERS_SIG_ALARM);
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.get_mean));
                 p.pc = 3u;
                 return;
     case 3:
@@ -81,7 +81,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                 s.tool_signal();
                 t.sum_wait = __dadd_rn(t.sum_wait, __dsub_rn(s.now, p.stamp));
                 s.timers_clear(pid);                    // cmb_process_timer_set = clear + add
-                (void)s.timer_add(pid, s.rng.exponential(*s.hot, 0.3), TIMERS_SIG_DOZE);
+                (void)s.timer_add(pid, gp_exponential(s.rng, *s.hot, 0.3), TIMERS_SIG_DOZE);
                 p.pc = 4u;                              // cmb_process_yield
                 return;
     case 4:
@@ -103,7 +103,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
         st->clerk_start_pending = 0u;
         p.jobs = (int32_t)s.rng.dice(2, 5);
         for (p.job = 0; p.job < p.jobs; p.job++) {
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 1u;
             return;
     case 11:
@@ -130,7 +130,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
     case 21:
             if (sig == (int32_t)SIG_SUCCESS) {
                 t.c[2] += 1u;
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 0.5));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 0.5));
                 p.pc = 2u;
                 return;
     case 22:
@@ -148,12 +148,12 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
     case 30:
         for (;;) {
             {
-                const double when = __dadd_rn(s.now, s.rng.exponential(*s.hot, 2.0));
+                const double when = __dadd_rn(s.now, gp_exponential(s.rng, *s.hot, 2.0));
                 const int32_t pri = (int32_t)s.rng.dice(-2, 2);
                 p.bell = s.schedule(ACT_BELL, SUBJ_MODEL, 0, when, pri);
                 st->bell = p.bell;
             }
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 0.7));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 0.7));
             p.pc = 1u;
             return;
     case 31:
@@ -161,7 +161,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
             if (s.event_is_scheduled(p.bell)) {
                 const long long op = s.rng.dice(0, 3);
                 if (op == 0) {
-                    (void)s.event_reschedule(p.bell, __dadd_rn(s.now, s.rng.exponential(*s.hot, 1.0)));
+                    (void)s.event_reschedule(p.bell, __dadd_rn(s.now, gp_exponential(s.rng, *s.hot, 1.0)));
                     t.c[5] += 1u;
                 }
                 else if (op == 1) {
@@ -198,7 +198,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                 }
             }
             else {
-                s.hold_begin(pid, s.rng.exponential(*s.hot, 0.5));
+                s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 0.5));
                 p.pc = 2u;
                 return;
     case 42:
@@ -219,7 +219,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
             else {
                 timers_note(t, sig);
             }
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 0.8));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 0.8));
             p.pc = 2u;
             return;
     case 52:
@@ -228,7 +228,7 @@ __device__ void timers_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
     // ---- nuisance (t_nuisance_body)
     case 60:
         for (;;) {
-            s.hold_begin(pid, s.rng.exponential(*s.hot, 1.0));
+            s.hold_begin(pid, gp_exponential(s.rng, *s.hot, 1.0));
             p.pc = 1u;
             return;
     case 61:
