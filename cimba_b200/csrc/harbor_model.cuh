@@ -101,6 +101,7 @@ struct HarborArgs {
     uint32_t *status, *max_queue;
     uint64_t *counters;
     void     *state;            // [num_trials] HarborState (lane per trial); unused by the on-chip kernel
+    uint32_t  repair;           // lane-per-trial kernel: only re-run trials whose status word is non-zero
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
@@ -663,6 +664,9 @@ harbor_kernel(const HarborArgs a)
     const uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (trial >= a.num_trials) {
         return;
+    }
+    if (a.repair && a.status[trial] == TRIAL_OK) {
+        return;                                         // the on-chip pass finished this one
     }
     harbor_trial<TRACE, HarborState, false>(a, trial, &((HarborState *)a.state)[trial], 0u, &hot);
 }

@@ -73,7 +73,10 @@ extern "C" {
                                     * cmb_resourcepools, a departure process on a second condition, an end event at t = num_objects
                                     * hours.  arr_mean = mean inter-arrival time, srv_mean = mean unloading time of a small ship.
                                     * counters: ships through (small, large), their mean system times, tug / berth history summaries,
-                                    * harbormaster reactivations - with the golden seed and 873 600 h exactly test/reference/condition.txt */
+                                    * harbormaster reactivations - with the golden seed and 873 600 h exactly test/reference/condition.txt.
+                                    * variant 0: up to 16 384 trials run one per WARP with the state in shared memory (tables for 43 ships
+                                    * alive) and any trial that outgrows them is re-run one per lane with the HBM tables (120 ships);
+                                    * 1 = warp-per-trial only, 2 = lane-per-trial only */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -5,7 +5,7 @@ import torch
 import cimba_b200 as cb
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 8736
-for variant in (0, 1):
+for variant in (0, 1, 2):
     cb.run_trials(T, arr_mean=2.0, srv_mean=8.0, num_objects=100, master_seed=1, model=cb.MODEL_HARBOR, servers=10, variant=variant)
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -545,7 +545,7 @@ def test_harbor_warp_per_trial_in_shared_memory_matches_oracle(cb, port, tugs, a
     assert [int(res.max_queue[i]) for i in keep] == [want[i].max_queue for i in keep]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_harbor_pop_order_bit_exact(cb, port, variant):
     n, cap, dur = 16, 12000, 1500
     res = cb.run_trials(n, arr_mean=2.0, srv_mean=8.0, num_objects=dur, master_seed=1010,
@@ -593,10 +593,25 @@ def test_harbor_reproduces_the_reference_golden_file_on_device(cb, golden):
 
 def test_harbor_ship_table_overflow_is_reported(cb):
     """More ships alive than the device table holds: flagged in status, never silent."""
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         res = cb.run_trials(8, arr_mean=0.7, srv_mean=8.0, num_objects=1000, master_seed=3, model=cb.MODEL_HARBOR,
                             servers=10, variant=variant)
         assert int((res.status != 0).sum()) == 8
+
+
+def test_harbor_default_repairs_trials_that_outgrow_the_on_chip_tables(cb, port):
+    """(5 tugs, 1.5 h between ships, 10 h unloading): up to 108 ships alive - more than the 43 the shared-memory
+    tables hold, fewer than the 120 of the HBM tables.  The default runs warp-per-trial first and re-runs
+    the overflowed trials lane-per-trial: every trial ends up exact, none is flagged."""
+    n = 96
+    want = run_trials(port, "port", 10, 5, KAT_SEED, 0, n, 777, 1.5, 10.0)
+    only_chip = cb.run_trials(n, arr_mean=1.5, srv_mean=10.0, num_objects=777, master_seed=KAT_SEED,
+                              model=cb.MODEL_HARBOR, servers=5, variant=1)
+    assert int((only_chip.status != 0).sum()) > 0
+    res = cb.run_trials(n, arr_mean=1.5, srv_mean=10.0, num_objects=777, master_seed=KAT_SEED,
+                        model=cb.MODEL_HARBOR, servers=5)
+    _compare(res, want, "harbor repair")
+    assert _counts(res.counters) == [w.counters() for w in want]
 
 
 # ------------------------------------------------------------------ hold model (warp per trial, 32-ary heap)
