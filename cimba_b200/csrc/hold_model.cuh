@@ -115,6 +115,9 @@ struct WarpHeap {
                 sts_u32(info + i * 4u, lds_u32(info + w * 4u));
             }
             i = w;
+            // the next round's store goes to a slot this round read; the warp-wide REDUX above already
+            // orders them (it consumes the loaded values), this makes the ordering explicit
+            __syncwarp();
         }
         if (lane == 0u) {
             sts_u64(t + i * 8u, mt);
@@ -199,6 +202,7 @@ hold_kernel(const HoldArgs a)
             const unsigned long long rt = lds_u64(h.t);
             const uint32_t rk = lds_u32(h.key);
             const uint32_t ri = lds_u32(h.info);
+            __syncwarp();                               // every lane has the root before lane 0 overwrites it below
             now = __longlong_as_double((long long)rt);
             if (TRACE) {
                 if (lane == 0u && pops < a.trace_cap) {
