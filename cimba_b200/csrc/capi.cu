@@ -23,6 +23,7 @@
 #include "mm1_fast.cuh"
 #include "gg1_fast.cuh"
 #include "pool_model.cuh"
+#include "pool_fast.cuh"
 #include "guarded_model.cuh"
 #include "preempt_model.cuh"
 #include "buffer_model.cuh"
@@ -322,11 +323,15 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         pa.trace_time = job->trace_time;
         const uint64_t blocks = (job->num_trials + POOL_BLOCK - 1) / POOL_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
-        if (trace) {
-            pool_kernel<true><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+        if (job->variant == 1) {                        // the readable formulation, pool_model.cuh
+            if (trace) pool_kernel<true><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+            else       pool_kernel<false><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+        }
+        else if (trace) {
+            pool_fast_kernel<true><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
         }
         else {
-            pool_kernel<false><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
+            pool_fast_kernel<false><<<(unsigned)blocks, POOL_BLOCK, 0, st>>>(pa);
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();

@@ -272,21 +272,24 @@ def test_full_size_trial_properties(cb, golden):
 
 # ------------------------------------------------------------------ M/M/c (cmb_resourcepool)
 
-@pytest.mark.parametrize("servers,arr,srv", [(8, 1 / 6.4, 1.0), (3, 0.5, 1.0), (1, 1 / 0.9, 1.0), (2, 0.55, 1.0)])
-def test_pool_trials_match_oracle(cb, port, servers, arr, srv):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("servers,arr,srv", [(8, 1 / 6.4, 1.0), (3, 0.5, 1.0), (1, 1 / 0.9, 1.0), (2, 0.55, 1.0), (12, 0.1, 1.0)])
+def test_pool_trials_match_oracle(cb, port, servers, arr, srv, variant):
+    """variant 0 = the predicated kernel (pool_fast.cuh), 1 = the readable formulation (pool_model.cuh)."""
     n, nobj = 130, 4000
     res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=KAT_SEED,
-                        model=cb.MODEL_MMC, servers=servers)
+                        model=cb.MODEL_MMC, servers=servers, variant=variant)
     want = run_trials(port, "port", 2, servers, KAT_SEED, 0, n, nobj, arr, srv)
     _compare(res, want, ("mmc", servers))
     # process structs ever created (reference: 62 for the 10^6 KAT) = most customers alive at once
     assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
 
 
-def test_pool_pop_order_bit_exact(cb, port):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_pool_pop_order_bit_exact(cb, port, variant):
     n, cap, nobj = 20, 6000, 2000
     res = cb.run_trials(n, arr_mean=1 / 6.4, srv_mean=1.0, num_objects=nobj, master_seed=31,
-                        model=cb.MODEL_MMC, servers=8, trace_cap=cap)
+                        model=cb.MODEL_MMC, servers=8, trace_cap=cap, variant=variant)
     keys, times = res.trace_key.cpu().numpy(), res.trace_time.cpu().numpy()
     for i in range(n):
         r, k, t = trace_trial(port, "port", 2, 8, cb.fmix64(31, i), nobj, 1 / 6.4, 1.0, cap)
@@ -303,10 +306,11 @@ def test_pool_tiny_object_counts(cb, port, nobj):
     _compare(res, want, ("mmc", nobj))
 
 
-def test_pool_overload_spills_wait_list(cb, port):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_pool_overload_spills_wait_list(cb, port, variant):
     """rho > 1: hundreds of customers queue at the guard (HBM spill ring), still bit-exact."""
     res = cb.run_trials(64, arr_mean=0.1, srv_mean=1.0, num_objects=1800, master_seed=2,
-                        model=cb.MODEL_MMC, servers=8)
+                        model=cb.MODEL_MMC, servers=8, variant=variant)
     want = run_trials(port, "port", 2, 8, 2, 0, 64, 1800, 0.1, 1.0)
     assert max(w.max_queue for w in want) > 150
     _compare(res, want, "mmc-spill")
