@@ -67,16 +67,21 @@ pool_fast_kernel(const PoolArgs a)
     const uint32_t capacity = (uint32_t)a.servers;
     const uint32_t quota = (uint32_t)a.num_objects;
 
+    // one raw output of look-ahead with its hot-path variate already formed (mm1_fast.cuh): the table
+    // look-up and the 64-bit -> double conversion leave the pop -> push chain; stream order unchanged
+    uint64_t u_next = 0u;
+    double e_next = 0.0;
     if (exists) {
         arr_mean = a.arr_mean[trial];
         srv_mean = a.srv_mean[trial];
         rng.seed(fmix64(a.master_seed, a.first_trial + trial));
         fel.schedule(ACT_START, TAG_GENERATOR, 0.0, 0.0);       // cmb_process_start(source)
+        u_next = rng.next();
+        e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
     }
 
     // bit 0 alive, bit 1 parked (a draw waits for the ziggurat slow path)
     uint32_t flags = exists ? 1u : 0u;
-    uint64_t parked_u = 0u;
     uint32_t parked_tag = 0u;
     double parked_pay = 0.0;
     uint32_t step = 0u;
@@ -171,20 +176,25 @@ pool_fast_kernel(const PoolArgs a)
 
         // ---------------- the hold: generator's next inter-arrival, or the customer's service
         const bool draw = got | (go & is_gen & (produced < quota));
-        if (draw) {
-            const uint64_t u = rng.next();
+        {
             const uint32_t tag = is_gen ? TAG_GENERATOR : TAG_CUSTOMER;
             const double keep = is_gen ? 0.0 : pay;     // the customer's arrival stamp travels with its event
-            if (Sfc64::exp_is_hot(u)) {
-                const double mean = is_gen ? arr_mean : srv_mean;
-                const double dur = __dmul_rn(mean, __dmul_rn(lds_f64(tab + ((uint32_t)u & 0xffu) * 8u), __ull2double_rn(u)));
-                if (!fel.schedule(ACT_WAKE_TIME, tag, __dadd_rn(now, dur), keep)) {
-                    status |= TRIAL_ERR_FEL_OVERFLOW;
-                }
+            const bool hot = Sfc64::exp_is_hot(u_next);
+            const bool push = draw & hot;
+            const double when = __dadd_rn(now, __dmul_rn(is_gen ? arr_mean : srv_mean, e_next));
+            const uint32_t k = fel.issued + (push ? 1u : 0u);
+            fel.issued = k;
+            const uint32_t at = min(fel.count, (uint32_t)POOL_FEL_CAP - 1u);
+            if (push & (fel.count >= (uint32_t)POOL_FEL_CAP)) status |= TRIAL_ERR_FEL_OVERFLOW;
+            if (push) {
+                EventList<POOL_FEL_CAP>::st_head(fel.head + at * fel.hstride, when, (k << 2) | ACT_WAKE_TIME, tag);
+                sts_f64(fel.pay + at * fel.pstride, keep);
+                fel.count = min(fel.count + 1u, (uint32_t)POOL_FEL_CAP);
+                u_next = rng.next();                    // refill the look-ahead
+                e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
             }
-            else {
+            if (draw & !hot) {
                 flags |= 2u;
-                parked_u = u;
                 parked_tag = tag;
                 parked_pay = keep;
             }
@@ -209,11 +219,13 @@ pool_fast_kernel(const PoolArgs a)
             if (__popc(pm) >= POOL_COLD_BATCH || pm == am) {
                 if (flags & 2u) {
                     const double mean = parked_tag == TAG_GENERATOR ? arr_mean : srv_mean;
-                    const double dur = __dmul_rn(mean, rng.exp_cold(parked_u));
+                    const double dur = __dmul_rn(mean, rng.exp_cold(u_next));
                     if (!fel.schedule(ACT_WAKE_TIME, parked_tag, __dadd_rn(now, dur), parked_pay)) {
                         status |= TRIAL_ERR_FEL_OVERFLOW;
                     }
                     flags &= ~2u;
+                    u_next = rng.next();
+                    e_next = __dmul_rn(lds_f64(tab + ((uint32_t)u_next & 0xffu) * 8u), __ull2double_rn(u_next));
                 }
             }
         }
