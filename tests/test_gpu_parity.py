@@ -712,3 +712,23 @@ def test_host_buffer_api_returns_counters_for_every_model(cb, port):
         assert int(exp["status"].sum()) == 0
         if model == cb.MODEL_HARBOR:
             assert exp["max_queue"].tolist() == [w.max_queue for w in want]
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 9])
+def test_survey_known_answers_on_device(cb, golden, model):
+    """SURVEY.md section 8c's full-size known answers, produced by the unmodified reference with the explicit
+    seed 0x34f05c64d7ad598f (M/M/1: 2 099 622 events, t_end 1109668.9795469602, sum_wait 9895522.5628889836;
+    M/M/c: 3 464 151 events; G/G/1: 2 292 998 events), run on the GPU with the master seed whose trial 0
+    maps to that seed (cmb_random_fmix64 is a bijection)."""
+    t = [x for x in golden["trials"] if x["model"] == model and x["num_objects"] == 1_000_000][0]
+    master = _inverse_fmix64(t["seed"])
+    res = cb.run_trials(1, arr_mean=float.fromhex(t["arr_mean"]), srv_mean=float.fromhex(t["srv_mean"]),
+                        num_objects=1_000_000, master_seed=master, model=model, servers=t["servers"])
+    assert int(res.status[0]) == 0
+    assert (int(res.events[0]), int(res.objects[0])) == (t["events"], t["objects"])
+    assert float.hex(float(res.t_end[0])) == t["t_end"] and float.hex(float(res.sum_wait[0])) == t["sum_wait"]
+    if model == 0:
+        assert int(res.events[0]) == 2_099_622 and float(res.t_end[0]) == 1109668.9795469602
+        assert float(res.sum_wait[0]) == 9895522.5628889836
+    if model == 9:
+        assert _counts(res.counters)[0] == t["counters"]
