@@ -33,9 +33,15 @@ CONFIGS = [
     ("HOLD 1000 processes 4096 trials (config 5's event-list shape; objects = duration/1000)", cb.MODEL_HOLD, 4096, 1.0, 1.0, 1000),
     ("HARBOR test_condition.c 4096 trials (config 5's cmb_condition shape; objects = hours/10)", cb.MODEL_HARBOR, 4096, 2.0, 8.0, 10),
     ("HARBOR test_condition.c 65536 trials", cb.MODEL_HARBOR, 65536, 2.0, 8.0, 10),
+    ("GUARDED bounded queue under interrupts, 65536 trials (objects = duration/100)", cb.MODEL_GUARDED, 65536, 1.0, 1.0, 10),
+    ("PREEMPT resourcepool with pre-emption, 65536 trials", cb.MODEL_PREEMPT, 65536, 1.0, 1.0, 20),
+    ("BUFFER + resource, 65536 trials", cb.MODEL_BUFFER, 65536, 1.0, 1.0, 10),
+    ("PRIOQ + condition, 65536 trials", cb.MODEL_PRIOQ, 65536, 1.0, 1.0, 8),
+    ("TIMERS waits observers, 65536 trials", cb.MODEL_TIMERS, 65536, 1.0, 0.6, 1),
     ("HARBOR warp per trial, state in shared memory (variant 1), 4096 trials", cb.MODEL_HARBOR, 4096, 2.0, 8.0, 10, 1),
     ("HARBOR warp per trial, state in shared memory (variant 1), 65536 trials", cb.MODEL_HARBOR, 65536, 2.0, 8.0, 10, 1),
 ]
+GENERAL = (cb.MODEL_GUARDED, cb.MODEL_PREEMPT, cb.MODEL_BUFFER, cb.MODEL_PRIOQ, cb.MODEL_TIMERS)
 dev = torch.device("cuda", 0)
 for name, model, n, arr, srv, servers, *rest in CONFIGS:
     variant = rest[0] if rest else 0
@@ -44,7 +50,8 @@ for name, model, n, arr, srv, servers, *rest in CONFIGS:
     a = torch.full((n,), arr, dtype=torch.float64, device=dev)
     s = torch.full((n,), srv, dtype=torch.float64, device=dev)
     bufs = TrialBuffers(n, dev, 0, model, servers, variant)
-    size = args.objects // 1000 if model == cb.MODEL_HOLD else (args.objects // 10 if model == cb.MODEL_HARBOR else args.objects)
+    size = args.objects // 1000 if model == cb.MODEL_HOLD else (args.objects // 10 if model == cb.MODEL_HARBOR else
+                                                          (args.objects // 100 if model in GENERAL else args.objects))
     run = lambda: cb.launch_trials(a, s, num_objects=size, master_seed=0x34F05C64D7AD598F,
                                    model=model, servers=servers, buffers=bufs, variant=variant)
     run()
