@@ -83,7 +83,7 @@ uint64_t deep_row_entries(int workers)
 bool is_general_model(int m)
 {
     return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
-           m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_TIMERS;
+           m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_TIMERS || m == CIMBA_B200_MODEL_GUARDED_RECORDED;
 }
 
 // ---------------------------------------------------------------- RNG KAT kernel
@@ -363,6 +363,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.max_queue = job->max_queue;
         ga.counters = job->counters;
         ga.state = (GeneralState *)job->workspace;
+        ga.record = job->model == CIMBA_B200_MODEL_GUARDED_RECORDED ? 1u : 0u;
         ga.trace_cap = job->trace_cap;
         ga.trace_key = job->trace_key;
         ga.trace_time = job->trace_time;

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "general.cuh"
+#include "summary.cuh"
 
 namespace cimba_b200 {
 
@@ -35,6 +36,7 @@ struct GuardedArgs {
     uint32_t *status, *max_queue;
     uint64_t *counters;                // [num_trials][8]
     GeneralState *state;               // [num_trials]
+    uint32_t  record;                  // model 11: fold the queue's history into a time-weighted summary
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
@@ -44,6 +46,8 @@ struct GuardedTally {
     uint64_t c[8];
     double   sum_wait;
     double   put_mean, get_mean;
+    uint32_t record;
+    TimeWeighted hist;                 // cmb_objectqueue_recording_start (test/test_objectqueue.c:191)
 };
 
 __device__ __forceinline__ void guarded_note(GuardedTally &t, int32_t sig, int which)
@@ -86,6 +90,7 @@ __device__ void guarded_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32
                     if (st->ring_len < st->ring_cap) {
                         st->ring[(st->ring_head + st->ring_len) % st->ring_cap] = p.stamp;
                         st->ring_len++;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->ring_len, s.now);
                         s.signal(0u, st->ring_len > 0u);
                         t.c[0] += 1u;
                         break;
@@ -107,6 +112,7 @@ __device__ void guarded_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32
                         const double stamp = st->ring[st->ring_head];
                         st->ring_head = (st->ring_head + 1u) % st->ring_cap;
                         st->ring_len--;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->ring_len, s.now);
                         s.signal(1u, st->ring_len < st->ring_cap);
                         t.c[1] += 1u;
                         t.sum_wait = __dadd_rn(t.sum_wait, __dsub_rn(s.now, stamp));
@@ -153,6 +159,11 @@ guarded_kernel(const GuardedArgs a)
     t.sum_wait = 0.0;
     t.put_mean = a.put_mean[trial];
     t.get_mean = a.get_mean[trial];
+    t.record = a.record;
+    t.hist.start();
+    if (t.record) {
+        t.hist.sample(0.0, 0.0);                        // the empty queue at t = 0
+    }
 
     st->fel.clear();
     st->guard[0].clear();
@@ -231,6 +242,11 @@ guarded_kernel(const GuardedArgs a)
     }
 
     t.c[6] = st->ring_len;
+    if (t.record) {                                     // recording_stop + cmb_timeseries_summarize
+        t.hist.sample((double)st->ring_len, s.now);
+        t.c[6] = (uint64_t)__double_as_longlong(t.hist.acc.m1);
+        deepest = (uint32_t)t.hist.acc.count;
+    }
     if (a.events)    a.events[trial] = pops;
     if (a.objects)   a.objects[trial] = t.c[1];
     if (a.t_end)     a.t_end[trial] = s.now;

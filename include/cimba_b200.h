@@ -77,6 +77,10 @@ extern "C" {
                                     * variant 0: up to 16 384 trials run one per WARP with the state in shared memory (tables for 43 ships
                                     * alive) and any trial that outgrows them is re-run one per lane with the HBM tables (120 ships);
                                     * 1 = warp-per-trial only, 2 = lane-per-trial only */
+#define CIMBA_B200_MODEL_GUARDED_RECORDED 11 /* MODEL_GUARDED with the queue's history on = test/test_objectqueue.c as it stands:
+                                    * counters[6] = time-weighted mean queue length (bits), max_queue = history samples with a
+                                    * duration; capacity 10, means 1, 1e6 time units and the golden seed give
+                                    * test/reference/objectqueue.txt's "N 5689021  Mean 5.008" */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

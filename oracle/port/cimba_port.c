@@ -1472,6 +1472,10 @@ typedef struct gsim {
     double  *ring;
     uint64_t cap, head, len;
     double   put_mean, get_mean;
+    bool     recording;                 /* model 11: the queue's history, fused as in record_sample() above */
+    uint64_t rec_n;
+    double   rec_x, rec_t;
+    port_wsummary hist;
     gproc    worker[G_WORKERS], nuisance;
     port_result *res;
     uint64_t trace_cap, *trace_key;
@@ -1606,6 +1610,20 @@ static void g_signal(gsim *s, heap *g, bool demand_holds)
     }
 }
 
+/* record_sample of the bounded queue, src/cmb_objectqueue.c:151-159 */
+static void g_record(gsim *s)
+{
+    if (!s->recording) {
+        return;
+    }
+    if (s->rec_n > 0u) {
+        (void)port_wsummary_add(&s->hist, s->rec_x, s->now - s->rec_t);
+    }
+    s->rec_x = (double)s->len;
+    s->rec_t = s->now;
+    s->rec_n++;
+}
+
 static void g_note(gsim *s, int64_t sig, unsigned which)
 {
     if (sig != SIG_SUCCESS) {
@@ -1642,6 +1660,7 @@ static void g_body(gsim *s, gproc *p, int64_t sig)
                     if (s->len < s->cap) {
                         s->ring[(s->head + s->len) % s->cap] = p->stamp;
                         s->len++;
+                        g_record(s);
                         g_signal(s, &s->front, s->len > 0u);
                         s->res->counter[0] += 1u;
                         break;
@@ -1663,6 +1682,7 @@ static void g_body(gsim *s, gproc *p, int64_t sig)
                         const double stamp = s->ring[s->head];
                         s->head = (s->head + 1u) % s->cap;
                         s->len--;
+                        g_record(s);
                         g_signal(s, &s->rear, s->len < s->cap);
                         s->res->counter[1] += 1u;
                         s->res->sum_wait += s->now - stamp;
@@ -1695,7 +1715,7 @@ static void g_stop(gsim *s, gproc *p)
 
 static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
                         double put_mean, double get_mean, uint64_t trace_cap,
-                        uint64_t *trace_key, double *trace_time, port_result *out)
+                        uint64_t *trace_key, double *trace_time, port_result *out, bool record)
 {
     gsim *s = calloc(1, sizeof(*s));
     memset(out, 0, sizeof(*out));
@@ -1710,6 +1730,11 @@ static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
     heap_init(&s->front, 3u, guard_before);
     heap_init(&s->rear, 3u, guard_before);
     s->cap = (uint64_t)capacity;
+    if (record) {                                       /* cmb_objectqueue_recording_start: the empty queue at t = 0 */
+        s->recording = true;
+        port_wsummary_init(&s->hist);
+        g_record(s);
+    }
     s->ring = calloc(s->cap, sizeof(double));
 
     for (int i = 0; i < G_WORKERS; i++) {
@@ -1772,6 +1797,11 @@ static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
     out->t_end = s->now;
     out->counter[6] = s->len;
     out->objects = out->counter[1];
+    if (record) {                                       /* recording_stop + cmb_timeseries_summarize */
+        g_record(s);
+        memcpy(&out->counter[6], &s->hist.ds.m1, 8);
+        out->max_queue = s->hist.ds.count;
+    }
     heap_free(&s->fel);
     heap_free(&s->front);
     heap_free(&s->rear);
@@ -3832,9 +3862,9 @@ static void *worker(void *arg)
                         0u, NULL, NULL, &j->out[k]);
             continue;
         }
-        if (j->model == 3) {
+        if (j->model == 3 || j->model == 11) {
             run_guarded(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
-                        j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+                        j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k], j->model == 11);
             continue;
         }
         run_one(j->model, j->servers, port_fmix64(j->master_seed, j->first + k),
@@ -3893,8 +3923,8 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
         run_preempt(servers, seed, num_objects, trace_cap, trace_key, trace_time, out);
         return 0;
     }
-    if (model == 3) {
-        run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+    if (model == 3 || model == 11) {
+        run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out, model == 11);
         return 0;
     }
     run_one(model, servers, seed, num_objects, arr_mean, srv_mean,

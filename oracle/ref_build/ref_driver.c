@@ -287,6 +287,12 @@ static void run_guarded_trial(struct ref_trial *t)
     w->trl = t;
     w->queue = cmb_objectqueue_create();
     cmb_objectqueue_initialize(w->queue, "Queue", (uint64_t)t->servers);
+    if (t->model == 11) {
+        /* model 11 = model 3 with the queue's history on, exactly test/test_objectqueue.c:187-191: with
+         * capacity 10, both means 1, duration 1e6 and seed 0x34f05c64d7ad598f the time-weighted queue length
+         * is test/reference/objectqueue.txt's "N 5689021 Mean 5.008" */
+        cmb_objectqueue_recording_start(w->queue);
+    }
     for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
         w->worker[i] = cmb_process_create();
         const int64_t pri = cmb_random_dice(-5, 5);
@@ -303,6 +309,16 @@ static void run_guarded_trial(struct ref_trial *t)
 
     t->counter[6] = cmb_objectqueue_length(w->queue);
     t->objects = t->counter[1];
+    if (t->model == 11) {
+        /* counter[6] = mean queue length (bits), max_queue = samples with a duration */
+        cmb_objectqueue_recording_stop(w->queue);
+        struct cmb_wtdsummary ws;
+        cmb_wtdsummary_initialize(&ws);
+        (void)cmb_timeseries_summarize(cmb_objectqueue_history(w->queue), &ws);
+        const double mean = cmb_wtdsummary_mean(&ws);
+        memcpy(&t->counter[6], &mean, 8);
+        t->max_queue = cmb_wtdsummary_count(&ws);
+    }
     for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
         cmb_process_terminate(w->worker[i]);
         cmb_process_destroy(w->worker[i]);
@@ -1538,7 +1554,7 @@ static void run_trial(void *vt)
     else if (t->model == 4) {
         run_preempt_trial(t);
     }
-    else if (t->model == 3) {
+    else if (t->model == 3 || t->model == 11) {
         run_guarded_trial(t);
     }
     else if (t->model == 2) {
