@@ -51,18 +51,19 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                 }
             }
         }
-        if (pid < 2u) {                                 // filler: cmb_buffer_put
+        if (pid < t.fillers) {                          // filler: cmb_buffer_put
             for (;;) {
                 s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.put_mean));
                 p.pc = 20u;
                 return;
     case 20:
                 buffer_note(t, s.hold_end(pid, sig));
-                p.req = (uint32_t)s.rng.dice(1, 8);
+                p.req = (uint32_t)s.rng.dice(1, t.amount_max);
                 p.rem = p.req;
                 for (;;) {
                     if (st->buf_cap - st->buf_level >= p.rem) {
                         st->buf_level += p.rem;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->buf_level, s.now);   // record_sample, src/cmb_buffer.c:129-136
                         p.rem = 0u;
                         s.signal(0u, st->buf_level > 0u);
                         if (st->buf_level < st->buf_cap) {
@@ -74,6 +75,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                     else if (st->buf_level < st->buf_cap) {
                         const uint32_t grab = st->buf_cap - st->buf_level;
                         st->buf_level = st->buf_cap;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->buf_level, s.now);   // record_sample, src/cmb_buffer.c:129-136
                         p.rem -= grab;
                         s.signal(0u, st->buf_level > 0u);
                     }
@@ -94,18 +96,19 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                 }
             }
         }
-        if (pid < 4u) {                                 // drainer: cmb_buffer_get
+        if (pid < t.fillers + t.drainers) {             // drainer: cmb_buffer_get
             for (;;) {
                 s.hold_begin(pid, gp_exponential(s.rng, *s.hot, t.get_mean));
                 p.pc = 30u;
                 return;
     case 30:
                 buffer_note(t, s.hold_end(pid, sig));
-                p.rem = (uint32_t)s.rng.dice(1, 8);
+                p.rem = (uint32_t)s.rng.dice(1, t.amount_max);
                 p.held = 0u;                            // amount obtained so far
                 for (;;) {
                     if (st->buf_level >= p.rem) {
                         st->buf_level -= p.rem;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->buf_level, s.now);   // record_sample, src/cmb_buffer.c:129-136
                         p.held += p.rem;
                         s.signal(1u, st->buf_level < st->buf_cap);
                         if (st->buf_level > 0u) {
@@ -117,6 +120,7 @@ __device__ void buffer_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32_
                     else if (st->buf_level > 0u) {
                         const uint32_t grab = st->buf_level;
                         st->buf_level = 0u;
+                        if (t.record) time_weighted_sample(t.hist, (double)st->buf_level, s.now);   // record_sample, src/cmb_buffer.c:129-136
                         p.held += grab;
                         p.rem -= grab;
                         s.signal(1u, st->buf_level < st->buf_cap);
@@ -224,6 +228,14 @@ buffer_kernel(const GuardedArgs a)
     t.sum_wait = 0.0;
     t.put_mean = a.put_mean[trial];
     t.get_mean = a.get_mean[trial];
+    t.record = a.record;                                // model 12 = test/test_buffer.c as it stands
+    t.fillers = a.record ? 3u : 2u;
+    t.drainers = a.record ? 3u : 2u;
+    t.amount_max = a.record ? 15 : 8;
+    t.hist.start();
+    if (t.record) {
+        t.hist.sample(0.0, 0.0);                        // cmb_buffer_recording_start: level 0 at t = 0
+    }
 
     st->fel.clear();
     st->guard[0].clear();
@@ -304,6 +316,11 @@ buffer_kernel(const GuardedArgs a)
     }
 
     t.c[7] = st->buf_level;
+    if (t.record) {                                     // recording_stop + cmb_timeseries_summarize
+        t.hist.sample((double)st->buf_level, s.now);
+        t.c[4] = (uint64_t)__double_as_longlong(t.hist.acc.m1);
+        deepest = (uint32_t)t.hist.acc.count;
+    }
     if (a.events)    a.events[trial] = pops;
     if (a.objects)   a.objects[trial] = t.c[1];
     if (a.t_end)     a.t_end[trial] = s.now;

@@ -48,6 +48,8 @@ struct GuardedTally {
     double   put_mean, get_mean;
     uint32_t record;
     TimeWeighted hist;                 // cmb_objectqueue_recording_start (test/test_objectqueue.c:191)
+    uint32_t fillers, drainers;        // buffer models: 2 + 2 (model 5) or 3 + 3 (model 12 = test/test_buffer.c)
+    int32_t  amount_max;               // ... moving 1..8 or 1..15 units
 };
 
 __device__ __forceinline__ void guarded_note(GuardedTally &t, int32_t sig, int which)

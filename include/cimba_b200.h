@@ -81,6 +81,10 @@ extern "C" {
                                     * counters[6] = time-weighted mean queue length (bits), max_queue = history samples with a
                                     * duration; capacity 10, means 1, 1e6 time units and the golden seed give
                                     * test/reference/objectqueue.txt's "N 5689021  Mean 5.008" */
+#define CIMBA_B200_MODEL_BUFFER_RECORDED 12 /* test/test_buffer.c as it stands: three putters and three getters moving 1..15 units
+                                    * through a cmb_buffer of capacity `servers`, a nuisance, the level history on.  counters[4] =
+                                    * time-weighted mean level (bits), max_queue = history samples with a duration; capacity 10, means 1,
+                                    * 10 000 time units and the golden seed give test/reference/buffer.txt's "N 41876  Mean 4.980" */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -2204,8 +2204,28 @@ typedef struct bsim {
     bproc   *tool_holder;
     uint64_t cap, level;
     double   put_mean, get_mean;
+    int      fillers, drainers;         /* model 5: 2 + 2 (+ 2 tool workers); model 12 (test/test_buffer.c): 3 + 3 */
+    long     amount_max;                /* 8 / 15 */
+    bool     recording;                 /* model 12: the level history, fused as in record_sample() above */
+    uint64_t rec_n;
+    double   rec_x, rec_t;
+    port_wsummary hist;
     bproc    proc[B_PROCS + 1];
 } bsim;
+
+/* record_sample, src/cmb_buffer.c:129-136 */
+static void b_record(bsim *w)
+{
+    if (!w->recording) {
+        return;
+    }
+    if (w->rec_n > 0u) {
+        (void)port_wsummary_add(&w->hist, w->rec_x, w->s.now - w->rec_t);
+    }
+    w->rec_x = (double)w->level;
+    w->rec_t = w->s.now;
+    w->rec_n++;
+}
 
 static void b_note(bsim *w, int64_t sig)
 {
@@ -2235,18 +2255,19 @@ static void b_body(bsim *w, bproc *p, int64_t sig)
                 }
             }
         }
-        if (id < 2) {                                   /* filler */
+        if (id < w->fillers) {                          /* filler */
             for (;;) {
                 g_hold_begin(s, &p->g, port_exponential(&s->rng, w->put_mean));
                 p->g.pc = 20;
                 return;
     case 20:
                 b_note(w, g_hold_end(s, &p->g, sig));
-                p->want = (uint64_t)port_dice(&s->rng, 1, 8);
+                p->want = (uint64_t)port_dice(&s->rng, 1, w->amount_max);
                 p->rem = p->want;                       /* cmb_buffer_put: *amntp and rem_claim move together */
                 for (;;) {
                     if (w->cap - w->level >= p->rem) {
                         w->level += p->rem;
+                        b_record(w);
                         p->rem = 0u;
                         g_signal(s, &s->front, w->level > 0u);
                         if (w->level < w->cap) {
@@ -2258,6 +2279,7 @@ static void b_body(bsim *w, bproc *p, int64_t sig)
                     else if (w->level < w->cap) {
                         const uint64_t grab = w->cap - w->level;
                         w->level = w->cap;
+                        b_record(w);
                         p->rem -= grab;
                         g_signal(s, &s->front, w->level > 0u);
                     }
@@ -2278,18 +2300,19 @@ static void b_body(bsim *w, bproc *p, int64_t sig)
                 }
             }
         }
-        if (id < 4) {                                   /* drainer */
+        if (id < w->fillers + w->drainers) {            /* drainer */
             for (;;) {
                 g_hold_begin(s, &p->g, port_exponential(&s->rng, w->get_mean));
                 p->g.pc = 30;
                 return;
     case 30:
                 b_note(w, g_hold_end(s, &p->g, sig));
-                p->rem = (uint64_t)port_dice(&s->rng, 1, 8);
+                p->rem = (uint64_t)port_dice(&s->rng, 1, w->amount_max);
                 p->moved = 0u;
                 for (;;) {                              /* cmb_buffer_get */
                     if (w->level >= p->rem) {
                         w->level -= p->rem;
+                        b_record(w);
                         p->moved += p->rem;
                         g_signal(s, &s->rear, w->level < w->cap);
                         if (w->level > 0u) {
@@ -2301,6 +2324,7 @@ static void b_body(bsim *w, bproc *p, int64_t sig)
                     else if (w->level > 0u) {
                         const uint64_t grab = w->level;
                         w->level = 0u;
+                        b_record(w);
                         p->moved += grab;
                         p->rem -= grab;
                         g_signal(s, &s->rear, w->level < w->cap);
@@ -2397,7 +2421,7 @@ static void b_stop(bsim *w, bproc *p)
 }
 
 static void run_buffer(int capacity, uint64_t seed, uint64_t duration, double put_mean, double get_mean,
-                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out)
+                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time, port_result *out, bool plain)
 {
     bsim *w = calloc(1, sizeof(*w));
     gsim *s = &w->s;
@@ -2411,6 +2435,14 @@ static void run_buffer(int capacity, uint64_t seed, uint64_t duration, double pu
     heap_init(&s->rear, 3u, guard_before);
     heap_init(&w->tool_guard, 3u, guard_before);
     w->cap = (uint64_t)capacity;
+    w->fillers = plain ? 3 : 2;
+    w->drainers = plain ? 3 : 2;
+    w->amount_max = plain ? 15 : 8;
+    if (plain) {                                        /* cmb_buffer_recording_start: level 0 at t = 0 */
+        w->recording = true;
+        port_wsummary_init(&w->hist);
+        b_record(w);
+    }
 
     for (int i = 0; i < B_PROCS; i++) {
         w->proc[i].g.prio = port_dice(&s->rng, -5, 5);
@@ -2466,6 +2498,11 @@ static void run_buffer(int capacity, uint64_t seed, uint64_t duration, double pu
     out->t_end = s->now;
     out->counter[7] = w->level;
     out->objects = out->counter[1];
+    if (plain) {                                        /* recording_stop + cmb_timeseries_summarize */
+        b_record(w);
+        memcpy(&out->counter[4], &w->hist.ds.m1, 8);
+        out->max_queue = w->hist.ds.count;
+    }
     heap_free(&s->fel);
     heap_free(&s->front);
     heap_free(&s->rear);
@@ -3852,9 +3889,9 @@ static void *worker(void *arg)
                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
             continue;
         }
-        if (j->model == 5) {
+        if (j->model == 5 || j->model == 12) {
             run_buffer(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
-                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k]);
+                       j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k], j->model == 12);
             continue;
         }
         if (j->model == 4) {
@@ -3915,8 +3952,8 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
         run_prioq(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;
     }
-    if (model == 5) {
-        run_buffer(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
+    if (model == 5 || model == 12) {
+        run_buffer(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out, model == 12);
         return 0;
     }
     if (model == 4) {

@@ -496,6 +496,7 @@ struct b_world {
     struct cmb_buffer *buffer;
     struct cmb_resource *tool;
     struct cmb_process *proc;           /* B_PROCS + 1 contiguous */
+    long amount_max;                    /* model 5: 8; model 12 (test/test_buffer.c as it stands): 15 */
 };
 
 static void b_note(struct b_world *w, int64_t sig)
@@ -511,7 +512,7 @@ static void *b_filler_body(struct cmb_process *me, void *vw)
     struct b_world *w = vw;
     for (;;) {
         b_note(w, cmb_process_hold(cmb_random_exponential(w->trl->arr_mean)));
-        const uint64_t want = (uint64_t)cmb_random_dice(1, 8);
+        const uint64_t want = (uint64_t)cmb_random_dice(1, w->amount_max);
         uint64_t amount = want;
         const int64_t sig = cmb_buffer_put(w->buffer, &amount);
         w->trl->counter[0] += want - amount;
@@ -528,7 +529,7 @@ static void *b_drainer_body(struct cmb_process *me, void *vw)
     struct b_world *w = vw;
     for (;;) {
         b_note(w, cmb_process_hold(cmb_random_exponential(w->trl->srv_mean)));
-        uint64_t amount = (uint64_t)cmb_random_dice(1, 8);
+        uint64_t amount = (uint64_t)cmb_random_dice(1, w->amount_max);
         const int64_t sig = cmb_buffer_get(w->buffer, &amount);
         w->trl->counter[1] += amount;
         if (sig != CMB_PROCESS_SUCCESS) {
@@ -593,13 +594,23 @@ static void run_buffer_trial(struct ref_trial *t)
     w->trl = t;
     w->buffer = cmb_buffer_create();
     cmb_buffer_initialize(w->buffer, "Buffer", (uint64_t)t->servers);
+    /* model 12 = test/test_buffer.c as it stands: three putters and three getters moving 1..15 units, the
+     * buffer's level history on.  With capacity 10, means 1, duration 10000 and seed 0x34f05c64d7ad598f the
+     * time-weighted level is test/reference/buffer.txt's "N 41876 Mean 4.980". */
+    const bool plain = t->model == 12;
+    const unsigned fillers = plain ? 3u : 2u, drainers = plain ? 3u : 2u;
+    w->amount_max = plain ? 15 : 8;
+    if (plain) {
+        cmb_buffer_recording_start(w->buffer);
+    }
     w->tool = cmb_resource_create();
     cmb_resource_initialize(w->tool, "Tool");
     w->proc = calloc(B_PROCS + 1u, sizeof(struct cmb_process));
     for (unsigned i = 0u; i < B_PROCS; i++) {
         const int64_t pri = cmb_random_dice(-5, 5);
         cmb_process_initialize(&w->proc[i], "Proc",
-                               (i < 2u) ? b_filler_body : (i < 4u) ? b_drainer_body : b_worker_body, w, pri);
+                               (i < fillers) ? b_filler_body : (i < fillers + drainers) ? b_drainer_body : b_worker_body,
+                               w, pri);
         cmb_process_start(&w->proc[i]);
     }
     cmb_process_initialize(&w->proc[B_PROCS], "Nuisance", b_nuisance_body, w, 0);
@@ -610,6 +621,16 @@ static void run_buffer_trial(struct ref_trial *t)
 
     t->counter[7] = cmb_buffer_level(w->buffer);
     t->objects = t->counter[1];
+    if (plain) {
+        /* counter[4] = time-weighted mean level (bits), max_queue = history samples with a duration */
+        cmb_buffer_recording_stop(w->buffer);
+        struct cmb_wtdsummary ws;
+        cmb_wtdsummary_initialize(&ws);
+        (void)cmb_timeseries_summarize(cmb_buffer_history(w->buffer), &ws);
+        const double mean = cmb_wtdsummary_mean(&ws);
+        memcpy(&t->counter[4], &mean, 8);
+        t->max_queue = cmb_wtdsummary_count(&ws);
+    }
     for (unsigned i = 0u; i <= B_PROCS; i++) {
         cmb_process_terminate(&w->proc[i]);
     }
@@ -1548,7 +1569,7 @@ static void run_trial(void *vt)
     else if (t->model == 6) {
         run_prioq_trial(t);
     }
-    else if (t->model == 5) {
+    else if (t->model == 5 || t->model == 12) {
         run_buffer_trial(t);
     }
     else if (t->model == 4) {

@@ -37,7 +37,9 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           8: dict(arr=1.0, srv=0.6, servers=1),      # model 8: num_objects = duration
           9: dict(arr=1 / 0.9, srv=1.0, servers=1),  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
           10: dict(arr=2.0, srv=8.0, servers=10),    # model 10: the harbor of test/test_condition.c (num_objects = hours)
-          11: dict(arr=1.0, srv=1.0, servers=10)}    # model 11: test/test_objectqueue.c with the queue history on
+          11: dict(arr=1.0, srv=1.0, servers=10),    # model 11: test/test_objectqueue.c with the queue history on
+          12: dict(arr=1.0, srv=1.0, servers=10)}    # model 12: test/test_buffer.c as it stands (golden run = the 1e4 record... see below)
+_UNUSED3 = {11: dict()}  # model 11: test/test_objectqueue.c with the queue history on
 _UNUSED2 = {10: dict()}  # model 10: the harbor of test/test_condition.c (num_objects = hours)
 _UNUSED = {9: dict()}  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
 
@@ -101,6 +103,14 @@ def main():
             # test/reference/condition.txt: the reference's own golden run, 100 simulated years
             r, _, _ = trace_trial(ref, "ref", 10, par["servers"], KAT_SEED, 24 * 7 * 52 * 100, par["arr"], par["srv"], 0)
             trials.append({"model": 10, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 24 * 7 * 52 * 100,
+                           "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
+                           "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
+                           "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
+                           "counters": r.counters()})
+        if model == 12:
+            # test/reference/buffer.txt: the reference's own golden run, 10 000 time units
+            r, _, _ = trace_trial(ref, "ref", 12, par["servers"], KAT_SEED, 10_000, par["arr"], par["srv"], 0)
+            trials.append({"model": 12, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 10_000,
                            "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                            "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
                            "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,

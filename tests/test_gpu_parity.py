@@ -763,3 +763,31 @@ def test_objectqueue_reproduces_the_reference_golden_file_on_device(cb, golden):
     assert c == t["counters"]
     assert (int(res.events[0]), int(res.objects[0])) == (t["events"], t["objects"])
     assert float.hex(float(res.t_end[0])) == t["t_end"] and float.hex(float(res.sum_wait[0])) == t["sum_wait"]
+
+
+@pytest.mark.parametrize("cap,dur,pm,gm", [(10, 600, 1.0, 1.0), (3, 400, 0.5, 1.0), (20, 300, 1.0, 0.6)])
+def test_recorded_buffer_matches_oracle(cb, port, cap, dur, pm, gm):
+    """Model 12 = test/test_buffer.c as it stands (3 putters, 3 getters, 1..15 units, level history on)."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=pm, srv_mean=gm, num_objects=dur, master_seed=KAT_SEED,
+                        model=cb.MODEL_BUFFER_RECORDED, servers=cap)
+    want = run_trials(port, "port", 12, cap, KAT_SEED, 0, n, dur, pm, gm)
+    _compare(res, want, ("buffer-recorded", cap))
+    assert _counts(res.counters) == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
+
+
+def test_buffer_reproduces_the_reference_golden_file_on_device(cb, golden):
+    """test/reference/buffer.txt on the GPU: seed 0x34f05c64d7ad598f, capacity 10, 10 000 time units:
+    level history N 41876, time-weighted mean 4.980, every exported word equal to the reference record."""
+    import struct
+    master = _inverse_fmix64(KAT_SEED)
+    t = [x for x in golden["trials"] if x["model"] == 12 and x["num_objects"] == 10_000 and x["seed"] == KAT_SEED][-1]
+    res = cb.run_trials(1, arr_mean=1.0, srv_mean=1.0, num_objects=10_000, master_seed=master,
+                        model=cb.MODEL_BUFFER_RECORDED, servers=10)
+    assert int(res.status[0]) == 0
+    c = _counts(res.counters)[0]
+    mean = struct.unpack("<d", struct.pack("<Q", c[4]))[0]
+    assert int(res.max_queue[0]) == 41876 and "%.3f" % mean == "4.980"
+    assert c == t["counters"] and int(res.events[0]) == t["events"]
+    assert float.hex(float(res.t_end[0])) == t["t_end"]

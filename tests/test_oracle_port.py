@@ -143,6 +143,18 @@ def test_objectqueue_reproduces_the_reference_golden_file(port, golden):
     assert r.max_queue == 5689021 and "%.4g" % mean == "5.008"
 
 
+def test_buffer_reproduces_the_reference_golden_file(port, golden):
+    """test/reference/buffer.txt (test/test_buffer.c, seed 0x34f05c64d7ad598f, 10 000 time units):
+    level history N 41876, time-weighted mean 4.980."""
+    import struct
+    t = [x for x in golden["trials"] if x["model"] == 12 and x["num_objects"] == 10_000 and x["seed"] == KAT_SEED][-1]
+    r, _, _ = trace_trial(port, "port", 12, 10, KAT_SEED, 10_000, 1.0, 1.0, 0)
+    assert (r.events, float.hex(r.t_end)) == (t["events"], t["t_end"])
+    assert r.counters() == t["counters"] and (r.max_fel, r.max_queue) == (t["max_fel"], t["max_queue"])
+    mean = struct.unpack("<d", struct.pack("<Q", r.counters()[4]))[0]
+    assert r.max_queue == 41876 and "%.3f" % mean == "4.980"
+
+
 def test_experiment_seeding_matches_golden(port, golden):
     g = golden["experiment_mm1"]
     res = run_trials(port, "port", 0, 1, g["master_seed"], 0, len(g["trials"]), g["num_objects"], 1 / 0.9, 1.0)
@@ -224,7 +236,8 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (8, 1.0, 0.6, 1), (8, 0.4, 1.2, 1),
                                                    (9, 1 / 0.9, 1.0, 1), (9, 2.0, 1.0, 1),
                                                    (10, 2.0, 8.0, 10), (10, 1.2, 8.0, 4), (10, 0.9, 8.0, 3),
-                                                   (11, 1.0, 1.0, 10), (11, 0.5, 1.0, 2)])
+                                                   (11, 1.0, 1.0, 10), (11, 0.5, 1.0, 2),
+                                                   (12, 1.0, 1.0, 10), (12, 0.5, 1.0, 4)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
