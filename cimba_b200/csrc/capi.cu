@@ -84,7 +84,7 @@ bool is_general_model(int m)
 {
     return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
            m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_TIMERS || m == CIMBA_B200_MODEL_GUARDED_RECORDED ||
-           m == CIMBA_B200_MODEL_BUFFER_RECORDED;
+           m == CIMBA_B200_MODEL_BUFFER_RECORDED || m == CIMBA_B200_MODEL_PRIOQ_RECORDED;
 }
 
 // ---------------------------------------------------------------- RNG KAT kernel
@@ -343,7 +343,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const bool prq = job->model == CIMBA_B200_MODEL_PRIOQ;
         const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
         const bool buf = job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_BUFFER_RECORDED;
-        if (!tmr && (job->servers < 1 || (!pre && !buf && job->servers > (prq ? 15 : 16))))
+        const bool pq13 = job->model == CIMBA_B200_MODEL_PRIOQ_RECORDED;
+        if (!tmr && (job->servers < 1 || (!pre && !buf && job->servers > ((prq || pq13) ? 15 : 16))))
             return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1 (and <= 16 for CIMBA_B200_MODEL_GUARDED)");
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -364,7 +365,9 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.max_queue = job->max_queue;
         ga.counters = job->counters;
         ga.state = (GeneralState *)job->workspace;
-        ga.record = (job->model == CIMBA_B200_MODEL_GUARDED_RECORDED || job->model == CIMBA_B200_MODEL_BUFFER_RECORDED) ? 1u : 0u;
+        ga.record = (job->model == CIMBA_B200_MODEL_GUARDED_RECORDED || job->model == CIMBA_B200_MODEL_BUFFER_RECORDED ||
+                     job->model == CIMBA_B200_MODEL_PRIOQ_RECORDED) ? 1u : 0u;
+        ga.use_pq = job->model == CIMBA_B200_MODEL_PRIOQ_RECORDED ? 1u : 0u;
         ga.trace_cap = job->trace_cap;
         ga.trace_key = job->trace_key;
         ga.trace_time = job->trace_time;

@@ -36,7 +36,8 @@ struct GuardedArgs {
     uint32_t *status, *max_queue;
     uint64_t *counters;                // [num_trials][8]
     GeneralState *state;               // [num_trials]
-    uint32_t  record;                  // model 11: fold the queue's history into a time-weighted summary
+    uint32_t  record;                  // models 11-13: fold the history into a time-weighted summary
+    uint32_t  use_pq;                  // model 13: the objects sit in a cmb_priorityqueue
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
@@ -48,6 +49,7 @@ struct GuardedTally {
     double   put_mean, get_mean;
     uint32_t record;
     TimeWeighted hist;                 // cmb_objectqueue_recording_start (test/test_objectqueue.c:191)
+    uint32_t use_pq;                   // model 13 = test/test_priorityqueue.c: priority desc, then FIFO
     uint32_t fillers, drainers;        // buffer models: 2 + 2 (model 5) or 3 + 3 (model 12 = test/test_buffer.c)
     int32_t  amount_max;               // ... moving 1..8 or 1..15 units
 };
@@ -90,7 +92,14 @@ __device__ void guarded_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32
                 p.stamp = s.now;
                 for (;;) {                              // cmb_objectqueue_put, src/cmb_objectqueue.c:262-314
                     if (st->ring_len < st->ring_cap) {
-                        st->ring[(st->ring_head + st->ring_len) % st->ring_cap] = p.stamp;
+                        if (t.use_pq) {                 // cmb_priorityqueue_put with the putter's priority (:237-262)
+                            if (st->pq.push(0u, p.stamp, p.prio, 0u, pid, 0) == 0u) {
+                                st->status |= TRIAL_ERR_QUEUE_OVERFLOW;
+                            }
+                        }
+                        else {
+                            st->ring[(st->ring_head + st->ring_len) % st->ring_cap] = p.stamp;
+                        }
                         st->ring_len++;
                         if (t.record) time_weighted_sample(t.hist, (double)st->ring_len, s.now);
                         s.signal(0u, st->ring_len > 0u);
@@ -111,8 +120,15 @@ __device__ void guarded_body(GeneralSim &s, GuardedTally &t, uint32_t pid, int32
             else {
                 for (;;) {                              // cmb_objectqueue_get, :203-260
                     if (st->ring_len > 0u) {
-                        const double stamp = st->ring[st->ring_head];
-                        st->ring_head = (st->ring_head + 1u) % st->ring_cap;
+                        double stamp;
+                        if (t.use_pq) {                 // cmb_priorityqueue_get (:189-212): the heap's first
+                            (void)st->pq.pop();
+                            stamp = st->pq.slot[0].d;
+                        }
+                        else {
+                            stamp = st->ring[st->ring_head];
+                            st->ring_head = (st->ring_head + 1u) % st->ring_cap;
+                        }
                         st->ring_len--;
                         if (t.record) time_weighted_sample(t.hist, (double)st->ring_len, s.now);
                         s.signal(1u, st->ring_len < st->ring_cap);
@@ -162,11 +178,13 @@ guarded_kernel(const GuardedArgs a)
     t.put_mean = a.put_mean[trial];
     t.get_mean = a.get_mean[trial];
     t.record = a.record;
+    t.use_pq = a.use_pq;
     t.hist.start();
     if (t.record) {
         t.hist.sample(0.0, 0.0);                        // the empty queue at t = 0
     }
 
+    st->pq.clear();
     st->fel.clear();
     st->guard[0].clear();
     st->guard[1].clear();

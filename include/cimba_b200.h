@@ -85,6 +85,10 @@ extern "C" {
                                     * through a cmb_buffer of capacity `servers`, a nuisance, the level history on.  counters[4] =
                                     * time-weighted mean level (bits), max_queue = history samples with a duration; capacity 10, means 1,
                                     * 10 000 time units and the golden seed give test/reference/buffer.txt's "N 41876  Mean 4.980" */
+#define CIMBA_B200_MODEL_PRIOQ_RECORDED 13 /* test/test_priorityqueue.c: MODEL_GUARDED_RECORDED's seven processes on a cmb_priorityqueue
+                                    * (capacity `servers` <= 15), objects put with the putter's own priority; same outputs.  Capacity 10,
+                                    * means 1, 1e6 time units and the golden seed give test/reference/priorityqueue.txt's
+                                    * "N 5689021  Mean 5.008" */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -1472,7 +1472,9 @@ typedef struct gsim {
     double  *ring;
     uint64_t cap, head, len;
     double   put_mean, get_mean;
-    bool     recording;                 /* model 11: the queue's history, fused as in record_sample() above */
+    bool     use_pq;                    /* model 13: the objects sit in a cmb_priorityqueue (priority desc, FIFO) */
+    heap     pq;
+    bool     recording;                 /* models 11, 13: the queue's history, fused as in record_sample() above */
     uint64_t rec_n;
     double   rec_x, rec_t;
     port_wsummary hist;
@@ -1610,6 +1612,8 @@ static void g_signal(gsim *s, heap *g, bool demand_holds)
     }
 }
 
+static bool prioq_before(const heap_tag *a, const heap_tag *b);    /* src/cmb_priorityqueue.c:43-54, defined with model 6 */
+
 /* record_sample of the bounded queue, src/cmb_objectqueue.c:151-159 */
 static void g_record(gsim *s)
 {
@@ -1658,7 +1662,14 @@ static void g_body(gsim *s, gproc *p, int64_t sig)
                 p->stamp = s->now;
                 for (;;) {                              /* cmb_objectqueue_put */
                     if (s->len < s->cap) {
-                        s->ring[(s->head + s->len) % s->cap] = p->stamp;
+                        if (s->use_pq) {                /* cmb_priorityqueue_put with the putter's priority, :237-262 */
+                            int64_t bits;
+                            memcpy(&bits, &p->stamp, 8);
+                            heap_push(&s->pq, 0u, 0.0, p->prio, bits, 0, 0);
+                        }
+                        else {
+                            s->ring[(s->head + s->len) % s->cap] = p->stamp;
+                        }
                         s->len++;
                         g_record(s);
                         g_signal(s, &s->front, s->len > 0u);
@@ -1679,8 +1690,15 @@ static void g_body(gsim *s, gproc *p, int64_t sig)
             else {
                 for (;;) {                              /* cmb_objectqueue_get */
                     if (s->len > 0u) {
-                        const double stamp = s->ring[s->head];
-                        s->head = (s->head + 1u) % s->cap;
+                        double stamp;
+                        if (s->use_pq) {                /* cmb_priorityqueue_get, :189-212 */
+                            heap_pop(&s->pq);
+                            memcpy(&stamp, &s->pq.slot[0].item[0], 8);
+                        }
+                        else {
+                            stamp = s->ring[s->head];
+                            s->head = (s->head + 1u) % s->cap;
+                        }
                         s->len--;
                         g_record(s);
                         g_signal(s, &s->rear, s->len < s->cap);
@@ -1715,7 +1733,7 @@ static void g_stop(gsim *s, gproc *p)
 
 static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
                         double put_mean, double get_mean, uint64_t trace_cap,
-                        uint64_t *trace_key, double *trace_time, port_result *out, bool record)
+                        uint64_t *trace_key, double *trace_time, port_result *out, bool record, bool use_pq)
 {
     gsim *s = calloc(1, sizeof(*s));
     memset(out, 0, sizeof(*out));
@@ -1730,6 +1748,8 @@ static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
     heap_init(&s->front, 3u, guard_before);
     heap_init(&s->rear, 3u, guard_before);
     s->cap = (uint64_t)capacity;
+    s->use_pq = use_pq;
+    heap_init(&s->pq, 3u, prioq_before);
     if (record) {                                       /* cmb_objectqueue_recording_start: the empty queue at t = 0 */
         s->recording = true;
         port_wsummary_init(&s->hist);
@@ -1806,6 +1826,7 @@ static void run_guarded(int capacity, uint64_t seed, uint64_t duration,
     heap_free(&s->front);
     heap_free(&s->rear);
     free(s->ring);
+    heap_free(&s->pq);
     free(s);
 }
 
@@ -3899,9 +3920,9 @@ static void *worker(void *arg)
                         0u, NULL, NULL, &j->out[k]);
             continue;
         }
-        if (j->model == 3 || j->model == 11) {
+        if (j->model == 3 || j->model == 11 || j->model == 13) {
             run_guarded(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
-                        j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k], j->model == 11);
+                        j->arr_mean, j->srv_mean, 0u, NULL, NULL, &j->out[k], j->model != 3, j->model == 13);
             continue;
         }
         run_one(j->model, j->servers, port_fmix64(j->master_seed, j->first + k),
@@ -3960,8 +3981,9 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
         run_preempt(servers, seed, num_objects, trace_cap, trace_key, trace_time, out);
         return 0;
     }
-    if (model == 3 || model == 11) {
-        run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out, model == 11);
+    if (model == 3 || model == 11 || model == 13) {
+        run_guarded(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out, model != 3,
+                    model == 13);
         return 0;
     }
     run_one(model, servers, seed, num_objects, arr_mean, srv_mean,

@@ -205,6 +205,7 @@ static void pump_events(struct ref_trial *t);
 struct g_world {
     struct ref_trial *trl;
     struct cmb_objectqueue *queue;
+    struct cmb_priorityqueue *pq;       /* model 13 (test/test_priorityqueue.c): the same workload on a priority queue */
     struct cmb_process *worker[G_PUTTERS + G_GETTERS];
     struct cmb_process *nuisance;
 };
@@ -219,14 +220,14 @@ static void note_signal(struct ref_trial *t, int64_t sig, unsigned which)
 
 static void *g_putter_body(struct cmb_process *me, void *vw)
 {
-    cmb_unused(me);
     struct g_world *w = vw;
     for (;;) {
         int64_t sig = cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
         note_signal(w->trl, sig, 2u);
         double *stamp = cmi_mempool_alloc(&stamp_pool);
         *stamp = cmb_time();
-        sig = cmb_objectqueue_put(w->queue, stamp);
+        sig = (w->pq != NULL) ? cmb_priorityqueue_put(w->pq, stamp, cmb_process_priority(me), NULL)
+                              : cmb_objectqueue_put(w->queue, stamp);
         if (sig == CMB_PROCESS_SUCCESS) {
             w->trl->counter[0] += 1u;
         }
@@ -245,7 +246,7 @@ static void *g_getter_body(struct cmb_process *me, void *vw)
         int64_t sig = cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
         note_signal(w->trl, sig, 2u);
         void *obj = NULL;
-        sig = cmb_objectqueue_get(w->queue, &obj);
+        sig = (w->pq != NULL) ? cmb_priorityqueue_get(w->pq, &obj) : cmb_objectqueue_get(w->queue, &obj);
         if (sig == CMB_PROCESS_SUCCESS) {
             w->trl->counter[1] += 1u;
             w->trl->sum_wait += cmb_time() - *(double *)obj;
@@ -293,6 +294,15 @@ static void run_guarded_trial(struct ref_trial *t)
          * is test/reference/objectqueue.txt's "N 5689021 Mean 5.008" */
         cmb_objectqueue_recording_start(w->queue);
     }
+    if (t->model == 13) {
+        /* model 13 = test/test_priorityqueue.c: the same seven processes on a cmb_priorityqueue, objects put
+         * with the putter's own priority, history on -> test/reference/priorityqueue.txt (the same "N 5689021
+         * Mean 5.008": which object a get returns does not change the event sequence; sum_wait does differ).
+         * The test itself passes the address of a local pointer as the object; here it is the stamp. */
+        w->pq = cmb_priorityqueue_create();
+        cmb_priorityqueue_initialize(w->pq, "Queue", (uint64_t)t->servers);
+        cmb_priorityqueue_recording_start(w->pq);
+    }
     for (unsigned i = 0u; i < G_PUTTERS + G_GETTERS; i++) {
         w->worker[i] = cmb_process_create();
         const int64_t pri = cmb_random_dice(-5, 5);
@@ -307,8 +317,18 @@ static void run_guarded_trial(struct ref_trial *t)
 
     pump_events(t);
 
-    t->counter[6] = cmb_objectqueue_length(w->queue);
+    t->counter[6] = (w->pq != NULL) ? cmb_priorityqueue_length(w->pq) : cmb_objectqueue_length(w->queue);
     t->objects = t->counter[1];
+    if (t->model == 13) {
+        cmb_priorityqueue_recording_stop(w->pq);
+        struct cmb_wtdsummary ws;
+        cmb_wtdsummary_initialize(&ws);
+        (void)cmb_timeseries_summarize(cmb_priorityqueue_history(w->pq), &ws);
+        const double mean = cmb_wtdsummary_mean(&ws);
+        memcpy(&t->counter[6], &mean, 8);
+        t->max_queue = cmb_wtdsummary_count(&ws);
+        cmb_priorityqueue_destroy(w->pq);
+    }
     if (t->model == 11) {
         /* counter[6] = mean queue length (bits), max_queue = samples with a duration */
         cmb_objectqueue_recording_stop(w->queue);
@@ -1575,7 +1595,7 @@ static void run_trial(void *vt)
     else if (t->model == 4) {
         run_preempt_trial(t);
     }
-    else if (t->model == 3 || t->model == 11) {
+    else if (t->model == 3 || t->model == 11 || t->model == 13) {
         run_guarded_trial(t);
     }
     else if (t->model == 2) {

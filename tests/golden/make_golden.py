@@ -38,7 +38,9 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           9: dict(arr=1 / 0.9, srv=1.0, servers=1),  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
           10: dict(arr=2.0, srv=8.0, servers=10),    # model 10: the harbor of test/test_condition.c (num_objects = hours)
           11: dict(arr=1.0, srv=1.0, servers=10),    # model 11: test/test_objectqueue.c with the queue history on
-          12: dict(arr=1.0, srv=1.0, servers=10)}    # model 12: test/test_buffer.c as it stands (golden run = the 1e4 record... see below)
+          12: dict(arr=1.0, srv=1.0, servers=10),    # model 12: test/test_buffer.c as it stands
+          13: dict(arr=1.0, srv=1.0, servers=10)}    # model 13: test/test_priorityqueue.c
+_UNUSED4 = {12: dict()}  # model 12: test/test_buffer.c as it stands (golden run = the 1e4 record... see below)
 _UNUSED3 = {11: dict()}  # model 11: test/test_objectqueue.c with the queue history on
 _UNUSED2 = {10: dict()}  # model 10: the harbor of test/test_condition.c (num_objects = hours)
 _UNUSED = {9: dict()}  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
@@ -115,10 +117,10 @@ def main():
                            "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
                            "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
                            "counters": r.counters()})
-        if model == 11:
-            # test/reference/objectqueue.txt: the reference's own golden run, 1e6 time units
-            r, _, _ = trace_trial(ref, "ref", 11, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
-            trials.append({"model": 11, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
+        if model in (11, 13):
+            # test/reference/objectqueue.txt / priorityqueue.txt: the reference's own golden runs, 1e6 time units
+            r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
+            trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
                            "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                            "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
                            "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,

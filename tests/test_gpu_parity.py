@@ -734,28 +734,30 @@ def test_survey_known_answers_on_device(cb, golden, model):
         assert _counts(res.counters)[0] == t["counters"]
 
 
-@pytest.mark.parametrize("cap,dur,pm,gm", [(10, 600, 1.0, 1.0), (2, 400, 0.5, 1.0), (1, 300, 1.0, 0.6)])
-def test_recorded_bounded_queue_matches_oracle(cb, port, cap, dur, pm, gm):
-    """Model 11 = test/test_objectqueue.c with its history on: everything model 3 checks plus the
-    time-weighted mean queue length (bits) and the number of history samples."""
+@pytest.mark.parametrize("model", [11, 13])
+@pytest.mark.parametrize("cap,dur,pm,gm", [(10, 600, 1.0, 1.0), (2, 400, 0.5, 1.0), (1, 300, 1.0, 0.6), (15, 300, 0.3, 0.6)])
+def test_recorded_bounded_queue_matches_oracle(cb, port, cap, dur, pm, gm, model):
+    """Model 11 = test/test_objectqueue.c with its history on, model 13 = test/test_priorityqueue.c: everything
+    model 3 checks plus the time-weighted mean queue length (bits) and the number of history samples."""
     n = 96
     res = cb.run_trials(n, arr_mean=pm, srv_mean=gm, num_objects=dur, master_seed=KAT_SEED,
-                        model=cb.MODEL_GUARDED_RECORDED, servers=cap)
-    want = run_trials(port, "port", 11, cap, KAT_SEED, 0, n, dur, pm, gm)
+                        model=model, servers=cap)
+    want = run_trials(port, "port", model, cap, KAT_SEED, 0, n, dur, pm, gm)
     _compare(res, want, ("guarded-recorded", cap))
     assert _counts(res.counters) == [w.counters() for w in want]
     assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
 
 
-def test_objectqueue_reproduces_the_reference_golden_file_on_device(cb, golden):
-    """test/reference/objectqueue.txt on the GPU: seed 0x34f05c64d7ad598f, capacity 10, 1e6 time units,
+@pytest.mark.parametrize("model", [11, 13])
+def test_objectqueue_reproduces_the_reference_golden_file_on_device(cb, golden, model):
+    """test/reference/objectqueue.txt (model 11) and priorityqueue.txt (model 13) on the GPU: seed 0x34f05c64d7ad598f, capacity 10, 1e6 time units,
     8.46 million events through the general interrupt / cancel / stop path in one lane: queue-length history
     N 5689021, time-weighted mean 5.008, and every exported word equal to the committed reference record."""
     import struct
     master = _inverse_fmix64(KAT_SEED)
-    t = [x for x in golden["trials"] if x["model"] == 11 and x["num_objects"] == 1_000_000][0]
+    t = [x for x in golden["trials"] if x["model"] == model and x["num_objects"] == 1_000_000][0]
     res = cb.run_trials(1, arr_mean=1.0, srv_mean=1.0, num_objects=1_000_000, master_seed=master,
-                        model=cb.MODEL_GUARDED_RECORDED, servers=10)
+                        model=model, servers=10)
     assert int(res.status[0]) == 0
     c = _counts(res.counters)[0]
     mean = struct.unpack("<d", struct.pack("<Q", c[6]))[0]

@@ -130,12 +130,13 @@ def test_harbor_reproduces_the_reference_golden_file(port, golden):
     assert (c[6] & 0xffffffff, c[6] >> 32) == (645947, 217380)
 
 
-def test_objectqueue_reproduces_the_reference_golden_file(port, golden):
-    """test/reference/objectqueue.txt (the reference's own golden output of test/test_objectqueue.c, seed
+@pytest.mark.parametrize("model", [11, 13])
+def test_objectqueue_and_priorityqueue_reproduce_the_reference_golden_files(port, golden, model):
+    """test/reference/objectqueue.txt and priorityqueue.txt (test/test_objectqueue.c / test_priorityqueue.c, seed
     0x34f05c64d7ad598f, 1e6 time units): queue-length history N 5689021, time-weighted mean 5.008."""
     import struct
-    t = [x for x in golden["trials"] if x["model"] == 11 and x["num_objects"] == 1_000_000][0]
-    r, _, _ = trace_trial(port, "port", 11, 10, KAT_SEED, 1_000_000, 1.0, 1.0, 0)
+    t = [x for x in golden["trials"] if x["model"] == model and x["num_objects"] == 1_000_000][0]
+    r, _, _ = trace_trial(port, "port", model, 10, KAT_SEED, 1_000_000, 1.0, 1.0, 0)
     assert (r.events, r.objects, float.hex(r.t_end), float.hex(r.sum_wait)) == \
            (t["events"], t["objects"], t["t_end"], t["sum_wait"])
     assert r.counters() == t["counters"] and (r.max_fel, r.max_queue) == (t["max_fel"], t["max_queue"])
@@ -237,7 +238,8 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (9, 1 / 0.9, 1.0, 1), (9, 2.0, 1.0, 1),
                                                    (10, 2.0, 8.0, 10), (10, 1.2, 8.0, 4), (10, 0.9, 8.0, 3),
                                                    (11, 1.0, 1.0, 10), (11, 0.5, 1.0, 2),
-                                                   (12, 1.0, 1.0, 10), (12, 0.5, 1.0, 4)])
+                                                   (12, 1.0, 1.0, 10), (12, 0.5, 1.0, 4),
+                                                   (13, 1.0, 1.0, 10), (13, 0.5, 1.0, 3)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
