@@ -40,10 +40,10 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           11: dict(arr=1.0, srv=1.0, servers=10),    # model 11: test/test_objectqueue.c with the queue history on
           12: dict(arr=1.0, srv=1.0, servers=10),    # model 12: test/test_buffer.c as it stands
           13: dict(arr=1.0, srv=1.0, servers=10)}    # model 13: test/test_priorityqueue.c
-_UNUSED4 = {12: dict()}  # model 12: test/test_buffer.c as it stands (golden run = the 1e4 record... see below)
-_UNUSED3 = {11: dict()}  # model 11: test/test_objectqueue.c with the queue history on
-_UNUSED2 = {10: dict()}  # model 10: the harbor of test/test_condition.c (num_objects = hours)
-_UNUSED = {9: dict()}  # model 9: M/M/1 with the queue history on (counters = wtdsummary bits)
+# the reference's own golden runs (test/reference/*.txt) that a model reproduces: model -> (file, size)
+GOLDEN_RUNS = {10: ("condition.txt", 24 * 7 * 52 * 100), 11: ("objectqueue.txt", 1_000_000),
+               12: ("buffer.txt", 10_000), 13: ("priorityqueue.txt", 1_000_000)}
+FULL_SIZE_KAT = (0, 1, 2, 9)             # 10^6 objects with the KAT seed
 
 
 def hexes(a):
@@ -89,7 +89,7 @@ def main():
             # model 3: the size is a duration; 0 would stop workers before they start (they then
             # run forever in the reference), so it starts at 1
             traced = 10 if model == 7 else 1000
-            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model in (0, 1, 2, 9) else ((1, 2, 3, 10, 50) if model == 7 else (1, 2, 3, 10, 100, 1000))):
+            for nobj in ((0, 1, 2, 3, 10, 1000, 100_000) if model in FULL_SIZE_KAT else ((1, 2, 3, 10, 50) if model == 7 else (1, 2, 3, 10, 100, 1000))):
                 r, keys, times = trace_trial(ref, "ref", model, par["servers"], seed, nobj,
                                              par["arr"], par["srv"], 512 if nobj == traced else 0)
                 rec = {"model": model, "servers": par["servers"], "seed": seed, "num_objects": nobj,
@@ -101,35 +101,12 @@ def main():
                     rec["trace_key"] = [int(k) for k in keys]
                     rec["trace_time"] = hexes(times)
                 trials.append(rec)
-        if model == 10:
-            # test/reference/condition.txt: the reference's own golden run, 100 simulated years
-            r, _, _ = trace_trial(ref, "ref", 10, par["servers"], KAT_SEED, 24 * 7 * 52 * 100, par["arr"], par["srv"], 0)
-            trials.append({"model": 10, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 24 * 7 * 52 * 100,
-                           "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
-                           "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
-                           "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
-                           "counters": r.counters()})
-        if model == 12:
-            # test/reference/buffer.txt: the reference's own golden run, 10 000 time units
-            r, _, _ = trace_trial(ref, "ref", 12, par["servers"], KAT_SEED, 10_000, par["arr"], par["srv"], 0)
-            trials.append({"model": 12, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 10_000,
-                           "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
-                           "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
-                           "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
-                           "counters": r.counters()})
-        if model in (11, 13):
-            # test/reference/objectqueue.txt / priorityqueue.txt: the reference's own golden runs, 1e6 time units
-            r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
-            trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
-                           "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
-                           "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
-                           "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
-                           "counters": r.counters()})
-        if model not in (0, 1, 2, 9):
+        big = GOLDEN_RUNS[model][1] if model in GOLDEN_RUNS else (1_000_000 if model in FULL_SIZE_KAT else None)
+        if big is None:
             continue
-        # the full-size known answer
-        r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, 1_000_000, par["arr"], par["srv"], 0)
-        trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": 1_000_000,
+        # one full-size record with the KAT seed: the reference's golden run / SURVEY.md section 8c's known answer
+        r, _, _ = trace_trial(ref, "ref", model, par["servers"], KAT_SEED, big, par["arr"], par["srv"], 0)
+        trials.append({"model": model, "servers": par["servers"], "seed": KAT_SEED, "num_objects": big,
                        "arr_mean": float.hex(par["arr"]), "srv_mean": float.hex(par["srv"]),
                        "events": r.events, "objects": r.objects, "t_end": float.hex(r.t_end),
                        "sum_wait": float.hex(r.sum_wait), "max_fel": r.max_fel, "max_queue": r.max_queue,
