@@ -681,8 +681,48 @@ struct PhaseClock {            // CIMBA_B200_TIMING=1: phase times of the host-b
 };
 }  // namespace
 
+namespace {
+int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const cimba_b200_experiment *d);
+
+// Trials per launch of the host-buffer path.  An experiment larger than this runs as consecutive chunks
+// (seeds depend on the global trial index only), so staging and workspace stay bounded - 1 Mi M/M/1
+// trials need 4.3 GB of spill ring - while every chunk still saturates the GPU (M/M/1 peaks at ~6e5).
+uint64_t chunk_trials()
+{
+    const char *env = getenv("CIMBA_B200_CHUNK_TRIALS");
+    if (env != nullptr) {
+        const unsigned long long v = strtoull(env, nullptr, 10);
+        if (v > 0ull) return (uint64_t)v;
+    }
+    return 1ull << 20;
+}
+}  // namespace
+
 int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
                               const cimba_b200_experiment *d)
+{
+    if (array == nullptr || d == nullptr) return fail(CIMBA_B200_EINVAL, "NULL experiment array or descriptor");
+    if (num_trials == 0u || stride == 0u) return fail(CIMBA_B200_EINVAL, "num_trials and trial_struct_size must be > 0");
+    const uint64_t chunk = chunk_trials();
+    int worst = CIMBA_B200_OK;
+    for (uint64_t off = 0; off < num_trials; off += chunk) {
+        const uint64_t m = num_trials - off < chunk ? num_trials - off : chunk;
+        cimba_b200_experiment sub = *d;
+        sub.first_trial = d->first_trial + off;
+        const int rc = run_experiment_chunk((char *)array + off * stride, m, stride, &sub);
+        if (rc == CIMBA_B200_ETRIAL) {
+            worst = rc;                                 // the other trials' results are valid: carry on
+        }
+        else if (rc != CIMBA_B200_OK) {
+            return rc;
+        }
+    }
+    if (worst != CIMBA_B200_OK) return fail(worst, "at least one trial reported a capacity violation");
+    return CIMBA_B200_OK;
+}
+
+namespace {
+int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const cimba_b200_experiment *d)
 {
     PhaseClock clk;
     if (array == nullptr || d == nullptr) return fail(CIMBA_B200_EINVAL, "NULL experiment array or descriptor");
@@ -797,6 +837,7 @@ int cimba_b200_run_experiment(void *array, uint64_t num_trials, size_t stride,
 done:
     return rc;
 }
+}  // namespace
 
 void cimba_b200_release_cache(void)
 {

@@ -793,3 +793,17 @@ def test_buffer_reproduces_the_reference_golden_file_on_device(cb, golden):
     assert int(res.max_queue[0]) == 41876 and "%.3f" % mean == "4.980"
     assert c == t["counters"] and int(res.events[0]) == t["events"]
     assert float.hex(float(res.t_end[0])) == t["t_end"]
+
+
+def test_host_buffer_api_chunks_large_experiments(cb, port, monkeypatch):
+    """An experiment larger than CIMBA_B200_CHUNK_TRIALS runs as consecutive launches; seeds follow the global
+    trial index, so the results are those of one launch."""
+    n = 1000
+    whole = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    whole["arr_mean"], whole["srv_mean"] = 1 / 0.9, 1.0
+    parts = whole.copy()
+    cb.cimba_run_experiment(whole, num_objects=700, master_seed=KAT_SEED)
+    monkeypatch.setenv("CIMBA_B200_CHUNK_TRIALS", "300")
+    cb.cimba_run_experiment(parts, num_objects=700, master_seed=KAT_SEED)
+    for f in ("events", "obj_cnt", "sum_wait", "t_end", "avg_wait", "status"):
+        assert np.array_equal(whole[f], parts[f]), f
