@@ -29,6 +29,7 @@
 #include "buffer_model.cuh"
 #include "prioq_model.cuh"
 #include "timers_model.cuh"
+#include "resource_model.cuh"
 #include "harbor_model.cuh"
 #include "hold_model.cuh"
 #include "hold_deep.cuh"
@@ -84,7 +85,8 @@ bool is_general_model(int m)
 {
     return m == CIMBA_B200_MODEL_GUARDED || m == CIMBA_B200_MODEL_PREEMPT || m == CIMBA_B200_MODEL_BUFFER ||
            m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_TIMERS || m == CIMBA_B200_MODEL_GUARDED_RECORDED ||
-           m == CIMBA_B200_MODEL_BUFFER_RECORDED || m == CIMBA_B200_MODEL_PRIOQ_RECORDED;
+           m == CIMBA_B200_MODEL_BUFFER_RECORDED || m == CIMBA_B200_MODEL_PRIOQ_RECORDED ||
+           m == CIMBA_B200_MODEL_RESOURCE_RECORDED;
 }
 
 // ---------------------------------------------------------------- RNG KAT kernel
@@ -339,7 +341,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
     }
     if (is_general_model(job->model)) {
-        const bool tmr = job->model == CIMBA_B200_MODEL_TIMERS;
+        const bool rsc = job->model == CIMBA_B200_MODEL_RESOURCE_RECORDED;
+        const bool tmr = job->model == CIMBA_B200_MODEL_TIMERS || rsc;      // no capacity argument
         const bool prq = job->model == CIMBA_B200_MODEL_PRIOQ;
         const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
         const bool buf = job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_BUFFER_RECORDED;
@@ -373,7 +376,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         ga.trace_time = job->trace_time;
         const uint64_t blocks = (job->num_trials + GUARDED_BLOCK - 1) / GUARDED_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
-        if (tmr) {
+        if (rsc) {
+            if (trace) resource_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+            else       resource_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
+        }
+        else if (tmr) {
             if (trace) timers_kernel<true><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
             else       timers_kernel<false><<<(unsigned)blocks, GUARDED_BLOCK, 0, st>>>(ga);
         }

@@ -89,6 +89,11 @@ extern "C" {
                                     * (capacity `servers` <= 15), objects put with the putter's own priority; same outputs.  Capacity 10,
                                     * means 1, 1e6 time units and the golden seed give test/reference/priorityqueue.txt's
                                     * "N 5689021  Mean 5.008" */
+#define CIMBA_B200_MODEL_RESOURCE_RECORDED 14 /* test/test_resource.c as it stands: three pre-emptable processes and a pre-empter on one
+                                    * cmb_resource, usage history on.  counters: [0] acquisitions by the targets [1] PREEMPTED received
+                                    * [2] acquisitions by the pre-empter [3] time-weighted mean utilisation (bits) [4] time of the first
+                                    * pre-emption (bits) [5] its victim + 1; max_queue = history samples.  25 time units and the golden
+                                    * seed give test/reference/resource.txt: "N 30  Mean 0.9816", Target_3 pre-empted at t = 6.3280 */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -3872,6 +3872,217 @@ static void run_harbor(int tugs, uint64_t seed, uint64_t duration, double arr_me
     free(w);
 }
 
+/* ======================================== model 14: test/test_resource.c as it stands
+ *
+ * cmb_resource_acquire / release / preempt with wakeup_event_preempt and the usage history
+ * (src/cmb_resource.c:45-57, 107-136, 182-320).  Workload: ref_driver.c model 14.
+ */
+typedef struct rsim {
+    gsim     s;
+    heap     guard;
+    gproc   *holder;
+    gproc    proc[4];
+    bool     holds[4];
+    double   since[4];
+    uint64_t rec_n;
+    double   rec_x, rec_t;
+    port_wsummary hist;
+} rsim;
+
+static void r_record(rsim *w)                           /* record_sample, src/cmb_resource.c:107-118 */
+{
+    if (w->rec_n > 0u) {
+        (void)port_wsummary_add(&w->hist, w->rec_x, w->s.now - w->rec_t);
+    }
+    w->rec_x = (w->holder != NULL) ? 1.0 : 0.0;
+    w->rec_t = w->s.now;
+    w->rec_n++;
+}
+
+static void r_grab(rsim *w, gproc *p)
+{
+    w->holder = p;
+    w->holds[p - w->proc] = true;
+}
+
+static void r_release(rsim *w, gproc *p)                /* cmb_resource_release, :234-250 */
+{
+    w->holds[p - w->proc] = false;
+    w->holder = NULL;
+    r_record(w);
+    g_signal(&w->s, &w->guard, w->holder == NULL);
+}
+
+static void r_body(rsim *w, gproc *p, int64_t sig)
+{
+    gsim *s = &w->s;
+    const int id = (int)(p - w->proc);
+    switch (p->pc) {
+    case 0:
+        if (id < 3) {                                   /* preemptable */
+            for (;;) {
+                if (w->holder == NULL) {                /* cmb_resource_acquire, :191-229 */
+                    r_grab(w, p);
+                    r_record(w);
+                    sig = SIG_SUCCESS;
+                }
+                else {
+                    g_wait_begin(s, &w->guard, p);
+                    p->pc = 1;
+                    return;
+    case 1:
+                    sig = g_wait_end(s, &w->guard, p, sig);
+                    if (sig == SIG_SUCCESS) {
+                        r_grab(w, p);
+                        r_record(w);
+                    }
+                }
+                if (sig == SIG_SUCCESS) {
+                    s->res->counter[0] += 1u;
+                    w->since[id] = s->now;
+                    g_hold_begin(s, p, port_exponential(&s->rng, 1.0));
+                    p->pc = 2;
+                    return;
+    case 2:
+                    sig = g_hold_end(s, p, sig);
+                    if (sig == SIG_SUCCESS) {
+                        r_release(w, p);
+                        s->res->sum_wait += s->now - w->since[id];
+                    }
+                    else {
+                        s->res->counter[1] += 1u;
+                        if (s->res->counter[5] == 0u) {
+                            memcpy(&s->res->counter[4], &s->now, 8);
+                            s->res->counter[5] = (uint64_t)id + 1u;
+                        }
+                    }
+                }
+                g_hold_begin(s, p, port_exponential(&s->rng, 1.0));
+                p->pc = 3;
+                return;
+    case 3:
+                (void)g_hold_end(s, p, sig);
+            }
+        }
+        for (;;) {                                      /* preempter */
+            if (w->holder == NULL) {                    /* cmb_resource_preempt, :270-320 */
+                r_grab(w, p);
+                r_record(w);
+            }
+            else if (p->prio >= w->holder->prio) {
+                gproc *victim = w->holder;
+                w->holds[victim - w->proc] = false;
+                g_cancel_awaiteds(s, p);                /* sic: the CALLER's awaiteds */
+                w->holder = NULL;
+                g_schedule(s, ACT_WAKE_PREEMPT, victim, SIG_PREEMPTED, s->now, victim->prio);
+                r_grab(w, p);
+            }
+            else {
+                g_wait_begin(s, &w->guard, p);
+                p->pc = 10;
+                return;
+    case 10:
+                sig = g_wait_end(s, &w->guard, p, sig);
+                if (sig == SIG_SUCCESS) {
+                    r_grab(w, p);
+                    r_record(w);
+                }
+            }
+            s->res->counter[2] += 1u;
+            g_hold_begin(s, p, port_exponential(&s->rng, 1.0));
+            p->pc = 11;
+            return;
+    case 11:
+            (void)g_hold_end(s, p, sig);
+            r_release(w, p);
+            g_hold_begin(s, p, port_exponential(&s->rng, 1.0));
+            p->pc = 12;
+            return;
+    case 12:
+            (void)g_hold_end(s, p, sig);
+        }
+    }
+}
+
+static void run_resource(uint64_t seed, uint64_t duration, uint64_t trace_cap, uint64_t *trace_key,
+                         double *trace_time, port_result *out)
+{
+    rsim *w = calloc(1, sizeof(*w));
+    gsim *s = &w->s;
+    memset(out, 0, sizeof(*out));
+    s->res = out;
+    port_rng_init(&s->rng, seed);
+    heap_init(&s->fel, 3u, fel_before);
+    heap_init(&w->guard, 3u, guard_before);
+    port_wsummary_init(&w->hist);
+    r_record(w);                                        /* cmb_resource_start_recording: idle at t = 0 */
+    for (int i = 0; i < 4; i++) {
+        w->proc[i].prio = (i < 3) ? port_dice(&s->rng, -5, 5) : 0;
+        g_schedule(s, ACT_START, &w->proc[i], 0, s->now, w->proc[i].prio);
+    }
+    g_schedule(s, ACT_USER_END, w, 0, (double)duration, 0);
+
+    uint64_t n = 0u;
+    for (;;) {
+        if (s->fel.count > out->max_fel) {
+            out->max_fel = s->fel.count;
+        }
+        if (!heap_pop(&s->fel)) {
+            break;
+        }
+        const heap_tag ev = s->fel.slot[0];
+        s->now = ev.d;
+        if (n < trace_cap) {
+            trace_key[n] = ev.key;
+            trace_time[n] = s->now;
+        }
+        n++;
+        gproc *p = (gproc *)(intptr_t)ev.item[1];
+        switch ((int)ev.item[0]) {
+        case ACT_START:
+            p->status = ST_RUNNING;
+            p->pc = 0;
+            r_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_TIME:
+            (void)aw_remove(p, AW_TIME, false, ev.key, NULL);
+            r_body(w, p, ev.item[2]);
+            break;
+        case ACT_WAKE_RESOURCE:
+        case ACT_WAKE_PREEMPT:
+            if (p->status == ST_RUNNING) {
+                r_body(w, p, ev.item[2]);
+            }
+            break;
+        case ACT_USER_END:
+            for (int i = 0; i < 4; i++) {               /* cmb_process_stop + resource_drop_holder, :45-57 */
+                gproc *q = &w->proc[i];
+                if (q->status != ST_RUNNING) {
+                    continue;
+                }
+                q->status = ST_FINISHED;
+                g_cancel_awaiteds(s, q);
+                if (w->holds[i]) {
+                    w->holds[i] = false;
+                    w->holder = NULL;
+                    r_record(w);
+                    g_signal(s, &w->guard, true);
+                }
+            }
+            break;
+        }
+    }
+    out->events = n;
+    out->t_end = s->now;
+    r_record(w);                                        /* cmb_resource_stop_recording */
+    memcpy(&out->counter[3], &w->hist.ds.m1, 8);
+    out->max_queue = w->hist.ds.count;
+    out->objects = out->counter[0] + out->counter[2];
+    heap_free(&s->fel);
+    heap_free(&w->guard);
+    free(w);
+}
+
 /* ------------------------------------------------- experiment executive */
 
 typedef struct {
@@ -3889,6 +4100,10 @@ static void *worker(void *arg)
         const uint64_t k = __atomic_fetch_add(&j->next, 1u, __ATOMIC_RELAXED);
         if (k >= j->count) {
             break;
+        }
+        if (j->model == 14) {
+            run_resource(port_fmix64(j->master_seed, j->first + k), j->num_objects, 0u, NULL, NULL, &j->out[k]);
+            continue;
         }
         if (j->model == 10) {
             run_harbor(j->servers, port_fmix64(j->master_seed, j->first + k), j->num_objects,
@@ -3957,6 +4172,10 @@ int port_trace_trial(int model, int servers, uint64_t seed, uint64_t num_objects
                      double arr_mean, double srv_mean, uint64_t trace_cap,
                      uint64_t *trace_key, double *trace_time, port_result *out)
 {
+    if (model == 14) {
+        run_resource(seed, num_objects, trace_cap, trace_key, trace_time, out);
+        return 0;
+    }
     if (model == 10) {
         run_harbor(servers, seed, num_objects, arr_mean, srv_mean, trace_cap, trace_key, trace_time, out);
         return 0;

@@ -1478,6 +1478,110 @@ static void run_harbor_trial(struct ref_trial *t)
     free(w);
 }
 
+/* ------------------------------------------------- model 14: test/test_resource.c as it stands
+ *
+ * Three "preemptable" processes with random priorities and one "preempter" (priority 0) competing for one
+ * cmb_resource whose usage history is recorded; an end event stops the four.  No nuisance.  With duration 25 and
+ * seed 0x34f05c64d7ad598f this is test/reference/resource.txt: history "N 30 Mean 0.9816", and Target_3 loses
+ * the resource to the preempter at t = 6.3280.
+ * counters: [0] acquisitions by the targets [1] PREEMPTED received [2] acquisitions by the preempter
+ *           [3] time-weighted mean utilisation (bits) [4] time of the first pre-emption (bits) [5] its victim + 1
+ * sum_wait = sum of the targets' completed tenures; max_queue = history samples with a duration
+ */
+struct r_world {
+    struct ref_trial *trl;
+    struct cmb_resource *res;
+    struct cmb_process *proc[4];
+};
+
+static void *r_target_body(struct cmb_process *me, void *vw)
+{
+    struct r_world *w = vw;
+    for (;;) {
+        int64_t sig = cmb_resource_acquire(w->res);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            w->trl->counter[0] += 1u;
+            const double since = cmb_time();
+            sig = cmb_process_hold(cmb_random_exponential(1.0));
+            if (sig == CMB_PROCESS_SUCCESS) {
+                cmb_resource_release(w->res);
+                w->trl->sum_wait += cmb_time() - since;
+            }
+            else {
+                w->trl->counter[1] += 1u;
+                if (w->trl->counter[5] == 0u) {
+                    const double when = cmb_time();
+                    memcpy(&w->trl->counter[4], &when, 8);
+                    for (unsigned i = 0u; i < 3u; i++) {
+                        if (w->proc[i] == me) {
+                            w->trl->counter[5] = i + 1u;
+                        }
+                    }
+                }
+            }
+        }
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+    }
+}
+
+static void *r_preempter_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct r_world *w = vw;
+    for (;;) {
+        (void)cmb_resource_preempt(w->res);
+        w->trl->counter[2] += 1u;
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        cmb_resource_release(w->res);
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+    }
+}
+
+static void r_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct r_world *w = subject;
+    for (unsigned i = 0u; i < 4u; i++) {
+        cmb_process_stop(w->proc[i], NULL);
+    }
+}
+
+static void run_resource_trial(struct ref_trial *t)
+{
+    struct r_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->res = cmb_resource_create();
+    cmb_resource_initialize(w->res, "Resource_1");
+    cmb_resource_start_recording(w->res);
+    for (unsigned i = 0u; i < 3u; i++) {
+        w->proc[i] = cmb_process_create();
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_initialize(w->proc[i], "Target", r_target_body, w, pri);
+        cmb_process_start(w->proc[i]);
+    }
+    w->proc[3] = cmb_process_create();
+    cmb_process_initialize(w->proc[3], "Preempter", r_preempter_body, w, 0);
+    cmb_process_start(w->proc[3]);
+    (void)cmb_event_schedule(r_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    cmb_resource_stop_recording(w->res);
+    struct cmb_wtdsummary ws;
+    cmb_wtdsummary_initialize(&ws);
+    (void)cmb_timeseries_summarize(cmb_resource_history(w->res), &ws);
+    const double mean = cmb_wtdsummary_mean(&ws);
+    memcpy(&t->counter[3], &mean, 8);
+    t->max_queue = cmb_wtdsummary_count(&ws);
+    t->objects = t->counter[0] + t->counter[2];
+    for (unsigned i = 0u; i < 4u; i++) {
+        cmb_process_terminate(w->proc[i]);
+        cmb_process_destroy(w->proc[i]);
+    }
+    cmb_resource_destroy(w->res);
+    free(w);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void pump_events(struct ref_trial *t)
@@ -1577,7 +1681,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 10) {
+    if (t->model == 14) {
+        run_resource_trial(t);
+    }
+    else if (t->model == 10) {
         run_harbor_trial(t);
     }
     else if (t->model == 8) {

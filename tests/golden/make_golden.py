@@ -39,10 +39,11 @@ MODELS = {0: dict(arr=1 / 0.9, srv=1.0, servers=1), 1: dict(arr=1.25, srv=1.0, s
           10: dict(arr=2.0, srv=8.0, servers=10),    # model 10: the harbor of test/test_condition.c (num_objects = hours)
           11: dict(arr=1.0, srv=1.0, servers=10),    # model 11: test/test_objectqueue.c with the queue history on
           12: dict(arr=1.0, srv=1.0, servers=10),    # model 12: test/test_buffer.c as it stands
-          13: dict(arr=1.0, srv=1.0, servers=10)}    # model 13: test/test_priorityqueue.c
+          13: dict(arr=1.0, srv=1.0, servers=10),    # model 13: test/test_priorityqueue.c
+          14: dict(arr=1.0, srv=1.0, servers=1)}     # model 14: test/test_resource.c as it stands
 # the reference's own golden runs (test/reference/*.txt) that a model reproduces: model -> (file, size)
 GOLDEN_RUNS = {10: ("condition.txt", 24 * 7 * 52 * 100), 11: ("objectqueue.txt", 1_000_000),
-               12: ("buffer.txt", 10_000), 13: ("priorityqueue.txt", 1_000_000)}
+               12: ("buffer.txt", 10_000), 13: ("priorityqueue.txt", 1_000_000), 14: ("resource.txt", 25)}
 FULL_SIZE_KAT = (0, 1, 2, 9)             # 10^6 objects with the KAT seed
 
 

@@ -807,3 +807,33 @@ def test_host_buffer_api_chunks_large_experiments(cb, port, monkeypatch):
     cb.cimba_run_experiment(parts, num_objects=700, master_seed=KAT_SEED)
     for f in ("events", "obj_cnt", "sum_wait", "t_end", "avg_wait", "status"):
         assert np.array_equal(whole[f], parts[f]), f
+
+
+@pytest.mark.parametrize("dur", [1, 2, 25, 300, 3000])
+def test_resource_with_preemption_matches_oracle(cb, port, dur):
+    """Model 14 = test/test_resource.c as it stands: acquire / release / preempt, wakeup_event_preempt, the usage
+    history as a time-weighted summary, the end-of-run drop."""
+    n = 96
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=dur, master_seed=KAT_SEED, model=cb.MODEL_RESOURCE_RECORDED)
+    want = run_trials(port, "port", 14, 1, KAT_SEED, 0, n, dur, 1.0, 1.0)
+    _compare(res, want, ("resource", dur))
+    assert _counts(res.counters) == [w.counters() for w in want]
+    assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
+
+
+def test_resource_reproduces_the_reference_golden_file_on_device(cb, port, golden):
+    """test/reference/resource.txt on the GPU: N 30, mean 0.9816, Target_3 pre-empted at t = 6.3280 - and the
+    pop order of the whole 85-event run."""
+    import struct
+    master = _inverse_fmix64(KAT_SEED)
+    t = [x for x in golden["trials"] if x["model"] == 14 and x["num_objects"] == 25 and x["seed"] == KAT_SEED][-1]
+    res = cb.run_trials(1, arr_mean=1.0, srv_mean=1.0, num_objects=25, master_seed=master,
+                        model=cb.MODEL_RESOURCE_RECORDED, trace_cap=128)
+    c = _counts(res.counters)[0]
+    f = lambda u: struct.unpack("<d", struct.pack("<Q", u))[0]
+    assert int(res.max_queue[0]) == 30 and "%.4f" % f(c[3]) == "0.9816"
+    assert "%.4f" % f(c[4]) == "6.3280" and c[5] == 3 and c[1] == 1
+    assert c == t["counters"] and int(res.events[0]) == t["events"] == 85
+    r, k, tt = trace_trial(port, "port", 14, 1, KAT_SEED, 25, 1.0, 1.0, 128)
+    assert list(res.trace_key.cpu().numpy()[0, :85]) == k
+    assert np.array_equal(_u64(res.trace_time.cpu().numpy()[0, :85]), _u64(np.array(tt)))

@@ -156,6 +156,19 @@ def test_buffer_reproduces_the_reference_golden_file(port, golden):
     assert r.max_queue == 41876 and "%.3f" % mean == "4.980"
 
 
+def test_resource_reproduces_the_reference_golden_file(port, golden):
+    """test/reference/resource.txt (test/test_resource.c, seed 0x34f05c64d7ad598f, 25 time units): usage history
+    N 30, time-weighted mean 0.9816, and the one logged pre-emption: Target_3 at t = 6.3280."""
+    import struct
+    t = [x for x in golden["trials"] if x["model"] == 14 and x["num_objects"] == 25 and x["seed"] == KAT_SEED][-1]
+    r, _, _ = trace_trial(port, "port", 14, 1, KAT_SEED, 25, 1.0, 1.0, 0)
+    assert (r.events, float.hex(r.t_end), float.hex(r.sum_wait)) == (t["events"], t["t_end"], t["sum_wait"])
+    assert r.counters() == t["counters"] and r.max_queue == t["max_queue"] == 30
+    f = lambda u: struct.unpack("<d", struct.pack("<Q", u))[0]
+    c = r.counters()
+    assert "%.4f" % f(c[3]) == "0.9816" and "%.4f" % f(c[4]) == "6.3280" and c[5] == 3 and c[1] == 1
+
+
 def test_experiment_seeding_matches_golden(port, golden):
     g = golden["experiment_mm1"]
     res = run_trials(port, "port", 0, 1, g["master_seed"], 0, len(g["trials"]), g["num_objects"], 1 / 0.9, 1.0)
@@ -239,7 +252,7 @@ def test_heap_script_orders_like_the_comparator(port):
                                                    (10, 2.0, 8.0, 10), (10, 1.2, 8.0, 4), (10, 0.9, 8.0, 3),
                                                    (11, 1.0, 1.0, 10), (11, 0.5, 1.0, 2),
                                                    (12, 1.0, 1.0, 10), (12, 0.5, 1.0, 4),
-                                                   (13, 1.0, 1.0, 10), (13, 0.5, 1.0, 3)])
+                                                   (13, 1.0, 1.0, 10), (13, 0.5, 1.0, 3), (14, 1.0, 1.0, 1)])
 def test_port_equals_live_reference(port, ref, model, arr, srv, servers):
     if ref is None:
         pytest.skip("oracle/_ref not built here (no /root/reference)")
