@@ -88,6 +88,24 @@ def test_wtdsummary_add_and_merge_match_reference_golden(cb, golden):
     assert z.add(3.0, 0.0) == 0 and z.count() == 0    # zero weight: ignored (src/cmb_wtdsummary.c:92-94)
 
 
+def test_alias_tables_match_the_oracle(cb, port):
+    """cimba_b200_alias_create (host code of the C-ABI library) vs the oracle's restatement of
+    cmb_random_alias_create (src/cmb_random.c:688-752), which test_oracle_port pins to the reference."""
+    for probs in ([0.05, 0.25, 0.4, 0.1, 0.2], [1.0], [0.5, 0.5], [0.999, 0.0005, 0.0005], [1 / 7] * 7,
+                  [0.01 * k for k in range(1, 14)] + [0.09]):
+        n = len(probs)
+        uprob, alias = cb.alias_create(probs)
+        pa = (C.c_double * n)(*probs)
+        pu = (C.c_uint64 * n)()
+        pal = (C.c_uint * n)()
+        port.port_alias_create.restype = None
+        port.port_alias_create.argtypes = [C.c_uint, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint)]
+        port.port_alias_create(n, pa, pu, pal)
+        assert uprob == list(pu) and alias == list(pal), probs
+    with pytest.raises(cb.CimbaError):
+        cb.alias_create([0.5, 0.2])                    # does not sum to one (src/cmb_random.c:634-642)
+
+
 WORKER = textwrap.dedent("""
     import os, sys, json
     sys.path.insert(0, {root!r})
