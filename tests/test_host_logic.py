@@ -157,3 +157,22 @@ def test_two_rank_gloo_merge_equals_single_process_merge(cb, tmp_path):
     w = np.random.default_rng(12).uniform(0.1, 2.0, size=2000)
     wwant = cb.WtdSummary.merge(_wtd_of(cb, x[:1000], w[:1000]), _wtd_of(cb, x[1000:], w[1000:]))
     assert wgot[0] == [float.hex(v) for v in wwant.fields()]
+
+
+def test_bench_reference_arm_prints_one_contract_line(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): exactly one JSON line on
+    stdout with the contract's keys, whatever the libraries print elsewhere."""
+    import json
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-trials", "8", "--objects", "2000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "events/s" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
