@@ -81,6 +81,12 @@ SYMBOLS = {
     "cimba_b200_datasummary_mean": (C.c_double, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_variance": (C.c_double, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_stddev": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_count": (C.c_uint64, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_max": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_min": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_skewness": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_kurtosis": (C.c_double, [C.POINTER(DataSummaryStruct)]),
+    "cimba_b200_datasummary_print": (None, [C.POINTER(DataSummaryStruct), C.c_void_p, C.c_int]),
     "cimba_b200_summarize_weighted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cimba_b200_merge_weighted_rows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cimba_b200_wtdsummary_initialize": (None, [C.POINTER(WtdSummaryStruct)]),
@@ -88,6 +94,10 @@ SYMBOLS = {
     "cimba_b200_wtdsummary_merge": (C.c_uint64, [C.POINTER(WtdSummaryStruct)] * 3),
     "cimba_b200_wtdsummary_mean": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
     "cimba_b200_wtdsummary_variance": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_stddev": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_skewness": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_kurtosis": (C.c_double, [C.POINTER(WtdSummaryStruct)]),
+    "cimba_b200_wtdsummary_print": (None, [C.POINTER(WtdSummaryStruct), C.c_void_p, C.c_int]),
     "cimba_b200_fmix64": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "cimba_b200_rng_draws": (C.c_int, [C.c_uint64, C.c_int, C.c_double, C.c_double,
                                        C.c_uint64, C.c_void_p, C.c_void_p]),

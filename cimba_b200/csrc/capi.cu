@@ -1020,4 +1020,48 @@ double cimba_b200_datasummary_stddev(const cimba_b200_datasummary *s)
     return sqrt(cimba_b200_datasummary_variance(s));
 }
 
+uint64_t cimba_b200_datasummary_count(const cimba_b200_datasummary *s) { return s->count; }
+double cimba_b200_datasummary_max(const cimba_b200_datasummary *s) { return s->max; }
+double cimba_b200_datasummary_min(const cimba_b200_datasummary *s) { return s->min; }
+
+double cimba_b200_datasummary_skewness(const cimba_b200_datasummary *s)
+{   // src/cmb_datasummary.c:214-230: population estimate, then the finite-sample correction
+    if (s->count <= 2u) return 0.0;
+    const double n = (double)s->count;
+    const double g = sqrt(n) * s->m3 / pow(s->m2, 1.5);
+    return sqrt(n * (n - 1.0)) * g / (n - 2.0);
+}
+
+double cimba_b200_datasummary_kurtosis(const cimba_b200_datasummary *s)
+{   // src/cmb_datasummary.c:233-249: sample excess kurtosis
+    if (s->count <= 3u) return 0.0;
+    const double n = (double)s->count;
+    const double g = n * s->m4 / (s->m2 * s->m2) - 3.0;
+    return (n - 1.0) / ((n - 2.0) * (n - 3.0)) * ((n + 1.0) * g + 6.0);
+}
+
+void cimba_b200_datasummary_print(const cimba_b200_datasummary *s, FILE *fp, int lead_ins)
+{   // src/cmb_datasummary.c:168-212: one line, a column only when the count supports the statistic
+    if (s == nullptr || fp == nullptr) return;
+    const bool li = lead_ins != 0;
+    fprintf(fp, "%s%8llu", li ? "N " : "", (unsigned long long)s->count);
+    if (s->count > 0u) fprintf(fp, "%s%#8.4g", li ? "  Mean " : "\t", cimba_b200_datasummary_mean(s));
+    if (s->count > 1u) {
+        const double var = cimba_b200_datasummary_variance(s);
+        fprintf(fp, "%s%#8.4g", li ? "  StdDev " : "\t", sqrt(var));
+        fprintf(fp, "%s%#8.4g", li ? "  Variance " : "\t", var);
+    }
+    if (s->count > 2u) fprintf(fp, "%s%#8.4g", li ? "  Skewness " : "\t", cimba_b200_datasummary_skewness(s));
+    if (s->count > 3u) fprintf(fp, "%s%#8.4g", li ? "  Kurtosis " : "\t", cimba_b200_datasummary_kurtosis(s));
+    fprintf(fp, "\n");
+}
+
+double cimba_b200_wtdsummary_stddev(const cimba_b200_wtdsummary *s) { return cimba_b200_datasummary_stddev(&s->base); }
+double cimba_b200_wtdsummary_skewness(const cimba_b200_wtdsummary *s) { return cimba_b200_datasummary_skewness(&s->base); }
+double cimba_b200_wtdsummary_kurtosis(const cimba_b200_wtdsummary *s) { return cimba_b200_datasummary_kurtosis(&s->base); }
+void cimba_b200_wtdsummary_print(const cimba_b200_wtdsummary *s, FILE *fp, int lead_ins)
+{
+    if (s != nullptr) cimba_b200_datasummary_print(&s->base, fp, lead_ins);
+}
+
 }  // extern "C"

@@ -18,6 +18,23 @@ import torch
 from ._lib import DataSummaryStruct, WtdSummaryStruct, lib, check
 
 
+def _printed(fn, struct, lead_ins: bool) -> str:
+    """Run one of the C print functions on a libc FILE* and return what it wrote."""
+    import tempfile
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    with tempfile.NamedTemporaryFile() as tmp:
+        fp = libc.fopen(tmp.name.encode(), b"w")
+        if not fp:
+            raise OSError(f"fopen({tmp.name}) failed")
+        fn(C.byref(struct), fp, 1 if lead_ins else 0)
+        libc.fclose(fp)
+        with open(tmp.name) as f:
+            return f.read()
+
+
 class DataSummary:
     """Same fields and semantics as the reference's ``struct cmb_datasummary``."""
 
@@ -52,6 +69,17 @@ class DataSummary:
 
     def stddev(self) -> float:
         return lib.cimba_b200_datasummary_stddev(C.byref(self._s))
+
+    def skewness(self) -> float:
+        return lib.cimba_b200_datasummary_skewness(C.byref(self._s))
+
+    def kurtosis(self) -> float:
+        """Sample excess kurtosis (src/cmb_datasummary.c:233-249)."""
+        return lib.cimba_b200_datasummary_kurtosis(C.byref(self._s))
+
+    def line(self, lead_ins: bool = True) -> str:
+        """The text cmb_datasummary_print writes (src/cmb_datasummary.c:168-212)."""
+        return _printed(lib.cimba_b200_datasummary_print, self._s, lead_ins)
 
     def half_width_95(self) -> float:
         """1.96 * stddev / sqrt(n), as printed by benchmark/MM1_multi.c:151-157."""
@@ -112,6 +140,19 @@ class WtdSummary:
 
     def variance(self) -> float:
         return lib.cimba_b200_wtdsummary_variance(C.byref(self._s))
+
+    def stddev(self) -> float:
+        return lib.cimba_b200_wtdsummary_stddev(C.byref(self._s))
+
+    def skewness(self) -> float:
+        return lib.cimba_b200_wtdsummary_skewness(C.byref(self._s))
+
+    def kurtosis(self) -> float:
+        return lib.cimba_b200_wtdsummary_kurtosis(C.byref(self._s))
+
+    def line(self, lead_ins: bool = True) -> str:
+        """The text cmb_wtdsummary_print writes (it prints the data summary part)."""
+        return _printed(lib.cimba_b200_wtdsummary_print, self._s, lead_ins)
 
     # --- the 8-word row {count (u64), min, max, m1..m4, wsum (f64 bits)} the engine writes ---
     def to_row(self) -> List[int]:

@@ -32,6 +32,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -252,6 +253,15 @@ uint64_t cimba_b200_datasummary_merge(cimba_b200_datasummary *tgt,
 double   cimba_b200_datasummary_mean(const cimba_b200_datasummary *dsp);
 double   cimba_b200_datasummary_variance(const cimba_b200_datasummary *dsp);
 double   cimba_b200_datasummary_stddev(const cimba_b200_datasummary *dsp);
+/* include/cmb_datasummary.h:133-179 (count / max / min), src/cmb_datasummary.c:214-249 (sample skewness and
+ * sample excess kurtosis with the finite-sample corrections), :168-212 (print: "N", "Mean", "StdDev", "Variance",
+ * "Skewness", "Kurtosis" as %#8.4g, each only when the count supports it; lead_ins = 0 prints tab-separated). */
+uint64_t cimba_b200_datasummary_count(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_max(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_min(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_skewness(const cimba_b200_datasummary *dsp);
+double   cimba_b200_datasummary_kurtosis(const cimba_b200_datasummary *dsp);
+void     cimba_b200_datasummary_print(const cimba_b200_datasummary *dsp, FILE *fp, int lead_ins);
 
 /* cmb_wtdsummary (include/cmb_wtdsummary.h:41-44: the data summary plus the sum of weights;
  * src/cmb_wtdsummary.c:82-137 add, :152-194 merge).  Same arithmetic as the device kernels. */
@@ -267,6 +277,11 @@ uint64_t cimba_b200_wtdsummary_merge(cimba_b200_wtdsummary *tgt,
                                      const cimba_b200_wtdsummary *ws2);
 double   cimba_b200_wtdsummary_mean(const cimba_b200_wtdsummary *wsp);
 double   cimba_b200_wtdsummary_variance(const cimba_b200_wtdsummary *wsp);
+/* include/cmb_wtdsummary.h:208-250 and src/cmb_wtdsummary.c (print): all delegate to the data summary part. */
+double   cimba_b200_wtdsummary_stddev(const cimba_b200_wtdsummary *wsp);
+double   cimba_b200_wtdsummary_skewness(const cimba_b200_wtdsummary *wsp);
+double   cimba_b200_wtdsummary_kurtosis(const cimba_b200_wtdsummary *wsp);
+void     cimba_b200_wtdsummary_print(const cimba_b200_wtdsummary *wsp, FILE *fp, int lead_ins);
 
 /* cmb_random_fmix64 (src/cmb_random.c:70-80): per-trial seed derivation. */
 uint64_t cimba_b200_fmix64(uint64_t seed, uint64_t nonce);

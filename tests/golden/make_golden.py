@@ -56,8 +56,52 @@ def checksum(a):
     return {"xor": int(np.bitwise_xor.reduce(u)), "sum": int(np.add.reduce(u, dtype=np.uint64))}
 
 
+def summary_stats(ref, x):
+    """Skewness, excess kurtosis and the printed line of the reference's own cmb_datasummary for prefixes of x
+    (the counts 0..4 exercise every column rule of cmb_datasummary_print, src/cmb_datasummary.c:168-212)."""
+    import tempfile
+
+    class DS(C.Structure):          # include/cmb_datasummary.h:42-51
+        _fields_ = [("cookie", C.c_uint64), ("count", C.c_uint64), ("min", C.c_double), ("max", C.c_double),
+                    ("m1", C.c_double), ("m2", C.c_double), ("m3", C.c_double), ("m4", C.c_double)]
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    for name in ("cmb_datasummary_skewness", "cmb_datasummary_kurtosis"):
+        getattr(ref, name).restype = C.c_double
+        getattr(ref, name).argtypes = [C.POINTER(DS)]
+    ref.cmb_datasummary_add.argtypes = [C.POINTER(DS), C.c_double]
+    ref.cmb_datasummary_print.argtypes = [C.POINTER(DS), C.c_void_p, C.c_bool]
+    stats = {}
+    for n in (0, 1, 2, 3, 4, 10, 1000):
+        ds = DS()
+        ref.cmb_datasummary_initialize(C.byref(ds))
+        for v in x[:n]:
+            ref.cmb_datasummary_add(C.byref(ds), float(v))
+        lines = []
+        for lead in (True, False):
+            with tempfile.NamedTemporaryFile() as tmp:
+                fp = libc.fopen(tmp.name.encode(), b"w")
+                ref.cmb_datasummary_print(C.byref(ds), fp, lead)
+                libc.fclose(fp)
+                lines.append(open(tmp.name).read())
+        stats[str(n)] = {"skewness": float.hex(ref.cmb_datasummary_skewness(C.byref(ds))),
+                         "kurtosis": float.hex(ref.cmb_datasummary_kurtosis(C.byref(ds))),
+                         "line": lines[0], "line_plain": lines[1]}
+    return stats
+
+
 def main():
     ref = load_ref()
+    if "--only-summary-stats" in sys.argv:      # refresh one block; everything else stays as committed
+        path = ROOT / "tests/golden/reference_vectors.json"
+        out = json.loads(path.read_text())
+        x = np.array([float.fromhex(v) for v in out["summary"]["x"]])
+        out["summary_stats"] = summary_stats(ref, x)
+        path.write_text(json.dumps(out, indent=0) + "\n")
+        print("updated summary_stats in", path)
+        return
     if ref is None:
         sys.exit("oracle/_ref is not built; run `make -C oracle ref` first")
     out = {"source": "ambonvik/cimba via oracle/_ref (unmodified reference build)"}
@@ -136,6 +180,7 @@ def main():
         ref.ref_datasummary_split_merge(xs, na, 1000, o7); summ[f"data_merge_{na}"] = hexes(o7[:7])
         ref.ref_wtdsummary_split_merge(xs, wsp, na, 1000, o8); summ[f"wtd_merge_{na}"] = hexes(o8[:8])
     out["summary"] = summ
+    out["summary_stats"] = summary_stats(ref, x)
 
     path = ROOT / "tests/golden/reference_vectors.json"
     path.write_text(json.dumps(out, indent=0) + "\n")

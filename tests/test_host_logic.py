@@ -31,6 +31,24 @@ def test_datasummary_merge_matches_reference_golden(cb, golden, na):
     assert [float.hex(v) for v in m.to_list()[:7]] == s[f"data_merge_{na}"]
 
 
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 10, 1000])
+def test_skewness_kurtosis_and_print_match_reference_golden(cb, golden, n):
+    """cmb_datasummary_skewness / _kurtosis / _print (src/cmb_datasummary.c:168-249) of the reference itself,
+    recorded by tests/golden/make_golden.py: same bits, same text, column rules included (n = 0..4)."""
+    x = [float.fromhex(v) for v in golden["summary"]["x"]]
+    want = golden["summary_stats"][str(n)]
+    ds = cb.DataSummary.of(x[:n])
+    assert float.hex(ds.skewness()) == want["skewness"]
+    assert float.hex(ds.kurtosis()) == want["kurtosis"]
+    assert ds.line(True) == want["line"] and ds.line(False) == want["line_plain"]
+    ws = cb.WtdSummary()
+    for v in x[:n]:
+        ws.add(v, 1.0)
+    assert ws.count() == n and ws.line(True).startswith("N ")
+    if n > 3:
+        assert math.isfinite(ws.skewness()) and math.isfinite(ws.kurtosis()) and ws.stddev() > 0.0
+
+
 def test_merge_with_empty_side_and_roundtrip(cb):
     a = cb.DataSummary.of([1.0, 2.0, 4.0])
     e = cb.DataSummary()
