@@ -92,7 +92,45 @@ def summary_stats(ref, x):
     return stats
 
 
+def awacs_vectors():
+    """tests/golden/awacs_vectors.json from the unmodified tutorial source (oracle/_ref/libawacs_ref.so)."""
+    import hashlib
+    from oracle_libs import AWACS_TERRAIN_SEED, awacs_terrain, awacs_trial, load_awacs_ref
+    ref = load_awacs_ref()
+    if ref is None:
+        sys.exit("oracle/_ref/libawacs_ref.so is not built; run `make -C oracle ref` first")
+    width, height, duration = 12.0, 10.0, 0.05
+    m, cols, rows, geom = awacs_terrain(ref, "ref", AWACS_TERRAIN_SEED, width, height)
+    out = {"source": "tutorial/tut_5_1.c, unmodified, behind oracle/ref_build/awacs_stubs/hdf5.h",
+           "terrain": {"seed": AWACS_TERRAIN_SEED, "width_nm": width, "height_nm": height, "cols": cols, "rows": rows,
+                       "geom": [float(v).hex() for v in geom], "map_sha256": hashlib.sha256(m.tobytes()).hexdigest()},
+           "duration_h": duration, "trials": [], "platform": {}}
+    for i in range(4):
+        seed = int(ref_fmix(KAT_SEED, i))
+        o, keys, times, per = awacs_trial(ref, "ref", seed, duration, trace_cap=4000)
+        trace = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
+        out["trials"].append({"seed": seed, "events": o.events, "t_end": o.t_end.hex(), "num_found": o.num_found,
+                              "tds_count": list(o.tds_count), "mode_count": list(o.mode_count),
+                              "sum_x": o.sum_x.hex(), "sum_y": o.sum_y.hex(), "trace_sha256": trace.hexdigest(),
+                              "tds_sha256": hashlib.sha256(np.array(per["tds"], dtype=np.int32).tobytes()).hexdigest()})
+    six, r = (C.c_float * 6)(), C.c_float()
+    for t in (0.0, 1.0, 150.0, 700.5, 900.0, 1400.25, 2000.0, 86399.0):
+        ref.awacs_ref_platform_state(C.c_double(t), six, C.byref(r))
+        out["platform"][repr(t)] = [float(v).hex() for v in six] + [float(r.value).hex()]
+    path = ROOT / "tests/golden/awacs_vectors.json"
+    path.write_text(json.dumps(out, indent=0) + "\n")
+    print("wrote", path, path.stat().st_size, "bytes")
+
+
+def ref_fmix(seed, nonce):
+    lib = load_ref()
+    return lib.ref_fmix64(seed, nonce)
+
+
 def main():
+    if "--only-awacs" in sys.argv:
+        awacs_vectors()
+        return
     ref = load_ref()
     if "--only-summary-stats" in sys.argv:      # refresh one block; everything else stays as committed
         path = ROOT / "tests/golden/reference_vectors.json"
@@ -185,6 +223,7 @@ def main():
     path = ROOT / "tests/golden/reference_vectors.json"
     path.write_text(json.dumps(out, indent=0) + "\n")
     print("wrote", path, path.stat().st_size, "bytes")
+    awacs_vectors()
 
 
 if __name__ == "__main__":

@@ -64,7 +64,8 @@ def _bind(lib, prefix):
 
 def load_port():
     so = ORACLE / "liboracle_port.so"
-    src = [ORACLE / "port/cimba_port.c", ORACLE / "port/cimba_port.h", ORACLE / "port/zig_tables.h"]
+    src = [ORACLE / "port/cimba_port.c", ORACLE / "port/awacs_port.c", ORACLE / "port/cimba_port.h",
+           ORACLE / "port/zig_tables.h"]
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in src):
         subprocess.run(["make", "-C", str(ORACLE), "port"], check=True, capture_output=True)
     lib = _bind(C.CDLL(str(so)), "port")
@@ -129,3 +130,66 @@ def rng_draws_ex(lib, prefix, seed, kind, params, n):
     rc = f(seed, kind, par, len(params), n, out)
     assert rc == 0, (prefix, kind, rc)
     return list(out)
+
+
+# ---------------------------------------------------------------- AWACS (tutorial/tut_5_1.c, BASELINE config 5)
+class AwacsOut(C.Structure):
+    _fields_ = [("events", C.c_uint64), ("t_end", C.c_double), ("num_found", C.c_uint32), ("tds_count", C.c_uint32 * 6),
+                ("mode_count", C.c_uint32 * 4), ("pad", C.c_uint32), ("sum_x", C.c_double), ("sum_y", C.c_double)]
+
+    def key(self):
+        return (self.events, self.t_end, self.num_found, list(self.tds_count), list(self.mode_count),
+                self.sum_x, self.sum_y)
+
+
+AWACS_TARGETS = 1000
+AWACS_TERRAIN_SEED = 0x34F05C64D7AD598F
+
+
+def load_awacs_ref():
+    """oracle/_ref/libawacs_ref.so = the UNMODIFIED tutorial source behind a stub hdf5.h; None when not built."""
+    so = ORACLE / "_ref/libawacs_ref.so"
+    if not so.exists():
+        return None
+    lib = C.CDLL(str(so))
+    lib.awacs_ref_map.restype = C.POINTER(C.c_float)
+    return lib
+
+
+def awacs_terrain(lib, prefix, seed, width_nm, height_nm):
+    """(map float32 [rows*cols], cols, rows, geom[6]) from the reference build ('ref') or the port ('port')."""
+    cols, rows, geom = C.c_uint32(), C.c_uint32(), (C.c_float * 6)()
+    if prefix == "ref":
+        lib.awacs_ref_terrain(C.c_uint64(seed), C.c_float(width_nm), C.c_float(height_nm), C.c_float(30.0),
+                              C.c_float(-10.0), C.byref(cols), C.byref(rows), geom)
+        n = cols.value * rows.value
+        m = np.ctypeslib.as_array(lib.awacs_ref_map(), shape=(n,)).copy()
+    else:
+        lib.port_awacs_grid(C.c_float(width_nm), C.c_float(height_nm), C.byref(cols), C.byref(rows))
+        m = np.empty(cols.value * rows.value, dtype=np.float32)
+        lib.port_awacs_terrain(C.c_uint64(seed), C.c_float(width_nm), C.c_float(height_nm), C.c_float(30.0),
+                               C.c_float(-10.0), m.ctypes.data_as(C.POINTER(C.c_float)), geom, None)
+    return m, cols.value, rows.value, np.array(list(geom), dtype=np.float32)
+
+
+def awacs_trial(lib, prefix, seed, duration_h, terrain=None, trace_cap=0):
+    """One trial: (AwacsOut, keys, times, per-target dict).  `terrain` = awacs_terrain(...) for the port; the
+    reference build uses the terrain its last awacs_ref_terrain call made."""
+    out = AwacsOut()
+    keys = (C.c_uint64 * max(1, trace_cap))()
+    times = (C.c_double * max(1, trace_cap))()
+    x, y = (C.c_float * AWACS_TARGETS)(), (C.c_float * AWACS_TARGETS)()
+    mode, tds, det = (C.c_int * AWACS_TARGETS)(), (C.c_int * AWACS_TARGETS)(), (C.c_int * AWACS_TARGETS)()
+    if prefix == "ref":
+        rc = lib.awacs_ref_trial(C.c_uint64(seed), C.c_double(duration_h), C.c_uint64(trace_cap), keys, times,
+                                 C.byref(out), x, y, mode, tds, det)
+    else:
+        m, cols, rows, geom = terrain
+        rc = lib.port_awacs_trial(C.c_uint64(seed), C.c_double(duration_h), m.ctypes.data_as(C.POINTER(C.c_float)),
+                                  C.c_uint32(cols), C.c_uint32(rows), geom.ctypes.data_as(C.POINTER(C.c_float)),
+                                  C.c_uint64(trace_cap), keys, times, C.byref(out), x, y, mode, tds, det)
+    assert rc == 0
+    n = min(trace_cap, out.events)
+    per = dict(x=np.array(x[:], dtype=np.float32), y=np.array(y[:], dtype=np.float32), mode=list(mode), tds=list(tds),
+               detected=list(det))
+    return out, list(keys)[:n], list(times)[:n], per
