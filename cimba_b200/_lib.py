@@ -17,7 +17,7 @@ LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
 
 NO_FIELD = C.c_size_t(-1).value
 
-MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED, MODEL_HARBOR, MODEL_GUARDED_RECORDED, MODEL_BUFFER_RECORDED, MODEL_PRIOQ_RECORDED, MODEL_RESOURCE_RECORDED = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
+MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED, MODEL_HARBOR, MODEL_GUARDED_RECORDED, MODEL_BUFFER_RECORDED, MODEL_PRIOQ_RECORDED, MODEL_RESOURCE_RECORDED, MODEL_AWACS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
 MAP_LANE, MAP_WARP = 1, 32
 
 OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -36,6 +36,13 @@ class DeviceJob(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("trace_cap", C.c_uint64), ("trace_key", C.c_void_p), ("trace_time", C.c_void_p),
     ]
+
+
+class AwacsTerrain(C.Structure):
+    """struct cimba_b200_awacs_terrain"""
+    _fields_ = [("map", C.c_void_p), ("cols", C.c_uint32), ("rows", C.c_uint32),
+                ("x_scale", C.c_float), ("y_scale", C.c_float),
+                ("x_min", C.c_float), ("x_max", C.c_float), ("y_min", C.c_float), ("y_max", C.c_float)]
 
 
 class Experiment(C.Structure):
@@ -75,6 +82,7 @@ SYMBOLS = {
     "cimba_b200_release_cache": (None, []),
     "cimba_b200_run_experiment_all_gpus": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment),
                                                      C.c_int]),
+    "cimba_b200_awacs_set_terrain": (C.c_int, [C.POINTER(AwacsTerrain)]),
     "cimba_b200_datasummary_initialize": (None, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_add": (C.c_uint64, [C.POINTER(DataSummaryStruct), C.c_double]),
     "cimba_b200_datasummary_merge": (C.c_uint64, [C.POINTER(DataSummaryStruct)] * 3),

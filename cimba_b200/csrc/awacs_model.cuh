@@ -1,0 +1,577 @@
+// awacs_model.cuh - the reference's AWACS model (tutorial/tut_5_1.c, BASELINE config 5), one trial per WARP.
+//
+// 1000 ground targets cycle hiding -> staging -> firing -> driving with exponential / Erlang dwell times
+// (tut_5_1.c:385-446); a radar process ticks every second and runs a five-stage detection chain over all of
+// them in float32 (:944-1036, :548-689) against a terrain map SHARED by every trial (one float per arc-second,
+// 14.4 GB at the tutorial's 1000 x 1000 nm - it lives in HBM once, read-only); the platform flies a racetrack
+// orbit given in closed form (:816-868); a progress-bar process holds 100 times (:1118-1137); an end event
+// stops everybody (:1100-1112).  oracle/port/awacs_port.c is the same model in plain C.
+//
+// Mapping onto the warp:
+//   * every lane carries the same generator state and executes every draw (the stream is per trial); the 32
+//     lanes differ only in which target they look at;
+//   * the event list: each target owns exactly one pending event, kept in its row of the per-trial state block
+//     (wake time + key); the radar, the end event and the progress bar own one each in registers.  The earliest
+//     target event is cached and found again by a 32-lane scan + REDUX only after a target event ran (about once
+//     per simulated second) - pop order is the total order (time, key) whatever the container;
+//   * one radar tick = three passes.  A: lanes take targets 32 at a time - dead reckoning, geometry, the three
+//     cheap tests (swept sector, horizon, nadir hole); survivors are appended to a list in target order.
+//     B: each survivor's line of sight is marched by the WHOLE warp (step i on lane i mod 32, four steps in
+//     flight per lane, one ballot per 128 steps): the reference's loop returns at the first step under the
+//     terrain, i.e. "any step is", which is order-free; neighbouring steps read neighbouring map cells.
+//     C: the unshielded survivors, in target order, compute their detection probability in parallel and then
+//     take their cmb_random_bernoulli draws one after the other - the only part that is serial by definition.
+//
+// Parity: the float32 functions the chain calls (sinf, cosf, atan2f, powf, expf) are evaluated in double and
+// rounded once, which reproduces a correctly rounded libm except within ~1e-8 of a rounding boundary, and
+// glibc's results wherever glibc rounds correctly (always for sqrtf and division, almost always for sinf / cosf /
+// expf / powf, not for its fdlibm atan2f).  A target passes or fails a test differently only if such a last-place
+// difference straddles the threshold, but when it does, the trial's one random stream shifts and everything after
+// differs: this model matches the oracle exactly on short runs and statistically on long ones.
+#pragma once
+
+#include "engine.cuh"
+#include "hold_deep.cuh"
+#include "rng.cuh"
+
+namespace cimba_b200 {
+
+constexpr int AWACS_BLOCK = 128;                // 4 trials per CTA
+constexpr int AWACS_TARGETS = 1000;             // NUM_TARGETS, tut_5_1.c:35
+constexpr int AWACS_STRIDE = 1024;              // rows per column of the state block
+// per-trial state block in HBM/L2, structure of arrays, AWACS_STRIDE entries each:
+//   float x, y, alt, dir, vel, time_s, rcs_now; uint32 flags; uint32 wake_key; double wake_t
+constexpr size_t AWACS_STATE_BYTES = (size_t)AWACS_STRIDE * (7 * 4 + 4 + 4 + 8);
+
+enum : uint32_t { AW_HIDING = 0, AW_STAGING = 1, AW_FIRING = 2, AW_DRIVING = 3 };
+enum : uint32_t { AW_UNDETERMINED = 0, AW_BEYOND_HORIZON, AW_NADIR_HOLE, AW_TERRAIN_SHIELDED, AW_MISSED, AW_DETECTED };
+constexpr uint32_t AW_F_MODE = 3u, AW_F_TDS_SHIFT = 4u, AW_F_TDS = 7u << 4, AW_F_FOUND = 1u << 8, AW_F_STARTED = 1u << 9;
+
+struct AwacsTerrain {           // struct terrain, tut_5_1.c:96-108
+    const float *map;
+    uint32_t cols, rows;
+    float x_scale, y_scale, x_min, x_max, y_min, y_max;
+};
+
+struct AwacsOrbit {             // struct racetrack after racetrack_initialize (:724-782), evaluated on the host
+    float start_time, orientation_r, length_m, turn_radius_m, altitude_m, velocity_ms;
+    float turn_dist_m, orbit_dist_m, side, roll_angle_r, rad_eff;
+    double cos_o, sin_o;        // cos / sin of orientation_r (:851-853), host libm
+};
+
+struct AwacsArgs {
+    uint64_t master_seed, first_trial, num_trials;
+    double   t_end_s;           // trial duration in seconds (struct trial.duration * 3600, :1213)
+    AwacsTerrain ter;
+    AwacsOrbit orbit;
+    unsigned char *state;       // [num_trials][AWACS_STATE_BYTES]
+    uint64_t *events, *objects;
+    double   *t_end, *sum_wait;
+    uint32_t *status, *max_queue;
+    uint64_t *counters;
+    uint64_t  trace_cap;
+    uint64_t *trace_key;
+    double   *trace_time;
+};
+
+// ---- float32 libm calls of the model, evaluated in double and rounded once
+__device__ __forceinline__ float aw_sinf(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float aw_cosf(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float aw_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+__device__ __forceinline__ float aw_powf(float a, float b) { return (float)pow((double)a, (double)b); }
+__device__ __forceinline__ float aw_expf(float x) { return (float)exp((double)x); }
+
+// terrain_index + terrain_elevation, tut_5_1.c:314-338
+__device__ __forceinline__ float aw_elevation(const AwacsTerrain &t, float x, float y)
+{
+    const int raw_col = (int)roundf(__fdiv_rn(x, t.x_scale)) + (int)(t.cols / 2u);
+    const int raw_row = (int)roundf(__fdiv_rn(y, t.y_scale)) + (int)(t.rows / 2u);
+    const uint32_t col = (uint32_t)(raw_col < 0 ? 0 : (raw_col >= (int)t.cols ? (int)t.cols - 1 : raw_col));
+    const uint32_t row = (uint32_t)(raw_row < 0 ? 0 : (raw_row >= (int)t.rows ? (int)t.rows - 1 : raw_row));
+    return __ldg(t.map + (size_t)row * t.cols + col);
+}
+
+struct AwacsPlatform { float x, y, dir, rol, alt; };
+
+// platform_state_update, tut_5_1.c:816-868 (double precision, no random numbers)
+__device__ __noinline__ void aw_platform_at(AwacsPlatform &st, const AwacsOrbit &o, double t)
+{
+    const double PI = 3.14159265358979323846;
+    const double delta_t = t - (double)o.start_time;
+    double d = fmod(delta_t * (double)o.velocity_ms, (double)o.orbit_dist_m);
+    if (d < 0) d += (double)o.orbit_dist_m;
+    double xl, yl, hdg, roll;
+    if (d < (double)o.length_m) {
+        xl = d; yl = 0.0; hdg = 0.0; roll = 0.0;
+    }
+    else if (d < (double)(o.length_m + o.turn_dist_m)) {
+        const double phi = (d - (double)o.length_m) / (double)o.turn_radius_m - PI / 2.0;
+        xl = (double)o.length_m + (double)o.turn_radius_m * cos(phi);
+        yl = (double)(o.side * o.turn_radius_m) * (1.0 + sin(phi));
+        hdg = (phi + PI / 2.0) * (double)o.side;
+        roll = (double)o.roll_angle_r;
+    }
+    else if (d < 2.0 * (double)o.length_m + (double)o.turn_dist_m) {
+        const double d_seg = d - (double)(o.length_m + o.turn_dist_m);
+        xl = (double)o.length_m - d_seg;
+        yl = (double)o.side * 2.0 * (double)o.turn_radius_m;
+        hdg = PI;
+        roll = 0.0;
+    }
+    else {
+        const double phi = (d - (2.0 * (double)o.length_m + (double)o.turn_dist_m)) / (double)o.turn_radius_m + PI / 2.0;
+        xl = (double)o.turn_radius_m * cos(phi);
+        yl = (double)(o.side * o.turn_radius_m) * (1.0 + sin(phi));
+        hdg = PI + (phi - PI / 2.0) * (double)o.side;
+        roll = (double)o.roll_angle_r;
+    }
+    st.x = (float)(xl * o.cos_o - yl * o.sin_o);
+    st.y = (float)(xl * o.sin_o + yl * o.cos_o);
+    st.dir = (float)fmod(hdg + (double)o.orientation_r + 2.0 * PI, 2.0 * PI);
+    st.rol = (float)roll;
+    st.alt = o.altitude_m;
+}
+
+// one trial's state block, column pointers
+struct AwacsState {
+    float *x, *y, *alt, *dir, *vel, *time_s, *rcs_now;
+    uint32_t *flags, *wake_key;
+    double *wake_t;
+    __device__ __forceinline__ explicit AwacsState(unsigned char *base)
+    {
+        float *f = reinterpret_cast<float *>(base);
+        x = f; y = f + AWACS_STRIDE; alt = f + 2 * AWACS_STRIDE; dir = f + 3 * AWACS_STRIDE; vel = f + 4 * AWACS_STRIDE;
+        time_s = f + 5 * AWACS_STRIDE; rcs_now = f + 6 * AWACS_STRIDE;
+        flags = reinterpret_cast<uint32_t *>(f + 7 * AWACS_STRIDE);
+        wake_key = flags + AWACS_STRIDE;
+        wake_t = reinterpret_cast<double *>(wake_key + AWACS_STRIDE);
+    }
+};
+
+// tgt->rcs_m2[] and tgt->state_time_s[] as run_trial sets them, tut_5_1.c:1153-1166 with :468-475
+__device__ __forceinline__ float aw_rcs(uint32_t mode)
+{
+    return mode == AW_HIDING ? 5.0f : (mode == AW_STAGING ? 100.0f : (mode == AW_FIRING ? 1000.0f : 50.0f));
+}
+__device__ __forceinline__ float aw_dwell(uint32_t mode)
+{
+    return mode == AW_HIDING ? __fmul_rn(3.0f, 3600.0f)
+                             : (mode == AW_STAGING ? __fmul_rn(5.0f, 60.0f) : (mode == AW_FIRING ? 30.0f : __fmul_rn(1.0f, 3600.0f)));
+}
+
+// the geometry of one target against the platform (tut_5_1.c:987-998) and the three cheap tests;
+// returns 0 = not in the swept sector (no change), else the tds it earns, or AW_UNDETERMINED + 16 = survivor
+struct AwacsSweep { float prev_dir, width, rad_eff, lo, hi; };
+
+__device__ __forceinline__ uint32_t aw_cheap_tests(const AwacsPlatform &h, const AwacsSweep &sw, float tx, float ty, float ta)
+{
+    const float TWO_PI_F = __fmul_rn(2.0f, (float)3.14159265358979323846);
+    const float dx = __fsub_rn(tx, h.x), dy = __fsub_rn(ty, h.y), dz = __fsub_rn(ta, h.alt);
+    const float d_2d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const float azi = aw_atan2f(dy, dx);
+    float rel = __fsub_rn(azi, sw.prev_dir);            // target_is_in_swept_sector, :548-561
+    while (rel < 0.0f) rel = __fadd_rn(rel, TWO_PI_F);
+    while (rel >= TWO_PI_F) rel = __fsub_rn(rel, TWO_PI_F);
+    if (!(rel <= sw.width)) return 0u;
+    {                                                   // target_is_beyond_horizon, :566-576
+        const float hs = fmaxf(0.0f, h.alt), ht = fmaxf(0.0f, ta);
+        const float reach = __fadd_rn(__fsqrt_rn(__fmul_rn(__fmul_rn(2.0f, sw.rad_eff), hs)),
+                                      __fsqrt_rn(__fmul_rn(__fmul_rn(2.0f, sw.rad_eff), ht)));
+        if (d_2d > reach) return AW_BEYOND_HORIZON;
+    }
+    {                                                   // target_is_outside_vertical, :583-593
+        const float rel_brg = __fsub_rn(azi, h.dir);
+        const float geom_elev = aw_atan2f(dz, d_2d);
+        const float apparent = __fsub_rn(geom_elev, __fmul_rn(h.rol, aw_sinf(rel_brg)));
+        if ((apparent < sw.lo) || (apparent > sw.hi)) return AW_NADIR_HOLE;
+    }
+    return 16u;
+}
+
+// target_attempt_detection up to the draw, tut_5_1.c:643-686
+__device__ __forceinline__ float aw_detection_probability(float sa, float ref_range, float ref_rcs, float ta, float tcx, float d_3d)
+{
+    const float r = fmaxf(1.0f, d_3d);
+    const float snr = __fmul_rn(aw_powf(__fdiv_rn(ref_range, r), 4.0f), __fdiv_rn(tcx, ref_rcs));
+    const float bv = ta < 400.0f ? 0.2f : (ta < 1000.0f ? 0.3f : 0.9f);
+    const float dz = __fsub_rn(sa, ta);
+    float sin_grazing = 0.0f;
+    if (dz > 0.0f) sin_grazing = fminf(1.0f, __fdiv_rn(dz, r));
+    const float clutter = __fsub_rn(1.0f, __fmul_rn(sin_grazing, 0.8f));
+    const float sinr = __fmul_rn(__fmul_rn(snr, bv), clutter);
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, aw_expf(__fmul_rn(-0.5f, __fsub_rn(sinr, 10.0f)))));
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(AWACS_BLOCK)
+awacs_kernel(const AwacsArgs a)
+{
+    __shared__ ZigHot hot;
+    __shared__ uint16_t list_smem[AWACS_BLOCK / 32][AWACS_STRIDE];
+
+    stage_zig_hot(hot, false);
+    __syncthreads();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
+    const uint64_t trial = (uint64_t)blockIdx.x * (AWACS_BLOCK / 32) + warp;
+    if (trial >= a.num_trials) {
+        return;
+    }
+    uint16_t *const list = list_smem[warp];
+    AwacsState S(a.state + trial * AWACS_STATE_BYTES);
+    const AwacsTerrain ter = a.ter;
+    const double PI = 3.14159265358979323846;
+    const float TWO_PI_F = __fmul_rn(2.0f, (float)PI);
+
+    Sfc64 rng;
+    rng.seed(fmix64(a.master_seed, a.first_trial + trial));
+
+    // ---- run_trial, tut_5_1.c:1139-1225: 1000 x cmb_process_start, the radar, the end event, the progress bar
+    for (unsigned i = lane; i < (unsigned)AWACS_STRIDE; i += 32u) {
+        S.x[i] = 0.0f; S.y[i] = 0.0f; S.alt[i] = 0.0f; S.dir[i] = 0.0f; S.vel[i] = 0.0f; S.time_s[i] = 0.0f; S.rcs_now[i] = 0.0f;
+        S.flags[i] = 0u;
+        S.wake_key[i] = i < (unsigned)AWACS_TARGETS ? i + 1u : 0u;
+        S.wake_t[i] = i < (unsigned)AWACS_TARGETS ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    }
+    __syncwarp();
+    uint32_t issued = (uint32_t)AWACS_TARGETS;
+    double radar_t = 0.0;
+    uint32_t radar_key = ++issued;
+    bool radar_started = false;
+    double end_t = a.t_end_s;
+    uint32_t end_key = ++issued;
+    double bar_t = 0.0;
+    uint32_t bar_key = ++issued;
+    uint32_t bar_cycles = 0u;
+    double bar_incr = 0.0;
+    bool targets_live = true;
+
+    AwacsPlatform host = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+    // sensor_initialize, :1045-1065 with :1200-1206
+    const float max_elev = (float)(60.0 * (2.0 * PI / 360.0));
+    const float min_elev = (float)(-20.0 * (2.0 * PI / 360.0));
+    const float ref_range_m = __fmul_rn(150.0f, (float)1852.0);
+    const float ref_rcs = 1.0f;
+    float cur_dir = (float)(PI / 2.0);
+    const float rot_inc = (float)((double)__fmul_rn(6.0f, __fdiv_rn(1.0f, 60.0f)) * ((double)2.0f * PI));
+
+    // earliest target event: (time bits, key, index); times are >= 0 so the bit patterns order like the values
+    unsigned long long tmin_t = 0ull;
+    uint32_t tmin_key = 1u, tmin_idx = 0u;
+    bool tmin_stale = true;
+
+    double now = 0.0;
+    uint64_t pops = 0u;
+    uint32_t status = TRIAL_OK;
+    const uint64_t pop_limit = (uint64_t)fmin(fmax(a.t_end_s, 0.0), 1.0e9) * 8u + 200000u;
+
+    for (;;) {
+        if (targets_live && tmin_stale) {               // 32-lane scan of the targets' pending events
+            unsigned long long bt = ~0ull;
+            uint32_t bk = 0xffffffffu, bi = 0u;
+            for (unsigned i = lane; i < (unsigned)AWACS_TARGETS; i += 32u) {
+                const unsigned long long t = (unsigned long long)__double_as_longlong(S.wake_t[i]);
+                const uint32_t k = S.wake_key[i];
+                if (goes_before(t, k, bt, bk)) { bt = t; bk = k; bi = i; }
+            }
+            const Picked p = warp_first(bt, bk);
+            tmin_t = p.t;
+            tmin_key = p.key;
+            tmin_idx = __shfl_sync(FULL, bi, p.lane);
+            tmin_stale = false;
+        }
+        // ---- pop-min over the four owners (time asc, key asc; every priority is 0)
+        const unsigned long long NONE = ~0ull;
+        unsigned long long bt = targets_live ? tmin_t : NONE;
+        uint32_t bk = tmin_key;
+        int kind = 0;
+        if (radar_key != 0u) {
+            const unsigned long long t = (unsigned long long)__double_as_longlong(radar_t);
+            if (bt == NONE || goes_before(t, radar_key, bt, bk)) { bt = t; bk = radar_key; kind = 1; }
+        }
+        if (end_key != 0u) {
+            const unsigned long long t = (unsigned long long)__double_as_longlong(end_t);
+            if (bt == NONE || goes_before(t, end_key, bt, bk)) { bt = t; bk = end_key; kind = 2; }
+        }
+        if (bar_key != 0u) {
+            const unsigned long long t = (unsigned long long)__double_as_longlong(bar_t);
+            if (bt == NONE || goes_before(t, bar_key, bt, bk)) { bt = t; bk = bar_key; kind = 3; }
+        }
+        if (bt == NONE) {
+            break;                                      // the list ran dry: cmb_event_queue_execute returns
+        }
+        if (pops >= pop_limit) {                        // cannot happen in a sane run; never spin on a broken one
+            status |= TRIAL_ERR_KEY_OVERFLOW;
+            break;
+        }
+        now = __longlong_as_double((long long)bt);
+        if (TRACE) {
+            if (lane == 0u && pops < a.trace_cap) {
+                a.trace_key[trial * a.trace_cap + pops] = bk;
+                a.trace_time[trial * a.trace_cap + pops] = now;
+            }
+        }
+        pops++;
+
+        if (kind == 0) {
+            // ================= a target's resume point, target_proc :385-446 (warp-uniform; lane 0 stores)
+            const uint32_t i = tmin_idx;
+            uint32_t fl = S.flags[i];
+            uint32_t mode = fl & AW_F_MODE;
+            float gx = S.x[i], gy = S.y[i], galt = S.alt[i], gdir = S.dir[i], gvel = S.vel[i], grcs = S.rcs_now[i];
+            bool to_hold = false;                       // run the loop top (hiding or driving branch) next
+            double wake = 0.0;
+            if (!(fl & AW_F_STARTED)) {                 // first entry, :393-402
+                gx = (float)rng.uniform((double)ter.x_min, (double)ter.x_max);
+                gy = (float)rng.uniform((double)ter.y_min, (double)ter.y_max);
+                galt = __fadd_rn(aw_elevation(ter, gx, gy), 2.0f);
+                const double ph = (double)__fdiv_rn(aw_dwell(AW_HIDING), __fadd_rn(aw_dwell(AW_HIDING), aw_dwell(AW_DRIVING)));
+                mode = rng.bernoulli(ph) ? AW_HIDING : AW_DRIVING;
+                fl = AW_F_STARTED;                      // tds = UNDETERMINED, not found
+                to_hold = true;
+            }
+            else if (mode == AW_HIDING) {               // unmask, :414-420
+                mode = AW_STAGING;
+                grcs = aw_rcs(AW_STAGING);
+                const double t_m = (double)__fdiv_rn(aw_dwell(AW_STAGING), (float)10u);
+                wake = __dadd_rn(now, rng.erlang(hot, 10u, t_m));
+            }
+            else if (mode == AW_STAGING) {              // shoot, :422-429
+                mode = AW_FIRING;
+                grcs = aw_rcs(AW_FIRING);
+                const double t_m = (double)__fdiv_rn(aw_dwell(AW_FIRING), (float)20u);
+                wake = __dadd_rn(now, rng.erlang(hot, 20u, t_m));
+            }
+            else if (mode == AW_FIRING) {               // scoot, :430
+                mode = AW_DRIVING;
+                to_hold = true;
+            }
+            else {                                      // done driving, :443
+                mode = AW_HIDING;
+                to_hold = true;
+            }
+            if (to_hold) {
+                if (mode == AW_HIDING) {                // :405-411
+                    grcs = aw_rcs(AW_HIDING);
+                    gvel = 0.0f;
+                    wake = __dadd_rn(now, rng.exponential(hot, (double)aw_dwell(AW_HIDING)));
+                }
+                else {                                  // :432-442
+                    grcs = aw_rcs(AW_DRIVING);
+                    gdir = (float)rng.uniform(0.0, 2.0 * PI);
+                    gvel = (float)rng.uniform(5.0, 20.0);
+                    const double t_m = (double)__fdiv_rn(aw_dwell(AW_DRIVING), (float)5u);
+                    wake = __dadd_rn(now, rng.erlang(hot, 5u, t_m));
+                }
+            }
+            issued++;
+            if (lane == 0u) {
+                S.x[i] = gx; S.y[i] = gy; S.alt[i] = galt; S.dir[i] = gdir; S.vel[i] = gvel; S.rcs_now[i] = grcs;
+                S.time_s[i] = (float)now;
+                S.flags[i] = (fl & ~AW_F_MODE) | mode;
+                S.wake_t[i] = wake;
+                S.wake_key[i] = issued;
+            }
+            __syncwarp();
+            tmin_stale = true;
+        }
+        else if (kind == 1) {
+            // ================= the radar, sensor_proc :944-1036
+            if (!radar_started) {
+                radar_started = true;
+                aw_platform_at(host, a.orbit, now);
+                radar_t = __dadd_rn(now, 1.0);
+                radar_key = ++issued;
+                continue;
+            }
+            const float prev_hdg = host.dir;
+            AwacsSweep sw;
+            sw.prev_dir = cur_dir;
+            aw_platform_at(host, a.orbit, now);
+            const float ddir = __fsub_rn(host.dir, prev_hdg);
+            float sweep_width = __fadd_rn(rot_inc, ddir);
+            cur_dir = __fadd_rn(cur_dir, sweep_width);
+            while (cur_dir >= TWO_PI_F) cur_dir = __fsub_rn(cur_dir, TWO_PI_F);
+            while (cur_dir < 0.0f) cur_dir = __fadd_rn(cur_dir, TWO_PI_F);
+            if (sweep_width < 0.0f) sweep_width = 0.01f;
+            sw.width = sweep_width;
+            sw.rad_eff = a.orbit.rad_eff;
+            sw.lo = min_elev;
+            sw.hi = max_elev;
+
+            // ---- pass A: dead reckoning + the cheap tests, 32 targets at a time; survivors listed in target order
+            uint32_t n_surv = 0u;
+            for (unsigned base = 0u; base < (unsigned)AWACS_TARGETS; base += 32u) {
+                const unsigned i = base + lane;
+                bool survivor = false;
+                if (i < (unsigned)AWACS_TARGETS) {
+                    float tx = S.x[i], ty = S.y[i], ta = S.alt[i];
+                    const float vel = S.vel[i];
+                    if (vel > 0.0f) {                   // target_position_update, :507-545
+                        const float dir = S.dir[i];
+                        const double dt = __dsub_rn(now, (double)S.time_s[i]);
+                        const double run = __dmul_rn(dt, (double)vel);
+                        float x = __fadd_rn(tx, (float)__dmul_rn(run, (double)aw_cosf(dir)));
+                        if (x > ter.x_max) x = __fadd_rn(ter.x_min, __fsub_rn(x, ter.x_max));
+                        else if (x < ter.x_min) x = __fsub_rn(ter.x_max, __fsub_rn(ter.x_min, x));
+                        float y = __fadd_rn(ty, (float)__dmul_rn(run, (double)aw_sinf(dir)));
+                        if (y > ter.y_max) y = __fadd_rn(ter.y_min, __fsub_rn(y, ter.y_max));
+                        else if (y < ter.y_min) y = __fsub_rn(ter.y_max, __fsub_rn(ter.y_min, y));
+                        ta = __fadd_rn(aw_elevation(ter, x, y), 2.0f);
+                        tx = x;
+                        ty = y;
+                        S.time_s[i] = (float)now;
+                        S.x[i] = tx;
+                        S.y[i] = ty;
+                        S.alt[i] = ta;
+                    }
+                    const uint32_t verdict = aw_cheap_tests(host, sw, tx, ty, ta);
+                    if (verdict == 16u) {
+                        survivor = true;
+                    }
+                    else if (verdict != 0u) {
+                        S.flags[i] = (S.flags[i] & ~AW_F_TDS) | (verdict << AW_F_TDS_SHIFT);
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, survivor);
+                if (survivor) {
+                    list[n_surv + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                }
+                n_surv += __popc(m);
+            }
+            __syncwarp();
+
+            // ---- pass B: target_is_terrain_shielded (:598-638), one line of sight marched by the whole warp
+            uint32_t n_cand = 0u;
+            for (uint32_t s = 0u; s < n_surv; s++) {
+                const unsigned i = list[s];
+                const float tx = S.x[i], ty = S.y[i], ta = S.alt[i];
+                const float dx = __fsub_rn(tx, host.x), dy = __fsub_rn(ty, host.y), dz = __fsub_rn(ta, host.alt);
+                const float d_2d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                const float step = __fmul_rn(fminf(ter.x_scale, ter.y_scale), 0.5f);
+                const int steps = (int)__fdiv_rn(d_2d, step);
+                bool shielded = false;
+                if (steps >= 1) {
+                    const float inv = __fdiv_rn(1.0f, (float)steps);
+                    for (int first = 1; first < steps && !shielded; first += 128) {
+                        bool hit = false;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int k = first + u * 32 + (int)lane;
+                            if (k < steps) {
+                                const float f = __fmul_rn((float)k, inv);
+                                float cx = __fadd_rn(host.x, __fmul_rn(dx, f));
+                                float cy = __fadd_rn(host.y, __fmul_rn(dy, f));
+                                const float ca = __fadd_rn(host.alt, __fmul_rn(dz, f));
+                                cx = fmaxf(ter.x_min, fminf(cx, ter.x_max));
+                                cy = fmaxf(ter.y_min, fminf(cy, ter.y_max));
+                                hit |= ca < aw_elevation(ter, cx, cy);
+                            }
+                        }
+                        shielded = __any_sync(FULL, hit);
+                    }
+                }
+                if (shielded) {
+                    if (lane == 0u) S.flags[i] = (S.flags[i] & ~AW_F_TDS) | (AW_TERRAIN_SHIELDED << AW_F_TDS_SHIFT);
+                }
+                else {
+                    if (lane == 0u) list[n_cand] = (uint16_t)i;     // n_cand <= s: never overtakes the reader
+                    n_cand++;
+                }
+                __syncwarp();
+            }
+
+            // ---- pass C: target_attempt_detection (:643-689); probabilities in parallel, draws in target order
+            for (uint32_t base = 0u; base < n_cand; base += 32u) {
+                const uint32_t mine = base + lane;
+                unsigned i = 0u;
+                float pd = 0.0f;
+                uint32_t fl = 0u;
+                if (mine < n_cand) {
+                    i = list[mine];
+                    const float tx = S.x[i], ty = S.y[i], ta = S.alt[i];
+                    const float dx = __fsub_rn(tx, host.x), dy = __fsub_rn(ty, host.y), dz = __fsub_rn(ta, host.alt);
+                    const float d_2d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                    const float d_3d = __fsqrt_rn(__fadd_rn(__fmul_rn(d_2d, d_2d), __fmul_rn(dz, dz)));
+                    pd = aw_detection_probability(host.alt, ref_range_m, ref_rcs, ta, S.rcs_now[i], d_3d);
+                    fl = S.flags[i];
+                }
+                const uint32_t count = min(32u, n_cand - base);
+                bool seen = false;
+                for (uint32_t k = 0u; k < count; k++) {
+                    const double u = rng.uniform01();   // cmb_random_bernoulli(pd): cmb_random() <= p
+                    if (lane == k) seen = u <= (double)pd;
+                }
+                if (mine < n_cand) {
+                    fl = (fl & ~AW_F_TDS) | ((seen ? AW_DETECTED : AW_MISSED) << AW_F_TDS_SHIFT);
+                    if (seen && (fl & AW_F_MODE) != AW_FIRING) fl |= AW_F_FOUND;
+                    S.flags[i] = fl;
+                }
+            }
+            __syncwarp();
+            radar_t = __dadd_rn(now, 1.0);
+            radar_key = ++issued;
+        }
+        else if (kind == 2) {
+            // ================= end_sim, :1100-1112: cmb_process_stop on the radar and on every target
+            end_key = 0u;
+            radar_key = 0u;
+            targets_live = false;
+        }
+        else {
+            // ================= ent_proc, :1118-1137: 100 holds of a hundredth of the run
+            if (bar_cycles == 0u) {
+                bar_incr = __ddiv_rn(__dsub_rn(a.t_end_s, now), 100.0);
+            }
+            if (bar_cycles < 100u) {
+                bar_cycles++;
+                bar_t = __dadd_rn(now, bar_incr);
+                bar_key = ++issued;
+            }
+            else {
+                bar_key = 0u;
+            }
+        }
+    }
+
+    // ---- results: struct trial.num_found (:1227-1232) and the final picture of the targets
+    uint32_t found = 0u, tds_n[6] = { 0u, 0u, 0u, 0u, 0u, 0u }, mode_n[4] = { 0u, 0u, 0u, 0u };
+    for (unsigned i = lane; i < (unsigned)AWACS_TARGETS; i += 32u) {
+        const uint32_t fl = S.flags[i];
+        found += (fl & AW_F_FOUND) ? 1u : 0u;
+        const uint32_t tds = (fl & AW_F_TDS) >> AW_F_TDS_SHIFT;
+#pragma unroll
+        for (uint32_t k = 0u; k < 6u; k++) tds_n[k] += tds == k ? 1u : 0u;
+#pragma unroll
+        for (uint32_t k = 0u; k < 4u; k++) mode_n[k] += (fl & AW_F_MODE) == k ? 1u : 0u;
+    }
+    found = __reduce_add_sync(FULL, found);
+#pragma unroll
+    for (uint32_t k = 0u; k < 6u; k++) tds_n[k] = __reduce_add_sync(FULL, tds_n[k]);
+#pragma unroll
+    for (uint32_t k = 0u; k < 4u; k++) mode_n[k] = __reduce_add_sync(FULL, mode_n[k]);
+    if (lane == 0u) {
+        double sum_x = 0.0, sum_y = 0.0;                // in target order, as the oracle adds them
+        for (unsigned i = 0u; i < (unsigned)AWACS_TARGETS; i++) {
+            sum_x = __dadd_rn(sum_x, (double)S.x[i]);
+            sum_y = __dadd_rn(sum_y, (double)S.y[i]);
+        }
+        if (a.events)    a.events[trial] = pops;
+        if (a.objects)   a.objects[trial] = found;
+        if (a.t_end)     a.t_end[trial] = now;
+        if (a.sum_wait)  a.sum_wait[trial] = sum_x;
+        if (a.status)    a.status[trial] = status;
+        if (a.max_queue) a.max_queue[trial] = (uint32_t)AWACS_TARGETS + 3u;
+        if (a.counters) {
+            uint64_t *c = a.counters + trial * 8u;
+#pragma unroll
+            for (uint32_t k = 0u; k < 6u; k++) c[k] = tds_n[k];
+            c[6] = (uint64_t)mode_n[0] | ((uint64_t)mode_n[1] << 16) | ((uint64_t)mode_n[2] << 32) | ((uint64_t)mode_n[3] << 48);
+            c[7] = (uint64_t)__double_as_longlong(sum_y);
+        }
+    }
+}
+
+}  // namespace cimba_b200

@@ -34,6 +34,7 @@
 #include "hold_model.cuh"
 #include "hold_deep.cuh"
 #include "hold_group.cuh"
+#include "awacs_model.cuh"
 #include "rng.cuh"
 #include "distributions.cuh"
 #include "summary.cuh"
@@ -176,6 +177,47 @@ uint64_t alias_secure(double p)        // src/cmb_random.c:672-686
     return (uint64_t)(p * (double)UINT64_MAX);
 }
 
+// ---------------------------------------------------------------- MODEL_AWACS host side
+constexpr int MAX_TERRAIN_DEVICES = 64;
+std::mutex g_terrain_mu;
+AwacsTerrain g_terrain[MAX_TERRAIN_DEVICES];
+bool g_terrain_set[MAX_TERRAIN_DEVICES];
+
+// racetrack_initialize with run_trial's arguments (tutorial/tut_5_1.c:724-782, :1177-1188): constants of the
+// model, evaluated once on the host with the host's libm, exactly as the reference evaluates them
+AwacsOrbit awacs_orbit()
+{
+    const double PI = 3.14159265358979323846;
+    const double deg_to_rad = (2.0 * PI / 360.0), nm_to_meters = 1852.0, feet_to_meters = 0.3048;
+    const double knots_to_ms = (1852.0 / 3600.0);
+    const double WGS84_A = 6378137.0, WGS84_F = (1.0 / 298.257223563), WGS84_E2 = (WGS84_F * (2.0 - WGS84_F));
+    const float start_time = 0.0f, anchor_lat = 30.0f, orientation = 0.0f, leg_length = 50.0f;
+    const float turn_radius = 10.0f, flight_level = 310.0f, velocity = 300.0f;
+    AwacsOrbit o{};
+    o.start_time = 3600.0f * start_time;
+    const float anchor_lat_r = (float)(anchor_lat * deg_to_rad);
+    o.orientation_r = (float)((90.0 - orientation) * deg_to_rad);
+    o.length_m = (float)(leg_length * nm_to_meters);
+    o.turn_radius_m = (float)(turn_radius * nm_to_meters);
+    o.altitude_m = (float)(flight_level * 100.0 * feet_to_meters);
+    o.velocity_ms = (float)(velocity * knots_to_ms);
+    o.turn_dist_m = (float)(PI * o.turn_radius_m);
+    o.orbit_dist_m = 2.0f * (o.length_m + o.turn_dist_m);
+    o.side = -1.0f;                                     // clockwise
+    const double sin_lat = sinf(anchor_lat_r);
+    const double common = 1.0 - (WGS84_E2 * sin_lat * sin_lat);
+    const double sqrt_common = sqrt(common);
+    const double M = WGS84_A * (1.0 - WGS84_E2) / (common * sqrt_common);
+    const double N = WGS84_A / sqrt_common;
+    const double g = 9.80665;
+    const double roll_mag = atan((o.velocity_ms * o.velocity_ms) / (o.turn_radius_m * g));
+    o.roll_angle_r = (float)(roll_mag * -o.side);
+    o.rad_eff = (float)(sqrt(M * N) * (4.0 / 3.0));
+    o.cos_o = cos((double)o.orientation_r);
+    o.sin_o = sin((double)o.orientation_r);
+    return o;
+}
+
 template <int MODEL>
 int launch_queue(const QueueArgs &qa, bool trace, dim3 grid, cudaStream_t st)
 {
@@ -223,6 +265,9 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (job->model == CIMBA_B200_MODEL_HOLD && job->variant != 1) {
         return job->num_trials * deep_row_entries(job->servers) * (uint64_t)sizeof(uint4);
     }
+    if (job->model == CIMBA_B200_MODEL_AWACS) {
+        return job->num_trials * (uint64_t)AWACS_STATE_BYTES;
+    }
     if (is_general_model(job->model)) {
         return job->num_trials * (uint64_t)sizeof(GeneralState);
     }
@@ -233,7 +278,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
 {
     if (job == nullptr) return fail(CIMBA_B200_EINVAL, "job is NULL");
     if (job->num_trials == 0u) return fail(CIMBA_B200_EINVAL, "num_trials must be > 0 (src/cimba.c:157)");
-    if (job->arr_mean == nullptr || job->srv_mean == nullptr)
+    if ((job->arr_mean == nullptr || job->srv_mean == nullptr) && job->model != CIMBA_B200_MODEL_AWACS)
         return fail(CIMBA_B200_EINVAL, "arr_mean/srv_mean device arrays are required");
     if (job->num_objects >= 0xffffffffull) return fail(CIMBA_B200_EINVAL, "num_objects must be < 2^32-1");
     const int mapping = job->mapping == 0 ? CIMBA_B200_MAP_LANE : job->mapping;
@@ -467,6 +512,44 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "harbor_kernel launch");
     }
+    if (job->model == CIMBA_B200_MODEL_AWACS) {
+        if (job->num_objects == 0u) return fail(CIMBA_B200_EINVAL, "MODEL_AWACS: num_objects = trial duration in seconds, > 0");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        AwacsArgs aa{};
+        {
+            std::lock_guard<std::mutex> hold(g_terrain_mu);
+            if (dev < 0 || dev >= MAX_TERRAIN_DEVICES || !g_terrain_set[dev])
+                return fail(CIMBA_B200_EINVAL, "MODEL_AWACS: no terrain registered on this device; call cimba_b200_awacs_set_terrain()");
+            aa.ter = g_terrain[dev];
+        }
+        aa.orbit = awacs_orbit();
+        aa.master_seed = job->master_seed;
+        aa.first_trial = job->first_trial;
+        aa.num_trials = job->num_trials;
+        aa.t_end_s = (double)job->num_objects;
+        aa.state = (unsigned char *)job->workspace;
+        aa.events = job->events;
+        aa.objects = job->objects;
+        aa.t_end = job->t_end;
+        aa.sum_wait = job->sum_wait;
+        aa.status = job->status;
+        aa.max_queue = job->max_queue;
+        aa.counters = job->counters;
+        aa.trace_cap = job->trace_cap;
+        aa.trace_key = job->trace_key;
+        aa.trace_time = job->trace_time;
+        const uint64_t per_block = AWACS_BLOCK / 32;
+        const uint64_t blocks = (job->num_trials + per_block - 1) / per_block;
+        if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
+        if (trace) awacs_kernel<true><<<(unsigned)blocks, AWACS_BLOCK, 0, st>>>(aa);
+        else       awacs_kernel<false><<<(unsigned)blocks, AWACS_BLOCK, 0, st>>>(aa);
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "awacs_kernel launch");
+    }
     if (job->model == CIMBA_B200_MODEL_HOLD) {
         const bool on_chip = job->variant == 1;         // hold_model.cuh: the whole list in shared memory
         if (job->servers < 1 || (on_chip && job->servers > HOLD_CAP - 8) ||
@@ -539,6 +622,21 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "hold_kernel launch");
     }
     return fail(CIMBA_B200_EINVAL, "unknown model");
+}
+
+int cimba_b200_awacs_set_terrain(const cimba_b200_awacs_terrain *t)
+{
+    if (t == nullptr || t->map == nullptr || t->cols < 2u || t->rows < 2u || !(t->x_scale > 0.0f) || !(t->y_scale > 0.0f) ||
+        !(t->x_min < t->x_max) || !(t->y_min < t->y_max))
+        return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_TERRAIN_DEVICES) return fail(CIMBA_B200_EINVAL, "device index out of range");
+    std::lock_guard<std::mutex> hold(g_terrain_mu);
+    g_terrain[dev] = AwacsTerrain{t->map, t->cols, t->rows, t->x_scale, t->y_scale, t->x_min, t->x_max, t->y_min, t->y_max};
+    g_terrain_set[dev] = true;
+    return CIMBA_B200_OK;
 }
 
 int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
@@ -734,6 +832,8 @@ int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const 
     PhaseClock clk;
     if (array == nullptr || d == nullptr) return fail(CIMBA_B200_EINVAL, "NULL experiment array or descriptor");
     if (num_trials == 0u || stride == 0u) return fail(CIMBA_B200_EINVAL, "num_trials and trial_struct_size must be > 0");
+    if (d->model == CIMBA_B200_MODEL_AWACS)
+        return fail(CIMBA_B200_EINVAL, "MODEL_AWACS runs through the device-resident interface (its terrain lives in HBM)");
     if (d->off_arr_mean == CIMBA_B200_NO_FIELD || d->off_srv_mean == CIMBA_B200_NO_FIELD)
         return fail(CIMBA_B200_EINVAL, "off_arr_mean and off_srv_mean are required");
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");

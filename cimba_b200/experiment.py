@@ -226,3 +226,50 @@ def alias_create(probabilities):
     alias = (C.c_uint32 * n)()
     check(lib.cimba_b200_alias_create(n, pa, uprob, alias))
     return list(uprob), list(alias)
+
+
+# ---------------------------------------------------------------- AWACS (tutorial/tut_5_1.c, BASELINE config 5)
+AWACS_TARGETS, AWACS_STRIDE = 1000, 1024
+AWACS_STATE_BYTES = AWACS_STRIDE * (7 * 4 + 4 + 4 + 8)
+_awacs_maps = {}        # device index -> the registered map tensor (kept alive while registered)
+
+
+def awacs_set_terrain(elevations: torch.Tensor, cols: int, rows: int, geom) -> None:
+    """Register the terrain every MODEL_AWACS trial on this device reads (struct terrain, tut_5_1.c:96-108):
+    ``elevations`` = float32 CUDA tensor of rows*cols metres, ``geom`` = (x_scale, y_scale, x_min, x_max,
+    y_min, y_max) as terrain_init (:197-294) computes them."""
+    if not elevations.is_cuda or elevations.dtype != torch.float32 or elevations.numel() != cols * rows:
+        raise ValueError("elevations must be a float32 CUDA tensor of rows * cols values (there is no CPU path)")
+    elevations = elevations.contiguous()
+    g = [float(v) for v in geom]
+    desc = _lib.AwacsTerrain(map=elevations.data_ptr(), cols=cols, rows=rows, x_scale=g[0], y_scale=g[1],
+                             x_min=g[2], x_max=g[3], y_min=g[4], y_max=g[5])
+    with torch.cuda.device(elevations.device):
+        check(lib.cimba_b200_awacs_set_terrain(C.byref(desc)))
+    _awacs_maps[elevations.device.index] = elevations
+
+
+def awacs_run(num_trials: int, *, duration_s: int, master_seed: int, first_trial: int = 0, trace_cap: int = 0,
+              device: Optional[torch.device] = None):
+    """Run MODEL_AWACS trials (seeds cmb_random_fmix64(master_seed, first_trial + i)) for ``duration_s`` simulated
+    seconds each.  Returns (TrialResults, per_target) after a sync; ``per_target`` holds [num_trials, 1000]
+    tensors x, y, alt, mode, tds, found read from the state blocks.  results.objects = targets found."""
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    b = TrialBuffers(num_trials, dev, trace_cap, _lib.MODEL_AWACS)
+    job = _lib.DeviceJob(
+        model=_lib.MODEL_AWACS, master_seed=master_seed & (2**64 - 1), first_trial=first_trial,
+        num_trials=num_trials, num_objects=int(duration_s),
+        events=b.events.data_ptr(), objects=b.objects.data_ptr(), t_end=b.t_end.data_ptr(),
+        sum_wait=b.sum_wait.data_ptr(), status=b.status.data_ptr(), max_queue=b.max_queue.data_ptr(),
+        counters=b.counters.data_ptr(), workspace=b.workspace.data_ptr(), workspace_bytes=b.workspace_bytes,
+        trace_cap=trace_cap, trace_key=b.trace_key.data_ptr() if trace_cap else None,
+        trace_time=b.trace_time.data_ptr() if trace_cap else None)
+    with torch.cuda.device(dev):
+        check(lib.cimba_b200_launch(C.byref(job), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize(dev)
+    blocks = b.workspace[:num_trials * AWACS_STATE_BYTES].view(num_trials, AWACS_STATE_BYTES)
+    col = AWACS_STRIDE * 4
+    f32 = lambda k: blocks[:, k * col:(k + 1) * col].contiguous().view(torch.float32)[:, :AWACS_TARGETS]   # noqa: E731
+    flags = blocks[:, 7 * col:8 * col].contiguous().view(torch.int32)[:, :AWACS_TARGETS]
+    per_target = dict(x=f32(0), y=f32(1), alt=f32(2), mode=flags & 3, tds=(flags >> 4) & 7, found=(flags >> 8) & 1)
+    return b.results(), per_target

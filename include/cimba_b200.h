@@ -96,6 +96,18 @@ extern "C" {
                                     * pre-emption (bits) [5] its victim + 1; max_queue = history samples.  25 time units and the golden
                                     * seed give test/reference/resource.txt: "N 30  Mean 0.9816", Target_3 pre-empted at t = 6.3280 */
 
+#define CIMBA_B200_MODEL_AWACS 15    /* tutorial/tut_5_1.c (BASELINE config 5), one trial per warp: 1000 ground targets cycling hiding ->
+                                    * staging -> firing -> driving, a radar ticking every second through a five-stage float32 detection
+                                    * chain (swept sector, horizon, nadir hole, terrain ray-march, clutter-limited probability with a
+                                    * cmb_random_bernoulli draw), the platform on its racetrack, the progress-bar process, the end event
+                                    * after num_objects SECONDS.  The terrain map all trials share is registered once per device with
+                                    * cimba_b200_awacs_set_terrain(); arr_mean / srv_mean are not used.  Results: objects = targets found
+                                    * (struct trial.num_found), sum_wait = sum of the targets' final x, counters[0..5] = targets per
+                                    * detect state, [6] = targets per mode (4 x 16 bits), [7] = sum of final y (bits); the per-target
+                                    * state stays in the workspace (layout: CIMBA_B200_AWACS_* below).  Device-resident interface only.
+                                    * Parity with the reference is exact while no float32 libm result straddles a test threshold, and
+                                    * statistical beyond */
+
 /* Error codes */
 #define CIMBA_B200_OK         0
 #define CIMBA_B200_EINVAL    -1  /* bad argument */
@@ -155,6 +167,24 @@ typedef struct cimba_b200_device_job {
     uint64_t *trace_key;        /* cmb_event_current() after each pop */
     double   *trace_time;       /* cmb_time() after each pop */
 } cimba_b200_device_job;
+
+/* MODEL_AWACS: the terrain every trial reads (struct terrain, tutorial/tut_5_1.c:96-108, as terrain_init :197-294 fills
+ * it).  map is a DEVICE pointer to rows x cols float32 elevations, row-major, and must stay valid while jobs run.
+ * Registered per CUDA device (the current one); later launches of MODEL_AWACS on that device use it. */
+typedef struct cimba_b200_awacs_terrain {
+    const float *map;
+    uint32_t cols, rows;
+    float x_scale, y_scale;         /* metres per arc-second */
+    float x_min, x_max, y_min, y_max;
+} cimba_b200_awacs_terrain;
+int cimba_b200_awacs_set_terrain(const cimba_b200_awacs_terrain *terrain);
+
+/* MODEL_AWACS workspace: per trial CIMBA_B200_AWACS_STATE_BYTES, columns of CIMBA_B200_AWACS_STRIDE entries in this
+ * order: float x, y, alt, dir, vel, time_s, rcs_now; uint32 flags (bits 0-1 mode, 4-6 detect state, 8 found);
+ * uint32 wake_key; double wake_t.  Entries 0..999 are the targets. */
+#define CIMBA_B200_AWACS_TARGETS 1000
+#define CIMBA_B200_AWACS_STRIDE 1024
+#define CIMBA_B200_AWACS_STATE_BYTES (CIMBA_B200_AWACS_STRIDE * (7 * 4 + 4 + 4 + 8))
 
 /* Bytes of HBM scratch the job needs (0 is possible). */
 uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job);
