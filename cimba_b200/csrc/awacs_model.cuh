@@ -16,9 +16,9 @@
 //     per simulated second) - pop order is the total order (time, key) whatever the container;
 //   * one radar tick = three passes.  A: lanes take targets 32 at a time - dead reckoning, geometry, the three
 //     cheap tests (swept sector, horizon, nadir hole); survivors are appended to a list in target order.
-//     B: each survivor's line of sight is marched by the WHOLE warp (step i on lane i mod 32, four steps in
-//     flight per lane, one ballot per 128 steps): the reference's loop returns at the first step under the
-//     terrain, i.e. "any step is", which is order-free; neighbouring steps read neighbouring map cells.
+//     B: each survivor's line of sight is marched by the WHOLE warp (256 steps per round, eight consecutive
+//     ones per lane, one ballot per round): the reference's loop returns at the first step under the terrain,
+//     i.e. "any step is", which is order-free; steps are half a cell apart, so a lane reads each cell once.
 //     C: the unshielded survivors, in target order, compute their detection probability in parallel and then
 //     take their cmb_random_bernoulli draws one after the other - the only part that is serial by definition.
 //
@@ -39,6 +39,9 @@ namespace cimba_b200 {
 constexpr int AWACS_BLOCK = 128;                // 4 trials per CTA
 constexpr int AWACS_TARGETS = 1000;             // NUM_TARGETS, tut_5_1.c:35
 constexpr int AWACS_STRIDE = 1024;              // rows per column of the state block
+#ifndef AWACS_CHUNK
+#define AWACS_CHUNK 8                           // consecutive line-of-sight steps per lane and round
+#endif
 // per-trial state block in HBM/L2, structure of arrays, AWACS_STRIDE entries each:
 //   float x, y, alt, dir, vel, time_s, rcs_now; uint32 flags; uint32 wake_key; double wake_t
 constexpr size_t AWACS_STATE_BYTES = (size_t)AWACS_STRIDE * (7 * 4 + 4 + 4 + 8);
@@ -82,6 +85,15 @@ __device__ __forceinline__ float aw_powf(float a, float b) { return (float)pow((
 __device__ __forceinline__ float aw_expf(float x) { return (float)exp((double)x); }
 
 // terrain_index + terrain_elevation, tut_5_1.c:314-338
+__device__ __forceinline__ size_t aw_cell(const AwacsTerrain &t, float x, float y)
+{
+    const int raw_col = (int)roundf(__fdiv_rn(x, t.x_scale)) + (int)(t.cols / 2u);
+    const int raw_row = (int)roundf(__fdiv_rn(y, t.y_scale)) + (int)(t.rows / 2u);
+    const uint32_t col = (uint32_t)(raw_col < 0 ? 0 : (raw_col >= (int)t.cols ? (int)t.cols - 1 : raw_col));
+    const uint32_t row = (uint32_t)(raw_row < 0 ? 0 : (raw_row >= (int)t.rows ? (int)t.rows - 1 : raw_row));
+    return (size_t)row * t.cols + col;
+}
+
 __device__ __forceinline__ float aw_elevation(const AwacsTerrain &t, float x, float y)
 {
     const int raw_col = (int)roundf(__fdiv_rn(x, t.x_scale)) + (int)(t.cols / 2u);
@@ -265,6 +277,7 @@ awacs_kernel(const AwacsArgs a)
     double now = 0.0;
     uint64_t pops = 0u;
     uint32_t status = TRIAL_OK;
+    uint64_t lookups = 0u;                              // terrain cells this lane read while ray-marching
     const uint64_t pop_limit = (uint64_t)fmin(fmax(a.t_end_s, 0.0), 1.0e9) * 8u + 200000u;
 
     for (;;) {
@@ -455,20 +468,36 @@ awacs_kernel(const AwacsArgs a)
                 bool shielded = false;
                 if (steps >= 1) {
                     const float inv = __fdiv_rn(1.0f, (float)steps);
-                    for (int first = 1; first < steps && !shielded; first += 128) {
+                    // a round = 32 x AWACS_CHUNK consecutive steps; each lane takes AWACS_CHUNK CONSECUTIVE ones, so the
+                    // two or three half-cell steps that fall into one map cell cost one read, and a lane's successive
+                    // cells share 32-byte sectors in L1 instead of every step asking L2 for its own sector
+                    for (int first = 1; first < steps && !shielded; first += 32 * AWACS_CHUNK) {
+                        size_t cell[AWACS_CHUNK];
+                        float ray_alt[AWACS_CHUNK], ground[AWACS_CHUNK];
+                        bool live[AWACS_CHUNK];
+#pragma unroll
+                        for (int u = 0; u < AWACS_CHUNK; u++) {
+                            const int k = first + (int)lane * AWACS_CHUNK + u;
+                            live[u] = k < steps;
+                            const float f = __fmul_rn((float)k, inv);
+                            float cx = __fadd_rn(host.x, __fmul_rn(dx, f));
+                            float cy = __fadd_rn(host.y, __fmul_rn(dy, f));
+                            ray_alt[u] = __fadd_rn(host.alt, __fmul_rn(dz, f));
+                            cx = fmaxf(ter.x_min, fminf(cx, ter.x_max));
+                            cy = fmaxf(ter.y_min, fminf(cy, ter.y_max));
+                            cell[u] = aw_cell(ter, cx, cy);
+                        }
+#pragma unroll
+                        for (int u = 0; u < AWACS_CHUNK; u++) {
+                            const bool fresh = live[u] && (u == 0 || cell[u] != cell[u - 1]);
+                            ground[u] = fresh ? __ldg(ter.map + cell[u]) : 0.0f;
+                            lookups += fresh ? 1u : 0u;
+                        }
                         bool hit = false;
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int k = first + u * 32 + (int)lane;
-                            if (k < steps) {
-                                const float f = __fmul_rn((float)k, inv);
-                                float cx = __fadd_rn(host.x, __fmul_rn(dx, f));
-                                float cy = __fadd_rn(host.y, __fmul_rn(dy, f));
-                                const float ca = __fadd_rn(host.alt, __fmul_rn(dz, f));
-                                cx = fmaxf(ter.x_min, fminf(cx, ter.x_max));
-                                cy = fmaxf(ter.y_min, fminf(cy, ter.y_max));
-                                hit |= ca < aw_elevation(ter, cx, cy);
-                            }
+                        for (int u = 0; u < AWACS_CHUNK; u++) {
+                            if (u > 0 && cell[u] == cell[u - 1]) ground[u] = ground[u - 1];
+                            hit |= live[u] && (ray_alt[u] < ground[u]);
                         }
                         shielded = __any_sync(FULL, hit);
                     }
@@ -548,6 +577,8 @@ awacs_kernel(const AwacsArgs a)
         for (uint32_t k = 0u; k < 4u; k++) mode_n[k] += (fl & AW_F_MODE) == k ? 1u : 0u;
     }
     found = __reduce_add_sync(FULL, found);
+    uint64_t marched = lookups;
+    for (int o = 16; o > 0; o >>= 1) marched += __shfl_xor_sync(FULL, marched, o);
 #pragma unroll
     for (uint32_t k = 0u; k < 6u; k++) tds_n[k] = __reduce_add_sync(FULL, tds_n[k]);
 #pragma unroll
@@ -569,7 +600,8 @@ awacs_kernel(const AwacsArgs a)
 #pragma unroll
             for (uint32_t k = 0u; k < 6u; k++) c[k] = tds_n[k];
             c[6] = (uint64_t)mode_n[0] | ((uint64_t)mode_n[1] << 16) | ((uint64_t)mode_n[2] << 32) | ((uint64_t)mode_n[3] << 48);
-            c[7] = (uint64_t)__double_as_longlong(sum_y);
+            c[7] = marched;
+            (void)sum_y;
         }
     }
 }

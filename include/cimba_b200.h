@@ -103,7 +103,7 @@ extern "C" {
                                     * after num_objects SECONDS.  The terrain map all trials share is registered once per device with
                                     * cimba_b200_awacs_set_terrain(); arr_mean / srv_mean are not used.  Results: objects = targets found
                                     * (struct trial.num_found), sum_wait = sum of the targets' final x, counters[0..5] = targets per
-                                    * detect state, [6] = targets per mode (4 x 16 bits), [7] = sum of final y (bits); the per-target
+                                    * detect state, [6] = targets per mode (4 x 16 bits), [7] = terrain cells read by the line-of-sight marches; the per-target
                                     * state stays in the workspace (layout: CIMBA_B200_AWACS_* below).  Device-resident interface only.
                                     * Parity with the reference is exact while no float32 libm result straddles a test threshold, and
                                     * statistical beyond */
