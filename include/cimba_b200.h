@@ -105,8 +105,8 @@ extern "C" {
                                     * (struct trial.num_found), sum_wait = sum of the targets' final x, counters[0..5] = targets per
                                     * detect state, [6] = targets per mode (4 x 16 bits), [7] = terrain cells read by the line-of-sight marches; the per-target
                                     * state stays in the workspace (layout: CIMBA_B200_AWACS_* below).  Device-resident interface only.
-                                    * Parity with the reference is exact while no float32 libm result straddles a test threshold, and
-                                    * statistical beyond */
+                                    * Parity with the reference (glibc libm): atan2f / sinf / cosf are restated exactly, powf / expf rounded
+                                    * once from double - exact until one of those straddles a test threshold, statistical beyond */
 
 /* Error codes */
 #define CIMBA_B200_OK         0

@@ -2,11 +2,12 @@
 itself bit-identical to the unmodified tutorial source (tests/test_oracle_awacs.py).
 
 The detection chain consumes the trial's random stream only for targets that survive float32 geometry built
-on sinf / cosf / atan2f / powf / expf, so the contract is (DESIGN.md section 8): identical to the oracle - pop
+on sinf / cosf / atan2f / powf / expf, so the contract is (DESIGN.md section 3.6): identical to the oracle - pop
 trace, per-target positions and detect states, targets found - as long as no last-place difference between the
-device's and glibc's float functions straddles a test threshold, and statistically equal beyond that.  At the
-size used here (1000 targets x 180 sweeps) such a straddle is rare, so most trials must match exactly and every
-trial must match in the quantities that do not depend on the stream."""
+device's and glibc's float functions straddles a test threshold, and statistically equal beyond that.  The
+device restates glibc's atan2f / sinf / cosf exactly and rounds powf / expf once from double; measured on B200:
+12 of 12 trials of this size bit-identical (profiles/r01_awacs.md).  One trial of slack is left for a host libm
+that differs from the one the restatement was checked against."""
 import numpy as np
 import pytest
 import torch
@@ -52,7 +53,7 @@ def test_awacs_trials_against_the_oracle(setup):
         assert abs(int(ev[i]) - o.events) <= 0.02 * o.events
         assert abs(int(found[i]) - o.num_found) <= 40
         assert np.abs(np.bincount(tds[i], minlength=6) - np.array(o.tds_count)).max() <= 60
-    assert exact >= TRIALS // 2, f"only {exact} of {TRIALS} trials identical to the oracle"
+    assert exact >= TRIALS - 1, f"only {exact} of {TRIALS} trials identical to the oracle"
 
 
 def test_awacs_results_do_not_depend_on_batching(setup):
