@@ -87,3 +87,24 @@ def test_product_never_touches_the_oracle():
             code = "\n".join(l for l in text.splitlines()
                              if not l.lstrip().startswith(("//", "/*", "*", "#", '"""')))
             assert "oracle_libs" not in code and "liboracle" not in code and "cimba_port" not in code, p
+
+
+def test_awacs_entry_points_validate_before_touching_a_device(cb):
+    """cimba_b200_awacs_set_terrain rejects an unusable struct terrain (tutorial/tut_5_1.c:96-108) with EINVAL, a usable
+    one needs a device, MODEL_AWACS refuses the host-buffer path, and its workspace is 44 KB per trial."""
+    import torch
+    from cimba_b200 import _lib
+    assert C.sizeof(_lib.AwacsTerrain) == 8 + 2 * 4 + 6 * 4
+    bad = _lib.AwacsTerrain(map=None, cols=10, rows=10, x_scale=1.0, y_scale=1.0, x_min=-1.0, x_max=1.0, y_min=-1.0, y_max=1.0)
+    assert _lib.lib.cimba_b200_awacs_set_terrain(C.byref(bad)) == -1          # CIMBA_B200_EINVAL
+    assert b"terrain" in _lib.lib.cimba_b200_last_error()
+    flat = _lib.AwacsTerrain(map=8, cols=10, rows=10, x_scale=1.0, y_scale=1.0, x_min=1.0, x_max=1.0, y_min=-1.0, y_max=1.0)
+    assert _lib.lib.cimba_b200_awacs_set_terrain(C.byref(flat)) == -1
+    job = _lib.DeviceJob(model=cb.MODEL_AWACS, num_trials=3)
+    assert _lib.lib.cimba_b200_workspace_bytes(C.byref(job)) == 3 * 1024 * 44
+    if not torch.cuda.is_available():
+        ok = _lib.AwacsTerrain(map=8, cols=10, rows=10, x_scale=1.0, y_scale=1.0, x_min=-1.0, x_max=1.0, y_min=-1.0, y_max=1.0)
+        assert _lib.lib.cimba_b200_awacs_set_terrain(C.byref(ok)) == -2       # CIMBA_B200_ENODEVICE
+        exp = np.zeros(2, dtype=cb.TRIAL_DTYPE)
+        with pytest.raises(cb.CimbaError):
+            cb.cimba_run_experiment(exp, model=cb.MODEL_AWACS, num_objects=60, master_seed=1)
