@@ -32,5 +32,13 @@ w = torch.rand(1000, dtype=torch.float64, device="cuda")
 cb.summarize_weighted_on_device(x, w)
 cb.rng_draws(K, 1, 1000, 1.0)
 cb.rng_draws_ex(K, 17, 500, [1.0, 2.0, 6.0])
+# MODEL_AWACS on a synthetic 300 x 200 ridge (the oracle's terrain generator is not needed for a memory check)
+cols, rows = 300, 200
+yy, xx = torch.meshgrid(torch.arange(rows, dtype=torch.float32), torch.arange(cols, dtype=torch.float32), indexing="ij")
+ridge = (400.0 + 300.0 * torch.sin(xx / 17.0) * torch.cos(yy / 11.0)).clamp_min(0.0).reshape(-1).cuda()
+cb.awacs_set_terrain(ridge, cols, rows, (27.0, 31.0, -27.0 * (cols - 1) / 2, 27.0 * (cols - 1) / 2,
+                                         -31.0 * (rows - 1) / 2, 31.0 * (rows - 1) / 2))
+res, per = cb.awacs_run(5, duration_s=12, master_seed=K, trace_cap=64)
+print("awacs", res.total_events(), int(res.objects.sum()), flush=True)
 torch.cuda.synchronize()
 print("done")
