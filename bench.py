@@ -22,7 +22,6 @@ is the 8-double cmb_datasummary all-gather after the timed region.
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess

@@ -2,7 +2,6 @@
 golden numbers and the oracle), and the cross-rank merge over gloo, world_size 2."""
 import ctypes as C
 import math
-import os
 import subprocess
 import sys
 import textwrap

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from oracle_libs import Result, rng_draws, run_trials, trace_trial
+from oracle_libs import rng_draws, run_trials, trace_trial
 
 KAT_SEED = 0x34F05C64D7AD598F
 
