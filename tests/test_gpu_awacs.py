@@ -56,6 +56,35 @@ def test_awacs_trials_against_the_oracle(setup):
     assert exact >= TRIALS - 1, f"only {exact} of {TRIALS} trials identical to the oracle"
 
 
+def test_awacs_twenty_minutes_cover_every_mode_transition():
+    """1200 sweeps on a small map: long enough for targets to unmask, stage, fire, drive off and hide again
+    (the 180-second test only sees the first hold of each target), still short enough for the CPU oracle."""
+    port = load_port()
+    ter = awacs_terrain(port, "port", AWACS_TERRAIN_SEED, 6.0, 5.0)
+    m, cols, rows, geom = ter
+    cb.awacs_set_terrain(torch.from_numpy(m).cuda(), cols, rows, geom)
+    try:
+        cap, seconds, first = 4096, 1200, 40
+        res, per = cb.awacs_run(2, duration_s=seconds, master_seed=MASTER, first_trial=first, trace_cap=cap)
+        assert (res.status.cpu().numpy() == 0).all()
+        exact = 0
+        for i in range(2):
+            o, keys, times, p = awacs_trial(port, "port", cb.fmix64(MASTER, first + i), seconds / 3600.0, ter, trace_cap=cap)
+            assert o.mode_count[1] + o.mode_count[2] > 0 and o.events > 1003 + seconds + 100 + 60   # transitions happened
+            n = min(cap, int(res.events[i]), o.events)
+            same = (int(res.events[i]) == o.events and int(res.objects[i]) == o.num_found
+                    and per["tds"][i].cpu().tolist() == p["tds"] and per["mode"][i].cpu().tolist() == p["mode"]
+                    and np.array_equal(per["x"][i].cpu().numpy().view(np.uint32), p["x"].view(np.uint32))
+                    and res.trace_key[i][:n].cpu().tolist() == keys[:n] and res.trace_time[i][:n].cpu().tolist() == times[:n])
+            exact += bool(same)
+            assert abs(int(res.events[i]) - o.events) <= 0.02 * o.events and abs(int(res.objects[i]) - o.num_found) <= 40
+            assert np.abs(np.bincount(per["mode"][i].cpu().numpy(), minlength=4) - np.array(o.mode_count)).max() <= 40
+        assert exact >= 1, "neither twenty-minute trial is identical to the oracle"
+    finally:                                            # the other tests of this module use the 12 x 10 nm map
+        big = awacs_terrain(port, "port", AWACS_TERRAIN_SEED, 12.0, 10.0)
+        cb.awacs_set_terrain(torch.from_numpy(big[0]).cuda(), big[1], big[2], big[3])
+
+
 def test_awacs_results_do_not_depend_on_batching(setup):
     a, pa = cb.awacs_run(5, duration_s=60, master_seed=MASTER, first_trial=2)
     b, pb = cb.awacs_run(3, duration_s=60, master_seed=MASTER, first_trial=4)
