@@ -16,6 +16,7 @@
  * unmodified source (oracle/_ref/libawacs_ref.so) use the same libm and agree bit for bit.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -94,10 +95,49 @@ void port_awacs_grid(float width_nm, float height_nm, uint32_t *cols, uint32_t *
     *rows = (unsigned int)(height_nm * k_nm_m / k_arcsec_m);
 }
 
+typedef struct { const int *p; float *map; uint32_t cols, rows; float x_scale, y_scale; unsigned first, stride; } fill_job;
+
+/* the deterministic part of terrain_init's cell loop (:241-267): six octaves of ridged noise, h * terrain_max */
+static void *fill_rows(void *arg)
+{
+    const fill_job *j = arg;
+    for (unsigned row = j->first; row < j->rows; row += j->stride) {
+        const float ys = ((float)row - (float)j->rows / 2.0f) * j->y_scale;
+        for (unsigned col = 0; col < j->cols; col++) {
+            const float xs = ((float)col - (float)j->cols / 2.0f) * j->x_scale;
+            float h = 0.0f, freq = k_initfreq, amp = 1.0f, weight = 1.0f, ampsum = 0.0f;
+            for (unsigned i = 0; i < k_octaves; i++) {
+                float n = noise2d(j->p, xs * freq, ys * freq);
+                n = powf(1.0f - fabsf(n), k_ridginess);
+                h += n * amp * weight;
+                weight = n;
+                freq *= 2.05f;
+                ampsum += amp;
+                amp *= 0.5f;
+            }
+            h /= ampsum;
+            h = powf(h, k_peakiness);
+            j->map[(size_t)row * j->cols + col] = (h * k_terrain_max);
+        }
+    }
+    return NULL;
+}
+
 /* terrain_init, :197-294, after cmb_random_initialize(seed) as main() does (:1270-1274).
  * map: cols * rows floats owned by the caller; geom = {x_scale, y_scale, x_min, x_max, y_min, y_max} */
+int port_awacs_terrain_mt(uint64_t seed, float width_nm, float height_nm, float ref_lat, float ref_lon,
+                          float *map, float *geom, int *blueprint_out, int threads);
+
 int port_awacs_terrain(uint64_t seed, float width_nm, float height_nm, float ref_lat, float ref_lon,
                        float *map, float *geom, int *blueprint_out)
+{
+    return port_awacs_terrain_mt(seed, width_nm, height_nm, ref_lat, ref_lon, map, geom, blueprint_out, 1);
+}
+
+/* the same map with the noise computed by `threads` workers (the tutorial's 60 000 x 60 000 grid takes a
+ * quarter of an hour on one core) */
+int port_awacs_terrain_mt(uint64_t seed, float width_nm, float height_nm, float ref_lat, float ref_lon,
+                          float *map, float *geom, int *blueprint_out, int threads)
 {
     (void)ref_lon;
     port_rng rng;
@@ -136,26 +176,29 @@ int port_awacs_terrain(uint64_t seed, float width_nm, float height_nm, float ref
     for (int i = 0; i < 256; i++) p[256 + i] = p[i];
     if (blueprint_out) memcpy(blueprint_out, p, sizeof(p));
 
-    for (unsigned row = 0; row < rows; row++) {
-        const float ys = ((float)row - (float)rows / 2.0f) * y_scale;
-        for (unsigned col = 0; col < cols; col++) {
-            const float xs = ((float)col - (float)cols / 2.0f) * x_scale;
-            float h = 0.0f, freq = k_initfreq, amp = 1.0f, weight = 1.0f, ampsum = 0.0f;
-            for (unsigned i = 0; i < k_octaves; i++) {
-                float n = noise2d(p, xs * freq, ys * freq);
-                n = powf(1.0f - fabsf(n), k_ridginess);
-                h += n * amp * weight;
-                weight = n;
-                freq *= 2.05f;
-                ampsum += amp;
-                amp *= 0.5f;
-            }
-            h /= ampsum;
-            h = powf(h, k_peakiness);
-            float h_sum = (h * k_terrain_max) + (float)port_normal(&rng, 0.0, k_terrain_sd);
-            h_sum = (h_sum < 0.0f) ? 0.0f : h_sum;
-            map[(size_t)row * cols + col] = h_sum;
+    /* The noise part of a cell does not touch the random stream, the final cmb_random_normal does: rows are filled by
+     * `threads` workers first (any order), then one pass adds the normals in the reference's cell order. */
+    fill_job job = { p, map, cols, rows, x_scale, y_scale, 0u, 1u };
+    if (threads <= 1) {
+        fill_rows(&job);
+    }
+    else {
+        if (threads > 256) threads = 256;
+        pthread_t tid[256];
+        fill_job jobs[256];
+        for (int t = 0; t < threads; t++) {
+            jobs[t] = job;
+            jobs[t].first = (unsigned)t;
+            jobs[t].stride = (unsigned)threads;
+            pthread_create(&tid[t], NULL, fill_rows, &jobs[t]);
         }
+        for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
+    }
+    const size_t cells = (size_t)rows * cols;
+    for (size_t c = 0; c < cells; c++) {
+        float h_sum = map[c] + (float)port_normal(&rng, 0.0, k_terrain_sd);
+        h_sum = (h_sum < 0.0f) ? 0.0f : h_sum;
+        map[c] = h_sum;
     }
     return 0;
 }

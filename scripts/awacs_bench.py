@@ -8,6 +8,7 @@ target sweeps/s (targets x radar ticks) and terrain look-ups/s of the line-of-si
 bytes (4 B each)."""
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -27,9 +28,10 @@ def main():
     ap.add_argument("--seconds", type=int, default=600)
     ap.add_argument("--trials", type=int, default=592)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1, help="host threads for the terrain generator")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    m, cols, rows, geom = awacs_terrain(load_port(), "port", AWACS_TERRAIN_SEED, args.width, args.height)
+    m, cols, rows, geom = awacs_terrain(load_port(), "port", AWACS_TERRAIN_SEED, args.width, args.height, args.threads)
     dev = torch.device("cuda", 0)
     cb.awacs_set_terrain(torch.from_numpy(m).to(dev), cols, rows, geom)
     cb.awacs_run(8, duration_s=30, master_seed=1, device=dev)              # warm-up

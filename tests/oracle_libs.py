@@ -156,8 +156,9 @@ def load_awacs_ref():
     return lib
 
 
-def awacs_terrain(lib, prefix, seed, width_nm, height_nm):
-    """(map float32 [rows*cols], cols, rows, geom[6]) from the reference build ('ref') or the port ('port')."""
+def awacs_terrain(lib, prefix, seed, width_nm, height_nm, threads=1):
+    """(map float32 [rows*cols], cols, rows, geom[6]) from the reference build ('ref') or the port ('port');
+    `threads` > 1 lets the port compute the noise part of the cells in parallel (same map)."""
     cols, rows, geom = C.c_uint32(), C.c_uint32(), (C.c_float * 6)()
     if prefix == "ref":
         lib.awacs_ref_terrain(C.c_uint64(seed), C.c_float(width_nm), C.c_float(height_nm), C.c_float(30.0),
@@ -167,8 +168,8 @@ def awacs_terrain(lib, prefix, seed, width_nm, height_nm):
     else:
         lib.port_awacs_grid(C.c_float(width_nm), C.c_float(height_nm), C.byref(cols), C.byref(rows))
         m = np.empty(cols.value * rows.value, dtype=np.float32)
-        lib.port_awacs_terrain(C.c_uint64(seed), C.c_float(width_nm), C.c_float(height_nm), C.c_float(30.0),
-                               C.c_float(-10.0), m.ctypes.data_as(C.POINTER(C.c_float)), geom, None)
+        lib.port_awacs_terrain_mt(C.c_uint64(seed), C.c_float(width_nm), C.c_float(height_nm), C.c_float(30.0),
+                                  C.c_float(-10.0), m.ctypes.data_as(C.POINTER(C.c_float)), geom, None, C.c_int(threads))
     return m, cols.value, rows.value, np.array(list(geom), dtype=np.float32)
 
 

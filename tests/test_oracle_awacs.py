@@ -34,6 +34,13 @@ def test_port_terrain_matches_the_reference_vectors(port_terrain):
     assert hashlib.sha256(m.tobytes()).hexdigest() == g["map_sha256"]
 
 
+def test_threaded_terrain_generation_gives_the_same_map(port, port_terrain):
+    g = GOLD["terrain"]
+    m, cols, rows, geom = awacs_terrain(port, "port", AWACS_TERRAIN_SEED, g["width_nm"], g["height_nm"], threads=5)
+    assert (cols, rows) == port_terrain[1:3] and np.array_equal(geom, port_terrain[3])
+    assert np.array_equal(m.view(np.uint32), port_terrain[0].view(np.uint32))
+
+
 @pytest.mark.parametrize("case", GOLD["trials"], ids=lambda c: f"seed{c['seed']}")
 def test_port_trial_matches_the_reference_vectors(port, port_terrain, case):
     out, keys, times, per = awacs_trial(port, "port", case["seed"], GOLD["duration_h"], port_terrain, trace_cap=4000)
