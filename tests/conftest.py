@@ -11,6 +11,14 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "last: run after every other test (long oracle comparisons)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `last` go to the end, so that under `-x` the short parity tests have all run before them."""
+    tail = [it for it in items if it.get_closest_marker("last")]
+    if tail:
+        items[:] = [it for it in items if not it.get_closest_marker("last")] + tail
 
 
 @pytest.fixture(scope="session")

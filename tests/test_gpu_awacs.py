@@ -56,6 +56,7 @@ def test_awacs_trials_against_the_oracle(setup):
     assert exact >= TRIALS - 1, f"only {exact} of {TRIALS} trials identical to the oracle"
 
 
+@pytest.mark.last
 def test_awacs_twenty_minutes_cover_every_mode_transition():
     """1200 sweeps on a small map: long enough for targets to unmask, stage, fire, drive off and hide again
     (the 180-second test only sees the first hold of each target), still short enough for the CPU oracle."""
