@@ -45,6 +45,10 @@ class AwacsTerrain(C.Structure):
                 ("x_min", C.c_float), ("x_max", C.c_float), ("y_min", C.c_float), ("y_max", C.c_float)]
 
 
+THREAD_INIT_FUNC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint64)     # cimba_thread_init_func, include/cimba.h:155
+THREAD_EXIT_FUNC = C.CFUNCTYPE(None, C.c_void_p)                      # cimba_thread_exit_func, :163
+
+
 class Experiment(C.Structure):
     """struct cimba_b200_experiment"""
     _fields_ = [
@@ -83,6 +87,8 @@ SYMBOLS = {
     "cimba_b200_run_experiment_all_gpus": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment),
                                                      C.c_int]),
     "cimba_b200_awacs_set_terrain": (C.c_int, [C.POINTER(AwacsTerrain)]),
+    "cimba_b200_set_thread_hooks": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cimba_b200_thread_context": (C.c_void_p, []),
     "cimba_b200_datasummary_initialize": (None, [C.POINTER(DataSummaryStruct)]),
     "cimba_b200_datasummary_add": (C.c_uint64, [C.POINTER(DataSummaryStruct), C.c_double]),
     "cimba_b200_datasummary_merge": (C.c_uint64, [C.POINTER(DataSummaryStruct)] * 3),

@@ -962,6 +962,24 @@ void cimba_b200_release_cache(void)
     if (count > 0) cudaSetDevice(before);
 }
 
+namespace {
+std::mutex g_hook_mu;
+cimba_b200_thread_init_func *g_hook_init = nullptr;
+cimba_b200_thread_exit_func *g_hook_exit = nullptr;
+void *g_hook_usrarg = nullptr;
+thread_local void *t_thread_context = nullptr;
+}  // namespace
+
+void cimba_b200_set_thread_hooks(cimba_b200_thread_init_func *initfunc, void *usrarg, cimba_b200_thread_exit_func *exitfunc)
+{   // src/cimba.c:65-73
+    std::lock_guard<std::mutex> hold(g_hook_mu);
+    g_hook_init = initfunc;
+    g_hook_usrarg = usrarg;
+    g_hook_exit = exitfunc;
+}
+
+void *cimba_b200_thread_context(void) { return t_thread_context; }     // src/cimba.c:75-78
+
 // The reference's executive starts one pthread per logical core and lets them pull
 // trials (src/cimba.c:151-188).  The counterpart here: one host thread per GPU, each
 // running a contiguous block of the trial array on its own device and stream.  Seeds
@@ -986,8 +1004,21 @@ int cimba_b200_run_experiment_all_gpus(void *array, uint64_t num_trials, size_t 
             cimba_b200_experiment mine = *d;
             mine.device = g;
             mine.first_trial = d->first_trial + lo;
+            cimba_b200_thread_init_func *init;
+            cimba_b200_thread_exit_func *done;
+            void *usrarg;
+            {
+                std::lock_guard<std::mutex> hold(g_hook_mu);
+                init = g_hook_init;
+                done = g_hook_exit;
+                usrarg = g_hook_usrarg;
+            }
+            (void)cudaSetDevice(g);
+            if (init != nullptr) t_thread_context = init(usrarg, (uint64_t)g);      // src/cimba.c:102-104
             rc[(size_t)g] = cimba_b200_run_experiment((char *)array + lo * stride, hi - lo, stride, &mine);
             msg[(size_t)g] = g_err;                     // thread-local message of this worker
+            if (done != nullptr) done(t_thread_context);                            // thread_exit_wrapper, :80-86
+            t_thread_context = nullptr;
         });
     }
     for (auto &t : pool) {

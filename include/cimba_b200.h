@@ -263,6 +263,18 @@ int cimba_b200_run_experiment_all_gpus(void *your_experiment_array,
                                        const cimba_b200_experiment *desc,
                                        int max_gpus);
 
+/* cimba_set_thread_hooks / cimba_thread_context (include/cimba.h:148-195, src/cimba.c:65-78, :97-140; CHANGELOG: "for
+ * managing CUDA streams").  The reference calls init(usrarg, tid) at the start of each of its worker pthreads, keeps
+ * the returned pointer as that thread's context and calls exit(context) before the thread ends.  Here the worker
+ * threads are the ones cimba_b200_run_experiment_all_gpus starts, one per GPU, and tid is the GPU's ordinal: the
+ * hooks run on that thread after cudaSetDevice(tid) and before / after its block of trials.
+ * cimba_b200_run_experiment runs on the caller's own thread and calls no hook. */
+typedef void *(cimba_b200_thread_init_func)(void *usrarg, uint64_t tid);
+typedef void (cimba_b200_thread_exit_func)(void *thrctx);
+void  cimba_b200_set_thread_hooks(cimba_b200_thread_init_func *initfunc, void *usrarg,
+                                  cimba_b200_thread_exit_func *exitfunc);
+void *cimba_b200_thread_context(void);
+
 /* ------------------------------------------------------------------------
  * cmb_datasummary on the host (reference include/cmb_datasummary.h:42-51,
  * src/cmb_datasummary.c:93-166): same field order and arithmetic, used to fold

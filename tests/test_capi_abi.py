@@ -108,3 +108,15 @@ def test_awacs_entry_points_validate_before_touching_a_device(cb):
         exp = np.zeros(2, dtype=cb.TRIAL_DTYPE)
         with pytest.raises(cb.CimbaError):
             cb.cimba_run_experiment(exp, model=cb.MODEL_AWACS, num_objects=60, master_seed=1)
+
+
+def test_thread_hooks_can_be_set_without_a_device(cb):
+    """cimba_set_thread_hooks / cimba_thread_context (include/cimba.h:148-195): outside a worker thread there is no
+    context, and setting or clearing the hooks needs no GPU."""
+    from cimba_b200 import _lib
+    calls = []
+    init = _lib.THREAD_INIT_FUNC(lambda usrarg, tid: calls.append(tid) or 0)
+    _lib.lib.cimba_b200_set_thread_hooks(C.cast(init, C.c_void_p), None, None)
+    assert _lib.lib.cimba_b200_thread_context() is None
+    _lib.lib.cimba_b200_set_thread_hooks(None, None, None)
+    assert calls == []

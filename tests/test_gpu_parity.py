@@ -837,3 +837,37 @@ def test_resource_reproduces_the_reference_golden_file_on_device(cb, port, golde
     r, k, tt = trace_trial(port, "port", 14, 1, KAT_SEED, 25, 1.0, 1.0, 128)
     assert list(res.trace_key.cpu().numpy()[0, :85]) == k
     assert np.array_equal(_u64(res.trace_time.cpu().numpy()[0, :85]), _u64(np.array(tt)))
+
+
+def test_thread_hooks_run_on_the_per_gpu_worker_threads(cb):
+    """cimba_set_thread_hooks (include/cimba.h:148-195, src/cimba.c:97-140): init(usrarg, tid) at the start of each worker
+    thread - here one per GPU, tid = GPU ordinal - its return value is cimba_thread_context() on that thread and the
+    argument of exit() when the thread is done."""
+    import ctypes as C
+    import threading
+    from cimba_b200 import _lib
+    seen = {"init": [], "exit": [], "threads": set()}
+
+    def on_init(usrarg, tid):
+        seen["init"].append((usrarg, tid))
+        seen["threads"].add(threading.get_ident())
+        return 0x5150 + tid
+
+    def on_exit(ctx):
+        seen["exit"].append(ctx)
+
+    init, done = _lib.THREAD_INIT_FUNC(on_init), _lib.THREAD_EXIT_FUNC(on_exit)
+    _lib.lib.cimba_b200_set_thread_hooks(C.cast(init, C.c_void_p), C.c_void_p(77), C.cast(done, C.c_void_p))
+    try:
+        exp = np.zeros(64, dtype=cb.TRIAL_DTYPE)
+        exp["arr_mean"], exp["srv_mean"] = 1 / 0.9, 1.0
+        cb.cimba_run_experiment(exp, num_objects=500, master_seed=KAT_SEED, all_gpus=True, max_gpus=1)
+        assert (exp["obj_cnt"] == 500).all()
+        assert seen["init"] == [(77, 0)] and seen["exit"] == [0x5150]
+        assert threading.get_ident() not in seen["threads"] and _lib.lib.cimba_b200_thread_context() is None
+        plain = np.zeros(8, dtype=cb.TRIAL_DTYPE)
+        plain["arr_mean"], plain["srv_mean"] = 1 / 0.9, 1.0
+        cb.cimba_run_experiment(plain, num_objects=100, master_seed=KAT_SEED)        # caller's thread: no hook
+        assert len(seen["init"]) == 1
+    finally:
+        _lib.lib.cimba_b200_set_thread_hooks(None, None, None)
