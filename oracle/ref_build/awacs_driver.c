@@ -34,41 +34,55 @@ struct awacs_out {
     double   sum_x, sum_y;      /* sum of the targets' last recorded positions */
 };
 
-static uint64_t g_pops;
-static double g_t_end;
-static struct target *g_targets;
-static uint64_t g_trace_cap;
-static uint64_t *g_trace_key;
-static double *g_trace_time;
-static float g_x[NUM_TARGETS], g_y[NUM_TARGETS], g_alt[NUM_TARGETS];
-static int g_mode[NUM_TARGETS], g_tds[NUM_TARGETS], g_det[NUM_TARGETS];
-static struct terrain *g_terrain;
+/* per-thread capture area (one pointer of TLS: the reference library's own initial-exec TLS leaves little room
+ * in a dlopen'ed object) */
+struct awacs_capture {
+    uint64_t pops;
+    double t_end;
+    struct target *targets;
+    uint64_t trace_cap;
+    uint64_t *trace_key;
+    double *trace_time;
+    float x[NUM_TARGETS], y[NUM_TARGETS];
+    int mode[NUM_TARGETS], tds[NUM_TARGETS], det[NUM_TARGETS];
+};
+static _Thread_local struct awacs_capture *t_cap;
+static struct terrain *g_terrain, *g_owned;   /* the map in use; the one this driver allocated itself */
+
+static struct awacs_capture *capture(void)
+{
+    if (t_cap == NULL) {
+        t_cap = calloc(1, sizeof(*t_cap));      /* lives as long as its thread */
+        if (t_cap == NULL) abort();
+    }
+    return t_cap;
+}
 
 void *awacs_noting_calloc(unsigned long long n, unsigned long long sz)
 {
     void *p = calloc(n, sz);
     if (p == NULL) abort();
-    if (n == NUM_TARGETS && sz == sizeof(struct target)) g_targets = p;
+    if (n == NUM_TARGETS && sz == sizeof(struct target)) capture()->targets = p;
     return p;
 }
 
 void awacs_counting_execute(void)
 {
+    struct awacs_capture *c = capture();
     while (cmb_event_execute_next()) {
-        if (g_pops < g_trace_cap) {
-            g_trace_key[g_pops] = cmb_event_current();
-            g_trace_time[g_pops] = cmb_time();
+        if (c->pops < c->trace_cap) {
+            c->trace_key[c->pops] = cmb_event_current();
+            c->trace_time[c->pops] = cmb_time();
         }
-        g_pops++;
+        c->pops++;
     }
-    g_t_end = cmb_time();
-    for (unsigned i = 0; i < NUM_TARGETS && g_targets != NULL; i++) {
-        g_x[i] = g_targets[i].x_m;
-        g_y[i] = g_targets[i].y_m;
-        g_alt[i] = g_targets[i].alt_m;
-        g_mode[i] = (int)g_targets[i].mode;
-        g_tds[i] = (int)g_targets[i].tds;
-        g_det[i] = g_targets[i].detected ? 1 : 0;
+    c->t_end = cmb_time();
+    for (unsigned i = 0; i < NUM_TARGETS && c->targets != NULL; i++) {
+        c->x[i] = c->targets[i].x_m;
+        c->y[i] = c->targets[i].y_m;
+        c->mode[i] = (int)c->targets[i].mode;
+        c->tds[i] = (int)c->targets[i].tds;
+        c->det[i] = c->targets[i].detected ? 1 : 0;
     }
 }
 
@@ -78,13 +92,14 @@ int awacs_ref_num_targets(void) { return NUM_TARGETS; }
 int awacs_ref_terrain(uint64_t seed, float width_nm, float height_nm, float ref_lat, float ref_lon,
                       uint32_t *cols, uint32_t *rows, float *geom /* x_scale y_scale x_min x_max y_min y_max */)
 {
-    if (g_terrain != NULL) {
-        terrain_terminate(g_terrain);
-        terrain_destroy(g_terrain);
-        g_terrain = NULL;
+    if (g_owned != NULL) {
+        terrain_terminate(g_owned);
+        terrain_destroy(g_owned);
+        g_owned = NULL;
     }
     cmb_random_initialize(seed);
-    g_terrain = terrain_create();
+    g_owned = terrain_create();
+    g_terrain = g_owned;
     terrain_init(g_terrain, width_nm, height_nm, ref_lat, ref_lon);
     cmb_random_terminate();
     *cols = g_terrain->cols;
@@ -95,18 +110,33 @@ int awacs_ref_terrain(uint64_t seed, float width_nm, float height_nm, float ref_
     return 0;
 }
 
+/* Use a map made elsewhere (the restatement's threaded generator produces the identical grid in a fraction of the
+ * time, tests/test_oracle_awacs.py) - for timing runs only.  The caller keeps `map` alive. */
+int awacs_ref_adopt_terrain(float *map, uint32_t cols, uint32_t rows, const float *geom)
+{
+    static struct terrain adopted;
+    adopted.cols = cols;
+    adopted.rows = rows;
+    adopted.map = map;
+    adopted.x_scale = geom[0]; adopted.y_scale = geom[1];
+    adopted.x_min = geom[2];   adopted.x_max = geom[3];
+    adopted.y_min = geom[4];   adopted.y_max = geom[5];
+    g_terrain = &adopted;
+    return 0;
+}
+
 const float *awacs_ref_map(void) { return g_terrain ? g_terrain->map : NULL; }
 const int *awacs_ref_blueprint(void) { return g_terrain ? g_terrain->p : NULL; }
 
-int awacs_ref_trial(uint64_t seed, double duration_h, uint64_t trace_cap, uint64_t *trace_key, double *trace_time,
-                    struct awacs_out *out, float *x, float *y, int *mode, int *tds, int *detected)
+static void one_trial(uint64_t seed, double duration_h, uint64_t trace_cap, uint64_t *trace_key, double *trace_time,
+                      struct awacs_out *out)
 {
-    if (g_terrain == NULL) return -1;
-    g_pops = 0u;
-    g_targets = NULL;
-    g_trace_cap = trace_cap;
-    g_trace_key = trace_key;
-    g_trace_time = trace_time;
+    struct awacs_capture *c = capture();
+    c->pops = 0u;
+    c->targets = NULL;
+    c->trace_cap = trace_cap;
+    c->trace_key = trace_key;
+    c->trace_time = trace_time;
     struct trial trl = {};
     trl.terrain = g_terrain;
     trl.duration = duration_h;
@@ -114,20 +144,55 @@ int awacs_ref_trial(uint64_t seed, double duration_h, uint64_t trace_cap, uint64
     cmb_random_initialize(seed);
     run_trial(&trl);                    /* ends with cmb_random_terminate() */
     memset(out, 0, sizeof(*out));
-    out->events = g_pops;
-    out->t_end = g_t_end;
+    out->events = c->pops;
+    out->t_end = c->t_end;
     out->num_found = trl.num_found;
     for (unsigned i = 0; i < NUM_TARGETS; i++) {
-        out->tds_count[g_tds[i]]++;
-        out->mode_count[g_mode[i]]++;
-        out->sum_x += g_x[i];
-        out->sum_y += g_y[i];
-        if (x) x[i] = g_x[i];
-        if (y) y[i] = g_y[i];
-        if (mode) mode[i] = g_mode[i];
-        if (tds) tds[i] = g_tds[i];
-        if (detected) detected[i] = g_det[i];
+        out->tds_count[c->tds[i]]++;
+        out->mode_count[c->mode[i]]++;
+        out->sum_x += c->x[i];
+        out->sum_y += c->y[i];
     }
+}
+
+int awacs_ref_trial(uint64_t seed, double duration_h, uint64_t trace_cap, uint64_t *trace_key, double *trace_time,
+                    struct awacs_out *out, float *x, float *y, int *mode, int *tds, int *detected)
+{
+    if (g_terrain == NULL) return -1;
+    one_trial(seed, duration_h, trace_cap, trace_key, trace_time, out);
+    const struct awacs_capture *c = capture();
+    for (unsigned i = 0; i < NUM_TARGETS; i++) {
+        if (x) x[i] = c->x[i];
+        if (y) y[i] = c->y[i];
+        if (mode) mode[i] = c->mode[i];
+        if (tds) tds[i] = c->tds[i];
+        if (detected) detected[i] = c->det[i];
+    }
+    return 0;
+}
+
+/* `count` trials through the reference's OWN executive, cimba_run_experiment (src/cimba.c:151-188: one pthread per
+ * logical core pulling trial indices), seeds cmb_random_fmix64(master_seed, first + i) */
+struct awacs_job { uint64_t seed; double duration_h; struct awacs_out out; };
+
+static void awacs_job_func(void *vjob)
+{
+    struct awacs_job *j = vjob;
+    one_trial(j->seed, j->duration_h, 0u, NULL, NULL, &j->out);
+}
+
+int awacs_ref_experiment(uint64_t master_seed, uint64_t first, uint64_t count, double duration_h, struct awacs_out *out)
+{
+    if (g_terrain == NULL || count == 0u) return -1;
+    struct awacs_job *jobs = calloc(count, sizeof(*jobs));
+    if (jobs == NULL) return -2;
+    for (uint64_t i = 0; i < count; i++) {
+        jobs[i].seed = cmb_random_fmix64(master_seed, first + i);
+        jobs[i].duration_h = duration_h;
+    }
+    cimba_run_experiment(jobs, count, sizeof(*jobs), awacs_job_func);
+    for (uint64_t i = 0; i < count; i++) out[i] = jobs[i].out;
+    free(jobs);
     return 0;
 }
 

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--trials", type=int, default=592)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1, help="host threads for the terrain generator")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="also time this many trials of the unmodified reference model on all host cores (oracle/_ref)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     m, cols, rows, geom = awacs_terrain(load_port(), "port", AWACS_TERRAIN_SEED, args.width, args.height, args.threads)
@@ -53,6 +55,24 @@ def main():
         print(json.dumps(row), flush=True)
         if best is None or row["ms"] < best["ms"]:
             best = row
+    if args.cpu_sample:
+        import ctypes as C
+        import time
+        from oracle_libs import awacs_ref_experiment, load_awacs_ref
+        ref = load_awacs_ref()
+        if ref is None:
+            best["cpu_baseline"] = {"unavailable": "oracle/_ref/libawacs_ref.so is not built"}
+        else:
+            ref.awacs_ref_adopt_terrain(m.ctypes.data_as(C.POINTER(C.c_float)), C.c_uint32(cols), C.c_uint32(rows),
+                                        geom.ctypes.data_as(C.POINTER(C.c_float)))
+            t0 = time.time()
+            outs = awacs_ref_experiment(ref, 0x34F05C64D7AD598F, 0, args.cpu_sample, args.seconds / 3600.0)
+            dt = time.time() - t0
+            best["cpu_baseline"] = {"kind": "reference", "cores": os.cpu_count(), "sample": f"{args.cpu_sample} trials x {args.seconds} s",
+                                    "seconds": dt, "target_sweeps_per_s": args.cpu_sample * args.seconds * 1000 / dt,
+                                    "events_per_s": sum(o.events for o in outs) / dt,
+                                    "found_mean": sum(o.num_found for o in outs) / len(outs)}
+        print(json.dumps(best["cpu_baseline"]), flush=True)
     if args.out:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
         Path(args.out).write_text(json.dumps(best, indent=1))

@@ -194,3 +194,12 @@ def awacs_trial(lib, prefix, seed, duration_h, terrain=None, trace_cap=0):
     per = dict(x=np.array(x[:], dtype=np.float32), y=np.array(y[:], dtype=np.float32), mode=list(mode), tds=list(tds),
                detected=list(det))
     return out, list(keys)[:n], list(times)[:n], per
+
+
+def awacs_ref_experiment(lib, master_seed, first, count, duration_h):
+    """`count` trials of the unmodified tutorial model through the reference's own cimba_run_experiment (all host
+    cores), seeds cmb_random_fmix64(master_seed, first + i); uses the terrain of the last awacs_ref_terrain call."""
+    out = (AwacsOut * count)()
+    rc = lib.awacs_ref_experiment(C.c_uint64(master_seed), C.c_uint64(first), C.c_uint64(count), C.c_double(duration_h), out)
+    assert rc == 0
+    return list(out)

@@ -73,3 +73,19 @@ def test_port_matches_the_live_reference_build(port):
         assert ro.key() == po.key() and rk == pk and rtm == ptm
         assert rper["tds"] == pper["tds"] and rper["detected"] == pper["detected"] and rper["mode"] == pper["mode"]
         assert np.array_equal(rper["x"].view(np.uint32), pper["x"].view(np.uint32))
+
+
+def test_reference_executive_runs_awacs_trials_in_parallel(port):
+    """cimba_run_experiment over the tutorial's run_trial (all host cores) gives what one-at-a-time runs give."""
+    from oracle_libs import awacs_ref_experiment, load_ref
+    ref = load_awacs_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/libawacs_ref.so not built (needs /root/reference)")
+    pt = awacs_terrain(port, "port", 77, 8.0, 6.0)
+    awacs_terrain(ref, "ref", 77, 8.0, 6.0)
+    master = 0x34F05C64D7AD598F
+    outs = awacs_ref_experiment(ref, master, 3, 6, 0.02)
+    fmix = load_ref().ref_fmix64
+    for i, o in enumerate(outs):
+        po, _, _, _ = awacs_trial(port, "port", fmix(master, 3 + i), 0.02, pt)
+        assert o.key() == po.key()
