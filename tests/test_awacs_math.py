@@ -19,3 +19,12 @@ def test_shipped_float_routines_match_the_host_libm(tmp_path):
     # not restated (table-driven in glibc): double results rounded once.  They differ from glibc's float routines only in
     # rare last places; the bound documents how rare (each detection attempt calls powf and expf once)
     assert out["powf_rounded_once"] <= out["n"] * 0.05 and out["expf_rounded_once"] <= out["n"] * 0.05, out
+
+
+def test_restated_double_exp_matches_the_host_libm(tmp_path):
+    """cimba_b200/csrc/glibc_exp.cuh (glibc's e_exp.c algorithm with a recomputed table) against the host's exp()."""
+    exe = tmp_path / "glibc_exp_harness"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", str(ROOT / "tests/glibc_exp_harness.cpp"), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = json.loads(subprocess.run([str(exe), "4000000"], check=True, capture_output=True, text=True).stdout)
+    assert out == {"n": 4000000, "exp": 0}
