@@ -31,9 +31,11 @@
 #pragma once
 
 #include "awacs_math.cuh"
+#ifndef AWACS_HOST_EMULATION      // tests/awacs_kernel_emulation.cpp supplies these pieces itself
 #include "engine.cuh"
 #include "hold_deep.cuh"
 #include "rng.cuh"
+#endif
 
 namespace cimba_b200 {
 
