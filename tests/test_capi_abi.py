@@ -120,3 +120,16 @@ def test_thread_hooks_can_be_set_without_a_device(cb):
     assert _lib.lib.cimba_b200_thread_context() is None
     _lib.lib.cimba_b200_set_thread_hooks(None, None, None)
     assert calls == []
+
+
+def test_the_header_is_plain_c_and_the_stub_of_integration_md_links(cb, tmp_path):
+    """include/cimba_b200.h compiled as C11 by gcc with warnings as errors, linked against the library, run."""
+    import subprocess
+    from cimba_b200 import _lib
+    exe = tmp_path / "c_binding_stub"
+    lib_dir = Path(_lib.LIB_PATH).parent
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests/c_binding_stub.c"),
+                    "-o", str(exe), f"-L{lib_dir}", "-lcimba_b200", f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True)
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "fmix a9668314774003f8" in run.stdout and "mean 2.0" in run.stdout and "N        5  Mean    2.000" in run.stdout
