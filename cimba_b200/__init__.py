@@ -8,12 +8,12 @@ happens in the hand-written sm_100a kernels under cimba_b200/csrc.
 from ._lib import (MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED, MODEL_HARBOR, MODEL_GUARDED_RECORDED, MODEL_BUFFER_RECORDED, MODEL_PRIOQ_RECORDED, MODEL_RESOURCE_RECORDED, MODEL_AWACS, MAP_LANE, MAP_WARP, CimbaError, lib)
 from .experiment import (TrialResults, cimba_run_experiment, launch_trials, run_trials,
                          rng_draws, rng_draws_ex, alias_create, fmix64, TRIAL_DTYPE,
-                         awacs_set_terrain, awacs_run)
+                         awacs_set_terrain, awacs_upload_terrain, awacs_run)
 from .summary import (DataSummary, WtdSummary, summarize_on_device, merge_across_ranks,
                       summarize_weighted_on_device, merge_weighted_rows_on_device, merge_weighted_across_ranks)
 
 __all__ = [
-    "MODEL_MM1", "MODEL_GG1", "MODEL_MMC", "MODEL_GUARDED", "MODEL_PREEMPT", "MODEL_BUFFER", "MODEL_PRIOQ", "MODEL_HOLD", "MODEL_TIMERS", "MODEL_MM1_RECORDED", "MODEL_HARBOR", "MODEL_GUARDED_RECORDED", "MODEL_BUFFER_RECORDED", "MODEL_PRIOQ_RECORDED", "MODEL_RESOURCE_RECORDED", "MODEL_AWACS", "awacs_set_terrain", "awacs_run", "MAP_LANE", "MAP_WARP", "CimbaError", "lib",
+    "MODEL_MM1", "MODEL_GG1", "MODEL_MMC", "MODEL_GUARDED", "MODEL_PREEMPT", "MODEL_BUFFER", "MODEL_PRIOQ", "MODEL_HOLD", "MODEL_TIMERS", "MODEL_MM1_RECORDED", "MODEL_HARBOR", "MODEL_GUARDED_RECORDED", "MODEL_BUFFER_RECORDED", "MODEL_PRIOQ_RECORDED", "MODEL_RESOURCE_RECORDED", "MODEL_AWACS", "awacs_set_terrain", "awacs_upload_terrain", "awacs_run", "MAP_LANE", "MAP_WARP", "CimbaError", "lib",
     "TrialResults", "cimba_run_experiment", "launch_trials", "run_trials", "rng_draws", "rng_draws_ex", "alias_create", "fmix64",
     "TRIAL_DTYPE", "DataSummary", "WtdSummary", "summarize_on_device", "merge_across_ranks",
     "summarize_weighted_on_device", "merge_weighted_rows_on_device", "merge_weighted_across_ranks",

@@ -87,6 +87,7 @@ SYMBOLS = {
     "cimba_b200_run_experiment_all_gpus": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t, C.POINTER(Experiment),
                                                      C.c_int]),
     "cimba_b200_awacs_set_terrain": (C.c_int, [C.POINTER(AwacsTerrain)]),
+    "cimba_b200_awacs_upload_terrain": (C.c_int, [C.POINTER(AwacsTerrain)]),
     "cimba_b200_set_thread_hooks": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cimba_b200_thread_context": (C.c_void_p, []),
     "cimba_b200_datasummary_initialize": (None, [C.POINTER(DataSummaryStruct)]),

@@ -182,6 +182,7 @@ constexpr int MAX_TERRAIN_DEVICES = 64;
 std::mutex g_terrain_mu;
 AwacsTerrain g_terrain[MAX_TERRAIN_DEVICES];
 bool g_terrain_set[MAX_TERRAIN_DEVICES];
+float *g_terrain_owned[MAX_TERRAIN_DEVICES];     // device copies made by cimba_b200_awacs_upload_terrain
 
 // racetrack_initialize with run_trial's arguments (tutorial/tut_5_1.c:724-782, :1177-1188): constants of the
 // model, evaluated once on the host with the host's libm, exactly as the reference evaluates them
@@ -639,6 +640,35 @@ int cimba_b200_awacs_set_terrain(const cimba_b200_awacs_terrain *t)
     return CIMBA_B200_OK;
 }
 
+int cimba_b200_awacs_upload_terrain(const cimba_b200_awacs_terrain *t)
+{
+    if (t == nullptr || t->map == nullptr || t->cols < 2u || t->rows < 2u)
+        return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
+    if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_TERRAIN_DEVICES) return fail(CIMBA_B200_EINVAL, "device index out of range");
+    const size_t bytes = (size_t)t->cols * (size_t)t->rows * sizeof(float);
+    float *copy = nullptr;
+    CUDA_TRY(cudaMalloc(&copy, bytes));
+    cudaError_t e = cudaMemcpy(copy, t->map, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(copy);
+        return cuda_fail(e, "terrain upload");
+    }
+    cimba_b200_awacs_terrain on_device = *t;
+    on_device.map = copy;
+    const int rc = cimba_b200_awacs_set_terrain(&on_device);
+    std::lock_guard<std::mutex> hold(g_terrain_mu);
+    if (rc != CIMBA_B200_OK) {
+        cudaFree(copy);
+        return rc;
+    }
+    if (g_terrain_owned[dev] != nullptr) cudaFree(g_terrain_owned[dev]);    // no job may still be reading the old map
+    g_terrain_owned[dev] = copy;
+    return CIMBA_B200_OK;
+}
+
 int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
                          uint64_t num_trials, double *out_summary, void *stream)
 {
@@ -957,6 +987,17 @@ void cimba_b200_release_cache(void)
         if (g_cache[g].dev || g_cache[g].h_in || g_cache[g].h_out || g_cache[g].st) {
             cudaSetDevice(g);
             g_cache[g].release();
+        }
+    }
+    {
+        std::lock_guard<std::mutex> hold(g_terrain_mu);
+        for (int g = 0; g < count && g < MAX_TERRAIN_DEVICES; g++) {
+            if (g_terrain_owned[g] != nullptr) {
+                cudaSetDevice(g);
+                cudaFree(g_terrain_owned[g]);
+                g_terrain_owned[g] = nullptr;
+                g_terrain_set[g] = false;
+            }
         }
     }
     if (count > 0) cudaSetDevice(before);

@@ -249,6 +249,21 @@ def awacs_set_terrain(elevations: torch.Tensor, cols: int, rows: int, geom) -> N
     _awacs_maps[elevations.device.index] = elevations
 
 
+def awacs_upload_terrain(elevations: np.ndarray, cols: int, rows: int, geom, device: Optional[torch.device] = None) -> None:
+    """The same from a HOST array (float32, rows * cols): the library makes and owns the device copy
+    (cimba_b200_awacs_upload_terrain) - what a C caller without CUDA code of its own uses."""
+    m = np.ascontiguousarray(elevations, dtype=np.float32)
+    if m.size != cols * rows:
+        raise ValueError("elevations must hold rows * cols values")
+    g = [float(v) for v in geom]
+    desc = _lib.AwacsTerrain(map=m.ctypes.data, cols=cols, rows=rows, x_scale=g[0], y_scale=g[1],
+                             x_min=g[2], x_max=g[3], y_min=g[4], y_max=g[5])
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        check(lib.cimba_b200_awacs_upload_terrain(C.byref(desc)))
+    _awacs_maps.pop(dev.index, None)
+
+
 def awacs_run(num_trials: int, *, duration_s: int, master_seed: int, first_trial: int = 0, trace_cap: int = 0,
               device: Optional[torch.device] = None):
     """Run MODEL_AWACS trials (seeds cmb_random_fmix64(master_seed, first_trial + i)) for ``duration_s`` simulated

@@ -178,6 +178,9 @@ typedef struct cimba_b200_awacs_terrain {
     float x_min, x_max, y_min, y_max;
 } cimba_b200_awacs_terrain;
 int cimba_b200_awacs_set_terrain(const cimba_b200_awacs_terrain *terrain);
+/* The same for a caller without CUDA code of its own: `terrain->map` is a HOST pointer (tp->map as terrain_init left
+ * it); the library keeps a device copy per GPU (replaced by the next upload, freed by cimba_b200_release_cache). */
+int cimba_b200_awacs_upload_terrain(const cimba_b200_awacs_terrain *terrain);
 
 /* MODEL_AWACS workspace: per trial CIMBA_B200_AWACS_STATE_BYTES, columns of CIMBA_B200_AWACS_STRIDE entries in this
  * order: float x, y, alt, dir, vel, time_s, rcs_now; uint32 flags (bits 0-1 mode, 4-6 detect state, 8 found);

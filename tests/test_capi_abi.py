@@ -100,11 +100,15 @@ def test_awacs_entry_points_validate_before_touching_a_device(cb):
     assert b"terrain" in _lib.lib.cimba_b200_last_error()
     flat = _lib.AwacsTerrain(map=8, cols=10, rows=10, x_scale=1.0, y_scale=1.0, x_min=1.0, x_max=1.0, y_min=-1.0, y_max=1.0)
     assert _lib.lib.cimba_b200_awacs_set_terrain(C.byref(flat)) == -1
+    assert _lib.lib.cimba_b200_awacs_upload_terrain(C.byref(bad)) == -1
     job = _lib.DeviceJob(model=cb.MODEL_AWACS, num_trials=3)
     assert _lib.lib.cimba_b200_workspace_bytes(C.byref(job)) == 3 * 1024 * 44
     if not torch.cuda.is_available():
         ok = _lib.AwacsTerrain(map=8, cols=10, rows=10, x_scale=1.0, y_scale=1.0, x_min=-1.0, x_max=1.0, y_min=-1.0, y_max=1.0)
         assert _lib.lib.cimba_b200_awacs_set_terrain(C.byref(ok)) == -2       # CIMBA_B200_ENODEVICE
+        host = np.zeros(100, dtype=np.float32)
+        ok.map = host.ctypes.data
+        assert _lib.lib.cimba_b200_awacs_upload_terrain(C.byref(ok)) == -2
         exp = np.zeros(2, dtype=cb.TRIAL_DTYPE)
         with pytest.raises(cb.CimbaError):
             cb.cimba_run_experiment(exp, model=cb.MODEL_AWACS, num_objects=60, master_seed=1)

@@ -93,6 +93,18 @@ def test_awacs_results_do_not_depend_on_batching(setup):
     assert torch.equal(pa["tds"][2:], pb["tds"]) and torch.equal(a.counters[2:], b.counters)
 
 
+def test_awacs_terrain_uploaded_from_a_host_array_gives_the_same_trials(setup):
+    port, ter = setup
+    a, pa = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
+    cb.awacs_upload_terrain(ter[0], ter[1], ter[2], ter[3])
+    try:
+        b, pb = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
+        assert torch.equal(a.events, b.events) and torch.equal(a.objects, b.objects) and torch.equal(a.counters, b.counters)
+        assert torch.equal(pa["tds"], pb["tds"]) and torch.equal(pa["x"], pb["x"])
+    finally:
+        cb.awacs_set_terrain(torch.from_numpy(ter[0]).cuda(), ter[1], ter[2], ter[3])
+
+
 def test_awacs_needs_a_terrain_and_the_device_interface():
     exp = np.zeros(4, dtype=cb.TRIAL_DTYPE)
     with pytest.raises(cb.CimbaError):
