@@ -28,3 +28,16 @@ def test_restated_double_exp_matches_the_host_libm(tmp_path):
                    check=True, capture_output=True)
     out = json.loads(subprocess.run([str(exe), "4000000"], check=True, capture_output=True, text=True).stdout)
     assert out == {"n": 4000000, "exp": 0}
+
+
+def test_restated_expf_and_powf_match_the_host_libm(tmp_path):
+    """cimba_b200/csrc/glibc_float.cuh (glibc's e_expf.c / e_powf.c algorithms) against the host's expf / powf: sampled on
+    every run; CIMBA_B200_EXHAUSTIVE=1 also walks every float of the fast paths (expf: |x| < 88; powf(x, 4): 2^-31..2^31)."""
+    import os
+    exe = tmp_path / "glibc_float_harness"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", str(ROOT / "tests/glibc_float_harness.cpp"), "-o", str(exe),
+                    "-lpthread"], check=True, capture_output=True)
+    args = [str(exe), "3000000"] + (["exhaustive"] if os.environ.get("CIMBA_B200_EXHAUSTIVE") else [])
+    out = json.loads(subprocess.run(args, check=True, capture_output=True, text=True, timeout=1200).stdout)
+    assert (out["expf"], out["powf"], out["powf4"]) == (0, 0, 0), out
+    assert (out["expf_all_floats"], out["powf4_all_floats"]) == (0, 0), out
