@@ -15,7 +15,7 @@ import torch
 import cimba_b200 as cb
 from oracle_libs import AWACS_TERRAIN_SEED, awacs_terrain, awacs_trial, load_port
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.last]      # the newest model: after every long-standing parity test
 MASTER = 0x34F05C64D7AD598F
 SECONDS = 180
 TRIALS = 6
@@ -56,7 +56,31 @@ def test_awacs_trials_against_the_oracle(setup):
     assert exact >= TRIALS - 1, f"only {exact} of {TRIALS} trials identical to the oracle"
 
 
-@pytest.mark.last
+def test_awacs_results_do_not_depend_on_batching(setup):
+    a, pa = cb.awacs_run(5, duration_s=60, master_seed=MASTER, first_trial=2)
+    b, pb = cb.awacs_run(3, duration_s=60, master_seed=MASTER, first_trial=4)
+    assert torch.equal(a.events[2:], b.events) and torch.equal(a.objects[2:], b.objects)
+    assert torch.equal(pa["tds"][2:], pb["tds"]) and torch.equal(a.counters[2:], b.counters)
+
+
+def test_awacs_needs_a_terrain_and_the_device_interface():
+    exp = np.zeros(4, dtype=cb.TRIAL_DTYPE)
+    with pytest.raises(cb.CimbaError):
+        cb.cimba_run_experiment(exp, model=cb.MODEL_AWACS, num_objects=60, master_seed=1)
+
+
+def test_awacs_terrain_uploaded_from_a_host_array_gives_the_same_trials(setup):
+    port, ter = setup
+    a, pa = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
+    cb.awacs_upload_terrain(ter[0], ter[1], ter[2], ter[3])
+    try:
+        b, pb = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
+        assert torch.equal(a.events, b.events) and torch.equal(a.objects, b.objects) and torch.equal(a.counters, b.counters)
+        assert torch.equal(pa["tds"], pb["tds"]) and torch.equal(pa["x"], pb["x"])
+    finally:
+        cb.awacs_set_terrain(torch.from_numpy(ter[0]).cuda(), ter[1], ter[2], ter[3])
+
+
 def test_awacs_twenty_minutes_cover_every_mode_transition():
     """1200 sweeps on a small map: long enough for targets to unmask, stage, fire, drive off and hide again
     (the 180-second test only sees the first hold of each target), still short enough for the CPU oracle."""
@@ -84,28 +108,3 @@ def test_awacs_twenty_minutes_cover_every_mode_transition():
     finally:                                            # the other tests of this module use the 12 x 10 nm map
         big = awacs_terrain(port, "port", AWACS_TERRAIN_SEED, 12.0, 10.0)
         cb.awacs_set_terrain(torch.from_numpy(big[0]).cuda(), big[1], big[2], big[3])
-
-
-def test_awacs_results_do_not_depend_on_batching(setup):
-    a, pa = cb.awacs_run(5, duration_s=60, master_seed=MASTER, first_trial=2)
-    b, pb = cb.awacs_run(3, duration_s=60, master_seed=MASTER, first_trial=4)
-    assert torch.equal(a.events[2:], b.events) and torch.equal(a.objects[2:], b.objects)
-    assert torch.equal(pa["tds"][2:], pb["tds"]) and torch.equal(a.counters[2:], b.counters)
-
-
-def test_awacs_terrain_uploaded_from_a_host_array_gives_the_same_trials(setup):
-    port, ter = setup
-    a, pa = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
-    cb.awacs_upload_terrain(ter[0], ter[1], ter[2], ter[3])
-    try:
-        b, pb = cb.awacs_run(3, duration_s=45, master_seed=MASTER, first_trial=9)
-        assert torch.equal(a.events, b.events) and torch.equal(a.objects, b.objects) and torch.equal(a.counters, b.counters)
-        assert torch.equal(pa["tds"], pb["tds"]) and torch.equal(pa["x"], pb["x"])
-    finally:
-        cb.awacs_set_terrain(torch.from_numpy(ter[0]).cuda(), ter[1], ter[2], ter[3])
-
-
-def test_awacs_needs_a_terrain_and_the_device_interface():
-    exp = np.zeros(4, dtype=cb.TRIAL_DTYPE)
-    with pytest.raises(cb.CimbaError):
-        cb.cimba_run_experiment(exp, model=cb.MODEL_AWACS, num_objects=60, master_seed=1)
