@@ -839,6 +839,7 @@ def test_resource_reproduces_the_reference_golden_file_on_device(cb, port, golde
     assert np.array_equal(_u64(res.trace_time.cpu().numpy()[0, :85]), _u64(np.array(tt)))
 
 
+@pytest.mark.last
 def test_thread_hooks_run_on_the_per_gpu_worker_threads(cb):
     """cimba_set_thread_hooks (include/cimba.h:148-195, src/cimba.c:97-140): init(usrarg, tid) at the start of each worker
     thread - here one per GPU, tid = GPU ordinal - its return value is cimba_thread_context() on that thread and the
