@@ -114,7 +114,15 @@ AW_MATH_FN float aw_sincosf(float y)
 }
 AW_MATH_FN float aw_sinf(float x) { return aw_sincosf<false>(x); }
 AW_MATH_FN float aw_cosf(float x) { return aw_sincosf<true>(x); }
+#ifdef AWACS_GLIBC_FLOAT     // opt-in build (scripts/build_variant.py ... -DAWACS_GLIBC_FLOAT): glibc's powf / expf restated as well
+}  // namespace cimba_b200
+#include "glibc_float.cuh"
+namespace cimba_b200 {
+AW_MATH_FN float aw_powf(float a, float b) { return glibc_powf(a, b); }
+AW_MATH_FN float aw_expf(float x) { return glibc_expf(x); }
+#else
 AW_MATH_FN float aw_powf(float a, float b) { return (float)pow((double)a, (double)b); }
 AW_MATH_FN float aw_expf(float x) { return (float)exp((double)x); }
+#endif
 
 }  // namespace cimba_b200

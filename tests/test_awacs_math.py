@@ -19,6 +19,13 @@ def test_shipped_float_routines_match_the_host_libm(tmp_path):
     # not restated (table-driven in glibc): double results rounded once.  They differ from glibc's float routines only in
     # rare last places; the bound documents how rare (each detection attempt calls powf and expf once)
     assert out["powf_rounded_once"] <= out["n"] * 0.05 and out["expf_rounded_once"] <= out["n"] * 0.05, out
+    # the opt-in build (-DAWACS_GLIBC_FLOAT: glibc's powf and expf restated too, csrc/glibc_float.cuh): nothing differs
+    exe2 = tmp_path / "awacs_math_harness_glibc_float"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DAWACS_GLIBC_FLOAT", str(ROOT / "tests/awacs_math_harness.cpp"),
+                    "-o", str(exe2)], check=True, capture_output=True)
+    out2 = json.loads(subprocess.run([str(exe2), "2000000"], check=True, capture_output=True, text=True).stdout)
+    assert {k: v for k, v in out2.items() if k != "n"} == {"atan2f": 0, "sinf": 0, "cosf": 0, "powf_rounded_once": 0,
+                                                             "expf_rounded_once": 0}, out2
 
 
 def test_restated_double_exp_matches_the_host_libm(tmp_path):
