@@ -35,6 +35,8 @@ class DeviceJob(C.Structure):
         ("status", C.c_void_p), ("max_queue", C.c_void_p), ("counters", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64),
         ("trace_cap", C.c_uint64), ("trace_key", C.c_void_p), ("trace_time", C.c_void_p),
+        ("queue_spill_cap", C.c_uint32), ("reserved0", C.c_uint32), ("diag", C.c_void_p),
+        ("params", C.POINTER(C.c_double)), ("num_params", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 
@@ -53,7 +55,7 @@ class Experiment(C.Structure):
     """struct cimba_b200_experiment"""
     _fields_ = [
         ("model", C.c_int32), ("servers", C.c_int32), ("mapping", C.c_int32), ("device", C.c_int32),
-        ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("variant", C.c_int32), ("queue_spill_cap", C.c_uint32),
         ("master_seed", C.c_uint64), ("first_trial", C.c_uint64), ("num_objects", C.c_uint64),
         ("off_arr_mean", C.c_size_t), ("off_srv_mean", C.c_size_t),
         ("off_obj_cnt", C.c_size_t), ("off_sum_wait", C.c_size_t), ("off_avg_wait", C.c_size_t),

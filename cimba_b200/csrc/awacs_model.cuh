@@ -35,6 +35,7 @@
 #include "engine.cuh"
 #include "hold_deep.cuh"
 #include "rng.cuh"
+#include "tma_bulk.cuh"
 #endif
 
 namespace cimba_b200 {
@@ -48,6 +49,11 @@ constexpr int AWACS_STRIDE = 1024;              // rows per column of the state 
 // per-trial state block in HBM/L2, structure of arrays, AWACS_STRIDE entries each:
 //   float x, y, alt, dir, vel, time_s, rcs_now; uint32 flags; uint32 wake_key; double wake_t
 constexpr size_t AWACS_STATE_BYTES = (size_t)AWACS_STRIDE * (7 * 4 + 4 + 4 + 8);
+// pass A streams the six columns it reads (x, y, alt, dir, vel, time_s) through shared memory in tiles of
+// AWACS_TILE_TARGETS rows, two tiles in flight per warp, moved by the TMA bulk-copy engine (tma_bulk.cuh)
+constexpr int AWACS_TILE_TARGETS = 128;
+constexpr int AWACS_TILES = AWACS_STRIDE / AWACS_TILE_TARGETS;      // 8 tiles cover the 1000 targets (+ 24 idle rows)
+constexpr int AWACS_STREAM_COLS = 6;
 
 enum : uint32_t { AW_HIDING = 0, AW_STAGING = 1, AW_FIRING = 2, AW_DRIVING = 3 };
 enum : uint32_t { AW_UNDETERMINED = 0, AW_BEYOND_HORIZON, AW_NADIR_HOLE, AW_TERRAIN_SHIELDED, AW_MISSED, AW_DETECTED };
@@ -57,7 +63,14 @@ struct AwacsTerrain {           // struct terrain, tut_5_1.c:96-108
     const float *map;
     uint32_t cols, rows;
     float x_scale, y_scale, x_min, x_max, y_min, y_max;
+    // not in the reference: the highest cell of every AWACS_TILE x AWACS_TILE block of the map ([trows][tcols], built
+    // once per registered terrain by aw_tile_max_kernel).  The line-of-sight march asks it which 256-step stretches
+    // of a ray can touch the ground at all; see pass B.
+    const float *tile_max;
+    uint32_t tcols, trows;
 };
+
+constexpr uint32_t AWACS_TILE_SHIFT = 7u, AWACS_TILE = 1u << AWACS_TILE_SHIFT;      // 128 x 128 cells: 64 KB of map per entry
 
 struct AwacsOrbit {             // struct racetrack after racetrack_initialize (:724-782), evaluated on the host
     float start_time, orientation_r, length_m, turn_radius_m, altitude_m, velocity_ms;
@@ -81,13 +94,23 @@ struct AwacsArgs {
 };
 
 // terrain_index + terrain_elevation, tut_5_1.c:314-338
-__device__ __forceinline__ size_t aw_cell(const AwacsTerrain &t, float x, float y)
+// (a cell index fits 32 bits: the tutorial's 60 000 x 60 000 map has 3.6e9 cells; registration refuses more than 2^32 - 1)
+__device__ __forceinline__ uint32_t aw_cell(const AwacsTerrain &t, float x, float y)
 {
     const int raw_col = (int)roundf(__fdiv_rn(x, t.x_scale)) + (int)(t.cols / 2u);
     const int raw_row = (int)roundf(__fdiv_rn(y, t.y_scale)) + (int)(t.rows / 2u);
     const uint32_t col = (uint32_t)(raw_col < 0 ? 0 : (raw_col >= (int)t.cols ? (int)t.cols - 1 : raw_col));
     const uint32_t row = (uint32_t)(raw_row < 0 ? 0 : (raw_row >= (int)t.rows ? (int)t.rows - 1 : raw_row));
-    return (size_t)row * t.cols + col;
+    return row * t.cols + col;
+}
+
+// column / row of terrain_index as two numbers (pass B brackets a stretch of a ray with them)
+__device__ __forceinline__ void aw_col_row(const AwacsTerrain &t, float x, float y, uint32_t &col, uint32_t &row)
+{
+    const int raw_col = (int)roundf(__fdiv_rn(x, t.x_scale)) + (int)(t.cols / 2u);
+    const int raw_row = (int)roundf(__fdiv_rn(y, t.y_scale)) + (int)(t.rows / 2u);
+    col = (uint32_t)(raw_col < 0 ? 0 : (raw_col >= (int)t.cols ? (int)t.cols - 1 : raw_col));
+    row = (uint32_t)(raw_row < 0 ? 0 : (raw_row >= (int)t.rows ? (int)t.rows - 1 : raw_row));
 }
 
 __device__ __forceinline__ float aw_elevation(const AwacsTerrain &t, float x, float y)
@@ -216,8 +239,15 @@ awacs_kernel(const AwacsArgs a)
 {
     __shared__ ZigHot hot;
     __shared__ uint16_t list_smem[AWACS_BLOCK / 32][AWACS_STRIDE];
+    __shared__ __align__(128) float tile_smem[AWACS_BLOCK / 32][2][AWACS_STREAM_COLS][AWACS_TILE_TARGETS];
+    __shared__ __align__(8) uint64_t tile_bar[AWACS_BLOCK / 32][2];
 
     stage_zig_hot(hot, false);
+    if ((threadIdx.x & 31u) == 0u) {
+        tma::barrier_init(&tile_bar[threadIdx.x >> 5][0], 1u);
+        tma::barrier_init(&tile_bar[threadIdx.x >> 5][1], 1u);
+        tma::barrier_init_fence();
+    }
     __syncthreads();
 
     constexpr unsigned FULL = 0xffffffffu;
@@ -228,6 +258,7 @@ awacs_kernel(const AwacsArgs a)
         return;
     }
     uint16_t *const list = list_smem[warp];
+    uint32_t tile_phase = 0u;                           // bit b = parity of the next completion of tile_bar[warp][b]
     AwacsState S(a.state + trial * AWACS_STATE_BYTES);
     const AwacsTerrain ter = a.ter;
     const double PI = 3.14159265358979323846;
@@ -410,49 +441,93 @@ awacs_kernel(const AwacsArgs a)
             sw.lo = min_elev;
             sw.hi = max_elev;
 
-            // ---- pass A: dead reckoning + the cheap tests, 32 targets at a time; survivors listed in target order
+            // ---- pass A: dead reckoning + the cheap tests, 32 targets at a time; survivors listed in target order.
+            // The six state columns it reads arrive through shared memory: lane 0 asks the TMA engine for tile t + 2
+            // (six 512-byte runs, one mbarrier) as soon as the warp is done with tile t, so the L2 / HBM latency of the
+            // state block is hidden behind two tiles of geometry and costs no registers.  What this pass writes back
+            // (position and time of the moving targets, verdicts) goes to the state block with ordinary stores; the
+            // proxy fence below orders last tick's stores before this tick's bulk reads.
             uint32_t n_surv = 0u;
-            for (unsigned base = 0u; base < (unsigned)AWACS_TARGETS; base += 32u) {
-                const unsigned i = base + lane;
-                bool survivor = false;
-                if (i < (unsigned)AWACS_TARGETS) {
-                    float tx = S.x[i], ty = S.y[i], ta = S.alt[i];
-                    const float vel = S.vel[i];
-                    if (vel > 0.0f) {                   // target_position_update, :507-545
-                        const float dir = S.dir[i];
-                        const double dt = __dsub_rn(now, (double)S.time_s[i]);
-                        const double run = __dmul_rn(dt, (double)vel);
-                        float x = __fadd_rn(tx, (float)__dmul_rn(run, (double)aw_cosf(dir)));
-                        if (x > ter.x_max) x = __fadd_rn(ter.x_min, __fsub_rn(x, ter.x_max));
-                        else if (x < ter.x_min) x = __fsub_rn(ter.x_max, __fsub_rn(ter.x_min, x));
-                        float y = __fadd_rn(ty, (float)__dmul_rn(run, (double)aw_sinf(dir)));
-                        if (y > ter.y_max) y = __fadd_rn(ter.y_min, __fsub_rn(y, ter.y_max));
-                        else if (y < ter.y_min) y = __fsub_rn(ter.y_max, __fsub_rn(ter.y_min, y));
-                        ta = __fadd_rn(aw_elevation(ter, x, y), 2.0f);
-                        tx = x;
-                        ty = y;
-                        S.time_s[i] = (float)now;
-                        S.x[i] = tx;
-                        S.y[i] = ty;
-                        S.alt[i] = ta;
-                    }
-                    const uint32_t verdict = aw_cheap_tests(host, sw, tx, ty, ta);
-                    if (verdict == 16u) {
-                        survivor = true;
-                    }
-                    else if (verdict != 0u) {
-                        S.flags[i] = (S.flags[i] & ~AW_F_TDS) | (verdict << AW_F_TDS_SHIFT);
+            __syncwarp();
+            if (lane == 0u) {
+                tma::fence_global_to_async();
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    tma::barrier_expect(&tile_bar[warp][t], (uint32_t)(AWACS_STREAM_COLS * AWACS_TILE_TARGETS * sizeof(float)));
+#pragma unroll
+                    for (int c = 0; c < AWACS_STREAM_COLS; c++) {
+                        tma::load(tile_smem[warp][t][c], S.x + c * AWACS_STRIDE + t * AWACS_TILE_TARGETS,
+                                  (uint32_t)(AWACS_TILE_TARGETS * sizeof(float)), &tile_bar[warp][t]);
                     }
                 }
-                const unsigned m = __ballot_sync(FULL, survivor);
-                if (survivor) {
-                    list[n_surv + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+            }
+            for (int t = 0; t < AWACS_TILES; t++) {
+                const int buf = t & 1;
+                tma::barrier_wait(&tile_bar[warp][buf], (tile_phase >> buf) & 1u);
+                tile_phase ^= 1u << buf;
+                const float (*col)[AWACS_TILE_TARGETS] = tile_smem[warp][buf];
+                for (unsigned sub = 0u; sub < (unsigned)AWACS_TILE_TARGETS; sub += 32u) {
+                    const unsigned j = sub + lane;
+                    const unsigned i = (unsigned)t * AWACS_TILE_TARGETS + j;
+                    bool survivor = false;
+                    if (i < (unsigned)AWACS_TARGETS) {
+                        float tx = col[0][j], ty = col[1][j], ta = col[2][j];
+                        const float vel = col[4][j];
+                        if (vel > 0.0f) {               // target_position_update, :507-545
+                            const float dir = col[3][j];
+                            const double dt = __dsub_rn(now, (double)col[5][j]);
+                            const double run = __dmul_rn(dt, (double)vel);
+                            float x = __fadd_rn(tx, (float)__dmul_rn(run, (double)aw_cosf(dir)));
+                            if (x > ter.x_max) x = __fadd_rn(ter.x_min, __fsub_rn(x, ter.x_max));
+                            else if (x < ter.x_min) x = __fsub_rn(ter.x_max, __fsub_rn(ter.x_min, x));
+                            float y = __fadd_rn(ty, (float)__dmul_rn(run, (double)aw_sinf(dir)));
+                            if (y > ter.y_max) y = __fadd_rn(ter.y_min, __fsub_rn(y, ter.y_max));
+                            else if (y < ter.y_min) y = __fsub_rn(ter.y_max, __fsub_rn(ter.y_min, y));
+                            ta = __fadd_rn(aw_elevation(ter, x, y), 2.0f);
+                            tx = x;
+                            ty = y;
+                            S.time_s[i] = (float)now;
+                            S.x[i] = tx;
+                            S.y[i] = ty;
+                            S.alt[i] = ta;
+                        }
+                        const uint32_t verdict = aw_cheap_tests(host, sw, tx, ty, ta);
+                        if (verdict == 16u) {
+                            survivor = true;
+                        }
+                        else if (verdict != 0u) {
+                            S.flags[i] = (S.flags[i] & ~AW_F_TDS) | (verdict << AW_F_TDS_SHIFT);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(FULL, survivor);
+                    if (survivor) {
+                        list[n_surv + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    }
+                    n_surv += __popc(m);
                 }
-                n_surv += __popc(m);
+                __syncwarp();                           // every lane is done reading this buffer
+                if (lane == 0u && t + 2 < AWACS_TILES) {
+                    tma::barrier_expect(&tile_bar[warp][buf], (uint32_t)(AWACS_STREAM_COLS * AWACS_TILE_TARGETS * sizeof(float)));
+#pragma unroll
+                    for (int c = 0; c < AWACS_STREAM_COLS; c++) {
+                        tma::load(tile_smem[warp][buf][c], S.x + c * AWACS_STRIDE + (t + 2) * AWACS_TILE_TARGETS,
+                                  (uint32_t)(AWACS_TILE_TARGETS * sizeof(float)), &tile_bar[warp][buf]);
+                    }
+                }
             }
             __syncwarp();
 
-            // ---- pass B: target_is_terrain_shielded (:598-638), one line of sight marched by the whole warp
+            // ---- pass B: target_is_terrain_shielded (:598-638), one line of sight marched by the whole warp.
+            // The reference walks the ray in half-cell steps k = 1 .. steps-1 and returns at the first step whose ray
+            // altitude is below the cell under it, i.e. "shielded" = "some step is".  A ray from 9.4 km down to a target
+            // spends most of its length far above any ground, so the steps are taken in stretches of
+            // 32 x AWACS_CHUNK = 256: first every lane brackets ONE stretch - the lowest ray altitude of its steps
+            // against the highest cell they can be over - and only stretches that fail that test are marched.  The
+            // bracket is exact, not approximate: step k's altitude host.alt + dz * (k * inv) and its clamped x and y are
+            // each a chain of correctly rounded operations that are monotone in k, so over steps k0..k1 the altitude is
+            // never below min(alt(k0), alt(k1)) and column and row stay between those of k0 and k1; a stretch is at
+            // most 128 cells long, so it lies in at most 2 x 2 tiles of the 128 x 128 tile-maximum map (more: march it).
+            // If that minimum is not below those tiles' maximum, no step of the stretch can be below its cell.
             uint32_t n_cand = 0u;
             for (uint32_t s = 0u; s < n_surv; s++) {
                 const unsigned i = list[s];
@@ -464,38 +539,72 @@ awacs_kernel(const AwacsArgs a)
                 bool shielded = false;
                 if (steps >= 1) {
                     const float inv = __fdiv_rn(1.0f, (float)steps);
-                    // a round = 32 x AWACS_CHUNK consecutive steps; each lane takes AWACS_CHUNK CONSECUTIVE ones, so the
-                    // two or three half-cell steps that fall into one map cell cost one read, and a lane's successive
-                    // cells share 32-byte sectors in L1 instead of every step asking L2 for its own sector
-                    for (int first = 1; first < steps && !shielded; first += 32 * AWACS_CHUNK) {
-                        size_t cell[AWACS_CHUNK];
-                        float ray_alt[AWACS_CHUNK], ground[AWACS_CHUNK];
-                        bool live[AWACS_CHUNK];
-#pragma unroll
-                        for (int u = 0; u < AWACS_CHUNK; u++) {
-                            const int k = first + (int)lane * AWACS_CHUNK + u;
-                            live[u] = k < steps;
-                            const float f = __fmul_rn((float)k, inv);
-                            float cx = __fadd_rn(host.x, __fmul_rn(dx, f));
-                            float cy = __fadd_rn(host.y, __fmul_rn(dy, f));
-                            ray_alt[u] = __fadd_rn(host.alt, __fmul_rn(dz, f));
-                            cx = fmaxf(ter.x_min, fminf(cx, ter.x_max));
-                            cy = fmaxf(ter.y_min, fminf(cy, ter.y_max));
-                            cell[u] = aw_cell(ter, cx, cy);
+                    constexpr int STRETCH = 32 * AWACS_CHUNK;
+                    for (int sbase = 1; sbase < steps && !shielded; sbase += 32 * STRETCH) {
+                        bool touch = false;
+                        {
+                            const int k0 = sbase + (int)lane * STRETCH;
+                            if (k0 < steps) {
+                                const int k1 = (k0 + STRETCH - 1 < steps - 1) ? k0 + STRETCH - 1 : steps - 1;
+                                const float f0 = __fmul_rn((float)k0, inv), f1 = __fmul_rn((float)k1, inv);
+                                const float low = fminf(__fadd_rn(host.alt, __fmul_rn(dz, f0)), __fadd_rn(host.alt, __fmul_rn(dz, f1)));
+                                uint32_t c0, r0, c1, r1;
+                                aw_col_row(ter, fmaxf(ter.x_min, fminf(__fadd_rn(host.x, __fmul_rn(dx, f0)), ter.x_max)),
+                                           fmaxf(ter.y_min, fminf(__fadd_rn(host.y, __fmul_rn(dy, f0)), ter.y_max)), c0, r0);
+                                aw_col_row(ter, fmaxf(ter.x_min, fminf(__fadd_rn(host.x, __fmul_rn(dx, f1)), ter.x_max)),
+                                           fmaxf(ter.y_min, fminf(__fadd_rn(host.y, __fmul_rn(dy, f1)), ter.y_max)), c1, r1);
+                                const uint32_t tc0 = (c0 < c1 ? c0 : c1) >> AWACS_TILE_SHIFT, tc1 = (c0 < c1 ? c1 : c0) >> AWACS_TILE_SHIFT;
+                                const uint32_t tr0 = (r0 < r1 ? r0 : r1) >> AWACS_TILE_SHIFT, tr1 = (r0 < r1 ? r1 : r0) >> AWACS_TILE_SHIFT;
+                                if (tc1 - tc0 > 1u || tr1 - tr0 > 1u) {
+                                    touch = true;
+                                }
+                                else {
+                                    const float *tm = ter.tile_max;
+                                    const float top = fmaxf(fmaxf(__ldg(tm + (size_t)tr0 * ter.tcols + tc0), __ldg(tm + (size_t)tr0 * ter.tcols + tc1)),
+                                                            fmaxf(__ldg(tm + (size_t)tr1 * ter.tcols + tc0), __ldg(tm + (size_t)tr1 * ter.tcols + tc1)));
+                                    touch = low < top;
+                                }
+                            }
                         }
+#ifdef AWACS_MARCH_EVERYTHING                                  // A/B: the round-1 march, every stretch walked
+                        touch = sbase + (int)lane * STRETCH < steps;
+#endif
+                        unsigned todo = __ballot_sync(FULL, touch);
+                        // a stretch = 32 x AWACS_CHUNK consecutive steps; each lane takes AWACS_CHUNK CONSECUTIVE ones, so the
+                        // two or three half-cell steps that fall into one map cell cost one read, and a lane's successive
+                        // cells share 32-byte sectors in L1 instead of every step asking L2 for its own sector
+                        while (todo != 0u && !shielded) {
+                            const int first = sbase + (__ffs(todo) - 1) * STRETCH;
+                            todo &= todo - 1u;
+                            uint32_t cell[AWACS_CHUNK];
+                            float ray_alt[AWACS_CHUNK], ground[AWACS_CHUNK];
+                            bool live[AWACS_CHUNK];
 #pragma unroll
-                        for (int u = 0; u < AWACS_CHUNK; u++) {
-                            const bool fresh = live[u] && (u == 0 || cell[u] != cell[u - 1]);
-                            ground[u] = fresh ? __ldg(ter.map + cell[u]) : 0.0f;
-                            lookups += fresh ? 1u : 0u;
-                        }
-                        bool hit = false;
+                            for (int u = 0; u < AWACS_CHUNK; u++) {
+                                const int k = first + (int)lane * AWACS_CHUNK + u;
+                                live[u] = k < steps;
+                                const float f = __fmul_rn((float)k, inv);
+                                float cx = __fadd_rn(host.x, __fmul_rn(dx, f));
+                                float cy = __fadd_rn(host.y, __fmul_rn(dy, f));
+                                ray_alt[u] = __fadd_rn(host.alt, __fmul_rn(dz, f));
+                                cx = fmaxf(ter.x_min, fminf(cx, ter.x_max));
+                                cy = fmaxf(ter.y_min, fminf(cy, ter.y_max));
+                                cell[u] = aw_cell(ter, cx, cy);
+                            }
 #pragma unroll
-                        for (int u = 0; u < AWACS_CHUNK; u++) {
-                            if (u > 0 && cell[u] == cell[u - 1]) ground[u] = ground[u - 1];
-                            hit |= live[u] && (ray_alt[u] < ground[u]);
+                            for (int u = 0; u < AWACS_CHUNK; u++) {
+                                const bool fresh = live[u] && (u == 0 || cell[u] != cell[u - 1]);
+                                ground[u] = fresh ? __ldg(ter.map + cell[u]) : 0.0f;
+                                lookups += fresh ? 1u : 0u;
+                            }
+                            bool hit = false;
+#pragma unroll
+                            for (int u = 0; u < AWACS_CHUNK; u++) {
+                                if (u > 0 && cell[u] == cell[u - 1]) ground[u] = ground[u - 1];
+                                hit |= live[u] && (ray_alt[u] < ground[u]);
+                            }
+                            shielded = __any_sync(FULL, hit);
                         }
-                        shielded = __any_sync(FULL, hit);
                     }
                 }
                 if (shielded) {
@@ -601,5 +710,27 @@ awacs_kernel(const AwacsArgs a)
         }
     }
 }
+
+#ifndef AWACS_HOST_EMULATION
+// The tile-maximum map of a terrain: one CTA per 128 x 128 tile, rows read as coalesced 512-byte segments.
+__global__ void __launch_bounds__(256)
+aw_tile_max_kernel(const float *map, uint32_t cols, uint32_t rows, float *tile_max, uint32_t tcols)
+{
+    __shared__ float part[8];
+    const uint32_t c0 = blockIdx.x << AWACS_TILE_SHIFT, r0 = blockIdx.y << AWACS_TILE_SHIFT;
+    float top = -3.402823466e+38f;                      // a caller's map may hold negative elevations
+    for (uint32_t e = threadIdx.x; e < AWACS_TILE * AWACS_TILE; e += blockDim.x) {
+        const uint32_t r = r0 + (e >> AWACS_TILE_SHIFT), c = c0 + (e & (AWACS_TILE - 1u));
+        if (r < rows && c < cols) top = fmaxf(top, __ldg(map + (size_t)r * cols + c));
+    }
+    for (int o = 16; o > 0; o >>= 1) top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+    if ((threadIdx.x & 31u) == 0u) part[threadIdx.x >> 5] = top;
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        for (int w = 1; w < 8; w++) top = fmaxf(top, part[w]);
+        tile_max[(size_t)blockIdx.y * tcols + blockIdx.x] = top;
+    }
+}
+#endif
 
 }  // namespace cimba_b200

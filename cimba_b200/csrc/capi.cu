@@ -64,7 +64,16 @@ int cuda_fail(cudaError_t e, const char *where)
         if (e_ != cudaSuccess) return cuda_fail(e_, #expr);        \
     } while (0)
 
-constexpr uint32_t QUEUE_SPILL_CAP = 512u;     // doubles per trial behind the 32-entry window
+constexpr uint32_t QUEUE_SPILL_CAP = 512u;     // default: doubles per trial behind the 32-entry window
+
+// job.queue_spill_cap: 0 = default, else a power of two up to 2^26; 0xffffffff = invalid
+uint32_t spill_cap_of(const cimba_b200_device_job *job)
+{
+    const uint32_t c = job->queue_spill_cap;
+    if (c == 0u) return QUEUE_SPILL_CAP;
+    if ((c & (c - 1u)) != 0u || c > (1u << 26)) return 0xffffffffu;
+    return c;
+}
 
 bool is_queue_model(int m)
 {
@@ -183,6 +192,7 @@ std::mutex g_terrain_mu;
 AwacsTerrain g_terrain[MAX_TERRAIN_DEVICES];
 bool g_terrain_set[MAX_TERRAIN_DEVICES];
 float *g_terrain_owned[MAX_TERRAIN_DEVICES];     // device copies made by cimba_b200_awacs_upload_terrain
+float *g_terrain_tiles[MAX_TERRAIN_DEVICES];     // tile-maximum maps (aw_tile_max_kernel), always library-owned
 
 // racetrack_initialize with run_trial's arguments (tutorial/tut_5_1.c:724-782, :1177-1188): constants of the
 // model, evaluated once on the host with the host's libm, exactly as the reference evaluates them
@@ -258,7 +268,8 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
         return 0u;
     }
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
-        return job->num_trials * (uint64_t)QUEUE_SPILL_CAP * sizeof(double);
+        const uint32_t cap = spill_cap_of(job);
+        return job->num_trials * (uint64_t)(cap == 0xffffffffu ? QUEUE_SPILL_CAP : cap) * sizeof(double);
     }
     if (job->model == CIMBA_B200_MODEL_HARBOR) {
         return job->num_trials * (uint64_t)sizeof(HarborState);
@@ -290,6 +301,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         return fail(CIMBA_B200_EINVAL, "trace_cap > 0 needs trace_key and trace_time");
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
     cudaStream_t st = (cudaStream_t)stream;
+    if (spill_cap_of(job) == 0xffffffffu)
+        return fail(CIMBA_B200_EINVAL, "queue_spill_cap must be 0 (default) or a power of two <= 2^26");
 
     if (is_queue_model(job->model)) {
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -310,10 +323,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         qa.max_queue = job->max_queue;
         qa.counters = job->counters;
         qa.spill = (double *)job->workspace;
-        qa.spill_cap = QUEUE_SPILL_CAP;
+        qa.spill_cap = spill_cap_of(job);
         qa.trace_cap = job->trace_cap;
         qa.trace_key = job->trace_key;
         qa.trace_time = job->trace_time;
+        qa.diag = (unsigned long long *)job->diag;
         const uint64_t threads = job->num_trials * (uint64_t)mapping;
         const uint64_t blocks = (threads + QUEUE_BLOCK - 1) / QUEUE_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
@@ -366,10 +380,11 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         pa.status = job->status;
         pa.max_queue = job->max_queue;
         pa.spill = (double *)job->workspace;
-        pa.spill_cap = QUEUE_SPILL_CAP;
+        pa.spill_cap = spill_cap_of(job);
         pa.trace_cap = job->trace_cap;
         pa.trace_key = job->trace_key;
         pa.trace_time = job->trace_time;
+        pa.diag = (unsigned long long *)job->diag;
         const uint64_t blocks = (job->num_trials + POOL_BLOCK - 1) / POOL_BLOCK;
         if (blocks > 0x7fffffffull) return fail(CIMBA_B200_EINVAL, "too many trials for one launch");
         if (job->variant == 1) {                        // the readable formulation, pool_model.cuh
@@ -625,25 +640,55 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
     return fail(CIMBA_B200_EINVAL, "unknown model");
 }
 
+namespace {
+bool terrain_descriptor_ok(const cimba_b200_awacs_terrain *t)
+{
+    return t != nullptr && t->map != nullptr && t->cols >= 2u && t->rows >= 2u && t->x_scale > 0.0f && t->y_scale > 0.0f &&
+           t->x_min < t->x_max && t->y_min < t->y_max && (uint64_t)t->cols * (uint64_t)t->rows <= 0xffffffffull;
+}
+
+// Registers `map` (a device pointer) for device `dev` and builds its tile-maximum map.  `owned` = the library made
+// this copy (upload path) and frees it when it is replaced.  Caller holds no lock.
+int register_terrain(int dev, const cimba_b200_awacs_terrain *t, const float *map, float *owned)
+{
+    const uint32_t tcols = (t->cols + AWACS_TILE - 1u) >> AWACS_TILE_SHIFT, trows = (t->rows + AWACS_TILE - 1u) >> AWACS_TILE_SHIFT;
+    float *tiles = nullptr;
+    CUDA_TRY(cudaMalloc(&tiles, (size_t)tcols * trows * sizeof(float)));
+    aw_tile_max_kernel<<<dim3(tcols, trows), 256>>>(map, t->cols, t->rows, tiles, tcols);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(tiles);
+        return cuda_fail(e, "aw_tile_max_kernel");
+    }
+    std::lock_guard<std::mutex> hold(g_terrain_mu);
+    // no job may still be reading the previous registration (the caller's contract, as for any model input)
+    if (g_terrain_tiles[dev] != nullptr) cudaFree(g_terrain_tiles[dev]);
+    if (g_terrain_owned[dev] != nullptr && g_terrain_owned[dev] != owned) cudaFree(g_terrain_owned[dev]);
+    g_terrain_tiles[dev] = tiles;
+    g_terrain_owned[dev] = owned;
+    g_terrain[dev] = AwacsTerrain{map, t->cols, t->rows, t->x_scale, t->y_scale, t->x_min, t->x_max, t->y_min, t->y_max,
+                                  tiles, tcols, trows};
+    g_terrain_set[dev] = true;
+    return CIMBA_B200_OK;
+}
+}  // namespace
+
 int cimba_b200_awacs_set_terrain(const cimba_b200_awacs_terrain *t)
 {
-    if (t == nullptr || t->map == nullptr || t->cols < 2u || t->rows < 2u || !(t->x_scale > 0.0f) || !(t->y_scale > 0.0f) ||
-        !(t->x_min < t->x_max) || !(t->y_min < t->y_max))
-        return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
+    if (!terrain_descriptor_ok(t)) return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_TERRAIN_DEVICES) return fail(CIMBA_B200_EINVAL, "device index out of range");
-    std::lock_guard<std::mutex> hold(g_terrain_mu);
-    g_terrain[dev] = AwacsTerrain{t->map, t->cols, t->rows, t->x_scale, t->y_scale, t->x_min, t->x_max, t->y_min, t->y_max};
-    g_terrain_set[dev] = true;
-    return CIMBA_B200_OK;
+    // a caller-owned map replaces (and frees) whatever copy an earlier upload left on this device
+    return register_terrain(dev, t, t->map, nullptr);
 }
 
 int cimba_b200_awacs_upload_terrain(const cimba_b200_awacs_terrain *t)
 {
-    if (t == nullptr || t->map == nullptr || t->cols < 2u || t->rows < 2u)
-        return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
+    if (!terrain_descriptor_ok(t)) return fail(CIMBA_B200_EINVAL, "bad terrain descriptor (tutorial/tut_5_1.c:96-108)");
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -656,17 +701,9 @@ int cimba_b200_awacs_upload_terrain(const cimba_b200_awacs_terrain *t)
         cudaFree(copy);
         return cuda_fail(e, "terrain upload");
     }
-    cimba_b200_awacs_terrain on_device = *t;
-    on_device.map = copy;
-    const int rc = cimba_b200_awacs_set_terrain(&on_device);
-    std::lock_guard<std::mutex> hold(g_terrain_mu);
-    if (rc != CIMBA_B200_OK) {
-        cudaFree(copy);
-        return rc;
-    }
-    if (g_terrain_owned[dev] != nullptr) cudaFree(g_terrain_owned[dev]);    // no job may still be reading the old map
-    g_terrain_owned[dev] = copy;
-    return CIMBA_B200_OK;
+    const int rc = register_terrain(dev, t, copy, copy);
+    if (rc != CIMBA_B200_OK) cudaFree(copy);
+    return rc;
 }
 
 int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,
@@ -904,6 +941,7 @@ int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const 
     job.servers = d->servers;
     job.mapping = d->mapping;
     job.variant = d->variant;
+    job.queue_spill_cap = d->queue_spill_cap;
     job.master_seed = d->master_seed;
     job.first_trial = d->first_trial;
     job.num_trials = n;
@@ -993,9 +1031,13 @@ void cimba_b200_release_cache(void)
         std::lock_guard<std::mutex> hold(g_terrain_mu);
         for (int g = 0; g < count && g < MAX_TERRAIN_DEVICES; g++) {
             if (g_terrain_owned[g] != nullptr) {
+                // the registered map IS the library's copy (register_terrain frees a stale copy when a caller-owned
+                // map replaces it), so the registration goes with it; a caller-owned registration stays valid
                 cudaSetDevice(g);
                 cudaFree(g_terrain_owned[g]);
                 g_terrain_owned[g] = nullptr;
+                if (g_terrain_tiles[g] != nullptr) cudaFree(g_terrain_tiles[g]);
+                g_terrain_tiles[g] = nullptr;
                 g_terrain_set[g] = false;
             }
         }

@@ -10,10 +10,13 @@
 //     Marsaglia-Tsang squeeze, so a last-place difference between CUDA's and glibc's log
 //     matters only if the two sides of that comparison agree to ~1e-16:
 //     std_gamma, gamma (shape >= 1), beta, PERT, chisquared (k >= 2), F, t;
-//   * within the accuracy of CUDA's log / exp / pow (<= 2 ulp) of the reference's glibc
-//     result, because the transcendental IS the variate: lognormal, logistic, weibull,
-//     pareto, gamma with shape < 1 (and what builds on it); geometric / negative_binomial
-//     apply ceil() to such a value and can differ by one on a measure-zero set.
+//   * bit-exact because the only libm call is exp(), restated from glibc (glibc_exp.cuh): lognormal
+//     (the ziggurat wedge tests in rng.cuh use the same routine);
+//   * within the accuracy of CUDA's log / pow (<= 2 ulp) of the reference's glibc result,
+//     because the transcendental IS the variate: logistic, weibull, pareto, gamma with
+//     shape < 1 (and what builds on it); geometric / negative_binomial apply ceil() to such a
+//     value and can differ by one on a measure-zero set.  glibc's log and pow tables were
+//     chosen by search and cannot be recomputed from first principles, so they stay CUDA's.
 // Compiled with -fmad=false: the expressions keep the reference's operation order.
 #pragma once
 
@@ -56,7 +59,7 @@ __device__ inline double rnd_triangular(Sfc64 &r, double min, double mode, doubl
 // include/cmb_random.h:249-257
 __device__ inline double rnd_lognormal(Sfc64 &r, const ZigHot &hot, double m, double s)
 {
-    return exp((m + s * gp_std_normal(r, hot)));
+    return glibc_exp((m + s * gp_std_normal(r, hot)));      // the variate IS an exp: glibc's bits (glibc_exp.cuh)
 }
 
 // :267-273
@@ -129,7 +132,10 @@ __device__ __noinline__ double rnd_std_gamma(Sfc64 &r, const ZigHot &hot, double
     }
 }
 
-// include/cmb_random.h:451-463; for shape < 1 the reference build draws std_gamma first
+// include/cmb_random.h:451-463.  For shape < 1 the reference writes
+// cmb_random_std_gamma(shape + 1) * pow(cmb_random(), 1 / shape): C leaves the evaluation order of the two operands
+// unspecified; gcc 13 (-O2/-O3, x86-64) - the build the oracle and the golden vectors come from - draws std_gamma
+// first, and so does this.  A different compiler could legitimately produce the other stream.
 __device__ inline double rnd_gamma(Sfc64 &r, const ZigHot &hot, double shape, double scale)
 {
     if (shape >= 1.0) {

@@ -1,11 +1,13 @@
-// glibc_exp.cuh - glibc's double-precision exp() restated (not wired into any kernel yet).
+// glibc_exp.cuh - glibc's double-precision exp() restated; used by the ziggurat wedge tests (rng.cuh) and by the
+// exp-valued distributions (distributions.cuh).
+// Provenance: glibc 2.39 sysdeps/ieee754/dbl-64/e_exp.c (LGPL-2.1-or-later), adopted from ARM optimized-routines
+// (MIT OR Apache-2.0 WITH LLVM-exception); restated from the published algorithm, table recomputed, no source text copied.
 //
 // The oracle is the reference linked against glibc 2.39.  Where a model's outcome depends on a libm result the
 // device must produce glibc's bits, not merely a correctly rounded value (awacs_math.cuh does this for atan2f /
 // sinf / cosf).  exp() matters in three places: cmb_random_lognormal returns one (src/cmb_random.c via
 // include/cmb_random.h:249-257), and both ziggurat samplers compare against one in their wedge tests
-// (src/cmb_random.c:255, :345) - today those use CUDA's exp(), whose last-place differences from glibc's have not
-// been seen to flip a comparison but could.
+// (src/cmb_random.c:255, :345) - with CUDA's exp() a last-place difference from glibc's could flip such a comparison.
 //
 // Algorithm: glibc >= 2.28 sysdeps/ieee754/dbl-64/e_exp.c (the ARM optimized-routines exp): x = k ln2/128 + r,
 // exp(x) = 2^(k/128) (1 + tail + p(r)) with a 128-entry table of 2^(i/128) split into a double and its relative

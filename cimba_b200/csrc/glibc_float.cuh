@@ -1,5 +1,7 @@
-// glibc_float.cuh - glibc's expf() and powf() restated (not wired into any kernel yet; see awacs_math.cuh for the
-// routines that are).
+// glibc_float.cuh - glibc's expf() and powf() restated; awacs_math.cuh uses them for the AWACS detection probability.
+// Provenance: the algorithms are those of glibc 2.39 sysdeps/ieee754/flt-32/e_expf.c and e_powf.c (LGPL-2.1-or-later),
+// which adopted them from ARM optimized-routines (MIT OR Apache-2.0 WITH LLVM-exception); restated here from the published
+// description, tables recomputed (see below), no source text copied.
 //
 // The AWACS detection probability (tutorial/tut_5_1.c:643-686) calls powf(ref_range / r, 4.0f) and expf(...) once per
 // attempt; awacs_math.cuh evaluates them in double and rounds once, which differs from glibc 2.39 on 0.065 % of

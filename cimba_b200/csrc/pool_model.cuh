@@ -55,6 +55,7 @@ struct PoolArgs {
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
+    unsigned long long *diag;          // optional: [0] += event-loop iterations of each warp, [1] += warps (bench.py)
 };
 
 enum : uint32_t { TAG_GENERATOR = 0u, TAG_CUSTOMER = 1u };

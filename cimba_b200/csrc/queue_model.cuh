@@ -41,6 +41,7 @@ struct QueueArgs {
     uint64_t  trace_cap;
     uint64_t *trace_key;
     double   *trace_time;
+    unsigned long long *diag;          // optional: [0] += event-loop iterations of each warp, [1] += warps (bench.py)
 };
 
 enum { PROC_ARRIVAL = 0, PROC_SERVICE = 1 };

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "glibc_exp.cuh"
 #include "zig_tables.cuh"
 
 namespace cimba_b200 {
@@ -50,6 +51,13 @@ __device__ __forceinline__ void stage_zig_hot(ZigHot &hot, bool want_normal)
         hot.exp_x[i] = zig::zig_exp_x[i];
         hot.nor_x[i] = want_normal ? zig::zig_nor_x[i] : 0.0;
     }
+}
+
+// exp() of the ziggurat wedge tests (src/cmb_random.c:255, :345), out of line: reached by 0.04 % of the draws, and
+// an inlined copy at each of the four call sites would only cost instruction-cache room
+__device__ __noinline__ double zig_exp(double x)
+{
+    return glibc_exp(x);
 }
 
 constexpr double TWO_POW_64 = 18446744073709551616.0;
@@ -176,7 +184,7 @@ struct Sfc64 {
                     const double y = __dadd_rn(__dmul_rn(y0, TWO_POW_64),
                                                __dmul_rn(__dsub_rn(zig::zig_exp_y[j], y0),
                                                          __ull2double_rn(uy)));
-                    if (y <= exp(-x)) {
+                    if (y <= zig_exp(-x)) {          // src/cmb_random.c:255: glibc's exp, bit for bit (glibc_exp.cuh)
                         return __dadd_rn(x, shift);
                     }
                     uy = next();
@@ -247,7 +255,7 @@ struct Sfc64 {
 
     static __device__ __forceinline__ double nor_pdf_scaled(double x)
     {                                                   // sc_nor_pdf, :340-343
-        return exp(__dmul_rn(__dmul_rn(-0.5, x), x));
+        return zig_exp(__dmul_rn(__dmul_rn(-0.5, x), x));    // glibc's exp, bit for bit (glibc_exp.cuh)
     }
 
     // cmi_random_nor_not_hot, src/cmb_random.c:352-451

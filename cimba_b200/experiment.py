@@ -36,7 +36,7 @@ def fmix64(seed: int, nonce: int) -> int:
 def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODEL_MM1,
                          num_objects: int, master_seed: int, first_trial: int = 0,
                          servers: int = 1, mapping: int = 0, device: int = -1, variant: int = 0,
-                         all_gpus: bool = False, max_gpus: int = 0) -> None:
+                         all_gpus: bool = False, max_gpus: int = 0, queue_spill_cap: int = 0) -> None:
     """Run every trial of a host-resident experiment array on the GPU, in place.
 
     ``experiment_array`` is a 1-D numpy structured array (any dtype that has
@@ -73,7 +73,7 @@ def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODE
     if "arr_mean" not in f or "srv_mean" not in f:
         raise TypeError("trial struct needs arr_mean and srv_mean double fields")
     desc = _lib.Experiment(
-        model=model, servers=servers, mapping=mapping, device=device, variant=variant, reserved=0,
+        model=model, servers=servers, mapping=mapping, device=device, variant=variant, queue_spill_cap=queue_spill_cap,
         master_seed=master_seed & (2**64 - 1), first_trial=first_trial, num_objects=num_objects,
         off_arr_mean=off("arr_mean", "<f8"), off_srv_mean=off("srv_mean", "<f8"),
         off_obj_cnt=off("obj_cnt", "<u8"), off_sum_wait=off("sum_wait", "<f8"),

@@ -166,7 +166,24 @@ typedef struct cimba_b200_device_job {
     uint64_t  trace_cap;
     uint64_t *trace_key;        /* cmb_event_current() after each pop */
     double   *trace_time;       /* cmb_time() after each pop */
+    /* capacity of the per-trial HBM ring behind the 32-entry on-chip window of the cmb_objectqueue (M/M/1, G/G/1)
+     * and of the resource pool's wait list (M/M/c): a power of two, 0 = the default (512).  The reference's queue
+     * is CMB_UNLIMITED (benchmark/MM1_multi.c:103): a trial that outgrows window + ring is not lost - it is re-run
+     * on the growable general engine by a repair pass inside the same launch - but a ring sized for
+     * the traffic (rho -> 1) keeps such trials on the fast kernel.  cimba_b200_workspace_bytes() honours it. */
+    uint32_t  queue_spill_cap;
+    uint32_t  reserved0;        /* 0 */
+    /* optional DEVICE pointer to 4 uint64 the simulation kernel ADDS to (zero them first): [0] event-loop
+     * iterations summed over warps, [1] warps that ran, [2] trials the repair pass re-ran, [3] reserved.
+     * bench.py turns [0] into issued warp-instructions with the loop's calibrated instruction count. */
+    uint64_t *diag;
+    /* experiment-wide model parameters for models built with the device authoring API (include/cmb_device.cuh):
+     * HOST pointer to num_params <= CIMBA_B200_MAX_MODEL_PARAMS doubles, copied at launch; NULL / 0 otherwise */
+    const double *params;
+    uint32_t  num_params;
+    uint32_t  reserved1;        /* 0 */
 } cimba_b200_device_job;
+#define CIMBA_B200_MAX_MODEL_PARAMS 16
 
 /* MODEL_AWACS: the terrain every trial reads (struct terrain, tutorial/tut_5_1.c:96-108, as terrain_init :197-294 fills
  * it).  map is a DEVICE pointer to rows x cols float32 elevations, row-major, and must stay valid while jobs run.
@@ -226,7 +243,7 @@ typedef struct cimba_b200_experiment {
     int32_t  mapping;           /* 0 = default */
     int32_t  device;            /* CUDA device ordinal, -1 = current */
     int32_t  variant;           /* kernel variant, as cimba_b200_device_job.variant (0 = default) */
-    int32_t  reserved;          /* 0 */
+    uint32_t queue_spill_cap;   /* as cimba_b200_device_job.queue_spill_cap (0 = default) */
     uint64_t master_seed;
     uint64_t first_trial;
     uint64_t num_objects;

@@ -43,6 +43,8 @@ struct ref_trial {
     double srv_mean;
     int32_t model;
     int32_t servers;
+    int32_t stock;              /* 1 = timed as the reference's benchmark runs it: no per-event bookkeeping (bench.py) */
+    int32_t pad_;
     /* out */
     uint64_t events;
     uint64_t objects;
@@ -117,6 +119,21 @@ static void *q_server_body(struct cmb_process *me, void *vw)
         w->trl->objects += 1u;
         cmi_mempool_free(&stamp_pool, obj);
     }
+}
+
+/* The arrival process exactly as benchmark/MM1_multi.c:52-68 has it - no queue-length bookkeeping per put.
+ * bench.py times THIS body (stock = 1); the instrumented one above serves the parity tests. */
+static void *q_source_body_stock(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct q_world *w = vw;
+    for (uint64_t i = 0u; i < w->trl->num_objects; i++) {
+        cmb_process_hold(draw_interarrival(w->trl));
+        double *stamp = cmi_mempool_alloc(&stamp_pool);
+        *stamp = cmb_time();
+        cmb_objectqueue_put(w->queue, stamp);
+    }
+    return NULL;
 }
 
 /* ----------------------------------------------------------------- M/M/c */
@@ -1584,8 +1601,26 @@ static void run_resource_trial(struct ref_trial *t)
 
 /* -------------------------------------------------------------- dispatcher */
 
+static void stock_noop_event(void *subject, void *object)
+{
+    cmb_unused(subject);
+    cmb_unused(object);
+}
+
 static void pump_events(struct ref_trial *t)
 {
+    if (t->stock) {
+        /* the benchmark's own dispatcher call, benchmark/MM1_multi.c:113.  The pop count comes for free
+         * afterwards: event handles are the event list's running enqueue counter (src/cmi_hashheap.c:449-453),
+         * the list ran dry, and models 0-2 never cancel an event, so a probe event's handle minus one is the
+         * number of events executed. */
+        cmb_event_queue_execute();
+        const uint64_t probe = cmb_event_schedule(stock_noop_event, NULL, NULL, cmb_time(), 0);
+        (void)cmb_event_cancel(probe);
+        t->events = probe - 1u;
+        t->t_end = cmb_time();
+        return;
+    }
     uint64_t n = 0u;
     for (;;) {
         const uint64_t depth = cmb_event_queue_count();
@@ -1616,7 +1651,7 @@ static void run_queue_trial(struct ref_trial *t)
         cmb_objectqueue_recording_start(w.queue);
     }
     w.source = cmb_process_create();
-    cmb_process_initialize(w.source, "Arrival", q_source_body, &w, 0);
+    cmb_process_initialize(w.source, "Arrival", t->stock ? q_source_body_stock : q_source_body, &w, 0);
     cmb_process_start(w.source);
     w.server = cmb_process_create();
     cmb_process_initialize(w.server, "Service", q_server_body, &w, 0);
@@ -1766,6 +1801,54 @@ int ref_run_trials(int model, int servers, uint64_t master_seed,
         out[i].max_fel = exp[i].max_fel;
         out[i].max_queue = exp[i].max_queue;
         memcpy(out[i].counter, exp[i].counter, sizeof(out[i].counter));
+    }
+    free(exp);
+    return 0;
+}
+
+/*
+ * The timed leg of bench.py: trials [first, first + count) of model 0 (M/M/1), 1 (G/G/1) or 2 (M/M/c) run the way
+ * the reference's benchmarks run them - stock process bodies, cmb_event_queue_execute() - through
+ * cimba_run_experiment() (threads == 0: one pthread per logical core, src/cimba.c:171) or serially on the calling
+ * thread (threads == 1: the benchmark/MM1_single.c row).  Results as ref_run_trials; max_fel / max_queue stay 0.
+ */
+int ref_bench_trials(int model, int servers, uint64_t master_seed,
+                     uint64_t first, uint64_t count, uint64_t num_objects,
+                     double arr_mean, double srv_mean, int threads,
+                     struct ref_result *out)
+{
+    if (model < 0 || model > 2) {
+        return -2;
+    }
+    struct ref_trial *exp = calloc(count, sizeof(*exp));
+    if (exp == NULL) {
+        return -1;
+    }
+    for (uint64_t i = 0u; i < count; i++) {
+        exp[i].seed = cmb_random_fmix64(master_seed, first + i);
+        exp[i].num_objects = num_objects;
+        exp[i].arr_mean = arr_mean;
+        exp[i].srv_mean = srv_mean;
+        exp[i].model = model;
+        exp[i].servers = servers;
+        exp[i].stock = 1;
+    }
+    if (threads == 1) {
+        for (uint64_t i = 0u; i < count; i++) {
+            run_trial(&exp[i]);
+        }
+    }
+    else {
+        cimba_run_experiment(exp, count, sizeof(*exp), run_trial);
+    }
+    for (uint64_t i = 0u; i < count; i++) {
+        out[i].events = exp[i].events;
+        out[i].objects = exp[i].objects;
+        out[i].t_end = exp[i].t_end;
+        out[i].sum_wait = exp[i].sum_wait;
+        out[i].max_fel = 0u;
+        out[i].max_queue = 0u;
+        memset(out[i].counter, 0, sizeof(out[i].counter));
     }
     free(exp);
     return 0;

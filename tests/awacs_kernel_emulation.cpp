@@ -206,6 +206,28 @@ static inline bool goes_before(unsigned long long at, uint32_t ak, unsigned long
 }
 }  // namespace cimba_b200
 
+// tma_bulk.cuh on the host.  An mbarrier is its 8 bytes: low word = phases completed, high word = bytes still expected
+// in the current phase.  A copy happens when it is issued and counts its bytes down; the phase completes when the
+// expected bytes have arrived; a waiter yields to the other lanes until the phase of the parity it names has completed
+// (the barrier's current parity differs from it) - the device semantics, minus the asynchrony.
+namespace cimba_b200 { namespace tma {
+static inline void barrier_init(uint64_t *bar, uint32_t) { *bar = 0u; }
+static inline void barrier_init_fence() {}
+static inline void barrier_expect(uint64_t *bar, uint32_t bytes) { *bar += (uint64_t)bytes << 32; }
+static inline void barrier_wait(uint64_t *bar, uint32_t parity)
+{
+    while ((uint32_t)(*bar & 1u) == parity) emu::yield_to_next();
+}
+static inline void load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    std::memcpy(dst, src, bytes);
+    *bar -= (uint64_t)bytes << 32;
+    if ((*bar >> 32) == 0u) *bar += 1u;                 // all announced bytes are in: the phase completes
+}
+static inline void fence_global_to_async() {}
+} }
+#define __align__(n)
+
 #define AWACS_HOST_EMULATION 1
 #include "../cimba_b200/csrc/awacs_model.cuh"
 
@@ -303,7 +325,16 @@ int main(int argc, char **argv)
     g_args.first_trial = trial_index;
     g_args.num_trials = 1;
     g_args.t_end_s = (double)seconds;
-    g_args.ter = AwacsTerrain{map.data(), cols, rows, geom[0], geom[1], geom[2], geom[3], geom[4], geom[5]};
+    // the tile-maximum map (capi.cu builds it with aw_tile_max_kernel when a terrain is registered)
+    const uint32_t tcols = (cols + AWACS_TILE - 1u) >> AWACS_TILE_SHIFT, trows = (rows + AWACS_TILE - 1u) >> AWACS_TILE_SHIFT;
+    std::vector<float> tiles((size_t)tcols * trows, -3.402823466e+38f);
+    for (uint32_t r = 0; r < rows; r++) {
+        for (uint32_t c = 0; c < cols; c++) {
+            float &t = tiles[(size_t)(r >> AWACS_TILE_SHIFT) * tcols + (c >> AWACS_TILE_SHIFT)];
+            t = std::fmax(t, map[(size_t)r * cols + c]);
+        }
+    }
+    g_args.ter = AwacsTerrain{map.data(), cols, rows, geom[0], geom[1], geom[2], geom[3], geom[4], geom[5], tiles.data(), tcols, trows};
     g_args.orbit = orbit_constants();
     g_args.state = state.data();
     g_args.events = &events; g_args.objects = &found; g_args.t_end = &t_end; g_args.sum_wait = &sum_x;
@@ -347,9 +378,10 @@ int main(int argc, char **argv)
     }
     std::printf("{\"seconds\": %d, \"trial\": %llu, \"events\": [%llu, %llu], \"found\": [%llu, %u], \"t_end_equal\": %s, \"status\": %u, "
                 "\"position_diffs\": %u, \"tds_diffs\": %u, \"mode_diffs\": %u, \"found_diffs\": %u, \"first_trace_diff\": %ld, "
-                "\"modes\": [%u, %u, %u, %u], \"compared_pops\": %llu}\n",
+                "\"modes\": [%u, %u, %u, %u], \"compared_pops\": %llu, \"cells_read\": %llu}\n",
                 seconds, (unsigned long long)trial_index, (unsigned long long)events, (unsigned long long)o.events,
                 (unsigned long long)found, o.num_found, t_end == o.t_end ? "true" : "false", status, x_diff, tds_diff, mode_diff,
-                found_diff, first_trace_diff, o.mode_count[0], o.mode_count[1], o.mode_count[2], o.mode_count[3], (unsigned long long)n);
+                found_diff, first_trace_diff, o.mode_count[0], o.mode_count[1], o.mode_count[2], o.mode_count[3], (unsigned long long)n,
+                (unsigned long long)counters[7]);
     return 0;
 }

@@ -115,8 +115,9 @@ DIST_CASES = [
     (30, [5, 0.05, 0.25, 0.4, 0.1, 0.2]), (31, [4.2]), (32, [1.0, 2.0, 6.0, 2.5]), (33, [3, 0.6]),
     (15, [0.6, 2.0]), (20, [1.0]), (31, [1.0]), (9, [0.0, 0.0, 1.0]), (28, [0.2]),
 ]
-# the variate IS a log / exp / pow result: CUDA's libm vs glibc may differ in the last places
-DIST_LIBM_KINDS = {10, 11, 18, 19}
+# the variate IS a log / pow result: CUDA's libm vs glibc may differ in the last places (lognormal, kind 10, is an
+# exp result and exact: csrc/glibc_exp.cuh restates glibc's exp)
+DIST_LIBM_KINDS = {11, 18, 19}
 
 
 def rng_draws_ex(lib, prefix, seed, kind, params, n):

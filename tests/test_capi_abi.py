@@ -33,8 +33,25 @@ def test_struct_layouts_match_the_header(cb):
     # struct cmb_datasummary is 8 x 8 bytes (reference include/cmb_datasummary.h:42-51)
     assert C.sizeof(_lib.DataSummaryStruct) == 64
     assert _lib.DataSummaryStruct.count.offset == 8 and _lib.DataSummaryStruct.m1.offset == 32
-    assert C.sizeof(_lib.DeviceJob) == 4 * 4 + 4 * 8 + 9 * 8 + 2 * 8 + 3 * 8
-    assert C.sizeof(_lib.Experiment) == 6 * 4 + 3 * 8 + 10 * C.sizeof(C.c_size_t)
+    # the ctypes mirrors against the C compiler's view of include/cimba_b200.h: size and every field offset
+    import subprocess, tempfile
+    structs = {"cimba_b200_device_job": _lib.DeviceJob, "cimba_b200_experiment": _lib.Experiment,
+               "cimba_b200_awacs_terrain": _lib.AwacsTerrain, "cimba_b200_wtdsummary": _lib.WtdSummaryStruct}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include/cimba_b200.h"}"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = Path(td) / "layout.c", Path(td) / "layout"
+        src.write_text("\n".join(lines))
+        subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True, capture_output=True)
+        seen = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(seen[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(seen[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
     # the reference's struct trial (benchmark/MM1_multi.c:39-45) is a prefix of TRIAL_DTYPE
     f = cb.TRIAL_DTYPE.fields
     assert [f[k][1] for k in ("arr_mean", "srv_mean", "obj_cnt", "sum_wait", "avg_wait")] == [0, 8, 16, 24, 32]
