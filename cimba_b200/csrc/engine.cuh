@@ -22,7 +22,9 @@
 #pragma once
 
 #include <cstdint>
+#ifndef CMB_HOST_BUILD     // tests/cmb_engine_host.cpp compiles this text for the CPU
 #include <cuda_runtime.h>
+#endif
 
 namespace cimba_b200 {
 
@@ -206,6 +208,7 @@ struct StampRing {
 
 }  // namespace cimba_b200
 
+#ifndef CMB_HOST_BUILD     // shared-memory containers with inline PTX: device only
 namespace cimba_b200 {
 
 // ---------------------------------------------------------------------------
@@ -346,3 +349,4 @@ struct EventList {
 };
 
 }  // namespace cimba_b200
+#endif  // CMB_HOST_BUILD

@@ -19,7 +19,9 @@
 #pragma once
 
 #include <cstdint>
+#ifndef CMB_HOST_BUILD     // tests/cmb_engine_host.cpp compiles this text for the CPU
 #include <cuda_runtime.h>
+#endif
 
 #include "glibc_exp.cuh"
 #include "zig_tables.cuh"

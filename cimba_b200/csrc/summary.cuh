@@ -15,7 +15,9 @@
 
 #include <cfloat>
 #include <cstdint>
+#ifndef CMB_HOST_BUILD     // tests/cmb_engine_host.cpp compiles this text for the CPU
 #include <cuda_runtime.h>
+#endif
 
 namespace cimba_b200 {
 
@@ -206,6 +208,7 @@ __device__ __noinline__ void time_weighted_sample(TimeWeighted &h, double value,
     h.sample(value, now);
 }
 
+#ifndef CMB_HOST_BUILD     // the reduction kernels below are device-only
 constexpr int SUMMARY_BLOCK = 256;
 
 // One CTA: thread t adds trials t, t+256, ... (coalesced reads), then a fixed
@@ -308,5 +311,7 @@ merge_weighted_rows_kernel(const uint64_t *__restrict__ rows, uint64_t n, uint64
     }
     wtd_block_reduce(acc, out_row);
 }
+
+#endif  // CMB_HOST_BUILD
 
 }  // namespace cimba_b200

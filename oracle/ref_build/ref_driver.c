@@ -948,6 +948,104 @@ static void run_hold_trial(struct ref_trial *t)
     free(w);
 }
 
+/* ------------------------------------------------- model 16: impatient customers (many processes, timers, cancels)
+ *
+ * The oracle of cimba_b200/models/renege_model.cuh, in the manner of tutorial/tut_3_1.c's reneging: `servers`
+ * customer processes with priorities drawn from 0..3 think (exponential, mean arr_mean), then ask a
+ * cmb_resourcepool of (servers + 7) / 8 clerks for one unit with a patience timer running
+ * (cmb_process_timer_add, exponential with mean par0, signal 17).  Served in time: cmb_process_timers_clear (the
+ * timer event is cancelled by handle), service hold (mean srv_mean), release.  Not served in time: the timer resumes
+ * the waiter, cmb_resourcepool_acquire unwinds and returns 17.  An end event at t = num_objects stops everybody.
+ * counters: [0] served [1] reneged [2] other signals [3] clerks in use at the end; sum_wait = time in line of the served.
+ */
+#define RN_TIMER_RENEGING 17
+
+struct rn_world {
+    struct ref_trial *trl;
+    struct cmb_resourcepool *clerks;
+    struct rn_customer *cust;
+    unsigned count;
+    double patience_mean;
+};
+
+struct rn_customer {
+    struct cmb_process proc;
+    struct rn_world *world;
+    double t_join;
+};
+
+static void *rn_customer_body(struct cmb_process *me, void *vw)
+{
+    struct rn_customer *cu = (struct rn_customer *)me;
+    struct rn_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        cu->t_join = cmb_time();
+        (void)cmb_process_timer_add(me, cmb_random_exponential(w->patience_mean), RN_TIMER_RENEGING);
+        const int64_t sig = cmb_resourcepool_acquire(w->clerks, 1u);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            cmb_process_timers_clear(me);
+            w->trl->sum_wait += cmb_time() - cu->t_join;
+            (void)cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
+            cmb_resourcepool_release(w->clerks, 1u);
+            w->trl->counter[0] += 1u;
+        }
+        else if (sig == RN_TIMER_RENEGING) {
+            w->trl->counter[1] += 1u;
+        }
+        else {
+            w->trl->counter[2] += 1u;
+        }
+    }
+}
+
+static void rn_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct rn_world *w = subject;
+    for (unsigned i = 0u; i < w->count; i++) {
+        cmb_process_stop(&w->cust[i].proc, NULL);
+    }
+}
+
+static double g_renege_patience = 0.0;          /* par0, set by ref_set_param before the trials run */
+
+void ref_set_param(int index, double value)
+{
+    if (index == 0) {
+        g_renege_patience = value;
+    }
+}
+
+static void run_renege_trial(struct ref_trial *t)
+{
+    struct rn_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->count = (unsigned)t->servers;
+    w->patience_mean = g_renege_patience > 0.0 ? g_renege_patience : t->srv_mean;
+    w->clerks = cmb_resourcepool_create();
+    cmb_resourcepool_initialize(w->clerks, "Clerks", (uint64_t)((w->count + 7u) / 8u));
+    w->cust = calloc(w->count, sizeof(struct rn_customer));
+    for (unsigned i = 0u; i < w->count; i++) {
+        const int64_t prio = cmb_random_dice(0, 3);
+        w->cust[i].world = w;
+        cmb_process_initialize(&w->cust[i].proc, "Customer", rn_customer_body, w, prio);
+        cmb_process_start(&w->cust[i].proc);
+    }
+    (void)cmb_event_schedule(rn_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    t->objects = t->counter[0];
+    t->counter[3] = cmb_resourcepool_in_use(w->clerks);
+    for (unsigned i = 0u; i < w->count; i++) {
+        cmb_process_terminate(&w->cust[i].proc);
+    }
+    free(w->cust);
+    cmb_resourcepool_destroy(w->clerks);
+    free(w);
+}
+
 /* ------------------------------------------------- model 8: timers, waits, observers
  *
  * The remaining asynchronous calls of cmb_process / cmb_event / cmb_resourceguard in one
@@ -1716,7 +1814,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 14) {
+    if (t->model == 16) {
+        run_renege_trial(t);
+    }
+    else if (t->model == 14) {
         run_resource_trial(t);
     }
     else if (t->model == 10) {
