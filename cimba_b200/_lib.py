@@ -18,6 +18,7 @@ LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
 NO_FIELD = C.c_size_t(-1).value
 
 MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED, MODEL_HARBOR, MODEL_GUARDED_RECORDED, MODEL_BUFFER_RECORDED, MODEL_PRIOQ_RECORDED, MODEL_RESOURCE_RECORDED, MODEL_AWACS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
+MODEL_RENEGE, MODEL_USER_BASE, VARIANT_GENERAL = 16, 1000, 3
 MAP_LANE, MAP_WARP = 1, 32
 
 OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -122,6 +123,8 @@ SYMBOLS = {
                                           C.c_uint64, C.c_void_p, C.c_void_p]),
     "cimba_b200_alias_create": (C.c_int, [C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint32)]),
+    "cimba_b200_model_load": (C.c_int, [C.c_char_p]),
+    "cimba_b200_model_name": (C.c_char_p, [C.c_int]),
     "cimba_b200_version": (C.c_char_p, []),
     "cimba_b200_last_error": (C.c_char_p, []),
     "cimba_b200_device_count": (C.c_int, []),

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +39,13 @@
 #include "rng.cuh"
 #include "distributions.cuh"
 #include "summary.cuh"
+#include "cmb_launch.cuh"
+#include "../models/mm1_model.cuh"
+#include "../models/gg1_model.cuh"
+#include "../models/mmc_model.cuh"
+#include "../models/renege_model.cuh"
+
+#include <dlfcn.h>      // cimba_b200_model_load: a model library built with scripts/build_model.py
 
 using namespace cimba_b200;
 
@@ -73,6 +81,60 @@ uint32_t spill_cap_of(const cimba_b200_device_job *job)
     if (c == 0u) return QUEUE_SPILL_CAP;
     if ((c & (c - 1u)) != 0u || c > (1u << 26)) return 0xffffffffu;
     return c;
+}
+
+// ---- the general engine behind the fixed-capacity fast kernels
+// A trial the fast M/M/1, G/G/1 or M/M/c kernel had to flag (its queue outgrew window + ring, its event list or wait list
+// their fixed tables) is re-run inside the same launch by the general engine, whose containers grow: the reference's
+// queue is CMB_UNLIMITED and so is the drop-in.  The repair kernel is enqueued unconditionally behind the fast one and
+// looks at the status words; with nothing flagged it costs one pass over them.
+constexpr uint32_t REPAIR_BITS = CIMBA_B200_TRIAL_QUEUE_OVERFLOW | CIMBA_B200_TRIAL_FEL_OVERFLOW |
+                                 CIMBA_B200_TRIAL_GUARD_OVERFLOW | CIMBA_B200_TRIAL_PROC_OVERFLOW;
+
+uint64_t repair_arena_bytes(const cimba_b200_device_job *job)
+{
+    uint64_t b = job->num_trials * 32768ull;
+    if (b < (64ull << 20)) b = 64ull << 20;
+    if (b > (4ull << 30)) b = 4ull << 30;
+    return cmb::ARENA_HEADER + b;
+}
+
+uint64_t align256(uint64_t v) { return (v + 255u) & ~(uint64_t)255u; }
+
+bool mmc_goes_general(const cimba_b200_device_job *job)
+{
+    return job->model == CIMBA_B200_MODEL_MMC && (job->variant == CIMBA_B200_VARIANT_GENERAL || job->servers > 14);
+}
+
+bool fast_goes_general(const cimba_b200_device_job *job)
+{
+    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_GENERAL;
+}
+
+// models loaded with cimba_b200_model_load
+struct UserModel {
+    void *handle;
+    std::string name;
+    uint64_t (*workspace_bytes)(const cimba_b200_device_job *);
+    int (*launch)(const cimba_b200_device_job *, void *);
+};
+std::mutex g_user_mu;
+std::deque<UserModel> g_user_models;          // a deque: loaded models never move
+
+const UserModel *user_model(int id)
+{
+    std::lock_guard<std::mutex> hold(g_user_mu);
+    const int k = id - CIMBA_B200_MODEL_USER_BASE;
+    return (k >= 0 && (size_t)k < g_user_models.size()) ? &g_user_models[(size_t)k] : nullptr;
+}
+
+template <class Model>
+int launch_general(const cimba_b200_device_job *job, unsigned char *arena, uint64_t bytes, uint32_t only_flagged, cudaStream_t st,
+                   const char *what)
+{
+    const int e = cmb::launch_model<Model>(*job, arena, bytes, only_flagged, st);
+    g_launches++;
+    return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, what);
 }
 
 bool is_queue_model(int m)
@@ -267,9 +329,21 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (job == nullptr) {
         return 0u;
     }
+    if (job->model >= CIMBA_B200_MODEL_USER_BASE) {
+        const UserModel *um = user_model(job->model);
+        return um ? um->workspace_bytes(job) : 0u;
+    }
+    if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
+    if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
+    if (fast_goes_general(job)) {
+        return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_for<models::MM1>(*job)
+                                                  : cmb::workspace_bytes_for<models::GG1>(*job);
+    }
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         const uint32_t cap = spill_cap_of(job);
-        return job->num_trials * (uint64_t)(cap == 0xffffffffu ? QUEUE_SPILL_CAP : cap) * sizeof(double);
+        const uint64_t rings = job->num_trials * (uint64_t)(cap == 0xffffffffu ? QUEUE_SPILL_CAP : cap) * sizeof(double);
+        // the rings of the fast kernel, then the growth arena of its repair pass
+        return align256(rings) + (job->model == CIMBA_B200_MODEL_MM1_RECORDED ? 0u : repair_arena_bytes(job));
     }
     if (job->model == CIMBA_B200_MODEL_HARBOR) {
         return job->num_trials * (uint64_t)sizeof(HarborState);
@@ -303,6 +377,32 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     if (spill_cap_of(job) == 0xffffffffu)
         return fail(CIMBA_B200_EINVAL, "queue_spill_cap must be 0 (default) or a power of two <= 2^26");
+    if (job->num_params > CIMBA_B200_MAX_MODEL_PARAMS || (job->num_params > 0u && job->params == nullptr))
+        return fail(CIMBA_B200_EINVAL, "params: at most CIMBA_B200_MAX_MODEL_PARAMS doubles behind a HOST pointer");
+
+    if (job->model >= CIMBA_B200_MODEL_USER_BASE) {
+        const UserModel *um = user_model(job->model);
+        if (um == nullptr) return fail(CIMBA_B200_EINVAL, "unknown model id (cimba_b200_model_load returns the ids of loaded models)");
+        if (job->workspace_bytes < um->workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        const int e = um->launch(job, stream);
+        g_launches++;
+        return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
+    }
+    if (job->model == CIMBA_B200_MODEL_RENEGE || mmc_goes_general(job) || fast_goes_general(job)) {
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
+        if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        unsigned char *ws = (unsigned char *)job->workspace;
+        if (job->model == CIMBA_B200_MODEL_RENEGE)
+            return launch_general<models::Renege>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Renege> launch");
+        if (job->model == CIMBA_B200_MODEL_MMC)
+            return launch_general<models::MMC>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MMC> launch");
+        if (job->model == CIMBA_B200_MODEL_MM1)
+            return launch_general<models::MM1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MM1> launch");
+        return launch_general<models::GG1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<GG1> launch");
+    }
 
     if (is_queue_model(job->model)) {
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -338,7 +438,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             else       gg1_kernel<false><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
             g_launches++;
             cudaError_t e = cudaGetLastError();
-            return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "gg1_kernel launch");
+            if (e != cudaSuccess) return cuda_fail(e, "gg1_kernel launch");
+            if (job->status == nullptr) return CIMBA_B200_OK;       // nobody could see a flag: nothing to repair by
+            return launch_general<models::GG1>(job, (unsigned char *)job->workspace + align256(job->num_trials * (uint64_t)qa.spill_cap * sizeof(double)),
+                                               repair_arena_bytes(job), REPAIR_BITS, st, "repair pass (G/G/1)");
         }
         if (job->model == CIMBA_B200_MODEL_MM1_RECORDED) {
             if (job->counters == nullptr)
@@ -358,7 +461,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "mm1_kernel launch");
+        if (e != cudaSuccess) return cuda_fail(e, "mm1_kernel launch");
+        if (job->status == nullptr) return CIMBA_B200_OK;           // nobody could see a flag: nothing to repair by
+        return launch_general<models::MM1>(job, (unsigned char *)job->workspace + align256(job->num_trials * (uint64_t)qa.spill_cap * sizeof(double)),
+                                           repair_arena_bytes(job), REPAIR_BITS, st, "repair pass (M/M/1)");
     }
     if (job->model == CIMBA_B200_MODEL_MMC) {
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1 for CIMBA_B200_MODEL_MMC");
@@ -399,7 +505,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "pool_kernel launch");
+        if (e != cudaSuccess) return cuda_fail(e, "pool_kernel launch");
+        if (job->status == nullptr) return CIMBA_B200_OK;
+        return launch_general<models::MMC>(job, (unsigned char *)job->workspace + align256(job->num_trials * (uint64_t)pa.spill_cap * sizeof(double)),
+                                           repair_arena_bytes(job), REPAIR_BITS, st, "repair pass (M/M/c)");
     }
     if (is_general_model(job->model)) {
         const bool rsc = job->model == CIMBA_B200_MODEL_RESOURCE_RECORDED;
@@ -704,6 +813,32 @@ int cimba_b200_awacs_upload_terrain(const cimba_b200_awacs_terrain *t)
     const int rc = register_terrain(dev, t, copy, copy);
     if (rc != CIMBA_B200_OK) cudaFree(copy);
     return rc;
+}
+
+int cimba_b200_model_load(const char *path)
+{
+    if (path == nullptr) return fail(CIMBA_B200_EINVAL, "NULL path");
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (h == nullptr) return fail(CIMBA_B200_EINVAL, "cannot load the model library: %s", dlerror());
+    UserModel um{};
+    um.handle = h;
+    um.workspace_bytes = (uint64_t (*)(const cimba_b200_device_job *))dlsym(h, "cimba_b200_user_model_workspace_bytes");
+    um.launch = (int (*)(const cimba_b200_device_job *, void *))dlsym(h, "cimba_b200_user_model_launch");
+    const char *(*name)(void) = (const char *(*)(void))dlsym(h, "cimba_b200_user_model_name");
+    if (um.workspace_bytes == nullptr || um.launch == nullptr || name == nullptr) {
+        dlclose(h);
+        return fail(CIMBA_B200_EINVAL, "%s does not export a model (end the model's .cu file with CMB_EXPORT_MODEL)", path);
+    }
+    um.name = name();
+    std::lock_guard<std::mutex> hold(g_user_mu);
+    g_user_models.push_back(um);
+    return CIMBA_B200_MODEL_USER_BASE + (int)g_user_models.size() - 1;
+}
+
+const char *cimba_b200_model_name(int model_id)
+{
+    const UserModel *um = user_model(model_id);
+    return um ? um->name.c_str() : nullptr;
 }
 
 int cimba_b200_summarize(const double *sum_wait, const uint64_t *objects,

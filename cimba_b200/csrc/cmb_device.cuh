@@ -697,6 +697,7 @@ struct Sim {
 
     CMB_FN void process_start(uint32_t pid)             // :127-135: a FINISHED process may be started again
     {
+        if (pid == NIL) return;                         // process_create found no memory: the trial is flagged and will not run
         schedule(ACT_CMB_START, pid, 0, now, proc[pid].prio);
     }
 
@@ -1207,6 +1208,8 @@ template <class Model, bool TRACE>
 CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *trace_key, double *trace_time)
 {
     for (;;) {
+        // a trial whose containers could not grow (workspace too small) is void: stop it where it stands, flagged
+        if (sim.status & TRIAL_ERR_ARENA) return;
         if (!sim.fel.dequeue()) return;
         const Tag ev = sim.fel.tag[0];
         sim.now = ev.d;

@@ -17,6 +17,7 @@
 // containers grow, so the reference's CMB_UNLIMITED queue holds there too - and clears the bits.
 #pragma once
 
+#include "../../include/cimba_b200.h"
 #include "cmb_device.cuh"
 
 namespace cimba_b200 {

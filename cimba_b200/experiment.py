@@ -105,11 +105,21 @@ class TrialResults:
         return int(self.events.sum().item())
 
 
+def load_model(path) -> int:
+    """cimba_b200_model_load: register a model library built from a .cu file written against
+    cimba_b200/csrc/cmb_device.cuh (scripts/build_model.py); returns the model id to pass as ``model=``."""
+    rc = lib.cimba_b200_model_load(str(path).encode())
+    if rc < 0:
+        check(rc)
+    return int(rc)
+
+
 class TrialBuffers:
     """Reusable device buffers for repeated launches of the same shape."""
 
     def __init__(self, num_trials: int, device: torch.device, trace_cap: int = 0,
-                 model: int = _lib.MODEL_MM1, servers: int = 1, variant: int = 0):
+                 model: int = _lib.MODEL_MM1, servers: int = 1, variant: int = 0, queue_spill_cap: int = 0,
+                 num_objects: int = 0):
         n = num_trials
         self.n = n
         self.device = device
@@ -125,7 +135,8 @@ class TrialBuffers:
         if trace_cap:
             self.trace_key = torch.zeros((n, trace_cap), dtype=torch.int64, device=device)
             self.trace_time = torch.zeros((n, trace_cap), dtype=torch.float64, device=device)
-        job = _lib.DeviceJob(model=model, num_trials=n, servers=servers, variant=variant)
+        job = _lib.DeviceJob(model=model, num_trials=n, servers=servers, variant=variant, queue_spill_cap=queue_spill_cap,
+                             num_objects=num_objects)
         ws = int(lib.cimba_b200_workspace_bytes(C.byref(job)))
         self.workspace = torch.empty(max(ws, 8), dtype=torch.uint8, device=device)
         self.workspace_bytes = ws
@@ -138,7 +149,8 @@ class TrialBuffers:
 def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects: int,
                   master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
                   servers: int = 1, mapping: int = 0, buffers: Optional[TrialBuffers] = None,
-                  trace_cap: int = 0, variant: int = 0) -> TrialResults:
+                  trace_cap: int = 0, variant: int = 0, queue_spill_cap: int = 0, params=(),
+                  diag: Optional[torch.Tensor] = None) -> TrialResults:
     """Asynchronously run one trial per element of ``arr_mean`` on the current stream.
 
     Inputs are float64 CUDA tensors already resident in HBM (the device-resident
@@ -155,10 +167,14 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
     n = arr_mean.numel()
     if n == 0:
         raise ValueError("num_trials must be > 0 (reference asserts this, src/cimba.c:157)")
-    b = buffers if buffers is not None else TrialBuffers(n, arr_mean.device, trace_cap, model, servers, variant)
+    b = buffers if buffers is not None else TrialBuffers(n, arr_mean.device, trace_cap, model, servers, variant,
+                                                        queue_spill_cap, num_objects)
     if b.n != n or b.trace_cap != trace_cap:
         raise ValueError("buffers do not match this launch")
+    par = (C.c_double * max(1, len(params)))(*[float(v) for v in params])
     job = _lib.DeviceJob(
+        queue_spill_cap=queue_spill_cap, params=par if len(params) else None, num_params=len(params),
+        diag=diag.data_ptr() if diag is not None else None,
         model=model, servers=servers, mapping=mapping, variant=variant,
         master_seed=master_seed & (2**64 - 1), first_trial=first_trial,
         num_trials=n, num_objects=num_objects,
@@ -179,14 +195,15 @@ def launch_trials(arr_mean: torch.Tensor, srv_mean: torch.Tensor, *, num_objects
 def run_trials(num_trials: int, *, arr_mean: float, srv_mean: float, num_objects: int,
                master_seed: int, first_trial: int = 0, model: int = _lib.MODEL_MM1,
                servers: int = 1, mapping: int = 0, trace_cap: int = 0, variant: int = 0,
-               device: Optional[torch.device] = None) -> TrialResults:
+               device: Optional[torch.device] = None, queue_spill_cap: int = 0, params=()) -> TrialResults:
     """Convenience: identical parameters for every trial, results after a sync."""
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     a = torch.full((num_trials,), arr_mean, dtype=torch.float64, device=dev)
     s = torch.full((num_trials,), srv_mean, dtype=torch.float64, device=dev)
     res = launch_trials(a, s, num_objects=num_objects, master_seed=master_seed,
                         first_trial=first_trial, model=model, servers=servers,
-                        mapping=mapping, trace_cap=trace_cap, variant=variant)
+                        mapping=mapping, trace_cap=trace_cap, variant=variant, queue_spill_cap=queue_spill_cap,
+                        params=params)
     torch.cuda.synchronize(dev)
     return res
 

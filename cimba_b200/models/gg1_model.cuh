@@ -1,0 +1,76 @@
+// gg1_model.cuh - BASELINE config 4 against the device authoring surface: benchmark/MM1_multi.c
+// with Erlang-2 inter-arrival times and normal service times redrawn while negative (oracle: ref_driver.c model 1).
+#pragma once
+#include "../csrc/cmb_kernel.cuh"
+
+namespace cimba_b200 {
+namespace models {
+
+struct GG1 {
+    cmb::objectqueue queue;
+    uint32_t arrival, service;
+    double   arr_mean, srv_mean, s;
+    uint64_t num_objects, obj_cnt;
+    double   sum_wait;
+    uint64_t ui, stamp, object;
+    enum : uint32_t { ARRIVAL, SERVICE };
+
+    CMB_FN void arrivalfunc(cmb::Sim &sim, uint32_t me, int64_t sig)
+    {
+        GG1 &m = *this;
+        CMB_PROCESS_BEGIN
+        for (ui = 0u; ui < num_objects; ui++) {
+            CMB_PROCESS_HOLD(cmb_random_erlang(2u, 0.5 * arr_mean));
+            stamp = (uint64_t)__double_as_longlong(cmb_time());
+            CMB_OBJECTQUEUE_PUT(queue, stamp);
+        }
+        CMB_PROCESS_END
+    }
+
+    CMB_FN void servicefunc(cmb::Sim &sim, uint32_t me, int64_t sig)
+    {
+        GG1 &m = *this;
+        CMB_PROCESS_BEGIN
+        for (;;) {
+            CMB_OBJECTQUEUE_GET(queue, object);
+            do {
+                s = cmb_random_normal(srv_mean, 0.25 * srv_mean);
+            } while (s < 0.0);
+            CMB_PROCESS_HOLD(s);
+            sum_wait += cmb_time() - __longlong_as_double((long long)object);
+            obj_cnt += 1u;
+        }
+        CMB_PROCESS_END
+    }
+
+    CMB_FN void run_trial(cmb::Sim &sim, const cmb::TrialIn &in)
+    {
+        arr_mean = in.arr_mean;
+        srv_mean = in.srv_mean;
+        num_objects = in.num_objects;
+        obj_cnt = 0u;
+        sum_wait = 0.0;
+        cmb_objectqueue_initialize(queue, CMB_UNLIMITED);
+        arrival = cmb_process_create(ARRIVAL, 0, 0u);
+        cmb_process_start(arrival);
+        service = cmb_process_create(SERVICE, 0, 0u);
+        cmb_process_start(service);
+    }
+
+    CMB_FN void process(cmb::Sim &sim, uint32_t me, uint32_t kind, int64_t sig)
+    {
+        if (kind == ARRIVAL) arrivalfunc(sim, me, sig);
+        else servicefunc(sim, me, sig);
+    }
+    CMB_FN void event(cmb::Sim &, uint32_t, uint32_t, int64_t) {}
+    CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return false; }
+
+    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    {
+        out.objects = obj_cnt;
+        out.sum_wait = sum_wait;
+    }
+};
+
+}  // namespace models
+}  // namespace cimba_b200

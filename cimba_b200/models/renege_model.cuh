@@ -21,6 +21,14 @@ struct Renege {
     enum : uint32_t { END_OF_DAY = cmb::ACT_CMB_USER };
     static constexpr int64_t TIMER_RENEGING = 17;
 
+    // growth memory of one trial: the process table, an event list of ~2 entries per customer with its key map, the
+    // wait list, and as much again for the blocks the doubling leaves behind
+    static uint64_t arena_bytes_per_trial(const cimba_b200_device_job &job)
+    {
+        const uint64_t n = (uint64_t)(job.servers < 8 ? 8 : job.servers);
+        return n * (2u * sizeof(cmb::Process) + 8u * sizeof(cmb::Tag) + 16u * sizeof(cmb::MapSlot) + 8u * sizeof(cmb::Node)) + 16384u;
+    }
+
     CMB_FN void customer(cmb::Sim &sim, uint32_t me, int64_t sig)
     {
         Renege &m = *this;

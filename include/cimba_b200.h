@@ -108,6 +108,30 @@ extern "C" {
                                     * Parity with the reference (glibc libm): atan2f / sinf / cosf are restated exactly, powf / expf rounded
                                     * once from double - exact until one of those straddles a test threshold, statistical beyond */
 
+#define CIMBA_B200_MODEL_RENEGE 16   /* cimba_b200/models/renege_model.cuh, written against the device authoring surface
+                                    * (cimba_b200/csrc/cmb_device.cuh) and run by the general engine: `servers` impatient customer
+                                    * PROCESSES (a thousand and more) with priorities 0..3 think (mean arr_mean), then ask a
+                                    * cmb_resourcepool of (servers + 7) / 8 clerks for a unit with a patience timer running
+                                    * (cmb_process_timer_add, mean params[0], default srv_mean): served in time -> timers_clear,
+                                    * service (mean srv_mean), release; else the timer resumes the waiter and the acquire unwinds.
+                                    * End event at t = num_objects stops everybody.  counters: [0] served [1] reneged [2] other
+                                    * signals [3] clerks busy at the end [4] stale wait-list entries [5] log2 of the event list's
+                                    * final capacity [6] its key map active [7] processes.  sum_wait = time in line of the served */
+
+/* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
+ * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */
+#define CIMBA_B200_MODEL_USER_BASE 1000
+/* Returns a model id >= CIMBA_B200_MODEL_USER_BASE usable wherever a CIMBA_B200_MODEL_* is (device jobs and
+ * cimba_b200_run_experiment alike), or a negative CIMBA_B200_E* code.  The library stays loaded for the process' life. */
+int cimba_b200_model_load(const char *path_to_model_library);
+/* The name the model registered, or NULL for an id nobody loaded. */
+const char *cimba_b200_model_name(int model_id);
+
+/* variant 3 of MODEL_MM1 / MODEL_GG1 / MODEL_MMC: the same model as cimba_b200/models/{mm1,gg1,mmc}_model.cuh run by the
+ * general engine (growable event list, wait lists and queues; any number of servers).  The fast kernels' repair pass
+ * and MODEL_MMC with more than 14 servers use it too. */
+#define CIMBA_B200_VARIANT_GENERAL 3
+
 /* Error codes */
 #define CIMBA_B200_OK         0
 #define CIMBA_B200_EINVAL    -1  /* bad argument */
@@ -123,6 +147,7 @@ extern "C" {
 #define CIMBA_B200_TRIAL_GUARD_OVERFLOW 8u
 #define CIMBA_B200_TRIAL_PROC_OVERFLOW  16u
 #define CIMBA_B200_TRIAL_NEGATIVE_HOLD  32u
+#define CIMBA_B200_TRIAL_ARENA_EXHAUSTED 64u   /* general engine: a container could not grow (workspace too small) */
 
 /* How trials map onto the machine.  LANE: one trial per CUDA thread (32 trials
  * advance per warp instruction; the default for models whose per-trial state is

@@ -1046,6 +1046,84 @@ static void run_renege_trial(struct ref_trial *t)
     free(w);
 }
 
+/* ------------------------------------------------- model 17: two stations in tandem, bounded buffer between them
+ *
+ * The oracle of examples/tandem_user_model.cu (a model that exists only as a user-built library on the device side):
+ * a source puts stamped objects into an unlimited queue; station 1 takes one, serves it (exponential, srv_mean) and
+ * puts it into a queue of `servers` places - blocking while that is full; station 2 takes it and serves it
+ * (uniform on 0.5 .. 1.5 srv_mean).  sum_wait = time from arrival to the end of station 2.
+ */
+struct td_world {
+    struct ref_trial *trl;
+    struct cmb_objectqueue *first, *second;
+    struct cmb_process *proc[3];
+};
+
+static void *td_source_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct td_world *w = vw;
+    for (uint64_t i = 0u; i < w->trl->num_objects; i++) {
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        double *stamp = cmi_mempool_alloc(&stamp_pool);
+        *stamp = cmb_time();
+        (void)cmb_objectqueue_put(w->first, stamp);
+    }
+    return NULL;
+}
+
+static void *td_station1_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct td_world *w = vw;
+    for (;;) {
+        void *obj = NULL;
+        (void)cmb_objectqueue_get(w->first, &obj);
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
+        (void)cmb_objectqueue_put(w->second, obj);
+    }
+}
+
+static void *td_station2_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct td_world *w = vw;
+    for (;;) {
+        void *obj = NULL;
+        (void)cmb_objectqueue_get(w->second, &obj);
+        (void)cmb_process_hold(cmb_random_uniform(0.5 * w->trl->srv_mean, 1.5 * w->trl->srv_mean));
+        w->trl->sum_wait += cmb_time() - *(double *)obj;
+        w->trl->objects += 1u;
+        cmi_mempool_free(&stamp_pool, obj);
+    }
+}
+
+static void run_tandem_trial(struct ref_trial *t)
+{
+    struct td_world w = { .trl = t };
+    w.first = cmb_objectqueue_create();
+    cmb_objectqueue_initialize(w.first, "First", CMB_UNLIMITED);
+    w.second = cmb_objectqueue_create();
+    cmb_objectqueue_initialize(w.second, "Second", (uint64_t)t->servers);
+    cmb_process_func *body[3] = { td_source_body, td_station1_body, td_station2_body };
+    for (int i = 0; i < 3; i++) {
+        w.proc[i] = cmb_process_create();
+        cmb_process_initialize(w.proc[i], "Tandem", body[i], &w, 0);
+        cmb_process_start(w.proc[i]);
+    }
+
+    pump_events(t);
+
+    cmb_process_stop(w.proc[1], NULL);
+    cmb_process_stop(w.proc[2], NULL);
+    for (int i = 0; i < 3; i++) {
+        cmb_process_terminate(w.proc[i]);
+        cmb_process_destroy(w.proc[i]);
+    }
+    cmb_objectqueue_destroy(w.first);
+    cmb_objectqueue_destroy(w.second);
+}
+
 /* ------------------------------------------------- model 8: timers, waits, observers
  *
  * The remaining asynchronous calls of cmb_process / cmb_event / cmb_resourceguard in one
@@ -1814,7 +1892,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 16) {
+    if (t->model == 17) {
+        run_tandem_trial(t);
+    }
+    else if (t->model == 16) {
         run_renege_trial(t);
     }
     else if (t->model == 14) {

@@ -1,0 +1,76 @@
+"""Throughput of the general engine (cimba_b200/csrc/cmb_device.cuh) next to the hand-fused kernels, CUDA-event timed.
+
+    python scripts/engine_bench.py [--out gpurun_out/engine_bench.json]
+
+M/M/1 and M/M/c: the model written against the authoring surface (variant 3) vs the fast kernel (variant 0), same
+trials, same answers; the reneging model (1000 processes per trial) on its own."""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import cimba_b200 as cb     # noqa: E402
+
+MASTER = 0x34F05C64D7AD598F
+
+
+def timed(fn, reps=2):
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None or ms < best else best
+    return res, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    rows = []
+    for name, model, servers, arr, srv, trials, nobj in (("M/M/1", cb.MODEL_MM1, 1, 1 / 0.9, 1.0, 65536, 100000),
+                                                         ("M/M/c c=8", cb.MODEL_MMC, 8, 1 / 6.4, 1.0, 32768, 100000)):
+        am = torch.full((trials,), arr, dtype=torch.float64, device=dev)
+        sm = torch.full((trials,), srv, dtype=torch.float64, device=dev)
+        out = {}
+        for label, variant in (("fast", 0), ("general", cb.VARIANT_GENERAL)):
+            bufs = cb.TrialBuffers(trials, dev, 0, model, servers, variant)
+            cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, model=model, servers=servers, variant=variant)
+            res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, model=model, servers=servers,
+                                                     variant=variant, buffers=bufs))
+            ev = int(res.events.sum().item())
+            out[label] = {"ms": ms, "events_per_s": ev / ms * 1e3, "events": ev, "bad": int((res.status != 0).sum().item()),
+                          "sum_check": float(res.sum_wait.sum().item())}
+        row = {"model": name, "trials": trials, "objects": nobj, **out,
+               "general_over_fast_time": out["general"]["ms"] / out["fast"]["ms"],
+               "same_answers": out["fast"]["sum_check"] == out["general"]["sum_check"] and out["fast"]["events"] == out["general"]["events"]}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    for trials, customers, T in ((4096, 1000, 50), (16384, 1000, 20)):
+        am = torch.full((trials,), 4.0, dtype=torch.float64, device=dev)
+        sm = torch.full((trials,), 1.0, dtype=torch.float64, device=dev)
+        bufs = cb.TrialBuffers(trials, dev, 0, cb.MODEL_RENEGE, customers, 0)
+        res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=T, master_seed=MASTER, model=cb.MODEL_RENEGE, servers=customers,
+                                                 params=[0.5], buffers=bufs))
+        ev = int(res.events.sum().item())
+        row = {"model": "reneging customers", "trials": trials, "processes_per_trial": customers, "sim_time": T, "ms": ms,
+               "events_per_s": ev / ms * 1e3, "events": ev, "bad": int((res.status != 0).sum().item()),
+               "workspace_MB": bufs.workspace_bytes / 1e6}
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    if a.out:
+        Path(a.out).parent.mkdir(parents=True, exist_ok=True)
+        Path(a.out).write_text(json.dumps(rows, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""Golden vectors for the general engine's models, produced by the UNMODIFIED reference (oracle/_ref/librefdrv.so: the
+same models written against the reference's API in oracle/ref_build/ref_driver.c).
+
+    python tests/golden/make_cmb_golden.py      -> tests/golden/cmb_engine_vectors.json
+
+Each case: model, servers, num_objects, arr_mean, srv_mean, params; per trial (seed cmb_random_fmix64(MASTER, i)):
+events, objects, t_end and sum_wait as hex floats, the first four counters, and the SHA-256 of the first `trace`
+pops (key, time).  Used by tests/test_cmb_engine.py (the engine's source text run on the CPU) and
+tests/test_gpu_cmb_engine.py (the same on the device) wherever the live reference build is absent."""
+import hashlib
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT / "tests"))
+from oracle_libs import load_ref, run_trials, trace_trial      # noqa: E402
+import ctypes as C                                              # noqa: E402
+
+MASTER = 0x34F05C64D7AD598F
+TRACE = 2000
+CASES = [
+    # model, servers, num_objects, arr_mean, srv_mean, params, trials
+    (0, 1, 20000, 1 / 0.9, 1.0, [], 6),
+    (0, 1, 60000, 1 / 0.99, 1.0, [], 4),          # heavy traffic: the queue passes the fast kernel's window + ring
+    (0, 1, 20000, 1 / 1.05, 1.0, [], 4),          # overload: the queue grows for the whole trial
+    (1, 1, 20000, 1.25, 1.0, [], 6),
+    (1, 1, 40000, 1.02, 1.0, [], 4),
+    (2, 8, 20000, 1 / 6.4, 1.0, [], 6),
+    (2, 3, 20000, 1 / 2.9, 1.0, [], 4),
+    (2, 64, 20000, 1 / 60.0, 1.0, [], 4),         # more servers than the fast kernel's event list holds
+    (2, 8, 20000, 1 / 8.4, 1.0, [], 4),           # overload: the wait list grows
+    (16, 40, 300, 3.0, 1.0, [0.7], 4),
+    (16, 1000, 60, 4.0, 1.0, [0.5], 4),
+    (16, 1500, 40, 2.0, 1.0, [1.5], 3),
+    (17, 4, 20000, 1.3, 1.0, [], 4),
+    (17, 1, 20000, 1.05, 1.0, [], 4),
+]
+
+
+def main():
+    ref = load_ref()
+    assert ref is not None, "oracle/_ref/librefdrv.so is not built (make -C oracle ref)"
+    ref.ref_set_param.argtypes = [C.c_int, C.c_double]
+    out = {"master": MASTER, "trace": TRACE, "cases": []}
+    for model, servers, nobj, arr, srv, params, n in CASES:
+        ref.ref_set_param(0, params[0] if params else 0.0)
+        res = run_trials(ref, "ref", model, servers, MASTER, 0, n, nobj, arr, srv, par=0)
+        trials = []
+        for i, r in enumerate(res):
+            _, keys, times = trace_trial(ref, "ref", model, servers, ref.ref_fmix64(MASTER, i), nobj, arr, srv, TRACE)
+            h = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
+            trials.append({"events": r.events, "objects": r.objects, "t_end": float(r.t_end).hex(), "sum_wait": float(r.sum_wait).hex(),
+                           "counters": list(r.counter)[:4], "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
+        out["cases"].append({"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
+                             "srv_mean": float(srv).hex(), "params": params, "trials": trials})
+        print(model, servers, nobj, [t["events"] for t in trials])
+    ref.ref_set_param(0, 0.0)
+    (ROOT / "tests/golden/cmb_engine_vectors.json").write_text(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""CPU tests of the general engine (cimba_b200/csrc/cmb_device.cuh) and of the models written against its authoring
+surface (cimba_b200/models/*.cuh, examples/tandem_model.cuh): the SAME source text compiled for the host
+(tests/cmb_engine_host.cpp) must reproduce, trial for trial, what the unmodified reference produced for the same
+models written against its own API (tests/golden/cmb_engine_vectors.json; and the live build oracle/_ref where
+present): event count, clock, sums, counters and the pop trace - M/M/1 (also in heavy traffic and overload, where the
+queue grows without bound), G/G/1, M/M/c (3, 8 and 64 servers, overload), the reneging model with 40, 1000 and 1500
+processes (timers, cancels by handle, wait-list removals, the stop cascade) and the tandem model with a blocking put."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from cmb_cases import GOLD, MASTER, TRACE, case_id, check_trial
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+class HostResult(C.Structure):
+    _fields_ = [("events", C.c_uint64), ("objects", C.c_uint64), ("t_end", C.c_double), ("sum_wait", C.c_double),
+                ("max_fel", C.c_uint64), ("max_queue", C.c_uint64), ("counter", C.c_uint64 * 8), ("status", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    so = tmp_path_factory.mktemp("cmb") / "libcmb_engine_host.so"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+                    "-shared", "-fPIC", str(ROOT / "tests/cmb_engine_host.cpp"), "-o", str(so)], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    f = lib.host_cmb_run_trials
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
+                  C.POINTER(C.c_double), C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                  C.POINTER(HostResult)]
+    return f
+
+
+def run_host(f, c, n, arena=1 << 26, first=0):
+    out = (HostResult * n)()
+    par = (C.c_double * max(1, len(c["params"])))(*c["params"])
+    keys = (C.c_uint64 * (n * TRACE))()
+    times = (C.c_double * (n * TRACE))()
+    rc = f(c["model"], c["servers"], MASTER, first, n, c["num_objects"], float.fromhex(c["arr_mean"]),
+           float.fromhex(c["srv_mean"]), par, len(c["params"]), arena, TRACE, keys, times, out)
+    assert rc == 0
+    return out, keys, times
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=case_id)
+def test_engine_source_on_the_cpu_matches_the_reference_vectors(host, case):
+    n = len(case["trials"])
+    out, keys, times = run_host(host, case, n)
+    for i, want in enumerate(case["trials"]):
+        assert out[i].status == 0
+        check_trial(want, out[i].events, out[i].objects, out[i].t_end, out[i].sum_wait, list(out[i].counter),
+                    keys[i * TRACE:(i + 1) * TRACE], times[i * TRACE:(i + 1) * TRACE], f"trial {i}")
+        if case["model"] == 2:
+            assert out[i].max_queue == want["max_queue"]        # process structs ever created
+
+
+def test_engine_matches_the_live_reference_build(host):
+    from oracle_libs import load_ref, run_trials
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/librefdrv.so not built (needs /root/reference)")
+    ref.ref_set_param.argtypes = [C.c_int, C.c_double]
+    for model, servers, nobj, arr, srv, params in ((0, 1, 7000, 1.0, 1.0, []), (2, 5, 7000, 0.22, 1.0, []),
+                                                   (16, 300, 25, 2.5, 1.0, [0.9]), (17, 2, 7000, 1.2, 1.0, [])):
+        case = {"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
+                "srv_mean": float(srv).hex(), "params": params}
+        ref.ref_set_param(0, params[0] if params else 0.0)
+        want = run_trials(ref, "ref", model, servers, MASTER, 11, 5, nobj, arr, srv, par=0)
+        ref.ref_set_param(0, 0.0)
+        out, _, _ = run_host(host, case, 5, first=11)
+        for o, w in zip(out, want):
+            assert (o.events, o.objects, o.t_end, o.sum_wait) == (w.events, w.objects, w.t_end, w.sum_wait)
+            assert list(o.counter)[:4] == list(w.counter)[:4] or model != 16
+
+
+def test_a_small_arena_is_reported_not_survived_silently(host):
+    """The event list of a 1000-process trial cannot grow out of 4 KB: the trial must say so in its status word."""
+    case = next(c for c in GOLD["cases"] if c["model"] == 16 and c["servers"] == 1000)
+    out, _, _ = run_host(host, case, 1, arena=4096)
+    assert out[0].status & 64           # CIMBA_B200_TRIAL_ARENA_EXHAUSTED
+
+
+def test_hashheap_growth_and_key_map(host):
+    """M/M/c with 64 servers grows the event list from 8 to 128 slots; the reneging model activates the key map."""
+    c64 = next(c for c in GOLD["cases"] if c["model"] == 2 and c["servers"] == 64)
+    out, _, _ = run_host(host, c64, 1)
+    assert out[0].max_fel == 128
+    rn = next(c for c in GOLD["cases"] if c["model"] == 16 and c["servers"] == 1500)
+    out, _, _ = run_host(host, rn, 1)
+    assert out[0].counter[5] >= 11 and out[0].counter[6] == 1 and out[0].counter[7] == 1500

@@ -1,0 +1,157 @@
+"""GPU parity of the general engine (cimba_b200/csrc/cmb_device.cuh) and of everything built on it, through the C-ABI:
+
+* the models written against the authoring surface (M/M/1, G/G/1, M/M/c, the 1000-process reneging model) against the
+  vectors the unmodified reference produced for the same models written against its own API
+  (tests/golden/cmb_engine_vectors.json) and, where it travelled with the snapshot, the live reference build;
+* the repair pass: trials the fixed-capacity fast kernels flag (rho = 0.99, rho > 1, a wait list that outgrows its
+  ring) come back with the reference's answer and a clean status word - the drop-in has no capacity the reference lacks;
+* MODEL_MMC with 64 servers (the fast kernel's event list holds 16 entries);
+* model libraries of one's own: examples/*.cu built with scripts/build_model.py, loaded with cimba_b200_model_load
+  and run through cimba_b200_run_experiment like any built-in model."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import cimba_b200 as cb
+from cmb_cases import GOLD, MASTER, TRACE, case_id, check_trial
+from oracle_libs import load_port, load_ref, run_trials
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 16: cb.MODEL_RENEGE}
+
+
+def run_case(case, model_id, variant, n, trace=True, spill=0):
+    return cb.run_trials(n, arr_mean=float.fromhex(case["arr_mean"]), srv_mean=float.fromhex(case["srv_mean"]),
+                         num_objects=case["num_objects"], master_seed=MASTER, model=model_id, servers=case["servers"],
+                         variant=variant, trace_cap=TRACE if trace else 0, params=case["params"], queue_spill_cap=spill)
+
+
+def compare(case, res, n):
+    ev, ob = res.events.cpu().numpy(), res.objects.cpu().numpy()
+    te, sw = res.t_end.cpu().numpy(), res.sum_wait.cpu().numpy()
+    cnt = res.counters.cpu().numpy()
+    tk = res.trace_key.cpu().numpy() if res.trace_key is not None else None
+    tt = res.trace_time.cpu().numpy() if res.trace_time is not None else None
+    assert (res.status.cpu().numpy()[:n] == 0).all(), res.status.cpu().numpy()[:n]
+    for i, want in enumerate(case["trials"][:n]):
+        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] == 16 else None,
+                    tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}")
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in BUILTIN], ids=case_id)
+def test_models_on_the_general_engine_match_the_reference_vectors(case):
+    n = len(case["trials"])
+    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] != 16 else 0, n)
+    compare(case, res, n)
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 2)], ids=case_id)
+def test_default_kernels_with_their_repair_pass_match_the_reference_vectors(case):
+    """variant 0 = the fast kernel; whatever it flags the repair pass re-runs.  The heavy-traffic, overload and
+    64-server cases cannot be served by the fixed tables alone."""
+    n = len(case["trials"])
+    res = run_case(case, BUILTIN[case["model"]], 0, n)
+    compare(case, res, n)
+
+
+def test_the_repair_pass_is_what_answers_in_overload():
+    """At rho = 1.05 every trial outgrows the 32 + 512 entry queue: the diag counter shows the repair pass re-ran
+    them all, and with a ring sized for the traffic the fast kernel keeps them (same answers either way)."""
+    case = next(c for c in GOLD["cases"] if c["model"] == 0 and float.fromhex(c["arr_mean"]) < 1.0)
+    n = len(case["trials"])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    arr = torch.full((n,), float.fromhex(case["arr_mean"]), dtype=torch.float64, device=dev)
+    srv = torch.full((n,), float.fromhex(case["srv_mean"]), dtype=torch.float64, device=dev)
+    for spill, want_repairs in ((0, n), (4096, 0)):
+        diag = torch.zeros(4, dtype=torch.int64, device=dev)
+        res = cb.launch_trials(arr, srv, num_objects=case["num_objects"], master_seed=MASTER, queue_spill_cap=spill, diag=diag)
+        torch.cuda.synchronize()
+        assert int(diag[2].item()) == want_repairs
+        compare(case, res, n)
+
+
+def test_host_buffer_entry_point_returns_the_reference_answer_in_heavy_traffic():
+    """cimba_b200_run_experiment at rho = 0.99: rc 0, no status bits, results as the reference's."""
+    case = next(c for c in GOLD["cases"] if c["model"] == 0 and c["num_objects"] == 60000)
+    n = len(case["trials"])
+    exp = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    exp["arr_mean"], exp["srv_mean"] = float.fromhex(case["arr_mean"]), float.fromhex(case["srv_mean"])
+    cb.cimba_run_experiment(exp, num_objects=case["num_objects"], master_seed=MASTER)
+    for i, want in enumerate(case["trials"]):
+        assert (int(exp["events"][i]), int(exp["obj_cnt"][i])) == (want["events"], want["objects"])
+        assert float(exp["t_end"][i]).hex() == want["t_end"] and float(exp["sum_wait"][i]).hex() == want["sum_wait"]
+        assert exp["status"][i] == 0
+
+
+def test_general_engine_against_the_oracle_at_other_sizes():
+    """Beyond the stored vectors: ragged trial counts, a few thousand trials taken grid-stride, against the C oracle."""
+    port = load_port()
+    for model, servers, arr, srv, nobj, n in ((0, 1, 1 / 0.9, 1.0, 700, 3000), (2, 8, 1 / 6.4, 1.0, 500, 2500),
+                                               (1, 1, 1.25, 1.0, 600, 1111)):
+        res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=MASTER, first_trial=5,
+                            model=BUILTIN[model], servers=servers, variant=cb.VARIANT_GENERAL)
+        want = run_trials(port, "port", model, servers, MASTER, 5, n, nobj, arr, srv)
+        ev, te, sw = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist()
+        assert res.status.abs().sum().item() == 0
+        for i, w in enumerate(want):
+            assert (ev[i], te[i], sw[i]) == (w.events, w.t_end, w.sum_wait), (model, i)
+
+
+def test_reneging_model_against_the_live_reference_build():
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/librefdrv.so did not travel with this snapshot")
+    ref.ref_set_param.argtypes = [C.c_int, C.c_double]
+    servers, think, srv, pat, T, n = 1200, 3.0, 1.0, 0.8, 30, 24
+    ref.ref_set_param(0, pat)
+    want = run_trials(ref, "ref", 16, servers, MASTER, 100, n, T, think, srv, par=1)
+    ref.ref_set_param(0, 0.0)
+    res = cb.run_trials(n, arr_mean=think, srv_mean=srv, num_objects=T, master_seed=MASTER, first_trial=100,
+                        model=cb.MODEL_RENEGE, servers=servers, params=[pat])
+    assert res.status.abs().sum().item() == 0
+    ev, te, sw, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist(), res.counters.cpu().tolist()
+    for i, w in enumerate(want):
+        assert (ev[i], te[i], sw[i], cnt[i][:4]) == (w.events, w.t_end, w.sum_wait, list(w.counter)[:4]), i
+        assert cnt[i][6] == 1 and cnt[i][7] == servers          # the key map was in use; every process was created
+
+
+def _model_library(stem):
+    sys.path.insert(0, str(ROOT / "scripts"))
+    so = ROOT / "cimba_b200/lib/models" / f"lib{stem}.so"
+    if not so.exists():                                 # built by __graft_entry__.build(); nvcc is on the GPU box too
+        import build_model
+        build_model.build(ROOT / "examples" / f"{stem}.cu")
+    return so
+
+
+def test_a_user_built_model_library_loads_and_matches_the_builtin_model():
+    mid = cb.load_model(_model_library("mm1_user_model"))
+    assert mid >= cb.MODEL_USER_BASE and cb.lib.cimba_b200_model_name(mid) == b"mm1 (user build)"
+    case = GOLD["cases"][0]
+    n = len(case["trials"])
+    compare(case, run_case(case, mid, 0, n), n)
+    # ... and through the host-buffer entry point, like any built-in model
+    exp = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    exp["arr_mean"], exp["srv_mean"] = float.fromhex(case["arr_mean"]), float.fromhex(case["srv_mean"])
+    cb.cimba_run_experiment(exp, model=mid, num_objects=case["num_objects"], master_seed=MASTER)
+    assert [int(v) for v in exp["events"]] == [t["events"] for t in case["trials"]]
+
+
+def test_a_model_that_exists_only_as_a_user_library_matches_the_reference():
+    """examples/tandem_model.cuh: two stations, a bounded buffer, a put that blocks - nowhere in the library."""
+    mid = cb.load_model(_model_library("tandem_user_model"))
+    for case in [c for c in GOLD["cases"] if c["model"] == 17]:
+        n = len(case["trials"])
+        compare(case, run_case(case, mid, 0, n), n)
+
+
+def test_unknown_model_ids_and_bad_libraries_are_refused():
+    with pytest.raises(cb.CimbaError):
+        cb.run_trials(4, arr_mean=1.0, srv_mean=1.0, num_objects=10, master_seed=1, model=cb.MODEL_USER_BASE + 999)
+    with pytest.raises(cb.CimbaError):
+        cb.load_model(ROOT / "oracle/liboracle_port.so")        # a library, but not a model
