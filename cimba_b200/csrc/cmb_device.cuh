@@ -658,8 +658,10 @@ struct Sim {
         if (nproc == proc_cap) {
             Process *bigger = (Process *)arena.alloc((uint64_t)(2u * proc_cap) * sizeof(Process));
             if (bigger == nullptr) {
+                // no memory: the trial is void from here (flagged; the dispatcher stops it at its next step).  Hand back
+                // an index that exists, so that model code which goes on to touch "the new process" stays in bounds.
                 status |= TRIAL_ERR_ARENA;
-                return NIL;
+                return nproc - 1u;
             }
             for (uint32_t i = 0u; i < nproc; i++) bigger[i] = proc[i];
             proc = bigger;
@@ -697,7 +699,7 @@ struct Sim {
 
     CMB_FN void process_start(uint32_t pid)             // :127-135: a FINISHED process may be started again
     {
-        if (pid == NIL) return;                         // process_create found no memory: the trial is flagged and will not run
+        if (status & TRIAL_ERR_ARENA) return;           // a void trial (a container could not grow) schedules nothing more
         schedule(ACT_CMB_START, pid, 0, now, proc[pid].prio);
     }
 

@@ -17,7 +17,7 @@ namespace cmb {
 // cimba_b200_device_job &)); the default suits models with a handful of processes.
 template <class Model, class = void>
 struct ArenaNeed {
-    static uint64_t per_trial(const cimba_b200_device_job &) { return 8192u; }
+    static uint64_t per_trial(const cimba_b200_device_job &) { return 32768u; }
 };
 template <class Model>
 struct ArenaNeed<Model, decltype((void)Model::arena_bytes_per_trial(*(const cimba_b200_device_job *)nullptr))> {

@@ -15,6 +15,13 @@ struct MMC {
     double   sum_wait;
     enum : uint32_t { SOURCE, CUSTOMER };
 
+    // growth memory of one trial: a process record per customer alive at once (a few dozen at rho = 0.8, more in
+    // overload), the wait list, an event list of servers + 2 entries - and as much again for what doubling leaves behind
+    static uint64_t arena_bytes_per_trial(const cimba_b200_device_job &job)
+    {
+        return 65536u + (uint64_t)(job.servers > 0 ? job.servers : 1) * 512u;
+    }
+
     CMB_FN void customer(cmb::Sim &sim, uint32_t me, int64_t sig)
     {
         MMC &m = *this;
