@@ -293,7 +293,7 @@ struct HashHeap {
         t.link = link;
         tag[at] = t;
         if (map_on) {
-            if (map_used + 1u > cap() + (cap() >> 1)) map_rebuild();     // keep never-used slots around: probes stay short
+            if (map_used + 1u >= (cap() << 1) - (cap() >> 2)) map_rebuild();    // nearly every slot has held a key: drop the tombstones
             else map_insert(at);
         }
         sift_up(at);
@@ -398,6 +398,9 @@ enum : uint32_t {
     ACT_CMB_USER = 32u,         // first action id a model may use for its own events (cmb_event_schedule)
 };
 
+// what a process body asks of the dispatcher when it returns (Sim::cmd)
+enum : uint32_t { CMD_NONE = 0u, CMD_HOLD = 1u, CMD_HOLD_EXPONENTIAL = 2u, CMD_GUARD_WAIT = 3u, CMD_EXIT = 4u };
+
 // demands a guard entry can carry (the reference stores a predicate function + context, src/cmb_resourceguard.c:125-152)
 enum : uint32_t {
     DEMAND_QUEUE_CONTENT = 1u,  // has_content,  src/cmb_objectqueue.c:119-133
@@ -495,6 +498,17 @@ struct Sim {
     Node           node_inline[8];
     uint64_t      *scratch;
     uint32_t       scratch_cap;
+    // The blocking call a process body ended on.  The body only RECORDS it and returns; the dispatcher carries it out
+    // right after, in code that every lane of the warp passes together - the event-list insert, the wait-list insert
+    // and the variate draw are the expensive parts of an event, and lanes whose trials are in different process bodies
+    // share them this way.  Nothing happens between the body's return and the command, so the order of key issues and
+    // random draws is the reference's.
+    uint32_t       cmd;
+    uint32_t       cmd_demand;
+    int32_t        cmd_ctx;
+    double         cmd_value;           // hold: the duration (or the mean of the exponential to draw); exit: unused
+    int64_t        cmd_exit;
+    resourceguard *cmd_guard;
 
     // ---------------------------------------------------------------- set-up
     CMB_FN void init(uint64_t seed, const ZigHot *tables, const Arena &a)
@@ -518,6 +532,7 @@ struct Sim {
         node_free = NIL;
         scratch = nullptr;
         scratch_cap = 0u;
+        cmd = 0u;
     }
 
     // ---------------------------------------------------------------- node pool
@@ -1267,6 +1282,19 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
             sim.current = pid;
             m.process(sim, pid, sim.proc[pid].kind, (int64_t)ev.arg);
             sim.current = NIL;
+            // the blocking call the body stopped at, carried out where the warp is together again
+            const uint32_t cmd = sim.cmd;
+            sim.cmd = CMD_NONE;
+            if (cmd == CMD_HOLD || cmd == CMD_HOLD_EXPONENTIAL) {
+                const double dur = cmd == CMD_HOLD ? sim.cmd_value : gp_exponential(sim.rng, *sim.hot, sim.cmd_value);
+                sim.hold_begin(pid, dur);
+            }
+            else if (cmd == CMD_GUARD_WAIT) {
+                sim.guard_wait_begin(*sim.cmd_guard, pid, sim.cmd_demand, sim.cmd_ctx);
+            }
+            else if (cmd == CMD_EXIT) {
+                process_exit(sim, m, pid, sim.cmd_exit);
+            }
         }
     }
 }
@@ -1280,16 +1308,24 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 // interrupt's signal).  Arguments are evaluated again after a wait: pass variables, not expressions with side effects
 // (cmb_time() after a wait is a different time - stamp first, then put the stamp).
 #define CMB_PROCESS_BEGIN        switch (sim.proc[me].pc) { case 0u:
-#define CMB_PROCESS_END          } cimba_b200::cmb::process_exit(sim, m, me, 0); return;
+#define CMB_PROCESS_END          } sim.cmd = cimba_b200::cmb::CMD_EXIT; sim.cmd_exit = 0; return;
 #define CMB_YIELD_AT_(n)         do { sim.proc[me].pc = (n); return; case (n):; } while (0)
 #define CMB_YIELD_()             CMB_YIELD_AT_(__COUNTER__ + 1u)
 
+// cmb_resourceguard_wait up to its yield: the wait-list insert is left to the dispatcher
+#define CMB_GUARD_WAIT_(g, demand, ctx) \
+    do { sim.cmd_guard = &(g); sim.cmd_demand = (demand); sim.cmd_ctx = (ctx); sim.cmd = cimba_b200::cmb::CMD_GUARD_WAIT; CMB_YIELD_(); } while (0)
+
 // cmb_process_hold(dur)
-#define CMB_PROCESS_HOLD(dur)    do { sim.hold_begin(me, (dur)); CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)
+#define CMB_PROCESS_HOLD(dur)    do { sim.cmd_value = (dur); sim.cmd = cimba_b200::cmb::CMD_HOLD; CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)
+// cmb_process_hold(cmb_random_exponential(mean)) with the draw left to the dispatcher, where the whole warp draws together
+// (same stream position: nothing draws between the body's return and the dispatcher)
+#define CMB_PROCESS_HOLD_EXPONENTIAL(mean) \
+    do { sim.cmd_value = (mean); sim.cmd = cimba_b200::cmb::CMD_HOLD_EXPONENTIAL; CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)
 // cmb_process_yield(): wait for whatever comes (a timer, a resume, an interrupt)
 #define CMB_PROCESS_YIELD()      do { CMB_YIELD_(); } while (0)
 // cmb_process_exit(value)
-#define CMB_PROCESS_EXIT(value)  do { cimba_b200::cmb::process_exit(sim, m, me, (value)); return; } while (0)
+#define CMB_PROCESS_EXIT(value)  do { sim.cmd = cimba_b200::cmb::CMD_EXIT; sim.cmd_exit = (value); return; } while (0)
 // cmb_process_wait_process(other) / cmb_process_wait_event(handle)
 #define CMB_PROCESS_WAIT_PROCESS(other) do { sim.wait_process_begin(me, (other)); CMB_YIELD_(); } while (0)
 #define CMB_PROCESS_WAIT_EVENT(handle)  do { sim.wait_event_begin(me, (handle)); CMB_YIELD_(); } while (0)
@@ -1298,14 +1334,14 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define CMB_OBJECTQUEUE_PUT(q, obj) \
     do { for (;;) { \
         if (cimba_b200::cmb::objectqueue_try_put(sim, m, (q), (uint64_t)(obj))) { sig = CMB_PROCESS_SUCCESS; break; } \
-        sim.guard_wait_begin((q).rear, me, cimba_b200::cmb::DEMAND_QUEUE_SPACE, 0); CMB_YIELD_(); \
+        CMB_GUARD_WAIT_((q).rear, cimba_b200::cmb::DEMAND_QUEUE_SPACE, 0); \
         sig = sim.guard_wait_end((q).rear, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } } while (0)
 
 // sig = cmb_objectqueue_get(&q, &obj)  (:203-260); obj is a uint64_t lvalue (0 when interrupted)
 #define CMB_OBJECTQUEUE_GET(q, obj) \
     do { for (;;) { \
         if (cimba_b200::cmb::objectqueue_try_get(sim, m, (q), (obj))) { sig = CMB_PROCESS_SUCCESS; break; } \
-        sim.guard_wait_begin((q).front, me, cimba_b200::cmb::DEMAND_QUEUE_CONTENT, 0); CMB_YIELD_(); \
+        CMB_GUARD_WAIT_((q).front, cimba_b200::cmb::DEMAND_QUEUE_CONTENT, 0); \
         sig = sim.guard_wait_end((q).front, me, sig); if (sig != CMB_PROCESS_SUCCESS) { (obj) = 0u; break; } } } while (0)
 
 // sig = cmb_resourcepool_acquire(&rp, amount) / cmb_resourcepool_preempt(&rp, amount)   (src/cmb_resourcepool.c:362-554)
@@ -1313,7 +1349,7 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
     do { sim.proc[me].fr[0] = cimba_b200::cmb::resourcepool_held_by_process(sim, (rp), me); sim.proc[me].fr[1] = (uint64_t)(amount); \
         for (;;) { \
         if (cimba_b200::cmb::pool_acquire_step(sim, m, (rp), me, (pre))) { sig = CMB_PROCESS_SUCCESS; break; } \
-        sim.guard_wait_begin((rp).guard, me, cimba_b200::cmb::DEMAND_POOL_AVAILABLE, 0); CMB_YIELD_(); \
+        CMB_GUARD_WAIT_((rp).guard, cimba_b200::cmb::DEMAND_POOL_AVAILABLE, 0); \
         sig = sim.guard_wait_end((rp).guard, me, sig); \
         if (sig != CMB_PROCESS_SUCCESS) { cimba_b200::cmb::pool_acquire_rollback(sim, m, (rp), me, sig); break; } } } while (0)
 #define CMB_RESOURCEPOOL_ACQUIRE(rp, amount) CMB_RESOURCEPOOL_ACQUIRE_(rp, amount, false)
@@ -1324,13 +1360,13 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define CMB_RESOURCE_ACQUIRE(r) \
     do { for (;;) { \
         if ((r).holder == cimba_b200::cmb::NIL) { cimba_b200::cmb::resource_grab(sim, (r), me); sig = CMB_PROCESS_SUCCESS; break; } \
-        sim.guard_wait_begin((r).guard, me, cimba_b200::cmb::DEMAND_RESOURCE_FREE, 0); CMB_YIELD_(); \
+        CMB_GUARD_WAIT_((r).guard, cimba_b200::cmb::DEMAND_RESOURCE_FREE, 0); \
         sig = sim.guard_wait_end((r).guard, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } } while (0)
 #define CMB_RESOURCE_RELEASE(r)  cimba_b200::cmb::resource_release(sim, m, (r), me)
 
 // sig = cmb_condition_wait(&c, predicate id, ctx)   (src/cmb_condition.c:63-80); spurious wake-ups are the caller's to re-test
 #define CMB_CONDITION_WAIT(c, demand_id, ctx) \
-    do { sim.guard_wait_begin((c).guard, me, (demand_id), (ctx)); CMB_YIELD_(); sig = sim.guard_wait_end((c).guard, me, sig); } while (0)
+    do { CMB_GUARD_WAIT_((c).guard, (demand_id), (ctx)); sig = sim.guard_wait_end((c).guard, me, sig); } while (0)
 
 // the non-blocking calls, by their reference names
 #define cmb_time()                          (sim.now)

@@ -88,14 +88,32 @@ trial_kernel(const LaunchArgs a)
     arena.cursor = (unsigned long long *)a.arena_base;
     arena.bytes = a.arena_bytes;
 
+    // The per-trial control block (cmb::Sim + the model) lives in HBM, one per THREAD, taken from the arena when the
+    // thread meets its first trial and reused for its later ones.  Lanes of a warp are in different process bodies most
+    // of the time, so what matters is that ONE lane's accesses are compact: a 40-byte heap tag is two 32-byte sectors
+    // of a block laid out per trial, but ten of a stack frame, which the hardware interleaves across the 32 lanes word
+    // by word (measured on the first form of this kernel: 1.5 useful bytes per sector moved, profiles/r02_engine.md).
+    struct Control {
+        Sim sim;
+        Model m;
+    };
+    Control *ctl = nullptr;
+
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; trial < a.num_trials; trial += stride) {
         if (a.only_flagged != 0u) {
             if ((a.status[trial] & a.only_flagged) == 0u) continue;
             if (a.diag != nullptr) atomicAdd(a.diag + 2, 1ull);
         }
-        Sim sim;
-        Model m;
+        if (ctl == nullptr) {
+            ctl = (Control *)arena.alloc(sizeof(Control));
+            if (ctl == nullptr) {                       // not even room for the control block: every trial of this thread is void
+                if (a.status) a.status[trial] = TRIAL_ERR_ARENA;
+                continue;
+            }
+        }
+        Sim &sim = ctl->sim;
+        Model &m = ctl->m;
         TrialIn in;
         TrialOut out;
         in.arr_mean = a.arr_mean[trial];

@@ -20,7 +20,7 @@ struct MM1 {
         MM1 &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
-            CMB_PROCESS_HOLD(cmb_random_exponential(arr_mean));
+            CMB_PROCESS_HOLD_EXPONENTIAL(arr_mean);
             stamp = (uint64_t)__double_as_longlong(cmb_time());
             CMB_OBJECTQUEUE_PUT(queue, stamp);
         }
@@ -33,7 +33,7 @@ struct MM1 {
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_OBJECTQUEUE_GET(queue, object);
-            CMB_PROCESS_HOLD(cmb_random_exponential(srv_mean));
+            CMB_PROCESS_HOLD_EXPONENTIAL(srv_mean);
             sum_wait += cmb_time() - __longlong_as_double((long long)object);
             obj_cnt += 1u;
         }

@@ -27,7 +27,7 @@ struct MMC {
         MMC &m = *this;
         CMB_PROCESS_BEGIN
         CMB_RESOURCEPOOL_ACQUIRE(pool, 1u);
-        CMB_PROCESS_HOLD(cmb_random_exponential(srv_mean));
+        CMB_PROCESS_HOLD_EXPONENTIAL(srv_mean);
         CMB_RESOURCEPOOL_RELEASE(pool, 1u);
         sum_wait += cmb_time() - sim.proc[me].f[0];                 // f[0] = the customer's arrival time
         objects += 1u;
@@ -41,7 +41,7 @@ struct MMC {
         MMC &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
-            CMB_PROCESS_HOLD(cmb_random_exponential(arr_mean));
+            CMB_PROCESS_HOLD_EXPONENTIAL(arr_mean);
             {
                 uint32_t cu = free_list;
                 if (cu != cmb::NIL) {

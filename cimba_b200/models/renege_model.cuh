@@ -34,14 +34,14 @@ struct Renege {
         Renege &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
-            CMB_PROCESS_HOLD(cmb_random_exponential(think_mean));
+            CMB_PROCESS_HOLD_EXPONENTIAL(think_mean);
             sim.proc[me].f[0] = cmb_time();                         // joined the line
             (void)cmb_process_timer_add(cmb_random_exponential(patience_mean), TIMER_RENEGING);
             CMB_RESOURCEPOOL_ACQUIRE(clerks, 1u);
             if (sig == CMB_PROCESS_SUCCESS) {
                 cmb_process_timers_clear(me);
                 sum_wait += cmb_time() - sim.proc[me].f[0];
-                CMB_PROCESS_HOLD(cmb_random_exponential(service_mean));
+                CMB_PROCESS_HOLD_EXPONENTIAL(service_mean);
                 CMB_RESOURCEPOOL_RELEASE(clerks, 1u);
                 served += 1u;
             }

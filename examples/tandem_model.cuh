@@ -21,7 +21,7 @@ struct Tandem {
         Tandem &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
-            CMB_PROCESS_HOLD(cmb_random_exponential(arr_mean));
+            CMB_PROCESS_HOLD_EXPONENTIAL(arr_mean);
             stamp = (uint64_t)__double_as_longlong(cmb_time());
             CMB_OBJECTQUEUE_PUT(first, stamp);
         }

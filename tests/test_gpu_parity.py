@@ -191,16 +191,22 @@ def test_per_trial_parameters(cb, port):
         assert (ev[i], te[i], sw[i]) == (r.events, r.t_end, r.sum_wait), i
 
 
-def test_queue_spill_path_and_overflow_flag(cb, port):
-    """rho > 1: the queue outgrows the 32-entry shared-memory window (spill ring in
-    HBM, still bit-exact) and finally the spill ring too (trial flagged, no crash)."""
+def test_queue_spill_path_and_beyond(cb, port):
+    """rho > 1: the queue outgrows the 32-entry shared-memory window (spill ring in HBM, still bit-exact) and
+    finally the spill ring too - then the repair pass re-runs the trial on the general engine, whose queue grows
+    like the reference's CMB_UNLIMITED one: no flag, the reference's answer.  (Without a status array there is
+    nothing to repair by; the unfused A/B kernel, variant 1, has no repair pass and still flags.)"""
     res = cb.run_trials(64, arr_mean=0.8, srv_mean=1.0, num_objects=1500, master_seed=3)
     want = run_trials(port, "port", 0, 1, 3, 0, 64, 1500, 0.8, 1.0)
     assert max(w.max_queue for w in want) > 200          # deep into the spill ring
     _compare(res, want, "spill")
     assert res.max_queue.cpu().tolist() == [w.max_queue for w in want]
-    with_overflow = cb.run_trials(8, arr_mean=0.25, srv_mean=1.0, num_objects=4000, master_seed=3)
-    assert all(s & 1 for s in with_overflow.status.cpu().tolist())
+    beyond = cb.run_trials(8, arr_mean=0.25, srv_mean=1.0, num_objects=4000, master_seed=3)
+    want = run_trials(port, "port", 0, 1, 3, 0, 8, 4000, 0.25, 1.0)
+    assert min(w.max_queue for w in want) > 32 + 512
+    _compare(beyond, want, "beyond the ring")
+    flagged = cb.run_trials(8, arr_mean=0.25, srv_mean=1.0, num_objects=4000, master_seed=3, variant=1)
+    assert all(s & 1 for s in flagged.status.cpu().tolist())
 
 
 def test_host_buffer_experiment_in_place(cb, port):
