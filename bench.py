@@ -605,6 +605,11 @@ def main():
         roofline["calibration"] = cal.get("source")
         roofline["peak_source"] = f"4 warp schedulers x {sms} SMs x {sm_mhz} MHz (nvidia-smi median during the timed region)"
         roofline["warp_instructions_per_event"] = inst / max(1, events_rank)
+        roofline["issue_active_pct_ncu"] = cal.get("issue_active_pct_under_ncu")
+        roofline["alu_pipe_pct_ncu"] = cal.get("alu_pipe_pct_under_ncu")
+        roofline["frac_note"] = ("frac = executed warp-instructions / (schedulers x clock x time), measured in this run; ncu's own "
+                                 "smsp__issue_active of the calibration launch is beside it (it counts issue-port cycles, which "
+                                 "the half-rate FP64 and ALU instructions of this loop hold for more than one)")
     if tr and args.variant == 0 and args.mapping == 1:
         roofline["traffic"] = tr["dram_bytes_per_event"] * events_rank
         roofline["traffic_source"] = tr["source"]
