@@ -190,9 +190,17 @@ mm1_kernel(const QueueArgs a)
         const uint32_t head_slot = win + (served & WMASK) * ROW;
         const double head_stamp = lds_f64(head_slot);   // harmless when the ring is empty
         if (take) stamp = head_stamp;
+#ifdef MM1_REFILL_BRANCH        // A/B: a warp-wide vote + branch around the refill instead of six predicated-off instructions per step
+        if (__any_sync(FULL, take & (produced - served > (uint32_t)QUEUE_WINDOW))) {
+            if (take & (produced - served > (uint32_t)QUEUE_WINDOW)) {
+                sts_f64(head_slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
+            }
+        }
+#else
         if (take & (produced - served > (uint32_t)QUEUE_WINDOW)) {      // rare: refill the freed slot from HBM
             sts_f64(head_slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
         }
+#endif
         if (take) served++;
 
         // ---------------- hold: consume the look-ahead variate, insert the wake-up
