@@ -88,16 +88,14 @@ trial_kernel(const LaunchArgs a)
     arena.cursor = (unsigned long long *)a.arena_base;
     arena.bytes = a.arena_bytes;
 
-    // The per-trial control block (cmb::Sim + the model) lives in HBM, one per THREAD, taken from the arena when the
-    // thread meets its first trial and reused for its later ones.  Lanes of a warp are in different process bodies most
-    // of the time, so what matters is that ONE lane's accesses are compact: a 40-byte heap tag is two 32-byte sectors
-    // of a block laid out per trial, but ten of a stack frame, which the hardware interleaves across the 32 lanes word
-    // by word (measured on the first form of this kernel: 1.5 useful bytes per sector moved, profiles/r02_engine.md).
-    struct Control {
-        Sim sim;
-        Model m;
-    };
-    Control *ctl = nullptr;
+    // The per-trial control block (cmb::Sim + the model) is the thread's stack frame, i.e. local memory: the hardware
+    // interleaves it across the lanes word by word and - what decides it - caches it WRITE-BACK in L1.  Measured
+    // (profiles/r02_engine.md): with the block in the HBM arena instead (compact per trial, but global stores write through
+    // and the L1 hit rate fell from 98.6 % to 56 %) the long-scoreboard stall per issued instruction went from 3.4 to 108
+    // and M/M/1 ran 2.1x slower.  Grown containers (heaps past their inline slots, the process table, queues) live in
+    // the arena either way.
+    Sim sim;
+    Model m;
 
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; trial < a.num_trials; trial += stride) {
@@ -105,15 +103,6 @@ trial_kernel(const LaunchArgs a)
             if ((a.status[trial] & a.only_flagged) == 0u) continue;
             if (a.diag != nullptr) atomicAdd(a.diag + 2, 1ull);
         }
-        if (ctl == nullptr) {
-            ctl = (Control *)arena.alloc(sizeof(Control));
-            if (ctl == nullptr) {                       // not even room for the control block: every trial of this thread is void
-                if (a.status) a.status[trial] = TRIAL_ERR_ARENA;
-                continue;
-            }
-        }
-        Sim &sim = ctl->sim;
-        Model &m = ctl->m;
         TrialIn in;
         TrialOut out;
         in.arr_mean = a.arr_mean[trial];
