@@ -611,10 +611,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         if (on_chip_first) {
             const size_t smem = (HARBOR_BLOCK_ON_CHIP / 32) * sizeof(HarborStateOnChip);
             const void *fn = trace ? (const void *)harbor_on_chip_kernel<true> : (const void *)harbor_on_chip_kernel<false>;
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int dev = 0, sms = 148, per_sm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            CUDA_TRY(cudaGetDevice(&dev));
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, HARBOR_BLOCK_ON_CHIP, smem);
             if (oe != cudaSuccess || per_sm < 1) per_sm = 4;
             const uint64_t per_block = HARBOR_BLOCK_ON_CHIP / 32;
@@ -707,8 +707,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
                            : lanes == 16 ? (trace ? (const void *)hold_group_kernel<16, true> : (const void *)hold_group_kernel<16, false>)
                                          : (trace ? (const void *)hold_group_kernel<8, true> : (const void *)hold_group_kernel<8, false>);
             int dev = 0, sms = 148, per_sm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            CUDA_TRY(cudaGetDevice(&dev));
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, DEEP_BLOCK, 0);
             if (oe != cudaSuccess || per_sm < 1) per_sm = 8;
             const uint64_t trials_per_block = (uint64_t)(DEEP_BLOCK / 32) * (uint64_t)(32 / lanes);
@@ -728,8 +728,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         // persistent one-warp CTAs: exactly as many as are resident at once (shared memory
         // bounds it at ~12 per SM), so no CTA waits for another to retire
         int dev = 0, sms = 148, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         cudaError_t oe = trace
             ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_kernel<true>, 32, HOLD_SMEM_BYTES)
             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hold_kernel<false>, 32, HOLD_SMEM_BYTES);
@@ -908,6 +908,16 @@ int cimba_b200_rng_draws_ex(uint64_t seed, int kind, const double *params, uint3
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
     DrawParams par{};
     for (uint32_t i = 0; i < num_params; i++) par.v[i] = params[i];
+    // kinds that carry an array inline: {n, v[n]} (13 hypoexponential, 29 loaded dice, 30 alias), {n, m[n], p[n]} (14
+    // hyperexponential); 26 / 27 / 33 read {n, p}.  The kernel indexes par.v[] by n: refuse what does not fit.
+    if (kind == 13 || kind == 14 || kind == 29 || kind == 30 || kind == 26 || kind == 27 || kind == 33) {
+        const double n = num_params > 0u ? params[0] : 0.0;
+        if (!(n >= 1.0) || !(n <= 4294967295.0) || n != floor(n))
+            return fail(CIMBA_B200_EINVAL, "params[0] must be a count >= 1 for this distribution");
+        const uint64_t cnt = (uint64_t)n;
+        const uint64_t need = (kind == 14) ? 1u + 2u * cnt : ((kind == 26 || kind == 27 || kind == 33) ? 2u : 1u + cnt);
+        if (need > num_params) return fail(CIMBA_B200_EINVAL, "params: the count in params[0] does not fit num_params");
+    }
     if (kind == 30) {
         const uint32_t cnt = num_params > 0u ? (uint32_t)params[0] : 0u;
         if (cnt == 0u || cnt + 1u > num_params) return fail(CIMBA_B200_EINVAL, "alias: params = {n, p[0..n-1]}");
@@ -1039,7 +1049,17 @@ int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const 
     if (d->off_arr_mean == CIMBA_B200_NO_FIELD || d->off_srv_mean == CIMBA_B200_NO_FIELD)
         return fail(CIMBA_B200_EINVAL, "off_arr_mean and off_srv_mean are required");
     if (cimba_b200_device_count() <= 0) return fail(CIMBA_B200_ENODEVICE, "no CUDA device");
-    if (d->device >= 0) CUDA_TRY(cudaSetDevice(d->device));
+    // the caller's current device is the caller's: put it back on every way out
+    struct DeviceGuard {
+        int before = -1;
+        bool armed = false;
+        ~DeviceGuard() { if (armed) (void)cudaSetDevice(before); }
+    } restore;
+    if (d->device >= 0) {
+        CUDA_TRY(cudaGetDevice(&restore.before));
+        CUDA_TRY(cudaSetDevice(d->device));
+        restore.armed = restore.before != d->device;
+    }
 
     const uint64_t n = num_trials;
     char *base = (char *)array;

@@ -1307,7 +1307,7 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 // the reference's calls.  `sig` holds the call's return value afterwards (CMB_PROCESS_SUCCESS, a timer's or an
 // interrupt's signal).  Arguments are evaluated again after a wait: pass variables, not expressions with side effects
 // (cmb_time() after a wait is a different time - stamp first, then put the stamp).
-#define CMB_PROCESS_BEGIN        switch (sim.proc[me].pc) { case 0u:
+#define CMB_PROCESS_BEGIN        (void)&m; switch (sim.proc[me].pc) { case 0u:
 #define CMB_PROCESS_END          } sim.cmd = cimba_b200::cmb::CMD_EXIT; sim.cmd_exit = 0; return;
 #define CMB_YIELD_AT_(n)         do { sim.proc[me].pc = (n); return; case (n):; } while (0)
 #define CMB_YIELD_()             CMB_YIELD_AT_(__COUNTER__ + 1u)
