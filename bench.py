@@ -370,7 +370,7 @@ def secondary_configs(args, cb, torch, dist, dev, rank, world, barrier):
         host = usable_cpus()
         m, cols, rows, geom = awacs_terrain(load_port(), "port", AWACS_TERRAIN_SEED, 100.0, 100.0, max(1, host["cores"] // max(1, world)))
         cb.awacs_set_terrain(torch.from_numpy(m).to(dev), cols, rows, geom)
-        cb.awacs_run(8, duration_s=20, master_seed=1, device=dev)
+        cb.awacs_run(trials, duration_s=5, master_seed=1, device=dev)     # warm-up at full width (buffers, clocks)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

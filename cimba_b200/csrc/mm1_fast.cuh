@@ -190,17 +190,11 @@ mm1_kernel(const QueueArgs a)
         const uint32_t head_slot = win + (served & WMASK) * ROW;
         const double head_stamp = lds_f64(head_slot);   // harmless when the ring is empty
         if (take) stamp = head_stamp;
-#ifdef MM1_REFILL_BRANCH        // A/B: a warp-wide vote + branch around the refill instead of six predicated-off instructions per step
-        if (__any_sync(FULL, take & (produced - served > (uint32_t)QUEUE_WINDOW))) {
-            if (take & (produced - served > (uint32_t)QUEUE_WINDOW)) {
-                sts_f64(head_slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
-            }
-        }
-#else
+        // (measured: a warp-wide vote + branch around these six predicated-off instructions is SLOWER, 1111 vs 1026 ms
+        // per step - the vote sits on the critical path of every step; profiles/r02_mm1.md)
         if (take & (produced - served > (uint32_t)QUEUE_WINDOW)) {      // rare: refill the freed slot from HBM
             sts_f64(head_slot, spill[(served + QUEUE_WINDOW) & spill_mask]);
         }
-#endif
         if (take) served++;
 
         // ---------------- hold: consume the look-ahead variate, insert the wake-up
