@@ -44,6 +44,7 @@
 #include "../models/gg1_model.cuh"
 #include "../models/mmc_model.cuh"
 #include "../models/renege_model.cuh"
+#include "../models/hold_general_model.cuh"
 
 #include <dlfcn.h>      // cimba_b200_model_load: a model library built with scripts/build_model.py
 
@@ -109,6 +110,11 @@ bool mmc_goes_general(const cimba_b200_device_job *job)
 bool fast_goes_general(const cimba_b200_device_job *job)
 {
     return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_GENERAL;
+}
+
+bool hold_goes_general(const cimba_b200_device_job *job)
+{
+    return job->model == CIMBA_B200_MODEL_HOLD && job->variant == CIMBA_B200_VARIANT_GENERAL;
 }
 
 // models loaded with cimba_b200_model_load
@@ -335,6 +341,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
+    if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
     if (fast_goes_general(job)) {
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_for<models::MM1>(*job)
                                                   : cmb::workspace_bytes_for<models::GG1>(*job);
@@ -389,7 +396,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
     }
-    if (job->model == CIMBA_B200_MODEL_RENEGE || mmc_goes_general(job) || fast_goes_general(job)) {
+    if (job->model == CIMBA_B200_MODEL_RENEGE || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -399,6 +406,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             return launch_general<models::Renege>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Renege> launch");
         if (job->model == CIMBA_B200_MODEL_MMC)
             return launch_general<models::MMC>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MMC> launch");
+        if (job->model == CIMBA_B200_MODEL_HOLD)
+            return launch_general<models::HoldGeneral>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<HoldGeneral> launch");
         if (job->model == CIMBA_B200_MODEL_MM1)
             return launch_general<models::MM1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MM1> launch");
         return launch_general<models::GG1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<GG1> launch");

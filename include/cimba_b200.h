@@ -127,10 +127,10 @@ int cimba_b200_model_load(const char *path_to_model_library);
 /* The name the model registered, or NULL for an id nobody loaded. */
 const char *cimba_b200_model_name(int model_id);
 
-/* variant 3 of MODEL_MM1 / MODEL_GG1 / MODEL_MMC: the same model as cimba_b200/models/{mm1,gg1,mmc}_model.cuh run by the
- * general engine (growable event list, wait lists and queues; any number of servers).  The fast kernels' repair pass
+/* variant 16 of MODEL_MM1 / MODEL_GG1 / MODEL_MMC / MODEL_HOLD: the same model as cimba_b200/models/{mm1,gg1,mmc,hold_general}_model.cuh
+ * run by the general engine (growable event list, wait lists and queues; any number of servers).  The fast kernels' repair pass
  * and MODEL_MMC with more than 14 servers use it too. */
-#define CIMBA_B200_VARIANT_GENERAL 3
+#define CIMBA_B200_VARIANT_GENERAL 16
 
 /* Error codes */
 #define CIMBA_B200_OK         0

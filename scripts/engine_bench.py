@@ -2,7 +2,7 @@
 
     python scripts/engine_bench.py [--out gpurun_out/engine_bench.json]
 
-M/M/1 and M/M/c: the model written against the authoring surface (variant 3) vs the fast kernel (variant 0), same
+M/M/1 and M/M/c: the model written against the authoring surface (CIMBA_B200_VARIANT_GENERAL) vs the fast kernel (variant 0), same
 trials, same answers; the reneging model (1000 processes per trial) on its own."""
 import argparse
 import json

@@ -32,6 +32,8 @@ CASES = [
     (2, 3, 20000, 1 / 2.9, 1.0, [], 4),
     (2, 64, 20000, 1 / 60.0, 1.0, [], 4),         # more servers than the fast kernel's event list holds
     (2, 8, 20000, 1 / 8.4, 1.0, [], 4),           # overload: the wait list grows
+    (7, 50, 40, 1.0, 1.0, [], 4),                 # the hold model: 50 and 2000 workers + ticker + end event
+    (7, 2000, 6, 1.0, 1.0, [], 3),
     (16, 40, 300, 3.0, 1.0, [0.7], 4),
     (16, 1000, 60, 4.0, 1.0, [0.5], 4),
     (16, 1500, 40, 2.0, 1.0, [1.5], 3),
