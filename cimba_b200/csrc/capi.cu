@@ -45,6 +45,7 @@
 #include "../models/mmc_model.cuh"
 #include "../models/renege_model.cuh"
 #include "../models/hold_general_model.cuh"
+#include "../models/cheese_model.cuh"
 
 #include <dlfcn.h>      // cimba_b200_model_load: a model library built with scripts/build_model.py
 
@@ -340,6 +341,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
         return um ? um->workspace_bytes(job) : 0u;
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
+    if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
     if (fast_goes_general(job)) {
@@ -396,7 +398,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
     }
-    if (job->model == CIMBA_B200_MODEL_RENEGE || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job)) {
+    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -404,6 +406,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         unsigned char *ws = (unsigned char *)job->workspace;
         if (job->model == CIMBA_B200_MODEL_RENEGE)
             return launch_general<models::Renege>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Renege> launch");
+        if (job->model == CIMBA_B200_MODEL_POOL_RECORDED)
+            return launch_general<models::Cheese>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Cheese> launch");
         if (job->model == CIMBA_B200_MODEL_MMC)
             return launch_general<models::MMC>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MMC> launch");
         if (job->model == CIMBA_B200_MODEL_HOLD)

@@ -528,6 +528,7 @@ struct Sim {
     // and the variate draw are the expensive parts of an event, and lanes whose trials are in different process bodies
     // share them this way.  Nothing happens between the body's return and the command, so the order of key issues and
     // random draws is the reference's.
+    FlipCache      flips;               // cmb_random_flip's 64 cached coin flips (src/cmb_random.c: one draw serves 64 calls)
     uint32_t       cmd;
     uint32_t       cmd_demand;
     int32_t        cmd_ctx;
@@ -558,6 +559,8 @@ struct Sim {
         scratch = nullptr;
         scratch_cap = 0u;
         cmd = 0u;
+        flips.bits = 0u;
+        flips.pos = 0u;
     }
 
     // ---------------------------------------------------------------- node pool
@@ -889,8 +892,6 @@ struct Sim {
         return sig;
     }
 
-    // ---------------------------------------------------------------- cmb_process_priority_set for a process that waits nowhere
-    CMB_FN void priority_set(uint32_t pid, int64_t pri) { proc[pid].prio = (int32_t)pri; }
 };
 
 // built-in demands, evaluated against the guard's owner
@@ -1025,6 +1026,12 @@ CMB_FN void resourcepool_recording_start(Sim &sim, resourcepool &rp)
     rp.history.sample((double)rp.in_use, sim.now);
 }
 
+CMB_FN void resourcepool_recording_stop(Sim &sim, resourcepool &rp)
+{
+    if (rp.recording) rp.history.sample((double)rp.in_use, sim.now);
+    rp.recording = 0u;
+}
+
 CMB_FN void pool_sample(Sim &sim, resourcepool &rp)
 {
     if (rp.recording) rp.history.sample((double)rp.in_use, sim.now);
@@ -1149,9 +1156,25 @@ CMB_FN_NOINLINE void pool_drop_holder(Sim &sim, Model &m, resourcepool &rp, uint
     const uint32_t k = rp.holders.find(sim.arena, key);
     if (k != 0u) {
         rp.in_use -= (uint64_t)(uint32_t)rp.holders.tag[k].arg;
-        (void)rp.holders.remove(sim.arena, key);
-        pool_sample(sim, rp);
+        (void)rp.holders.remove(sim.arena, key);        // (no history sample here: resourcepool_drop_holder takes none)
         (void)guard_signal(sim, m, rp.guard);
+    }
+}
+
+// cmb_process_priority_set, src/cmb_process.c:150-198: the process' events move in the event list, its records in the
+// pools it holds from are reshuffled (reprioritize_holder, src/cmb_resourcepool.c:127-137).  An entry in a guard's wait list
+// is NOT found - the reference looks it up by process address while entries are keyed by sequence number.
+CMB_FN_NOINLINE void process_priority_set(Sim &sim, uint32_t pid, int64_t pri)
+{
+    sim.proc[pid].prio = (int32_t)pri;
+    for (uint32_t n = sim.proc[pid].awaits; n != NIL; n = sim.node[n].next) {
+        if (sim.node[n].a == AWAIT_TIME) (void)sim.event_reprioritize(sim.node[n].b, pri);
+    }
+    for (uint32_t n = sim.proc[pid].holds; n != NIL; n = sim.node[n].next) {
+        if (sim.node[n].a == HOLD_POOL) {
+            resourcepool &rp = *(resourcepool *)(uintptr_t)sim.node[n].b;
+            (void)rp.holders.reprioritize(sim.arena, (uint64_t)pid + 1u, 0.0, (int32_t)pri);
+        }
     }
 }
 
@@ -1416,6 +1439,11 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define cmb_process_timer_cancel(handle)    (sim.timer_cancel(me, (handle)))
 #define cmb_process_timers_clear(pid)       (sim.timers_clear(pid))
 #define cmb_process_priority(pid)           ((int64_t)sim.proc[pid].prio)
+#define cmb_process_priority_set(pid, pri)  (cimba_b200::cmb::process_priority_set(sim, (pid), (pri)))
+#define cmb_random_flip()                   (cimba_b200::rnd_flip(sim.rng, sim.flips))
+#define cmb_resourcepool_held_by_process(rp, pid) (cimba_b200::cmb::resourcepool_held_by_process(sim, (rp), (pid)))
+#define cmb_resourcepool_start_recording(rp) (cimba_b200::cmb::resourcepool_recording_start(sim, (rp)))
+#define cmb_resourcepool_stop_recording(rp)  (cimba_b200::cmb::resourcepool_recording_stop(sim, (rp)))
 #define cmb_process_status(pid)             (sim.proc[pid].status)
 #define cmb_event_schedule(act, subj, arg, t, prio) (sim.schedule((act), (subj), (arg), (t), (prio)))
 #define cmb_event_cancel(handle)            (sim.event_cancel(handle))

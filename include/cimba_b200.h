@@ -118,6 +118,14 @@ extern "C" {
                                     * signals [3] clerks busy at the end [4] stale wait-list entries [5] log2 of the event list's
                                     * final capacity [6] its key map active [7] processes.  sum_wait = time in line of the served */
 
+#define CIMBA_B200_MODEL_POOL_RECORDED 18 /* cimba_b200/models/cheese_model.cuh = test/test_resourcepool.c as it stands, on the general
+                                    * engine: three mice (cmb_process_priority_set + acquire 1..10 units), two rats (pre-empt), a cat
+                                    * interrupting them (cmb_random_flip), a pool of `servers` units with its usage history on, end
+                                    * event at t = num_objects.  counters[0..7] = the history's cmb_wtdsummary {count, min, max, m1,
+                                    * m2, m3, m4, wsum} (count as u64, the rest as bit patterns); objects = successful acquisitions.
+                                    * 20 units, 100 time units and the golden seed give test/reference/resourcepool.txt's
+                                    * "N 120  Mean 19.77  StdDev 1.147  Variance 1.316  Skewness -6.626  Kurtosis 46.75" */
+
 /* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
  * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */
 #define CIMBA_B200_MODEL_USER_BASE 1000

@@ -1124,6 +1124,175 @@ static void run_tandem_trial(struct ref_trial *t)
     cmb_objectqueue_destroy(w.second);
 }
 
+/* ------------------------------------------------- model 18: test/test_resourcepool.c as it stands
+ *
+ * The reference's own pool test (test/test_resourcepool.c:50-305) with counters instead of log lines and the pool's usage
+ * history on, as the test has it: three mice (priority_set + acquire 1..10), two rats (pre-empt 1..10), a cat interrupting
+ * a random rodent with INTERRUPTED or a signal in 10..100 (cmb_random_flip decides), on a pool of `servers` units; end event
+ * at t = num_objects.  With 20 units, 100 time units and cmb_random_initialize(0x34f05c64d7ad598f) this is
+ * test/reference/resourcepool.txt: "N 120  Mean 19.77  StdDev 1.147 ...".  The six process structs are contiguous here
+ * (the test mallocs them one after the other): the holders' tie-break by address is then by index.
+ * counters[0..7] = the usage history's cmb_wtdsummary {count, min, max, m1, m2, m3, m4, wsum} (bit patterns);
+ * objects = successful acquisitions + pre-emptions; sum_wait = sum of cmb_time() over them.
+ */
+#define CH_MICE 3u
+#define CH_RATS 2u
+#define CH_RODENTS (CH_MICE + CH_RATS)
+
+struct ch_world {
+    struct ref_trial *trl;
+    struct cmb_resourcepool *cheese;
+    struct cmb_process *proc;           /* mice, rats, cat: contiguous */
+};
+
+static void *ch_mouse_body(struct cmb_process *me, void *vw)
+{
+    struct ch_world *w = vw;
+    uint64_t held = 0u;
+    for (;;) {
+        const uint64_t req = (uint64_t)cmb_random_dice(1, 10);
+        const int64_t pri = cmb_random_dice(-10, 10);
+        cmb_process_priority_set(me, pri);
+        int64_t sig = cmb_resourcepool_acquire(w->cheese, req);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            held += req;
+            w->trl->objects += 1u;
+            w->trl->sum_wait += cmb_time();
+            sig = cmb_process_hold(cmb_random_exponential(1.0));
+            if (sig == CMB_PROCESS_SUCCESS) {
+                uint64_t rel = (uint64_t)cmb_random_dice(1, 10);
+                if (rel > held) {
+                    rel = held;
+                }
+                cmb_resourcepool_release(w->cheese, rel);
+                held -= rel;
+            }
+            else if (sig == CMB_PROCESS_PREEMPTED) {
+                held = 0u;
+            }
+        }
+        else if (sig == CMB_PROCESS_PREEMPTED) {
+            held = 0u;
+        }
+        sig = cmb_process_hold(cmb_random_exponential(1.0));
+        if (sig == CMB_PROCESS_PREEMPTED) {
+            held = 0u;
+        }
+    }
+}
+
+static void *ch_rat_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct ch_world *w = vw;
+    uint64_t held = 0u;
+    for (;;) {
+        const uint64_t req = (uint64_t)cmb_random_dice(1, 10);
+        int64_t sig = cmb_resourcepool_preempt(w->cheese, req);
+        if (sig == CMB_PROCESS_SUCCESS) {
+            held += req;
+            w->trl->objects += 1u;
+            w->trl->sum_wait += cmb_time();
+            sig = cmb_process_hold(cmb_random_exponential(1.0));
+            if (sig == CMB_PROCESS_SUCCESS) {
+                uint64_t rel = (uint64_t)cmb_random_dice(1, 10);
+                if (rel > held) {
+                    rel = held;
+                }
+                cmb_resourcepool_release(w->cheese, rel);
+                held -= rel;
+            }
+            else if (sig == CMB_PROCESS_PREEMPTED) {
+                held = 0u;
+            }
+        }
+        else if (sig == CMB_PROCESS_PREEMPTED) {
+            held = 0u;
+        }
+        sig = cmb_process_hold(cmb_random_exponential(1.0));
+        if (sig == CMB_PROCESS_PREEMPTED) {
+            held = 0u;
+        }
+    }
+}
+
+/* cmb_random_flip keeps 64 cached bits in a function-static thread-local that survives cmb_random_initialize
+ * (src/cmb_random.c:541-552): in the reference a trial's coin flips depend on what the previous trial on the same pthread
+ * left in the cache.  The device gives every trial a fresh cache - what the reference does for the first trial of a thread,
+ * and what its own golden run (one trial per process) sees.  To be an oracle for THAT, this driver counts its flips and
+ * uses up the leftover bits before a trial starts (no generator draw happens while the cache is non-empty). */
+static CMB_THREAD_LOCAL uint64_t ch_flips_taken = 0u;
+
+static int ch_flip(void)
+{
+    ch_flips_taken++;
+    return cmb_random_flip();
+}
+
+static void ch_flip_align(void)
+{
+    while ((ch_flips_taken & 63u) != 0u) {
+        (void)ch_flip();
+    }
+}
+
+static void *ch_cat_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct ch_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(1.0));
+        const long victim = cmb_random_dice(0, (long)CH_RODENTS - 1);
+        const int64_t loud = cmb_random_dice(10, 100);
+        const int64_t sig = ch_flip() ? CMB_PROCESS_INTERRUPTED : loud;
+        cmb_process_interrupt(&w->proc[victim], sig, 0);
+    }
+}
+
+static void ch_end_event(void *subject, void *object)
+{
+    cmb_unused(object);
+    struct ch_world *w = subject;
+    for (unsigned i = 0u; i <= CH_RODENTS; i++) {
+        cmb_process_stop(&w->proc[i], NULL);
+    }
+}
+
+static void run_cheese_trial(struct ref_trial *t)
+{
+    ch_flip_align();
+    struct ch_world *w = calloc(1, sizeof(*w));
+    w->trl = t;
+    w->cheese = cmb_resourcepool_create();
+    cmb_resourcepool_initialize(w->cheese, "Cheese", (uint64_t)t->servers);
+    cmb_resourcepool_start_recording(w->cheese);
+    w->proc = calloc(CH_RODENTS + 1u, sizeof(struct cmb_process));
+    for (unsigned i = 0u; i <= CH_RODENTS; i++) {
+        const int64_t pri = cmb_random_dice(-5, 5);
+        cmb_process_func *body = (i < CH_MICE) ? ch_mouse_body : ((i < CH_RODENTS) ? ch_rat_body : ch_cat_body);
+        cmb_process_initialize(&w->proc[i], "Rodent", body, w, pri);
+        cmb_process_start(&w->proc[i]);
+    }
+    (void)cmb_event_schedule(ch_end_event, w, NULL, (double)t->num_objects, 0);
+
+    pump_events(t);
+
+    cmb_resourcepool_stop_recording(w->cheese);
+    struct cmb_wtdsummary ws;
+    cmb_wtdsummary_initialize(&ws);
+    (void)cmb_timeseries_summarize(cmb_resourcepool_get_history(w->cheese), &ws);
+    const struct cmb_datasummary *ds = (const struct cmb_datasummary *)&ws;
+    const double v[7] = { ds->min, ds->max, ds->m1, ds->m2, ds->m3, ds->m4, ws.wsum };
+    t->counter[0] = ds->count;
+    memcpy(&t->counter[1], v, sizeof(v));
+    for (unsigned i = 0u; i <= CH_RODENTS; i++) {
+        cmb_process_terminate(&w->proc[i]);
+    }
+    free(w->proc);
+    cmb_resourcepool_destroy(w->cheese);
+    free(w);
+}
+
 /* ------------------------------------------------- model 8: timers, waits, observers
  *
  * The remaining asynchronous calls of cmb_process / cmb_event / cmb_resourceguard in one
@@ -1892,7 +2061,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 17) {
+    if (t->model == 18) {
+        run_cheese_trial(t);
+    }
+    else if (t->model == 17) {
         run_tandem_trial(t);
     }
     else if (t->model == 16) {

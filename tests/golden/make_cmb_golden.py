@@ -38,6 +38,8 @@ CASES = [
     (16, 1000, 60, 4.0, 1.0, [0.5], 4),
     (16, 1500, 40, 2.0, 1.0, [1.5], 3),
     (17, 4, 20000, 1.3, 1.0, [], 4),
+    (18, 20, 100, 1.0, 1.0, [], 6),               # test/test_resourcepool.c as it stands (20 units, 100 time units)
+    (18, 7, 300, 1.0, 1.0, [], 4),
     (17, 1, 20000, 1.05, 1.0, [], 4),
 ]
 
@@ -55,7 +57,7 @@ def main():
             _, keys, times = trace_trial(ref, "ref", model, servers, ref.ref_fmix64(MASTER, i), nobj, arr, srv, TRACE)
             h = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
             trials.append({"events": r.events, "objects": r.objects, "t_end": float(r.t_end).hex(), "sum_wait": float(r.sum_wait).hex(),
-                           "counters": list(r.counter)[:4], "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
+                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model == 18), "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
         out["cases"].append({"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
                              "srv_mean": float(srv).hex(), "params": params, "trials": trials})
         print(model, servers, nobj, [t["events"] for t in trials])

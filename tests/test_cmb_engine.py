@@ -11,7 +11,7 @@ from pathlib import Path
 
 import pytest
 
-from cmb_cases import GOLD, MASTER, TRACE, case_id, check_trial
+from cmb_cases import GOLD, MASTER, RESOURCEPOOL_GOLDEN_LINE, TRACE, case_id, check_trial, inverse_fmix64, wtdsummary_line
 
 ROOT = Path(__file__).resolve().parents[1]
 
@@ -36,12 +36,12 @@ def host(tmp_path_factory):
     return f
 
 
-def run_host(f, c, n, arena=1 << 26, first=0):
+def run_host(f, c, n, arena=1 << 26, first=0, master=MASTER):
     out = (HostResult * n)()
     par = (C.c_double * max(1, len(c["params"])))(*c["params"])
     keys = (C.c_uint64 * (n * TRACE))()
     times = (C.c_double * (n * TRACE))()
-    rc = f(c["model"], c["servers"], MASTER, first, n, c["num_objects"], float.fromhex(c["arr_mean"]),
+    rc = f(c["model"], c["servers"], master, first, n, c["num_objects"], float.fromhex(c["arr_mean"]),
            float.fromhex(c["srv_mean"]), par, len(c["params"]), arena, TRACE, keys, times, out)
     assert rc == 0
     return out, keys, times
@@ -93,3 +93,14 @@ def test_hashheap_growth_and_key_map(host):
     rn = next(c for c in GOLD["cases"] if c["model"] == 16 and c["servers"] == 1500)
     out, _, _ = run_host(host, rn, 1)
     assert out[0].counter[5] >= 11 and out[0].counter[6] == 1 and out[0].counter[7] == 1500
+
+
+def test_engine_reproduces_the_reference_resourcepool_golden_file(host):
+    """test/reference/resourcepool.txt - the golden file round 1 left open (its result depends on the holders' tie-break by
+    process address): the reference's own pool test written against the authoring surface (cimba_b200/models/cheese_model.cuh),
+    seeded like the test (cmb_random_initialize(0x34f05c64d7ad598f)), 20 units, 100 time units, gives the file's summary line."""
+    import cimba_b200 as cb
+    case = {"model": 18, "servers": 20, "num_objects": 100, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
+    assert out[0].status == 0 and out[0].counter[0] == 120
+    assert wtdsummary_line(cb.lib, list(out[0].counter)) == RESOURCEPOOL_GOLDEN_LINE

@@ -17,12 +17,12 @@ import pytest
 import torch
 
 import cimba_b200 as cb
-from cmb_cases import GOLD, MASTER, TRACE, case_id, check_trial
+from cmb_cases import GOLD, MASTER, RESOURCEPOOL_GOLDEN_LINE, TRACE, case_id, check_trial, inverse_fmix64, wtdsummary_line
 from oracle_libs import load_port, load_ref, run_trials
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
-BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 16: cb.MODEL_RENEGE}
+BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 16: cb.MODEL_RENEGE, 18: cb.MODEL_POOL_RECORDED}
 
 
 def run_case(case, model_id, variant, n, trace=True, spill=0):
@@ -39,14 +39,14 @@ def compare(case, res, n):
     tt = res.trace_time.cpu().numpy() if res.trace_time is not None else None
     assert (res.status.cpu().numpy()[:n] == 0).all(), res.status.cpu().numpy()[:n]
     for i, want in enumerate(case["trials"][:n]):
-        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 16) else None,
+        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 16, 18) else None,
                     tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}")
 
 
 @pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in BUILTIN], ids=case_id)
 def test_models_on_the_general_engine_match_the_reference_vectors(case):
     n = len(case["trials"])
-    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] != 16 else 0, n)
+    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) else 0, n)
     compare(case, res, n)
 
 
@@ -155,3 +155,15 @@ def test_unknown_model_ids_and_bad_libraries_are_refused():
         cb.run_trials(4, arr_mean=1.0, srv_mean=1.0, num_objects=10, master_seed=1, model=cb.MODEL_USER_BASE + 999)
     with pytest.raises(cb.CimbaError):
         cb.load_model(ROOT / "oracle/liboracle_port.so")        # a library, but not a model
+
+
+def test_resourcepool_golden_file_reproduced_on_device():
+    """test/reference/resourcepool.txt on the GPU: the reference's own pool test (pre-emption, priority changes, interrupts,
+    the holders' tie-break) on the general engine, seed 0x34f05c64d7ad598f, 20 units, 100 time units: the usage history's
+    summary line as the reference prints it."""
+    res = cb.run_trials(1, arr_mean=1.0, srv_mean=1.0, num_objects=100, master_seed=inverse_fmix64(0x34F05C64D7AD598F),
+                        model=cb.MODEL_POOL_RECORDED, servers=20)
+    assert int(res.status[0]) == 0
+    counters = [int(v) & (2**64 - 1) for v in res.counters[0].cpu().tolist()]
+    assert counters[0] == 120 and int(res.max_queue[0]) == 120
+    assert wtdsummary_line(cb.lib, counters) == RESOURCEPOOL_GOLDEN_LINE
