@@ -144,22 +144,9 @@ struct PrioOrder {
     }
 };
 
-// Where a heap's tags live: slots 0 .. inl_slots - 1 - the root, the first levels, everything for a small model - stay in
-// the per-trial control block (local memory, write-back cached in L1); what the heap grows beyond that lives in the HBM
-// arena.  The top of a binary heap is what every sift touches, the deep levels only one path each: north_star's "heap
-// staged on chip, deep levels spilled to HBM", for a lane-private heap.  tag[k] is the one accessor.
-struct TagStore {
-    Tag     *inl;
-    Tag     *ext;
-    uint32_t inl_slots;
-
-    CMB_FN Tag &operator[](uint32_t k) { return k < inl_slots ? inl[k] : ext[k - inl_slots]; }
-    CMB_FN const Tag &operator[](uint32_t k) const { return k < inl_slots ? inl[k] : ext[k - inl_slots]; }
-};
-
 template <class Order>
 struct HashHeap {
-    TagStore  tag;              // [cap + 1], 1-based; tag[0] = the entry popped last (src/cmi_hashheap.c:496-498)
+    Tag      *tag;              // [cap + 1], 1-based; tag[0] = the entry popped last (src/cmi_hashheap.c:496-498)
     MapSlot  *map;              // [2 * cap] once active
     uint32_t  exp;              // cap = 1 << exp (heap_exp_cur)
     uint32_t  count;
@@ -171,9 +158,7 @@ struct HashHeap {
 
     CMB_FN void init(Tag *inline_store, uint32_t inline_exp)
     {
-        tag.inl = inline_store;
-        tag.ext = nullptr;
-        tag.inl_slots = (1u << inline_exp) + 1u;
+        tag = inline_store;
         map = nullptr;
         exp = inline_exp;
         count = 0u;
@@ -263,11 +248,10 @@ struct HashHeap {
     CMB_FN_NOINLINE bool grow(Arena &arena)
     {
         const uint32_t old_cap = cap();
-        // the inline slots stay where they are; the arena part doubles with the heap
-        Tag *bigger = (Tag *)arena.alloc((uint64_t)(2u * old_cap + 1u - tag.inl_slots) * sizeof(Tag));
+        Tag *bigger = (Tag *)arena.alloc((uint64_t)(2u * old_cap + 1u) * sizeof(Tag));
         if (bigger == nullptr) return false;
-        for (uint32_t k = tag.inl_slots; k <= count; k++) bigger[k - tag.inl_slots] = tag.ext[k - tag.inl_slots];
-        tag.ext = bigger;
+        for (uint32_t k = 0u; k <= count; k++) bigger[k] = tag[k];
+        tag = bigger;
         exp++;
         if (map_on) {
             map = (MapSlot *)arena.alloc((uint64_t)(cap() << 1) * sizeof(MapSlot));
@@ -444,16 +428,6 @@ struct Process {
     uint64_t u[2];
 };
 
-// The process table: the first PROC_INLINE records in the control block (local memory), later ones in the arena.  Models
-// recycle finished processes through a free list, so low indices are the busy ones.  proc[pid] is the one accessor.
-constexpr uint32_t PROC_INLINE = 16u;
-struct ProcTable {
-    Process  inl[PROC_INLINE];
-    Process *ext;
-
-    CMB_FN Process &operator[](uint32_t pid) { return pid < PROC_INLINE ? inl[pid] : ext[pid - PROC_INLINE]; }
-};
-
 constexpr uint32_t GUARD_INLINE_EXP = 2u;               // 4 waiters inline, then the arena
 constexpr uint32_t FEL_INLINE_EXP = 3u;                 // the reference starts its event list at 2^3 (src/cmb_event.c:47)
 constexpr uint32_t HOLDERS_INLINE_EXP = 3u;
@@ -516,8 +490,9 @@ struct Sim {
     Arena          arena;
     HashHeap<EventOrder> fel;
     Tag            fel_store[(1u << FEL_INLINE_EXP) + 1u];
-    ProcTable      proc;
+    Process       *proc;
     uint32_t       nproc, proc_cap;
+    Process        proc_inline[4];
     Node          *node;
     uint32_t       node_cap, node_top, node_free;
     Node           node_inline[8];
@@ -549,9 +524,9 @@ struct Sim {
         pops = 0u;
         arena = a;
         fel.init(fel_store, FEL_INLINE_EXP);
-        proc.ext = nullptr;
+        proc = proc_inline;
         nproc = 0u;
-        proc_cap = PROC_INLINE;
+        proc_cap = 4u;
         node = node_inline;
         node_cap = 8u;
         node_top = 0u;
@@ -698,10 +673,17 @@ struct Sim {
     // cmb_process_create + cmb_process_initialize: returns the process index the other calls take
     CMB_FN_NOINLINE uint32_t process_create(uint32_t kind, int64_t prio, uint32_t ctx)
     {
-        if (nproc == proc_cap && !proc_grow()) {
-            // no memory: the trial is void from here (flagged; the dispatcher stops it at its next step).  Hand back
-            // an index that exists, so that model code which goes on to touch "the new process" stays in bounds.
-            return nproc - 1u;
+        if (nproc == proc_cap) {
+            Process *bigger = (Process *)arena.alloc((uint64_t)(2u * proc_cap) * sizeof(Process));
+            if (bigger == nullptr) {
+                // no memory: the trial is void from here (flagged; the dispatcher stops it at its next step).  Hand back
+                // an index that exists, so that model code which goes on to touch "the new process" stays in bounds.
+                status |= TRIAL_ERR_ARENA;
+                return nproc - 1u;
+            }
+            for (uint32_t i = 0u; i < nproc; i++) bigger[i] = proc[i];
+            proc = bigger;
+            proc_cap *= 2u;
         }
         Process &p = proc[nproc];
         p.pc = 0u;
@@ -718,24 +700,17 @@ struct Sim {
         return nproc++;
     }
 
-    CMB_FN_NOINLINE bool proc_grow()                    // twice the table; the inline records stay where they are
-    {
-        const uint32_t new_cap = 2u * proc_cap;
-        Process *bigger = (Process *)arena.alloc((uint64_t)(new_cap - PROC_INLINE) * sizeof(Process));
-        if (bigger == nullptr) {
-            status |= TRIAL_ERR_ARENA;
-            return false;
-        }
-        for (uint32_t i = PROC_INLINE; i < nproc; i++) bigger[i - PROC_INLINE] = proc.ext[i - PROC_INLINE];
-        proc.ext = bigger;
-        proc_cap = new_cap;
-        return true;
-    }
-
     CMB_FN bool process_reserve(uint32_t n)             // room for n processes in one step
     {
         while (proc_cap < n) {
-            if (!proc_grow()) return false;
+            Process *bigger = (Process *)arena.alloc((uint64_t)(2u * proc_cap) * sizeof(Process));
+            if (bigger == nullptr) {
+                status |= TRIAL_ERR_ARENA;
+                return false;
+            }
+            for (uint32_t i = 0u; i < nproc; i++) bigger[i] = proc[i];
+            proc = bigger;
+            proc_cap *= 2u;
         }
         return true;
     }
