@@ -46,6 +46,7 @@
 #include "../models/renege_model.cuh"
 #include "../models/hold_general_model.cuh"
 #include "../models/cheese_model.cuh"
+#include "../models/harbor_general_model.cuh"
 
 #include <dlfcn.h>      // cimba_b200_model_load: a model library built with scripts/build_model.py
 
@@ -116,6 +117,11 @@ bool fast_goes_general(const cimba_b200_device_job *job)
 bool hold_goes_general(const cimba_b200_device_job *job)
 {
     return job->model == CIMBA_B200_MODEL_HOLD && job->variant == CIMBA_B200_VARIANT_GENERAL;
+}
+
+bool harbor_goes_general(const cimba_b200_device_job *job)
+{
+    return job->model == CIMBA_B200_MODEL_HARBOR && job->variant == CIMBA_B200_VARIANT_GENERAL;
 }
 
 // models loaded with cimba_b200_model_load
@@ -344,6 +350,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
+    if (harbor_goes_general(job)) return cmb::workspace_bytes_for<models::HarborGeneral>(*job);
     if (fast_goes_general(job)) {
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_for<models::MM1>(*job)
                                                   : cmb::workspace_bytes_for<models::GG1>(*job);
@@ -398,7 +405,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         g_launches++;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
     }
-    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job)) {
+    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -412,6 +419,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             return launch_general<models::MMC>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MMC> launch");
         if (job->model == CIMBA_B200_MODEL_HOLD)
             return launch_general<models::HoldGeneral>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<HoldGeneral> launch");
+        if (job->model == CIMBA_B200_MODEL_HARBOR) {
+            if (job->servers < 3) return fail(CIMBA_B200_EINVAL, "tugs (servers) must be >= 3 for CIMBA_B200_MODEL_HARBOR (a large ship needs 3)");
+            return launch_general<models::HarborGeneral>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<HarborGeneral> launch");
+        }
         if (job->model == CIMBA_B200_MODEL_MM1)
             return launch_general<models::MM1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MM1> launch");
         return launch_general<models::GG1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<GG1> launch");

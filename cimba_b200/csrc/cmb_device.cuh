@@ -492,6 +492,7 @@ struct Sim {
     Tag            fel_store[(1u << FEL_INLINE_EXP) + 1u];
     Process       *proc;
     uint32_t       nproc, proc_cap;
+    uint32_t       proc_free;           // LIFO of records given back with process_destroy (linked through Process::pc)
     Process        proc_inline[4];
     Node          *node;
     uint32_t       node_cap, node_top, node_free;
@@ -527,6 +528,7 @@ struct Sim {
         proc = proc_inline;
         nproc = 0u;
         proc_cap = 4u;
+        proc_free = NIL;
         node = node_inline;
         node_cap = 8u;
         node_top = 0u;
@@ -673,19 +675,27 @@ struct Sim {
     // cmb_process_create + cmb_process_initialize: returns the process index the other calls take
     CMB_FN_NOINLINE uint32_t process_create(uint32_t kind, int64_t prio, uint32_t ctx)
     {
-        if (nproc == proc_cap) {
-            Process *bigger = (Process *)arena.alloc((uint64_t)(2u * proc_cap) * sizeof(Process));
-            if (bigger == nullptr) {
-                // no memory: the trial is void from here (flagged; the dispatcher stops it at its next step).  Hand back
-                // an index that exists, so that model code which goes on to touch "the new process" stays in bounds.
-                status |= TRIAL_ERR_ARENA;
-                return nproc - 1u;
-            }
-            for (uint32_t i = 0u; i < nproc; i++) bigger[i] = proc[i];
-            proc = bigger;
-            proc_cap *= 2u;
+        uint32_t pid;
+        if (proc_free != NIL) {                         // a record a finished process gave back (cmb_process_destroy)
+            pid = proc_free;
+            proc_free = proc[pid].pc;
         }
-        Process &p = proc[nproc];
+        else {
+            if (nproc == proc_cap) {
+                Process *bigger = (Process *)arena.alloc((uint64_t)(2u * proc_cap) * sizeof(Process));
+                if (bigger == nullptr) {
+                    // no memory: the trial is void from here (flagged; the dispatcher stops it at its next step).  Hand back
+                    // an index that exists, so that model code which goes on to touch "the new process" stays in bounds.
+                    status |= TRIAL_ERR_ARENA;
+                    return nproc - 1u;
+                }
+                for (uint32_t i = 0u; i < nproc; i++) bigger[i] = proc[i];
+                proc = bigger;
+                proc_cap *= 2u;
+            }
+            pid = nproc++;
+        }
+        Process &p = proc[pid];
         p.pc = 0u;
         p.status = PROC_CREATED;
         p.kind = kind;
@@ -697,7 +707,17 @@ struct Sim {
         p.fr[0] = p.fr[1] = p.fr[2] = 0u;
         p.f[0] = p.f[1] = 0.0;
         p.u[0] = p.u[1] = 0u;
-        return nproc++;
+        return pid;
+    }
+
+    // cmb_process_terminate + cmb_process_destroy of a process that is FINISHED (or was never started): its record may be
+    // handed out again by the next cmb_process_create.  Models that create a process per arrival call this when they are
+    // done with its exit value, as the reference's frees its struct (test/test_condition.c:441-446).
+    CMB_FN void process_destroy(uint32_t pid)
+    {
+        proc[pid].status = PROC_FINISHED;
+        proc[pid].pc = proc_free;
+        proc_free = pid;
     }
 
     CMB_FN bool process_reserve(uint32_t n)             // room for n processes in one step
@@ -1404,8 +1424,18 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define cmb_random_bernoulli(p)             (sim.rng.bernoulli(p))
 #define cmb_random_dice(lo, hi)             (sim.rng.dice((lo), (hi)))
 #define cmb_random_triangular(a, b, c)      (cimba_b200::rnd_triangular(sim.rng, (a), (b), (c)))
+#define cmb_random_rayleigh(s)              (cimba_b200::rnd_rayleigh(sim.rng, *sim.hot, (s)))
+#define cmb_random_PERT(lo, mode, hi)       (cimba_b200::rnd_PERT_mod(sim.rng, *sim.hot, (lo), (mode), (hi), 4.0))
+#define cmb_random_gamma(shape, scale)      (cimba_b200::rnd_gamma(sim.rng, *sim.hot, (shape), (scale)))
+#define cmb_random_beta(a, b, lo, hi)       (cimba_b200::rnd_beta(sim.rng, *sim.hot, (a), (b), (lo), (hi)))
+#define cmb_random_weibull(shape, scale)    (cimba_b200::rnd_weibull(sim.rng, *sim.hot, (shape), (scale)))
+#define cmb_random_lognormal(m, sd)         (cimba_b200::rnd_lognormal(sim.rng, *sim.hot, (m), (sd)))
+#define cmb_random_poisson(rate)            (cimba_b200::rnd_poisson(sim.rng, *sim.hot, (rate)))
+#define cmb_resourcepool_available(rp)      ((rp).capacity - (rp).in_use)
 #define cmb_process_create(kind, prio, ctx) (sim.process_create((kind), (prio), (ctx)))
 #define cmb_process_start(pid)              (sim.process_start(pid))
+#define cmb_process_destroy(pid)            (sim.process_destroy(pid))
+#define cmb_process_exit_value(pid)         (sim.proc[pid].exit_value)
 #define cmb_process_stop(pid, value)        (cimba_b200::cmb::process_stop(sim, m, (pid), (value)))
 #define cmb_process_interrupt(pid, s, pri)  (sim.interrupt((pid), (s), (pri)))
 #define cmb_process_resume(pid, s)          (sim.resume((pid), (s)))

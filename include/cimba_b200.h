@@ -135,7 +135,8 @@ int cimba_b200_model_load(const char *path_to_model_library);
 /* The name the model registered, or NULL for an id nobody loaded. */
 const char *cimba_b200_model_name(int model_id);
 
-/* variant 16 of MODEL_MM1 / MODEL_GG1 / MODEL_MMC / MODEL_HOLD: the same model as cimba_b200/models/{mm1,gg1,mmc,hold_general}_model.cuh
+/* variant 16 of MODEL_MM1 / MODEL_GG1 / MODEL_MMC / MODEL_HOLD / MODEL_HARBOR: the same model as
+ * cimba_b200/models/{mm1,gg1,mmc,hold_general,harbor_general}_model.cuh
  * run by the general engine (growable event list, wait lists and queues; any number of servers).  The fast kernels' repair pass
  * and MODEL_MMC with more than 14 servers use it too. */
 #define CIMBA_B200_VARIANT_GENERAL 16

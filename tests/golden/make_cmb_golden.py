@@ -34,6 +34,8 @@ CASES = [
     (2, 8, 20000, 1 / 8.4, 1.0, [], 4),           # overload: the wait list grows
     (7, 50, 40, 1.0, 1.0, [], 4),                 # the hold model: 50 and 2000 workers + ticker + end event
     (7, 2000, 6, 1.0, 1.0, [], 3),
+    (10, 10, 1500, 2.0, 8.0, [], 4),              # the harbor (test/test_condition.c): 10 tugs; 4 tugs under load
+    (10, 4, 1200, 1.5, 8.0, [], 3),
     (16, 40, 300, 3.0, 1.0, [0.7], 4),
     (16, 1000, 60, 4.0, 1.0, [0.5], 4),
     (16, 1500, 40, 2.0, 1.0, [1.5], 3),
@@ -57,7 +59,7 @@ def main():
             _, keys, times = trace_trial(ref, "ref", model, servers, ref.ref_fmix64(MASTER, i), nobj, arr, srv, TRACE)
             h = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
             trials.append({"events": r.events, "objects": r.objects, "t_end": float(r.t_end).hex(), "sum_wait": float(r.sum_wait).hex(),
-                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model == 18), "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
+                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model in (10, 18)), "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
         out["cases"].append({"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
                              "srv_mean": float(srv).hex(), "params": params, "trials": trials})
         print(model, servers, nobj, [t["events"] for t in trials])

@@ -104,3 +104,19 @@ def test_engine_reproduces_the_reference_resourcepool_golden_file(host):
     out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
     assert out[0].status == 0 and out[0].counter[0] == 120
     assert wtdsummary_line(cb.lib, list(out[0].counter)) == RESOURCEPOOL_GOLDEN_LINE
+
+
+def test_engine_reproduces_the_reference_condition_golden_file(host):
+    """test/reference/condition.txt: the reference's harbor (test/test_condition.c = tutorial/tut_4_1.c) written against the
+    authoring surface (cimba_b200/models/harbor_general_model.cuh), seeded like the test, 100 simulated years: 4 579 051 events,
+    the file's ship counts (:8, :35), mean system times, tug (:85) and berth (:62, :75) history sizes and the tug mean."""
+    import struct
+    case = {"model": 10, "servers": 10, "num_objects": 873600, "arr_mean": (2.0).hex(), "srv_mean": (8.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
+    o = out[0]
+    f = lambda u: struct.unpack("<d", struct.pack("<Q", u))[0]
+    c = list(o.counter)
+    assert o.status == 0 and o.events == 4579051
+    assert (c[0], c[1]) == (328781, 109454) and ("%.4g" % f(c[2]), "%.4g" % f(c[3])) == ("10.91", "17.48")
+    assert c[4] == 1736975 and "%.4g" % f(c[5]) == "0.8025"
+    assert (c[6] & 0xffffffff, c[6] >> 32) == (645947, 217380)

@@ -22,7 +22,8 @@ from oracle_libs import load_port, load_ref, run_trials
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
-BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 16: cb.MODEL_RENEGE, 18: cb.MODEL_POOL_RECORDED}
+BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 10: cb.MODEL_HARBOR, 16: cb.MODEL_RENEGE,
+           18: cb.MODEL_POOL_RECORDED}
 
 
 def run_case(case, model_id, variant, n, trace=True, spill=0):
@@ -39,7 +40,7 @@ def compare(case, res, n):
     tt = res.trace_time.cpu().numpy() if res.trace_time is not None else None
     assert (res.status.cpu().numpy()[:n] == 0).all(), res.status.cpu().numpy()[:n]
     for i, want in enumerate(case["trials"][:n]):
-        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 16, 18) else None,
+        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18) else None,
                     tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}")
 
 
