@@ -46,6 +46,9 @@
 #include "../models/renege_model.cuh"
 #include "../models/hold_general_model.cuh"
 #include "../models/cheese_model.cuh"
+#include "../models/guarded_model.cuh"
+#include "../models/workshop_model.cuh"
+#include "../models/coverage_models.cuh"
 #include "../models/harbor_general_model.cuh"
 
 #include <dlfcn.h>      // cimba_b200_model_load: a model library built with scripts/build_model.py
@@ -150,6 +153,31 @@ int launch_general(const cimba_b200_device_job *job, unsigned char *arena, uint6
     return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, what);
 }
 
+// the reference's own test worlds (models 3-6, 8, 11-14) run on the general engine; variant 1 = the fixed-capacity
+// kernels they had in round 1 (csrc/general.cuh), kept for A/B runs
+bool coverage_goes_general(const cimba_b200_device_job *job);
+
+template <template <class> class F, class... A>
+auto for_coverage_model(int model, A &&...a)
+{
+    switch (model) {
+    case CIMBA_B200_MODEL_GUARDED:           return F<models::Guarded<false, false>>::call(a...);
+    case CIMBA_B200_MODEL_GUARDED_RECORDED:  return F<models::Guarded<false, true>>::call(a...);
+    case CIMBA_B200_MODEL_PRIOQ_RECORDED:    return F<models::Guarded<true, true>>::call(a...);
+    case CIMBA_B200_MODEL_PREEMPT:           return F<models::PoolFight>::call(a...);
+    case CIMBA_B200_MODEL_BUFFER:            return F<models::Workshop<false>>::call(a...);
+    case CIMBA_B200_MODEL_BUFFER_RECORDED:   return F<models::Workshop<true>>::call(a...);
+    case CIMBA_B200_MODEL_PRIOQ:             return F<models::QueueAndTide>::call(a...);
+    case CIMBA_B200_MODEL_TIMERS:            return F<models::FrontDesk>::call(a...);
+    default:                                 return F<models::Tool>::call(a...);       // CIMBA_B200_MODEL_RESOURCE_RECORDED
+    }
+}
+
+template <class Model>
+struct WorkspaceOf {
+    static uint64_t call(const cimba_b200_device_job *job) { return cmb::workspace_bytes_for<Model>(*job); }
+};
+
 bool is_queue_model(int m)
 {
     return m == CIMBA_B200_MODEL_MM1 || m == CIMBA_B200_MODEL_GG1 || m == CIMBA_B200_MODEL_MM1_RECORDED;
@@ -173,6 +201,19 @@ bool is_general_model(int m)
            m == CIMBA_B200_MODEL_BUFFER_RECORDED || m == CIMBA_B200_MODEL_PRIOQ_RECORDED ||
            m == CIMBA_B200_MODEL_RESOURCE_RECORDED;
 }
+
+bool coverage_goes_general(const cimba_b200_device_job *job)
+{
+    return is_general_model(job->model) && job->variant != 1;
+}
+
+template <class Model>
+struct LaunchOf {
+    static int call(const cimba_b200_device_job *job, cudaStream_t st)
+    {
+        return launch_general<Model>(job, (unsigned char *)job->workspace, job->workspace_bytes, 0u, st, "trial_kernel launch");
+    }
+};
 
 // ---------------------------------------------------------------- RNG KAT kernel
 __global__ void rng_draws_kernel(uint64_t seed, int kind, double p0, double p1, uint64_t n, double *out)
@@ -348,6 +389,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
     if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
+    if (coverage_goes_general(job)) return for_coverage_model<WorkspaceOf>(job->model, job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
     if (harbor_goes_general(job)) return cmb::workspace_bytes_for<models::HarborGeneral>(*job);
@@ -404,6 +446,14 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const int e = um->launch(job, stream);
         g_launches++;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
+    }
+    if (coverage_goes_general(job)) {
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
+        const bool no_capacity = job->model == CIMBA_B200_MODEL_TIMERS || job->model == CIMBA_B200_MODEL_RESOURCE_RECORDED;
+        if (!no_capacity && job->servers < 1) return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        return for_coverage_model<LaunchOf>(job->model, job, st);
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");

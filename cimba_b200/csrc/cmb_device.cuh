@@ -45,6 +45,9 @@
 #endif
 
 // ---- the reference's constants, same values (include/cmb_process.h:59-99, include/cmb_objectqueue.h)
+#define CMB_PROCESS_CREATED     (cimba_b200::cmb::PROC_CREATED)      // what cmb_process_status(pid) returns
+#define CMB_PROCESS_RUNNING     (cimba_b200::cmb::PROC_RUNNING)
+#define CMB_PROCESS_FINISHED    (cimba_b200::cmb::PROC_FINISHED)
 #define CMB_PROCESS_SUCCESS     ((int64_t)0)
 #define CMB_PROCESS_PREEMPTED   ((int64_t)-1)
 #define CMB_PROCESS_INTERRUPTED ((int64_t)-2)
@@ -407,6 +410,10 @@ enum : uint32_t {
     DEMAND_QUEUE_SPACE = 2u,    // has_space,    :135-149
     DEMAND_POOL_AVAILABLE = 3u, // is_available, src/cmb_resourcepool.c:198-211
     DEMAND_RESOURCE_FREE = 4u,  // is_available, src/cmb_resource.c:155-167
+    DEMAND_BUFFER_CONTENT = 5u, // buffer_has_content, src/cmb_buffer.c:96-108
+    DEMAND_BUFFER_SPACE = 6u,   // buffer_has_space,   :110-122
+    DEMAND_PQ_CONTENT = 7u,     // has_content, src/cmb_priorityqueue.c:119-133
+    DEMAND_PQ_SPACE = 8u,       // has_space,   :135-149
     DEMAND_USER = 16u,          // first id of a model's own predicates (cmb_condition_wait)
 };
 
@@ -465,6 +472,26 @@ struct resourcepool {
 struct resource {
     resourceguard guard;
     uint32_t holder;            // process index, NIL = free
+    uint32_t recording;
+    TimeWeighted history;       // 1 while held, 0 while free
+};
+
+// struct cmb_buffer (include/cmb_buffer.h): an amount between 0 and capacity, put and got in parts
+struct buffer {
+    resourceguard front, rear;  // getters wait at the front guard, putters at the rear
+    uint64_t level, capacity;
+    uint32_t recording;
+    TimeWeighted history;
+};
+
+// struct cmb_priorityqueue (include/cmb_priorityqueue.h): objects ordered by priority, then FIFO; handles = keys
+struct priorityqueue {
+    resourceguard front, rear;
+    HashHeap<PrioOrder> queue;  // tag.d carries the object (64 bits), tag.prio its priority
+    Tag      store[9];
+    uint64_t capacity;
+    uint32_t recording;
+    TimeWeighted history;
 };
 
 // struct cmb_condition (include/cmb_condition.h): a guard whose demands are the model's own predicates
@@ -897,6 +924,10 @@ CMB_FN bool builtin_demand(uint32_t demand, void *owner)
     case DEMAND_QUEUE_SPACE:   return ((objectqueue *)owner)->length < ((objectqueue *)owner)->capacity;
     case DEMAND_POOL_AVAILABLE: return ((resourcepool *)owner)->capacity - ((resourcepool *)owner)->in_use > 0u;
     case DEMAND_RESOURCE_FREE: return ((resource *)owner)->holder == NIL;
+    case DEMAND_BUFFER_CONTENT: return ((buffer *)owner)->level > 0u;
+    case DEMAND_BUFFER_SPACE:  return ((buffer *)owner)->level < ((buffer *)owner)->capacity;
+    case DEMAND_PQ_CONTENT:    return ((priorityqueue *)owner)->queue.count > 0u;
+    case DEMAND_PQ_SPACE:      return ((priorityqueue *)owner)->queue.count < ((priorityqueue *)owner)->capacity;
     }
     return false;
 }
@@ -1178,20 +1209,209 @@ CMB_FN void resource_initialize(Sim &sim, resource &r)
 {
     sim.guard_init(r.guard, &r);
     r.holder = NIL;
+    r.recording = 0u;
 }
 
-template <class Model>
-CMB_FN void resource_release(Sim &sim, Model &m, resource &r, uint32_t pid)        // src/cmb_resource.c:234-250
+CMB_FN void resource_sample(Sim &sim, resource &r)                                 // record_sample, src/cmb_resource.c
 {
-    (void)sim.list_remove(sim.proc[pid].holds, HOLD_RESOURCE, (uint64_t)(uintptr_t)&r, false);
-    r.holder = NIL;
-    (void)guard_signal(sim, m, r.guard);
+    if (r.recording) r.history.sample(r.holder != NIL ? 1.0 : 0.0, sim.now);
+}
+
+CMB_FN void resource_recording_start(Sim &sim, resource &r)
+{
+    r.recording = 1u;
+    r.history.start();
+    r.history.sample(r.holder != NIL ? 1.0 : 0.0, sim.now);
+}
+
+CMB_FN void resource_recording_stop(Sim &sim, resource &r)
+{
+    resource_sample(sim, r);
+    r.recording = 0u;
 }
 
 CMB_FN void resource_grab(Sim &sim, resource &r, uint32_t pid)                     // :182-189
 {
     r.holder = pid;
     sim.list_push(sim.proc[pid].holds, HOLD_RESOURCE, (uint64_t)(uintptr_t)&r);
+}
+
+template <class Model>
+CMB_FN void resource_release(Sim &sim, Model &m, resource &r, uint32_t pid)        // :234-250
+{
+    (void)sim.list_remove(sim.proc[pid].holds, HOLD_RESOURCE, (uint64_t)(uintptr_t)&r, false);
+    r.holder = NIL;
+    resource_sample(sim, r);
+    (void)guard_signal(sim, m, r.guard);
+}
+
+// cmb_resource_preempt, :270-320, up to its polite branch: true = the caller holds the resource now
+CMB_FN_NOINLINE bool resource_preempt_step(Sim &sim, resource &r, uint32_t pid)
+{
+    const uint32_t victim = r.holder;
+    if (victim == NIL) {
+        resource_grab(sim, r, pid);
+        resource_sample(sim, r);
+        return true;
+    }
+    if (sim.proc[pid].prio >= sim.proc[victim].prio) {
+        (void)sim.list_remove(sim.proc[victim].holds, HOLD_RESOURCE, (uint64_t)(uintptr_t)&r, false);
+        sim.cancel_awaiteds(pid);                       // sic: the CALLER's awaiteds (cmi_process_cancel_awaiteds(pp), :296)
+        r.holder = NIL;
+        sim.schedule(ACT_CMB_WAKE_PREEMPT, victim, CMB_PROCESS_PREEMPTED, sim.now, sim.proc[victim].prio);
+        resource_grab(sim, r, pid);                     // no history sample: the resource stays occupied
+        return true;
+    }
+    return false;                                       // wait politely: cmb_resource_acquire
+}
+
+// ------------------------------------------------------------------------------------------------ buffer
+CMB_FN void buffer_initialize(Sim &sim, buffer &b, uint64_t capacity)              // src/cmb_buffer.c:45-75
+{
+    sim.guard_init(b.front, &b);
+    sim.guard_init(b.rear, &b);
+    b.level = 0u;
+    b.capacity = capacity;
+    b.recording = 0u;
+}
+
+CMB_FN void buffer_sample(Sim &sim, buffer &b)
+{
+    if (b.recording) b.history.sample((double)b.level, sim.now);
+}
+
+CMB_FN void buffer_recording_start(Sim &sim, buffer &b)
+{
+    b.recording = 1u;
+    b.history.start();
+    b.history.sample((double)b.level, sim.now);
+}
+
+CMB_FN void buffer_recording_stop(Sim &sim, buffer &b)
+{
+    buffer_sample(sim, b);
+    b.recording = 0u;
+}
+
+// cmb_buffer_get up to its wait (:194-264): fr[1] = remaining claim, fr[2] = obtained so far.  true = satisfied.
+template <class Model>
+CMB_FN_NOINLINE bool buffer_get_step(Sim &sim, Model &m, buffer &b, uint32_t pid)
+{
+    uint64_t rem = sim.proc[pid].fr[1];
+    if (b.level >= rem) {
+        b.level -= rem;
+        buffer_sample(sim, b);
+        sim.proc[pid].fr[2] += rem;
+        (void)guard_signal(sim, m, b.rear);
+        if (b.level > 0u) (void)guard_signal(sim, m, b.front);         // leftovers for the next getter
+        return true;
+    }
+    if (b.level > 0u) {
+        const uint64_t grab = b.level;
+        b.level = 0u;
+        buffer_sample(sim, b);
+        sim.proc[pid].fr[2] += grab;
+        rem -= grab;
+        (void)guard_signal(sim, m, b.rear);
+    }
+    sim.proc[pid].fr[1] = rem;
+    (void)guard_signal(sim, m, b.rear);                 // once more before waiting (:241)
+    return false;
+}
+
+// cmb_buffer_put up to its wait (:279-346): fr[1] = remaining to put.  true = everything is in.
+template <class Model>
+CMB_FN_NOINLINE bool buffer_put_step(Sim &sim, Model &m, buffer &b, uint32_t pid)
+{
+    uint64_t rem = sim.proc[pid].fr[1];
+    if (b.capacity - b.level >= rem) {
+        b.level += rem;
+        buffer_sample(sim, b);
+        sim.proc[pid].fr[1] = 0u;
+        (void)guard_signal(sim, m, b.front);
+        if (b.level < b.capacity) (void)guard_signal(sim, m, b.rear);
+        return true;
+    }
+    if (b.level < b.capacity) {
+        const uint64_t grab = b.capacity - b.level;
+        b.level = b.capacity;
+        buffer_sample(sim, b);
+        rem -= grab;
+        (void)guard_signal(sim, m, b.front);
+    }
+    sim.proc[pid].fr[1] = rem;
+    (void)guard_signal(sim, m, b.front);
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------ priorityqueue
+CMB_FN void priorityqueue_initialize(Sim &sim, priorityqueue &q, uint64_t capacity)    // src/cmb_priorityqueue.c:56-117
+{
+    sim.guard_init(q.front, &q);
+    sim.guard_init(q.rear, &q);
+    q.queue.init(q.store, 3u);
+    q.capacity = capacity;
+    q.recording = 0u;
+}
+
+CMB_FN void priorityqueue_sample(Sim &sim, priorityqueue &q)
+{
+    if (q.recording) q.history.sample((double)q.queue.count, sim.now);
+}
+
+CMB_FN void priorityqueue_recording_start(Sim &sim, priorityqueue &q)
+{
+    q.recording = 1u;
+    q.history.start();
+    q.history.sample((double)q.queue.count, sim.now);
+}
+
+CMB_FN void priorityqueue_recording_stop(Sim &sim, priorityqueue &q)
+{
+    priorityqueue_sample(sim, q);
+    q.recording = 0u;
+}
+
+template <class Model>
+CMB_FN bool priorityqueue_try_put(Sim &sim, Model &m, priorityqueue &q, uint64_t obj, int64_t prio, uint64_t *handle)   // :237-284
+{
+    if (q.queue.count >= q.capacity) return false;
+    const uint64_t h = q.queue.enqueue(sim.arena, 0u, __longlong_as_double((long long)obj), (int32_t)prio, NIL, 0u, 0, NIL);
+    if (h == 0u) sim.status |= TRIAL_ERR_ARENA;
+    if (handle != nullptr) *handle = h;
+    priorityqueue_sample(sim, q);
+    (void)guard_signal(sim, m, q.front);
+    return true;
+}
+
+template <class Model>
+CMB_FN bool priorityqueue_try_get(Sim &sim, Model &m, priorityqueue &q, uint64_t &obj)       // :189-235
+{
+    if (q.queue.count == 0u) return false;
+    (void)q.queue.dequeue();
+    obj = (uint64_t)__double_as_longlong(q.queue.tag[0].d);
+    priorityqueue_sample(sim, q);
+    (void)guard_signal(sim, m, q.rear);
+    return true;
+}
+
+// cmb_priorityqueue_reprioritize, include/cmb_priorityqueue.h:170-180 (the tag's double is the object here: it stays)
+CMB_FN void priorityqueue_reprioritize(Sim &sim, priorityqueue &q, uint64_t handle, int64_t prio)
+{
+    const uint32_t at = q.queue.find(sim.arena, handle);
+    if (at != 0u) (void)q.queue.reprioritize(sim.arena, handle, q.queue.tag[at].d, (int32_t)prio);
+}
+
+// cmb_priorityqueue_position, :286-320: 1 = next to be taken, 0 = not in the queue
+CMB_FN_NOINLINE uint64_t priorityqueue_position(Sim &sim, priorityqueue &q, uint64_t handle)
+{
+    const uint32_t at = q.queue.find(sim.arena, handle);
+    if (at == 0u) return 0u;
+    uint64_t ahead = 0u;
+    for (uint32_t k = 1u; k <= q.queue.count; k++) {
+        if (k != at && PrioOrder::before(q.queue.tag[k], q.queue.tag[at])) ahead++;
+    }
+    return ahead + 1u;
 }
 
 // ------------------------------------------------------------------------------------------------ condition
@@ -1234,6 +1454,7 @@ CMB_FN_NOINLINE void drop_resources(Sim &sim, Model &m, uint32_t pid)
         }
         else if (kind == HOLD_RESOURCE) {               // resource_drop_holder, src/cmb_resource.c:45-56
             ((resource *)res)->holder = NIL;
+            resource_sample(sim, *(resource *)res);
             (void)guard_signal(sim, m, ((resource *)res)->guard);
         }
     }
@@ -1370,7 +1591,9 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 // cmb_process_exit(value)
 #define CMB_PROCESS_EXIT(value)  do { sim.cmd = cimba_b200::cmb::CMD_EXIT; sim.cmd_exit = (value); return; } while (0)
 // cmb_process_wait_process(other) / cmb_process_wait_event(handle)
-#define CMB_PROCESS_WAIT_PROCESS(other) do { sim.wait_process_begin(me, (other)); CMB_YIELD_(); } while (0)
+#define CMB_PROCESS_WAIT_PROCESS(other) \
+    do { if (sim.proc[(other)].status == cimba_b200::cmb::PROC_FINISHED) { sig = CMB_PROCESS_SUCCESS; } \
+         else { sim.wait_process_begin(me, (other)); CMB_YIELD_(); } } while (0)
 #define CMB_PROCESS_WAIT_EVENT(handle)  do { sim.wait_event_begin(me, (handle)); CMB_YIELD_(); } while (0)
 
 // sig = cmb_objectqueue_put(&q, obj)   (src/cmb_objectqueue.c:262-314)
@@ -1399,13 +1622,47 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define CMB_RESOURCEPOOL_PREEMPT(rp, amount) CMB_RESOURCEPOOL_ACQUIRE_(rp, amount, true)
 #define CMB_RESOURCEPOOL_RELEASE(rp, amount) cimba_b200::cmb::resourcepool_release(sim, m, (rp), me, (uint64_t)(amount))
 
-// sig = cmb_resource_acquire(&r)       (src/cmb_resource.c:191-229)
+// sig = cmb_resource_acquire(&r)       (src/cmb_resource.c:191-229): ONE wait, and after a successful one the resource is
+// taken without another look - as the reference has it
 #define CMB_RESOURCE_ACQUIRE(r) \
-    do { for (;;) { \
-        if ((r).holder == cimba_b200::cmb::NIL) { cimba_b200::cmb::resource_grab(sim, (r), me); sig = CMB_PROCESS_SUCCESS; break; } \
-        CMB_GUARD_WAIT_((r).guard, cimba_b200::cmb::DEMAND_RESOURCE_FREE, 0); \
-        sig = sim.guard_wait_end((r).guard, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } } while (0)
+    do { if ((r).holder == cimba_b200::cmb::NIL) { \
+            cimba_b200::cmb::resource_grab(sim, (r), me); cimba_b200::cmb::resource_sample(sim, (r)); sig = CMB_PROCESS_SUCCESS; } \
+        else { CMB_GUARD_WAIT_((r).guard, cimba_b200::cmb::DEMAND_RESOURCE_FREE, 0); \
+            sig = sim.guard_wait_end((r).guard, me, sig); \
+            if (sig == CMB_PROCESS_SUCCESS) { cimba_b200::cmb::resource_grab(sim, (r), me); cimba_b200::cmb::resource_sample(sim, (r)); } } } while (0)
+// sig = cmb_resource_preempt(&r)       (:270-320)
+#define CMB_RESOURCE_PREEMPT(r) \
+    do { if (cimba_b200::cmb::resource_preempt_step(sim, (r), me)) { sig = CMB_PROCESS_SUCCESS; } else { CMB_RESOURCE_ACQUIRE(r); } } while (0)
 #define CMB_RESOURCE_RELEASE(r)  cimba_b200::cmb::resource_release(sim, m, (r), me)
+
+// sig = cmb_buffer_get(&b, &amount) / cmb_buffer_put(&b, &amount)   (src/cmb_buffer.c:194-346); `amount` is a uint64_t lvalue:
+// in = the amount wanted / offered, out = the amount obtained (get) / still in hand (put) - partial when interrupted
+#define CMB_BUFFER_GET(b, amount) \
+    do { sim.proc[me].fr[1] = (uint64_t)(amount); sim.proc[me].fr[2] = 0u; \
+        for (;;) { \
+        if (cimba_b200::cmb::buffer_get_step(sim, m, (b), me)) { sig = CMB_PROCESS_SUCCESS; break; } \
+        CMB_GUARD_WAIT_((b).front, cimba_b200::cmb::DEMAND_BUFFER_CONTENT, 0); \
+        sig = sim.guard_wait_end((b).front, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } \
+        (amount) = sim.proc[me].fr[2]; } while (0)
+#define CMB_BUFFER_PUT(b, amount) \
+    do { sim.proc[me].fr[1] = (uint64_t)(amount); \
+        for (;;) { \
+        if (cimba_b200::cmb::buffer_put_step(sim, m, (b), me)) { sig = CMB_PROCESS_SUCCESS; break; } \
+        CMB_GUARD_WAIT_((b).rear, cimba_b200::cmb::DEMAND_BUFFER_SPACE, 0); \
+        sig = sim.guard_wait_end((b).rear, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } \
+        (amount) = sim.proc[me].fr[1]; } while (0)
+
+// sig = cmb_priorityqueue_put(&q, obj, priority, &handle) / cmb_priorityqueue_get(&q, &obj)   (src/cmb_priorityqueue.c:189-284)
+#define CMB_PRIORITYQUEUE_PUT(q, obj, prio, handle_ptr) \
+    do { for (;;) { \
+        if (cimba_b200::cmb::priorityqueue_try_put(sim, m, (q), (uint64_t)(obj), (prio), (handle_ptr))) { sig = CMB_PROCESS_SUCCESS; break; } \
+        CMB_GUARD_WAIT_((q).rear, cimba_b200::cmb::DEMAND_PQ_SPACE, 0); \
+        sig = sim.guard_wait_end((q).rear, me, sig); if (sig != CMB_PROCESS_SUCCESS) break; } } while (0)
+#define CMB_PRIORITYQUEUE_GET(q, obj) \
+    do { for (;;) { \
+        if (cimba_b200::cmb::priorityqueue_try_get(sim, m, (q), (obj))) { sig = CMB_PROCESS_SUCCESS; break; } \
+        CMB_GUARD_WAIT_((q).front, cimba_b200::cmb::DEMAND_PQ_CONTENT, 0); \
+        sig = sim.guard_wait_end((q).front, me, sig); if (sig != CMB_PROCESS_SUCCESS) { (obj) = 0u; break; } } } while (0)
 
 // sig = cmb_condition_wait(&c, predicate id, ctx)   (src/cmb_condition.c:63-80); spurious wake-ups are the caller's to re-test
 #define CMB_CONDITION_WAIT(c, demand_id, ctx) \
@@ -1460,6 +1717,21 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define cmb_resourcepool_initialize(rp, cap) (cimba_b200::cmb::resourcepool_initialize(sim, (rp), (cap)))
 #define cmb_resourcepool_in_use(rp)         ((rp).in_use)
 #define cmb_resource_initialize(r)          (cimba_b200::cmb::resource_initialize(sim, (r)))
+#define cmb_resource_start_recording(r)     (cimba_b200::cmb::resource_recording_start(sim, (r)))
+#define cmb_resource_stop_recording(r)      (cimba_b200::cmb::resource_recording_stop(sim, (r)))
+#define cmb_buffer_initialize(b, cap)       (cimba_b200::cmb::buffer_initialize(sim, (b), (cap)))
+#define cmb_buffer_recording_start(b)       (cimba_b200::cmb::buffer_recording_start(sim, (b)))
+#define cmb_buffer_recording_stop(b)        (cimba_b200::cmb::buffer_recording_stop(sim, (b)))
+#define cmb_buffer_level(b)                 ((b).level)
+#define cmb_priorityqueue_initialize(q, cap) (cimba_b200::cmb::priorityqueue_initialize(sim, (q), (cap)))
+#define cmb_priorityqueue_recording_start(q) (cimba_b200::cmb::priorityqueue_recording_start(sim, (q)))
+#define cmb_priorityqueue_recording_stop(q)  (cimba_b200::cmb::priorityqueue_recording_stop(sim, (q)))
+#define cmb_priorityqueue_length(q)         ((uint64_t)(q).queue.count)
+#define cmb_priorityqueue_position(q, h)    (cimba_b200::cmb::priorityqueue_position(sim, (q), (h)))
+#define cmb_priorityqueue_cancel(q, h)      ((q).queue.remove(sim.arena, (h)))
+#define cmb_priorityqueue_reprioritize(q, h, pri) (cimba_b200::cmb::priorityqueue_reprioritize(sim, (q), (h), (pri)))
+#define cmb_objectqueue_recording_start(q)  (cimba_b200::cmb::objectqueue_recording_start(sim, (q)))
+#define cmb_objectqueue_recording_stop(q)   (cimba_b200::cmb::objectqueue_recording_stop(sim, (q)))
 #define cmb_condition_initialize(c)         (cimba_b200::cmb::condition_initialize(sim, (c)))
 #define cmb_condition_signal(c)             (cimba_b200::cmb::condition_signal(sim, m, (c)))
 #define cmb_resourceguard_register(g, obs)  (cimba_b200::cmb::guard_register(m, (g), (obs)))

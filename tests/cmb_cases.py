@@ -21,7 +21,7 @@ def trace_digest(keys, times, pops):
     return hashlib.sha256(np.asarray(keys[:n], dtype=np.uint64).tobytes() + np.asarray(times[:n], dtype=np.float64).tobytes()).hexdigest()
 
 
-def check_trial(want, events, objects, t_end, sum_wait, counters, keys, times, what=""):
+def check_trial(want, events, objects, t_end, sum_wait, counters, keys, times, what="", max_queue=None):
     assert int(events) == want["events"], (what, "events", int(events), want["events"])
     assert int(objects) == want["objects"], (what, "objects")
     assert float(t_end).hex() == want["t_end"], (what, "t_end", float(t_end), float.fromhex(want["t_end"]))
@@ -30,6 +30,8 @@ def check_trial(want, events, objects, t_end, sum_wait, counters, keys, times, w
         assert [int(v) for v in counters[:4]] == want["counters"], (what, "counters")
         if want.get("counters8") and int(want.get("all8", 0)):
             assert [int(v) & (2**64 - 1) for v in counters[:8]] == want["counters8"], (what, "all eight counters")
+    if max_queue is not None:                           # the callers pass it for the models whose max_queue is a history's sample count
+        assert int(max_queue) == want["max_queue"], (what, "history samples", int(max_queue), want["max_queue"])
     if keys is not None:
         assert trace_digest(keys, times, events) == want["trace_sha256"], (what, "pop trace")
 

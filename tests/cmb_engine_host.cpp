@@ -46,6 +46,9 @@ static inline unsigned long long __cvta_generic_to_shared(const void *p) { retur
 #include "../cimba_b200/models/hold_general_model.cuh"
 #include "../cimba_b200/models/cheese_model.cuh"
 #include "../cimba_b200/models/harbor_general_model.cuh"
+#include "../cimba_b200/models/guarded_model.cuh"
+#include "../cimba_b200/models/workshop_model.cuh"
+#include "../cimba_b200/models/coverage_models.cuh"
 #include "../examples/tandem_model.cuh"
 
 using namespace cimba_b200;
@@ -79,7 +82,7 @@ static void run_model(uint64_t seed, const cmb::TrialIn &in, cmb::Arena &arena, 
     r.pad = 0u;
 }
 
-// model: 0 = MM1, 1 = GG1, 2 = MMC, 7 = HOLD, 10 = HARBOR, 16 = RENEGE (the CIMBA_B200_MODEL_* numbers), 17 = examples/tandem_model.cuh, 18 = CHEESE (test/test_resourcepool.c).  arena_bytes of growth memory per call.
+// model: 0 = MM1, 1 = GG1, 2 = MMC, 3 / 11 / 13 = the guarded queue tests, 5 / 12 = buffer + resource, 14 = test_resource.c, 7 = HOLD, 10 = HARBOR, 16 = RENEGE (the CIMBA_B200_MODEL_* numbers), 17 = examples/tandem_model.cuh, 18 = CHEESE (test/test_resourcepool.c).  arena_bytes of growth memory per call.
 extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed, uint64_t first, uint64_t count,
                                    uint64_t num_objects, double arr_mean, double srv_mean,
                                    const double *params, uint32_t num_params, uint64_t arena_bytes,
@@ -110,6 +113,15 @@ extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed,
         case 1:  run_model<models::GG1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 7:  run_model<models::HoldGeneral>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 10: run_model<models::HarborGeneral>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 3:  run_model<models::Guarded<false, false>>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 11: run_model<models::Guarded<false, true>>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 13: run_model<models::Guarded<true, true>>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 5:  run_model<models::Workshop<false>>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 12: run_model<models::Workshop<true>>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 14: run_model<models::Tool>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 4:  run_model<models::PoolFight>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 6:  run_model<models::QueueAndTide>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 8:  run_model<models::FrontDesk>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 18: run_model<models::Cheese>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 17: run_model<tandem_example::Tandem>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 2:  run_model<models::MMC>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;

@@ -43,6 +43,22 @@ CASES = [
     (18, 20, 100, 1.0, 1.0, [], 6),               # test/test_resourcepool.c as it stands (20 units, 100 time units)
     (18, 7, 300, 1.0, 1.0, [], 4),
     (17, 1, 20000, 1.05, 1.0, [], 4),
+    (3, 10, 3000, 1.0, 1.0, [], 4),               # test/test_objectqueue.c's workload; a tight queue (both guards busy)
+    (3, 2, 2000, 0.6, 1.0, [], 4),
+    (11, 10, 20000, 1.0, 1.0, [], 3),             # ... with the length history on
+    (13, 10, 20000, 1.0, 1.0, [], 3),             # test/test_priorityqueue.c
+    (13, 3, 3000, 0.7, 1.0, [], 4),
+    (5, 10, 3000, 1.0, 1.0, [], 4),               # buffer + resource with pre-emption under a nuisance
+    (5, 4, 2000, 0.8, 1.0, [], 4),
+    (12, 10, 10000, 1.0, 1.0, [], 3),             # test/test_buffer.c as it stands (trial 0 of the reference's seed is in test_cmb_engine.py)
+    (14, 1, 25, 1.0, 1.0, [], 6),                 # test/test_resource.c as it stands
+    (14, 1, 5000, 1.0, 1.0, [], 3),
+    (4, 8, 3000, 1.0, 1.0, [], 4),                # pool with pre-emption, priority changes, interrupts
+    (4, 3, 2000, 1.0, 1.0, [], 4),
+    (6, 6, 3000, 0.7, 1.0, [], 4),                # priority queue by handle + condition with two predicates
+    (6, 2, 2000, 0.5, 1.0, [], 4),
+    (8, 1, 3000, 1.0, 0.8, [], 4),                # timers, yield / resume, waits on processes and events, an observing guard
+    (8, 1, 2000, 0.4, 1.5, [], 4),
 ]
 
 
@@ -59,7 +75,7 @@ def main():
             _, keys, times = trace_trial(ref, "ref", model, servers, ref.ref_fmix64(MASTER, i), nobj, arr, srv, TRACE)
             h = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
             trials.append({"events": r.events, "objects": r.objects, "t_end": float(r.t_end).hex(), "sum_wait": float(r.sum_wait).hex(),
-                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model in (10, 18)), "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
+                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model in (3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 18)), "max_queue": r.max_queue, "pops": len(keys), "trace_sha256": h.hexdigest()})
         out["cases"].append({"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
                              "srv_mean": float(srv).hex(), "params": params, "trials": trials})
         print(model, servers, nobj, [t["events"] for t in trials])

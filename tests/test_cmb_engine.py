@@ -57,6 +57,8 @@ def test_engine_source_on_the_cpu_matches_the_reference_vectors(host, case):
                     keys[i * TRACE:(i + 1) * TRACE], times[i * TRACE:(i + 1) * TRACE], f"trial {i}")
         if case["model"] == 2:
             assert out[i].max_queue == want["max_queue"]        # process structs ever created
+        if case["model"] in (11, 12, 13, 14):
+            assert out[i].max_queue == want["max_queue"]        # samples in the recorded history
 
 
 def test_engine_matches_the_live_reference_build(host):
@@ -120,3 +122,36 @@ def test_engine_reproduces_the_reference_condition_golden_file(host):
     assert (c[0], c[1]) == (328781, 109454) and ("%.4g" % f(c[2]), "%.4g" % f(c[3])) == ("10.91", "17.48")
     assert c[4] == 1736975 and "%.4g" % f(c[5]) == "0.8025"
     assert (c[6] & 0xffffffff, c[6] >> 32) == (645947, 217380)
+
+
+def _double(u):
+    import struct
+    return struct.unpack("<d", struct.pack("<Q", int(u) & (2**64 - 1)))[0]
+
+
+@pytest.mark.parametrize("model", [11, 13])
+def test_engine_reproduces_the_reference_queue_golden_files(host, model):
+    """test/reference/objectqueue.txt (model 11, cmb_objectqueue) and priorityqueue.txt (model 13, cmb_priorityqueue): the
+    reference's queue tests written against the authoring surface (cimba_b200/models/guarded_model.cuh), seeded like the
+    tests, capacity 10, 1e6 time units: length history N 5689021, time-weighted mean 5.008."""
+    case = {"model": model, "servers": 10, "num_objects": 1_000_000, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
+    assert out[0].status == 0 and out[0].max_queue == 5689021 and "%.4g" % _double(out[0].counter[6]) == "5.008"
+
+
+def test_engine_reproduces_the_reference_buffer_golden_file(host):
+    """test/reference/buffer.txt: test/test_buffer.c on the engine's cmb_buffer (cimba_b200/models/workshop_model.cuh), capacity 10,
+    10 000 time units: level history N 41876, time-weighted mean 4.980."""
+    case = {"model": 12, "servers": 10, "num_objects": 10_000, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
+    assert out[0].status == 0 and out[0].max_queue == 41876 and "%.3f" % _double(out[0].counter[4]) == "4.980"
+
+
+def test_engine_reproduces_the_reference_resource_golden_file(host):
+    """test/reference/resource.txt: test/test_resource.c on the engine's cmb_resource with pre-emption: history N 30, mean 0.9816,
+    one pre-emption - Target_3 loses the resource at t = 6.3280 - in a run of 85 events."""
+    case = {"model": 14, "servers": 1, "num_objects": 25, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, 1, master=inverse_fmix64(0x34F05C64D7AD598F))
+    c = list(out[0].counter)
+    assert out[0].status == 0 and out[0].events == 85 and out[0].max_queue == 30
+    assert "%.4f" % _double(c[3]) == "0.9816" and "%.4f" % _double(c[4]) == "6.3280" and c[5] == 3 and c[1] == 1

@@ -23,7 +23,11 @@ from oracle_libs import load_port, load_ref, run_trials
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 10: cb.MODEL_HARBOR, 16: cb.MODEL_RENEGE,
-           18: cb.MODEL_POOL_RECORDED}
+           18: cb.MODEL_POOL_RECORDED,
+           # the reference's own test worlds: since round 2 they run on the general engine by default
+           3: cb.MODEL_GUARDED, 4: cb.MODEL_PREEMPT, 5: cb.MODEL_BUFFER, 6: cb.MODEL_PRIOQ, 8: cb.MODEL_TIMERS,
+           11: cb.MODEL_GUARDED_RECORDED, 12: cb.MODEL_BUFFER_RECORDED, 13: cb.MODEL_PRIOQ_RECORDED, 14: cb.MODEL_RESOURCE_RECORDED}
+COVERAGE = (3, 4, 5, 6, 8, 11, 12, 13, 14)
 
 
 def run_case(case, model_id, variant, n, trace=True, spill=0):
@@ -40,14 +44,15 @@ def compare(case, res, n):
     tt = res.trace_time.cpu().numpy() if res.trace_time is not None else None
     assert (res.status.cpu().numpy()[:n] == 0).all(), res.status.cpu().numpy()[:n]
     for i, want in enumerate(case["trials"][:n]):
-        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18) else None,
-                    tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}")
+        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18) + COVERAGE else None,
+                    tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}",
+                    max_queue=int(res.max_queue[i]) if case["model"] in (11, 12, 13, 14) else None)
 
 
 @pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in BUILTIN], ids=case_id)
 def test_models_on_the_general_engine_match_the_reference_vectors(case):
     n = len(case["trials"])
-    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) else 0, n)
+    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) + COVERAGE else 0, n)
     compare(case, res, n)
 
 
