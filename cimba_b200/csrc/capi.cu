@@ -153,8 +153,9 @@ int launch_general(const cimba_b200_device_job *job, unsigned char *arena, uint6
     return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, what);
 }
 
-// the reference's own test worlds (models 3-6, 8, 11-14) run on the general engine; variant 1 = the fixed-capacity
-// kernels they had in round 1 (csrc/general.cuh), kept for A/B runs
+// the reference's own test worlds (models 3-6, 8, 11-14): like M/M/1, G/G/1 and M/M/c they have a fixed-capacity kernel
+// (csrc/general.cuh, 2.5-6x the engine's speed, profiles/r02_engine.md) behind which the general engine re-runs whatever that
+// kernel flags; a capacity its tables cannot hold, or CIMBA_B200_VARIANT_GENERAL, goes to the engine directly
 bool coverage_goes_general(const cimba_b200_device_job *job);
 
 template <template <class> class F, class... A>
@@ -204,14 +205,19 @@ bool is_general_model(int m)
 
 bool coverage_goes_general(const cimba_b200_device_job *job)
 {
-    return is_general_model(job->model) && job->variant != 1;
+    if (!is_general_model(job->model)) return false;
+    if (job->variant == CIMBA_B200_VARIANT_GENERAL) return true;
+    const int m = job->model;
+    if (m == CIMBA_B200_MODEL_TIMERS || m == CIMBA_B200_MODEL_RESOURCE_RECORDED || m == CIMBA_B200_MODEL_PREEMPT ||
+        m == CIMBA_B200_MODEL_BUFFER || m == CIMBA_B200_MODEL_BUFFER_RECORDED) return false;      // no table sized by `servers`
+    return job->servers > ((m == CIMBA_B200_MODEL_PRIOQ || m == CIMBA_B200_MODEL_PRIOQ_RECORDED) ? 15 : 16);
 }
 
 template <class Model>
 struct LaunchOf {
-    static int call(const cimba_b200_device_job *job, cudaStream_t st)
+    static int call(const cimba_b200_device_job *job, unsigned char *arena, uint64_t bytes, uint32_t only_flagged, cudaStream_t st)
     {
-        return launch_general<Model>(job, (unsigned char *)job->workspace, job->workspace_bytes, 0u, st, "trial_kernel launch");
+        return launch_general<Model>(job, arena, bytes, only_flagged, st, only_flagged ? "repair pass" : "trial_kernel launch");
     }
 };
 
@@ -413,7 +419,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
         return job->num_trials * (uint64_t)AWACS_STATE_BYTES;
     }
     if (is_general_model(job->model)) {
-        return job->num_trials * (uint64_t)sizeof(GeneralState);
+        return align256(job->num_trials * (uint64_t)sizeof(GeneralState)) + repair_arena_bytes(job);
     }
     return 0u;
 }
@@ -453,7 +459,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         if (!no_capacity && job->servers < 1) return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
-        return for_coverage_model<LaunchOf>(job->model, job, st);
+        return for_coverage_model<LaunchOf>(job->model, job, (unsigned char *)job->workspace, job->workspace_bytes, 0u, st);
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
@@ -591,8 +597,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const bool pre = job->model == CIMBA_B200_MODEL_PREEMPT;
         const bool buf = job->model == CIMBA_B200_MODEL_BUFFER || job->model == CIMBA_B200_MODEL_BUFFER_RECORDED;
         const bool pq13 = job->model == CIMBA_B200_MODEL_PRIOQ_RECORDED;
-        if (!tmr && (job->servers < 1 || (!pre && !buf && job->servers > ((prq || pq13) ? 15 : 16))))
-            return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1 (and <= 16 for CIMBA_B200_MODEL_GUARDED)");
+        if (!tmr && job->servers < 1) return fail(CIMBA_B200_EINVAL, "capacity (servers) must be >= 1");
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "MODEL_GUARDED supports CIMBA_B200_MAP_LANE only");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
@@ -648,7 +653,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         }
         g_launches++;
         cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "guarded_kernel launch");
+        if (e != cudaSuccess) return cuda_fail(e, "guarded_kernel launch");
+        if (job->status == nullptr) return CIMBA_B200_OK;
+        return for_coverage_model<LaunchOf>(job->model, job, (unsigned char *)job->workspace + align256(job->num_trials * (uint64_t)sizeof(GeneralState)),
+                                            repair_arena_bytes(job), REPAIR_BITS, st);
     }
     if (job->model == CIMBA_B200_MODEL_HARBOR) {
         if (job->servers < 3 || job->servers > 255)

@@ -532,6 +532,7 @@ struct Sim {
     // share them this way.  Nothing happens between the body's return and the command, so the order of key issues and
     // random draws is the reference's.
     FlipCache      flips;               // cmb_random_flip's 64 cached coin flips (src/cmb_random.c: one draw serves 64 calls)
+    uint32_t       fel_high;            // the deepest the event list was at a pop (what the oracle calls max_fel)
     uint32_t       cmd;
     uint32_t       cmd_demand;
     int32_t        cmd_ctx;
@@ -550,6 +551,7 @@ struct Sim {
         current_event = 0u;
         guard_seq = 0u;
         pops = 0u;
+        fel_high = 0u;
         arena = a;
         fel.init(fel_store, FEL_INLINE_EXP);
         proc = proc_inline;
@@ -1491,6 +1493,7 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
     for (;;) {
         // a trial whose containers could not grow (workspace too small) is void: stop it where it stands, flagged
         if (sim.status & TRIAL_ERR_ARENA) return;
+        if (sim.fel.count > sim.fel_high) sim.fel_high = sim.fel.count;        // the deepest the event list was when an event was taken
         if (!sim.fel.dequeue()) return;
         const Tag ev = sim.fel.tag[0];
         sim.now = ev.d;

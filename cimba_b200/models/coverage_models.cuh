@@ -124,13 +124,13 @@ struct PoolFight {
     }
     CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return false; }
 
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    CMB_FN void finish(cmb::Sim &sim, cmb::TrialOut &out)
     {
         counter[6] = cmb_resourcepool_in_use(pool);
         for (uint32_t i = 0u; i < 8u; i++) out.counters[i] = counter[i];
         out.objects = counter[0] + counter[1];
         out.sum_wait = sum_wait;
-        out.max_queue = 0u;
+        out.max_queue = sim.fel_high;
     }
 };
 
@@ -316,13 +316,13 @@ struct QueueAndTide {
 
     CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t ctx) { return level >= threshold[ctx]; }
 
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    CMB_FN void finish(cmb::Sim &sim, cmb::TrialOut &out)
     {
         counter[7] = cmb_priorityqueue_length(pq);
         for (uint32_t i = 0u; i < 8u; i++) out.counters[i] = counter[i];
         out.objects = counter[0];
         out.sum_wait = sum_wait;
-        out.max_queue = 0u;
+        out.max_queue = sim.fel_high;
     }
 };
 
@@ -549,12 +549,12 @@ struct FrontDesk {
 
     CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return desk.holder == cmb::NIL; }
 
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    CMB_FN void finish(cmb::Sim &sim, cmb::TrialOut &out)
     {
         for (uint32_t i = 0u; i < 8u; i++) out.counters[i] = counter[i];
         out.objects = counter[0];
         out.sum_wait = sum_wait;
-        out.max_queue = 0u;
+        out.max_queue = sim.fel_high;
     }
 };
 

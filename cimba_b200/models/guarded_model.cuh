@@ -123,7 +123,7 @@ struct Guarded {
     CMB_FN void finish(cmb::Sim &sim, cmb::TrialOut &out)
     {
         counter[6] = PRIORITY ? cmb_priorityqueue_length(pq) : cmb_objectqueue_length(queue);
-        out.max_queue = 0u;
+        out.max_queue = sim.fel_high;
         if (PRIORITY) {
             cmb_priorityqueue_recording_stop(pq);
             counter[6] = (uint64_t)__double_as_longlong(pq.history.acc.m1);

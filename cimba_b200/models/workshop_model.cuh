@@ -153,7 +153,7 @@ struct Workshop {
     CMB_FN void finish(cmb::Sim &sim, cmb::TrialOut &out)
     {
         counter[7] = cmb_buffer_level(store);
-        out.max_queue = 0u;
+        out.max_queue = sim.fel_high;
         if (PLAIN) {
             cmb_buffer_recording_stop(store);
             counter[4] = (uint64_t)__double_as_longlong(store.history.acc.m1);

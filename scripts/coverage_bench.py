@@ -1,5 +1,5 @@
-"""The reference's own test worlds (models 3-6, 8, 11-14) on the general engine (variant 0, the default since round 2) next to
-the fixed-capacity kernels they had in round 1 (variant 1): same trials, same answers, CUDA-event timed.
+"""The reference's own test worlds (models 3-6, 8, 11-14) on the general engine (CIMBA_B200_VARIANT_GENERAL) next to their
+fixed-capacity kernels (variant 0: csrc/general.cuh + the engine as repair pass): same trials, same answers, CUDA-event timed.
 
     python scripts/coverage_bench.py [--trials 32768] [--duration 200] [--out gpurun_out/coverage_bench.json]"""
 import argparse
@@ -37,7 +37,7 @@ def main():
         am = torch.full((a.trials,), arr, dtype=torch.float64, device=dev)
         sm = torch.full((a.trials,), srv, dtype=torch.float64, device=dev)
         out = {}
-        for label, variant in (("engine", 0), ("round1_kernel", 1)):
+        for label, variant in (("engine", cb.VARIANT_GENERAL), ("round1_kernel", 0)):
             bufs = cb.TrialBuffers(a.trials, dev, 0, model, servers, variant)
             cb.launch_trials(am[:256], sm[:256], num_objects=20, master_seed=1, model=model, servers=servers, variant=variant)
             res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=a.duration, master_seed=MASTER, model=model, servers=servers,

@@ -20,12 +20,30 @@ runs = [
     dict(model=cb.MODEL_HARBOR, n=40, arr=2.0, srv=8.0, size=200, servers=10),
     dict(model=cb.MODEL_HARBOR, n=40, arr=1.5, srv=10.0, size=300, servers=5),     # on-chip overflow -> repair pass
     dict(model=cb.MODEL_HARBOR, n=70, arr=2.0, srv=8.0, size=100, servers=10, variant=2),
+    # the general engine: every model written against the authoring surface
+    dict(model=cb.MODEL_MM1, n=64, arr=1 / 0.9, srv=1.0, size=300, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_GG1, n=64, arr=1.25, srv=1.0, size=300, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_MMC, n=64, arr=1 / 60.0, srv=1.0, size=300, servers=64),
+    dict(model=cb.MODEL_RENEGE, n=8, arr=3.0, srv=1.0, size=10, servers=1000, params=[0.7]),
+    dict(model=cb.MODEL_POOL_RECORDED, n=64, arr=1.0, srv=1.0, size=60, servers=20),
+    dict(model=cb.MODEL_HOLD, n=8, arr=1.0, srv=1.0, size=3, servers=2000, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_HARBOR, n=32, arr=2.0, srv=8.0, size=150, servers=10, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_GUARDED, n=64, arr=0.5, srv=1.0, size=60, servers=100),
+    dict(model=cb.MODEL_GUARDED_RECORDED, n=64, arr=1.0, srv=1.0, size=60, servers=10, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_PRIOQ_RECORDED, n=64, arr=0.5, srv=1.0, size=60, servers=40),
+    dict(model=cb.MODEL_PREEMPT, n=64, arr=1.0, srv=1.0, size=60, servers=20, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_BUFFER, n=64, arr=1.0, srv=1.0, size=60, servers=10, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_BUFFER_RECORDED, n=64, arr=1.0, srv=1.0, size=60, servers=10, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_PRIOQ, n=64, arr=0.7, srv=1.0, size=60, servers=8, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_TIMERS, n=64, arr=1.0, srv=0.6, size=60, variant=cb.VARIANT_GENERAL),
+    dict(model=cb.MODEL_RESOURCE_RECORDED, n=64, arr=1.0, srv=1.0, size=60, variant=cb.VARIANT_GENERAL),
 ] + [dict(model=cb.MODEL_HOLD, n=9, arr=1.0, srv=1.0, size=4, servers=w, variant=v)
      for v in (1, 2, 3, 4) for w in (40, 600)] + [dict(model=cb.MODEL_HOLD, n=5, arr=1.0, srv=1.0, size=2, servers=3000, variant=v)
                                                    for v in (2, 3, 4)]
 for r in runs:
     res = cb.run_trials(r["n"], arr_mean=r["arr"], srv_mean=r["srv"], num_objects=r["size"], master_seed=K,
-                        model=r["model"], servers=r.get("servers", 1), variant=r.get("variant", 0))
+                        model=r["model"], servers=r.get("servers", 1), variant=r.get("variant", 0), params=r.get("params", ()))
+    assert int(res.status.abs().sum()) == 0 or r["model"] == cb.MODEL_MM1, (r, res.status.cpu().tolist())
     print(r["model"], r.get("variant", 0), res.total_events(), flush=True)
 x = torch.rand(1000, dtype=torch.float64, device="cuda")
 w = torch.rand(1000, dtype=torch.float64, device="cuda")

@@ -59,6 +59,8 @@ def test_engine_source_on_the_cpu_matches_the_reference_vectors(host, case):
             assert out[i].max_queue == want["max_queue"]        # process structs ever created
         if case["model"] in (11, 12, 13, 14):
             assert out[i].max_queue == want["max_queue"]        # samples in the recorded history
+        if case["model"] in (3, 4, 5, 6, 8):
+            assert out[i].max_queue == want["max_fel"]          # the deepest the event list was at a pop
 
 
 def test_engine_matches_the_live_reference_build(host):

@@ -47,12 +47,14 @@ def compare(case, res, n):
         check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18) + COVERAGE else None,
                     tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}",
                     max_queue=int(res.max_queue[i]) if case["model"] in (11, 12, 13, 14) else None)
+        if case["model"] in (3, 4, 5, 6, 8):
+            assert int(res.max_queue[i]) == want["max_fel"]
 
 
 @pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in BUILTIN], ids=case_id)
 def test_models_on_the_general_engine_match_the_reference_vectors(case):
     n = len(case["trials"])
-    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) + COVERAGE else 0, n)
+    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) else 0, n)
     compare(case, res, n)
 
 
@@ -106,6 +108,20 @@ def test_general_engine_against_the_oracle_at_other_sizes():
         assert res.status.abs().sum().item() == 0
         for i, w in enumerate(want):
             assert (ev[i], te[i], sw[i]) == (w.events, w.t_end, w.sum_wait), (model, i)
+
+
+@pytest.mark.parametrize("model,servers", [(3, 40), (3, 1000), (13, 64), (6, 33), (11, 200)])
+def test_queue_capacities_the_round_one_tables_could_not_hold(model, servers):
+    """Capacities beyond 16 (15 for the priority queue) used to be refused; they go to the general engine now."""
+    port = load_port()
+    n, dur = 64, 300
+    res = cb.run_trials(n, arr_mean=0.5, srv_mean=1.0, num_objects=dur, master_seed=MASTER, model=BUILTIN[model], servers=servers)
+    want = run_trials(port, "port", model, servers, MASTER, 0, n, dur, 0.5, 1.0)
+    assert res.status.abs().sum().item() == 0
+    ev, te, sw, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist(), res.counters.cpu().numpy()
+    for i, w in enumerate(want):
+        assert (ev[i], te[i], sw[i]) == (w.events, w.t_end, w.sum_wait), (model, i)
+        assert [int(v) & (2**64 - 1) for v in cnt[i]] == list(w.counter), (model, i)
 
 
 def test_reneging_model_against_the_live_reference_build():
