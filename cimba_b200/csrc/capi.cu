@@ -117,6 +117,11 @@ bool fast_goes_general(const cimba_b200_device_job *job)
     return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_GENERAL;
 }
 
+bool goes_static(const cimba_b200_device_job *job)
+{
+    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_STATIC;
+}
+
 bool hold_goes_general(const cimba_b200_device_job *job)
 {
     return job->model == CIMBA_B200_MODEL_HOLD && job->variant == CIMBA_B200_VARIANT_GENERAL;
@@ -399,6 +404,10 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
     if (harbor_goes_general(job)) return cmb::workspace_bytes_for<models::HarborGeneral>(*job);
+    if (goes_static(job)) {
+        return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_static<models::MM1T, 2, 1>(*job)
+                                                  : cmb::workspace_bytes_static<models::GG1T, 2, 1>(*job);
+    }
     if (fast_goes_general(job)) {
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_for<models::MM1>(*job)
                                                   : cmb::workspace_bytes_for<models::GG1>(*job);
@@ -452,6 +461,15 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         const int e = um->launch(job, stream);
         g_launches++;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, um->name.c_str());
+    }
+    if (goes_static(job)) {
+        if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the static tier runs one trial per lane (CIMBA_B200_MAP_LANE)");
+        if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
+            return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
+        const int e = job->model == CIMBA_B200_MODEL_MM1 ? cmb::launch_static_model<models::MM1T, 2, 1>(*job, st)
+                                                         : cmb::launch_static_model<models::GG1T, 2, 1>(*job, st);
+        g_launches += job->status != nullptr ? 2 : 1;
+        return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, "static_trial_kernel launch");
     }
     if (coverage_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");

@@ -506,6 +506,7 @@ struct condition {
 // (static dispatch: the kernel is instantiated per model type, nothing is called through a pointer)
 
 struct Sim {
+    using queue_type = objectqueue;     // what a model template declares its queues as (cmb_static.cuh has another)
     Sfc64          rng;
     const ZigHot  *hot;
     double         now;
@@ -898,6 +899,15 @@ struct Sim {
         g.heap.init(g.store, GUARD_INLINE_EXP);
         g.owner = owner;
         g.observers[0] = g.observers[1] = 0u;
+    }
+
+    // what CMB_GUARD_WAIT_ records for the dispatcher (the static tier, cmb_static.cuh, registers the waiter at once instead)
+    CMB_FN void guard_wait_cmd(resourceguard &g, uint32_t, uint32_t demand, int32_t ctx)
+    {
+        cmd_guard = &g;
+        cmd_demand = demand;
+        cmd_ctx = ctx;
+        cmd = CMD_GUARD_WAIT;
     }
 
     CMB_FN void guard_wait_begin(resourceguard &g, uint32_t pid, uint32_t demand, int32_t ctx)     // :125-152
@@ -1581,7 +1591,7 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 
 // cmb_resourceguard_wait up to its yield: the wait-list insert is left to the dispatcher
 #define CMB_GUARD_WAIT_(g, demand, ctx) \
-    do { sim.cmd_guard = &(g); sim.cmd_demand = (demand); sim.cmd_ctx = (ctx); sim.cmd = cimba_b200::cmb::CMD_GUARD_WAIT; CMB_YIELD_(); } while (0)
+    do { sim.guard_wait_cmd((g), me, (demand), (ctx)); CMB_YIELD_(); } while (0)
 
 // cmb_process_hold(dur)
 #define CMB_PROCESS_HOLD(dur)    do { sim.cmd_value = (dur); sim.cmd = cimba_b200::cmb::CMD_HOLD; CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)

@@ -9,6 +9,7 @@
 
 #include "../../include/cimba_b200.h"
 #include "cmb_kernel.cuh"
+#include "cmb_static.cuh"
 
 namespace cimba_b200 {
 namespace cmb {
@@ -91,8 +92,91 @@ int launch_model(const cimba_b200_device_job &job, unsigned char *arena, uint64_
     return (int)cudaGetLastError();
 }
 
+// ---- the static tier (cmb_static.cuh): ModelT<StaticSim<NPROC, NQUEUE>> first, ModelT<Sim> for what it flags
+constexpr uint32_t STATIC_REPAIR_BITS = CIMBA_B200_TRIAL_QUEUE_OVERFLOW | CIMBA_B200_TRIAL_FEL_OVERFLOW |
+                                        CIMBA_B200_TRIAL_GUARD_OVERFLOW | CIMBA_B200_TRIAL_PROC_OVERFLOW;
+
+inline uint32_t static_spill_cap(const cimba_b200_device_job &job)     // HBM ring entries per queue and trial (a power of two)
+{
+    const uint64_t c = job.queue_spill_cap;
+    if (c == 0u) return 512u;
+    return (c & (c - 1u)) == 0u && c <= (1ull << 26) ? (uint32_t)c : 0u;
+}
+
+inline uint64_t static_rings_bytes(const cimba_b200_device_job &job, int nqueue)
+{
+    const uint64_t b = job.num_trials * (uint64_t)nqueue * static_spill_cap(job) * sizeof(double);
+    return (b + 255u) & ~(uint64_t)255u;
+}
+
+template <template <class> class ModelT, int NPROC, int NQUEUE>
+uint64_t workspace_bytes_static(const cimba_b200_device_job &job)
+{
+    // the rings of the static kernel, then the growth arena of its repair pass (a share of the trials, not all of them)
+    const uint64_t arena = ARENA_HEADER + (job.num_trials / 8u + 256u) * ArenaNeed<ModelT<Sim>>::per_trial(job) + (64ull << 20);
+    return static_rings_bytes(job, NQUEUE) + arena;
+}
+
+template <template <class> class ModelT, int NPROC, int NQUEUE>
+int launch_static_model(const cimba_b200_device_job &job, cudaStream_t stream)
+{
+    const uint32_t cap = static_spill_cap(job);
+    const uint64_t rings = static_rings_bytes(job, NQUEUE);
+    if (cap == 0u || job.workspace == nullptr || job.workspace_bytes < workspace_bytes_static<ModelT, NPROC, NQUEUE>(job))
+        return (int)cudaErrorInvalidValue;
+    StaticArgs sa{};
+    LaunchArgs &a = sa.base;
+    a.master_seed = job.master_seed;
+    a.first_trial = job.first_trial;
+    a.num_trials = job.num_trials;
+    a.num_objects = job.num_objects;
+    a.servers = job.servers;
+    a.arr_mean = job.arr_mean;
+    a.srv_mean = job.srv_mean;
+    a.events = job.events;
+    a.objects = job.objects;
+    a.t_end = job.t_end;
+    a.sum_wait = job.sum_wait;
+    a.status = job.status;
+    a.max_queue = job.max_queue;
+    a.counters = job.counters;
+    a.trace_cap = job.trace_cap;
+    a.trace_key = job.trace_key;
+    a.trace_time = job.trace_time;
+    a.diag = (unsigned long long *)job.diag;
+    a.num_params = job.params != nullptr ? (job.num_params < 16u ? job.num_params : 16u) : 0u;
+    for (uint32_t k = 0; k < a.num_params; k++) a.params[k] = job.params[k];
+    sa.spill = (double *)job.workspace;
+    sa.spill_cap = cap;
+    const uint64_t blocks = (job.num_trials + STATIC_BLOCK - 1) / STATIC_BLOCK;
+    if (blocks == 0u || blocks > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    const bool trace = job.trace_cap > 0u;
+    const void *fn = trace ? (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, true>
+                           : (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, false>;
+    void *kargs[] = { (void *)&sa };
+    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(STATIC_BLOCK), kargs, 0, stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
+    if (e != cudaSuccess || job.status == nullptr) return (int)e;      // nobody could see a flag: nothing to repair by
+    return launch_model<ModelT<Sim>>(job, (unsigned char *)job.workspace + rings, job.workspace_bytes - rings, STATIC_REPAIR_BITS, stream);
+}
+
 }  // namespace cmb
 }  // namespace cimba_b200
+
+// A model template of the static tier in a library of its own: ModelT<cmb::StaticSim<NPROC, NQUEUE>> runs first, and
+// ModelT<cmb::Sim> re-runs what that flags
+#define CMB_EXPORT_STATIC_MODEL(ModelT, NPROC, NQUEUE, name_string)                                                   \
+    extern "C" const char *cimba_b200_user_model_name(void) { return name_string; }                                  \
+    extern "C" uint64_t cimba_b200_user_model_workspace_bytes(const cimba_b200_device_job *job)                      \
+    {                                                                                                                 \
+        return job ? cimba_b200::cmb::workspace_bytes_static<ModelT, NPROC, NQUEUE>(*job) : 0u;                       \
+    }                                                                                                                 \
+    extern "C" int cimba_b200_user_model_launch(const cimba_b200_device_job *job, void *stream)                      \
+    {                                                                                                                 \
+        if (job == nullptr || job->workspace == nullptr) return (int)cudaErrorInvalidValue;                          \
+        return cimba_b200::cmb::launch_static_model<ModelT, NPROC, NQUEUE>(*job, (cudaStream_t)stream);               \
+    }
 
 // A model in a library of its own: the three C entry points cimba_b200_model_load() looks up.
 #define CMB_EXPORT_MODEL(Model, name_string)                                                                          \

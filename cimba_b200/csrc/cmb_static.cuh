@@ -1,0 +1,422 @@
+// cmb_static.cuh - the static tier of the authoring surface.
+//
+// The general engine (cmb_device.cuh) runs ANY model, and pays for it: every container is in memory and grows.  Many models
+// need none of that: a FIXED set of processes that only hold and wait at queues - the benchmark's M/M/1
+// (benchmark/MM1_multi.c:52-125), G/G/1, a tandem line.  For those, the same model text - the same CMB_PROCESS_* /
+// CMB_OBJECTQUEUE_* macros, the same cmb_* names - compiles against cmb::StaticSim<NPROC, NQUEUE> instead of cmb::Sim:
+//   * the event list is one slot per process in registers (SlotFel, engine.cuh): a process that can only hold or wait owns at
+//     most one pending event, so an insert is a register write and pop-min an NPROC-way compare;
+//   * process records, guards (a bit and a sequence number per process) and the model struct stay in registers: process ids
+//     are compile-time constants after inlining, nothing takes an address;
+//   * a queue is a ring with its oldest 32 entries in shared memory and the rest in an HBM ring (StampRing, engine.cuh);
+//   * blocking calls are commands carried out by the dispatcher where the warp is together, and the ziggurat's slow path
+//     is taken by parked lanes in batches - as in the fused kernels (queue_model.cuh, whose shape this generalises).
+// What the tier does NOT have - process creation beyond NPROC, priorities other than 0, timers, interrupts, a queue that
+// outgrows window + ring - is not an error: the trial is flagged and the launch re-runs it on the general engine from the SAME
+// model template (launch_static_model below), so the answer is the reference's either way.
+//
+// A model is `template <class S> struct M` with S = cmb::Sim or cmb::StaticSim<...>, its queues declared as
+// `typename S::queue_type`, exported with CMB_EXPORT_STATIC_MODEL(M, NPROC, NQUEUE, "name").
+#pragma once
+
+#include "cmb_kernel.cuh"
+
+namespace cimba_b200 {
+namespace cmb {
+
+constexpr int STATIC_WINDOW = 32;       // on-chip entries per queue and trial
+constexpr int STATIC_BLOCK = 64;
+
+// the wait list of a guard whose only possible waiters are the NPROC processes: who waits, and since when (FIFO)
+template <int NPROC>
+struct static_guard {
+    uint32_t waiting;
+    uint32_t seq[NPROC];
+};
+
+template <int NPROC>
+struct static_objectqueue {
+    static_guard<NPROC> front, rear;
+    StampRing<STATIC_WINDOW> ring;
+    uint64_t capacity;
+    uint32_t longest;
+};
+
+template <int NPROC, int NQUEUE>
+struct StaticSim {
+    using queue_type = static_objectqueue<NPROC>;
+    struct Proc {
+        uint32_t pc, status, kind, ctx;
+        double   f[2];
+        uint64_t u[2];
+        int64_t  exit_value;
+    };
+    Sfc64          rng;
+    const ZigHot  *hot;
+    double         now;
+    uint32_t       status;
+    uint32_t       current;
+    uint32_t       current_event;
+    uint64_t       pops;
+    uint32_t       nproc, nqueue, guard_seq;
+    Proc           proc[NPROC];
+    SlotFel<NPROC> fel;
+    uint32_t       cmd;
+    double         cmd_value;
+    int64_t        cmd_exit;
+    // where this trial's queues live: column `tid` of the CTA's shared-memory rings, and its HBM rings
+    double        *ring_win;
+    uint32_t       ring_stride;
+    double        *spill;
+    uint32_t       spill_cap;
+
+    CMB_FN void init(uint64_t seed, const ZigHot *tables, double *win, uint32_t stride, double *spill_rings, uint32_t cap)
+    {
+        rng.seed(seed);
+        hot = tables;
+        now = 0.0;
+        status = 0u;
+        current = NIL;
+        current_event = 0u;
+        pops = 0u;
+        nproc = nqueue = guard_seq = 0u;
+        fel.clear();
+        cmd = CMD_NONE;
+        cmd_value = 0.0;
+        cmd_exit = 0;
+        ring_win = win;
+        ring_stride = stride;
+        spill = spill_rings;
+        spill_cap = cap;
+#pragma unroll
+        for (int i = 0; i < NPROC; i++) {
+            proc[i].pc = 0u;
+            proc[i].status = PROC_CREATED;
+            proc[i].kind = 0u;
+            proc[i].ctx = 0u;
+            proc[i].f[0] = proc[i].f[1] = 0.0;
+            proc[i].u[0] = proc[i].u[1] = 0u;
+            proc[i].exit_value = 0;
+        }
+    }
+
+    // cmb_process_create + cmb_process_initialize.  One process more than the tier holds, or a priority: the trial goes
+    // to the general engine.
+    CMB_FN uint32_t process_create(uint32_t kind, int64_t prio, uint32_t ctx)
+    {
+        const uint32_t id = nproc;
+        if (id >= (uint32_t)NPROC || prio != 0) {
+            status |= TRIAL_ERR_PROC_OVERFLOW;
+            return 0u;
+        }
+        nproc = id + 1u;
+#pragma unroll
+        for (int i = 0; i < NPROC; i++) {
+            if ((uint32_t)i == id) {
+                proc[i].kind = kind;
+                proc[i].ctx = ctx;
+                proc[i].status = PROC_CREATED;
+            }
+        }
+        return id;
+    }
+
+    CMB_FN void process_start(uint32_t pid)             // src/cmb_process.c:127-135
+    {
+        if (!fel.schedule((int)pid, ACT_START, now)) status |= TRIAL_ERR_FEL_OVERFLOW;
+    }
+
+    CMB_FN int64_t hold_end(uint32_t, int64_t sig) { return sig; }          // nobody interrupts here
+
+    // cmb_resourceguard_wait up to its yield (src/cmb_resourceguard.c:125-152)
+    CMB_FN void guard_wait_cmd(static_guard<NPROC> &g, uint32_t pid, uint32_t, int32_t)
+    {
+        const uint32_t s = ++guard_seq;
+        g.waiting |= 1u << pid;
+#pragma unroll
+        for (int i = 0; i < NPROC; i++) {
+            if ((uint32_t)i == pid) g.seq[i] = s;
+        }
+        cmd = CMD_NONE;
+    }
+
+    CMB_FN int64_t guard_wait_end(static_guard<NPROC> &, uint32_t, int64_t sig) { return sig; }
+
+    // cmb_resourceguard_signal (:202-226): the HEAD waiter, if its demand holds - `ok`, which the caller knows (every waiter
+    // of a queue's front guard wants content, of its rear guard space)
+    CMB_FN void guard_signal(static_guard<NPROC> &g, bool ok)
+    {
+        if (g.waiting == 0u || !ok) return;
+        uint32_t head = 0u, best = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < NPROC; i++) {
+            const bool here = ((g.waiting >> i) & 1u) != 0u && g.seq[i] < best;
+            if (here) {
+                head = (uint32_t)i;
+                best = g.seq[i];
+            }
+        }
+        g.waiting &= ~(1u << head);
+        if (!fel.schedule((int)head, ACT_WAKE_RESOURCE, now)) status |= TRIAL_ERR_FEL_OVERFLOW;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ objectqueue
+template <int NPROC, int NQUEUE>
+CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC> &q, uint64_t capacity)
+{
+    uint32_t k = sim.nqueue;
+    if (k >= (uint32_t)NQUEUE) {
+        sim.status |= TRIAL_ERR_PROC_OVERFLOW;
+        k = 0u;
+    }
+    sim.nqueue = k + 1u;
+    q.front.waiting = q.rear.waiting = 0u;
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) q.front.seq[i] = q.rear.seq[i] = 0u;
+    q.ring.init(sim.ring_win + (size_t)k * STATIC_WINDOW * sim.ring_stride, sim.ring_stride,
+                sim.spill_cap ? sim.spill + (size_t)k * sim.spill_cap : nullptr, sim.spill_cap);
+    q.capacity = capacity;
+    q.longest = 0u;
+}
+
+template <class Model, int NPROC, int NQUEUE>
+CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC> &q, uint64_t obj)
+{
+    if ((uint64_t)q.ring.len >= q.capacity) return false;
+    if (!q.ring.put(__longlong_as_double((long long)obj))) sim.status |= TRIAL_ERR_QUEUE_OVERFLOW;     // void from here on: re-run
+    q.longest = q.ring.len > q.longest ? q.ring.len : q.longest;
+    sim.guard_signal(q.front, true);
+    return true;
+}
+
+template <class Model, int NPROC, int NQUEUE>
+CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC> &q, uint64_t &obj)
+{
+    if (q.ring.len == 0u) return false;
+    obj = (uint64_t)__double_as_longlong(q.ring.take());
+    sim.guard_signal(q.rear, true);
+    return true;
+}
+
+// cmb_process_stop (src/cmb_process.c:698-723) as far as this tier can need it: the process's pending event goes, it is
+// FINISHED; an entry it may have in a guard stays and will swallow one signal
+template <class Model, int NPROC, int NQUEUE>
+CMB_FN void process_stop(StaticSim<NPROC, NQUEUE> &sim, Model &, uint32_t pid, int64_t value)
+{
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if ((uint32_t)i == pid && sim.proc[i].status == PROC_RUNNING) {
+            sim.proc[i].status = PROC_FINISHED;
+            sim.proc[i].exit_value = value;
+            sim.fel.t[i] = __longlong_as_double(0x7ff0000000000000LL);
+            sim.fel.key[i] = 0u;
+            sim.fel.act[i] = ACT_NONE;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatcher
+template <class Model, int NPROC, int NQUEUE, int I>
+struct StaticDispatch {
+    static CMB_FN void run(StaticSim<NPROC, NQUEUE> &sim, Model &m, int who)
+    {
+        if (who == I) m.process(sim, (uint32_t)I, sim.proc[I].kind, CMB_PROCESS_SUCCESS);
+        else StaticDispatch<Model, NPROC, NQUEUE, I + 1>::run(sim, m, who);
+    }
+};
+template <class Model, int NPROC, int NQUEUE>
+struct StaticDispatch<Model, NPROC, NQUEUE, NPROC> {
+    static CMB_FN void run(StaticSim<NPROC, NQUEUE> &, Model &, int) {}
+};
+
+// one step of cmb_event_queue_execute (src/cmb_event.c:229-252): pop, advance the clock, resume the process.  false = the
+// list ran dry.  The body's blocking call is left in sim.cmd for the caller (`who` = the process it belongs to).
+template <class Model, int NPROC, int NQUEUE>
+CMB_FN bool static_step(StaticSim<NPROC, NQUEUE> &sim, Model &m, int &who)
+{
+    uint32_t act, key;
+    double when;
+    if (!sim.fel.pop(who, act, when, key)) return false;
+    sim.now = when;
+    sim.current_event = key;
+    sim.pops++;
+    sim.cmd = CMD_NONE;
+    bool run = true;
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if (i == who) {
+            if (act == ACT_START) {
+                sim.proc[i].status = PROC_RUNNING;
+                sim.proc[i].pc = 0u;
+            }
+            run = sim.proc[i].status == PROC_RUNNING;
+        }
+    }
+    if (run) {
+        sim.current = (uint32_t)who;
+        StaticDispatch<Model, NPROC, NQUEUE, 0>::run(sim, m, who);
+        sim.current = NIL;
+    }
+    return true;
+}
+
+// the blocking call the body ended on, except the exponential hold (whose draw the callers batch): true = handled
+template <int NPROC, int NQUEUE>
+CMB_FN void static_finish_command(StaticSim<NPROC, NQUEUE> &sim, int who, uint32_t cmd)
+{
+    if (cmd == CMD_HOLD) {
+        if (sim.cmd_value < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
+        if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, sim.cmd_value))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+    }
+    else if (cmd == CMD_EXIT) {                         // cmb_process_exit: nothing pending, nobody waiting for it here
+#pragma unroll
+        for (int i = 0; i < NPROC; i++) {
+            if (i == who) {
+                sim.proc[i].status = PROC_FINISHED;
+                sim.proc[i].exit_value = sim.cmd_exit;
+            }
+        }
+    }
+}
+
+#ifdef CMB_HOST_BUILD
+// the tier's source text run on the CPU (tests/cmb_engine_host.cpp): one trial, the slow path taken where it occurs
+template <class Model, int NPROC, int NQUEUE>
+inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const TrialIn &in, TrialOut &out,
+                                  uint64_t trace_cap, uint64_t *trace_key, double *trace_time)
+{
+    out.objects = 0u;
+    out.sum_wait = 0.0;
+    out.max_queue = 0u;
+    for (int k = 0; k < 8; k++) out.counters[k] = 0u;
+    m.run_trial(sim, in);
+    int who = 0;
+    while (static_step(sim, m, who)) {
+        if (sim.pops <= trace_cap) {
+            trace_key[sim.pops - 1u] = sim.current_event;
+            trace_time[sim.pops - 1u] = sim.now;
+        }
+        const uint32_t cmd = sim.cmd;
+        sim.cmd = CMD_NONE;
+        if (cmd == CMD_HOLD_EXPONENTIAL) {
+            const double dur = gp_exponential(sim.rng, *sim.hot, sim.cmd_value);
+            if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+        }
+        else {
+            static_finish_command(sim, who, cmd);
+        }
+    }
+    m.finish(sim, out);
+}
+#else
+
+#ifndef STATIC_COLD_BATCH
+#define STATIC_COLD_BATCH 4
+#endif
+
+struct StaticArgs {
+    LaunchArgs base;
+    double    *spill;           // [num_trials][NQUEUE][spill_cap]
+    uint32_t   spill_cap;
+};
+
+template <template <class> class ModelT, int NPROC, int NQUEUE, bool TRACE>
+__global__ void __launch_bounds__(STATIC_BLOCK)
+static_trial_kernel(const StaticArgs sa)
+{
+    using S = StaticSim<NPROC, NQUEUE>;
+    __shared__ ZigHot hot;
+    __shared__ double ring_smem[NQUEUE * STATIC_WINDOW * STATIC_BLOCK];
+    const LaunchArgs &a = sa.base;
+    stage_zig_hot(hot, true);
+    __syncthreads();
+
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint64_t trial = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = trial < a.num_trials;
+
+    S sim;
+    ModelT<S> m;
+    TrialOut out;
+    out.objects = 0u;
+    out.sum_wait = 0.0;
+    out.max_queue = 0u;
+    for (int k = 0; k < 8; k++) out.counters[k] = 0u;
+    sim.init(alive ? fmix64(a.master_seed, a.first_trial + trial) : 0u, &hot, &ring_smem[threadIdx.x], STATIC_BLOCK,
+             (sa.spill_cap && alive) ? sa.spill + trial * (uint64_t)NQUEUE * sa.spill_cap : nullptr, sa.spill_cap);
+    if (alive) {
+        TrialIn in;
+        in.arr_mean = a.arr_mean[trial];
+        in.srv_mean = a.srv_mean[trial];
+        in.num_objects = a.num_objects;
+        in.servers = a.servers;
+        in.num_params = a.num_params;
+        for (int k = 0; k < 16; k++) in.params[k] = a.params[k];
+        in.trial = a.first_trial + trial;
+        m.run_trial(sim, in);
+    }
+
+    bool parked = false;            // the exponential hold of this lane needs the ziggurat's slow path: wait for company
+    uint64_t parked_u = 0u;
+    int parked_who = 0;
+
+    while (__any_sync(FULL, alive)) {
+        bool draw = false;
+        int who = 0;
+        if (alive && !parked) {
+            if (!static_step(sim, m, who)) {
+                alive = false;                          // cmb_event_queue_execute returns
+                m.finish(sim, out);
+                if (a.events)    a.events[trial] = sim.pops;
+                if (a.objects)   a.objects[trial] = out.objects;
+                if (a.t_end)     a.t_end[trial] = sim.now;
+                if (a.sum_wait)  a.sum_wait[trial] = out.sum_wait;
+                if (a.status)    a.status[trial] = sim.status;
+                if (a.max_queue) a.max_queue[trial] = out.max_queue;
+                if (a.counters) {
+                    for (int k = 0; k < 8; k++) a.counters[trial * 8u + k] = out.counters[k];
+                }
+            }
+            else {
+                if (TRACE) {
+                    if (sim.pops <= a.trace_cap) {
+                        a.trace_key[trial * a.trace_cap + sim.pops - 1u] = sim.current_event;
+                        a.trace_time[trial * a.trace_cap + sim.pops - 1u] = sim.now;
+                    }
+                }
+                const uint32_t cmd = sim.cmd;
+                draw = cmd == CMD_HOLD_EXPONENTIAL;
+                if (!draw) static_finish_command(sim, who, cmd);
+            }
+        }
+        // ---- converged: the hold's variate and its wake-up event (cmb_process_hold, src/cmb_process.c:262-285)
+        if (draw) {
+            const uint64_t u = sim.rng.next();
+            if (Sfc64::exp_is_hot(u)) {
+                const double dur = __dmul_rn(sim.cmd_value, Sfc64::exp_hot(hot, u));
+                if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+            }
+            else {
+                parked = true;
+                parked_u = u;
+                parked_who = who;
+            }
+        }
+        const unsigned pm = __ballot_sync(FULL, parked);
+        if (pm != 0u) {
+            const unsigned am = __ballot_sync(FULL, alive);
+            if (__popc(pm) >= STATIC_COLD_BATCH || pm == am) {
+                if (parked) {
+                    const double dur = __dmul_rn(sim.cmd_value, sim.rng.exp_cold(parked_u));
+                    if (!sim.fel.schedule(parked_who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+                    parked = false;
+                }
+            }
+        }
+    }
+}
+#endif  // CMB_HOST_BUILD
+
+}  // namespace cmb
+}  // namespace cimba_b200

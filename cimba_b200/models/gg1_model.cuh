@@ -1,13 +1,16 @@
 // gg1_model.cuh - BASELINE config 4 against the device authoring surface: benchmark/MM1_multi.c
 // with Erlang-2 inter-arrival times and normal service times redrawn while negative (oracle: ref_driver.c model 1).
+// A template over the engine, like mm1_model.cuh: GG1T<cmb::Sim> and GG1T<cmb::StaticSim<2, 1>>.
 #pragma once
 #include "../csrc/cmb_kernel.cuh"
+#include "../csrc/cmb_static.cuh"
 
 namespace cimba_b200 {
 namespace models {
 
-struct GG1 {
-    cmb::objectqueue queue;
+template <class S>
+struct GG1T {
+    typename S::queue_type queue;
     uint32_t arrival, service;
     double   arr_mean, srv_mean, s;
     uint64_t num_objects, obj_cnt;
@@ -15,9 +18,9 @@ struct GG1 {
     uint64_t ui, stamp, object;
     enum : uint32_t { ARRIVAL, SERVICE };
 
-    CMB_FN void arrivalfunc(cmb::Sim &sim, uint32_t me, int64_t sig)
+    CMB_FN void arrivalfunc(S &sim, uint32_t me, int64_t sig)
     {
-        GG1 &m = *this;
+        GG1T &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
             CMB_PROCESS_HOLD(cmb_random_erlang(2u, 0.5 * arr_mean));
@@ -27,9 +30,9 @@ struct GG1 {
         CMB_PROCESS_END
     }
 
-    CMB_FN void servicefunc(cmb::Sim &sim, uint32_t me, int64_t sig)
+    CMB_FN void servicefunc(S &sim, uint32_t me, int64_t sig)
     {
-        GG1 &m = *this;
+        GG1T &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_OBJECTQUEUE_GET(queue, object);
@@ -43,7 +46,7 @@ struct GG1 {
         CMB_PROCESS_END
     }
 
-    CMB_FN void run_trial(cmb::Sim &sim, const cmb::TrialIn &in)
+    CMB_FN void run_trial(S &sim, const cmb::TrialIn &in)
     {
         arr_mean = in.arr_mean;
         srv_mean = in.srv_mean;
@@ -57,20 +60,22 @@ struct GG1 {
         cmb_process_start(service);
     }
 
-    CMB_FN void process(cmb::Sim &sim, uint32_t me, uint32_t kind, int64_t sig)
+    CMB_FN void process(S &sim, uint32_t me, uint32_t kind, int64_t sig)
     {
         if (kind == ARRIVAL) arrivalfunc(sim, me, sig);
         else servicefunc(sim, me, sig);
     }
-    CMB_FN void event(cmb::Sim &, uint32_t, uint32_t, int64_t) {}
-    CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return false; }
+    CMB_FN void event(S &, uint32_t, uint32_t, int64_t) {}
+    CMB_FN bool demand(S &, uint32_t, uint32_t, int32_t) { return false; }
 
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    CMB_FN void finish(S &, cmb::TrialOut &out)
     {
         out.objects = obj_cnt;
         out.sum_wait = sum_wait;
     }
 };
+
+using GG1 = GG1T<cmb::Sim>;
 
 }  // namespace models
 }  // namespace cimba_b200

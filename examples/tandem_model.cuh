@@ -1,24 +1,28 @@
 // examples/tandem_model.cuh - a model that exists NOWHERE in the library: two stations in tandem with a bounded buffer
 // between them (a putter blocks on a full cmb_objectqueue), written from scratch against the authoring surface
 // (cimba_b200/csrc/cmb_device.cuh).  examples/tandem_user_model.cu exports it as a loadable model library; the same
-// model written against the reference's API is oracle/ref_build/ref_driver.c model 17.
+// model written against the reference's API is oracle/ref_build/ref_driver.c model 17.  A template over the engine: the same
+// text runs on the general engine (cmb::Sim) and, three processes and two queues being all it has, on the static tier
+// (cmb::StaticSim<3, 2>, cimba_b200/csrc/cmb_static.cuh).
 #pragma once
 #include "../cimba_b200/csrc/cmb_kernel.cuh"
+#include "../cimba_b200/csrc/cmb_static.cuh"
 
 namespace tandem_example {
 using namespace cimba_b200;
 
-struct Tandem {
-    cmb::objectqueue first, second;                     // unlimited in front of station 1, `servers` places in front of station 2
+template <class S>
+struct TandemT {
+    typename S::queue_type first, second;                     // unlimited in front of station 1, `servers` places in front of station 2
     double   arr_mean, srv_mean;
     uint64_t num_objects, done;
     double   sum_wait;
     uint64_t ui, stamp, at1, at2;
     enum : uint32_t { SOURCE, STATION1, STATION2 };
 
-    CMB_FN void source(cmb::Sim &sim, uint32_t me, int64_t sig)
+    CMB_FN void source(S &sim, uint32_t me, int64_t sig)
     {
-        Tandem &m = *this;
+        TandemT &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
             CMB_PROCESS_HOLD_EXPONENTIAL(arr_mean);
@@ -27,9 +31,9 @@ struct Tandem {
         }
         CMB_PROCESS_END
     }
-    CMB_FN void station1(cmb::Sim &sim, uint32_t me, int64_t sig)
+    CMB_FN void station1(S &sim, uint32_t me, int64_t sig)
     {
-        Tandem &m = *this;
+        TandemT &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_OBJECTQUEUE_GET(first, at1);
@@ -38,9 +42,9 @@ struct Tandem {
         }
         CMB_PROCESS_END
     }
-    CMB_FN void station2(cmb::Sim &sim, uint32_t me, int64_t sig)
+    CMB_FN void station2(S &sim, uint32_t me, int64_t sig)
     {
-        Tandem &m = *this;
+        TandemT &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_OBJECTQUEUE_GET(second, at2);
@@ -51,7 +55,7 @@ struct Tandem {
         CMB_PROCESS_END
     }
 
-    CMB_FN void run_trial(cmb::Sim &sim, const cmb::TrialIn &in)
+    CMB_FN void run_trial(S &sim, const cmb::TrialIn &in)
     {
         arr_mean = in.arr_mean;
         srv_mean = in.srv_mean;
@@ -64,18 +68,19 @@ struct Tandem {
         cmb_process_start(cmb_process_create(STATION1, 0, 0u));
         cmb_process_start(cmb_process_create(STATION2, 0, 0u));
     }
-    CMB_FN void process(cmb::Sim &sim, uint32_t me, uint32_t kind, int64_t sig)
+    CMB_FN void process(S &sim, uint32_t me, uint32_t kind, int64_t sig)
     {
         if (kind == SOURCE) source(sim, me, sig);
         else if (kind == STATION1) station1(sim, me, sig);
         else station2(sim, me, sig);
     }
-    CMB_FN void event(cmb::Sim &, uint32_t, uint32_t, int64_t) {}
-    CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return false; }
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)
+    CMB_FN void event(S &, uint32_t, uint32_t, int64_t) {}
+    CMB_FN bool demand(S &, uint32_t, uint32_t, int32_t) { return false; }
+    CMB_FN void finish(S &, cmb::TrialOut &out)
     {
         out.objects = done;
         out.sum_wait = sum_wait;
     }
 };
+using Tandem = TandemT<cmb::Sim>;     // on the general engine; TandemT<cmb::StaticSim<3, 2>> is the static tier's (tandem_static_user_model.cu)
 }  // namespace tandem_example

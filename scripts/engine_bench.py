@@ -42,7 +42,7 @@ def main():
         am = torch.full((trials,), arr, dtype=torch.float64, device=dev)
         sm = torch.full((trials,), srv, dtype=torch.float64, device=dev)
         out = {}
-        for label, variant in (("fast", 0), ("general", cb.VARIANT_GENERAL)):
+        for label, variant in (("fast", 0), ("general", cb.VARIANT_GENERAL)) + ((("static", cb.VARIANT_STATIC),) if model == cb.MODEL_MM1 else ()):
             bufs = cb.TrialBuffers(trials, dev, 0, model, servers, variant)
             cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, model=model, servers=servers, variant=variant)
             res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, model=model, servers=servers,
@@ -52,7 +52,8 @@ def main():
                           "sum_check": float(res.sum_wait.sum().item())}
         row = {"model": name, "trials": trials, "objects": nobj, **out,
                "general_over_fast_time": out["general"]["ms"] / out["fast"]["ms"],
-               "same_answers": out["fast"]["sum_check"] == out["general"]["sum_check"] and out["fast"]["events"] == out["general"]["events"]}
+               "static_over_fast_time": out["static"]["ms"] / out["fast"]["ms"] if "static" in out else None,
+               "same_answers": all(o["sum_check"] == out["fast"]["sum_check"] and o["events"] == out["fast"]["events"] for o in out.values())}
         rows.append(row)
         print(json.dumps(row), flush=True)
     for trials, customers, T in ((4096, 1000, 50), (16384, 1000, 20)):

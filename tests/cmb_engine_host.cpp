@@ -82,6 +82,30 @@ static void run_model(uint64_t seed, const cmb::TrialIn &in, cmb::Arena &arena, 
     r.pad = 0u;
 }
 
+// the static tier (csrc/cmb_static.cuh): the same model template on cmb::StaticSim; spill_cap entries of HBM-ring stand-in per queue
+template <template <class> class ModelT, int NPROC, int NQUEUE>
+static void run_static(uint64_t seed, const cmb::TrialIn &in, const ZigHot &hot, HostResult &r, uint32_t spill_cap,
+                       uint64_t trace_cap, uint64_t *trace_key, double *trace_time)
+{
+    using S = cmb::StaticSim<NPROC, NQUEUE>;
+    S sim;
+    ModelT<S> m;
+    cmb::TrialOut out;
+    std::vector<double> win((size_t)NQUEUE * cmb::STATIC_WINDOW), ring((size_t)NQUEUE * (spill_cap ? spill_cap : 1u));
+    sim.init(seed, &hot, win.data(), 1u, ring.data(), spill_cap);
+    cmb::static_run_trial_host(sim, m, in, out, trace_cap, trace_key, trace_time);
+    r.events = sim.pops;
+    r.objects = out.objects;
+    r.t_end = sim.now;
+    r.sum_wait = out.sum_wait;
+    r.max_fel = NPROC;
+    r.max_queue = out.max_queue;
+    std::memcpy(r.counter, out.counters, sizeof(r.counter));
+    r.status = sim.status;
+    r.pad = 0u;
+}
+
+// model + 100 = the same model on the static tier (arena_bytes then = entries of the HBM-ring stand-in per queue).
 // model: 0 = MM1, 1 = GG1, 2 = MMC, 3 / 11 / 13 = the guarded queue tests, 5 / 12 = buffer + resource, 14 = test_resource.c, 7 = HOLD, 10 = HARBOR, 16 = RENEGE (the CIMBA_B200_MODEL_* numbers), 17 = examples/tandem_model.cuh, 18 = CHEESE (test/test_resourcepool.c).  arena_bytes of growth memory per call.
 extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed, uint64_t first, uint64_t count,
                                    uint64_t num_objects, double arr_mean, double srv_mean,
@@ -93,7 +117,7 @@ extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed,
         hot.exp_x[i] = zig::zig_exp_x[i];
         hot.nor_x[i] = zig::zig_nor_x[i];
     }
-    std::vector<unsigned char> mem(arena_bytes + 256);
+    std::vector<unsigned char> mem((model >= 100 ? 0u : arena_bytes) + 256);
     for (uint64_t i = 0; i < count; i++) {
         unsigned long long cursor = 0;
         cmb::Arena arena{mem.data(), &cursor, arena_bytes};
@@ -110,6 +134,9 @@ extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed,
         double *tt = trace_cap ? trace_time + i * trace_cap : nullptr;
         switch (model) {
         case 0:  run_model<models::MM1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 100: run_static<models::MM1T, 2, 1>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
+        case 101: run_static<models::GG1T, 2, 1>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
+        case 117: run_static<tandem_example::TandemT, 3, 2>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
         case 1:  run_model<models::GG1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 7:  run_model<models::HoldGeneral>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 10: run_model<models::HarborGeneral>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;

@@ -157,3 +157,22 @@ def test_engine_reproduces_the_reference_resource_golden_file(host):
     c = list(out[0].counter)
     assert out[0].status == 0 and out[0].events == 85 and out[0].max_queue == 30
     assert "%.4f" % _double(c[3]) == "0.9816" and "%.4f" % _double(c[4]) == "6.3280" and c[5] == 3 and c[1] == 1
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 17)], ids=case_id)
+def test_static_tier_source_on_the_cpu_matches_the_reference_vectors(host, case):
+    """csrc/cmb_static.cuh: the same model templates (mm1_model.cuh, gg1_model.cuh, examples/tandem_model.cuh) compiled against
+    cmb::StaticSim - one event slot per process, guards as a bit per process, queues as rings - on the CPU.  With a ring of 512
+    entries behind the 32-entry window an overloaded trial is flagged (and would be re-run by the general engine on the device);
+    with a ring sized for it the tier itself gives the reference's answer."""
+    n = len(case["trials"])
+    static_case = dict(case, model=case["model"] + 100)
+    for ring in (512, 1 << 17):
+        out, keys, times = run_host(host, static_case, n, arena=ring)
+        for i, want in enumerate(case["trials"]):
+            if ring == 512 and out[i].status:
+                assert out[i].status == 1               # CIMBA_B200_TRIAL_QUEUE_OVERFLOW: the repair pass's business
+                continue
+            assert out[i].status == 0
+            check_trial(want, out[i].events, out[i].objects, out[i].t_end, out[i].sum_wait, None,
+                        keys[i * TRACE:(i + 1) * TRACE], times[i * TRACE:(i + 1) * TRACE], f"trial {i}")

@@ -172,6 +172,46 @@ def test_a_model_that_exists_only_as_a_user_library_matches_the_reference():
         compare(case, run_case(case, mid, 0, n), n)
 
 
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1)], ids=case_id)
+def test_static_tier_matches_the_reference_vectors(case):
+    """CIMBA_B200_VARIANT_STATIC: mm1_model.cuh / gg1_model.cuh - the text the general engine runs - compiled against
+    cmb::StaticSim<2, 1> (registers + shared memory).  Heavy traffic and overload outgrow its 32 + 512 entry queue: those trials
+    come back through the general engine from the same template, with the reference's answer."""
+    n = len(case["trials"])
+    compare(case, run_case(case, BUILTIN[case["model"]], cb.VARIANT_STATIC, n), n)
+    compare(case, run_case(case, BUILTIN[case["model"]], cb.VARIANT_STATIC, n, spill=8192), n)
+
+
+def test_static_tier_against_the_oracle_at_other_sizes():
+    port = load_port()
+    for model, arr, srv, nobj, n in ((0, 1 / 0.9, 1.0, 900, 3000), (1, 1.25, 1.0, 700, 1111), (0, 1 / 0.97, 1.0, 3000, 257)):
+        res = cb.run_trials(n, arr_mean=arr, srv_mean=srv, num_objects=nobj, master_seed=MASTER, first_trial=9,
+                            model=BUILTIN[model], variant=cb.VARIANT_STATIC)
+        want = run_trials(port, "port", model, 1, MASTER, 9, n, nobj, arr, srv)
+        ev, te, sw = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.sum_wait.cpu().tolist()
+        assert res.status.abs().sum().item() == 0
+        for i, w in enumerate(want):
+            assert (ev[i], te[i], sw[i]) == (w.events, w.t_end, w.sum_wait), (model, i)
+
+
+def test_user_built_static_tier_libraries_match_the_reference():
+    """examples/tandem_static_user_model.cu (three processes, two queues, a put that blocks on the bounded one) and
+    examples/mm1_static_user_model.cu: CMB_EXPORT_STATIC_MODEL, scripts/build_model.py, cimba_b200_model_load."""
+    mid = cb.load_model(_model_library("tandem_static_user_model"))
+    assert b"static tier" in cb.lib.cimba_b200_model_name(mid)
+    for case in [c for c in GOLD["cases"] if c["model"] == 17]:
+        n = len(case["trials"])
+        compare(case, run_case(case, mid, 0, n), n)             # servers = 1, rho > 1: queue 1 outgrows the ring -> repaired
+    mm1 = cb.load_model(_model_library("mm1_static_user_model"))
+    case = GOLD["cases"][0]
+    n = len(case["trials"])
+    compare(case, run_case(case, mm1, 0, n), n)
+    exp = np.zeros(n, dtype=cb.TRIAL_DTYPE)
+    exp["arr_mean"], exp["srv_mean"] = float.fromhex(case["arr_mean"]), float.fromhex(case["srv_mean"])
+    cb.cimba_run_experiment(exp, model=mm1, num_objects=case["num_objects"], master_seed=MASTER)
+    assert [int(v) for v in exp["events"]] == [t["events"] for t in case["trials"]]
+
+
 def test_unknown_model_ids_and_bad_libraries_are_refused():
     with pytest.raises(cb.CimbaError):
         cb.run_trials(4, arr_mean=1.0, srv_mean=1.0, num_objects=10, master_seed=1, model=cb.MODEL_USER_BASE + 999)
