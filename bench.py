@@ -27,7 +27,8 @@ step 0, which is what lets the same trials be checked against the CPU reference 
             (scheduler affinity and the cgroup CPU quota), `threads` what cimba_run_experiment starts (one per
             logical CPU it sees, src/cimba.c:171) - on a quota-limited box they differ and the line says so.
   secondary one entry per other BASELINE configuration (rho = 0.8; config 3 M/M/c c = 8; config 4 G/G/1 at
-            1 048 576 replications; config 5 AWACS, short; the hold model; M/M/1 on the general engine), each timed
+            1 048 576 replications; config 5 AWACS, short; the hold model; M/M/1 and G/G/1 from their authoring-surface
+            source on the static tier; M/M/1 on the general engine), each timed
             the same way on this run's GPUs with its own parity sample against the reference build, and the
             single-core benchmark/MM1_single.c row.
 """
@@ -61,7 +62,7 @@ def parse_args():
     p.add_argument("--trials", type=int, default=65536, help="replications per GPU per step")
     p.add_argument("--objects", type=int, default=1_000_000, help="customers per replication")
     p.add_argument("--mapping", type=int, default=1, choices=[1, 32], help="1 lane/trial or 32 (warp/trial)")
-    p.add_argument("--variant", type=int, default=0, help="0 default kernel, 1 unfused formulation, 16 general engine (A/B)")
+    p.add_argument("--variant", type=int, default=0, help="0 default kernel, 1 unfused formulation, 16 general engine, 17 static tier (A/B)")
     p.add_argument("--ref-trials", type=int, default=0, help="CPU sample size (0 = 16 per usable core)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -338,6 +339,12 @@ def secondary_configs(args, cb, torch, dist, dev, rank, world, barrier):
                                merge_nccl=True))
     guarded(lambda: queue_like("config 4: G/G/1 (Erlang-2 arrivals, ziggurat-normal service), 1048576 replications in all",
                                cb.MODEL_GG1, 1, 1.25, 1.0, 1048576, 0, 1))
+    guarded(lambda: queue_like("M/M/1 written against the device authoring surface (cimba_b200/models/mm1_model.cuh, 50 lines), on the STATIC "
+                               "tier (CIMBA_B200_VARIANT_STATIC: registers + shared memory, general engine as repair pass), "
+                               "65536 replications per GPU at full length", cb.MODEL_MM1, 1, 1.0 / ARRIVAL_RATE, 1.0, 0, args.trials, 0,
+                               variant=cb.VARIANT_STATIC))
+    guarded(lambda: queue_like("G/G/1 (config 4's model) from its authoring-surface source on the static tier, 1048576 replications in all",
+                               cb.MODEL_GG1, 1, 1.25, 1.0, 1048576, 0, 1, variant=cb.VARIANT_STATIC))
     guarded(lambda: queue_like("M/M/1 written against the device authoring surface, on the general engine (CIMBA_B200_VARIANT_GENERAL), "
                                "65536 replications per GPU x 1e5 objects", cb.MODEL_MM1, 1, 1.0 / ARRIVAL_RATE, 1.0, 0, args.trials, 0,
                                variant=cb.VARIANT_GENERAL, objects=min(args.objects, 100_000)))
@@ -581,7 +588,7 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     kernel_s = sum(kernel_ms) / len(kernel_ms) * 1e-3
-    kname = {0: "mm1_kernel", 1: "queue_kernel<0>", 16: "trial_kernel<MM1> (general engine)"}.get(args.variant, "mm1_kernel")
+    kname = {0: "mm1_kernel", 1: "queue_kernel<0>", 16: "trial_kernel<MM1> (general engine)", 17: "static_trial_kernel<MM1T, 2, 1> (static tier)"}.get(args.variant, "mm1_kernel")
     cal = issue_calibration().get(kname if args.mapping == 1 else "", {})
     tr = measured_traffic()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count

@@ -19,6 +19,8 @@
 // `typename S::queue_type`, exported with CMB_EXPORT_STATIC_MODEL(M, NPROC, NQUEUE, "name").
 #pragma once
 
+#include <type_traits>
+
 #include "cmb_kernel.cuh"
 
 namespace cimba_b200 {
@@ -314,6 +316,23 @@ inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const
 #ifndef STATIC_COLD_BATCH
 #define STATIC_COLD_BATCH 4
 #endif
+#ifndef STATIC_PARK_MASK
+#define STATIC_PARK_MASK 3u     // the parked set is examined every 4th step
+#endif
+
+// A model whose process bodies never draw themselves - every variate is the duration of a CMB_PROCESS_HOLD_EXPONENTIAL, drawn
+// by the dispatcher - may say `static constexpr bool exponential_holds_only = true;`.  The dispatcher then keeps one raw sfc64
+// output of look-ahead with its hot-path variate already formed (as mm1_fast.cuh does): the table look-up and the 64-bit ->
+// double conversion leave the pop -> push chain.  The stream order is unchanged BECAUSE nothing else draws in between; a model
+// with a cmb_random_* call in a body must not claim it.
+template <class Model, class = void>
+struct StaticLookahead {
+    static constexpr bool value = false;
+};
+template <class Model>
+struct StaticLookahead<Model, typename std::enable_if<Model::exponential_holds_only>::type> {
+    static constexpr bool value = true;
+};
 
 struct StaticArgs {
     LaunchArgs base;
@@ -357,9 +376,21 @@ static_trial_kernel(const StaticArgs sa)
         m.run_trial(sim, in);
     }
 
+#ifdef STATIC_NO_LOOKAHEAD
+    constexpr bool AHEAD = false;
+#else
+    constexpr bool AHEAD = StaticLookahead<ModelT<S>>::value;
+#endif
     bool parked = false;            // the exponential hold of this lane needs the ziggurat's slow path: wait for company
     uint64_t parked_u = 0u;
     int parked_who = 0;
+    uint64_t u_next = 0u;           // AHEAD: the next raw output, drawn as soon as the previous one was consumed ...
+    double e_next = 0.0;            // ... and its hot-path standard exponential
+    if (AHEAD && alive) {
+        u_next = sim.rng.next();
+        e_next = Sfc64::exp_hot(hot, u_next);
+    }
+    uint32_t step = 0u;
 
     while (__any_sync(FULL, alive)) {
         bool draw = false;
@@ -392,10 +423,14 @@ static_trial_kernel(const StaticArgs sa)
         }
         // ---- converged: the hold's variate and its wake-up event (cmb_process_hold, src/cmb_process.c:262-285)
         if (draw) {
-            const uint64_t u = sim.rng.next();
+            const uint64_t u = AHEAD ? u_next : sim.rng.next();
             if (Sfc64::exp_is_hot(u)) {
-                const double dur = __dmul_rn(sim.cmd_value, Sfc64::exp_hot(hot, u));
+                const double dur = __dmul_rn(sim.cmd_value, AHEAD ? e_next : Sfc64::exp_hot(hot, u));
                 if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+                if (AHEAD) {
+                    u_next = sim.rng.next();
+                    e_next = Sfc64::exp_hot(hot, u_next);
+                }
             }
             else {
                 parked = true;
@@ -403,6 +438,7 @@ static_trial_kernel(const StaticArgs sa)
                 parked_who = who;
             }
         }
+        if ((++step & STATIC_PARK_MASK) != 0u) continue;
         const unsigned pm = __ballot_sync(FULL, parked);
         if (pm != 0u) {
             const unsigned am = __ballot_sync(FULL, alive);
@@ -411,6 +447,10 @@ static_trial_kernel(const StaticArgs sa)
                     const double dur = __dmul_rn(sim.cmd_value, sim.rng.exp_cold(parked_u));
                     if (!sim.fel.schedule(parked_who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
                     parked = false;
+                    if (AHEAD) {
+                        u_next = sim.rng.next();
+                        e_next = Sfc64::exp_hot(hot, u_next);
+                    }
                 }
             }
         }

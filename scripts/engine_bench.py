@@ -34,9 +34,21 @@ def timed(fn, reps=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--static-only", action="store_true", help="time M/M/1 on the static tier only (variant sweeps)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     rows = []
+    if a.static_only:
+        trials, nobj = 65536, 100000
+        am = torch.full((trials,), 1 / 0.9, dtype=torch.float64, device=dev)
+        sm = torch.full((trials,), 1.0, dtype=torch.float64, device=dev)
+        bufs = cb.TrialBuffers(trials, dev, 0, cb.MODEL_MM1, 1, cb.VARIANT_STATIC)
+        cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, variant=cb.VARIANT_STATIC)
+        res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, variant=cb.VARIANT_STATIC, buffers=bufs), reps=3)
+        ev = int(res.events.sum().item())
+        print(json.dumps({"static_ms": ms, "events_per_s": ev / ms * 1e3, "bad": int((res.status != 0).sum().item()),
+                          "sum_check": float(res.sum_wait.sum().item())}), flush=True)
+        return
     for name, model, servers, arr, srv, trials, nobj in (("M/M/1", cb.MODEL_MM1, 1, 1 / 0.9, 1.0, 65536, 100000),
                                                          ("M/M/c c=8", cb.MODEL_MMC, 8, 1 / 6.4, 1.0, 32768, 100000)):
         am = torch.full((trials,), arr, dtype=torch.float64, device=dev)

@@ -20,6 +20,10 @@ runs = [
     dict(model=cb.MODEL_HARBOR, n=40, arr=2.0, srv=8.0, size=200, servers=10),
     dict(model=cb.MODEL_HARBOR, n=40, arr=1.5, srv=10.0, size=300, servers=5),     # on-chip overflow -> repair pass
     dict(model=cb.MODEL_HARBOR, n=70, arr=2.0, srv=8.0, size=100, servers=10, variant=2),
+    # the static tier (cmb_static.cuh), with and without trials for its repair pass
+    dict(model=cb.MODEL_MM1, n=100, arr=1 / 0.9, srv=1.0, size=300, variant=cb.VARIANT_STATIC),
+    dict(model=cb.MODEL_MM1, n=70, arr=0.5, srv=1.0, size=3000, variant=cb.VARIANT_STATIC),
+    dict(model=cb.MODEL_GG1, n=100, arr=1.25, srv=1.0, size=300, variant=cb.VARIANT_STATIC),
     # the general engine: every model written against the authoring surface
     dict(model=cb.MODEL_MM1, n=64, arr=1 / 0.9, srv=1.0, size=300, variant=cb.VARIANT_GENERAL),
     dict(model=cb.MODEL_GG1, n=64, arr=1.25, srv=1.0, size=300, variant=cb.VARIANT_GENERAL),
