@@ -27,6 +27,7 @@
 #pragma once
 
 #include <cstdint>
+#include <utility>
 #ifndef CMB_HOST_BUILD
 #include <cuda_runtime.h>
 #endif
@@ -402,7 +403,7 @@ enum : uint32_t {
 };
 
 // what a process body asks of the dispatcher when it returns (Sim::cmd)
-enum : uint32_t { CMD_NONE = 0u, CMD_HOLD = 1u, CMD_HOLD_EXPONENTIAL = 2u, CMD_GUARD_WAIT = 3u, CMD_EXIT = 4u };
+enum : uint32_t { CMD_NONE = 0u, CMD_HOLD = 1u, CMD_HOLD_EXPONENTIAL = 2u, CMD_GUARD_WAIT = 3u, CMD_EXIT = 4u, CMD_HOLD_SAMPLED = 5u };
 
 // demands a guard entry can carry (the reference stores a predicate function + context, src/cmb_resourceguard.c:125-152)
 enum : uint32_t {
@@ -535,6 +536,7 @@ struct Sim {
     FlipCache      flips;               // cmb_random_flip's 64 cached coin flips (src/cmb_random.c: one draw serves 64 calls)
     uint32_t       fel_high;            // the deepest the event list was at a pop (what the oracle calls max_fel)
     uint32_t       cmd;
+    uint32_t       cmd_sample;          // CMD_HOLD_SAMPLED: which of the model's samplers draws the duration
     uint32_t       cmd_demand;
     int32_t        cmd_ctx;
     double         cmd_value;           // hold: the duration (or the mean of the exponential to draw); exit: unused
@@ -1495,6 +1497,16 @@ CMB_FN_NOINLINE void process_stop(Sim &sim, Model &m, uint32_t pid, int64_t valu
     sim.wake_process_waiters(pid, CMB_PROCESS_STOPPED);
 }
 
+// CMB_PROCESS_HOLD_SAMPLED(id): the duration is `m.sample(sim, id)`, drawn by the dispatcher (a model without samplers has none)
+template <class Model, class S, class = void>
+struct ModelSampler {
+    static CMB_FN double draw(Model &, S &, uint32_t) { return 0.0; }
+};
+template <class Model, class S>
+struct ModelSampler<Model, S, decltype((void)std::declval<Model &>().sample(std::declval<S &>(), 0u))> {
+    static CMB_FN double draw(Model &m, S &sim, uint32_t id) { return m.sample(sim, id); }
+};
+
 // ------------------------------------------------------------------------------------------------ dispatcher
 // cmb_event_queue_execute, src/cmb_event.c:259-267 + cmb_event_execute_next, :229-252
 template <class Model, bool TRACE>
@@ -1566,6 +1578,9 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
                 const double dur = cmd == CMD_HOLD ? sim.cmd_value : gp_exponential(sim.rng, *sim.hot, sim.cmd_value);
                 sim.hold_begin(pid, dur);
             }
+            else if (cmd == CMD_HOLD_SAMPLED) {
+                sim.hold_begin(pid, ModelSampler<Model, Sim>::draw(m, sim, sim.cmd_sample));
+            }
             else if (cmd == CMD_GUARD_WAIT) {
                 sim.guard_wait_begin(*sim.cmd_guard, pid, sim.cmd_demand, sim.cmd_ctx);
             }
@@ -1576,6 +1591,24 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
     }
 }
 
+}  // namespace cmb
+}  // namespace cimba_b200
+
+namespace cimba_b200 {
+namespace cmb {
+// cmb_random_erlang on either engine: k exponentials added up (include/cmb_random.h:366)
+template <class S>
+CMB_FN double draw_erlang(S &sim, unsigned k, double mean)
+{
+    double x = 0.0;
+    for (unsigned i = 0u; i < k; i++) x = __dadd_rn(x, draw_exponential(sim, mean));
+    return x;
+}
+
+// the two ziggurat draws behind cmb_random_exponential / cmb_random_normal: out of line on the general engine (one copy of the
+// slow paths per kernel); the static tier (cmb_static.cuh) overloads them inline, where a call would force its state into memory
+CMB_FN double draw_exponential(Sim &sim, double mean) { return gp_exponential(sim.rng, *sim.hot, mean); }
+CMB_FN double draw_std_normal(Sim &sim) { return gp_std_normal(sim.rng, *sim.hot); }
 }  // namespace cmb
 }  // namespace cimba_b200
 
@@ -1599,6 +1632,12 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 // (same stream position: nothing draws between the body's return and the dispatcher)
 #define CMB_PROCESS_HOLD_EXPONENTIAL(mean) \
     do { sim.cmd_value = (mean); sim.cmd = cimba_b200::cmb::CMD_HOLD_EXPONENTIAL; CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)
+// cmb_process_hold(<a variate>) with the draw left to the dispatcher: the model's `double sample(S &sim, uint32_t id)` - a pure
+// function of the generator and the model's parameters, e.g. `return cmb_random_erlang(2u, 0.5 * arr_mean);` - is called right
+// after the body returns (same stream position as a draw in the hold's argument), where the warp is together; the static tier
+// first tries it with the ziggurats' hot paths only and parks the lane if that is not enough (cmb_static.cuh)
+#define CMB_PROCESS_HOLD_SAMPLED(id) \
+    do { sim.cmd_sample = (id); sim.cmd = cimba_b200::cmb::CMD_HOLD_SAMPLED; CMB_YIELD_(); sig = sim.hold_end(me, sig); } while (0)
 // cmb_process_yield(): wait for whatever comes (a timer, a resume, an interrupt)
 #define CMB_PROCESS_YIELD()      do { CMB_YIELD_(); } while (0)
 // cmb_process_exit(value)
@@ -1686,11 +1725,11 @@ CMB_FN_NOINLINE void execute(Sim &sim, Model &m, uint64_t trace_cap, uint64_t *t
 #define cmb_process_current()               (sim.current)
 #define cmb_event_current()                 (sim.current_event)
 #define cmb_random()                        (sim.rng.uniform01())
-#define cmb_random_exponential(mean)        (cimba_b200::gp_exponential(sim.rng, *sim.hot, (mean)))
-#define cmb_random_std_normal()             (cimba_b200::gp_std_normal(sim.rng, *sim.hot))
-#define cmb_random_normal(mu, sigma)        (__dadd_rn((mu), __dmul_rn((sigma), cimba_b200::gp_std_normal(sim.rng, *sim.hot))))
+#define cmb_random_exponential(mean)        (cimba_b200::cmb::draw_exponential(sim, (mean)))
+#define cmb_random_std_normal()             (cimba_b200::cmb::draw_std_normal(sim))
+#define cmb_random_normal(mu, sigma)        (__dadd_rn((mu), __dmul_rn((sigma), cimba_b200::cmb::draw_std_normal(sim))))
 #define cmb_random_uniform(lo, hi)          (sim.rng.uniform((lo), (hi)))
-#define cmb_random_erlang(k, mean)          (sim.rng.erlang(*sim.hot, (k), (mean)))
+#define cmb_random_erlang(k, mean)          (cimba_b200::cmb::draw_erlang(sim, (k), (mean)))
 #define cmb_random_bernoulli(p)             (sim.rng.bernoulli(p))
 #define cmb_random_dice(lo, hi)             (sim.rng.dice((lo), (hi)))
 #define cmb_random_triangular(a, b, c)      (cimba_b200::rnd_triangular(sim.rng, (a), (b), (c)))

@@ -64,8 +64,11 @@ struct StaticSim {
     Proc           proc[NPROC];
     SlotFel<NPROC> fel;
     uint32_t       cmd;
+    uint32_t       cmd_sample;
     double         cmd_value;
     int64_t        cmd_exit;
+    bool           hot_only;        // a sampler is being tried with the ziggurats' rectangles only ...
+    bool           hot_failed;      // ... and that was not enough: the draw will be repeated with the slow paths, in a batch
     // where this trial's queues live: column `tid` of the CTA's shared-memory rings, and its HBM rings
     double        *ring_win;
     uint32_t       ring_stride;
@@ -84,8 +87,10 @@ struct StaticSim {
         nproc = nqueue = guard_seq = 0u;
         fel.clear();
         cmd = CMD_NONE;
+        cmd_sample = 0u;
         cmd_value = 0.0;
         cmd_exit = 0;
+        hot_only = hot_failed = false;
         ring_win = win;
         ring_stride = stride;
         spill = spill_rings;
@@ -162,6 +167,37 @@ struct StaticSim {
         if (!fel.schedule((int)head, ACT_WAKE_RESOURCE, now)) status |= TRIAL_ERR_FEL_OVERFLOW;
     }
 };
+
+// cmb_random_exponential / cmb_random_normal in a process body: inline (a call would take the generator's address and put the
+// whole control block in local memory)
+// In a sampler the dispatcher is trying out (hot_only), a draw that leaves its ziggurat's rectangles gives up - the dispatcher
+// rewinds the generator and repeats the whole sampler later, slow paths allowed, together with other lanes in the same position.
+template <int NPROC, int NQUEUE>
+CMB_FN double draw_exponential(StaticSim<NPROC, NQUEUE> &sim, double mean)        // include/cmb_random.h:319-352
+{
+    if (sim.hot_failed) return mean;
+    const uint64_t u = sim.rng.next();
+    if (Sfc64::exp_is_hot(u)) return __dmul_rn(mean, Sfc64::exp_hot(*sim.hot, u));
+    if (sim.hot_only) {
+        sim.hot_failed = true;
+        return mean;
+    }
+    return __dmul_rn(mean, sim.rng.exp_cold(u));
+}
+
+template <int NPROC, int NQUEUE>
+CMB_FN double draw_std_normal(StaticSim<NPROC, NQUEUE> &sim)                       // include/cmb_random.h:206-215
+{
+    if (sim.hot_failed) return 1.0;
+    const int64_t ix = (int64_t)sim.rng.next();
+    const unsigned i = (unsigned)(ix & 0xff);
+    if (i <= ZIG_NOR_MAX) return __dmul_rn(sim.hot->nor_x[i], __ll2double_rn(ix));
+    if (sim.hot_only) {
+        sim.hot_failed = true;
+        return 1.0;
+    }
+    return sim.rng.nor_cold(*sim.hot, ix);
+}
 
 // ------------------------------------------------------------------------------------------------ objectqueue
 template <int NPROC, int NQUEUE>
@@ -305,6 +341,21 @@ inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const
             const double dur = gp_exponential(sim.rng, *sim.hot, sim.cmd_value);
             if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
         }
+        else if (cmd == CMD_HOLD_SAMPLED) {
+            // as the device does it: the rectangles only first, and if they do not suffice the generator rewound and the whole sampler again
+            const Sfc64 saved = sim.rng;
+            sim.hot_only = true;
+            sim.hot_failed = false;
+            double dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE>>::draw(m, sim, sim.cmd_sample);
+            sim.hot_only = false;
+            if (sim.hot_failed) {
+                sim.hot_failed = false;
+                sim.rng = saved;
+                dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE>>::draw(m, sim, sim.cmd_sample);
+            }
+            if (dur < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
+            if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
+        }
         else {
             static_finish_command(sim, who, cmd);
         }
@@ -384,6 +435,7 @@ static_trial_kernel(const StaticArgs sa)
     bool parked = false;            // the exponential hold of this lane needs the ziggurat's slow path: wait for company
     uint64_t parked_u = 0u;
     int parked_who = 0;
+    bool parked_sampled = false;    // ... or the sampler of its CMB_PROCESS_HOLD_SAMPLED does
     uint64_t u_next = 0u;           // AHEAD: the next raw output, drawn as soon as the previous one was consumed ...
     double e_next = 0.0;            // ... and its hot-path standard exponential
     if (AHEAD && alive) {
@@ -393,7 +445,7 @@ static_trial_kernel(const StaticArgs sa)
     uint32_t step = 0u;
 
     while (__any_sync(FULL, alive)) {
-        bool draw = false;
+        bool draw = false, sampled = false;
         int who = 0;
         if (alive && !parked) {
             if (!static_step(sim, m, who)) {
@@ -418,7 +470,28 @@ static_trial_kernel(const StaticArgs sa)
                 }
                 const uint32_t cmd = sim.cmd;
                 draw = cmd == CMD_HOLD_EXPONENTIAL;
-                if (!draw) static_finish_command(sim, who, cmd);
+                sampled = cmd == CMD_HOLD_SAMPLED;
+                if (!draw && !sampled) static_finish_command(sim, who, cmd);
+            }
+        }
+        // ---- converged: a sampled hold (CMB_PROCESS_HOLD_SAMPLED) - the model's sampler with the rectangles only; a lane whose
+        // draw needs more rewinds the generator and parks
+        if (sampled) {
+            const Sfc64 saved = sim.rng;
+            sim.hot_only = true;
+            sim.hot_failed = false;
+            const double dur = ModelSampler<ModelT<S>, S>::draw(m, sim, sim.cmd_sample);
+            sim.hot_only = false;
+            if (sim.hot_failed) {
+                sim.hot_failed = false;
+                sim.rng = saved;
+                parked = true;
+                parked_sampled = true;
+                parked_who = who;
+            }
+            else {
+                if (dur < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
+                if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
             }
         }
         // ---- converged: the hold's variate and its wake-up event (cmb_process_hold, src/cmb_process.c:262-285)
@@ -444,9 +517,17 @@ static_trial_kernel(const StaticArgs sa)
             const unsigned am = __ballot_sync(FULL, alive);
             if (__popc(pm) >= STATIC_COLD_BATCH || pm == am) {
                 if (parked) {
-                    const double dur = __dmul_rn(sim.cmd_value, sim.rng.exp_cold(parked_u));
+                    double dur;
+                    if (parked_sampled) {
+                        dur = ModelSampler<ModelT<S>, S>::draw(m, sim, sim.cmd_sample);
+                        if (dur < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
+                    }
+                    else {
+                        dur = __dmul_rn(sim.cmd_value, sim.rng.exp_cold(parked_u));
+                    }
                     if (!sim.fel.schedule(parked_who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
                     parked = false;
+                    parked_sampled = false;
                     if (AHEAD) {
                         u_next = sim.rng.next();
                         e_next = Sfc64::exp_hot(hot, u_next);

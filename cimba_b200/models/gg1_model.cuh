@@ -12,7 +12,7 @@ template <class S>
 struct GG1T {
     typename S::queue_type queue;
     uint32_t arrival, service;
-    double   arr_mean, srv_mean, s;
+    double   arr_mean, srv_mean;
     uint64_t num_objects, obj_cnt;
     double   sum_wait;
     uint64_t ui, stamp, object;
@@ -23,7 +23,7 @@ struct GG1T {
         GG1T &m = *this;
         CMB_PROCESS_BEGIN
         for (ui = 0u; ui < num_objects; ui++) {
-            CMB_PROCESS_HOLD(cmb_random_erlang(2u, 0.5 * arr_mean));
+            CMB_PROCESS_HOLD_SAMPLED(ARRIVAL);          // cmb_process_hold(<Erlang-2>): drawn by the dispatcher, see sample()
             stamp = (uint64_t)__double_as_longlong(cmb_time());
             CMB_OBJECTQUEUE_PUT(queue, stamp);
         }
@@ -36,14 +36,22 @@ struct GG1T {
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_OBJECTQUEUE_GET(queue, object);
-            do {
-                s = cmb_random_normal(srv_mean, 0.25 * srv_mean);
-            } while (s < 0.0);
-            CMB_PROCESS_HOLD(s);
+            CMB_PROCESS_HOLD_SAMPLED(SERVICE);          // cmb_process_hold(<normal, redrawn while negative>)
             sum_wait += cmb_time() - __longlong_as_double((long long)object);
             obj_cnt += 1u;
         }
         CMB_PROCESS_END
+    }
+
+    // the durations of the two holds, as SURVEY.md section 8d-4 defines them
+    CMB_FN double sample(S &sim, uint32_t which)
+    {
+        if (which == ARRIVAL) return cmb_random_erlang(2u, 0.5 * arr_mean);
+        double v;
+        do {
+            v = cmb_random_normal(srv_mean, 0.25 * srv_mean);
+        } while (v < 0.0);
+        return v;
     }
 
     CMB_FN void run_trial(S &sim, const cmb::TrialIn &in)

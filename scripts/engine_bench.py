@@ -34,10 +34,28 @@ def timed(fn, reps=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--gg1", action="store_true", help="G/G/1: gg1_kernel next to gg1_model.cuh on the static tier")
     ap.add_argument("--static-only", action="store_true", help="time M/M/1 on the static tier only (variant sweeps)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     rows = []
+    if a.gg1:
+        trials, nobj = 262144, 100000
+        am = torch.full((trials,), 1.25, dtype=torch.float64, device=dev)
+        sm = torch.full((trials,), 1.0, dtype=torch.float64, device=dev)
+        out = {}
+        for label, variant in (("fast", 0), ("static", cb.VARIANT_STATIC)):
+            bufs = cb.TrialBuffers(trials, dev, 0, cb.MODEL_GG1, 1, variant)
+            cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, model=cb.MODEL_GG1, variant=variant)
+            res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, model=cb.MODEL_GG1, variant=variant, buffers=bufs))
+            ev = int(res.events.sum().item())
+            out[label] = {"ms": ms, "events_per_s": ev / ms * 1e3, "events": ev, "bad": int((res.status != 0).sum().item()),
+                          "sum_check": float(res.sum_wait.sum().item())}
+            del bufs
+        print(json.dumps({"model": "G/G/1", "trials": trials, "objects": nobj, **out,
+                          "static_over_fast_time": out["static"]["ms"] / out["fast"]["ms"],
+                          "same_answers": out["fast"]["sum_check"] == out["static"]["sum_check"] and out["fast"]["events"] == out["static"]["events"]}), flush=True)
+        return
     if a.static_only:
         trials, nobj = 65536, 100000
         am = torch.full((trials,), 1 / 0.9, dtype=torch.float64, device=dev)
