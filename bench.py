@@ -343,9 +343,9 @@ def secondary_configs(args, cb, torch, dist, dev, rank, world, barrier):
                                "tier (CIMBA_B200_VARIANT_STATIC: registers + shared memory, general engine as repair pass), "
                                "65536 replications per GPU at full length", cb.MODEL_MM1, 1, 1.0 / ARRIVAL_RATE, 1.0, 0, args.trials, 0,
                                variant=cb.VARIANT_STATIC))
-    guarded(lambda: queue_like("G/G/1 (config 4's model) from its authoring-surface source on the static tier, 262144 replications in all "
-                               "x 1e5 objects (its bodies draw Erlang and normal variates themselves, slow paths inline: profiles/r02_engine.md)",
-                               cb.MODEL_GG1, 1, 1.25, 1.0, 262144, 0, 1, variant=cb.VARIANT_STATIC, objects=min(args.objects, 100_000)))
+    guarded(lambda: queue_like("G/G/1 (config 4's model) from its authoring-surface source (gg1_model.cuh: Erlang-2 and redrawn-normal holds as "
+                               "CMB_PROCESS_HOLD_SAMPLED) on the static tier, 1048576 replications in all x 1e5 objects",
+                               cb.MODEL_GG1, 1, 1.25, 1.0, 1048576, 0, 1, variant=cb.VARIANT_STATIC, objects=min(args.objects, 100_000)))
     guarded(lambda: queue_like("M/M/1 written against the device authoring surface, on the general engine (CIMBA_B200_VARIANT_GENERAL), "
                                "65536 replications per GPU x 1e5 objects", cb.MODEL_MM1, 1, 1.0 / ARRIVAL_RATE, 1.0, 0, args.trials, 0,
                                variant=cb.VARIANT_GENERAL, objects=min(args.objects, 100_000)))
