@@ -152,7 +152,12 @@ const char *cimba_b200_model_name(int model_id);
 #define CIMBA_B200_ETRIAL    -4  /* at least one trial reported a non-zero status */
 #define CIMBA_B200_ENOMEM    -5
 
-/* Per-trial status bits (0 = ok) */
+/* Per-trial status bits (0 = ok).  Bits 1, 2, 8 and 16 are what a fixed-capacity kernel (the fused M/M/1, G/G/1, M/M/c kernels,
+ * the static tier, the round-1 coverage kernels) sets when a trial outgrows its tables: the launch re-runs such trials on the
+ * general engine by itself, so a caller only sees them with status == NULL (no repair possible) or variant 1.  Bit 4: the fused
+ * kernels keep event keys in 30 bits (the reference: 64) - a trial of more than 2^30 events is flagged, not repaired (the general
+ * engine has 64-bit keys but would need hours for such a trial).  Bit 64: the general engine's growth arena ran out -
+ * pass a larger workspace (cimba_b200_workspace_bytes sizes it for the model's declared need). */
 #define CIMBA_B200_TRIAL_QUEUE_OVERFLOW 1u
 #define CIMBA_B200_TRIAL_FEL_OVERFLOW   2u
 #define CIMBA_B200_TRIAL_KEY_OVERFLOW   4u
