@@ -29,6 +29,75 @@ namespace cmb {
 constexpr int STATIC_WINDOW = 32;       // on-chip entries per queue and trial
 constexpr int STATIC_BLOCK = 64;
 
+// One event slot per process (the shape of SlotFel, engine.cuh), the action packed into the key's two low bits as mm1_fast.cuh
+// does: key = (issue counter << 2) | action, 0 = empty.  Counters are unique, so ordering by this word is ordering by issue
+// counter - the reference's tie-break (src/cmi_hashheap.c:55-80).
+template <int N>
+struct StaticFel {
+    double   t[N];
+    uint32_t key[N];
+    uint32_t issued;
+
+    CMB_FN void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            t[i] = __longlong_as_double(0x7ff0000000000000LL);
+            key[i] = 0u;
+        }
+        issued = 0u;
+    }
+
+    CMB_FN bool schedule(int p, uint32_t action, double time)      // false: the process already had a pending event
+    {
+        const uint32_t k = (++issued << 2) | action;
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i == p) {
+                ok = key[i] == 0u;
+                t[i] = time;
+                key[i] = k;
+            }
+        }
+        return ok;
+    }
+
+    CMB_FN void drop(int p)
+    {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i == p) {
+                t[i] = __longlong_as_double(0x7ff0000000000000LL);
+                key[i] = 0u;
+            }
+        }
+    }
+
+    // cmi_hashheap_dequeue: the first entry under (time asc, key asc); false when the list is empty
+    CMB_FN bool pop(int &p, uint32_t &action, double &time, uint32_t &counter)
+    {
+        int best = 0;
+        double bt = t[0];
+        uint32_t bk = key[0];
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const bool before = (t[i] < bt) | ((t[i] == bt) & (key[i] < bk));
+            if (before) {
+                best = i;
+                bt = t[i];
+                bk = key[i];
+            }
+        }
+        drop(best);
+        p = best;
+        action = bk & 3u;
+        time = bt;
+        counter = bk >> 2;
+        return bk != 0u;
+    }
+};
+
 // the wait list of a guard whose only possible waiters are the NPROC processes: who waits, and since when (FIFO)
 template <int NPROC>
 struct static_guard {
@@ -59,10 +128,10 @@ struct StaticSim {
     uint32_t       status;
     uint32_t       current;
     uint32_t       current_event;
-    uint64_t       pops;
+    uint32_t       pops;
     uint32_t       nproc, nqueue, guard_seq;
     Proc           proc[NPROC];
-    SlotFel<NPROC> fel;
+    StaticFel<NPROC> fel;
     uint32_t       cmd;
     uint32_t       cmd_sample;
     double         cmd_value;
@@ -247,19 +316,50 @@ CMB_FN void process_stop(StaticSim<NPROC, NQUEUE> &sim, Model &, uint32_t pid, i
         if ((uint32_t)i == pid && sim.proc[i].status == PROC_RUNNING) {
             sim.proc[i].status = PROC_FINISHED;
             sim.proc[i].exit_value = value;
-            sim.fel.t[i] = __longlong_as_double(0x7ff0000000000000LL);
-            sim.fel.key[i] = 0u;
-            sim.fel.act[i] = ACT_NONE;
+            sim.fel.drop(i);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ dispatcher
+// A model may state the kinds of its processes in creation order - `static CMB_FN constexpr uint32_t static_kind(uint32_t i)` -
+// and the dispatcher then knows at compile time which body process i runs (one copy of each body instead of NPROC, no run-time
+// branch on the kind); a trial whose cmb_process_create calls disagree with the table is flagged and goes to the general engine.
+template <class Model, class = void>
+struct StaticKinds {
+    static constexpr bool known = false;
+    template <int I>
+    static CMB_FN uint32_t of(uint32_t runtime_kind) { return runtime_kind; }
+    template <int NPROC, int NQUEUE>
+    static CMB_FN bool agree(const StaticSim<NPROC, NQUEUE> &) { return true; }
+};
+template <class Model>
+struct StaticKinds<Model, decltype((void)Model::static_kind(0u))> {
+    static constexpr bool known = true;
+    template <int I>
+    static CMB_FN uint32_t of(uint32_t) { return Model::static_kind((uint32_t)I); }
+    template <int NPROC, int NQUEUE>
+    static CMB_FN bool agree(const StaticSim<NPROC, NQUEUE> &sim)
+    {
+        return agree_from<NPROC, NQUEUE, 0>(sim);
+    }
+    template <int NPROC, int NQUEUE, int I>
+    static CMB_FN bool agree_from(const StaticSim<NPROC, NQUEUE> &sim)
+    {
+        if constexpr (I < NPROC) {
+            return ((uint32_t)I >= sim.nproc || sim.proc[I].kind == Model::static_kind((uint32_t)I)) && agree_from<NPROC, NQUEUE, I + 1>(sim);
+        }
+        else {
+            return true;
+        }
+    }
+};
+
 template <class Model, int NPROC, int NQUEUE, int I>
 struct StaticDispatch {
     static CMB_FN void run(StaticSim<NPROC, NQUEUE> &sim, Model &m, int who)
     {
-        if (who == I) m.process(sim, (uint32_t)I, sim.proc[I].kind, CMB_PROCESS_SUCCESS);
+        if (who == I) m.process(sim, (uint32_t)I, StaticKinds<Model>::template of<I>(sim.proc[I].kind), CMB_PROCESS_SUCCESS);
         else StaticDispatch<Model, NPROC, NQUEUE, I + 1>::run(sim, m, who);
     }
 };
@@ -329,6 +429,7 @@ inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const
     out.max_queue = 0u;
     for (int k = 0; k < 8; k++) out.counters[k] = 0u;
     m.run_trial(sim, in);
+    if (!StaticKinds<Model>::agree(sim)) sim.status |= TRIAL_ERR_PROC_OVERFLOW;
     int who = 0;
     while (static_step(sim, m, who)) {
         if (sim.pops <= trace_cap) {
@@ -425,6 +526,7 @@ static_trial_kernel(const StaticArgs sa)
         for (int k = 0; k < 16; k++) in.params[k] = a.params[k];
         in.trial = a.first_trial + trial;
         m.run_trial(sim, in);
+        if (!StaticKinds<ModelT<S>>::agree(sim)) sim.status |= TRIAL_ERR_PROC_OVERFLOW;
     }
 
 #ifdef STATIC_NO_LOOKAHEAD
@@ -455,7 +557,7 @@ static_trial_kernel(const StaticArgs sa)
                 if (a.objects)   a.objects[trial] = out.objects;
                 if (a.t_end)     a.t_end[trial] = sim.now;
                 if (a.sum_wait)  a.sum_wait[trial] = out.sum_wait;
-                if (a.status)    a.status[trial] = sim.status;
+                if (a.status)    a.status[trial] = sim.status | (sim.fel.issued > 0x3ffffff0u ? TRIAL_ERR_KEY_OVERFLOW : 0u);
                 if (a.max_queue) a.max_queue[trial] = out.max_queue;
                 if (a.counters) {
                     for (int k = 0; k < 8; k++) a.counters[trial * 8u + k] = out.counters[k];

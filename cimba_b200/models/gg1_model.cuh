@@ -17,6 +17,7 @@ struct GG1T {
     double   sum_wait;
     uint64_t ui, stamp, object;
     enum : uint32_t { ARRIVAL, SERVICE };
+    static CMB_FN constexpr uint32_t static_kind(uint32_t i) { return i == 0u ? ARRIVAL : SERVICE; }    // creation order (run_trial): what the static tier dispatches by
 
     CMB_FN void arrivalfunc(S &sim, uint32_t me, int64_t sig)
     {

@@ -18,6 +18,7 @@ struct MM1T {
     double   sum_wait;
     uint64_t ui, stamp, object;                         // body locals that live across a blocking call
     enum : uint32_t { ARRIVAL, SERVICE };
+    static CMB_FN constexpr uint32_t static_kind(uint32_t i) { return i == 0u ? ARRIVAL : SERVICE; }    // creation order (run_trial): what the static tier dispatches by
     static constexpr bool exponential_holds_only = true;     // no body draws: the static tier may look one variate ahead
 
     CMB_FN void arrivalfunc(S &sim, uint32_t me, int64_t sig)            // :52-68

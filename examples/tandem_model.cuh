@@ -19,6 +19,7 @@ struct TandemT {
     double   sum_wait;
     uint64_t ui, stamp, at1, at2;
     enum : uint32_t { SOURCE, STATION1, STATION2 };
+    static CMB_FN constexpr uint32_t static_kind(uint32_t i) { return i == 0u ? SOURCE : (i == 1u ? STATION1 : STATION2); }   // creation order, for the static tier's dispatcher
 
     CMB_FN void source(S &sim, uint32_t me, int64_t sig)
     {
