@@ -46,6 +46,7 @@
 #include "../models/renege_model.cuh"
 #include "../models/hold_general_model.cuh"
 #include "../models/cheese_model.cuh"
+#include "../models/mm1_recorded_model.cuh"
 #include "../models/guarded_model.cuh"
 #include "../models/workshop_model.cuh"
 #include "../models/coverage_models.cuh"
@@ -114,12 +115,14 @@ bool mmc_goes_general(const cimba_b200_device_job *job)
 
 bool fast_goes_general(const cimba_b200_device_job *job)
 {
-    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_GENERAL;
+    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1 || job->model == CIMBA_B200_MODEL_MM1_RECORDED) &&
+           job->variant == CIMBA_B200_VARIANT_GENERAL;
 }
 
 bool goes_static(const cimba_b200_device_job *job)
 {
-    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1) && job->variant == CIMBA_B200_VARIANT_STATIC;
+    return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1 || job->model == CIMBA_B200_MODEL_MM1_RECORDED) &&
+           job->variant == CIMBA_B200_VARIANT_STATIC;
 }
 
 bool hold_goes_general(const cimba_b200_device_job *job)
@@ -406,17 +409,19 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (harbor_goes_general(job)) return cmb::workspace_bytes_for<models::HarborGeneral>(*job);
     if (goes_static(job)) {
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_static<models::MM1T, 2, 1>(*job)
-                                                  : cmb::workspace_bytes_static<models::GG1T, 2, 1>(*job);
+             : job->model == CIMBA_B200_MODEL_GG1 ? cmb::workspace_bytes_static<models::GG1T, 2, 1>(*job)
+                                                  : cmb::workspace_bytes_static<models::MM1RecordedT, 2, 1>(*job);
     }
     if (fast_goes_general(job)) {
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_for<models::MM1>(*job)
-                                                  : cmb::workspace_bytes_for<models::GG1>(*job);
+             : job->model == CIMBA_B200_MODEL_GG1 ? cmb::workspace_bytes_for<models::GG1>(*job)
+                                                  : cmb::workspace_bytes_for<models::MM1Recorded>(*job);
     }
     if (is_queue_model(job->model) || job->model == CIMBA_B200_MODEL_MMC) {
         const uint32_t cap = spill_cap_of(job);
         const uint64_t rings = job->num_trials * (uint64_t)(cap == 0xffffffffu ? QUEUE_SPILL_CAP : cap) * sizeof(double);
         // the rings of the fast kernel, then the growth arena of its repair pass
-        return align256(rings) + (job->model == CIMBA_B200_MODEL_MM1_RECORDED ? 0u : repair_arena_bytes(job));
+        return align256(rings) + repair_arena_bytes(job);
     }
     if (job->model == CIMBA_B200_MODEL_HARBOR) {
         return job->num_trials * (uint64_t)sizeof(HarborState);
@@ -467,7 +472,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
         const int e = job->model == CIMBA_B200_MODEL_MM1 ? cmb::launch_static_model<models::MM1T, 2, 1>(*job, st)
-                                                         : cmb::launch_static_model<models::GG1T, 2, 1>(*job, st);
+                    : job->model == CIMBA_B200_MODEL_GG1 ? cmb::launch_static_model<models::GG1T, 2, 1>(*job, st)
+                                                         : cmb::launch_static_model<models::MM1RecordedT, 2, 1>(*job, st);
         g_launches += job->status != nullptr ? 2 : 1;
         return e == 0 ? CIMBA_B200_OK : cuda_fail((cudaError_t)e, "static_trial_kernel launch");
     }
@@ -499,6 +505,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         }
         if (job->model == CIMBA_B200_MODEL_MM1)
             return launch_general<models::MM1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MM1> launch");
+        if (job->model == CIMBA_B200_MODEL_MM1_RECORDED)
+            return launch_general<models::MM1Recorded>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<MM1Recorded> launch");
         return launch_general<models::GG1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<GG1> launch");
     }
 
@@ -548,7 +556,10 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             else       queue_kernel<0, false, true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
             g_launches++;
             cudaError_t e = cudaGetLastError();
-            return e == cudaSuccess ? CIMBA_B200_OK : cuda_fail(e, "queue_kernel (recorded) launch");
+            if (e != cudaSuccess) return cuda_fail(e, "queue_kernel (recorded) launch");
+            if (job->status == nullptr) return CIMBA_B200_OK;
+            return launch_general<models::MM1Recorded>(job, (unsigned char *)job->workspace + align256(job->num_trials * (uint64_t)qa.spill_cap * sizeof(double)),
+                                                       repair_arena_bytes(job), REPAIR_BITS, st, "repair pass (M/M/1 with its queue history)");
         }
         if (job->variant == 1) return launch_queue<0>(qa, trace, grid, st);
         if (trace) {

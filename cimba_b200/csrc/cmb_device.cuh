@@ -508,6 +508,7 @@ struct condition {
 
 struct Sim {
     using queue_type = objectqueue;     // what a model template declares its queues as (cmb_static.cuh has another)
+    using recorded_queue_type = objectqueue;    // ... a queue whose length history will be switched on
     Sfc64          rng;
     const ZigHot  *hot;
     double         now;

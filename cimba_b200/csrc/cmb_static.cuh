@@ -105,17 +105,31 @@ struct static_guard {
     uint32_t seq[NPROC];
 };
 
-template <int NPROC>
-struct static_objectqueue {
+// RECORD: the queue can keep its length history (cmb_objectqueue_recording_start, src/cmb_objectqueue.c:161-177), folded on the
+// fly into the time-weighted summary cmb_timeseries_summarize would make of it (TimeWeighted, summary.cuh).  A queue type of its
+// own (S::recorded_queue_type) so that models that never record carry neither the registers nor the sampling code.
+template <bool RECORD>
+struct static_history {
+};
+template <>
+struct static_history<true> {
+    uint32_t recording;
+    TimeWeighted history;
+};
+
+template <int NPROC, bool RECORD = false>
+struct static_objectqueue : static_history<RECORD> {
     static_guard<NPROC> front, rear;
     StampRing<STATIC_WINDOW> ring;
     uint64_t capacity;
     uint32_t longest;
+    uint32_t length;            // = ring.len (cmb_objectqueue_length)
 };
 
 template <int NPROC, int NQUEUE>
 struct StaticSim {
-    using queue_type = static_objectqueue<NPROC>;
+    using queue_type = static_objectqueue<NPROC, false>;
+    using recorded_queue_type = static_objectqueue<NPROC, true>;
     struct Proc {
         uint32_t pc, status, kind, ctx;
         double   f[2];
@@ -269,8 +283,8 @@ CMB_FN double draw_std_normal(StaticSim<NPROC, NQUEUE> &sim)                    
 }
 
 // ------------------------------------------------------------------------------------------------ objectqueue
-template <int NPROC, int NQUEUE>
-CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC> &q, uint64_t capacity)
+template <int NPROC, int NQUEUE, bool RECORD>
+CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, RECORD> &q, uint64_t capacity)
 {
     uint32_t k = sim.nqueue;
     if (k >= (uint32_t)NQUEUE) {
@@ -285,23 +299,48 @@ CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectq
                 sim.spill_cap ? sim.spill + (size_t)k * sim.spill_cap : nullptr, sim.spill_cap);
     q.capacity = capacity;
     q.longest = 0u;
+    q.length = 0u;
+    if constexpr (RECORD) q.recording = 0u;
 }
 
-template <class Model, int NPROC, int NQUEUE>
-CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC> &q, uint64_t obj)
+template <int NPROC, int NQUEUE>
+CMB_FN void objectqueue_recording_start(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, true> &q)
+{
+    q.recording = 1u;
+    q.history.start();
+    q.history.sample((double)q.ring.len, sim.now);
+}
+
+template <int NPROC, int NQUEUE>
+CMB_FN void objectqueue_recording_stop(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, true> &q)
+{
+    if (q.recording) q.history.sample((double)q.ring.len, sim.now);
+    q.recording = 0u;
+}
+
+template <class Model, int NPROC, int NQUEUE, bool RECORD>
+CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t obj)
 {
     if ((uint64_t)q.ring.len >= q.capacity) return false;
     if (!q.ring.put(__longlong_as_double((long long)obj))) sim.status |= TRIAL_ERR_QUEUE_OVERFLOW;     // void from here on: re-run
     q.longest = q.ring.len > q.longest ? q.ring.len : q.longest;
+    q.length = q.ring.len;
+    if constexpr (RECORD) {
+        if (q.recording) q.history.sample((double)q.ring.len, sim.now);        // record_sample in put, :289
+    }
     sim.guard_signal(q.front, true);
     return true;
 }
 
-template <class Model, int NPROC, int NQUEUE>
-CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC> &q, uint64_t &obj)
+template <class Model, int NPROC, int NQUEUE, bool RECORD>
+CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t &obj)
 {
     if (q.ring.len == 0u) return false;
     obj = (uint64_t)__double_as_longlong(q.ring.take());
+    q.length = q.ring.len;
+    if constexpr (RECORD) {
+        if (q.recording) q.history.sample((double)q.ring.len, sim.now);        // ... and in get, :226-229
+    }
     sim.guard_signal(q.rear, true);
     return true;
 }

@@ -25,9 +25,9 @@ ROOT = Path(__file__).resolve().parents[1]
 BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 10: cb.MODEL_HARBOR, 16: cb.MODEL_RENEGE,
            18: cb.MODEL_POOL_RECORDED,
            # the reference's own test worlds: since round 2 they run on the general engine by default
-           3: cb.MODEL_GUARDED, 4: cb.MODEL_PREEMPT, 5: cb.MODEL_BUFFER, 6: cb.MODEL_PRIOQ, 8: cb.MODEL_TIMERS,
+           9: cb.MODEL_MM1_RECORDED, 3: cb.MODEL_GUARDED, 4: cb.MODEL_PREEMPT, 5: cb.MODEL_BUFFER, 6: cb.MODEL_PRIOQ, 8: cb.MODEL_TIMERS,
            11: cb.MODEL_GUARDED_RECORDED, 12: cb.MODEL_BUFFER_RECORDED, 13: cb.MODEL_PRIOQ_RECORDED, 14: cb.MODEL_RESOURCE_RECORDED}
-COVERAGE = (3, 4, 5, 6, 8, 11, 12, 13, 14)
+COVERAGE = (3, 4, 5, 6, 8, 9, 11, 12, 13, 14)
 
 
 def run_case(case, model_id, variant, n, trace=True, spill=0):
@@ -58,7 +58,7 @@ def test_models_on_the_general_engine_match_the_reference_vectors(case):
     compare(case, res, n)
 
 
-@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 2)], ids=case_id)
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 2, 9)], ids=case_id)
 def test_default_kernels_with_their_repair_pass_match_the_reference_vectors(case):
     """variant 0 = the fast kernel; whatever it flags the repair pass re-runs.  The heavy-traffic, overload and
     64-server cases cannot be served by the fixed tables alone."""
@@ -172,7 +172,7 @@ def test_a_model_that_exists_only_as_a_user_library_matches_the_reference():
         compare(case, run_case(case, mid, 0, n), n)
 
 
-@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1)], ids=case_id)
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 9)], ids=case_id)
 def test_static_tier_matches_the_reference_vectors(case):
     """CIMBA_B200_VARIANT_STATIC: mm1_model.cuh / gg1_model.cuh - the text the general engine runs - compiled against
     cmb::StaticSim<2, 1> (registers + shared memory).  Heavy traffic and overload outgrow its 32 + 512 entry queue: those trials
