@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ.get("CIMBA_B200_LIB") or
 NO_FIELD = C.c_size_t(-1).value
 
 MODEL_MM1, MODEL_GG1, MODEL_MMC, MODEL_GUARDED, MODEL_PREEMPT, MODEL_BUFFER, MODEL_PRIOQ, MODEL_HOLD, MODEL_TIMERS, MODEL_MM1_RECORDED, MODEL_HARBOR, MODEL_GUARDED_RECORDED, MODEL_BUFFER_RECORDED, MODEL_PRIOQ_RECORDED, MODEL_RESOURCE_RECORDED, MODEL_AWACS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
-MODEL_RENEGE, MODEL_POOL_RECORDED, MODEL_USER_BASE, VARIANT_GENERAL, VARIANT_STATIC = 16, 18, 1000, 16, 17
+MODEL_RENEGE, MODEL_POOL_RECORDED, MODEL_TUTORIAL1, MODEL_USER_BASE, VARIANT_GENERAL, VARIANT_STATIC = 16, 18, 19, 1000, 16, 17
 MAP_LANE, MAP_WARP = 1, 32
 
 OK, EINVAL, ENODEVICE, ECUDA, ETRIAL, ENOMEM = 0, -1, -2, -3, -4, -5
@@ -62,6 +62,7 @@ class Experiment(C.Structure):
         ("off_obj_cnt", C.c_size_t), ("off_sum_wait", C.c_size_t), ("off_avg_wait", C.c_size_t),
         ("off_events", C.c_size_t), ("off_t_end", C.c_size_t), ("off_status", C.c_size_t),
         ("off_max_queue", C.c_size_t), ("off_counters", C.c_size_t),
+        ("params", C.POINTER(C.c_double)), ("num_params", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

@@ -47,6 +47,7 @@
 #include "../models/hold_general_model.cuh"
 #include "../models/cheese_model.cuh"
 #include "../models/mm1_recorded_model.cuh"
+#include "../models/tutorial1_model.cuh"
 #include "../models/guarded_model.cuh"
 #include "../models/workshop_model.cuh"
 #include "../models/coverage_models.cuh"
@@ -403,6 +404,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
     if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
+    if (job->model == CIMBA_B200_MODEL_TUTORIAL1) return cmb::workspace_bytes_for<models::Tutorial1>(*job);
     if (coverage_goes_general(job)) return for_coverage_model<WorkspaceOf>(job->model, job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
@@ -485,7 +487,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
         return for_coverage_model<LaunchOf>(job->model, job, (unsigned char *)job->workspace, job->workspace_bytes, 0u, st);
     }
-    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
+    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || job->model == CIMBA_B200_MODEL_TUTORIAL1 || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -493,6 +495,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         unsigned char *ws = (unsigned char *)job->workspace;
         if (job->model == CIMBA_B200_MODEL_RENEGE)
             return launch_general<models::Renege>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Renege> launch");
+        if (job->model == CIMBA_B200_MODEL_TUTORIAL1)
+            return launch_general<models::Tutorial1>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Tutorial1> launch");
         if (job->model == CIMBA_B200_MODEL_POOL_RECORDED)
             return launch_general<models::Cheese>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Cheese> launch");
         if (job->model == CIMBA_B200_MODEL_MMC)
@@ -1208,6 +1212,8 @@ int run_experiment_chunk(void *array, uint64_t num_trials, size_t stride, const 
     job.mapping = d->mapping;
     job.variant = d->variant;
     job.queue_spill_cap = d->queue_spill_cap;
+    job.params = d->params;
+    job.num_params = d->num_params;
     job.master_seed = d->master_seed;
     job.first_trial = d->first_trial;
     job.num_trials = n;

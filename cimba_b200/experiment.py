@@ -36,7 +36,7 @@ def fmix64(seed: int, nonce: int) -> int:
 def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODEL_MM1,
                          num_objects: int, master_seed: int, first_trial: int = 0,
                          servers: int = 1, mapping: int = 0, device: int = -1, variant: int = 0,
-                         all_gpus: bool = False, max_gpus: int = 0, queue_spill_cap: int = 0) -> None:
+                         all_gpus: bool = False, max_gpus: int = 0, queue_spill_cap: int = 0, params=()) -> None:
     """Run every trial of a host-resident experiment array on the GPU, in place.
 
     ``experiment_array`` is a 1-D numpy structured array (any dtype that has
@@ -80,6 +80,10 @@ def cimba_run_experiment(experiment_array: np.ndarray, *, model: int = _lib.MODE
         off_avg_wait=off("avg_wait", "<f8"), off_events=off("events", "<u8"),
         off_t_end=off("t_end", "<f8"), off_status=off("status", "<u4"),
         off_max_queue=off("max_queue", "<u4"), off_counters=off_counters)
+    par = (C.c_double * max(1, len(params)))(*[float(v) for v in params])
+    if len(params):
+        desc.params = C.cast(par, C.POINTER(C.c_double))
+        desc.num_params = len(params)
     if all_gpus:
         check(lib.cimba_b200_run_experiment_all_gpus(arr.ctypes.data_as(C.c_void_p), len(arr),
                                                      arr.dtype.itemsize, C.byref(desc), max_gpus))

@@ -125,6 +125,10 @@ extern "C" {
                                     * m2, m3, m4, wsum} (count as u64, the rest as bit patterns); objects = successful acquisitions.
                                     * 20 units, 100 time units and the golden seed give test/reference/resourcepool.txt's
                                     * "N 120  Mean 19.77  StdDev 1.147  Variance 1.316  Skewness -6.626  Kurtosis 46.75" */
+#define CIMBA_B200_MODEL_TUTORIAL1 19    /* cimba_b200/models/tutorial1_model.cuh = the trial of tutorial/tut_1_7.c (run_MM1_trial :155-222): M/M/1 in a
+                                          * cmb_buffer, level history on from params[0] (warm-up time) for num_objects time units, end event of
+                                          * priority -100; arr_mean / srv_mean = 1 / arr_rate, 1 / srv_rate; counters[0..7] = the history's
+                                          * cmb_wtdsummary (counters[3] = the tutorial's avg_queue_length, as a double's bits).  General engine. */
 
 /* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
  * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */
@@ -300,6 +304,11 @@ typedef struct cimba_b200_experiment {
     size_t off_status;          /* uint32, out (or NO_FIELD) */
     size_t off_max_queue;       /* uint32, out (or NO_FIELD): longest queue / deepest list / most ships alive */
     size_t off_counters;        /* uint64[8], out (or NO_FIELD): the model's counters (see CIMBA_B200_MODEL_*) */
+    /* the model's scalar parameters, as cimba_b200_device_job.params: HOST pointer to num_params doubles (or NULL, 0) -
+     * e.g. the warm-up time of CIMBA_B200_MODEL_TUTORIAL1, the patience of CIMBA_B200_MODEL_RENEGE */
+    const double *params;
+    uint32_t num_params;
+    uint32_t reserved;
 } cimba_b200_experiment;
 
 /* Blocks until all trials are done; results written into the caller's array.

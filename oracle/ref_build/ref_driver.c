@@ -1009,11 +1009,13 @@ static void rn_end_event(void *subject, void *object)
 }
 
 static double g_renege_patience = 0.0;          /* par0, set by ref_set_param before the trials run */
+static double g_warmup_time = 0.0;              /* par0 of model 19 */
 
 void ref_set_param(int index, double value)
 {
     if (index == 0) {
         g_renege_patience = value;
+        g_warmup_time = value;
     }
 }
 
@@ -1944,6 +1946,98 @@ static void run_resource_trial(struct ref_trial *t)
     free(w);
 }
 
+/* ------------------------------------------------- model 19: the trial of the reference's first tutorial
+ *
+ * tutorial/tut_1_7.c run_MM1_trial (:155-222) and its two processes and three events (:69-151): an M/M/1 queue held in a
+ * cmb_buffer (amounts of 1), the level history switched on by an event at the warm-up time and off by an event at warm-up +
+ * duration, where an end event of priority -100 stops both processes.  The tutorial's result is the time-weighted mean level.
+ *   arr_mean / srv_mean = 1 / arr_rate, 1 / srv_rate; num_objects = duration; par0 = warm-up time.
+ * counters[0..7] = the eight words of the history's cmb_wtdsummary; objects = units put; sum_wait = units got.
+ */
+struct u_world {
+    struct ref_trial *trl;
+    struct cmb_buffer *que;
+    struct cmb_process *arr, *srv;
+};
+
+static void *u_arrival_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct u_world *w = vw;
+    for (;;) {
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->arr_mean));
+        uint64_t n = 1u;
+        (void)cmb_buffer_put(w->que, &n);
+        w->trl->objects += 1u;
+    }
+}
+
+static void *u_service_body(struct cmb_process *me, void *vw)
+{
+    cmb_unused(me);
+    struct u_world *w = vw;
+    for (;;) {
+        uint64_t n = 1u;
+        (void)cmb_buffer_get(w->que, &n);
+        w->trl->sum_wait += 1.0;
+        (void)cmb_process_hold(cmb_random_exponential(w->trl->srv_mean));
+    }
+}
+
+static void u_start_rec(void *subject, void *object)
+{
+    cmb_unused(subject);
+    cmb_buffer_recording_start(((struct u_world *)object)->que);
+}
+
+static void u_stop_rec(void *subject, void *object)
+{
+    cmb_unused(subject);
+    cmb_buffer_recording_stop(((struct u_world *)object)->que);
+}
+
+static void u_end_sim(void *subject, void *object)
+{
+    cmb_unused(subject);
+    struct u_world *w = object;
+    cmb_process_stop(w->arr, NULL);
+    cmb_process_stop(w->srv, NULL);
+}
+
+static void run_tutorial1_trial(struct ref_trial *t)
+{
+    struct u_world w = { .trl = t };
+    w.que = cmb_buffer_create();
+    cmb_buffer_initialize(w.que, "Queue", CMB_UNLIMITED);
+    w.arr = cmb_process_create();
+    cmb_process_initialize(w.arr, "Arrival", u_arrival_body, &w, 0);
+    cmb_process_start(w.arr);
+    w.srv = cmb_process_create();
+    cmb_process_initialize(w.srv, "Service", u_service_body, &w, 0);
+    cmb_process_start(w.srv);
+    double when = g_warmup_time;
+    (void)cmb_event_schedule(u_start_rec, NULL, &w, when, 0);
+    when += (double)t->num_objects;
+    (void)cmb_event_schedule(u_stop_rec, NULL, &w, when, 0);
+    (void)cmb_event_schedule(u_end_sim, NULL, &w, when, -100);
+
+    pump_events(t);
+
+    struct cmb_wtdsummary ws;
+    cmb_wtdsummary_initialize(&ws);
+    (void)cmb_timeseries_summarize(cmb_buffer_history(w.que), &ws);
+    const struct cmb_datasummary *ds = (const struct cmb_datasummary *)&ws;
+    const double v[7] = { ds->min, ds->max, ds->m1, ds->m2, ds->m3, ds->m4, ws.wsum };
+    t->counter[0] = ds->count;
+    memcpy(&t->counter[1], v, sizeof(v));
+    cmb_process_terminate(w.srv);
+    cmb_process_destroy(w.srv);
+    cmb_process_terminate(w.arr);
+    cmb_process_destroy(w.arr);
+    cmb_buffer_terminate(w.que);
+    cmb_buffer_destroy(w.que);
+}
+
 /* -------------------------------------------------------------- dispatcher */
 
 static void stock_noop_event(void *subject, void *object)
@@ -2061,7 +2155,10 @@ static void run_trial(void *vt)
     cmb_random_initialize(t->seed);
     cmb_event_queue_initialize(0.0);
     memset(t->counter, 0, sizeof(t->counter));
-    if (t->model == 18) {
+    if (t->model == 19) {
+        run_tutorial1_trial(t);
+    }
+    else if (t->model == 18) {
         run_cheese_trial(t);
     }
     else if (t->model == 17) {

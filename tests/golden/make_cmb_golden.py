@@ -61,6 +61,9 @@ CASES = [
     (8, 1, 2000, 0.4, 1.5, [], 4),
     (9, 1, 20000, 1 / 0.9, 1.0, [], 6),           # tutorial 1 / test/test_cimba.c: M/M/1 with the queue's history on
     (9, 1, 30000, 1 / 0.97, 1.0, [], 3),
+    (19, 1, 20000, 1 / 0.9, 1.0, [1000.0], 6),    # tutorial/tut_1_7.c's trial: warm-up 1000, duration 20000, rho 0.9
+    (19, 1, 30000, 1 / 0.5, 1.0, [0.0], 4),       # no warm-up, rho 0.5
+    (19, 1, 5000, 1 / 0.975, 1.0, [250.5], 4),    # the tutorial's heaviest load
 ]
 
 
@@ -77,7 +80,7 @@ def main():
             _, keys, times = trace_trial(ref, "ref", model, servers, ref.ref_fmix64(MASTER, i), nobj, arr, srv, TRACE)
             h = hashlib.sha256(np.array(keys, dtype=np.uint64).tobytes() + np.array(times, dtype=np.float64).tobytes())
             trials.append({"events": r.events, "objects": r.objects, "t_end": float(r.t_end).hex(), "sum_wait": float(r.sum_wait).hex(),
-                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model in (3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 18)), "max_queue": r.max_queue, "max_fel": r.max_fel, "pops": len(keys), "trace_sha256": h.hexdigest()})
+                           "counters": list(r.counter)[:4], "counters8": list(r.counter), "all8": int(model in (3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 18, 19)), "max_queue": r.max_queue, "max_fel": r.max_fel, "pops": len(keys), "trace_sha256": h.hexdigest()})
         out["cases"].append({"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(),
                              "srv_mean": float(srv).hex(), "params": params, "trials": trials})
         print(model, servers, nobj, [t["events"] for t in trials])

@@ -23,7 +23,7 @@ from oracle_libs import load_port, load_ref, run_trials
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 BUILTIN = {0: cb.MODEL_MM1, 1: cb.MODEL_GG1, 2: cb.MODEL_MMC, 7: cb.MODEL_HOLD, 10: cb.MODEL_HARBOR, 16: cb.MODEL_RENEGE,
-           18: cb.MODEL_POOL_RECORDED,
+           18: cb.MODEL_POOL_RECORDED, 19: cb.MODEL_TUTORIAL1,
            # the reference's own test worlds: since round 2 they run on the general engine by default
            9: cb.MODEL_MM1_RECORDED, 3: cb.MODEL_GUARDED, 4: cb.MODEL_PREEMPT, 5: cb.MODEL_BUFFER, 6: cb.MODEL_PRIOQ, 8: cb.MODEL_TIMERS,
            11: cb.MODEL_GUARDED_RECORDED, 12: cb.MODEL_BUFFER_RECORDED, 13: cb.MODEL_PRIOQ_RECORDED, 14: cb.MODEL_RESOURCE_RECORDED}
@@ -44,7 +44,7 @@ def compare(case, res, n):
     tt = res.trace_time.cpu().numpy() if res.trace_time is not None else None
     assert (res.status.cpu().numpy()[:n] == 0).all(), res.status.cpu().numpy()[:n]
     for i, want in enumerate(case["trials"][:n]):
-        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18) + COVERAGE else None,
+        check_trial(want, ev[i], ob[i], te[i], sw[i], cnt[i] if case["model"] in (7, 10, 16, 18, 19) + COVERAGE else None,
                     tk[i] if tk is not None else None, tt[i] if tt is not None else None, f"trial {i}",
                     max_queue=int(res.max_queue[i]) if case["model"] in (11, 12, 13, 14) else None)
         if case["model"] in (3, 4, 5, 6, 8):
@@ -54,7 +54,7 @@ def compare(case, res, n):
 @pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in BUILTIN], ids=case_id)
 def test_models_on_the_general_engine_match_the_reference_vectors(case):
     n = len(case["trials"])
-    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18) else 0, n)
+    res = run_case(case, BUILTIN[case["model"]], cb.VARIANT_GENERAL if case["model"] not in (16, 18, 19) else 0, n)
     compare(case, res, n)
 
 
@@ -210,6 +210,35 @@ def test_user_built_static_tier_libraries_match_the_reference():
     exp["arr_mean"], exp["srv_mean"] = float.fromhex(case["arr_mean"]), float.fromhex(case["srv_mean"])
     cb.cimba_run_experiment(exp, model=mm1, num_objects=case["num_objects"], master_seed=MASTER)
     assert [int(v) for v in exp["events"]] == [t["events"] for t in case["trials"]]
+
+
+def test_tutorial_one_as_an_experiment_through_the_host_buffer_entry():
+    """tutorial/tut_1_7.c: 39 utilisations x replications in ONE trial array, cimba_run_experiment over it, each trial's result
+    the time-weighted mean queue length.  Here: the same array through cimba_b200_run_experiment (MODEL_TUTORIAL1, warm-up time in
+    the descriptor's params), every trial's avg_queue_length bit-identical to the unmodified reference running the tutorial's trial."""
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/librefdrv.so did not travel with this snapshot")
+    ref.ref_set_param.argtypes = [C.c_int, C.c_double]
+    rhos = [0.025 * (k + 1) for k in range(39)]
+    reps, warmup, duration = 2, 100.0, 2000
+    dt = np.dtype([("arr_mean", "<f8"), ("srv_mean", "<f8"), ("events", "<u8"), ("t_end", "<f8"), ("status", "<u4"), ("pad", "<u4"),
+                   ("counters", "<u8", (8,))])
+    exp = np.zeros(len(rhos) * reps, dtype=dt)
+    for i in range(len(exp)):
+        exp["arr_mean"][i], exp["srv_mean"][i] = 1.0 / rhos[i // reps], 1.0
+    cb.cimba_run_experiment(exp, model=cb.MODEL_TUTORIAL1, num_objects=duration, master_seed=MASTER, params=[warmup])
+    assert not exp["status"].any()
+    ref.ref_set_param(0, warmup)
+    try:
+        for i in range(len(exp)):
+            w = run_trials(ref, "ref", 19, 1, MASTER, i, 1, duration, float(exp["arr_mean"][i]), 1.0, par=0)[0]
+            assert (int(exp["events"][i]), float(exp["t_end"][i])) == (w.events, w.t_end), i
+            assert [int(v) for v in exp["counters"][i]] == list(w.counter), i
+    finally:
+        ref.ref_set_param(0, 0.0)
+    mean_len = exp["counters"][:, 3].copy().view("<f8")
+    assert mean_len[-1] > mean_len[0]                   # rho 0.975 queues more than rho 0.025
 
 
 def test_unknown_model_ids_and_bad_libraries_are_refused():
