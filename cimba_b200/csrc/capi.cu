@@ -120,8 +120,15 @@ bool fast_goes_general(const cimba_b200_device_job *job)
            job->variant == CIMBA_B200_VARIANT_GENERAL;
 }
 
+// the tutorial's trial runs on the static tier (two processes, a buffer, three events of its own) unless the general engine is asked for
+bool tutorial1_goes_static(const cimba_b200_device_job *job)
+{
+    return job->model == CIMBA_B200_MODEL_TUTORIAL1 && job->variant != CIMBA_B200_VARIANT_GENERAL;
+}
+
 bool goes_static(const cimba_b200_device_job *job)
 {
+    if (tutorial1_goes_static(job)) return true;
     return (job->model == CIMBA_B200_MODEL_MM1 || job->model == CIMBA_B200_MODEL_GG1 || job->model == CIMBA_B200_MODEL_MM1_RECORDED) &&
            job->variant == CIMBA_B200_VARIANT_STATIC;
 }
@@ -404,12 +411,13 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     }
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
     if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
-    if (job->model == CIMBA_B200_MODEL_TUTORIAL1) return cmb::workspace_bytes_for<models::Tutorial1>(*job);
+    if (job->model == CIMBA_B200_MODEL_TUTORIAL1 && !tutorial1_goes_static(job)) return cmb::workspace_bytes_for<models::Tutorial1>(*job);
     if (coverage_goes_general(job)) return for_coverage_model<WorkspaceOf>(job->model, job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
     if (hold_goes_general(job)) return cmb::workspace_bytes_for<models::HoldGeneral>(*job);
     if (harbor_goes_general(job)) return cmb::workspace_bytes_for<models::HarborGeneral>(*job);
     if (goes_static(job)) {
+        if (job->model == CIMBA_B200_MODEL_TUTORIAL1) return cmb::workspace_bytes_static<models::Tutorial1T, 2, 0, 3>(*job);
         return job->model == CIMBA_B200_MODEL_MM1 ? cmb::workspace_bytes_static<models::MM1T, 2, 1>(*job)
              : job->model == CIMBA_B200_MODEL_GG1 ? cmb::workspace_bytes_static<models::GG1T, 2, 1>(*job)
                                                   : cmb::workspace_bytes_static<models::MM1RecordedT, 2, 1>(*job);
@@ -473,7 +481,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the static tier runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
-        const int e = job->model == CIMBA_B200_MODEL_MM1 ? cmb::launch_static_model<models::MM1T, 2, 1>(*job, st)
+        const int e = job->model == CIMBA_B200_MODEL_TUTORIAL1 ? cmb::launch_static_model<models::Tutorial1T, 2, 0, 3>(*job, st)
+                    : job->model == CIMBA_B200_MODEL_MM1 ? cmb::launch_static_model<models::MM1T, 2, 1>(*job, st)
                     : job->model == CIMBA_B200_MODEL_GG1 ? cmb::launch_static_model<models::GG1T, 2, 1>(*job, st)
                                                          : cmb::launch_static_model<models::MM1RecordedT, 2, 1>(*job, st);
         g_launches += job->status != nullptr ? 2 : 1;

@@ -509,6 +509,8 @@ struct condition {
 struct Sim {
     using queue_type = objectqueue;     // what a model template declares its queues as (cmb_static.cuh has another)
     using recorded_queue_type = objectqueue;    // ... a queue whose length history will be switched on
+    using buffer_type = buffer;
+    using recorded_buffer_type = buffer;
     Sfc64          rng;
     const ZigHot  *hot;
     double         now;

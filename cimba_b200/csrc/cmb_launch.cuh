@@ -109,7 +109,7 @@ inline uint64_t static_rings_bytes(const cimba_b200_device_job &job, int nqueue)
     return (b + 255u) & ~(uint64_t)255u;
 }
 
-template <template <class> class ModelT, int NPROC, int NQUEUE>
+template <template <class> class ModelT, int NPROC, int NQUEUE, int NEVENT = 0>
 uint64_t workspace_bytes_static(const cimba_b200_device_job &job)
 {
     // the rings of the static kernel, then the growth arena of its repair pass (a share of the trials, not all of them)
@@ -117,12 +117,12 @@ uint64_t workspace_bytes_static(const cimba_b200_device_job &job)
     return static_rings_bytes(job, NQUEUE) + arena;
 }
 
-template <template <class> class ModelT, int NPROC, int NQUEUE>
+template <template <class> class ModelT, int NPROC, int NQUEUE, int NEVENT = 0>
 int launch_static_model(const cimba_b200_device_job &job, cudaStream_t stream)
 {
     const uint32_t cap = static_spill_cap(job);
     const uint64_t rings = static_rings_bytes(job, NQUEUE);
-    if (cap == 0u || job.workspace == nullptr || job.workspace_bytes < workspace_bytes_static<ModelT, NPROC, NQUEUE>(job))
+    if (cap == 0u || job.workspace == nullptr || job.workspace_bytes < workspace_bytes_static<ModelT, NPROC, NQUEUE, NEVENT>(job))
         return (int)cudaErrorInvalidValue;
     StaticArgs sa{};
     LaunchArgs &a = sa.base;
@@ -151,8 +151,8 @@ int launch_static_model(const cimba_b200_device_job &job, cudaStream_t stream)
     const uint64_t blocks = (job.num_trials + STATIC_BLOCK - 1) / STATIC_BLOCK;
     if (blocks == 0u || blocks > 0x7fffffffull) return (int)cudaErrorInvalidValue;
     const bool trace = job.trace_cap > 0u;
-    const void *fn = trace ? (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, true>
-                           : (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, false>;
+    const void *fn = trace ? (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, NEVENT, true>
+                           : (const void *)static_trial_kernel<ModelT, NPROC, NQUEUE, NEVENT, false>;
     void *kargs[] = { (void *)&sa };
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(STATIC_BLOCK), kargs, 0, stream);
     if (e != cudaSuccess) return (int)e;
@@ -166,16 +166,18 @@ int launch_static_model(const cimba_b200_device_job &job, cudaStream_t stream)
 
 // A model template of the static tier in a library of its own: ModelT<cmb::StaticSim<NPROC, NQUEUE>> runs first, and
 // ModelT<cmb::Sim> re-runs what that flags
-#define CMB_EXPORT_STATIC_MODEL(ModelT, NPROC, NQUEUE, name_string)                                                   \
+#define CMB_EXPORT_STATIC_MODEL(ModelT, NPROC, NQUEUE, name_string) CMB_EXPORT_STATIC_MODEL_EVENTS(ModelT, NPROC, NQUEUE, 0, name_string)
+// ... with NEVENT slots for events of the model's own (cmb_event_schedule), which also makes the event list order by priority
+#define CMB_EXPORT_STATIC_MODEL_EVENTS(ModelT, NPROC, NQUEUE, NEVENT, name_string)                                    \
     extern "C" const char *cimba_b200_user_model_name(void) { return name_string; }                                  \
     extern "C" uint64_t cimba_b200_user_model_workspace_bytes(const cimba_b200_device_job *job)                      \
     {                                                                                                                 \
-        return job ? cimba_b200::cmb::workspace_bytes_static<ModelT, NPROC, NQUEUE>(*job) : 0u;                       \
+        return job ? cimba_b200::cmb::workspace_bytes_static<ModelT, NPROC, NQUEUE, NEVENT>(*job) : 0u;               \
     }                                                                                                                 \
     extern "C" int cimba_b200_user_model_launch(const cimba_b200_device_job *job, void *stream)                      \
     {                                                                                                                 \
         if (job == nullptr || job->workspace == nullptr) return (int)cudaErrorInvalidValue;                          \
-        return cimba_b200::cmb::launch_static_model<ModelT, NPROC, NQUEUE>(*job, (cudaStream_t)stream);               \
+        return cimba_b200::cmb::launch_static_model<ModelT, NPROC, NQUEUE, NEVENT>(*job, (cudaStream_t)stream);       \
     }
 
 // A model in a library of its own: the three C entry points cimba_b200_model_load() looks up.

@@ -3,7 +3,7 @@
 // The general engine (cmb_device.cuh) runs ANY model, and pays for it: every container is in memory and grows.  Many models
 // need none of that: a FIXED set of processes that only hold and wait at queues - the benchmark's M/M/1
 // (benchmark/MM1_multi.c:52-125), G/G/1, a tandem line.  For those, the same model text - the same CMB_PROCESS_* /
-// CMB_OBJECTQUEUE_* macros, the same cmb_* names - compiles against cmb::StaticSim<NPROC, NQUEUE> instead of cmb::Sim:
+// CMB_OBJECTQUEUE_* macros, the same cmb_* names - compiles against cmb::StaticSim<NPROC, NQUEUE, NEVENT> instead of cmb::Sim:
 //   * the event list is one slot per process in registers (SlotFel, engine.cuh): a process that can only hold or wait owns at
 //     most one pending event, so an insert is a register write and pop-min an NPROC-way compare;
 //   * process records, guards (a bit and a sequence number per process) and the model struct stay in registers: process ids
@@ -32,10 +32,11 @@ constexpr int STATIC_BLOCK = 64;
 // One event slot per process (the shape of SlotFel, engine.cuh), the action packed into the key's two low bits as mm1_fast.cuh
 // does: key = (issue counter << 2) | action, 0 = empty.  Counters are unique, so ordering by this word is ordering by issue
 // counter - the reference's tie-break (src/cmi_hashheap.c:55-80).
-template <int N>
+template <int N, bool PRIO = false>
 struct StaticFel {
     double   t[N];
     uint32_t key[N];
+    int32_t  prio[N];           // PRIO only (a model with events of its own): higher goes first at equal times
     uint32_t issued;
 
     CMB_FN void clear()
@@ -44,11 +45,12 @@ struct StaticFel {
         for (int i = 0; i < N; i++) {
             t[i] = __longlong_as_double(0x7ff0000000000000LL);
             key[i] = 0u;
+            prio[i] = 0;
         }
         issued = 0u;
     }
 
-    CMB_FN bool schedule(int p, uint32_t action, double time)      // false: the process already had a pending event
+    CMB_FN bool schedule(int p, uint32_t action, double time, int32_t priority = 0)     // false: slot p already had a pending event
     {
         const uint32_t k = (++issued << 2) | action;
         bool ok = true;
@@ -58,6 +60,7 @@ struct StaticFel {
                 ok = key[i] == 0u;
                 t[i] = time;
                 key[i] = k;
+                if (PRIO) prio[i] = priority;
             }
         }
         return ok;
@@ -74,19 +77,28 @@ struct StaticFel {
         }
     }
 
-    // cmi_hashheap_dequeue: the first entry under (time asc, key asc); false when the list is empty
+    // cmi_hashheap_dequeue: the first entry under (time asc, priority desc, key asc) - default_compare, src/cmi_hashheap.c:55-80;
+    // false when the list is empty
     CMB_FN bool pop(int &p, uint32_t &action, double &time, uint32_t &counter)
     {
         int best = 0;
         double bt = t[0];
         uint32_t bk = key[0];
+        int32_t bp = PRIO ? prio[0] : 0;
 #pragma unroll
         for (int i = 1; i < N; i++) {
-            const bool before = (t[i] < bt) | ((t[i] == bt) & (key[i] < bk));
+            bool before;
+            if (PRIO) {
+                before = (t[i] < bt) | ((t[i] == bt) & ((prio[i] > bp) | ((prio[i] == bp) & (key[i] < bk))));
+            }
+            else {
+                before = (t[i] < bt) | ((t[i] == bt) & (key[i] < bk));
+            }
             if (before) {
                 best = i;
                 bt = t[i];
                 bk = key[i];
+                if (PRIO) bp = prio[i];
             }
         }
         drop(best);
@@ -126,15 +138,33 @@ struct static_objectqueue : static_history<RECORD> {
     uint32_t length;            // = ring.len (cmb_objectqueue_length)
 };
 
-template <int NPROC, int NQUEUE>
+// struct cmb_buffer for a fixed set of processes (amounts put and got in parts, src/cmb_buffer.c:194-346)
+template <int NPROC, bool RECORD = false>
+struct static_buffer : static_history<RECORD> {
+    static_guard<NPROC> front, rear;
+    uint64_t level, capacity;
+};
+
+// NEVENT: how many events of its own (cmb_event_schedule) a model may have pending at once; with any, the event list also
+// orders by priority
+template <int NPROC, int NQUEUE, int NEVENT = 0>
 struct StaticSim {
     using queue_type = static_objectqueue<NPROC, false>;
     using recorded_queue_type = static_objectqueue<NPROC, true>;
+    using buffer_type = static_buffer<NPROC, false>;
+    using recorded_buffer_type = static_buffer<NPROC, true>;
+    static constexpr int PROCESSES = NPROC;
+    static constexpr int SLOTS = NPROC + NEVENT;
     struct Proc {
         uint32_t pc, status, kind, ctx;
         double   f[2];
         uint64_t u[2];
+        uint64_t fr[3];         // scratch of the blocking calls in progress (a buffer call's remaining / obtained amounts)
         int64_t  exit_value;
+    };
+    struct UserEvent {
+        uint32_t act, subj;
+        int64_t  arg;
     };
     Sfc64          rng;
     const ZigHot  *hot;
@@ -145,7 +175,8 @@ struct StaticSim {
     uint32_t       pops;
     uint32_t       nproc, nqueue, guard_seq;
     Proc           proc[NPROC];
-    StaticFel<NPROC> fel;
+    StaticFel<NPROC + NEVENT, (NEVENT > 0)> fel;
+    UserEvent      uev[NEVENT > 0 ? NEVENT : 1];
     uint32_t       cmd;
     uint32_t       cmd_sample;
     double         cmd_value;
@@ -186,8 +217,34 @@ struct StaticSim {
             proc[i].ctx = 0u;
             proc[i].f[0] = proc[i].f[1] = 0.0;
             proc[i].u[0] = proc[i].u[1] = 0u;
+            proc[i].fr[0] = proc[i].fr[1] = proc[i].fr[2] = 0u;
             proc[i].exit_value = 0;
         }
+    }
+
+    // cmb_event_schedule(action, subject, object, time, priority) for an event of the model's own (src/cmb_event.c:123-140):
+    // one of the NEVENT spare slots.  Returns the handle (= key), 0 if there is no slot left (the trial is flagged).
+    CMB_FN uint64_t schedule(uint32_t act, uint32_t subj, int64_t arg, double t, int64_t prio)
+    {
+        int slot = -1;
+#pragma unroll
+        for (int i = NPROC; i < NPROC + NEVENT; i++) {
+            if (slot < 0 && fel.key[i] == 0u) slot = i;
+        }
+        if (slot < 0) {
+            status |= TRIAL_ERR_FEL_OVERFLOW;
+            return 0u;
+        }
+        (void)fel.schedule(slot, 0u, t, (int32_t)prio);
+#pragma unroll
+        for (int i = 0; i < NEVENT; i++) {
+            if (i == slot - NPROC) {
+                uev[i].act = act;
+                uev[i].subj = subj;
+                uev[i].arg = arg;
+            }
+        }
+        return (uint64_t)fel.issued;
     }
 
     // cmb_process_create + cmb_process_initialize.  One process more than the tier holds, or a priority: the trial goes
@@ -255,8 +312,8 @@ struct StaticSim {
 // whole control block in local memory)
 // In a sampler the dispatcher is trying out (hot_only), a draw that leaves its ziggurat's rectangles gives up - the dispatcher
 // rewinds the generator and repeats the whole sampler later, slow paths allowed, together with other lanes in the same position.
-template <int NPROC, int NQUEUE>
-CMB_FN double draw_exponential(StaticSim<NPROC, NQUEUE> &sim, double mean)        // include/cmb_random.h:319-352
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN double draw_exponential(StaticSim<NPROC, NQUEUE, NEVENT> &sim, double mean)        // include/cmb_random.h:319-352
 {
     if (sim.hot_failed) return mean;
     const uint64_t u = sim.rng.next();
@@ -268,8 +325,8 @@ CMB_FN double draw_exponential(StaticSim<NPROC, NQUEUE> &sim, double mean)      
     return __dmul_rn(mean, sim.rng.exp_cold(u));
 }
 
-template <int NPROC, int NQUEUE>
-CMB_FN double draw_std_normal(StaticSim<NPROC, NQUEUE> &sim)                       // include/cmb_random.h:206-215
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN double draw_std_normal(StaticSim<NPROC, NQUEUE, NEVENT> &sim)                       // include/cmb_random.h:206-215
 {
     if (sim.hot_failed) return 1.0;
     const int64_t ix = (int64_t)sim.rng.next();
@@ -283,8 +340,8 @@ CMB_FN double draw_std_normal(StaticSim<NPROC, NQUEUE> &sim)                    
 }
 
 // ------------------------------------------------------------------------------------------------ objectqueue
-template <int NPROC, int NQUEUE, bool RECORD>
-CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, RECORD> &q, uint64_t capacity)
+template <int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_objectqueue<NPROC, RECORD> &q, uint64_t capacity)
 {
     uint32_t k = sim.nqueue;
     if (k >= (uint32_t)NQUEUE) {
@@ -303,23 +360,23 @@ CMB_FN void objectqueue_initialize(StaticSim<NPROC, NQUEUE> &sim, static_objectq
     if constexpr (RECORD) q.recording = 0u;
 }
 
-template <int NPROC, int NQUEUE>
-CMB_FN void objectqueue_recording_start(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, true> &q)
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void objectqueue_recording_start(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_objectqueue<NPROC, true> &q)
 {
     q.recording = 1u;
     q.history.start();
     q.history.sample((double)q.ring.len, sim.now);
 }
 
-template <int NPROC, int NQUEUE>
-CMB_FN void objectqueue_recording_stop(StaticSim<NPROC, NQUEUE> &sim, static_objectqueue<NPROC, true> &q)
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void objectqueue_recording_stop(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_objectqueue<NPROC, true> &q)
 {
     if (q.recording) q.history.sample((double)q.ring.len, sim.now);
     q.recording = 0u;
 }
 
-template <class Model, int NPROC, int NQUEUE, bool RECORD>
-CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t obj)
+template <class Model, int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t obj)
 {
     if ((uint64_t)q.ring.len >= q.capacity) return false;
     if (!q.ring.put(__longlong_as_double((long long)obj))) sim.status |= TRIAL_ERR_QUEUE_OVERFLOW;     // void from here on: re-run
@@ -332,8 +389,8 @@ CMB_FN bool objectqueue_try_put(StaticSim<NPROC, NQUEUE> &sim, Model &, static_o
     return true;
 }
 
-template <class Model, int NPROC, int NQUEUE, bool RECORD>
-CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t &obj)
+template <class Model, int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &, static_objectqueue<NPROC, RECORD> &q, uint64_t &obj)
 {
     if (q.ring.len == 0u) return false;
     obj = (uint64_t)__double_as_longlong(q.ring.take());
@@ -345,10 +402,123 @@ CMB_FN bool objectqueue_try_get(StaticSim<NPROC, NQUEUE> &sim, Model &, static_o
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ buffer
+template <int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN void buffer_initialize(StaticSim<NPROC, NQUEUE, NEVENT> &, static_buffer<NPROC, RECORD> &b, uint64_t capacity)
+{
+    b.front.waiting = b.rear.waiting = 0u;
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) b.front.seq[i] = b.rear.seq[i] = 0u;
+    b.level = 0u;
+    b.capacity = capacity;
+    if constexpr (RECORD) b.recording = 0u;
+}
+
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void buffer_recording_start(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_buffer<NPROC, true> &b)
+{
+    b.recording = 1u;
+    b.history.start();
+    b.history.sample((double)b.level, sim.now);
+}
+
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void buffer_recording_stop(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_buffer<NPROC, true> &b)
+{
+    if (b.recording) b.history.sample((double)b.level, sim.now);
+    b.recording = 0u;
+}
+
+template <int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN void buffer_sample(StaticSim<NPROC, NQUEUE, NEVENT> &sim, static_buffer<NPROC, RECORD> &b)
+{
+    if constexpr (RECORD) {
+        if (b.recording) b.history.sample((double)b.level, sim.now);
+    }
+}
+
+// cmb_buffer_get / cmb_buffer_put up to their waits, as cmb_device.cuh's buffer_get_step / buffer_put_step (src/cmb_buffer.c:194-346)
+template <class Model, int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN bool buffer_get_step(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &, static_buffer<NPROC, RECORD> &b, uint32_t pid)
+{
+    uint64_t rem = 0u, got = 0u;
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if ((uint32_t)i == pid) {
+            rem = sim.proc[i].fr[1];
+            got = sim.proc[i].fr[2];
+        }
+    }
+    bool done;
+    if (b.level >= rem) {
+        b.level -= rem;
+        buffer_sample(sim, b);
+        got += rem;
+        sim.guard_signal(b.rear, b.level < b.capacity);
+        if (b.level > 0u) sim.guard_signal(b.front, true);
+        done = true;
+    }
+    else {
+        if (b.level > 0u) {
+            const uint64_t grab = b.level;
+            b.level = 0u;
+            buffer_sample(sim, b);
+            got += grab;
+            rem -= grab;
+            sim.guard_signal(b.rear, b.level < b.capacity);
+        }
+        sim.guard_signal(b.rear, b.level < b.capacity);
+        done = false;
+    }
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if ((uint32_t)i == pid) {
+            sim.proc[i].fr[1] = rem;
+            sim.proc[i].fr[2] = got;
+        }
+    }
+    return done;
+}
+
+template <class Model, int NPROC, int NQUEUE, int NEVENT, bool RECORD>
+CMB_FN bool buffer_put_step(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &, static_buffer<NPROC, RECORD> &b, uint32_t pid)
+{
+    uint64_t rem = 0u;
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if ((uint32_t)i == pid) rem = sim.proc[i].fr[1];
+    }
+    bool done;
+    if (b.capacity - b.level >= rem) {
+        b.level += rem;
+        buffer_sample(sim, b);
+        rem = 0u;
+        sim.guard_signal(b.front, b.level > 0u);
+        if (b.level < b.capacity) sim.guard_signal(b.rear, true);
+        done = true;
+    }
+    else {
+        if (b.level < b.capacity) {
+            const uint64_t grab = b.capacity - b.level;
+            b.level = b.capacity;
+            buffer_sample(sim, b);
+            rem -= grab;
+            sim.guard_signal(b.front, b.level > 0u);
+        }
+        sim.guard_signal(b.front, b.level > 0u);
+        done = false;
+    }
+#pragma unroll
+    for (int i = 0; i < NPROC; i++) {
+        if ((uint32_t)i == pid) sim.proc[i].fr[1] = rem;
+    }
+    return done;
+}
+
 // cmb_process_stop (src/cmb_process.c:698-723) as far as this tier can need it: the process's pending event goes, it is
 // FINISHED; an entry it may have in a guard stays and will swallow one signal
-template <class Model, int NPROC, int NQUEUE>
-CMB_FN void process_stop(StaticSim<NPROC, NQUEUE> &sim, Model &, uint32_t pid, int64_t value)
+template <class Model, int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void process_stop(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &, uint32_t pid, int64_t value)
 {
 #pragma unroll
     for (int i = 0; i < NPROC; i++) {
@@ -369,24 +539,24 @@ struct StaticKinds {
     static constexpr bool known = false;
     template <int I>
     static CMB_FN uint32_t of(uint32_t runtime_kind) { return runtime_kind; }
-    template <int NPROC, int NQUEUE>
-    static CMB_FN bool agree(const StaticSim<NPROC, NQUEUE> &) { return true; }
+    template <class S>
+    static CMB_FN bool agree(const S &) { return true; }
 };
 template <class Model>
 struct StaticKinds<Model, decltype((void)Model::static_kind(0u))> {
     static constexpr bool known = true;
     template <int I>
     static CMB_FN uint32_t of(uint32_t) { return Model::static_kind((uint32_t)I); }
-    template <int NPROC, int NQUEUE>
-    static CMB_FN bool agree(const StaticSim<NPROC, NQUEUE> &sim)
+    template <class S>
+    static CMB_FN bool agree(const S &sim)
     {
-        return agree_from<NPROC, NQUEUE, 0>(sim);
+        return agree_from<S, 0>(sim);
     }
-    template <int NPROC, int NQUEUE, int I>
-    static CMB_FN bool agree_from(const StaticSim<NPROC, NQUEUE> &sim)
+    template <class S, int I>
+    static CMB_FN bool agree_from(const S &sim)
     {
-        if constexpr (I < NPROC) {
-            return ((uint32_t)I >= sim.nproc || sim.proc[I].kind == Model::static_kind((uint32_t)I)) && agree_from<NPROC, NQUEUE, I + 1>(sim);
+        if constexpr (I < S::PROCESSES) {
+            return ((uint32_t)I >= sim.nproc || sim.proc[I].kind == Model::static_kind((uint32_t)I)) && agree_from<S, I + 1>(sim);
         }
         else {
             return true;
@@ -394,23 +564,23 @@ struct StaticKinds<Model, decltype((void)Model::static_kind(0u))> {
     }
 };
 
-template <class Model, int NPROC, int NQUEUE, int I>
+template <class Model, int NPROC, int NQUEUE, int NEVENT, int I>
 struct StaticDispatch {
-    static CMB_FN void run(StaticSim<NPROC, NQUEUE> &sim, Model &m, int who)
+    static CMB_FN void run(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &m, int who)
     {
         if (who == I) m.process(sim, (uint32_t)I, StaticKinds<Model>::template of<I>(sim.proc[I].kind), CMB_PROCESS_SUCCESS);
-        else StaticDispatch<Model, NPROC, NQUEUE, I + 1>::run(sim, m, who);
+        else StaticDispatch<Model, NPROC, NQUEUE, NEVENT, I + 1>::run(sim, m, who);
     }
 };
-template <class Model, int NPROC, int NQUEUE>
-struct StaticDispatch<Model, NPROC, NQUEUE, NPROC> {
-    static CMB_FN void run(StaticSim<NPROC, NQUEUE> &, Model &, int) {}
+template <class Model, int NPROC, int NQUEUE, int NEVENT>
+struct StaticDispatch<Model, NPROC, NQUEUE, NEVENT, NPROC> {
+    static CMB_FN void run(StaticSim<NPROC, NQUEUE, NEVENT> &, Model &, int) {}
 };
 
 // one step of cmb_event_queue_execute (src/cmb_event.c:229-252): pop, advance the clock, resume the process.  false = the
 // list ran dry.  The body's blocking call is left in sim.cmd for the caller (`who` = the process it belongs to).
-template <class Model, int NPROC, int NQUEUE>
-CMB_FN bool static_step(StaticSim<NPROC, NQUEUE> &sim, Model &m, int &who)
+template <class Model, int NPROC, int NQUEUE, int NEVENT>
+CMB_FN bool static_step(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &m, int &who)
 {
     uint32_t act, key;
     double when;
@@ -419,6 +589,13 @@ CMB_FN bool static_step(StaticSim<NPROC, NQUEUE> &sim, Model &m, int &who)
     sim.current_event = key;
     sim.pops++;
     sim.cmd = CMD_NONE;
+    if (NEVENT > 0 && who >= NPROC) {                   // an event of the model's own: its action function, no process resumed
+#pragma unroll
+        for (int i = 0; i < NEVENT; i++) {
+            if (i == who - NPROC) m.event(sim, sim.uev[i].act, sim.uev[i].subj, sim.uev[i].arg);
+        }
+        return true;
+    }
     bool run = true;
 #pragma unroll
     for (int i = 0; i < NPROC; i++) {
@@ -432,15 +609,15 @@ CMB_FN bool static_step(StaticSim<NPROC, NQUEUE> &sim, Model &m, int &who)
     }
     if (run) {
         sim.current = (uint32_t)who;
-        StaticDispatch<Model, NPROC, NQUEUE, 0>::run(sim, m, who);
+        StaticDispatch<Model, NPROC, NQUEUE, NEVENT, 0>::run(sim, m, who);
         sim.current = NIL;
     }
     return true;
 }
 
 // the blocking call the body ended on, except the exponential hold (whose draw the callers batch): true = handled
-template <int NPROC, int NQUEUE>
-CMB_FN void static_finish_command(StaticSim<NPROC, NQUEUE> &sim, int who, uint32_t cmd)
+template <int NPROC, int NQUEUE, int NEVENT>
+CMB_FN void static_finish_command(StaticSim<NPROC, NQUEUE, NEVENT> &sim, int who, uint32_t cmd)
 {
     if (cmd == CMD_HOLD) {
         if (sim.cmd_value < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
@@ -459,8 +636,8 @@ CMB_FN void static_finish_command(StaticSim<NPROC, NQUEUE> &sim, int who, uint32
 
 #ifdef CMB_HOST_BUILD
 // the tier's source text run on the CPU (tests/cmb_engine_host.cpp): one trial, the slow path taken where it occurs
-template <class Model, int NPROC, int NQUEUE>
-inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const TrialIn &in, TrialOut &out,
+template <class Model, int NPROC, int NQUEUE, int NEVENT>
+inline void static_run_trial_host(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &m, const TrialIn &in, TrialOut &out,
                                   uint64_t trace_cap, uint64_t *trace_key, double *trace_time)
 {
     out.objects = 0u;
@@ -486,12 +663,12 @@ inline void static_run_trial_host(StaticSim<NPROC, NQUEUE> &sim, Model &m, const
             const Sfc64 saved = sim.rng;
             sim.hot_only = true;
             sim.hot_failed = false;
-            double dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE>>::draw(m, sim, sim.cmd_sample);
+            double dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE, NEVENT>>::draw(m, sim, sim.cmd_sample);
             sim.hot_only = false;
             if (sim.hot_failed) {
                 sim.hot_failed = false;
                 sim.rng = saved;
-                dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE>>::draw(m, sim, sim.cmd_sample);
+                dur = ModelSampler<Model, StaticSim<NPROC, NQUEUE, NEVENT>>::draw(m, sim, sim.cmd_sample);
             }
             if (dur < 0.0) sim.status |= TRIAL_ERR_NEGATIVE_HOLD;
             if (!sim.fel.schedule(who, ACT_WAKE_TIME, __dadd_rn(sim.now, dur))) sim.status |= TRIAL_ERR_FEL_OVERFLOW;
@@ -531,13 +708,13 @@ struct StaticArgs {
     uint32_t   spill_cap;
 };
 
-template <template <class> class ModelT, int NPROC, int NQUEUE, bool TRACE>
+template <template <class> class ModelT, int NPROC, int NQUEUE, int NEVENT, bool TRACE>
 __global__ void __launch_bounds__(STATIC_BLOCK)
 static_trial_kernel(const StaticArgs sa)
 {
-    using S = StaticSim<NPROC, NQUEUE>;
+    using S = StaticSim<NPROC, NQUEUE, NEVENT>;
     __shared__ ZigHot hot;
-    __shared__ double ring_smem[NQUEUE * STATIC_WINDOW * STATIC_BLOCK];
+    __shared__ double ring_smem[(NQUEUE > 0 ? NQUEUE : 1) * STATIC_WINDOW * STATIC_BLOCK];
     const LaunchArgs &a = sa.base;
     stage_zig_hot(hot, true);
     __syncthreads();

@@ -5,23 +5,29 @@
 // level (its avg_queue_length); here the whole cmb_wtdsummary goes to counters[0..7].
 //   arr_mean / srv_mean = 1 / arr_rate, 1 / srv_rate; num_objects = duration; params[0] = warm-up time.
 // Oracle: oracle/ref_build/ref_driver.c model 19 (the same trial against the reference's API).
+// A template over the engine: cmb::Sim (general), or cmb::StaticSim<2, 0, 3> - the static tier with a cmb_buffer, three slots for
+// the model's own events and the event list ordered by priority as well.
 #pragma once
 #include "../csrc/cmb_kernel.cuh"
+#include "../csrc/cmb_static.cuh"
 
 namespace cimba_b200 {
 namespace models {
 
-struct Tutorial1 {
-    cmb::buffer que;                                    // struct simulation, tut_1_7.c:36-41
+template <class S>
+struct Tutorial1T {
+    typename S::recorded_buffer_type que;                                    // struct simulation, tut_1_7.c:36-41
     uint32_t arr, srv;
     double   t_ia_mean, t_srv_mean;                     // 1 / arr_rate, 1 / srv_rate (:117, :141)
     uint64_t n, units_put, units_got;
     enum : uint32_t { ARRIVAL, SERVICE };
     enum : uint32_t { START_REC = cmb::ACT_CMB_USER, STOP_REC, END_SIM };
+    static constexpr bool exponential_holds_only = true;
+    static CMB_FN constexpr uint32_t static_kind(uint32_t i) { return i == 0u ? ARRIVAL : SERVICE; }
 
-    CMB_FN void arrival(cmb::Sim &sim, uint32_t me, int64_t sig)               // :107-128
+    CMB_FN void arrival(S &sim, uint32_t me, int64_t sig)               // :107-128
     {
-        Tutorial1 &m = *this;
+        Tutorial1T &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
             CMB_PROCESS_HOLD_EXPONENTIAL(t_ia_mean);
@@ -32,9 +38,9 @@ struct Tutorial1 {
         CMB_PROCESS_END
     }
 
-    CMB_FN void service(cmb::Sim &sim, uint32_t me, int64_t sig)               // :133-151
+    CMB_FN void service(S &sim, uint32_t me, int64_t sig)               // :133-151
     {
-        Tutorial1 &m = *this;
+        Tutorial1T &m = *this;
         CMB_PROCESS_BEGIN
         for (;;) {
             n = 1u;
@@ -45,7 +51,7 @@ struct Tutorial1 {
         CMB_PROCESS_END
     }
 
-    CMB_FN void run_trial(cmb::Sim &sim, const cmb::TrialIn &in)               // :155-200
+    CMB_FN void run_trial(S &sim, const cmb::TrialIn &in)               // :155-200
     {
         t_ia_mean = in.arr_mean;
         t_srv_mean = in.srv_mean;
@@ -62,15 +68,15 @@ struct Tutorial1 {
         (void)cmb_event_schedule(END_SIM, cmb::NIL, 0, t, -100);               // after everything else at that time
     }
 
-    CMB_FN void process(cmb::Sim &sim, uint32_t me, uint32_t kind, int64_t sig)
+    CMB_FN void process(S &sim, uint32_t me, uint32_t kind, int64_t sig)
     {
         if (kind == ARRIVAL) arrival(sim, me, sig);
         else service(sim, me, sig);
     }
 
-    CMB_FN void event(cmb::Sim &sim, uint32_t action, uint32_t, int64_t)       // start_rec, stop_rec, end_sim, :69-101
+    CMB_FN void event(S &sim, uint32_t action, uint32_t, int64_t)       // start_rec, stop_rec, end_sim, :69-101
     {
-        Tutorial1 &m = *this;
+        Tutorial1T &m = *this;
         if (action == START_REC) {
             cmb_buffer_recording_start(que);
         }
@@ -82,9 +88,9 @@ struct Tutorial1 {
             cmb_process_stop(srv, 0);
         }
     }
-    CMB_FN bool demand(cmb::Sim &, uint32_t, uint32_t, int32_t) { return false; }
+    CMB_FN bool demand(S &, uint32_t, uint32_t, int32_t) { return false; }
 
-    CMB_FN void finish(cmb::Sim &, cmb::TrialOut &out)                          // :205-209: cmb_timeseries_summarize of the history
+    CMB_FN void finish(S &, cmb::TrialOut &out)                          // :205-209: cmb_timeseries_summarize of the history
     {
         const WtdAcc &h = que.history.acc;
         out.counters[0] = h.count;
@@ -99,6 +105,8 @@ struct Tutorial1 {
         out.sum_wait = (double)units_got;
     }
 };
+
+using Tutorial1 = Tutorial1T<cmb::Sim>;      // on the static tier: Tutorial1T<cmb::StaticSim<2, 0, 3>> (two processes, no object queue, three events)
 
 }  // namespace models
 }  // namespace cimba_b200

@@ -128,7 +128,8 @@ extern "C" {
 #define CIMBA_B200_MODEL_TUTORIAL1 19    /* cimba_b200/models/tutorial1_model.cuh = the trial of tutorial/tut_1_7.c (run_MM1_trial :155-222): M/M/1 in a
                                           * cmb_buffer, level history on from params[0] (warm-up time) for num_objects time units, end event of
                                           * priority -100; arr_mean / srv_mean = 1 / arr_rate, 1 / srv_rate; counters[0..7] = the history's
-                                          * cmb_wtdsummary (counters[3] = the tutorial's avg_queue_length, as a double's bits).  General engine. */
+                                          * cmb_wtdsummary (counters[3] = the tutorial's avg_queue_length, as a double's bits).  Runs on the static tier
+                                          * (cmb_static.cuh: two processes, a buffer, three events of its own); CIMBA_B200_VARIANT_GENERAL = general engine. */
 
 /* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
  * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */

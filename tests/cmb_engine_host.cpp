@@ -85,15 +85,15 @@ static void run_model(uint64_t seed, const cmb::TrialIn &in, cmb::Arena &arena, 
 }
 
 // the static tier (csrc/cmb_static.cuh): the same model template on cmb::StaticSim; spill_cap entries of HBM-ring stand-in per queue
-template <template <class> class ModelT, int NPROC, int NQUEUE>
+template <template <class> class ModelT, int NPROC, int NQUEUE, int NEVENT = 0>
 static void run_static(uint64_t seed, const cmb::TrialIn &in, const ZigHot &hot, HostResult &r, uint32_t spill_cap,
                        uint64_t trace_cap, uint64_t *trace_key, double *trace_time)
 {
-    using S = cmb::StaticSim<NPROC, NQUEUE>;
+    using S = cmb::StaticSim<NPROC, NQUEUE, NEVENT>;
     S sim;
     ModelT<S> m;
     cmb::TrialOut out;
-    std::vector<double> win((size_t)NQUEUE * cmb::STATIC_WINDOW), ring((size_t)NQUEUE * (spill_cap ? spill_cap : 1u));
+    std::vector<double> win((size_t)(NQUEUE + 1) * cmb::STATIC_WINDOW), ring((size_t)(NQUEUE + 1) * (spill_cap ? spill_cap : 1u));
     sim.init(seed, &hot, win.data(), 1u, ring.data(), spill_cap);
     cmb::static_run_trial_host(sim, m, in, out, trace_cap, trace_key, trace_time);
     r.events = sim.pops;
@@ -138,6 +138,7 @@ extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed,
         case 0:  run_model<models::MM1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 19: run_model<models::Tutorial1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 9:  run_model<models::MM1Recorded>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 119: run_static<models::Tutorial1T, 2, 0, 3>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
         case 109: run_static<models::MM1RecordedT, 2, 1>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
         case 100: run_static<models::MM1T, 2, 1>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;
         case 101: run_static<models::GG1T, 2, 1>(seed, in, hot, out[i], (uint32_t)arena_bytes, trace_cap, tk, tt); break;

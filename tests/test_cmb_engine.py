@@ -159,7 +159,7 @@ def test_engine_reproduces_the_reference_resource_golden_file(host):
     assert "%.4f" % _double(c[3]) == "0.9816" and "%.4f" % _double(c[4]) == "6.3280" and c[5] == 3 and c[1] == 1
 
 
-@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 9, 17)], ids=case_id)
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] in (0, 1, 9, 17, 19)], ids=case_id)
 def test_static_tier_source_on_the_cpu_matches_the_reference_vectors(host, case):
     """csrc/cmb_static.cuh: the same model templates (mm1_model.cuh, gg1_model.cuh, examples/tandem_model.cuh) compiled against
     cmb::StaticSim - one event slot per process, guards as a bit per process, queues as rings - on the CPU.  With a ring of 512
@@ -175,5 +175,5 @@ def test_static_tier_source_on_the_cpu_matches_the_reference_vectors(host, case)
                 continue
             assert out[i].status == 0
             check_trial(want, out[i].events, out[i].objects, out[i].t_end, out[i].sum_wait,
-                        list(out[i].counter) if case["model"] == 9 else None,       # the queue history's eight summary words
+                        list(out[i].counter) if case["model"] in (9, 19) else None,    # the history's eight summary words
                         keys[i * TRACE:(i + 1) * TRACE], times[i * TRACE:(i + 1) * TRACE], f"trial {i}")
