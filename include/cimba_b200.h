@@ -130,6 +130,12 @@ extern "C" {
                                           * priority -100; arr_mean / srv_mean = 1 / arr_rate, 1 / srv_rate; counters[0..7] = the history's
                                           * cmb_wtdsummary (counters[3] = the tutorial's avg_queue_length, as a double's bits).  Runs on the static tier
                                           * (cmb_static.cuh: two processes, a buffer, three events of its own); CIMBA_B200_VARIANT_GENERAL = general engine. */
+#define CIMBA_B200_MODEL_PARK 20         /* cimba_b200/models/park_model.cuh = the reference's third tutorial, tutorial/tut_3_1.c: a theme park of nine
+                                          * attractions (11 cmb_priorityqueues, 14 batch servers), visitors as processes that balk, jockey and
+                                          * renege on patience timers, gold-card priorities, Vose alias routing, PERT rides; 16 simulated hours.
+                                          * No parameters (the park is the tutorial's hard-coded one).  counters[0..4] = the tutorial's five
+                                          * results - mean time in park, riding, waiting, walking, mean number of rides - as doubles' bits,
+                                          * [5] = visitors departed; objects = visitors created.  General engine. */
 
 /* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
  * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */

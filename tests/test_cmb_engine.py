@@ -177,3 +177,18 @@ def test_static_tier_source_on_the_cpu_matches_the_reference_vectors(host, case)
             check_trial(want, out[i].events, out[i].objects, out[i].t_end, out[i].sum_wait,
                         list(out[i].counter) if case["model"] in (9, 19) else None,    # the history's eight summary words
                         keys[i * TRACE:(i + 1) * TRACE], times[i * TRACE:(i + 1) * TRACE], f"trial {i}")
+
+
+def test_theme_park_tutorial_on_the_engine_matches_the_unmodified_tutorial_source(host):
+    """tutorial/tut_3_1.c (nine attractions, priority queues, batch servers, visitors that balk, jockey and renege on timers) written
+    against the authoring surface (cimba_b200/models/park_model.cuh): events executed, final clock and the tutorial's five averages
+    of 64 trials, bit for bit, against vectors the UNMODIFIED tutorial source produced (tests/golden/make_park_golden.py)."""
+    import json
+    import struct
+    gold = json.loads((ROOT / "tests/golden/park_vectors.json").read_text())
+    n = len(gold["trials"])
+    case = {"model": 20, "servers": 1, "num_objects": 0, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, n, master=gold["master"])
+    for i, want in enumerate(gold["trials"]):
+        d = [struct.unpack("<d", struct.pack("<Q", v))[0].hex() for v in list(out[i].counter)[:5]]
+        assert out[i].status == 0 and (out[i].events, float(out[i].t_end).hex(), d) == (want["events"], want["t_end"], want["means"]), i

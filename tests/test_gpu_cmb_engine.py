@@ -241,6 +241,38 @@ def test_tutorial_one_as_an_experiment_through_the_host_buffer_entry():
     assert mean_len[-1] > mean_len[0]                   # rho 0.975 queues more than rho 0.025
 
 
+def test_theme_park_tutorial_on_device_matches_the_unmodified_tutorial_source():
+    """MODEL_PARK = tutorial/tut_3_1.c on the general engine: 64 trials against the vectors of the unmodified tutorial source
+    (tests/golden/park_vectors.json), and 300 more against the tutorial itself where its build travelled with the snapshot."""
+    import json
+    gold = json.loads((ROOT / "tests/golden/park_vectors.json").read_text())
+    n = len(gold["trials"])
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=0, master_seed=gold["master"], model=cb.MODEL_PARK)
+    assert res.status.abs().sum().item() == 0
+    ev, te, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.counters.cpu().numpy()
+    for i, want in enumerate(gold["trials"]):
+        means = [float(v).hex() for v in cnt[i][:5].copy().view("<f8")]
+        assert (ev[i], float(te[i]).hex(), means) == (want["events"], want["t_end"], want["means"]), i
+    so = ROOT / "oracle/_ref/libtut3_ref.so"
+    ref = load_ref()
+    if ref is None or not so.exists():
+        return
+
+    class Tut3Out(C.Structure):
+        _fields_ = [("events", C.c_uint64), ("t_end", C.c_double), ("park", C.c_double), ("riding", C.c_double),
+                    ("waiting", C.c_double), ("walking", C.c_double), ("rides", C.c_double)]
+    lib = C.CDLL(str(so))
+    lib.tut3_ref_trial.argtypes = [C.c_uint64, C.POINTER(Tut3Out)]
+    first, more = 1000, 300
+    res = cb.run_trials(more, arr_mean=1.0, srv_mean=1.0, num_objects=0, master_seed=MASTER, first_trial=first, model=cb.MODEL_PARK)
+    ev, te, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.counters.cpu().numpy()
+    for i in range(more):
+        o = Tut3Out()
+        assert lib.tut3_ref_trial(ref.ref_fmix64(MASTER, first + i), C.byref(o)) == 0
+        assert (ev[i], te[i]) == (o.events, o.t_end), i
+        assert list(cnt[i][:5].copy().view("<f8")) == [o.park, o.riding, o.waiting, o.walking, o.rides], i
+
+
 def test_unknown_model_ids_and_bad_libraries_are_refused():
     with pytest.raises(cb.CimbaError):
         cb.run_trials(4, arr_mean=1.0, srv_mean=1.0, num_objects=10, master_seed=1, model=cb.MODEL_USER_BASE + 999)
