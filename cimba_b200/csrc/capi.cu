@@ -49,6 +49,7 @@
 #include "../models/mm1_recorded_model.cuh"
 #include "../models/tutorial1_model.cuh"
 #include "../models/park_model.cuh"
+#include "../models/tutorial2_model.cuh"
 #include "../models/guarded_model.cuh"
 #include "../models/workshop_model.cuh"
 #include "../models/coverage_models.cuh"
@@ -413,6 +414,7 @@ uint64_t cimba_b200_workspace_bytes(const cimba_b200_device_job *job)
     if (job->model == CIMBA_B200_MODEL_RENEGE) return cmb::workspace_bytes_for<models::Renege>(*job);
     if (job->model == CIMBA_B200_MODEL_POOL_RECORDED) return cmb::workspace_bytes_for<models::Cheese>(*job);
     if (job->model == CIMBA_B200_MODEL_PARK) return cmb::workspace_bytes_for<models::Park>(*job);
+    if (job->model == CIMBA_B200_MODEL_TUTORIAL2) return cmb::workspace_bytes_for<models::Tutorial2>(*job);
     if (job->model == CIMBA_B200_MODEL_TUTORIAL1 && !tutorial1_goes_static(job)) return cmb::workspace_bytes_for<models::Tutorial1>(*job);
     if (coverage_goes_general(job)) return for_coverage_model<WorkspaceOf>(job->model, job);
     if (mmc_goes_general(job)) return cmb::workspace_bytes_for<models::MMC>(*job);
@@ -498,7 +500,7 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
             return fail(CIMBA_B200_EINVAL, "workspace too small; see cimba_b200_workspace_bytes()");
         return for_coverage_model<LaunchOf>(job->model, job, (unsigned char *)job->workspace, job->workspace_bytes, 0u, st);
     }
-    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || job->model == CIMBA_B200_MODEL_TUTORIAL1 || job->model == CIMBA_B200_MODEL_PARK || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
+    if (job->model == CIMBA_B200_MODEL_RENEGE || job->model == CIMBA_B200_MODEL_POOL_RECORDED || job->model == CIMBA_B200_MODEL_TUTORIAL1 || job->model == CIMBA_B200_MODEL_PARK || job->model == CIMBA_B200_MODEL_TUTORIAL2 || mmc_goes_general(job) || fast_goes_general(job) || hold_goes_general(job) || harbor_goes_general(job)) {
         if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "the general engine runs one trial per lane (CIMBA_B200_MAP_LANE)");
         if (job->servers < 1) return fail(CIMBA_B200_EINVAL, "servers must be >= 1");
         if (job->workspace_bytes < cimba_b200_workspace_bytes(job) || job->workspace == nullptr)
@@ -506,6 +508,8 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
         unsigned char *ws = (unsigned char *)job->workspace;
         if (job->model == CIMBA_B200_MODEL_RENEGE)
             return launch_general<models::Renege>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Renege> launch");
+        if (job->model == CIMBA_B200_MODEL_TUTORIAL2)
+            return launch_general<models::Tutorial2>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Tutorial2> launch");
         if (job->model == CIMBA_B200_MODEL_PARK)
             return launch_general<models::Park>(job, ws, job->workspace_bytes, 0u, st, "trial_kernel<Park> launch");
         if (job->model == CIMBA_B200_MODEL_TUTORIAL1)

@@ -136,6 +136,10 @@ extern "C" {
                                           * No parameters (the park is the tutorial's hard-coded one).  counters[0..4] = the tutorial's five
                                           * results - mean time in park, riding, waiting, walking, mean number of rides - as doubles' bits,
                                           * [5] = visitors departed; objects = visitors created.  General engine. */
+#define CIMBA_B200_MODEL_TUTORIAL2 21    /* cimba_b200/models/tutorial2_model.cuh = the reference's second tutorial, tutorial/tut_2_1.c: five mice
+                                          * acquiring, two rats pre-empting, a cat interrupting, 20 units of cheese, 100 000 time units.  No
+                                          * parameters.  counters[0] = the random stream's next raw output after the run, [1] = units in use at
+                                          * the end, [2] = objects = successful acquires + pre-empts.  General engine. */
 
 /* Models of your own: write them against cimba_b200/csrc/cmb_device.cuh, end the .cu file with
  * CMB_EXPORT_MODEL(YourModel, "name"), build it with scripts/build_model.py (nvcc, sm_100a) and load the library: */

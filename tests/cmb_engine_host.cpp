@@ -43,6 +43,7 @@ static inline unsigned long long __cvta_generic_to_shared(const void *p) { retur
 #include "../cimba_b200/models/mm1_recorded_model.cuh"
 #include "../cimba_b200/models/tutorial1_model.cuh"
 #include "../cimba_b200/models/park_model.cuh"
+#include "../cimba_b200/models/tutorial2_model.cuh"
 #include "../cimba_b200/models/mmc_model.cuh"
 #include "../cimba_b200/models/renege_model.cuh"
 #include "../cimba_b200/models/gg1_model.cuh"
@@ -137,6 +138,7 @@ extern "C" int host_cmb_run_trials(int model, int servers, uint64_t master_seed,
         double *tt = trace_cap ? trace_time + i * trace_cap : nullptr;
         switch (model) {
         case 0:  run_model<models::MM1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
+        case 21: run_model<models::Tutorial2>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 20: run_model<models::Park>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 19: run_model<models::Tutorial1>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;
         case 9:  run_model<models::MM1Recorded>(seed, in, arena, hot, out[i], trace_cap, tk, tt); break;

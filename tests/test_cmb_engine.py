@@ -192,3 +192,17 @@ def test_theme_park_tutorial_on_the_engine_matches_the_unmodified_tutorial_sourc
     for i, want in enumerate(gold["trials"]):
         d = [struct.unpack("<d", struct.pack("<Q", v))[0].hex() for v in list(out[i].counter)[:5]]
         assert out[i].status == 0 and (out[i].events, float(out[i].t_end).hex(), d) == (want["events"], want["t_end"], want["means"]), i
+
+
+def test_second_tutorial_on_the_engine_matches_the_unmodified_tutorial_source(host):
+    """tutorial/tut_2_1.c (mice acquire, rats pre-empt, a cat interrupts; ~670 000 events per trial) written against the authoring
+    surface (cimba_b200/models/tutorial2_model.cuh): events executed, final clock and the random stream's position after the run,
+    against the UNMODIFIED tutorial source run as a program (tests/golden/make_tutorial2_golden.py)."""
+    import json
+    gold = json.loads((ROOT / "tests/golden/tutorial2_vectors.json").read_text())
+    n = 12
+    case = {"model": 21, "servers": 1, "num_objects": 0, "arr_mean": (1.0).hex(), "srv_mean": (1.0).hex(), "params": []}
+    out, _, _ = run_host(host, case, n, master=gold["master"])
+    for i, want in enumerate(gold["trials"][:n]):
+        assert out[i].status == 0
+        assert (out[i].events, float(out[i].t_end).hex(), out[i].counter[0]) == (want["events"], want["t_end"], want["next_raw"]), i

@@ -273,6 +273,19 @@ def test_theme_park_tutorial_on_device_matches_the_unmodified_tutorial_source():
         assert list(cnt[i][:5].copy().view("<f8")) == [o.park, o.riding, o.waiting, o.walking, o.rides], i
 
 
+def test_second_tutorial_on_device_matches_the_unmodified_tutorial_source():
+    """MODEL_TUTORIAL2 = tutorial/tut_2_1.c on the general engine, 32 trials of ~670 000 events against the vectors of the unmodified
+    tutorial source: events executed, final clock, the random stream's position after the run."""
+    import json
+    gold = json.loads((ROOT / "tests/golden/tutorial2_vectors.json").read_text())
+    n = len(gold["trials"])
+    res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=0, master_seed=gold["master"], model=cb.MODEL_TUTORIAL2)
+    assert res.status.abs().sum().item() == 0
+    ev, te, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.counters.cpu().numpy()
+    for i, want in enumerate(gold["trials"]):
+        assert (ev[i], float(te[i]).hex(), int(cnt[i][0]) & (2**64 - 1)) == (want["events"], want["t_end"], want["next_raw"]), i
+
+
 def test_unknown_model_ids_and_bad_libraries_are_refused():
     with pytest.raises(cb.CimbaError):
         cb.run_trials(4, arr_mean=1.0, srv_mean=1.0, num_objects=10, master_seed=1, model=cb.MODEL_USER_BASE + 999)
