@@ -274,15 +274,16 @@ def test_theme_park_tutorial_on_device_matches_the_unmodified_tutorial_source():
 
 
 def test_second_tutorial_on_device_matches_the_unmodified_tutorial_source():
-    """MODEL_TUTORIAL2 = tutorial/tut_2_1.c on the general engine, 32 trials of ~670 000 events against the vectors of the unmodified
-    tutorial source: events executed, final clock, the random stream's position after the run."""
+    """MODEL_TUTORIAL2 = tutorial/tut_2_1.c on the general engine, trials of ~670 000 events each (the tutorial's length is hard-coded)
+    against the vectors of the unmodified tutorial source: events executed, final clock, the random stream's position after the
+    run.  Four trials here (one lane each of one warp: ~30 s); tests/test_cmb_engine.py holds the engine's host build to twelve."""
     import json
     gold = json.loads((ROOT / "tests/golden/tutorial2_vectors.json").read_text())
-    n = len(gold["trials"])
+    n = 4
     res = cb.run_trials(n, arr_mean=1.0, srv_mean=1.0, num_objects=0, master_seed=gold["master"], model=cb.MODEL_TUTORIAL2)
     assert res.status.abs().sum().item() == 0
     ev, te, cnt = res.events.cpu().tolist(), res.t_end.cpu().tolist(), res.counters.cpu().numpy()
-    for i, want in enumerate(gold["trials"]):
+    for i, want in enumerate(gold["trials"][:n]):
         assert (ev[i], float(te[i]).hex(), int(cnt[i][0]) & (2**64 - 1)) == (want["events"], want["t_end"], want["next_raw"]), i
 
 
