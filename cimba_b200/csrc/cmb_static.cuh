@@ -8,15 +8,19 @@
 //     most one pending event, so an insert is a register write and pop-min an NPROC-way compare;
 //   * process records, guards (a bit and a sequence number per process) and the model struct stay in registers: process ids
 //     are compile-time constants after inlining, nothing takes an address;
-//   * a queue is a ring with its oldest 32 entries in shared memory and the rest in an HBM ring (StampRing, engine.cuh);
+//   * a queue is a ring with its oldest 32 entries in shared memory and the rest in an HBM ring (StampRing, engine.cuh); a
+//     cmb_buffer is two counters; either can keep its time-weighted history (S::recorded_queue_type, S::recorded_buffer_type);
 //   * blocking calls are commands carried out by the dispatcher where the warp is together, and the ziggurat's slow path
-//     is taken by parked lanes in batches - as in the fused kernels (queue_model.cuh, whose shape this generalises).
+//     is taken by parked lanes in batches - as in the fused kernels (queue_model.cuh, whose shape this generalises); a hold
+//     of any distribution can be drawn there too (CMB_PROCESS_HOLD_SAMPLED: rectangles first, rewind + park + batch otherwise).
 // What the tier does NOT have - process creation beyond NPROC, priorities other than 0, timers, interrupts, a queue that
 // outgrows window + ring - is not an error: the trial is flagged and the launch re-runs it on the general engine from the SAME
 // model template (launch_static_model below), so the answer is the reference's either way.
 //
 // A model is `template <class S> struct M` with S = cmb::Sim or cmb::StaticSim<...>, its queues declared as
-// `typename S::queue_type`, exported with CMB_EXPORT_STATIC_MODEL(M, NPROC, NQUEUE, "name").
+// `typename S::queue_type`, exported with CMB_EXPORT_STATIC_MODEL(M, NPROC, NQUEUE, "name") (or ..._EVENTS(M, NPROC, NQUEUE,
+// NEVENT, "name")).  In this library: mm1_model.cuh, gg1_model.cuh, mm1_recorded_model.cuh, tutorial1_model.cuh (the reference's
+// first tutorial: two processes, a buffer, three events); examples/tandem_model.cuh.
 #pragma once
 
 #include <type_traits>
@@ -615,7 +619,7 @@ CMB_FN bool static_step(StaticSim<NPROC, NQUEUE, NEVENT> &sim, Model &m, int &wh
     return true;
 }
 
-// the blocking call the body ended on, except the exponential hold (whose draw the callers batch): true = handled
+// the blocking call the body ended on, except the holds whose duration the caller draws (exponential, sampled)
 template <int NPROC, int NQUEUE, int NEVENT>
 CMB_FN void static_finish_command(StaticSim<NPROC, NQUEUE, NEVENT> &sim, int who, uint32_t cmd)
 {
