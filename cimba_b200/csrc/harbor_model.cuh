@@ -42,6 +42,9 @@
 
 namespace cimba_b200 {
 
+#ifndef HARBOR_INLINE_ON_CHIP
+#define HARBOR_INLINE_ON_CHIP 1     // 0: the warp-per-trial kernel calls the out-of-line bindings too (an A/B knob: code size vs call latency)
+#endif
 constexpr uint32_t HARBOR_FIXED = 5u;                   // weather, tide, arrivals, departures, dots
 constexpr uint16_t HARBOR_NONE = 0xffffu;
 constexpr int HARBOR_BLOCK_ON_CHIP = 128;               // 4 warps = 4 trials per CTA when the state is in shared memory
@@ -145,7 +148,7 @@ struct HarborSim {
     }
 
     __device__ __noinline__ void await_push_out(HarborProc &p, uint32_t type, uint32_t ref) { return await_push_impl(p, type, ref); }
-    __device__ __forceinline__ void await_push(HarborProc &p, uint32_t type, uint32_t ref) { if (IN_SHARED) return await_push_impl(p, type, ref); else return await_push_out(p, type, ref); }
+    __device__ __forceinline__ void await_push(HarborProc &p, uint32_t type, uint32_t ref) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return await_push_impl(p, type, ref); else return await_push_out(p, type, ref); }
     __device__ __forceinline__ void await_push_impl(HarborProc &p, uint32_t type, uint32_t ref)
     {
         if (p.n_awaits >= 2u) {
@@ -160,7 +163,7 @@ struct HarborSim {
     }
 
     __device__ __noinline__ void await_remove_out(HarborProc &p, uint32_t type, bool any, uint32_t ref) { return await_remove_impl(p, type, any, ref); }
-    __device__ __forceinline__ void await_remove(HarborProc &p, uint32_t type, bool any, uint32_t ref) { if (IN_SHARED) return await_remove_impl(p, type, any, ref); else return await_remove_out(p, type, any, ref); }
+    __device__ __forceinline__ void await_remove(HarborProc &p, uint32_t type, bool any, uint32_t ref) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return await_remove_impl(p, type, any, ref); else return await_remove_out(p, type, any, ref); }
     __device__ __forceinline__ void await_remove_impl(HarborProc &p, uint32_t type, bool any, uint32_t ref)
     {
         for (uint32_t k = 0u; k < p.n_awaits; k++) {
@@ -176,7 +179,7 @@ struct HarborSim {
     }
 
     __device__ __noinline__ void hold_begin_out(uint32_t pid, double dur) { return hold_begin_impl(pid, dur); }
-    __device__ __forceinline__ void hold_begin(uint32_t pid, double dur) { if (IN_SHARED) return hold_begin_impl(pid, dur); else return hold_begin_out(pid, dur); }
+    __device__ __forceinline__ void hold_begin(uint32_t pid, double dur) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return hold_begin_impl(pid, dur); else return hold_begin_out(pid, dur); }
     __device__ __forceinline__ void hold_begin_impl(uint32_t pid, double dur)        // src/cmb_process.c:262-273
     {
         HarborProc &p = S().proc[pid];
@@ -187,7 +190,7 @@ struct HarborSim {
     template <class Guard>
     __device__ __noinline__ void wait_begin_out(Guard &g, uint32_t gid, uint32_t pid) { return wait_begin_impl(g, gid, pid); }
     template <class Guard>
-    __device__ __forceinline__ void wait_begin(Guard &g, uint32_t gid, uint32_t pid) { if (IN_SHARED) return wait_begin_impl(g, gid, pid); else return wait_begin_out(g, gid, pid); }
+    __device__ __forceinline__ void wait_begin(Guard &g, uint32_t gid, uint32_t pid) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return wait_begin_impl(g, gid, pid); else return wait_begin_out(g, gid, pid); }
     template <class Guard>
     __device__ __forceinline__ void wait_begin_impl(Guard &g, uint32_t gid, uint32_t pid)    // src/cmb_resourceguard.c:125-152
     {
@@ -218,7 +221,7 @@ struct HarborSim {
     template <class Guard>
     __device__ __noinline__ bool pool_grab_out(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held) { return pool_grab_impl(p, g, rem, held); }
     template <class Guard>
-    __device__ __forceinline__ bool pool_grab(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held) { if (IN_SHARED) return pool_grab_impl(p, g, rem, held); else return pool_grab_out(p, g, rem, held); }
+    __device__ __forceinline__ bool pool_grab(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return pool_grab_impl(p, g, rem, held); else return pool_grab_out(p, g, rem, held); }
     template <class Guard>
     __device__ __forceinline__ bool pool_grab_impl(HarborPool &p, Guard &g, uint8_t &rem, uint8_t &held)
     {
@@ -243,7 +246,7 @@ struct HarborSim {
     template <class Guard>
     __device__ __noinline__ void pool_release_out(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held) { return pool_release_impl(p, g, amount, held); }
     template <class Guard>
-    __device__ __forceinline__ void pool_release(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held) { if (IN_SHARED) return pool_release_impl(p, g, amount, held); else return pool_release_out(p, g, amount, held); }
+    __device__ __forceinline__ void pool_release(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return pool_release_impl(p, g, amount, held); else return pool_release_out(p, g, amount, held); }
     template <class Guard>
     __device__ __forceinline__ void pool_release_impl(HarborPool &p, Guard &g, uint32_t amount, uint8_t &held)   // :561-605
     {
@@ -263,7 +266,7 @@ struct HarborSim {
 
     // cmb_condition_signal, src/cmb_condition.c:120-167
     __device__ __noinline__ uint32_t harbormaster_signal_out() { return harbormaster_signal_impl(); }
-    __device__ __forceinline__ uint32_t harbormaster_signal() { if (IN_SHARED) return harbormaster_signal_impl(); else return harbormaster_signal_out(); }
+    __device__ __forceinline__ uint32_t harbormaster_signal() { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return harbormaster_signal_impl(); else return harbormaster_signal_out(); }
     __device__ __forceinline__ uint32_t harbormaster_signal_impl()
     {
         auto &cv = S().harbormaster;
@@ -283,7 +286,7 @@ struct HarborSim {
     }
 
     __device__ __noinline__ void davyjones_signal_out() { return davyjones_signal_impl(); }
-    __device__ __forceinline__ void davyjones_signal() { if (IN_SHARED) return davyjones_signal_impl(); else return davyjones_signal_out(); }
+    __device__ __forceinline__ void davyjones_signal() { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return davyjones_signal_impl(); else return davyjones_signal_out(); }
     __device__ __forceinline__ void davyjones_signal_impl()
     {
         auto &cv = S().davyjones;
@@ -301,7 +304,7 @@ struct HarborSim {
     }
 
     __device__ __noinline__ double pert_out(double min, double mode, double max) { return pert_impl(min, mode, max); }
-    __device__ __forceinline__ double pert(double min, double mode, double max) { if (IN_SHARED) return pert_impl(min, mode, max); else return pert_out(min, mode, max); }
+    __device__ __forceinline__ double pert(double min, double mode, double max) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return pert_impl(min, mode, max); else return pert_out(min, mode, max); }
     __device__ __forceinline__ double pert_impl(double min, double mode, double max)
     {
         return rnd_PERT_mod(rng, *hot, min, mode, max, 4.0);
@@ -311,7 +314,7 @@ struct HarborSim {
 
     // cmb_process_stop, src/cmb_process.c:698-723
     __device__ __noinline__ void stop_out(uint32_t pid) { return stop_impl(pid); }
-    __device__ __forceinline__ void stop(uint32_t pid) { if (IN_SHARED) return stop_impl(pid); else return stop_out(pid); }
+    __device__ __forceinline__ void stop(uint32_t pid) { if (IN_SHARED && HARBOR_INLINE_ON_CHIP) return stop_impl(pid); else return stop_out(pid); }
     __device__ __forceinline__ void stop_impl(uint32_t pid)
     {
         HarborProc &p = S().proc[pid];
