@@ -22,6 +22,7 @@
 #include "engine.cuh"
 #include "queue_model.cuh"
 #include "mm1_fast.cuh"
+#include "mm1_pc.cuh"
 #include "gg1_fast.cuh"
 #include "pool_model.cuh"
 #include "pool_fast.cuh"
@@ -583,7 +584,13 @@ int cimba_b200_launch(const cimba_b200_device_job *job, void *stream)
                                                        repair_arena_bytes(job), REPAIR_BITS, st, "repair pass (M/M/1 with its queue history)");
         }
         if (job->variant == 1) return launch_queue<0>(qa, trace, grid, st);
-        if (trace) {
+        if (job->variant == 2) {                        // variates from producer warps (mm1_pc.cuh): an experiment, same answers
+            if (mapping != CIMBA_B200_MAP_LANE) return fail(CIMBA_B200_EINVAL, "variant 2 of MODEL_MM1 runs one trial per lane");
+            const dim3 pc_grid((unsigned)((job->num_trials + MM1_PC_CONSUMERS - 1) / MM1_PC_CONSUMERS));
+            if (trace) mm1_pc_kernel<true><<<pc_grid, 2 * MM1_PC_CONSUMERS, 0, st>>>(qa);
+            else       mm1_pc_kernel<false><<<pc_grid, 2 * MM1_PC_CONSUMERS, 0, st>>>(qa);
+        }
+        else if (trace) {
             mm1_kernel<true><<<grid, QUEUE_BLOCK, 0, st>>>(qa);
         }
         else {

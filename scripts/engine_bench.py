@@ -34,6 +34,7 @@ def timed(fn, reps=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--pc-only", action="store_true", help="M/M/1: mm1_kernel next to mm1_pc_kernel (variates from producer warps)")
     ap.add_argument("--gg1", action="store_true", help="G/G/1: gg1_kernel next to gg1_model.cuh on the static tier")
     ap.add_argument("--static-only", action="store_true", help="time M/M/1 on the static tier only (variant sweeps)")
     a = ap.parse_args()
@@ -56,6 +57,18 @@ def main():
                           "static_over_fast_time": out["static"]["ms"] / out["fast"]["ms"],
                           "same_answers": out["fast"]["sum_check"] == out["static"]["sum_check"] and out["fast"]["events"] == out["static"]["events"]}), flush=True)
         return
+    if a.pc_only:
+        trials, nobj = 65536, 100000
+        am = torch.full((trials,), 1 / 0.9, dtype=torch.float64, device=dev)
+        sm = torch.full((trials,), 1.0, dtype=torch.float64, device=dev)
+        for label, variant in (("fast", 0), ("producer_consumer", 2)):
+            bufs = cb.TrialBuffers(trials, dev, 0, cb.MODEL_MM1, 1, variant)
+            cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, variant=variant)
+            res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, variant=variant, buffers=bufs), reps=3)
+            ev = int(res.events.sum().item())
+            print(json.dumps({"kernel": label, "ms": ms, "events_per_s": ev / ms * 1e3, "bad": int((res.status != 0).sum().item()),
+                              "sum_check": float(res.sum_wait.sum().item())}), flush=True)
+        return
     if a.static_only:
         trials, nobj = 65536, 100000
         am = torch.full((trials,), 1 / 0.9, dtype=torch.float64, device=dev)
@@ -72,7 +85,7 @@ def main():
         am = torch.full((trials,), arr, dtype=torch.float64, device=dev)
         sm = torch.full((trials,), srv, dtype=torch.float64, device=dev)
         out = {}
-        for label, variant in (("fast", 0), ("general", cb.VARIANT_GENERAL)) + ((("static", cb.VARIANT_STATIC),) if model == cb.MODEL_MM1 else ()):
+        for label, variant in (("fast", 0), ("general", cb.VARIANT_GENERAL)) + ((("static", cb.VARIANT_STATIC), ("producer_consumer", 2)) if model == cb.MODEL_MM1 else ()):
             bufs = cb.TrialBuffers(trials, dev, 0, model, servers, variant)
             cb.launch_trials(am[:256], sm[:256], num_objects=1000, master_seed=1, model=model, servers=servers, variant=variant)
             res, ms = timed(lambda: cb.launch_trials(am, sm, num_objects=nobj, master_seed=MASTER, model=model, servers=servers,

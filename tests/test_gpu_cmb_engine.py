@@ -67,6 +67,14 @@ def test_default_kernels_with_their_repair_pass_match_the_reference_vectors(case
     compare(case, res, n)
 
 
+@pytest.mark.parametrize("case", [c for c in GOLD["cases"] if c["model"] == 0], ids=case_id)
+def test_producer_consumer_variant_of_the_headline_kernel_matches_the_reference_vectors(case):
+    """variant 2 of MODEL_MM1 (csrc/mm1_pc.cuh): the variates come from producer warps through shared-memory rings - same stream,
+    same answers, pop traces included; flagged trials go to the repair pass like the default kernel's."""
+    n = len(case["trials"])
+    compare(case, run_case(case, cb.MODEL_MM1, 2, n), n)
+
+
 def test_the_repair_pass_is_what_answers_in_overload():
     """At rho = 1.05 every trial outgrows the 32 + 512 entry queue: the diag counter shows the repair pass re-ran
     them all, and with a ring sized for the traffic the fast kernel keeps them (same answers either way)."""
