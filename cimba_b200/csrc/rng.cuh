@@ -73,28 +73,7 @@ struct Sfc64 {
     __device__ __forceinline__ uint64_t next()
     {
         const uint64_t out = a + b + d++;
-#if !defined(SFC64_NO_IMAD) && !defined(CMB_HOST_BUILD)
-        // The generator's shift, rotation and multiplication by nine as wide multiplications (IMAD.WIDE on the FMA pipe, 12 - 16 % busy)
-        // instead of SHF / PRMT / LEA on the half-rate ALU pipe (64 - 70 % busy, the busiest pipe of every event loop here): five
-        // ALU instructions fewer per draw, the same number of instructions, the same values (profiles/r02_mm1.md).
-        // b >> 11 from two wide multiplications by 2^21 (upper word of lo * 2^21 = lo >> 11; hi * 2^21 = {hi >> 11 : hi << 21}),
-        // the OR and the XOR folded into one three-input logic operation per word
-        {
-            uint32_t lo, hi;
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(b));
-            uint64_t wl, wh;
-            asm("mul.wide.u32 %0, %1, 2097152;" : "=l"(wl) : "r"(lo));
-            asm("mul.wide.u32 %0, %1, 2097152;" : "=l"(wh) : "r"(hi));
-            uint32_t wl_lo, wl_hi, wh_lo, wh_hi;
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(wl_lo), "=r"(wl_hi) : "l"(wl));
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(wh_lo), "=r"(wh_hi) : "l"(wh));
-            const uint32_t alo = (wl_hi | wh_lo) ^ lo;
-            const uint32_t ahi = wh_hi ^ hi;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(alo), "r"(ahi));
-        }
-#else
         a = b ^ (b >> 11);
-#endif
 #if !defined(SFC64_NO_IMAD) && !defined(CMB_HOST_BUILD)
         // c + (c << 3) = 9 c as IMAD.WIDE + IMAD (FMA pipe) instead of LEA + LEA.HI.X (the half-rate ALU pipe, the busiest pipe of
         // every event loop here): mm1_kernel 103.32 -> 102.27 ms per 1.376e10 events, profiles/r02_mm1.md.  Same value, bit for bit.
@@ -112,23 +91,7 @@ struct Sfc64 {
 #else
         b = c + (c << 3);
 #endif
-#if !defined(SFC64_NO_IMAD) && !defined(CMB_HOST_BUILD)
-        // rotl(c, 24) = lo * 2^24 + swap(hi * 2^24) (the two products have no bit in common), added to `out` in one three-operand sum
-        {
-            uint32_t lo, hi;
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(c));
-            uint64_t w1, w2;
-            asm("mul.wide.u32 %0, %1, 16777216;" : "=l"(w1) : "r"(lo));
-            asm("mul.wide.u32 %0, %1, 16777216;" : "=l"(w2) : "r"(hi));
-            uint32_t w2_lo, w2_hi;
-            asm("mov.b64 {%0, %1}, %2;" : "=r"(w2_lo), "=r"(w2_hi) : "l"(w2));
-            uint64_t swapped;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(swapped) : "r"(w2_hi), "r"(w2_lo));
-            c = out + w1 + swapped;
-        }
-#else
         c = ((c << 24) | (c >> 40)) + out;
-#endif
         return out;
     }
 
