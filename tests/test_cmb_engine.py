@@ -206,3 +206,26 @@ def test_second_tutorial_on_the_engine_matches_the_unmodified_tutorial_source(ho
     for i, want in enumerate(gold["trials"][:n]):
         assert out[i].status == 0
         assert (out[i].events, float(out[i].t_end).hex(), out[i].counter[0]) == (want["events"], want["t_end"], want["next_raw"]), i
+
+
+def test_static_tier_and_general_engine_agree_on_parameters_no_vector_covers(host):
+    """The same model templates compiled against cmb::StaticSim and cmb::Sim, run side by side on parameter sets drawn here (no
+    stored vector knows them): events executed, final clock, sums, counters and the first pops must be the same for every trial."""
+    import random
+    rnd = random.Random(20260921)
+    for model, servers_of, params_of in ((0, lambda: 1, lambda: []), (1, lambda: 1, lambda: []), (9, lambda: 1, lambda: []),
+                                         (17, lambda: rnd.randint(1, 6), lambda: []), (19, lambda: 1, lambda: [rnd.uniform(0.0, 300.0)])):
+        for _ in range(4):
+            rho = rnd.uniform(0.3, 1.02)
+            case = {"model": model, "servers": servers_of(), "num_objects": rnd.randint(500, 4000), "arr_mean": (1.0 / rho).hex(),
+                    "srv_mean": rnd.choice([1.0, 0.7, 1.3]).hex(), "params": params_of()}
+            first = rnd.randint(0, 10_000)
+            general, gk, gt = run_host(host, case, 3, first=first)
+            static, sk, st = run_host(host, dict(case, model=model + 100), 3, arena=1 << 16, first=first)
+            for i in range(3):
+                assert general[i].status == 0 and static[i].status == 0, (case, i)
+                assert (general[i].events, general[i].objects, general[i].t_end, general[i].sum_wait, list(general[i].counter)) == \
+                       (static[i].events, static[i].objects, static[i].t_end, static[i].sum_wait, list(static[i].counter)), (case, i)
+                n = min(int(general[i].events), TRACE)
+                assert list(gk[i * TRACE:i * TRACE + n]) == list(sk[i * TRACE:i * TRACE + n]), (case, i)
+                assert list(gt[i * TRACE:i * TRACE + n]) == list(st[i * TRACE:i * TRACE + n]), (case, i)
