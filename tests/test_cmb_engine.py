@@ -229,3 +229,34 @@ def test_static_tier_and_general_engine_agree_on_parameters_no_vector_covers(hos
                 n = min(int(general[i].events), TRACE)
                 assert list(gk[i * TRACE:i * TRACE + n]) == list(sk[i * TRACE:i * TRACE + n]), (case, i)
                 assert list(gt[i * TRACE:i * TRACE + n]) == list(st[i * TRACE:i * TRACE + n]), (case, i)
+
+
+def test_engine_against_the_live_reference_on_drawn_parameters(host):
+    """Beyond the stored vectors: the reference's test worlds and tutorial 1 on the engine's host build against the live reference
+    build (oracle/_ref/librefdrv.so), parameters drawn here - capacities 1..40, durations, means, warm-up times."""
+    import random
+    from oracle_libs import load_ref, run_trials
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/librefdrv.so not built (needs /root/reference)")
+    ref.ref_set_param.argtypes = [C.c_int, C.c_double]
+    rnd = random.Random(7)
+    try:
+        for model in (3, 4, 5, 6, 8, 9, 11, 12, 13, 14, 18, 19):
+            for _ in range(3):
+                servers = 1 if model in (8, 9, 14, 19) else rnd.randint(1, 40)
+                nobj = rnd.randint(150, 1500)
+                arr, srv = rnd.choice([0.4, 0.7, 1.0, 1.6]), rnd.choice([0.6, 1.0, 1.4])
+                params = [rnd.uniform(0.0, 100.0)] if model == 19 else []
+                case = {"model": model, "servers": servers, "num_objects": nobj, "arr_mean": float(arr).hex(), "srv_mean": float(srv).hex(),
+                        "params": params}
+                first = rnd.randint(0, 5000)
+                ref.ref_set_param(0, params[0] if params else 0.0)
+                want = run_trials(ref, "ref", model, servers, MASTER, first, 4, nobj, arr, srv, par=0)
+                out, _, _ = run_host(host, case, 4, first=first)
+                for i, (o, w) in enumerate(zip(out, want)):
+                    assert o.status == 0, (case, i)
+                    assert (o.events, o.objects, o.t_end, o.sum_wait) == (w.events, w.objects, w.t_end, w.sum_wait), (case, i)
+                    assert list(o.counter) == list(w.counter), (case, i)
+    finally:
+        ref.ref_set_param(0, 0.0)
