@@ -242,7 +242,8 @@ def test_engine_against_the_live_reference_on_drawn_parameters(host):
     ref.ref_set_param.argtypes = [C.c_int, C.c_double]
     rnd = random.Random(7)
     try:
-        for model in (3, 4, 5, 6, 8, 9, 11, 12, 13, 14, 18, 19):
+        # (not model 18: its cmb_random_flip calls would leave cached bits in the reference's thread-local cache for later tests)
+        for model in (3, 4, 5, 6, 8, 9, 11, 12, 13, 14, 19):
             for _ in range(3):
                 servers = 1 if model in (8, 9, 14, 19) else rnd.randint(1, 40)
                 nobj = rnd.randint(150, 1500)
